@@ -1,0 +1,197 @@
+"""ORACLE (test infrastructure) — PyTorch-CPU restatement of the reference's HAM loops.
+
+``phase_b_step`` follows mesh_sfs_optim.py:253-310 line for line and ``phase_a_step`` follows
+mesh_sfs_optim.py:198-237, with ``oracle.raster`` standing in for ``nvdiffrast.torch`` and
+``oracle.refmath`` for ``models.utils``.  ``render_views`` follows the init render at
+mesh_sfs_optim.py:138-148 plus the shading of :282-287 and is used to synthesise targets.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import raster as dr
+from .refmath import get_normals, get_radiance, laplacian_smoothing
+
+
+def _clip_positions(vertices, w2c, proj):
+    """mesh_sfs_optim.py:262-264."""
+    n = w2c.shape[0]
+    vertsw = torch.cat([vertices, torch.ones_like(vertices[:, 0:1])], axis=1).unsqueeze(0).expand(n, -1, -1)
+    rot_verts = torch.einsum('ijk,ikl->ijl', vertsw, w2c)
+    proj_verts = torch.einsum('ijk,ikl->ijl', rot_verts, proj)
+    return vertsw, proj_verts
+
+
+def render_views(vertices, faces, albedo, sh, w2cs, projs, H, W):
+    """Returns numpy (img[n,H,W,3], coverage[n,H,W], aa_coverage[n,H,W])."""
+    with torch.no_grad():
+        vertices = torch.as_tensor(vertices, dtype=torch.float32)
+        faces = torch.as_tensor(faces, dtype=torch.int32)
+        albedo = torch.as_tensor(albedo, dtype=torch.float32)
+        sh = torch.as_tensor(sh, dtype=torch.float32)
+        w2c = torch.as_tensor(w2cs, dtype=torch.float32)
+        proj = torch.as_tensor(projs, dtype=torch.float32)
+        n = w2c.shape[0]
+        glctx = dr.RasterizeGLContext()
+        vertsw, proj_verts = _clip_positions(vertices, w2c, proj)
+        normals = get_normals(vertsw[:, :, :3], faces.long())
+        rast_out, _ = dr.rasterize(glctx, proj_verts, faces, resolution=(H, W))
+        feat = torch.cat([normals, albedo[None].expand(n, -1, -1), torch.ones_like(vertsw[:, :, :1])], dim=2)
+        feat, _ = dr.interpolate(feat, rast_out, faces)
+        pred_normals = F.normalize(feat[..., :3].contiguous(), p=2, dim=3)
+        rast_albedo = feat[..., 3:6].contiguous()
+        pred_mask = feat[..., 6:7].contiguous()
+        aa_mask = dr.antialias(pred_mask, rast_out, proj_verts, faces).squeeze(-1)
+        valid_idx = torch.where(rast_out[..., 3] > 0)
+        radiance = get_radiance(sh[valid_idx[0]], pred_normals[valid_idx], 3).unsqueeze(-1)
+        img = torch.zeros(n, H, W, 3)
+        img[valid_idx] = radiance * rast_albedo[valid_idx]
+        img = dr.antialias(img, rast_out, proj_verts, faces)
+        cov = (rast_out[..., 3] > 0).float()
+    return img.numpy(), cov.numpy(), aa_mask.numpy()
+
+
+class HamState:
+    """Optimisation state exactly as mesh_sfs_optim.py:176-193,242-244 sets it up."""
+
+    def __init__(self, scene):
+        t = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
+        self.H, self.W = scene["H"], scene["W"]
+        self.conf = dict(scene["conf"])
+        self.faces = t(scene["faces"], torch.int32)
+        self.vertices_tmp = t(scene["vertices"])
+        self.imgs, self.masks, self.valid_masks = t(scene["imgs"]), t(scene["masks"]), t(scene["valid_masks"])
+        self.w2cs, self.projs = t(scene["w2cs"]), t(scene["projs"])
+        self.albedo = t(scene["albedo"]).unsqueeze(0).clone().requires_grad_(True)
+        self.sh_coeffs = t(scene["sh_coeffs"]).clone().requires_grad_(True)
+        self.delta = torch.zeros_like(self.vertices_tmp).requires_grad_(True)
+        v, f = self.vertices_tmp, self.faces.long()
+        a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+        # mesh_sfs_optim.py:184-188
+        self.edge_length_mean = torch.cat([((a - b) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)]).mean()
+        self.glctx = dr.RasterizeGLContext()
+        self.opt_a = None
+        self.opt_b = None
+
+    def optimizer_a(self):
+        if self.opt_a is None:  # mesh_sfs_optim.py:193
+            c = self.conf
+            self.opt_a = torch.optim.Adam([{'params': self.albedo, 'lr': c["albedo_lr"]},
+                                           {'params': self.sh_coeffs, 'lr': c["sh_lr"]}])
+        return self.opt_a
+
+    def optimizer_b(self):
+        if self.opt_b is None:  # mesh_sfs_optim.py:242-244
+            c = self.conf
+            self.sh_coeffs.requires_grad_(False)
+            self.opt_b = torch.optim.Adam([{'params': self.delta, 'lr': c["lr"]},
+                                           {'params': self.albedo, 'lr': c["albedo_lr"]},
+                                           {'params': self.sh_coeffs, 'lr': c["sh_lr"]}])
+        return self.opt_b
+
+
+def phase_b_forward(st, view_idx, albedo_weight=None, keep=None):
+    """Forward of one phase-B iteration (mesh_sfs_optim.py:253-306).  Returns (loss, dict of loss terms)."""
+    c = st.conf
+    faces = st.faces
+    resolution = (st.H, st.W)
+    albedo_weight = c["albedo_weight"] if albedo_weight is None else albedo_weight
+    perm = torch.as_tensor(view_idx, dtype=torch.long)
+    vertices = st.vertices_tmp + st.delta
+    n = perm.numel()
+    w2c, proj = st.w2cs[perm], st.projs[perm]
+    img, mask, valid_mask = st.imgs[perm], st.masks[perm], st.valid_masks[perm]
+    sh_coeff = st.sh_coeffs[perm]
+
+    vertsw, proj_verts = _clip_positions(vertices, w2c, proj)
+    normals = get_normals(vertsw[:, :, :3], faces.long())
+
+    rast_out, _ = dr.rasterize(st.glctx, proj_verts, faces, resolution=resolution)
+    feat = torch.cat([normals, st.albedo.expand(n, -1, -1), torch.ones_like(vertsw[:, :, :1])], dim=2)
+    feat, _ = dr.interpolate(feat, rast_out, faces)
+    pred_normals = feat[:, :, :, :3].contiguous()
+    rast_albedo = feat[:, :, :, 3:6].contiguous()
+    pred_mask = feat[:, :, :, 6:7].contiguous()
+    pred_normals = F.normalize(pred_normals, p=2, dim=3)
+    pred_mask = dr.antialias(pred_mask, rast_out, proj_verts, faces).squeeze(-1)
+
+    valid_idx = torch.where((mask > 0) & (rast_out[:, :, :, 3] > 0))
+    valid_normals = pred_normals[valid_idx]
+    valid_shcoeff = sh_coeff[valid_idx[0]]
+    valid_albedo = rast_albedo[valid_idx]
+    valid_img = img[valid_idx]
+    radiance = get_radiance(valid_shcoeff, valid_normals, 3).unsqueeze(-1)
+    pred_img = radiance * valid_albedo
+
+    tmp_img = torch.zeros_like(img)
+    tmp_img[valid_idx] = pred_img
+    tmp_img = dr.antialias(tmp_img, rast_out, proj_verts, faces)
+
+    sfs_loss = c["sfs_weight"] * F.l1_loss(tmp_img[valid_idx], valid_img)
+    lap_loss = c["lap_weight"] * laplacian_smoothing(vertices, faces.long(), method="uniform")
+    albedo_loss = albedo_weight * laplacian_smoothing(st.albedo.squeeze(0), faces.long(), method="uniform")
+    mask_loss = c["mask_weight"] * F.mse_loss(pred_mask, valid_mask)
+    a = vertices[faces[:, 0].long()]
+    b = vertices[faces[:, 1].long()]
+    cc = vertices[faces[:, 2].long()]
+    edge_length = torch.cat([((a - b) ** 2).sum(1), ((cc - b) ** 2).sum(1), ((a - cc) ** 2).sum(1)])
+    edge_loss = torch.clip(edge_length - st.edge_length_mean, 0, 1).mean() * c["edge_weight"]
+    delta_loss = (st.delta ** 2).sum(1).mean() * c["delta_weight"]
+    loss = sfs_loss + lap_loss + albedo_loss + mask_loss + delta_loss + edge_loss
+    terms = dict(sfs=sfs_loss, lap=lap_loss, albedo=albedo_loss, mask=mask_loss, edge=edge_loss, delta=delta_loss,
+                 n_valid=valid_idx[0].numel())
+    if keep is not None:
+        keep.update(rast_out=rast_out.detach(), proj_verts=proj_verts.detach(), tmp_img=tmp_img.detach(),
+                    pred_mask=pred_mask.detach(), normals=normals.detach(), vertices=vertices.detach())
+    return loss, terms
+
+
+def phase_b_step(st, view_idx, albedo_weight=None, keep=None):
+    """One full phase-B iteration: forward, backward, Adam (mesh_sfs_optim.py:253-310)."""
+    opt = st.optimizer_b()
+    loss, terms = phase_b_forward(st, view_idx, albedo_weight, keep)
+    opt.zero_grad()
+    loss.backward()
+    if keep is not None:
+        keep.update(grad_delta=st.delta.grad.detach().clone(), grad_albedo=st.albedo.grad.detach().clone())
+    opt.step()
+    return {k: (float(v) if torch.is_tensor(v) else v) for k, v in terms.items()}
+
+
+def phase_a_step(st, view_idx, keep=None):
+    """One phase-A (albedo + SH warm-up) iteration, mesh_sfs_optim.py:198-237."""
+    c = st.conf
+    opt = st.optimizer_a()
+    faces = st.faces
+    perm = torch.as_tensor(view_idx, dtype=torch.long)
+    vertices = (st.vertices_tmp + st.delta).detach()
+    n = perm.numel()
+    w2c, proj = st.w2cs[perm], st.projs[perm]
+    img, mask = st.imgs[perm], st.masks[perm]
+    sh_coeff = st.sh_coeffs[perm]
+    vertsw, proj_verts = _clip_positions(vertices, w2c, proj)
+    normals = get_normals(vertsw[:, :, :3], faces.long())
+    rast_out, _ = dr.rasterize(st.glctx, proj_verts, faces, resolution=(st.H, st.W))
+    feat = torch.cat([normals, st.albedo.expand(n, -1, -1)], dim=2)
+    feat, _ = dr.interpolate(feat, rast_out, faces)
+    pred_normals = feat[:, :, :, :3].contiguous()
+    rast_albedo = feat[:, :, :, 3:6].contiguous()
+    pred_normals = dr.antialias(pred_normals, rast_out, proj_verts, faces)
+    pred_normals = F.normalize(pred_normals, p=2, dim=3)
+    rast_albedo = dr.antialias(rast_albedo, rast_out, proj_verts, faces)
+    valid_idx = torch.where((mask > 0) & (rast_out[:, :, :, 3] > 0))
+    valid_normals = pred_normals[valid_idx]
+    valid_shcoeff = sh_coeff[valid_idx[0]]
+    valid_albedo = rast_albedo[valid_idx]
+    valid_img = img[valid_idx]
+    radiance = get_radiance(valid_shcoeff, valid_normals, 3).unsqueeze(-1)
+    pred_img = radiance * valid_albedo
+    sfs_loss = c["sfs_weight"] * F.l1_loss(pred_img, valid_img)
+    albedo_loss = c["albedo_weight"] * laplacian_smoothing(st.albedo.squeeze(0), faces.long(), method="uniform")
+    loss = sfs_loss
+    opt.zero_grad()
+    loss.backward()
+    if keep is not None:
+        keep.update(grad_albedo=st.albedo.grad.detach().clone(), grad_sh=st.sh_coeffs.grad.detach().clone())
+    opt.step()
+    return dict(sfs=float(sfs_loss), albedo=float(albedo_loss), n_valid=valid_idx[0].numel())

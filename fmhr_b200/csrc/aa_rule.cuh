@@ -1,0 +1,129 @@
+// Silhouette-edge analysis of one pixel pair, shared by the stand-alone antialias op (antialias.cu) and the fused
+// HAM kernels (ham.cu).  Semantics follow nvdiffrast's antialias; every decision-relevant
+// operation is an exactly-rounded, un-contracted fp32 op in the same order as oracle/raster_oracle.cpp::aa_analyse,
+// so the discrete choices (which triangle, which edge, blend or not) are bit-identical to the oracle's.
+#pragma once
+#include "common.cuh"
+
+namespace fmhr {
+
+struct AAPair {
+    int tri;      // chosen triangle
+    int di;       // chosen edge: runs from corner (di+1)%3 to corner (di+2)%3
+    int from1;    // 1 if the chosen triangle belongs to the second pixel of the pair
+    int clamped;  // crossing parameter was clamped -> no position gradient
+    int i1, i2;   // vertex ids of the chosen edge
+    float alpha;  // blend weight; receiver is pixel0 if alpha > 0 else pixel1
+};
+
+__device__ __forceinline__ bool aa_same_sign(float a, float b) {
+    return (int)(__float_as_uint(a) ^ __float_as_uint(b)) >= 0;
+}
+__device__ __forceinline__ bool aa_rational_gt(float n0, float d0, float n1, float d1) {
+    const float l = xm(n0, d1), r = xm(n1, d0);
+    const bool flip = (d0 < 0.0f) != (d1 < 0.0f);
+    return flip ? (l < r) : (l > r);
+}
+__device__ __forceinline__ void aa_project(const float4 p, float xh, float yh, float fx, float fy, float& x, float& y) {
+    const float iw = xd(1.0f, p.w);
+    x = xs(xm(xm(p.x, iw), xh), fx);
+    y = xs(xm(xm(p.y, iw), yh), fy);
+}
+
+// (px,py) = first pixel of the pair, d = 0 (right neighbour) or 1 (down neighbour);
+// tri0/z0 and tri1/z1 are triangle id (-1 = empty) and z/w of the two pixels; P = this view's clip positions.
+__device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z1, int px, int py, int d,
+                                           const float* __restrict__ P, const int32_t* __restrict__ tri,
+                                           const int32_t* __restrict__ opp, int V, int T, int H, int W, AAPair& out) {
+    int t = (tri0 >= 0) ? tri0 : tri1;
+    if (tri0 >= 0 && tri1 >= 0) t = (z0 < z1) ? tri0 : tri1;
+    const bool from1 = (t == tri1);
+    if (from1) { px += 1 - d; py += d; }
+    if (t < 0 || t >= T) return false;
+    const int v0 = __ldg(tri + 3 * t), v1 = __ldg(tri + 3 * t + 1), v2 = __ldg(tri + 3 * t + 2);
+    if ((unsigned)v0 >= (unsigned)V || (unsigned)v1 >= (unsigned)V || (unsigned)v2 >= (unsigned)V) return false;
+    const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
+    const float fx = xs(xa((float)px, 0.5f), xh), fy = xs(xa((float)py, 0.5f), yh);
+    float x0, y0, x1, y1, x2, y2;
+    aa_project(ldg4(P + 4 * (size_t)v0), xh, yh, fx, fy, x0, y0);
+    aa_project(ldg4(P + 4 * (size_t)v1), xh, yh, fx, fy, x1, y1);
+    aa_project(ldg4(P + 4 * (size_t)v2), xh, yh, fx, fy, x2, y2);
+    const int o0 = __ldg(opp + 3 * t), o1 = __ldg(opp + 3 * t + 1), o2 = __ldg(opp + 3 * t + 2);
+    float ox0 = x0, oy0 = y0, ox1 = x1, oy1 = y1, ox2 = x2, oy2 = y2;
+    if ((unsigned)o0 < (unsigned)V) aa_project(ldg4(P + 4 * (size_t)o0), xh, yh, fx, fy, ox0, oy0);
+    if ((unsigned)o1 < (unsigned)V) aa_project(ldg4(P + 4 * (size_t)o1), xh, yh, fx, fy, ox1, oy1);
+    if ((unsigned)o2 < (unsigned)V) aa_project(ldg4(P + 4 * (size_t)o2), xh, yh, fx, fy, ox2, oy2);
+    const float bb = xs(xm(xs(x1, x0), xs(y2, y0)), xm(xs(x2, x0), xs(y1, y0)));
+    const float a0 = xs(xm(xs(x1, ox0), xs(y2, oy0)), xm(xs(x2, ox0), xs(y1, oy0)));
+    const float a1 = xs(xm(xs(x2, ox1), xs(y0, oy1)), xm(xs(x0, ox1), xs(y2, oy1)));
+    const float a2 = xs(xm(xs(x0, ox2), xs(y1, oy2)), xm(xs(x1, ox2), xs(y0, oy2)));
+    const bool s0 = aa_same_sign(a0, bb), s1 = aa_same_sign(a1, bb), s2 = aa_same_sign(a2, bb);
+    if (!(s0 || s1 || s2)) return false;
+    if (d) {
+        float tmp;
+        tmp = x0; x0 = y0; y0 = tmp;
+        tmp = x1; x1 = y1; y1 = tmp;
+        tmp = x2; x2 = y2; y2 = tmp;
+    }
+    float dx0 = xs(x2, x1), dx1 = xs(x0, x2), dx2 = xs(x1, x0);
+    float dy0 = xs(y2, y1), dy1 = xs(y0, y2), dy2 = xs(y1, y0);
+    const float ds = from1 ? -1.0f : 1.0f;
+    const float NEG = -3.402823466e38f;
+    float d0 = xm(ds, xs(xm(x1, dy0), xm(y1, dx0)));
+    float d1 = xm(ds, xs(xm(x2, dy1), xm(y2, dx1)));
+    float d2 = xm(ds, xs(xm(x0, dy2), xm(y0, dx2)));
+    if (aa_same_sign(y1, y2)) { d0 = NEG; dy0 = 1.0f; }
+    if (aa_same_sign(y2, y0)) { d1 = NEG; dy1 = 1.0f; }
+    if (aa_same_sign(y0, y1)) { d2 = NEG; dy2 = 1.0f; }
+    const bool g10 = aa_rational_gt(d1, dy1, d0, dy0);
+    const bool g20 = aa_rational_gt(d2, dy2, d0, dy0);
+    const bool g21 = aa_rational_gt(d2, dy2, d1, dy1);
+    const int di = (g20 && g21) ? 2 : (g10 ? 1 : 0);
+    float dc = NEG;
+    if (di == 0 && s0 && fabsf(dy0) >= fabsf(dx0)) dc = xd(d0, dy0);
+    if (di == 1 && s1 && fabsf(dy1) >= fabsf(dx1)) dc = xd(d1, dy1);
+    if (di == 2 && s2 && fabsf(dy2) >= fabsf(dx2)) dc = xd(d2, dy2);
+    const float eps = 0.0625f;
+    if (!(dc > -eps && dc < 1.0f + eps)) return false;
+    out.clamped = !(dc > 0.0f && dc < 1.0f);
+    dc = fminf(fmaxf(dc, 0.0f), 1.0f);
+    out.tri = t;
+    out.di = di;
+    out.from1 = from1 ? 1 : 0;
+    out.alpha = xm(ds, xs(0.5f, dc));
+    out.i1 = (di == 0) ? v1 : ((di == 1) ? v2 : v0);
+    out.i2 = (di == 0) ? v2 : ((di == 1) ? v0 : v1);
+    return true;
+}
+
+// d(alpha)/d(clip position) of the two edge vertices, scaled by `dd` = d(loss)/d(alpha).
+// (px,py) is the pair's FIRST pixel.  Returns the two float4 gradients (x, y, 0, w).
+__device__ __forceinline__ void aa_pos_grad(const AAPair& pr, int px, int py, int d, const float* __restrict__ P, int H,
+                                            int W, float dd, float4& g1, float4& g2) {
+    const int qx = px + (pr.from1 ? 1 - d : 0), qy = py + (pr.from1 ? d : 0);
+    const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
+    const float fx = (float)qx + 0.5f - xh, fy = (float)qy + 0.5f - yh;
+    const float4 p1 = ldg4(P + 4 * (size_t)pr.i1), p2 = ldg4(P + 4 * (size_t)pr.i2);
+    const float iw1 = 1.0f / p1.w, iw2 = 1.0f / p2.w;
+    float x1 = p1.x * iw1 * xh - fx, y1 = p1.y * iw1 * yh - fy;
+    float x2 = p2.x * iw2 * xh - fx, y2 = p2.y * iw2 * yh - fy;
+    if (d) {
+        float tmp;
+        tmp = x1; x1 = y1; y1 = tmp;
+        tmp = x2; x2 = y2; y2 = tmp;
+    }
+    const float ex = x2 - x1, ey = y2 - y1, iy = 1.0f / ey;
+    float ax1 = -y2 * iy, ax2 = y1 * iy;
+    float ay1 = ex * y2 * iy * iy, ay2 = -ex * y1 * iy * iy;
+    if (d) {
+        float tmp;
+        tmp = ax1; ax1 = ay1; ay1 = tmp;
+        tmp = ax2; ax2 = ay2; ay2 = tmp;
+    }
+    g1 = make_float4(dd * ax1 * xh * iw1, dd * ay1 * yh * iw1, 0.0f,
+                     -dd * (ax1 * xh * p1.x + ay1 * yh * p1.y) * iw1 * iw1);
+    g2 = make_float4(dd * ax2 * xh * iw2, dd * ay2 * yh * iw2, 0.0f,
+                     -dd * (ax2 * xh * p2.x + ay2 * yh * p2.y) * iw2 * iw2);
+}
+
+}  // namespace fmhr

@@ -1,0 +1,926 @@
+// Fused HAM iteration (mesh_sfs_optim.py:198-237 phase A, :253-310 phase B).
+//
+// One iteration is two C-ABI calls so that a multi-GPU host can all-reduce the packed gradient buffer between them:
+//   fmhr_ham_step_render : vertices = vertices_tmp + delta -> vertex normals -> per-view clip positions ->
+//                          z-buffer coverage -> shade (interpolate + normalise + SH + albedo) -> antialias + losses ->
+//                          pixel backward (antialias / shading / interpolate / rasterize gradients scattered straight
+//                          into WORLD-space per-vertex accumulators with float4 vector atomics)
+//   fmhr_ham_step_update : regularisers (uniform Laplacian x2, edge hinge, delta), normal backward, loss
+//                          normalisation by the global valid-pixel count, fused Adam.
+// Nothing here materialises rast_out, the [n,V,7] attribute tensor, the [n,H,W,7] interpolated plane or the
+// [n,F,3,3] face-vertex gather of the reference; per pixel the only HBM planes are the 8-byte z-buffer, one float4
+// shaded colour and one float4 pixel-gradient (two of each in phase A, where 6 channels are antialiased).
+#include "aa_rule.cuh"
+
+namespace fmhr {
+
+int launch_raster_coverage(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
+                           unsigned long long* zbuf, cudaStream_t st);
+int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
+                              int V, float* normals, float* raw, cudaStream_t st);
+
+struct HamWs {
+    unsigned long long* zbuf;  // [n,H,W]
+    float4* plane[4];          // [n,H,W] each
+    float4* pos;               // [n,V]
+    float* vertices;           // [V,3]
+    float* normals;            // [V,3] normalised
+    float* raw;                // [V,3] un-normalised normal sums
+    float* gN;                 // [V,3]
+    float* yhat_v;             // [V,3]
+    float* yhat_a;             // [V,3]
+    float* gsh;                // [n_sh_rows,9] un-normalised SH gradients by SH row (phase A)
+    double* acc;               // [8]: 0 n_valid, 1 abs_sum, 2 mask_sq, 3 lap_v, 4 lap_a, 5 edge, 6 delta
+    float* adam_sc;            // [8]: step_size / bias2_sqrt for delta, albedo, sh
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
+    const size_t P = (size_t)c->n_views * c->H * c->W, V = (size_t)c->V;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
+    char* p;
+    p = take(P * 8); if (ws) ws->zbuf = (unsigned long long*)p;
+    const int nplanes = c->phase == 0 ? 4 : 2;
+    for (int i = 0; i < 4; i++) {
+        p = (i < nplanes) ? take(P * 16) : nullptr;
+        if (ws) ws->plane[i] = (float4*)p;
+    }
+    p = take((size_t)c->n_views * V * 16); if (ws) ws->pos = (float4*)p;
+    p = take(V * 12); if (ws) ws->vertices = (float*)p;
+    p = take(V * 12); if (ws) ws->normals = (float*)p;
+    p = take(V * 12); if (ws) ws->raw = (float*)p;
+    p = take(V * 12); if (ws) ws->gN = (float*)p;
+    p = take(V * 12); if (ws) ws->yhat_v = (float*)p;
+    p = take(V * 12); if (ws) ws->yhat_a = (float*)p;
+    p = take((size_t)c->n_sh_rows * 9 * 4); if (ws) ws->gsh = (float*)p;
+    p = take(8 * sizeof(double)); if (ws) ws->acc = (double*)p;
+    p = take(8 * sizeof(float)); if (ws) ws->adam_sc = (float*)p;
+    return off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertex-domain prologue
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __restrict__ vtmp,
+                                                              const float* __restrict__ delta, int n3,
+                                                              float* __restrict__ vertices) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) vertices[i] = vtmp[i] + delta[i];  // mesh_sfs_optim.py:253
+}
+
+// clip = ([v,1] @ w2c) @ proj, both matrices stored transposed (mesh_sfs_optim.py:262-264, get_data.py:96-97)
+__global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restrict__ vertices,
+                                                            const float* __restrict__ w2cs,
+                                                            const float* __restrict__ projs,
+                                                            const int32_t* __restrict__ view_idx, int V,
+                                                            float4* __restrict__ pos) {
+    __shared__ float Wm[16], Pm[16];
+    const int n = blockIdx.y;
+    const int view = __ldg(view_idx + n);
+    if (threadIdx.x < 16) Wm[threadIdx.x] = w2cs[(size_t)view * 16 + threadIdx.x];
+    else if (threadIdx.x < 32) Pm[threadIdx.x - 16] = projs[(size_t)view * 16 + threadIdx.x - 16];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const float x = vertices[3 * (size_t)i], y = vertices[3 * (size_t)i + 1], z = vertices[3 * (size_t)i + 2];
+    float r[4], c[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) r[j] = x * Wm[j] + y * Wm[4 + j] + z * Wm[8 + j] + Wm[12 + j];
+#pragma unroll
+    for (int j = 0; j < 4; j++) c[j] = r[0] * Pm[j] + r[1] * Pm[4 + j] + r[2] * Pm[8 + j] + r[3] * Pm[12 + j];
+    pos[(size_t)n * V + i] = make_float4(c[0], c[1], c[2], c[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pixel-domain helpers
+// ------------------------------------------------------------------------------------------------
+struct PixTri {
+    int i0, i1, i2;
+    float4 p0, p1, p2;
+    float u, v;
+};
+
+__device__ __forceinline__ void load_pixtri(int t, int px, int py, const float4* __restrict__ P,
+                                            const int32_t* __restrict__ tri, float invW, float invH, PixTri& q) {
+    q.i0 = __ldg(tri + 3 * t); q.i1 = __ldg(tri + 3 * t + 1); q.i2 = __ldg(tri + 3 * t + 2);
+    q.p0 = __ldg(P + q.i0); q.p1 = __ldg(P + q.i1); q.p2 = __ldg(P + q.i2);
+    const Bary b = bary_at(q.p0, q.p1, q.p2, px, py, invW, invH);
+    q.u = b.u; q.v = b.v;
+}
+
+__device__ __forceinline__ float3 interp3(const float* __restrict__ a, const PixTri& q) {
+    const float w = 1.0f - q.u - q.v;
+    const float* a0 = a + 3 * (size_t)q.i0;
+    const float* a1 = a + 3 * (size_t)q.i1;
+    const float* a2 = a + 3 * (size_t)q.i2;
+    return make_float3(q.u * __ldg(a0) + q.v * __ldg(a1) + w * __ldg(a2),
+                       q.u * __ldg(a0 + 1) + q.v * __ldg(a1 + 1) + w * __ldg(a2 + 1),
+                       q.u * __ldg(a0 + 2) + q.v * __ldg(a1 + 2) + w * __ldg(a2 + 2));
+}
+
+// models/utils.py:208-226, same term order
+__device__ __forceinline__ float sh_radiance(const float* c, float x, float y, float z) {
+    float r = c[0];
+    r = r + c[1] * y;
+    r = r + c[2] * z;
+    r = r + c[3] * x;
+    r = r + c[4] * x * y;
+    r = r + c[5] * y * z;
+    r = r + c[6] * (2 * z * z - x * x - y * y);
+    r = r + c[7] * z * x;
+    r = r + c[8] * (x * x - y * y);
+    return r;
+}
+
+struct ViewCtx {
+    float M[12];  // rows 0..2 of (w2c @ proj), columns x,y,z,w : d(clip_j)/d(world_i) = M[4i+j]
+    float sh[9];
+};
+
+__device__ __forceinline__ void load_view_ctx(ViewCtx* s, const float* __restrict__ w2cs,
+                                              const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
+                                              int view, int sh_row) {
+    if (threadIdx.x < 12) {
+        const int i = threadIdx.x >> 2, j = threadIdx.x & 3;
+        const float* Wm = w2cs + (size_t)view * 16;
+        const float* Pm = projs + (size_t)view * 16;
+        s->M[threadIdx.x] = Wm[4 * i] * Pm[j] + Wm[4 * i + 1] * Pm[4 + j] + Wm[4 * i + 2] * Pm[8 + j] +
+                            Wm[4 * i + 3] * Pm[12 + j];
+    } else if (threadIdx.x >= 32 && threadIdx.x < 41) {
+        s->sh[threadIdx.x - 32] = sh_coeffs[(size_t)sh_row * 9 + threadIdx.x - 32];
+    }
+}
+
+// clip-space gradient (x, y, -, w) -> world-space xyz
+__device__ __forceinline__ float3 clip_to_world(const float* M, float gx, float gy, float gw) {
+    return make_float3(M[0] * gx + M[1] * gy + M[3] * gw, M[4] * gx + M[5] * gy + M[7] * gw,
+                       M[8] * gx + M[9] * gy + M[11] * gw);
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* sm) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.0f;
+    if (threadIdx.x < 8) r = sm[threadIdx.x];
+    if (threadIdx.x < 32) {
+        r += __shfl_xor_sync(0xffffffffu, r, 4);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+    }
+    __syncthreads();
+    return r;  // valid in thread 0
+}
+
+// Per-vertex accumulator layout in `packed` (12 floats = 3 float4):
+//   A = (photo_pos.xyz, mask_pos.x)  B = (mask_pos.yz, normal.xy)  C = (normal.z, albedo.bgr)
+// photo_* are gradients of the UN-NORMALISED photometric sum  sum |tmp_img - img|, mask_pos of sum (pred - valid)^2 / 2.
+
+// ------------------------------------------------------------------------------------------------
+// shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A)
+// ------------------------------------------------------------------------------------------------
+template <int PHASE>
+__global__ void __launch_bounds__(256) ham_shade_kernel(const unsigned long long* __restrict__ zbuf,
+                                                        const float4* __restrict__ pos,
+                                                        const int32_t* __restrict__ tri,
+                                                        const float* __restrict__ normals,
+                                                        const float* __restrict__ albedo,
+                                                        const float* __restrict__ masks,
+                                                        const float* __restrict__ sh_coeffs,
+                                                        const int32_t* __restrict__ view_idx,
+                                                        const int32_t* __restrict__ sh_idx, int V, int H, int W,
+                                                        float4* __restrict__ plane0, float4* __restrict__ plane1,
+                                                        double* __restrict__ acc) {
+    __shared__ float sh[9];
+    __shared__ float red[8];
+    const int n = blockIdx.y;
+    const int view = __ldg(view_idx + n);
+    if (PHASE == 1 && threadIdx.x < 9) sh[threadIdx.x] = sh_coeffs[(size_t)__ldg(sh_idx + n) * 9 + threadIdx.x];
+    __syncthreads();
+    const int hw = H * W;
+    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+    float nvalid = 0.0f;
+    if (rem < hw) {
+        const size_t pix = (size_t)n * hw + rem;
+        const unsigned long long key = zbuf[pix];
+        if (key != ZB_EMPTY) {
+            const int py = rem / W, px = rem - py * W;
+            const int t = (int)(uint32_t)key;
+            const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
+            PixTri q;
+            load_pixtri(t, px, py, pos + (size_t)n * V, tri, invW, invH, q);
+            const float3 m = interp3(normals, q);
+            const float3 a = interp3(albedo, q);
+            const bool valid = __ldg(masks + (size_t)view * hw + rem) > 0.0f;
+            nvalid = valid ? 1.0f : 0.0f;
+            if (PHASE == 1) {
+                float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {
+                    const float inv = 1.0f / fmaxf(sqrtf(m.x * m.x + m.y * m.y + m.z * m.z), 1e-12f);
+                    const float r = sh_radiance(sh, m.x * inv, m.y * inv, m.z * inv);
+                    col = make_float4(r * a.x, r * a.y, r * a.z, 1.0f);
+                }
+                plane0[pix] = col;
+            } else {
+                plane0[pix] = make_float4(m.x, m.y, m.z, nvalid);
+                plane1[pix] = make_float4(a.x, a.y, a.z, 0.0f);
+            }
+        }
+    }
+    const float s = block_sum_256(nvalid, red);
+    if (threadIdx.x == 0 && s != 0.0f) atomicAdd(acc + 0, (double)s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// antialias (gather form) + losses
+// ------------------------------------------------------------------------------------------------
+struct NbrKeys {
+    int tri;   // -1 empty
+    float zw;
+};
+__device__ __forceinline__ NbrKeys decode_key(unsigned long long key) {
+    NbrKeys k;
+    if (key == ZB_EMPTY) { k.tri = -1; k.zw = 0.0f; }
+    else { k.tri = (int)(uint32_t)key; k.zw = depth_from_key((uint32_t)(key >> 32)); }
+    return k;
+}
+
+// Visits the (up to) four pixel pairs that contain pixel (px,py).  For every pair whose analysis finds a silhouette
+// crossing, calls f(pair, pix_first, pix_second, d, self_is_first).
+template <typename F>
+__device__ __forceinline__ void for_each_pair(const unsigned long long* __restrict__ zb, int px, int py, int H, int W,
+                                              const float* __restrict__ P, const int32_t* __restrict__ tri,
+                                              const int32_t* __restrict__ opp, int V, int T, NbrKeys self, F f) {
+    const int rem = py * W + px;
+    // d = 0: (self, right) ; d = 1: (self, down) ; then (left, self), (up, self)
+#pragma unroll
+    for (int which = 0; which < 4; which++) {
+        const int d = which & 1;
+        const bool self_first = which < 2;
+        const int qx = self_first ? px : px - (1 - d), qy = self_first ? py : py - d;  // first pixel of the pair
+        const int ox = self_first ? px + (1 - d) : qx, oy = self_first ? py + d : qy;  // the OTHER pixel
+        if (ox < 0 || oy < 0 || ox >= W || oy >= H) continue;
+        const int orem = oy * W + ox;
+        const NbrKeys other = decode_key(zb[orem]);
+        if (other.tri == self.tri) continue;
+        const NbrKeys k0 = self_first ? self : other, k1 = self_first ? other : self;
+        AAPair pr;
+        if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, qx, qy, d, P, tri, opp, V, T, H, W, pr)) continue;
+        f(pr, self_first ? rem : orem, self_first ? orem : rem, d, self_first, qx, qy);
+    }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(256) ham_aa_loss_kernel(
+    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
+    const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
+    int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
+    float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
+    float* __restrict__ dbg_image, float* __restrict__ dbg_mask) {
+    __shared__ float sh[9];
+    __shared__ float red[8];
+    const int n = blockIdx.y;
+    const int view = __ldg(view_idx + n);
+    if (PHASE == 0 && threadIdx.x < 9) sh[threadIdx.x] = sh_coeffs[(size_t)__ldg(sh_idx + n) * 9 + threadIdx.x];
+    __syncthreads();
+    const int hw = H * W;
+    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+    float abs_sum = 0.0f, msk_sum = 0.0f;
+    float gc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) gc[k] = 0.0f;
+    if (rem < hw) {
+        const size_t base = (size_t)n * hw;
+        const size_t pix = base + rem;
+        const unsigned long long* zb = zbuf + base;
+        const NbrKeys self = decode_key(zb[rem]);
+        const int py = rem / W, px = rem - py * W;
+        const float* P = reinterpret_cast<const float*>(pos + (size_t)n * V);
+        // own (pre-antialias) values; empty pixels are zero in every channel
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (self.tri >= 0) {
+            c0 = plane0[pix];
+            if (PHASE == 0) c1 = plane1[pix];
+        }
+        const float cov_self = self.tri >= 0 ? 1.0f : 0.0f;
+        float4 a0 = c0, a1 = c1;  // antialiased accumulators
+        float amask = cov_self;
+        for_each_pair(zb, px, py, H, W, P, tri, opp, V, T, self,
+                      [&](const AAPair& pr, int r_first, int r_second, int d, bool self_first, int qx, int qy) {
+                          const bool recv_first = pr.alpha > 0.0f;
+                          if (recv_first != self_first) return;  // this pixel is not the receiver
+                          const int orem = self_first ? r_second : r_first;
+                          const bool ocov = decode_key(zb[orem]).tri >= 0;
+                          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                          if (ocov) {
+                              o0 = plane0[base + orem];
+                              if (PHASE == 0) o1 = plane1[base + orem];
+                          }
+                          // out[recv] += alpha * (color[second] - color[first])
+                          const float sgn = self_first ? pr.alpha : -pr.alpha;  // alpha*(other - self) or alpha*(self - other)
+                          a0.x += sgn * (o0.x - c0.x); a0.y += sgn * (o0.y - c0.y); a0.z += sgn * (o0.z - c0.z);
+                          if (PHASE == 0) { a1.x += sgn * (o1.x - c1.x); a1.y += sgn * (o1.y - c1.y); a1.z += sgn * (o1.z - c1.z); }
+                          if (PHASE == 1) amask += sgn * ((ocov ? 1.0f : 0.0f) - cov_self);
+                      });
+        const bool valid = self.tri >= 0 && c0.w > 0.0f;
+        const float* img = imgs + ((size_t)view * hw + rem) * 3;
+        if (PHASE == 1) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {  // mesh_sfs_optim.py:289  l1 over tmp_img[valid_idx]
+                const float d0 = a0.x - __ldg(img), d1 = a0.y - __ldg(img + 1), d2 = a0.z - __ldg(img + 2);
+                abs_sum = fabsf(d0) + fabsf(d1) + fabsf(d2);
+                g.x = (d0 > 0.f) - (d0 < 0.f); g.y = (d1 > 0.f) - (d1 < 0.f); g.z = (d2 > 0.f) - (d2 < 0.f);
+            }
+            const float dm = amask - __ldg(valid_masks + (size_t)view * hw + rem);  // mesh_sfs_optim.py:295
+            msk_sum = dm * dm;
+            g.w = dm;
+            gplane0[pix] = g;
+            if (dbg_image) { dbg_image[pix * 3] = a0.x; dbg_image[pix * 3 + 1] = a0.y; dbg_image[pix * 3 + 2] = a0.z; }
+            if (dbg_mask) dbg_mask[pix] = amask;
+        } else {
+            // phase A (mesh_sfs_optim.py:217-230): a0 = antialiased normals, a1 = antialiased albedo
+            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+            float3 pred = make_float3(0.f, 0.f, 0.f);
+            if (valid) {
+                const float len = sqrtf(a0.x * a0.x + a0.y * a0.y + a0.z * a0.z);
+                const float inv = 1.0f / fmaxf(len, 1e-12f);
+                const float nx = a0.x * inv, ny = a0.y * inv, nz = a0.z * inv;
+                const float r = sh_radiance(sh, nx, ny, nz);
+                pred = make_float3(r * a1.x, r * a1.y, r * a1.z);
+                const float d0 = pred.x - __ldg(img), d1 = pred.y - __ldg(img + 1), d2 = pred.z - __ldg(img + 2);
+                abs_sum = fabsf(d0) + fabsf(d1) + fabsf(d2);
+                const float s0 = (d0 > 0.f) - (d0 < 0.f), s1 = (d1 > 0.f) - (d1 < 0.f), s2 = (d2 > 0.f) - (d2 < 0.f);
+                g1 = make_float4(s0 * r, s1 * r, s2 * r, 0.0f);  // d/d(albedo_aa)
+                const float gr = s0 * a1.x + s1 * a1.y + s2 * a1.z;
+                gc[0] = gr; gc[1] = gr * ny; gc[2] = gr * nz; gc[3] = gr * nx; gc[4] = gr * nx * ny; gc[5] = gr * ny * nz;
+                gc[6] = gr * (2 * nz * nz - nx * nx - ny * ny); gc[7] = gr * nz * nx; gc[8] = gr * (nx * nx - ny * ny);
+                // normals are not trainable in phase A (vertices detached, mesh_sfs_optim.py:191,196): g0 stays 0
+            }
+            gplane0[pix] = g0;
+            gplane1[pix] = g1;
+            if (dbg_image) { dbg_image[pix * 3] = pred.x; dbg_image[pix * 3 + 1] = pred.y; dbg_image[pix * 3 + 2] = pred.z; }
+        }
+    }
+    float s = block_sum_256(abs_sum, red);
+    if (threadIdx.x == 0 && s != 0.0f) atomicAdd(acc + 1, (double)s);
+    if (PHASE == 1) {
+        s = block_sum_256(msk_sum, red);
+        if (threadIdx.x == 0 && s != 0.0f) atomicAdd(acc + 2, (double)s);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            s = block_sum_256(gc[k], red);
+            if (threadIdx.x == 0 && s != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pixel backward: antialias bwd (gather form for colours, owner-scatter for positions), shading bwd,
+// interpolate bwd, rasterize bwd; everything lands in the per-vertex world-space accumulators.
+// ------------------------------------------------------------------------------------------------
+template <int PHASE>
+__global__ void __launch_bounds__(256) ham_pixel_bwd_kernel(
+    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
+    const float* __restrict__ w2cs, const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
+    const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
+    const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
+    const float4* __restrict__ gplane1, float4* __restrict__ G) {
+    __shared__ ViewCtx ctx;
+    const int n = blockIdx.y;
+    const int view = __ldg(view_idx + n);
+    load_view_ctx(&ctx, w2cs, projs, sh_coeffs, view, __ldg(sh_idx + n));
+    __syncthreads();
+    const int hw = H * W;
+    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rem >= hw) return;
+    const size_t base = (size_t)n * hw;
+    const size_t pix = base + rem;
+    const unsigned long long* zb = zbuf + base;
+    const NbrKeys self = decode_key(zb[rem]);
+    const int py = rem / W, px = rem - py * W;
+    const float4* Pv = pos + (size_t)n * V;
+    const float* P = reinterpret_cast<const float*>(Pv);
+    const bool covered = self.tri >= 0;
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+    if (covered) {
+        c0 = plane0[pix];
+        if (PHASE == 0) c1 = plane1[pix];
+    }
+    const float cov_self = covered ? 1.0f : 0.0f;
+    // gradient w.r.t. this pixel's PRE-antialias values: pass-through + pair terms
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    if (covered) {  // empty pixels have no upstream producer
+        g0 = gplane0[pix];
+        if (PHASE == 0) g1 = gplane1[pix];
+    }
+    for_each_pair(zb, px, py, H, W, P, tri, opp, V, T, self,
+                  [&](const AAPair& pr, int r_first, int r_second, int d, bool self_first, int qx, int qy) {
+                      const int recv = (pr.alpha > 0.0f) ? r_first : r_second;
+                      const float4 gr0 = gplane0[base + recv];
+                      float4 gr1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                      if (PHASE == 0) gr1 = gplane1[base + recv];
+                      // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g
+                      const float sg = self_first ? -pr.alpha : pr.alpha;
+                      g0.x += sg * gr0.x; g0.y += sg * gr0.y; g0.z += sg * gr0.z;
+                      if (PHASE == 0) { g1.x += sg * gr1.x; g1.y += sg * gr1.y; g1.z += sg * gr1.z; }
+                      if (PHASE == 1 && self_first && !pr.clamped) {
+                          // position gradient: the pair's first pixel owns the scatter
+                          const int orem = r_second;
+                          const bool ocov = decode_key(zb[orem]).tri >= 0;
+                          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                          if (ocov) o0 = plane0[base + orem];
+                          const float dd_img = gr0.x * (o0.x - c0.x) + gr0.y * (o0.y - c0.y) + gr0.z * (o0.z - c0.z);
+                          const float dd_msk = gr0.w * ((ocov ? 1.0f : 0.0f) - cov_self);
+                          if (dd_img != 0.0f || dd_msk != 0.0f) {
+                              float4 e1, e2;
+                              aa_pos_grad(pr, qx, qy, d, P, H, W, 1.0f, e1, e2);
+                              const float3 w1 = clip_to_world(ctx.M, e1.x, e1.y, e1.w);
+                              const float3 w2 = clip_to_world(ctx.M, e2.x, e2.y, e2.w);
+                              atomicAdd(G + 3 * (size_t)pr.i1, make_float4(dd_img * w1.x, dd_img * w1.y, dd_img * w1.z, dd_msk * w1.x));
+                              atomicAdd(G + 3 * (size_t)pr.i1 + 1, make_float4(dd_msk * w1.y, dd_msk * w1.z, 0.f, 0.f));
+                              atomicAdd(G + 3 * (size_t)pr.i2, make_float4(dd_img * w2.x, dd_img * w2.y, dd_img * w2.z, dd_msk * w2.x));
+                              atomicAdd(G + 3 * (size_t)pr.i2 + 1, make_float4(dd_msk * w2.y, dd_msk * w2.z, 0.f, 0.f));
+                          }
+                      }
+                  });
+    if (!covered) return;
+    const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
+    PixTri q;
+    load_pixtri(self.tri, px, py, Pv, tri, invW, invH, q);
+    const float w = 1.0f - q.u - q.v;
+    if (PHASE == 0) {
+        // only the albedo attribute is trainable: interpolate bwd
+        if (g1.x == 0.0f && g1.y == 0.0f && g1.z == 0.0f) return;
+        atomicAdd(G + 3 * (size_t)q.i0 + 2, make_float4(0.f, q.u * g1.x, q.u * g1.y, q.u * g1.z));
+        atomicAdd(G + 3 * (size_t)q.i1 + 2, make_float4(0.f, q.v * g1.x, q.v * g1.y, q.v * g1.z));
+        atomicAdd(G + 3 * (size_t)q.i2 + 2, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
+        return;
+    }
+    // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286)
+    if (!(c0.w > 0.0f)) return;
+    if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) return;
+    const float3 m = interp3(normals, q);
+    const float3 a = interp3(albedo, q);
+    const float len = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
+    const float inv = 1.0f / fmaxf(len, 1e-12f);
+    const float nx = m.x * inv, ny = m.y * inv, nz = m.z * inv;
+    const float* c = ctx.sh;
+    const float r = sh_radiance(c, nx, ny, nz);
+    const float3 ga = make_float3(g0.x * r, g0.y * r, g0.z * r);           // d/d(interpolated albedo)
+    const float gr = g0.x * a.x + g0.y * a.y + g0.z * a.z;                 // d/d(radiance)
+    float3 gn = make_float3(gr * (c[3] + c[4] * ny - 2 * c[6] * nx + c[7] * nz + 2 * c[8] * nx),
+                            gr * (c[1] + c[4] * nx + c[5] * nz - 2 * c[6] * ny - 2 * c[8] * ny),
+                            gr * (c[2] + c[5] * ny + 4 * c[6] * nz + c[7] * nx));
+    float3 gm;  // through F.normalize(eps=1e-12), mesh_sfs_optim.py:273
+    if (len > 1e-12f) {
+        const float dt = nx * gn.x + ny * gn.y + nz * gn.z;
+        gm = make_float3((gn.x - nx * dt) * inv, (gn.y - ny * dt) * inv, (gn.z - nz * dt) * inv);
+    } else {
+        gm = make_float3(gn.x * inv, gn.y * inv, gn.z * inv);
+    }
+    // interpolate bwd: d/du, d/dv over the six differentiable attributes
+    const float* n0 = normals + 3 * (size_t)q.i0; const float* n1 = normals + 3 * (size_t)q.i1; const float* n2 = normals + 3 * (size_t)q.i2;
+    const float* b0 = albedo + 3 * (size_t)q.i0; const float* b1 = albedo + 3 * (size_t)q.i1; const float* b2 = albedo + 3 * (size_t)q.i2;
+    const float n2x = __ldg(n2), n2y = __ldg(n2 + 1), n2z = __ldg(n2 + 2);
+    const float b2x = __ldg(b2), b2y = __ldg(b2 + 1), b2z = __ldg(b2 + 2);
+    const float du = gm.x * (__ldg(n0) - n2x) + gm.y * (__ldg(n0 + 1) - n2y) + gm.z * (__ldg(n0 + 2) - n2z) +
+                     ga.x * (__ldg(b0) - b2x) + ga.y * (__ldg(b0 + 1) - b2y) + ga.z * (__ldg(b0 + 2) - b2z);
+    const float dv = gm.x * (__ldg(n1) - n2x) + gm.y * (__ldg(n1 + 1) - n2y) + gm.z * (__ldg(n1 + 2) - n2z) +
+                     ga.x * (__ldg(b1) - b2x) + ga.y * (__ldg(b1 + 1) - b2y) + ga.z * (__ldg(b1 + 2) - b2z);
+    // rasterize bwd
+    const float fx = (float)(2 * px + 1) / (float)W - 1.0f;
+    const float fy = (float)(2 * py + 1) / (float)H - 1.0f;
+    const float q0x = q.p0.x - fx * q.p0.w, q0y = q.p0.y - fy * q.p0.w;
+    const float q1x = q.p1.x - fx * q.p1.w, q1y = q.p1.y - fy * q.p1.w;
+    const float q2x = q.p2.x - fx * q.p2.w, q2y = q.p2.y - fy * q.p2.w;
+    const float e0 = q1x * q2y - q1y * q2x, e1 = q2x * q0y - q2y * q0x, e2 = q0x * q1y - q0y * q1x;
+    const float at = e0 + e1 + e2;
+    const float iw = 1.0f / (at + copysignf(1e-6f, at));
+    const float bb0 = e0 * iw, bb1 = e1 * iw;
+    const float gb0 = du * iw, gb1 = dv * iw, gbb = gb0 * bb0 + gb1 * bb1;
+    const float g0x = gbb * (q2y - q1y) - gb1 * q2y;
+    const float g1x = gbb * (q0y - q2y) + gb0 * q2y;
+    const float g2x = gbb * (q1y - q0y) - gb0 * q1y + gb1 * q0y;
+    const float g0y = gbb * (q1x - q2x) + gb1 * q2x;
+    const float g1y = gbb * (q2x - q0x) - gb0 * q2x;
+    const float g2y = gbb * (q0x - q1x) + gb0 * q1x - gb1 * q0x;
+    const float3 w0 = clip_to_world(ctx.M, g0x, g0y, -fx * g0x - fy * g0y);
+    const float3 w1 = clip_to_world(ctx.M, g1x, g1y, -fx * g1x - fy * g1y);
+    const float3 w2 = clip_to_world(ctx.M, g2x, g2y, -fx * g2x - fy * g2y);
+    float4* G0 = G + 3 * (size_t)q.i0; float4* G1 = G + 3 * (size_t)q.i1; float4* G2 = G + 3 * (size_t)q.i2;
+    atomicAdd(G0, make_float4(w0.x, w0.y, w0.z, 0.f));
+    atomicAdd(G0 + 1, make_float4(0.f, 0.f, q.u * gm.x, q.u * gm.y));
+    atomicAdd(G0 + 2, make_float4(q.u * gm.z, q.u * ga.x, q.u * ga.y, q.u * ga.z));
+    atomicAdd(G1, make_float4(w1.x, w1.y, w1.z, 0.f));
+    atomicAdd(G1 + 1, make_float4(0.f, 0.f, q.v * gm.x, q.v * gm.y));
+    atomicAdd(G1 + 2, make_float4(q.v * gm.z, q.v * ga.x, q.v * ga.y, q.v * ga.z));
+    atomicAdd(G2, make_float4(w2.x, w2.y, w2.z, 0.f));
+    atomicAdd(G2 + 1, make_float4(0.f, 0.f, w * gm.x, w * gm.y));
+    atomicAdd(G2 + 2, make_float4(w * gm.z, w * ga.x, w * ga.y, w * ga.z));
+}
+
+__global__ void ham_finalize_scalars_kernel(const double* __restrict__ acc, float* __restrict__ scal) {
+    if (threadIdx.x == 0) {
+        scal[0] = (float)acc[0];
+        scal[1] = (float)acc[1];
+        scal[2] = (float)acc[2];
+        scal[3] = 0.0f;
+    }
+}
+
+// zbuf -> rast_out for fmhr_ham_debug_export
+__global__ void __launch_bounds__(256) ham_export_rast_kernel(const unsigned long long* __restrict__ zbuf,
+                                                              const float4* __restrict__ pos,
+                                                              const int32_t* __restrict__ tri, int V, int H, int W,
+                                                              float4* __restrict__ rast) {
+    const int n = blockIdx.y, hw = H * W;
+    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rem >= hw) return;
+    const size_t pix = (size_t)n * hw + rem;
+    const unsigned long long key = zbuf[pix];
+    if (key == ZB_EMPTY) { rast[pix] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    const int t = (int)(uint32_t)key, py = rem / W, px = rem - py * W;
+    const float4* P = pos + (size_t)n * V;
+    const Bary b = bary_at(__ldg(P + __ldg(tri + 3 * t)), __ldg(P + __ldg(tri + 3 * t + 1)),
+                           __ldg(P + __ldg(tri + 3 * t + 2)), px, py, xd(1.0f, (float)W), xd(1.0f, (float)H));
+    rast[pix] = make_float4(b.u, b.v, b.zw, (float)(t + 1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// update: regularisers, normal backward, normalisation, Adam
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 ldf3(const float* p) { return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+
+// pass 1: Laplacian forward for vertices and albedo, edge/delta losses, projector of the normal backward, Adam scalars
+__global__ void __launch_bounds__(128) ham_update_pass1_kernel(
+    fmhr_ham_config cfg, const float* __restrict__ vertices, const float* __restrict__ delta,
+    const float* __restrict__ albedo, const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr,
+    const int32_t* __restrict__ v2f_idx, const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx,
+    const float* __restrict__ raw, const float* __restrict__ packed, float* __restrict__ yhat_v,
+    float* __restrict__ yhat_a, float* __restrict__ gN, double* __restrict__ acc, int32_t* __restrict__ adam_step,
+    float* __restrict__ adam_sc) {
+    __shared__ float red[4][4];
+    const int V = cfg.V;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lv = 0.f, la = 0.f, le = 0.f, ld = 0.f;
+    if (i < V) {
+        const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
+        float3 sv = make_float3(0.f, 0.f, 0.f), sa = sv;
+        for (int j = b; j < e; j++) {
+            const size_t nb = 3 * (size_t)__ldg(v2v_idx + j);
+            const float3 xv = ldf3(vertices + nb), xa_ = ldf3(albedo + nb);
+            sv.x += xv.x; sv.y += xv.y; sv.z += xv.z;
+            sa.x += xa_.x; sa.y += xa_.y; sa.z += xa_.z;
+        }
+        const float invd = (e > b) ? 1.0f / (float)(e - b) : 0.0f;
+        const float3 vi = ldf3(vertices + 3 * (size_t)i), ai = ldf3(albedo + 3 * (size_t)i);
+        sv = make_float3(sv.x * invd - vi.x, sv.y * invd - vi.y, sv.z * invd - vi.z);
+        sa = make_float3(sa.x * invd - ai.x, sa.y * invd - ai.y, sa.z * invd - ai.z);
+        lv = sqrtf(sv.x * sv.x + sv.y * sv.y + sv.z * sv.z);
+        la = sqrtf(sa.x * sa.x + sa.y * sa.y + sa.z * sa.z);
+        const float iv = lv > 0.f ? 1.0f / lv : 0.f, ia = la > 0.f ? 1.0f / la : 0.f;
+        yhat_v[3 * (size_t)i] = sv.x * iv; yhat_v[3 * (size_t)i + 1] = sv.y * iv; yhat_v[3 * (size_t)i + 2] = sv.z * iv;
+        yhat_a[3 * (size_t)i] = sa.x * ia; yhat_a[3 * (size_t)i + 1] = sa.y * ia; yhat_a[3 * (size_t)i + 2] = sa.z * ia;
+        // edge hinge (mesh_sfs_optim.py:296-302): every half-edge is seen from both of its endpoints -> weight 1/2
+        const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
+        for (int j = fb; j < fe; j++) {
+            const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
+#pragma unroll
+            for (int s = 1; s <= 2; s++) {
+                const float3 o = ldf3(vertices + 3 * (size_t)__ldg(tri + 3 * t + (k + s) % 3));
+                const float dx = vi.x - o.x, dy = vi.y - o.y, dz = vi.z - o.z;
+                const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
+                le += 0.5f * fminf(fmaxf(x, 0.0f), 1.0f);
+            }
+        }
+        const float3 di = ldf3(delta + 3 * (size_t)i);
+        ld = di.x * di.x + di.y * di.y + di.z * di.z;
+        // normal backward, step 1: through the normalisation (un-normalised photometric scale; linear, scaled later)
+        const float* Gi = packed + 12 * (size_t)i;
+        const float3 g = make_float3(Gi[6], Gi[7], Gi[8]);
+        const float3 N = ldf3(raw + 3 * (size_t)i);
+        const float len = sqrtf(N.x * N.x + N.y * N.y + N.z * N.z);
+        float3 r;
+        if (len > 1e-6f) {
+            const float inv = 1.0f / len;
+            const float3 nh = make_float3(N.x * inv, N.y * inv, N.z * inv);
+            const float d = nh.x * g.x + nh.y * g.y + nh.z * g.z;
+            r = make_float3((g.x - nh.x * d) * inv, (g.y - nh.y * d) * inv, (g.z - nh.z * d) * inv);
+        } else {
+            r = make_float3(g.x * 1e6f, g.y * 1e6f, g.z * 1e6f);
+        }
+        gN[3 * (size_t)i] = r.x; gN[3 * (size_t)i + 1] = r.y; gN[3 * (size_t)i + 2] = r.z;
+    }
+    lv = warp_sum(lv); la = warp_sum(la); le = warp_sum(le); ld = warp_sum(ld);
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        red[0][w] = lv; red[1][w] = la; red[2][w] = le; red[3][w] = ld;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const float s = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+        if (s != 0.0f) atomicAdd(acc + 3 + threadIdx.x, (double)s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // Adam bias corrections (torch.optim.Adam defaults); which parameters step depends on the phase:
+        //   phase A: albedo, sh   (mesh_sfs_optim.py:193)     phase B: delta, albedo   (:242-244, sh has no grad)
+        const int steps[3] = {cfg.phase == 1, 1, cfg.phase == 0};
+        const float lrs[3] = {cfg.lr, cfg.albedo_lr, cfg.sh_lr};
+        for (int k = 0; k < 3; k++) {
+            const int t = adam_step[k] + steps[k];
+            adam_step[k] = t;
+            const double b1 = 1.0 - pow((double)cfg.beta1, (double)max(t, 1));
+            const double b2 = 1.0 - pow((double)cfg.beta2, (double)max(t, 1));
+            adam_sc[2 * k] = (float)((double)lrs[k] / b1);
+            adam_sc[2 * k + 1] = (float)sqrt(b2);
+        }
+    }
+}
+
+__device__ __forceinline__ float adam_update(float p, float g, float* m, float* v, float b1, float b2, float eps,
+                                             float step_size, float bias2_sqrt) {
+    const float mm = *m + (g - *m) * (1.0f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
+    const float vv = *v * b2 + (1.0f - b2) * g * g;
+    *m = mm;
+    *v = vv;
+    const float denom = sqrtf(vv) / bias2_sqrt + eps;
+    return p - step_size * (mm / denom);
+}
+
+// pass 2: gather every gradient term per vertex, then Adam on delta (phase B) and albedo
+__global__ void __launch_bounds__(128) ham_update_pass2_kernel(
+    fmhr_ham_config cfg, const float* __restrict__ vertices, float* __restrict__ delta, float* __restrict__ albedo,
+    const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr, const int32_t* __restrict__ v2f_idx,
+    const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed,
+    const float* __restrict__ yhat_v, const float* __restrict__ yhat_a, const float* __restrict__ gN,
+    float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
+    const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad) {
+    const int V = cfg.V;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* scal = packed + 12 * (size_t)V;
+    const float n_valid = scal[0];
+    const float P_global = (float)cfg.n_views_global * (float)cfg.H * (float)cfg.W;
+    const float s_photo = cfg.sfs_weight / (3.0f * n_valid);            // F.l1_loss mean over [N_valid,3]
+    const float s_mask = 2.0f * cfg.mask_weight / P_global;              // F.mse_loss mean over n*H*W
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const float sfs = cfg.sfs_weight * scal[1] / (3.0f * n_valid);
+        const float lap = cfg.lap_weight * (float)(acc[3] / (double)V);
+        const float alb = cfg.albedo_weight * (float)(acc[4] / (double)V);
+        const float msk = cfg.phase == 1 ? cfg.mask_weight * scal[2] / P_global : 0.0f;
+        const float edg = cfg.edge_weight * (float)(acc[5] / (3.0 * (double)cfg.T));
+        const float del = cfg.delta_weight * (float)(acc[6] / (double)V);
+        losses[0] = sfs; losses[1] = cfg.phase == 1 ? lap : 0.0f; losses[2] = alb; losses[3] = msk;
+        losses[4] = cfg.phase == 1 ? edg : 0.0f; losses[5] = cfg.phase == 1 ? del : 0.0f; losses[6] = n_valid;
+        losses[7] = cfg.phase == 1 ? sfs + lap + alb + msk + edg + del : sfs;
+    }
+    if (i >= V) return;
+    const float* Gi = packed + 12 * (size_t)i;
+    // Laplacian backward rows (L^T yhat) for vertices and albedo
+    float3 lv = make_float3(0.f, 0.f, 0.f), la = lv;
+    {
+        const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
+        for (int q = b; q < e; q++) {
+            const int j = __ldg(v2v_idx + q);
+            const float invd = 1.0f / (float)(__ldg(v2v_ptr + j + 1) - __ldg(v2v_ptr + j));
+            const float3 yv = ldf3(yhat_v + 3 * (size_t)j), ya = ldf3(yhat_a + 3 * (size_t)j);
+            lv.x += yv.x * invd; lv.y += yv.y * invd; lv.z += yv.z * invd;
+            la.x += ya.x * invd; la.y += ya.y * invd; la.z += ya.z * invd;
+        }
+        const float3 yv = ldf3(yhat_v + 3 * (size_t)i), ya = ldf3(yhat_a + 3 * (size_t)i);
+        const float iv = 1.0f / (float)V;
+        lv = make_float3((lv.x - yv.x) * iv, (lv.y - yv.y) * iv, (lv.z - yv.z) * iv);
+        la = make_float3((la.x - ya.x) * iv, (la.y - ya.y) * iv, (la.z - ya.z) * iv);
+    }
+    // albedo gradient (phase A: photometric only, mesh_sfs_optim.py:233; phase B adds the albedo Laplacian)
+    float3 ga = make_float3(s_photo * Gi[9], s_photo * Gi[10], s_photo * Gi[11]);
+    if (cfg.phase == 1) { ga.x += cfg.albedo_weight * la.x; ga.y += cfg.albedo_weight * la.y; ga.z += cfg.albedo_weight * la.z; }
+    float3 gd = make_float3(0.f, 0.f, 0.f);
+    if (cfg.phase == 1) {
+        const float3 vi = ldf3(vertices + 3 * (size_t)i);
+        // normal backward gather + edge hinge gradient over incident faces
+        float3 gnb = make_float3(0.f, 0.f, 0.f), ge = gnb;
+        const float3 gi = ldf3(gN + 3 * (size_t)i);
+        const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
+        for (int j = fb; j < fe; j++) {
+            const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
+            const int ia = __ldg(tri + 3 * t + (k + 1) % 3), ib = __ldg(tri + 3 * t + (k + 2) % 3);
+            const float3 pa = ldf3(vertices + 3 * (size_t)ia), pb = ldf3(vertices + 3 * (size_t)ib);
+            const float3 ka = ldf3(gN + 3 * (size_t)ia), kb = ldf3(gN + 3 * (size_t)ib);
+            const float3 Gs = make_float3(gi.x + ka.x + kb.x, gi.y + ka.y + kb.y, gi.z + ka.z + kb.z);
+            const float3 ed = make_float3(pa.x - pb.x, pa.y - pb.y, pa.z - pb.z);
+            gnb.x += ed.y * Gs.z - ed.z * Gs.y; gnb.y += ed.z * Gs.x - ed.x * Gs.z; gnb.z += ed.x * Gs.y - ed.y * Gs.x;
+            const float3 o[2] = {pa, pb};
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const float dx = vi.x - o[s].x, dy = vi.y - o[s].y, dz = vi.z - o[s].z;
+                const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
+                if (x >= 0.0f && x <= 1.0f) { ge.x += 2.0f * dx; ge.y += 2.0f * dy; ge.z += 2.0f * dz; }
+            }
+        }
+        const float s_edge = cfg.edge_weight / (3.0f * (float)cfg.T);
+        const float s_delta = 2.0f * cfg.delta_weight / (float)V;
+        const float3 di = ldf3(delta + 3 * (size_t)i);
+        gd.x = s_photo * (Gi[0] + gnb.x) + s_mask * Gi[3] + cfg.lap_weight * lv.x + s_edge * ge.x + s_delta * di.x;
+        gd.y = s_photo * (Gi[1] + gnb.y) + s_mask * Gi[4] + cfg.lap_weight * lv.y + s_edge * ge.y + s_delta * di.y;
+        gd.z = s_photo * (Gi[2] + gnb.z) + s_mask * Gi[5] + cfg.lap_weight * lv.z + s_edge * ge.z + s_delta * di.z;
+    }
+    if (dbg_grad) {
+        dbg_grad[6 * (size_t)i] = gd.x; dbg_grad[6 * (size_t)i + 1] = gd.y; dbg_grad[6 * (size_t)i + 2] = gd.z;
+        dbg_grad[6 * (size_t)i + 3] = ga.x; dbg_grad[6 * (size_t)i + 4] = ga.y; dbg_grad[6 * (size_t)i + 5] = ga.z;
+    }
+    const float gds[3] = {gd.x, gd.y, gd.z}, gas[3] = {ga.x, ga.y, ga.z};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const size_t k = 3 * (size_t)i + c;
+        if (cfg.phase == 1)
+            delta[k] = adam_update(delta[k], gds[c], adam_m + k, adam_v + k, cfg.beta1, cfg.beta2, cfg.eps, adam_sc[0],
+                                   adam_sc[1]);
+        const size_t ka = 3 * (size_t)V + k;
+        albedo[k] = adam_update(albedo[k], gas[c], adam_m + ka, adam_v + ka, cfg.beta1, cfg.beta2, cfg.eps, adam_sc[2],
+                                adam_sc[3]);
+    }
+}
+
+// phase A: Adam on sh_coeffs.  torch.optim.Adam steps the WHOLE [num,9] tensor every iteration (rows of views outside
+// the batch have zero gradient but keep moving on their momentum, mesh_sfs_optim.py:193,205,237), so this runs over
+// every SH row resident on this rank; rows are view-local and never reduced across ranks.
+__global__ void ham_update_sh_kernel(fmhr_ham_config cfg, const float* __restrict__ gsh,
+                                     const float* __restrict__ packed, float* __restrict__ sh_coeffs,
+                                     float* __restrict__ adam_m, float* __restrict__ adam_v,
+                                     const float* __restrict__ adam_sc, float* __restrict__ dbg_grad_sh) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cfg.n_sh_rows * 9) return;
+    const float n_valid = packed[12 * (size_t)cfg.V];
+    const float g = cfg.sfs_weight / (3.0f * n_valid) * gsh[k];
+    if (dbg_grad_sh) dbg_grad_sh[k] = g;
+    const size_t ks = 6 * (size_t)cfg.V + k;
+    sh_coeffs[k] = adam_update(sh_coeffs[k], g, adam_m + ks, adam_v + ks, cfg.beta1, cfg.beta2, cfg.eps, adam_sc[4],
+                               adam_sc[5]);
+}
+
+static int check_cfg(const fmhr_ham_config* c) {
+    FMHR_CHECK_ARG(c != nullptr);
+    FMHR_CHECK_ARG(c->V > 0 && c->T > 0 && c->H > 0 && c->W > 0 && c->n_views > 0 && c->n_views_global >= c->n_views);
+    FMHR_CHECK_ARG(c->phase == 0 || c->phase == 1);
+    FMHR_CHECK_ARG(c->n_sh_rows >= 1);
+    FMHR_CHECK_ARG((long long)c->H * c->W < (1ll << 31));
+    return FMHR_OK;
+}
+
+}  // namespace fmhr
+
+using namespace fmhr;
+
+extern "C" size_t fmhr_ham_workspace_bytes(const fmhr_ham_config* cfg) {
+    if (!cfg || check_cfg(cfg) != FMHR_OK) return 0;
+    return ham_layout(cfg, nullptr, nullptr);
+}
+
+extern "C" size_t fmhr_ham_packed_floats(const fmhr_ham_config* cfg) {
+    if (!cfg || cfg->V <= 0) return 0;
+    return 12 * (size_t)cfg->V + 4;
+}
+
+static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b) {
+    FMHR_CHECK_ARG(b != nullptr);
+    FMHR_CHECK_ARG(b->tri && b->opp && b->v2f_ptr && b->v2f_idx && b->v2v_ptr && b->v2v_idx);
+    FMHR_CHECK_ARG(b->vertices_tmp && b->delta && b->albedo && b->sh_coeffs && b->adam_m && b->adam_v && b->adam_step);
+    FMHR_CHECK_ARG(b->imgs && b->masks && b->valid_masks && b->w2cs && b->projs && b->view_idx);
+    FMHR_CHECK_ARG(b->packed && b->losses && b->workspace);
+    FMHR_CHECK_ARG(b->workspace_bytes >= fmhr_ham_workspace_bytes(cfg));
+    FMHR_CHECK_ARG(((uintptr_t)b->packed & 15) == 0 && ((uintptr_t)b->workspace & 255) == 0);
+    return FMHR_OK;
+}
+
+template <int PHASE>
+static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b, cudaStream_t st, float* dbg_image,
+                           float* dbg_mask, bool forward_only) {
+    HamWs ws;
+    ham_layout(cfg, (char*)b->workspace, &ws);
+    const int V = cfg->V, T = cfg->T, H = cfg->H, W = cfg->W, n = cfg->n_views;
+    const size_t P = (size_t)n * H * W;
+    const int32_t* sh_idx = b->sh_idx ? b->sh_idx : b->view_idx;
+    FMHR_CUDA(cudaMemsetAsync(b->packed, 0, fmhr_ham_packed_floats(cfg) * sizeof(float), st));
+    FMHR_CUDA(cudaMemsetAsync(ws.acc, 0, 8 * sizeof(double), st));
+    FMHR_CUDA(cudaMemsetAsync(ws.zbuf, 0xFF, P * 8, st));
+    if (PHASE == 0) FMHR_CUDA(cudaMemsetAsync(ws.gsh, 0, (size_t)cfg->n_sh_rows * 9 * sizeof(float), st));
+    ham_vertex_prep_kernel<<<cdiv(3 * V, 256), 256, 0, st>>>(b->vertices_tmp, b->delta, 3 * V, ws.vertices);
+    FMHR_LAUNCH_CHECK();
+    int rc = launch_vertex_normals_fwd(ws.vertices, b->tri, b->v2f_ptr, b->v2f_idx, V, ws.normals, ws.raw, st);
+    if (rc) return rc;
+    ham_transform_kernel<<<dim3(cdiv(V, 256), n), 256, 0, st>>>(ws.vertices, b->w2cs, b->projs, b->view_idx, V, ws.pos);
+    FMHR_LAUNCH_CHECK();
+    rc = launch_raster_coverage((const float*)ws.pos, b->tri, n, V, T, H, W, ws.zbuf, st);
+    if (rc) return rc;
+    const dim3 pgrid(cdiv((long long)H * W, 256), n);
+    ham_shade_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, ws.normals, b->albedo, b->masks,
+                                                   b->sh_coeffs, b->view_idx, sh_idx, V, H, W, ws.plane[0],
+                                                   ws.plane[1], ws.acc);
+    FMHR_LAUNCH_CHECK();
+    float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
+    float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
+    ham_aa_loss_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, b->opp, b->imgs, b->valid_masks,
+                                                     b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
+                                                     ws.plane[1], g0, g1, ws.acc, ws.gsh, dbg_image, dbg_mask);
+    FMHR_LAUNCH_CHECK();
+    if (!forward_only) {
+        ham_pixel_bwd_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
+                                                           b->w2cs, b->projs, b->sh_coeffs, b->view_idx, sh_idx, V, T,
+                                                           H, W, ws.plane[0], ws.plane[1], g0, g1, (float4*)b->packed);
+        FMHR_LAUNCH_CHECK();
+    }
+    ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->packed + 12 * (size_t)V);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_step_render(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return cfg->phase == 0 ? ham_render_impl<0>(cfg, buf, st, nullptr, nullptr, false)
+                           : ham_render_impl<1>(cfg, buf, st, nullptr, nullptr, false);
+}
+
+extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    HamWs ws;
+    ham_layout(cfg, (char*)buf->workspace, &ws);
+    const int V = cfg->V;
+    ham_update_pass1_kernel<<<cdiv(V, 128), 128, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
+                                                          buf->v2f_ptr, buf->v2f_idx, buf->v2v_ptr, buf->v2v_idx,
+                                                          ws.raw, buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, ws.acc,
+                                                          buf->adam_step, ws.adam_sc);
+    FMHR_LAUNCH_CHECK();
+    ham_update_pass2_kernel<<<cdiv(V, 128), 128, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
+                                                          buf->v2f_ptr, buf->v2f_idx, buf->v2v_ptr, buf->v2v_idx,
+                                                          buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, buf->adam_m,
+                                                          buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad);
+    FMHR_LAUNCH_CHECK();
+    if (cfg->phase == 0) {
+        ham_update_sh_kernel<<<cdiv(cfg->n_sh_rows * 9, 128), 128, 0, st>>>(*cfg, ws.gsh, buf->packed, buf->sh_coeffs,
+                                                                            buf->adam_m, buf->adam_v, ws.adam_sc,
+                                                                            buf->dbg_grad_sh);
+        FMHR_LAUNCH_CHECK();
+    }
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* pos, float* rast,
+                                     float* image, float* pred_mask, float* normals, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // re-run the forward with export pointers (leaves `packed` holding forward-only partials)
+    rc = cfg->phase == 0 ? ham_render_impl<0>(cfg, buf, st, image, pred_mask, true)
+                         : ham_render_impl<1>(cfg, buf, st, image, pred_mask, true);
+    if (rc) return rc;
+    HamWs ws;
+    ham_layout(cfg, (char*)buf->workspace, &ws);
+    const size_t nV = (size_t)cfg->n_views * cfg->V;
+    if (pos) FMHR_CUDA(cudaMemcpyAsync(pos, ws.pos, nV * 16, cudaMemcpyDeviceToDevice, st));
+    if (normals) FMHR_CUDA(cudaMemcpyAsync(normals, ws.normals, (size_t)cfg->V * 12, cudaMemcpyDeviceToDevice, st));
+    if (rast) {
+        const dim3 pgrid(cdiv((long long)cfg->H * cfg->W, 256), cfg->n_views);
+        ham_export_rast_kernel<<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, buf->tri, cfg->V, cfg->H, cfg->W, (float4*)rast);
+        FMHR_LAUNCH_CHECK();
+    }
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_step_host(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* imgs_host,
+                                  const float* masks_host, const float* valid_masks_host, const float* w2cs_host,
+                                  const float* projs_host, float* losses_host, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(imgs_host && masks_host && valid_masks_host && w2cs_host && projs_host && losses_host);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t hw = (size_t)cfg->H * cfg->W, n = cfg->n_views;
+    // stage this step's batch into rows [0, n_views) of the device view arrays (view_idx must be 0..n_views-1)
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->imgs, imgs_host, n * hw * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->masks, masks_host, n * hw * sizeof(float), cudaMemcpyHostToDevice, st));
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->valid_masks, valid_masks_host, n * hw * sizeof(float), cudaMemcpyHostToDevice, st));
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->w2cs, w2cs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = fmhr_ham_step_render(cfg, buf, stream);
+    if (rc) return rc;
+    rc = fmhr_ham_step_update(cfg, buf, stream);
+    if (rc) return rc;
+    FMHR_CUDA(cudaMemcpyAsync(losses_host, buf->losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return FMHR_OK;
+}

@@ -1,0 +1,202 @@
+"""Native HAM optimiser: the reference's two loops (mesh_sfs_optim.py:193-240 phase A, :242-317 phase B) with every
+iteration executed by two C-ABI calls (fmhr_ham_step_render / fmhr_ham_step_update) and, on more than one GPU, one
+NCCL all-reduce of the packed gradient buffer between them (views shard across ranks).
+
+State names follow the reference: vertices_tmp, delta, albedo [1,V,3], sh_coeffs [num,9], valid_masks, ...
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import HamBuffers, HamConfig, check, ptr, stream
+from .dr import Topology
+
+
+class HamOptimizer:
+    def __init__(self, vertices, faces, imgs, masks, valid_masks, w2cs, projs, sh_coeffs, albedo, conf,
+                 process_group=None, n_views_global=None, debug=False):
+        """All tensors CUDA.  vertices [V,3], faces [F,3] int32, imgs [num,H,W,3], masks/valid_masks [num,H,W],
+        w2cs/projs [num,4,4] (transposed, get_data.py:96-97), sh_coeffs [num,9], albedo [1,V,3] or [V,3];
+        conf: dict with the weights and learning rates of conf/*.conf."""
+        self.lib = _lib.load()
+        _lib.require_cuda(vertices, faces, imgs, masks, valid_masks, w2cs, projs, sh_coeffs, albedo)
+        dev = vertices.device
+        self.device = dev
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        self.vertices_tmp = f32(vertices).clone()
+        self.faces = faces.detach().to(torch.int32).contiguous()
+        self.V, self.T = self.vertices_tmp.shape[0], self.faces.shape[0]
+        self.imgs, self.masks, self.valid_masks = f32(imgs), f32(masks), f32(valid_masks)
+        self.w2cs, self.projs = f32(w2cs), f32(projs)
+        self.num, self.H, self.W = self.imgs.shape[0], self.imgs.shape[1], self.imgs.shape[2]
+        self.sh_coeffs = f32(sh_coeffs).clone()
+        self.albedo = f32(albedo).reshape(self.V, 3).clone()
+        self.delta = torch.zeros_like(self.vertices_tmp)
+        self.conf = dict(conf)
+        self.topo = Topology(self.faces, self.V)
+        # mesh_sfs_optim.py:184-188: mean of squared lengths of the 3F half-edges of the initial mesh
+        v, f = self.vertices_tmp, self.faces.long()
+        a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+        self.edge_length_mean = float(torch.cat([((a - b) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)]).mean())
+        n_state = 6 * self.V + 9 * self.num
+        self.adam_m = torch.zeros(n_state, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(n_state, dtype=torch.float32, device=dev)
+        self.adam_step = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.packed = torch.zeros(12 * self.V + 4, dtype=torch.float32, device=dev)
+        self.losses = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.workspace = None
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.n_views_global_override = n_views_global
+        self.dbg_grad = torch.zeros(self.V, 6, dtype=torch.float32, device=dev) if debug else None
+        self.dbg_grad_sh = None
+        self.debug = debug
+        self.phase = 0
+        self._view_idx_cache = {}
+
+    # ------------------------------------------------------------------ reference-shaped accessors
+    @property
+    def vertices(self):
+        return self.vertices_tmp + self.delta
+
+    def begin_phase_b(self):
+        """mesh_sfs_optim.py:242-244: a fresh Adam over (delta, albedo, sh_coeffs) -> moments and steps restart."""
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+        self.adam_step.zero_()
+        self.phase = 1
+
+    # ------------------------------------------------------------------ plumbing
+    def _cfg(self, n_views, phase, albedo_weight):
+        c = self.conf
+        cfg = HamConfig()
+        cfg.V, cfg.T, cfg.H, cfg.W = self.V, self.T, self.H, self.W
+        cfg.n_views = n_views
+        cfg.n_views_global = self.n_views_global_override or n_views * self.world
+        cfg.phase = phase
+        cfg.n_sh_rows = self.num
+        cfg.sfs_weight, cfg.lap_weight = c["sfs_weight"], c["lap_weight"]
+        cfg.albedo_weight = c["albedo_weight"] if albedo_weight is None else albedo_weight
+        cfg.mask_weight, cfg.edge_weight, cfg.delta_weight = c["mask_weight"], c["edge_weight"], c["delta_weight"]
+        cfg.lr, cfg.albedo_lr, cfg.sh_lr = c["lr"], c["albedo_lr"], c["sh_lr"]
+        cfg.beta1, cfg.beta2, cfg.eps = 0.9, 0.999, 1e-8
+        cfg.edge_length_mean = self.edge_length_mean
+        return cfg
+
+    def _buffers(self, cfg, view_idx, imgs=None, masks=None, valid_masks=None, w2cs=None, projs=None, sh_idx=None):
+        need = self.lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg))
+        if need == 0:
+            raise RuntimeError("fmhr_b200: invalid HAM configuration")
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        b = HamBuffers()
+        t = self.topo
+        b.tri, b.opp = ptr(self.faces), ptr(t.opp)
+        b.v2f_ptr, b.v2f_idx, b.v2v_ptr, b.v2v_idx = ptr(t.v2f_ptr), ptr(t.v2f_idx), ptr(t.v2v_ptr), ptr(t.v2v_idx)
+        b.vertices_tmp, b.delta, b.albedo, b.sh_coeffs = ptr(self.vertices_tmp), ptr(self.delta), ptr(self.albedo), ptr(self.sh_coeffs)
+        b.adam_m, b.adam_v, b.adam_step = ptr(self.adam_m), ptr(self.adam_v), ptr(self.adam_step)
+        b.imgs = ptr(self.imgs if imgs is None else imgs)
+        b.masks = ptr(self.masks if masks is None else masks)
+        b.valid_masks = ptr(self.valid_masks if valid_masks is None else valid_masks)
+        b.w2cs = ptr(self.w2cs if w2cs is None else w2cs)
+        b.projs = ptr(self.projs if projs is None else projs)
+        b.view_idx = ptr(view_idx)
+        b.sh_idx = ptr(sh_idx)
+        b.packed, b.losses = ptr(self.packed), ptr(self.losses)
+        b.workspace, b.workspace_bytes = ptr(self.workspace), self.workspace.numel()
+        b.dbg_grad = ptr(self.dbg_grad)
+        if self.debug and cfg.phase == 0:
+            self.dbg_grad_sh = torch.zeros(self.num, 9, dtype=torch.float32, device=self.device)
+        b.dbg_grad_sh = ptr(self.dbg_grad_sh if (self.debug and cfg.phase == 0) else None)
+        return b
+
+    def _views(self, view_idx):
+        if torch.is_tensor(view_idx):
+            return view_idx.to(device=self.device, dtype=torch.int32).contiguous()
+        key = tuple(int(i) for i in view_idx)
+        t = self._view_idx_cache.get(key)
+        if t is None:
+            t = torch.tensor(key, dtype=torch.int32, device=self.device)
+            if len(self._view_idx_cache) < 64:
+                self._view_idx_cache[key] = t
+        return t
+
+    def _step(self, phase, view_idx, albedo_weight=None):
+        vi = self._views(view_idx)
+        cfg = self._cfg(vi.numel(), phase, albedo_weight)
+        buf = self._buffers(cfg, vi)
+        with torch.cuda.device(self.device):
+            check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), stream()), "ham_step_render")
+            if self.world > 1:
+                torch.distributed.all_reduce(self.packed, group=self.pg)  # one NCCL sum per iteration
+            check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), stream()), "ham_step_update")
+        return self.losses
+
+    # ------------------------------------------------------------------ the two loops' bodies
+    def step_phase_a(self, view_idx):
+        """One iteration of mesh_sfs_optim.py:198-237 (albedo + SH warm-up).  Returns the device loss record
+        [sfs, 0, albedo(display), 0, 0, 0, n_valid, total]; no host sync."""
+        return self._step(0, view_idx)
+
+    def step_phase_b(self, view_idx, albedo_weight=None):
+        """One iteration of mesh_sfs_optim.py:253-310.  Returns the device loss record
+        [sfs, lap, albedo, mask, edge, delta, n_valid, total]; no host sync."""
+        if self.phase != 1:
+            self.begin_phase_b()
+        return self._step(1, view_idx, albedo_weight)
+
+    def export(self, view_idx, phase=1):
+        """Forward-only inspection of the fused path (parity tests): pos, rast, antialiased image, antialiased
+        coverage, vertex normals."""
+        vi = self._views(view_idx)
+        n = vi.numel()
+        cfg = self._cfg(n, phase, None)
+        buf = self._buffers(cfg, vi)
+        dev = self.device
+        pos = torch.empty(n, self.V, 4, dtype=torch.float32, device=dev)
+        rast = torch.empty(n, self.H, self.W, 4, dtype=torch.float32, device=dev)
+        image = torch.zeros(n, self.H, self.W, 3, dtype=torch.float32, device=dev)
+        pmask = torch.zeros(n, self.H, self.W, dtype=torch.float32, device=dev)
+        normals = torch.empty(self.V, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.fmhr_ham_debug_export(ctypes.byref(cfg), ctypes.byref(buf), ptr(pos), ptr(rast), ptr(image),
+                                                 ptr(pmask), ptr(normals), stream()), "ham_debug_export")
+        return dict(pos=pos, rast=rast, image=image, pred_mask=pmask, normals=normals)
+
+
+class HostStreamingStepper:
+    """End-to-end variant used by bench.py's `e2e` leg: the step's view batch lives in PINNED HOST memory and is copied
+    to the device inside the call (fmhr_ham_step_host), and the 8-float loss record is copied back."""
+
+    def __init__(self, opt, n_views):
+        self.opt = opt
+        self.n = n_views
+        dev = opt.device
+        H, W = opt.H, opt.W
+        self.d_imgs = torch.empty(n_views, H, W, 3, dtype=torch.float32, device=dev)
+        self.d_masks = torch.empty(n_views, H, W, dtype=torch.float32, device=dev)
+        self.d_valid = torch.empty(n_views, H, W, dtype=torch.float32, device=dev)
+        self.d_w2cs = torch.empty(n_views, 4, 4, dtype=torch.float32, device=dev)
+        self.d_projs = torch.empty(n_views, 4, 4, dtype=torch.float32, device=dev)
+        self.rows = torch.arange(n_views, dtype=torch.int32, device=dev)
+        self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = 4 * (n_views * H * W * 5 + n_views * 32)
+        self.d2h_bytes = 32
+
+    def step_phase_b(self, h_imgs, h_masks, h_valid, h_w2cs, h_projs, sh_rows, albedo_weight=None):
+        """h_* are pinned host tensors holding this step's n_views rows; sh_rows = int32 device tensor of SH rows."""
+        o = self.opt
+        if o.phase != 1:
+            o.begin_phase_b()
+        cfg = o._cfg(self.n, 1, albedo_weight)
+        buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows)
+        if o.world > 1:
+            raise RuntimeError("HostStreamingStepper is single-process; use HamOptimizer under torch.distributed")
+        with torch.cuda.device(o.device):
+            check(o.lib.fmhr_ham_step_host(ctypes.byref(cfg), ctypes.byref(buf), ptr(h_imgs), ptr(h_masks), ptr(h_valid),
+                                           ptr(h_w2cs), ptr(h_projs), ptr(self.losses_host), stream()), "ham_step_host")
+        return self.losses_host

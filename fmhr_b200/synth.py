@@ -250,6 +250,9 @@ WORKLOADS = {
     "stress_128x2048x2048": dict(n=128, H=2048, W=2048, subdiv=4, hands=1, conf="ih_sfs"),
     "tiny": dict(n=4, H=96, W=80, subdiv=1, hands=1, conf="ih_sfs"),
     "small": dict(n=6, H=160, W=128, subdiv=2, hands=1, conf="ih_sfs"),
+    # triangles larger than a pixel: the regime where antialias finds silhouette edges (it only inspects the edges
+    # of the triangle visible in the pixel, so micropolygon meshes rarely blend)
+    "coarse": dict(n=4, H=288, W=240, subdiv=0, hands=1, conf="demo_sfs"),
 }
 
 
@@ -274,8 +277,10 @@ def build_scene(workload, render_fn, n_views=None, view_offset=0, view_stride=1)
     alb_true = smooth_albedo(verts.shape[0], faces)
     img, cov, _ = render_fn(target_verts, faces, alb_true, sh_true, w2cs, projs, H, W)
     _, _, valid_mask = render_fn(verts, faces, alb_true, sh_true, w2cs, projs, H, W)
-    # initial state as after the reference's init (mesh_sfs_optim.py:124-188): mean albedo, fitted SH (here: truth + noise)
-    alb0 = np.broadcast_to(alb_true.mean(0, keepdims=True), alb_true.shape).copy()
+    # initial state as after the reference's init + phase A (mesh_sfs_optim.py:124-240): near-mean albedo, fitted SH
+    # (not exactly constant: on a constant albedo the uniform Laplacian is pure rounding noise and its
+    #  sub-gradient direction is undefined, in the reference as well; phase A leaves it non-constant)
+    alb0 = (0.7 * alb_true.mean(0, keepdims=True) + 0.3 * alb_true).astype(np.float32)
     sh0 = (sh_true + np.random.default_rng(4).normal(0, 0.01, sh_true.shape)).astype(np.float32)
     conf = dict(CONF[wl["conf"]])
     return dict(vertices=verts, faces=faces, w2cs=w2cs, projs=projs, imgs=img, masks=cov, valid_masks=valid_mask,

@@ -1,0 +1,192 @@
+/* fmhr_b200 — C ABI of the B200-native HAM inverse-rendering hot path.
+ *
+ * Drop-in boundary for the path BASELINE.json's north_star names: the rasterize / interpolate /
+ * antialias operators that /root/reference calls through `nvdiffrast.torch`
+ * (mesh_sfs_optim.py:14,120,142-147,212-219,267-287; train_mlp.py:178,184; get_data.py:246-253)
+ * plus the fused kernels of the HAM iteration itself (mesh_sfs_optim.py:198-237 phase A,
+ * :253-310 phase B; models/utils.py:188-226,508-548,661-722).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - fp32 data, int32 indices, row-major / channel-last layouts exactly as the reference's tensors;
+ *  - the caller allocates every output and every workspace (sizes from the *_workspace_bytes queries);
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the
+ *    device or allocates memory, except the *_build setup calls, which say so;
+ *  - return value 0 = success, otherwise a negative FMHR_E* code; the message is available from
+ *    fmhr_last_error_string() (thread-local).  No C++ exception crosses this boundary.
+ */
+#ifndef FMHR_B200_H
+#define FMHR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMHR_OK 0
+#define FMHR_EINVAL (-1)    /* bad argument (null pointer, non-positive size, too-small workspace) */
+#define FMHR_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed */
+#define FMHR_EUNSUPPORTED (-3)
+
+typedef void* fmhr_stream_t;
+
+int fmhr_version(void);
+const char* fmhr_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * dr.rasterize(glctx, pos, tri, resolution)          [mesh_sfs_optim.py:142,212,267]
+ *   pos  [N,V,4] clip-space positions (instanced mode), tri [T,3]
+ *   rast [N,H,W,4] = (u, v, z/w, triangle_id+1), 0 where empty;  rast_db [N,H,W,4] or NULL
+ * Deterministic coverage rule (DESIGN.md "Rasterisation rule"): 1/256-pixel snapping, 64-bit integer
+ * edge functions, top-left style tie-break, 64-bit atomicMin z-buffer keyed (depth, triangle id).
+ * workspace: N*H*W*8 bytes (the z-buffer).
+ * ------------------------------------------------------------------------------------------- */
+size_t fmhr_rasterize_workspace_bytes(int N, int H, int W);
+int fmhr_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
+                       float* rast, float* rast_db, void* workspace, size_t workspace_bytes, fmhr_stream_t stream);
+/* grad_pos [N,V,4] is overwritten with d(sum dy.rast)/d(pos); only the u,v channels of dy carry gradient. */
+int fmhr_rasterize_bwd(const float* pos, const int32_t* tri, const float* rast, const float* dy,
+                       int N, int V, int T, int H, int W, float* grad_pos, fmhr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * dr.interpolate(attr, rast, tri)                    [mesh_sfs_optim.py:143,214,269; train_mlp.py:184]
+ *   attr [NA,V,A] with NA == N, or NA == 1 to broadcast one attribute set to all N images
+ *   out  [N,H,W,A] = u*a0 + v*a1 + (1-u-v)*a2, 0 where empty
+ * bwd overwrites grad_attr [NA,V,A] and grad_rast [N,H,W,4] (channels 2,3 are zero).
+ * ------------------------------------------------------------------------------------------- */
+int fmhr_interpolate_fwd(const float* attr, const float* rast, const int32_t* tri, int N, int NA, int V, int T,
+                         int H, int W, int A, float* out, fmhr_stream_t stream);
+int fmhr_interpolate_bwd(const float* attr, const float* rast, const int32_t* tri, const float* dy, int N, int NA,
+                         int V, int T, int H, int W, int A, float* grad_attr, float* grad_rast, fmhr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mesh topology (setup; once per `tri` tensor).  Replaces nvdiffrast's per-call topology hash
+ * (antialias(..., topology_hash=None)) and the per-call sparse-Laplacian rebuild of
+ * models/utils.py:551-571,661-693.
+ *   opp      [T,3]  vertex opposite to the edge facing corner k in the lowest-indexed other triangle on
+ *                   that edge, -1 on a boundary
+ *   v2f_ptr  [V+1], v2f_idx [3T]   vertex -> incident (triangle*4 + corner), ascending
+ *   v2v_ptr  [V+1], v2v_idx [6T]   vertex -> unique neighbour vertices, ascending (first v2v_ptr[V] used)
+ * This call synchronises `stream` once (it returns the directed-edge count through n_dir_edges_host).
+ * Any of the three groups may be NULL to skip it.
+ * ------------------------------------------------------------------------------------------- */
+size_t fmhr_mesh_topology_workspace_bytes(int V, int T);
+int fmhr_mesh_topology_build(const int32_t* tri, int V, int T, int32_t* opp, int32_t* v2f_ptr, int32_t* v2f_idx,
+                             int32_t* v2v_ptr, int32_t* v2v_idx, int* n_dir_edges_host, void* workspace,
+                             size_t workspace_bytes, fmhr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * dr.antialias(color, rast, pos, tri)                [mesh_sfs_optim.py:146-147,217-219,274,287]
+ *   color [N,H,W,C], rast [N,H,W,4], pos [N,V,4], tri [T,3], opp [T,3] from fmhr_mesh_topology_build
+ * bwd overwrites grad_color [N,H,W,C] and grad_pos [N,V,4] (grad_pos may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int fmhr_antialias_fwd(const float* color, const float* rast, const float* pos, const int32_t* tri,
+                       const int32_t* opp, int N, int H, int W, int C, int V, int T, float* out, fmhr_stream_t stream);
+int fmhr_antialias_bwd(const float* color, const float* rast, const float* pos, const int32_t* tri,
+                       const int32_t* opp, const float* dy, int N, int H, int W, int C, int V, int T,
+                       float* grad_color, float* grad_pos, fmhr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * models/utils.py operators used by the loop, stand-alone (autograd.Function building blocks).
+ * ------------------------------------------------------------------------------------------- */
+/* get_normals (models/utils.py:508-548): normals [V,3] = normalize(sum of incident face cross products, eps 1e-6);
+ * raw [V,3] receives the un-normalised sums (needed by the backward).  One copy, not n. */
+int fmhr_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
+                            int V, int T, float* normals, float* raw, fmhr_stream_t stream);
+/* grad_verts [V,3] overwritten; scratch [V,3] floats. */
+int fmhr_vertex_normals_bwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
+                            const float* raw, const float* grad_normals, int V, int T, float* scratch,
+                            float* grad_verts, fmhr_stream_t stream);
+/* laplacian_smoothing(x, faces, "uniform") (models/utils.py:696-722): *loss = sum_i ||(Lx)_i|| / V.
+ * yhat [V,C] receives (Lx)_i/||(Lx)_i|| (0 where the norm is 0) for the backward; C in {1..4}. */
+int fmhr_laplacian_fwd(const float* x, const int32_t* v2v_ptr, const int32_t* v2v_idx, int V, int C, float* yhat,
+                       float* loss, fmhr_stream_t stream);
+/* grad_x [V,C] overwritten with scale * L^T yhat / V. */
+int fmhr_laplacian_bwd(const float* yhat, const int32_t* v2v_ptr, const int32_t* v2v_idx, int V, int C, float scale,
+                       float* grad_x, fmhr_stream_t stream);
+/* get_radiance (models/utils.py:208-226), degree 3: radiance[i] = coeff[i or 0] . basis(normal[i]). */
+int fmhr_sh_radiance_fwd(const float* coeff, int coeff_rows, const float* normal, int n, float* radiance,
+                         fmhr_stream_t stream);
+int fmhr_sh_radiance_bwd(const float* coeff, int coeff_rows, const float* normal, const float* grad_radiance, int n,
+                         float* grad_coeff, float* grad_normal, fmhr_stream_t stream);
+/* NCC (models/ncc_utils.py:4-35): ref [1,Np,Npx], src/mask [Nv,Np,Npx] -> ncc [Nv,Np]. */
+int fmhr_ncc_fwd(const float* ref, const float* src, const float* src_mask, int Nv, int Np, int Npx, float* ncc,
+                 fmhr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused HAM iteration (mesh_sfs_optim.py:198-237 phase A, :253-310 phase B).
+ * The context owns nothing: every buffer below is caller memory; `workspace` holds the z-buffer, the
+ * shaded-colour and pixel-gradient planes and the per-vertex gradient accumulators.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fmhr_ham_config {
+    int32_t V, T, H, W;
+    int32_t n_views;          /* views in this step's batch on THIS rank */
+    int32_t n_views_global;   /* views in the step's batch over all ranks (mask-loss denominator) */
+    int32_t phase;            /* 0 = phase A (albedo + SH), 1 = phase B (delta + albedo) */
+    int32_t n_sh_rows;        /* rows of sh_coeffs resident on this rank (= its number of views) */
+    float sfs_weight, lap_weight, albedo_weight, mask_weight, edge_weight, delta_weight;
+    float lr, albedo_lr, sh_lr;
+    float beta1, beta2, eps;
+    float edge_length_mean;   /* mesh_sfs_optim.py:188 */
+} fmhr_ham_config;
+
+typedef struct fmhr_ham_buffers {
+    /* mesh + topology (static) */
+    const int32_t* tri;       /* [T,3] */
+    const int32_t* opp;       /* [T,3] */
+    const int32_t* v2f_ptr;   /* [V+1] */
+    const int32_t* v2f_idx;   /* [3T] */
+    const int32_t* v2v_ptr;   /* [V+1] */
+    const int32_t* v2v_idx;   /* [2E] */
+    /* optimisation state */
+    const float* vertices_tmp; /* [V,3] */
+    float* delta;              /* [V,3] */
+    float* albedo;             /* [V,3] */
+    float* sh_coeffs;          /* [n_sh_rows,9] */
+    float* adam_m;             /* [6V + 9*n_sh_rows]  (delta | albedo | sh) */
+    float* adam_v;             /* same layout */
+    int32_t* adam_step;        /* [3] step counters (delta, albedo, sh) */
+    /* per-view data of all views resident on this rank */
+    const float* imgs;         /* [num,H,W,3] */
+    const float* masks;        /* [num,H,W] */
+    const float* valid_masks;  /* [num,H,W] */
+    const float* w2cs;         /* [num,4,4] transposed (row-vector) */
+    const float* projs;        /* [num,4,4] transposed */
+    const int32_t* view_idx;   /* [n_views] rows of the per-view arrays used by this step (the perm slice) */
+    const int32_t* sh_idx;     /* [n_views] rows of sh_coeffs for those views; NULL = same as view_idx */
+    /* packed reduction buffer: [12V gradient accumulators | 16 scalars]; all-reduced (sum) across ranks
+     * between fmhr_ham_step_render and fmhr_ham_step_update when world size > 1 */
+    float* packed;
+    /* loss record written by fmhr_ham_step_update: sfs, lap, albedo, mask, edge, delta, n_valid, total */
+    float* losses;             /* [8] */
+    void* workspace;
+    size_t workspace_bytes;
+    /* optional inspection outputs for parity tests (NULL in production): the gradients Adam consumed */
+    float* dbg_grad;           /* [V,6] = (d loss/d delta xyz, d loss/d albedo bgr) */
+    float* dbg_grad_sh;        /* [n_sh_rows,9] (phase A) */
+} fmhr_ham_buffers;
+
+size_t fmhr_ham_workspace_bytes(const fmhr_ham_config* cfg);
+size_t fmhr_ham_packed_floats(const fmhr_ham_config* cfg);
+/* forward + pixel backward: fills `packed` with un-normalised gradient accumulators and loss partials. */
+int fmhr_ham_step_render(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
+/* normalises with the (all-reduced) counts, adds the regulariser gradients, applies Adam, writes `losses`. */
+int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
+/* Inspection for parity tests: copies internal planes of the last fmhr_ham_step_render into caller buffers
+ * (any may be NULL): pos [n,V,4], rast [n,H,W,4], image [n,H,W,3] (antialiased), pred_mask [n,H,W],
+ * normals [V,3]. */
+int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* pos, float* rast,
+                          float* image, float* pred_mask, float* normals, fmhr_stream_t stream);
+/* Host-buffer variant (end-to-end measurement path): copies this step's view batch (img/mask/valid_mask/w2c/proj
+ * rows, all HOST pinned pointers, n_views rows each) into the device staging planes named by `buf`, runs
+ * render+update, and copies the 8-float loss record back to losses_host. */
+int fmhr_ham_step_host(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* imgs_host,
+                       const float* masks_host, const float* valid_masks_host, const float* w2cs_host,
+                       const float* projs_host, float* losses_host, fmhr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMHR_B200_H */

@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — HAM iterations/sec (fwd + bwd + Adam) on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one phase-B HAM iteration (mesh_sfs_optim.py:253-310) over ALL views of the workload in one batch
+(SURVEY.md 8d).  Default workload = BASELINE.json configs[1]: InterHand-shaped 48 views x 512x334, 3x-subdivided
+single hand (49,281 verts / 98,432 faces), conf/ih_sfs.conf weights.  Multi-GPU is weak scaling: every rank holds the
+workload's view set (its own seeded camera ring), the global batch is N x 48 views, vertex / albedo gradients are
+summed with one NCCL all-reduce per iteration and `value` counts 48-view iteration equivalents per second.
+
+Prints ONE JSON line (see the contract in the task description): value (device-resident inputs, CUDA-event timed),
+e2e (host buffers, H2D + D2H inside the timed region), roofline (dominant kernel, measured live), cpu_baseline
+(the oracle = restated reference loop on the host cores), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "HAM iters/sec (fwd+bwd, views x res)"
+UNIT = "iters/s"
+KERNELS_PER_STEP = 10  # prep, normals, transform, coverage, shade, antialias_loss, pixel_backward, finalize, update x2
+
+
+def b_alg_bytes(n, H, W, V, F, E):
+    """Algorithmic bytes of one iteration, SURVEY.md 8(d) / BASELINE.md section 3."""
+    P = n * H * W
+    return 68 * P + 204 * V + 12 * F + 8 * (2 * E + V) + 4 * (V + 1) + 164 * n
+
+
+# Algorithmic HBM bytes per launch of each fused kernel (DESIGN.md "Kernels"): per pixel P, per vertex V, per view n
+def stage_bytes(stage, n, H, W, V, F):
+    P = n * H * W
+    return {
+        "clears": 8 * P,                                   # z-buffer reset
+        "vertex_normals": 36 * V + 12 * F + 24 * V,        # read vtmp, delta, faces; write vertices, normals
+        "clip_transform": 12 * V + 16 * n * V,             # write [n,V,4]
+        "coverage": 16 * n * V + 12 * F,                   # read clip positions + faces (atomics hit L2)
+        "shade": 8 * P + 4 * P + 16 * P,                   # read z-buffer + mask, write colour plane
+        "antialias_loss": 8 * P + 16 * P + 12 * P + 4 * P + 16 * P,  # zbuf, colour, img, valid_mask, write pixel grads
+        "pixel_backward": 8 * P + 16 * P + 16 * P,         # zbuf, colour, pixel grads (vertex atomics hit L2)
+        "update_adam": 204 * V + 12 * F,
+    }[stage]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                clk, mxc = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for nme, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+        if not sm:
+            sm = [float(l.split(",")[0]) for _, l in self.rows[-3:] if l.split(",")[0].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_step_rate(scene, steps, warmup, threads):
+    """Times the oracle (restated reference loop, PyTorch-CPU + C++ reference rasteriser) on the host cores."""
+    import torch
+    from oracle import ham as oham
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    st = oham.HamState(scene)
+    views = list(range(scene["imgs"].shape[0]))
+    for _ in range(warmup):
+        oham.phase_b_step(st, views)
+    t = time.time()
+    for _ in range(steps):
+        oham.phase_b_step(st, views)
+    return steps / (time.time() - t)
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path = the oracle port (nvdiffrast has no
+    CPU build and is not vendored, so rasterize/interpolate/antialias are the plain C++ reference rasteriser)."""
+    if rank != 0:
+        return
+    warnings.filterwarnings("ignore")
+    from fmhr_b200 import synth
+    from oracle import ham as oham
+    from oracle import raster as oraster
+    oraster.build()
+    threads = os.cpu_count() or 1
+    wl = dict(synth.WORKLOADS[args.workload])
+    scene = synth.build_scene(wl, oham.render_views)
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate = cpu_reference_step_rate(scene, steps, warm, threads)
+    sample = "full workload, %d timed iteration(s) after %d warm-up" % (steps, warm)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1000.0 / rate, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "views": wl["n"], "H": wl["H"], "W": wl["W"],
+                   "verts": int(scene["vertices"].shape[0]), "faces": int(scene["faces"].shape[0])},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="interhand_48x512x334")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    warnings.filterwarnings("ignore")
+    import torch
+    import torch.distributed as dist
+    from fmhr_b200 import _lib, synth
+    from fmhr_b200.ham import HamOptimizer, HostStreamingStepper
+    from fmhr_b200.render import render_views
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = dict(synth.WORKLOADS[args.workload])
+    scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), camera_seed=1 + rank)
+    n, H, W = scene["imgs"].shape[0], scene["H"], scene["W"]
+    c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt, device=dev)
+    opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
+                       c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs)
+    V, F = opt.V, opt.T
+    E = opt.topo.n_dir_edges // 2
+    views = torch.arange(n, dtype=torch.int32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident throughput
+    for _ in range(args.warmup):
+        opt.step_phase_b(views)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        opt.step_phase_b(views)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * 1000.0 / ms_per_step  # 48-view iteration equivalents per second over all ranks
+    losses = opt.losses.cpu().tolist()
+
+    # ---------------------------------------------------------------- end to end (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda k: torch.tensor(scene[k], dtype=torch.float32).contiguous().pin_memory()
+        h_imgs, h_masks, h_valid, h_w2cs, h_projs = pin("imgs"), pin("masks"), pin("valid_masks"), pin("w2cs"), pin("projs")
+        stepper = HostStreamingStepper(opt, n)
+        k_e2e = max(3, min(args.steps, 30))
+
+        def e2e_step():
+            if world == 1:
+                stepper.step_phase_b(h_imgs, h_masks, h_valid, h_w2cs, h_projs, views)
+                torch.cuda.current_stream().synchronize()   # the loss record is now readable on the host
+                return stepper.losses_host
+            stepper.d_imgs.copy_(h_imgs, non_blocking=True)
+            stepper.d_masks.copy_(h_masks, non_blocking=True)
+            stepper.d_valid.copy_(h_valid, non_blocking=True)
+            stepper.d_w2cs.copy_(h_w2cs, non_blocking=True)
+            stepper.d_projs.copy_(h_projs, non_blocking=True)
+            opt.imgs, opt.masks, opt.valid_masks, opt.w2cs, opt.projs = (stepper.d_imgs, stepper.d_masks, stepper.d_valid,
+                                                                          stepper.d_w2cs, stepper.d_projs)
+            return opt.step_phase_b(views).cpu()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(k_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * 1000.0 * k_e2e / float(ms2.item()), "unit": UNIT, "steps": k_e2e,
+               "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0, N=1 timing)
+    peak, peak_src = measured_peak_gbs()
+    roof = None
+    stages = None
+    if world == 1:
+        stages = opt.stage_times(views, repeats=10)
+        top = max(stages, key=lambda k: stages[k])
+        byts = stage_bytes(top, n, H, W, V, F)
+        ach = byts / (stages[top] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "algorithmic_bytes": byts, "kernel_ms": stages[top], "peak_source": peak_src,
+                "stage_ms": stages}
+    balg = b_alg_bytes(n, H, W, V, F, E)
+    iter_ach = balg / (ms_per_step * 1e-3) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import raster as oraster
+        oraster.build()
+        threads = os.cpu_count() or 1
+        rate = cpu_reference_step_rate(scene, 1, 1, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "full workload (%d views), 1 timed iteration after 1 warm-up" % n}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "views_per_gpu": n, "global_views": n * world, "H": H, "W": W, "verts": V,
+                   "faces": F, "phase": "B (delta+albedo, conf/ih_sfs.conf weights)",
+                   "launch": "eager" if args.no_graphs else "cuda-graph replay",
+                   "l2": "per-iteration working set %.0f MB > 126 MB L2 (no flush needed)" % (
+                       (8 + 32 + 20) * n * H * W / 1e6),
+                   "parallelism": "views x%d (weak), 1 NCCL all-reduce/iter" % world if world > 1 else "single GPU"},
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "clocks": clocks,
+        "e2e": e2e,
+        "roofline": roof,
+        "roofline_iteration": {"algorithmic_bytes": balg, "achieved": iter_ach, "peak": peak, "unit": "GB/s",
+                               "frac": iter_ach / peak, "note": "SURVEY.md 8(d) B_alg / t_iter (north-star figure)"},
+        "cpu_baseline": cpu,
+        "losses_last": {k: v for k, v in zip(["sfs", "lap", "albedo", "mask", "edge", "delta", "n_valid", "total"], losses)},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,8 @@ _SIGS = {
     "fmhr_ham_packed_floats": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_step_render": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
     "fmhr_ham_step_update": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
+    "fmhr_ham_stage_times": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), ctypes.POINTER(c_f),
+                                   ctypes.POINTER(c_i), c_p]),
     "fmhr_ham_debug_export": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p]),
     "fmhr_ham_step_host": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
 }

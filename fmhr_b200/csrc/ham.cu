@@ -36,6 +36,17 @@ struct HamWs {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Optional per-kernel timing (fmhr_ham_stage_times): events recorded on the launching stream between launches.
+constexpr int kMaxStages = 16;
+struct StageTimer {
+    cudaEvent_t ev[kMaxStages + 1];
+    int n = 0;
+    cudaStream_t st;
+    void mark() { if (n <= kMaxStages) cudaEventRecord(ev[n++], st); }
+};
+static thread_local StageTimer* g_timer = nullptr;
+#define FMHR_STAGE_MARK() do { if (g_timer) g_timer->mark(); } while (0)
+
 static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     const size_t P = (size_t)c->n_views * c->H * c->W, V = (size_t)c->V;
     size_t off = 0;
@@ -809,25 +820,31 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     FMHR_CUDA(cudaMemsetAsync(ws.acc, 0, 8 * sizeof(double), st));
     FMHR_CUDA(cudaMemsetAsync(ws.zbuf, 0xFF, P * 8, st));
     if (PHASE == 0) FMHR_CUDA(cudaMemsetAsync(ws.gsh, 0, (size_t)cfg->n_sh_rows * 9 * sizeof(float), st));
+    FMHR_STAGE_MARK();  // 0: clears
     ham_vertex_prep_kernel<<<cdiv(3 * V, 256), 256, 0, st>>>(b->vertices_tmp, b->delta, 3 * V, ws.vertices);
     FMHR_LAUNCH_CHECK();
     int rc = launch_vertex_normals_fwd(ws.vertices, b->tri, b->v2f_ptr, b->v2f_idx, V, ws.normals, ws.raw, st);
     if (rc) return rc;
+    FMHR_STAGE_MARK();  // 1: vertex prep + normals
     ham_transform_kernel<<<dim3(cdiv(V, 256), n), 256, 0, st>>>(ws.vertices, b->w2cs, b->projs, b->view_idx, V, ws.pos);
     FMHR_LAUNCH_CHECK();
+    FMHR_STAGE_MARK();  // 2: transform
     rc = launch_raster_coverage((const float*)ws.pos, b->tri, n, V, T, H, W, ws.zbuf, st);
     if (rc) return rc;
+    FMHR_STAGE_MARK();  // 3: coverage
     const dim3 pgrid(cdiv((long long)H * W, 256), n);
     ham_shade_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, ws.normals, b->albedo, b->masks,
                                                    b->sh_coeffs, b->view_idx, sh_idx, V, H, W, ws.plane[0],
                                                    ws.plane[1], ws.acc);
     FMHR_LAUNCH_CHECK();
+    FMHR_STAGE_MARK();  // 4: shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
     ham_aa_loss_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, b->opp, b->imgs, b->valid_masks,
                                                      b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
                                                      ws.plane[1], g0, g1, ws.acc, ws.gsh, dbg_image, dbg_mask);
     FMHR_LAUNCH_CHECK();
+    FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
         ham_pixel_bwd_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
                                                            b->w2cs, b->projs, b->sh_coeffs, b->view_idx, sh_idx, V, T,
@@ -836,6 +853,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     }
     ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->packed + 12 * (size_t)V);
     FMHR_LAUNCH_CHECK();
+    FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
     return FMHR_OK;
 }
 
@@ -868,6 +886,7 @@ extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_b
                                                           buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, buf->adam_m,
                                                           buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad);
     FMHR_LAUNCH_CHECK();
+    FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)
     if (cfg->phase == 0) {
         ham_update_sh_kernel<<<cdiv(cfg->n_sh_rows * 9, 128), 128, 0, st>>>(*cfg, ws.gsh, buf->packed, buf->sh_coeffs,
                                                                             buf->adam_m, buf->adam_v, ws.adam_sc,
@@ -875,6 +894,30 @@ extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_b
         FMHR_LAUNCH_CHECK();
     }
     return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_stage_times(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* ms_host,
+                                    int* n_stages_host, fmhr_stream_t stream) {
+    FMHR_CHECK_ARG(ms_host && n_stages_host);
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm;
+    tm.st = st;
+    for (int i = 0; i <= kMaxStages; i++) FMHR_CUDA(cudaEventCreate(&tm.ev[i]));
+    tm.mark();
+    g_timer = &tm;
+    int rc = fmhr_ham_step_render(cfg, buf, stream);
+    if (rc == FMHR_OK) rc = fmhr_ham_step_update(cfg, buf, stream);
+    g_timer = nullptr;
+    if (rc == FMHR_OK) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("fmhr_ham_stage_times: %s", cudaGetErrorString(e)); rc = FMHR_ECUDA; }
+    }
+    if (rc == FMHR_OK) {
+        *n_stages_host = tm.n - 1;
+        for (int i = 0; i + 1 < tm.n; i++) cudaEventElapsedTime(&ms_host[i], tm.ev[i], tm.ev[i + 1]);
+    }
+    for (int i = 0; i <= kMaxStages; i++) cudaEventDestroy(tm.ev[i]);
+    return rc;
 }
 
 extern "C" int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* pos, float* rast,

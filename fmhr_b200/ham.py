@@ -15,7 +15,7 @@ from .dr import Topology
 
 class HamOptimizer:
     def __init__(self, vertices, faces, imgs, masks, valid_masks, w2cs, projs, sh_coeffs, albedo, conf,
-                 process_group=None, n_views_global=None, debug=False):
+                 process_group=None, n_views_global=None, debug=False, use_graphs=False):
         """All tensors CUDA.  vertices [V,3], faces [F,3] int32, imgs [num,H,W,3], masks/valid_masks [num,H,W],
         w2cs/projs [num,4,4] (transposed, get_data.py:96-97), sh_coeffs [num,9], albedo [1,V,3] or [V,3];
         conf: dict with the weights and learning rates of conf/*.conf."""
@@ -56,6 +56,9 @@ class HamOptimizer:
         self.debug = debug
         self.phase = 0
         self._view_idx_cache = {}
+        self.use_graphs = bool(use_graphs) and not debug
+        self._graphs = {}
+        self._struct_cache = {}
 
     # ------------------------------------------------------------------ reference-shaped accessors
     @property
@@ -92,6 +95,7 @@ class HamOptimizer:
             raise RuntimeError("fmhr_b200: invalid HAM configuration")
         if self.workspace is None or self.workspace.numel() < need:
             self.workspace = None
+            self._graphs = {}
             self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         b = HamBuffers()
         t = self.topo
@@ -126,14 +130,82 @@ class HamOptimizer:
         return t
 
     def _step(self, phase, view_idx, albedo_weight=None):
+        if self.use_graphs:
+            return self._step_graph(phase, view_idx, albedo_weight)
         vi = self._views(view_idx)
-        cfg = self._cfg(vi.numel(), phase, albedo_weight)
-        buf = self._buffers(cfg, vi)
-        with torch.cuda.device(self.device):
-            check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), stream()), "ham_step_render")
-            if self.world > 1:
-                torch.distributed.all_reduce(self.packed, group=self.pg)  # one NCCL sum per iteration
-            check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), stream()), "ham_step_update")
+        key = (phase, vi.data_ptr(), vi.numel(), albedo_weight)
+        cb = self._struct_cache.get(key)
+        if cb is None or cb[2] != (self.workspace.data_ptr() if self.workspace is not None else 0):
+            cfg = self._cfg(vi.numel(), phase, albedo_weight)
+            buf = self._buffers(cfg, vi)
+            cb = (cfg, buf, self.workspace.data_ptr(), vi)
+            if len(self._struct_cache) > 256:
+                self._struct_cache.clear()
+            self._struct_cache[key] = cb
+        cfg, buf = cb[0], cb[1]
+        if torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)
+        sp = stream()
+        check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_render")
+        if self.world > 1:
+            torch.distributed.all_reduce(self.packed, group=self.pg)  # one NCCL sum per iteration
+        check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_update")
+        return self.losses
+
+    def _step_graph(self, phase, view_idx, albedo_weight):
+        """CUDA-graph replay of the iteration: the ~14 launches + memsets of render/update are captured once per
+        (phase, batch size, albedo_weight) and replayed with one launch; the step's view indices are copied into a
+        persistent device buffer the captured kernels read.  With more than one rank the NCCL all-reduce runs eagerly
+        between the two captured halves."""
+        n = view_idx.numel() if torch.is_tensor(view_idx) else len(view_idx)
+        key = (phase, n, None if albedo_weight is None else float(albedo_weight))
+        g = self._graphs.get(key)
+        if g is None:
+            slot = torch.zeros(n, dtype=torch.int32, device=self.device)
+            cfg = self._cfg(n, phase, albedo_weight)
+            buf = self._buffers(cfg, slot)
+            ws_ptr = self.workspace.data_ptr()
+            slot.copy_(self._views(view_idx))
+            # state touched by a trial run is restored so that capture does not advance the optimiser
+            saved = [t.clone() for t in (self.delta, self.albedo, self.sh_coeffs, self.adam_m, self.adam_v, self.adam_step)]
+            torch.cuda.synchronize(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            graphs = []
+            with torch.cuda.stream(side):
+                sp = _lib.c_p(side.cuda_stream)
+                for fn, name in ((self.lib.fmhr_ham_step_render, "ham_step_render"), (self.lib.fmhr_ham_step_update, "ham_step_update")):
+                    check(fn(ctypes.byref(cfg), ctypes.byref(buf), sp), name)  # warm-up outside capture
+                side.synchronize()
+                if self.world == 1:
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, stream=side):
+                        sp2 = _lib.c_p(torch.cuda.current_stream(self.device).cuda_stream)
+                        check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp2), "ham_step_render")
+                        check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), sp2), "ham_step_update")
+                    graphs = [gr]
+                else:
+                    for fn, name in ((self.lib.fmhr_ham_step_render, "ham_step_render"), (self.lib.fmhr_ham_step_update, "ham_step_update")):
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr, stream=side):
+                            sp2 = _lib.c_p(torch.cuda.current_stream(self.device).cuda_stream)
+                            check(fn(ctypes.byref(cfg), ctypes.byref(buf), sp2), name)
+                        graphs.append(gr)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            for t, sv in zip((self.delta, self.albedo, self.sh_coeffs, self.adam_m, self.adam_v, self.adam_step), saved):
+                t.copy_(sv)
+            g = (graphs, slot, ws_ptr, cfg, buf)
+            self._graphs[key] = g
+        graphs, slot, ws_ptr, _, _ = g
+        if self.workspace.data_ptr() != ws_ptr:
+            raise RuntimeError("fmhr_b200: workspace was reallocated after graph capture")
+        vi = self._views(view_idx)
+        if vi.data_ptr() != slot.data_ptr():
+            slot.copy_(vi, non_blocking=True)
+        graphs[0].replay()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.packed, group=self.pg)
+            graphs[1].replay()
         return self.losses
 
     # ------------------------------------------------------------------ the two loops' bodies
@@ -148,6 +220,25 @@ class HamOptimizer:
         if self.phase != 1:
             self.begin_phase_b()
         return self._step(1, view_idx, albedo_weight)
+
+    STAGES = ("clears", "vertex_normals", "clip_transform", "coverage", "shade", "antialias_loss", "pixel_backward",
+              "update_adam")
+
+    def stage_times(self, view_idx, phase=1, repeats=5):
+        """Per-kernel device time (ms) of one iteration, averaged over `repeats` (each advances the optimiser)."""
+        vi = self._views(view_idx)
+        cfg = self._cfg(vi.numel(), phase, None)
+        buf = self._buffers(cfg, vi)
+        ms = (_lib.c_f * 16)()
+        n = _lib.c_i(0)
+        acc = [0.0] * len(self.STAGES)
+        with torch.cuda.device(self.device):
+            for _ in range(repeats):
+                check(self.lib.fmhr_ham_stage_times(ctypes.byref(cfg), ctypes.byref(buf), ms, ctypes.byref(n), stream()),
+                      "ham_stage_times")
+                for i in range(min(n.value, len(acc))):
+                    acc[i] += ms[i] / repeats
+        return dict(zip(self.STAGES, acc))
 
     def export(self, view_idx, phase=1):
         """Forward-only inspection of the fused path (parity tests): pos, rast, antialiased image, antialiased
@@ -190,6 +281,9 @@ class HostStreamingStepper:
     def step_phase_b(self, h_imgs, h_masks, h_valid, h_w2cs, h_projs, sh_rows, albedo_weight=None):
         """h_* are pinned host tensors holding this step's n_views rows; sh_rows = int32 device tensor of SH rows."""
         o = self.opt
+        for t in (h_imgs, h_masks, h_valid, h_w2cs, h_projs):
+            if t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or not t.is_pinned():
+                raise RuntimeError("HostStreamingStepper: host batches must be pinned, contiguous float32 CPU tensors")
         if o.phase != 1:
             o.begin_phase_b()
         cfg = o._cfg(self.n, 1, albedo_weight)

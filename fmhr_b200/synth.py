@@ -205,7 +205,9 @@ def make_cameras(n, H, W, center, extent=0.4, radius=1.9, frac=0.45, seed=1):
         proj[3, 2] = 1.0
         w2cs.append(w2c.T)
         projs.append(proj.T)
-    return np.stack(w2cs).astype(np.float32), np.stack(projs).astype(np.float32)
+    # np.stack of .T views yields Fortran-ordered memory; downstream code hands raw pointers to the C ABI
+    return (np.ascontiguousarray(np.stack(w2cs), dtype=np.float32),
+            np.ascontiguousarray(np.stack(projs), dtype=np.float32))
 
 
 def smooth_albedo(n_verts, faces, seed=3, steps=5):
@@ -256,7 +258,7 @@ WORKLOADS = {
 }
 
 
-def build_scene(workload, render_fn, n_views=None, view_offset=0, view_stride=1):
+def build_scene(workload, render_fn, n_views=None, view_offset=0, view_stride=1, camera_seed=1):
     """Assemble one HAM problem.  `render_fn(vertices, faces, albedo, sh, w2cs, projs, H, W)` must return
     (img[n,H,W,3], coverage[n,H,W], aa_coverage[n,H,W]) as numpy float32; the caller passes the product
     renderer (bench) or the oracle renderer (CPU tests).  Views [view_offset::view_stride] of the
@@ -266,12 +268,12 @@ def build_scene(workload, render_fn, n_views=None, view_offset=0, view_stride=1)
     verts, faces = hand_mesh(wl["subdiv"], wl["hands"], seed=0)
     center = verts.mean(0).astype(np.float64)
     extent = float(verts[:, 1].max() - verts[:, 1].min())
-    w2cs, projs = make_cameras(n_all, H, W, center, extent=extent)
+    w2cs, projs = make_cameras(n_all, H, W, center, extent=extent, seed=camera_seed)
     sh = sh_lighting(n_all)
     sel = np.arange(view_offset, n_all, view_stride)
     if n_views is not None:
         sel = sel[:n_views]
-    w2cs, projs, sh_true = w2cs[sel], projs[sel], sh[sel]
+    w2cs, projs, sh_true = np.ascontiguousarray(w2cs[sel]), np.ascontiguousarray(projs[sel]), sh[sel]
     rng = np.random.default_rng(2)
     target_verts = (verts + rng.normal(0.0, 1e-3, verts.shape)).astype(np.float32)
     alb_true = smooth_albedo(verts.shape[0], faces)

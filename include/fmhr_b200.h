@@ -179,6 +179,11 @@ int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf
  * normals [V,3]. */
 int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* pos, float* rast,
                           float* image, float* pred_mask, float* normals, fmhr_stream_t stream);
+/* Measurement aid: runs ONE render+update with CUDA events between the launches and returns the device time of each
+ * stage in milliseconds (ms_host[16]): 0 clears, 1 vertex prep + normals, 2 clip transform, 3 coverage, 4 shade,
+ * 5 antialias + losses, 6 pixel backward, 7 update/Adam.  Synchronises the stream; advances the optimiser one step. */
+int fmhr_ham_stage_times(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* ms_host, int* n_stages_host,
+                         fmhr_stream_t stream);
 /* Host-buffer variant (end-to-end measurement path): copies this step's view batch (img/mask/valid_mask/w2c/proj
  * rows, all HOST pinned pointers, n_views rows each) into the device staging planes named by `buf`, runs
  * render+update, and copies the 8-float loss record back to losses_host. */

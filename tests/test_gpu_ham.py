@@ -119,6 +119,24 @@ def _masked_param_err(ours, ref, g_ref, lr):
     return float((ours - ref).abs()[sig].max()) / lr
 
 
+def _sync_oracle(st, opt, phase_b):
+    V = opt.V
+    with torch.no_grad():
+        st.delta.copy_(opt.delta.cpu())
+        st.albedo.copy_(opt.albedo.cpu()[None])
+        st.sh_coeffs.copy_(opt.sh_coeffs.cpu())
+    o = st.opt_b if phase_b else st.opt_a
+    m, v, steps = opt.adam_m.cpu(), opt.adam_v.cpu(), opt.adam_step.cpu().tolist()
+    parts = {"delta": (m[:3 * V].view(V, 3), v[:3 * V].view(V, 3), steps[0]),
+             "albedo": (m[3 * V:6 * V].view(1, V, 3), v[3 * V:6 * V].view(1, V, 3), steps[1]),
+             "sh": (m[6 * V:].view(-1, 9), v[6 * V:].view(-1, 9), steps[2])}
+    for p, name in ((st.delta, "delta"), (st.albedo, "albedo"), (st.sh_coeffs, "sh")):
+        if p in o.state and len(o.state[p]):
+            o.state[p]["exp_avg"].copy_(parts[name][0])
+            o.state[p]["exp_avg_sq"].copy_(parts[name][1])
+            o.state[p]["step"].fill_(float(parts[name][2]))
+
+
 def test_fused_phase_b_step(scene):
     """losses, gradients and the Adam update of 3 consecutive iterations."""
     opt = _make_opt(scene)
@@ -147,15 +165,18 @@ def test_fused_phase_b_step(scene):
         chk.step()
         assert torch.allclose(opt.delta.cpu(), chk_d.detach(), rtol=1e-4, atol=1e-6 * conf["lr"] * 100), it
         assert torch.allclose(opt.albedo.cpu(), chk_a.detach(), rtol=1e-5, atol=1e-6), it
-        assert _masked_param_err(opt.delta.cpu(), st.delta.detach(), keep["grad_delta"], conf["lr"]) < 0.02 * (it + 1)
-        assert _masked_param_err(opt.albedo.cpu(), st.albedo.detach()[0], keep["grad_albedo"][0], conf["albedo_lr"]) < 0.02 * (it + 1)
+        assert _masked_param_err(opt.delta.cpu(), st.delta.detach(), keep["grad_delta"], conf["lr"]) < 0.02
+        assert _masked_param_err(opt.albedo.cpu(), st.albedo.detach()[0], keep["grad_albedo"][0], conf["albedo_lr"]) < 0.02
+        # re-synchronise the oracle to the fused path's state: every iteration is then compared on IDENTICAL inputs
+        # (two free-running trajectories diverge chaotically through the hinge / L1 kinks, which says nothing about parity)
+        _sync_oracle(st, opt, phase_b=True)
 
 
 def test_fused_phase_a_step(scene):
     opt = _make_opt(scene)
     st = oham.HamState(scene)
     n = scene["imgs"].shape[0]
-    for it, views in enumerate([list(range(n)), [1, 3]]):
+    for it, views in enumerate([list(range(n)), [1, 3], [0, 2, 1]]):
         keep = {}
         ref = oham.phase_a_step(st, views, keep=keep)
         rec = opt.step_phase_a(views).cpu().tolist()
@@ -164,8 +185,9 @@ def test_fused_phase_a_step(scene):
         assert rec[6] == ref["n_valid"]
         assert _rel(opt.dbg_grad.cpu()[:, 3:], keep["grad_albedo"][0]) < 2e-4
         assert _rel(opt.dbg_grad_sh.cpu(), keep["grad_sh"]) < 2e-4
-        assert _masked_param_err(opt.albedo.cpu(), st.albedo.detach()[0], keep["grad_albedo"][0], scene["conf"]["albedo_lr"]) < 0.02 * (it + 1)
-        assert float((opt.sh_coeffs.cpu() - st.sh_coeffs.detach()).abs().max()) < 0.02 * scene["conf"]["sh_lr"] * (it + 1)
+        assert _masked_param_err(opt.albedo.cpu(), st.albedo.detach()[0], keep["grad_albedo"][0], scene["conf"]["albedo_lr"]) < 0.02
+        assert float((opt.sh_coeffs.cpu() - st.sh_coeffs.detach()).abs().max()) < 0.02 * scene["conf"]["sh_lr"]
+        _sync_oracle(st, opt, phase_b=False)
     assert float(opt.delta.abs().max()) == 0.0
 
 
@@ -201,3 +223,39 @@ def test_shim_loop_matches_fused(scene):
         assert abs(rec[k] - ref[name]) <= 2e-5 * abs(ref[name]) + 1e-7, (name, rec[k], ref[name])
     assert _rel(opt.dbg_grad[:, :3].cpu(), keep["grad_delta"].cpu()) < 2e-4
     assert _rel(opt.dbg_grad[:, 3:].cpu(), keep["grad_albedo"][0].cpu()) < 2e-4
+
+
+def test_graph_replay_matches_eager(scene):
+    """CUDA-graph replay of the iteration (the bench path) produces the same trajectory as eager launches."""
+    a = _make_opt(scene, debug=False)
+    from fmhr_b200.ham import HamOptimizer
+    c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt).cuda()
+    b = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
+                     c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=True)
+    n = scene["imgs"].shape[0]
+    for views in ([0, 1, 2], [3, 1, 0], list(range(n)), [2, 0, 1]):
+        la = a.step_phase_b(views).cpu()
+        lb = b.step_phase_b(views).cpu()
+        assert torch.allclose(la, lb, rtol=1e-4, atol=1e-6), (la, lb)
+    assert torch.allclose(a.delta, b.delta, atol=2e-2 * scene["conf"]["lr"])
+    assert int(b.adam_step[0]) == 4 and len(b._graphs) == 2
+
+
+def test_host_streaming_step_matches_resident(scene):
+    """fmhr_ham_step_host (pinned host batch -> H2D -> render+update -> D2H loss record), the bench's e2e path."""
+    from fmhr_b200.ham import HostStreamingStepper
+    a = _make_opt(scene, debug=False)
+    b = _make_opt(scene, debug=False)
+    n = scene["imgs"].shape[0]
+    views = torch.arange(n, dtype=torch.int32, device="cuda")
+    pin = lambda k: torch.tensor(scene[k], dtype=torch.float32).contiguous().pin_memory()
+    h = [pin(k) for k in ("imgs", "masks", "valid_masks", "w2cs", "projs")]
+    stepper = HostStreamingStepper(b, n)
+    for _ in range(2):
+        la = a.step_phase_b(views).cpu()
+        stepper.step_phase_b(*h, views)
+        torch.cuda.synchronize()
+        assert torch.allclose(la, stepper.losses_host, rtol=1e-4, atol=1e-6), (la, stepper.losses_host)
+    assert torch.allclose(a.delta, b.delta, atol=2e-2 * scene["conf"]["lr"])
+    with pytest.raises(RuntimeError):
+        stepper.step_phase_b(h[0], h[1], h[2], h[3].transpose(1, 2), h[4], views)

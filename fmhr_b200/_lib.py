@@ -22,7 +22,7 @@ class HamConfig(ctypes.Structure):
     """struct fmhr_ham_config"""
     _fields_ = [("V", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
                 ("n_views", ctypes.c_int32), ("n_views_global", ctypes.c_int32), ("phase", ctypes.c_int32),
-                ("n_sh_rows", ctypes.c_int32),
+                ("n_sh_rows", ctypes.c_int32), ("zbuf_slot", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("sfs_weight", c_f), ("lap_weight", c_f), ("albedo_weight", c_f), ("mask_weight", c_f),
                 ("edge_weight", c_f), ("delta_weight", c_f),
                 ("lr", c_f), ("albedo_lr", c_f), ("sh_lr", c_f),
@@ -34,7 +34,7 @@ class HamBuffers(ctypes.Structure):
     _fields_ = [(n, c_p) for n in (
         "tri", "opp", "v2f_ptr", "v2f_idx", "v2v_ptr", "v2v_idx",
         "vertices_tmp", "delta", "albedo", "sh_coeffs", "adam_m", "adam_v", "adam_step",
-        "imgs", "masks", "valid_masks", "w2cs", "projs", "view_idx", "sh_idx",
+        "imgs", "masks", "valid_masks", "view_vm2", "w2cs", "projs", "view_idx", "sh_idx",
         "packed", "losses", "workspace")] + [("workspace_bytes", c_sz), ("dbg_grad", c_p), ("dbg_grad_sh", c_p)]
 
 
@@ -59,6 +59,8 @@ _SIGS = {
     "fmhr_ncc_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_ham_workspace_bytes": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_packed_floats": (c_sz, [ctypes.POINTER(HamConfig)]),
+    "fmhr_ham_reset": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
+    "fmhr_ham_prepare_views": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_ham_step_render": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
     "fmhr_ham_step_update": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
     "fmhr_ham_stage_times": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), ctypes.POINTER(c_f),

@@ -30,20 +30,23 @@ __device__ __forceinline__ void aa_project(const float4 p, float xh, float yh, f
     y = xs(xm(xm(p.y, iw), yh), fy);
 }
 
-// (px,py) = first pixel of the pair, d = 0 (right neighbour) or 1 (down neighbour);
-// tri0/z0 and tri1/z1 are triangle id (-1 = empty) and z/w of the two pixels; P = this view's clip positions.
-__device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z1, int px, int py, int d,
-                                           const float* __restrict__ P, const int32_t* __restrict__ tri,
-                                           const int32_t* __restrict__ opp, int V, int T, int H, int W, AAPair& out) {
-    int t = (tri0 >= 0) ? tri0 : tri1;
-    if (tri0 >= 0 && tri1 >= 0) t = (z0 < z1) ? tri0 : tri1;
-    const bool from1 = (t == tri1);
-    if (from1) { px += 1 - d; py += d; }
+// Projected corners of triangle t relative to the centre of its OWNING pixel (qx,qy), plus the three silhouette-candidate
+// bits: bit k set <=> the wing across the edge facing corner k lies on the same side as the triangle itself (or the
+// edge is a mesh boundary).  bits == 0 means no edge of this triangle can ever blend, whatever the neighbour.
+struct AAGeom {
+    int v0, v1, v2;
+    float x0, y0, x1, y1, x2, y2;
+    int bits;
+};
+
+__device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const float* __restrict__ P,
+                                                 const int32_t* __restrict__ tri, const int32_t* __restrict__ opp,
+                                                 int V, int T, int H, int W, AAGeom& g) {
     if (t < 0 || t >= T) return false;
     const int v0 = __ldg(tri + 3 * t), v1 = __ldg(tri + 3 * t + 1), v2 = __ldg(tri + 3 * t + 2);
     if ((unsigned)v0 >= (unsigned)V || (unsigned)v1 >= (unsigned)V || (unsigned)v2 >= (unsigned)V) return false;
     const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
-    const float fx = xs(xa((float)px, 0.5f), xh), fy = xs(xa((float)py, 0.5f), yh);
+    const float fx = xs(xa((float)qx, 0.5f), xh), fy = xs(xa((float)qy, 0.5f), yh);
     float x0, y0, x1, y1, x2, y2;
     aa_project(ldg4(P + 4 * (size_t)v0), xh, yh, fx, fy, x0, y0);
     aa_project(ldg4(P + 4 * (size_t)v1), xh, yh, fx, fy, x1, y1);
@@ -57,8 +60,18 @@ __device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z
     const float a0 = xs(xm(xs(x1, ox0), xs(y2, oy0)), xm(xs(x2, ox0), xs(y1, oy0)));
     const float a1 = xs(xm(xs(x2, ox1), xs(y0, oy1)), xm(xs(x0, ox1), xs(y2, oy1)));
     const float a2 = xs(xm(xs(x0, ox2), xs(y1, oy2)), xm(xs(x1, ox2), xs(y0, oy2)));
-    const bool s0 = aa_same_sign(a0, bb), s1 = aa_same_sign(a1, bb), s2 = aa_same_sign(a2, bb);
-    if (!(s0 || s1 || s2)) return false;
+    g.v0 = v0; g.v1 = v1; g.v2 = v2;
+    g.x0 = x0; g.y0 = y0; g.x1 = x1; g.y1 = y1; g.x2 = x2; g.y2 = y2;
+    g.bits = (aa_same_sign(a0, bb) ? 1 : 0) | (aa_same_sign(a1, bb) ? 2 : 0) | (aa_same_sign(a2, bb) ? 4 : 0);
+    return true;
+}
+
+// Edge selection for the pair whose chosen triangle has geometry g (d = 0 right / 1 down neighbour, from1 = the chosen
+// triangle belongs to the pair's second pixel).
+__device__ __forceinline__ bool aa_select_edge(const AAGeom& g, int t, int d, bool from1, AAPair& out) {
+    if (g.bits == 0) return false;
+    const bool s0 = g.bits & 1, s1 = g.bits & 2, s2 = g.bits & 4;
+    float x0 = g.x0, y0 = g.y0, x1 = g.x1, y1 = g.y1, x2 = g.x2, y2 = g.y2;
     if (d) {
         float tmp;
         tmp = x0; x0 = y0; y0 = tmp;
@@ -91,9 +104,23 @@ __device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z
     out.di = di;
     out.from1 = from1 ? 1 : 0;
     out.alpha = xm(ds, xs(0.5f, dc));
-    out.i1 = (di == 0) ? v1 : ((di == 1) ? v2 : v0);
-    out.i2 = (di == 0) ? v2 : ((di == 1) ? v0 : v1);
+    out.i1 = (di == 0) ? g.v1 : ((di == 1) ? g.v2 : g.v0);
+    out.i2 = (di == 0) ? g.v2 : ((di == 1) ? g.v0 : g.v1);
     return true;
+}
+
+// (px,py) = first pixel of the pair, d = 0 (right neighbour) or 1 (down neighbour);
+// tri0/z0 and tri1/z1 are triangle id (-1 = empty) and z/w of the two pixels; P = this view's clip positions.
+__device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z1, int px, int py, int d,
+                                           const float* __restrict__ P, const int32_t* __restrict__ tri,
+                                           const int32_t* __restrict__ opp, int V, int T, int H, int W, AAPair& out) {
+    int t = (tri0 >= 0) ? tri0 : tri1;
+    if (tri0 >= 0 && tri1 >= 0) t = (z0 < z1) ? tri0 : tri1;
+    const bool from1 = (t == tri1);
+    if (from1) { px += 1 - d; py += d; }
+    AAGeom g;
+    if (!aa_triangle_geom(t, px, py, P, tri, opp, V, T, H, W, g)) return false;
+    return aa_select_edge(g, t, d, from1, out);
 }
 
 // d(alpha)/d(clip position) of the two edge vertices, scaled by `dd` = d(loss)/d(alpha).

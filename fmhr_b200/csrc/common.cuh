@@ -1,6 +1,7 @@
 // Shared device/host helpers for the fmhr_b200 kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/fmhr_b200.h"
@@ -76,6 +77,21 @@ __device__ __forceinline__ Bary bary_at(const float4 p0, const float4 p1, const 
     float wd = xa(xa(xm(p0.w, a0), xm(p1.w, a1)), xm(p2.w, a2));
     b.zw = xa(clampzx(xd(zn, wd)), 0.0f);
     return b;
+}
+
+// clip -> 24.8 fixed-point window coordinates (pixel centre at integer + 0.5 -> +128); rejects vertices outside the clip
+// volume / guard band.  Same operation order as the oracle's snap_tri().
+constexpr float kGuard = 16384.0f;
+constexpr int kSnapRejected = INT_MIN;
+__device__ __forceinline__ bool snap_vertex(const float4 p, float hw, float hh, int& X, int& Y) {
+    if (!(p.w > 0.0f)) return false;
+    if (!(p.z >= -p.w && p.z <= p.w)) return false;
+    float sx = xa(xm(xd(p.x, p.w), hw), hw);
+    float sy = xa(xm(xd(p.y, p.w), hh), hh);
+    if (!(fabsf(sx) <= kGuard) || !(fabsf(sy) <= kGuard)) return false;
+    X = __float2int_rn(xm(sx, 256.0f));
+    Y = __float2int_rn(xm(sy, 256.0f));
+    return true;
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

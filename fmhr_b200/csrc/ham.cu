@@ -14,15 +14,31 @@
 
 namespace fmhr {
 
-int launch_raster_coverage(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
-                           unsigned long long* zbuf, cudaStream_t st);
+int launch_raster_coverage_snapped(const float4* pos, const int2* snap, const int32_t* tri, int N, int V, int T, int H,
+                                   int W, unsigned long long* zbuf, uint32_t* tbits, uint32_t* tlist, int* tcount,
+                                   int tiles_x, int tiles_per_view, cudaStream_t st);
 int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
                               int V, float* normals, float* raw, cudaStream_t st);
 
 struct HamWs {
-    unsigned long long* zbuf;  // [n,H,W]
+    unsigned long long* zbuf[2];  // [n,H,W] x2: `zbuf_slot` is rasterised this step, the other is reset for the next
     float4* plane[4];          // [n,H,W] each
-    float4* pos;               // [n,V]
+    float4* pos;               // [n,V] clip positions
+    int2* snap;                // [n,V] 24.8 fixed-point window coordinates (x == INT_MIN: vertex rejected)
+    // Active-tile work lists (16x16 tiles).  slot[s]: tiles of z-buffer slot s that received fragments (bitmap for
+    // de-duplication + compact list + count, filled by the coverage kernel); act: those tiles dilated by their four
+    // edge neighbours (antialias pairs straddle tile edges), filled by the shade pass.  The pixel passes are persistent
+    // kernels that walk these lists, so idle tiles cost nothing (launching a block per tile spent ~80 us per pass on
+    // ~25k blocks whose only instruction was a flag load).
+    char* slot_region[2];        // [count (256 B) | bitmap] zeroed together when the slot is reused
+    int* tcount[2];
+    uint32_t* tbits[2];          // [n, words_per_view]
+    uint32_t* tlist[2];          // [n * tiles_per_view]
+    char* common_region;         // [acc | acount | abits] zeroed every step
+    size_t common_bytes, slot_bytes;
+    int* acount;
+    uint32_t* abits;
+    uint32_t* alist;
     float* vertices;           // [V,3]
     float* normals;            // [V,3] normalised
     float* raw;                // [V,3] un-normalised normal sums
@@ -30,7 +46,8 @@ struct HamWs {
     float* yhat_v;             // [V,3]
     float* yhat_a;             // [V,3]
     float* gsh;                // [n_sh_rows,9] un-normalised SH gradients by SH row (phase A)
-    double* acc;               // [8]: 0 n_valid, 1 abs_sum, 2 mask_sq, 3 lap_v, 4 lap_a, 5 edge, 6 delta
+    double* acc;               // [8][32] (32-way spread against same-address atomics):
+                               // 0 n_valid, 1 abs_sum, 2 mask_sq correction, 3 lap_v, 4 lap_a, 5 edge, 6 delta
     float* adam_sc;            // [8]: step_size / bias2_sqrt for delta, albedo, sh
 };
 
@@ -52,13 +69,30 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
     char* p;
-    p = take(P * 8); if (ws) ws->zbuf = (unsigned long long*)p;
+    for (int i = 0; i < 2; i++) { p = take(P * 8); if (ws) ws->zbuf[i] = (unsigned long long*)p; }
     const int nplanes = c->phase == 0 ? 4 : 2;
     for (int i = 0; i < 4; i++) {
         p = (i < nplanes) ? take(P * 16) : nullptr;
         if (ws) ws->plane[i] = (float4*)p;
     }
     p = take((size_t)c->n_views * V * 16); if (ws) ws->pos = (float4*)p;
+    p = take((size_t)c->n_views * V * 8); if (ws) ws->snap = (int2*)p;
+    const size_t tiles_pv = (size_t)((c->W + 15) / 16) * ((c->H + 15) / 16);
+    const size_t words = (size_t)c->n_views * ((tiles_pv + 31) / 32);
+    const size_t slot_bytes = 256 + align256(words * 4);
+    for (int i = 0; i < 2; i++) {
+        p = take(slot_bytes);
+        if (ws) { ws->slot_region[i] = p; ws->tcount[i] = (int*)p; ws->tbits[i] = (uint32_t*)(p + 256); }
+        p = take((size_t)c->n_views * tiles_pv * 4); if (ws) ws->tlist[i] = (uint32_t*)p;
+    }
+    p = take((size_t)c->n_views * tiles_pv * 4); if (ws) ws->alist = (uint32_t*)p;
+    const size_t common_bytes = 8 * 32 * sizeof(double) + 256 + align256(words * 4);
+    p = take(common_bytes);
+    if (ws) {
+        ws->common_region = p; ws->common_bytes = common_bytes; ws->slot_bytes = slot_bytes;
+        ws->acc = (double*)p; ws->acount = (int*)(p + 8 * 32 * sizeof(double));
+        ws->abits = (uint32_t*)(p + 8 * 32 * sizeof(double) + 256);
+    }
     p = take(V * 12); if (ws) ws->vertices = (float*)p;
     p = take(V * 12); if (ws) ws->normals = (float*)p;
     p = take(V * 12); if (ws) ws->raw = (float*)p;
@@ -66,7 +100,6 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take(V * 12); if (ws) ws->yhat_v = (float*)p;
     p = take(V * 12); if (ws) ws->yhat_a = (float*)p;
     p = take((size_t)c->n_sh_rows * 9 * 4); if (ws) ws->gsh = (float*)p;
-    p = take(8 * sizeof(double)); if (ws) ws->acc = (double*)p;
     p = take(8 * sizeof(float)); if (ws) ws->adam_sc = (float*)p;
     return off;
 }
@@ -81,27 +114,31 @@ __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __res
     if (i < n3) vertices[i] = vtmp[i] + delta[i];  // mesh_sfs_optim.py:253
 }
 
-// clip = ([v,1] @ w2c) @ proj, both matrices stored transposed (mesh_sfs_optim.py:262-264, get_data.py:96-97)
+// clip = ([v,1] @ w2c) @ proj, both matrices stored transposed (mesh_sfs_optim.py:262-264, get_data.py:96-97); also snaps
+// every vertex to the rasteriser's fixed-point grid once per (view, vertex) instead of once per (view, triangle corner).
 __global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restrict__ vertices,
                                                             const float* __restrict__ w2cs,
                                                             const float* __restrict__ projs,
-                                                            const int32_t* __restrict__ view_idx, int V,
-                                                            float4* __restrict__ pos) {
-    __shared__ float Wm[16], Pm[16];
+                                                            const int32_t* __restrict__ view_idx, int V, int H, int W,
+                                                            float4* __restrict__ pos, int2* __restrict__ snap) {
     const int n = blockIdx.y;
     const int view = __ldg(view_idx + n);
-    if (threadIdx.x < 16) Wm[threadIdx.x] = w2cs[(size_t)view * 16 + threadIdx.x];
-    else if (threadIdx.x < 32) Pm[threadIdx.x - 16] = projs[(size_t)view * 16 + threadIdx.x - 16];
-    __syncthreads();
+    const float* Wm = w2cs + (size_t)view * 16;  // block-uniform addresses: broadcast loads
+    const float* Pm = projs + (size_t)view * 16;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float x = vertices[3 * (size_t)i], y = vertices[3 * (size_t)i + 1], z = vertices[3 * (size_t)i + 2];
     float r[4], c[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) r[j] = x * Wm[j] + y * Wm[4 + j] + z * Wm[8 + j] + Wm[12 + j];
+    for (int j = 0; j < 4; j++) r[j] = x * __ldg(Wm + j) + y * __ldg(Wm + 4 + j) + z * __ldg(Wm + 8 + j) + __ldg(Wm + 12 + j);
 #pragma unroll
-    for (int j = 0; j < 4; j++) c[j] = r[0] * Pm[j] + r[1] * Pm[4 + j] + r[2] * Pm[8 + j] + r[3] * Pm[12 + j];
-    pos[(size_t)n * V + i] = make_float4(c[0], c[1], c[2], c[3]);
+    for (int j = 0; j < 4; j++)
+        c[j] = r[0] * __ldg(Pm + j) + r[1] * __ldg(Pm + 4 + j) + r[2] * __ldg(Pm + 8 + j) + r[3] * __ldg(Pm + 12 + j);
+    const float4 p = make_float4(c[0], c[1], c[2], c[3]);
+    pos[(size_t)n * V + i] = p;
+    int X = kSnapRejected, Y = 0;
+    if (!snap_vertex(p, (float)W * 0.5f, (float)H * 0.5f, X, Y)) X = kSnapRejected;
+    snap[(size_t)n * V + i] = make_int2(X, Y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,6 +182,10 @@ __device__ __forceinline__ float sh_radiance(const float* c, float x, float y, f
     return r;
 }
 
+// pixel kernels run 16x16 tiles: 2-D locality keeps the hand's pixels in few, densely active blocks
+constexpr int kTile = 16;
+__device__ __forceinline__ int tile_tid() { return threadIdx.y * kTile + threadIdx.x; }
+
 struct ViewCtx {
     float M[12];  // rows 0..2 of (w2c @ proj), columns x,y,z,w : d(clip_j)/d(world_i) = M[4i+j]
     float sh[9];
@@ -153,14 +194,14 @@ struct ViewCtx {
 __device__ __forceinline__ void load_view_ctx(ViewCtx* s, const float* __restrict__ w2cs,
                                               const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
                                               int view, int sh_row) {
-    if (threadIdx.x < 12) {
-        const int i = threadIdx.x >> 2, j = threadIdx.x & 3;
+    const int tid = tile_tid();
+    if (tid < 12) {
+        const int i = tid >> 2, j = tid & 3;
         const float* Wm = w2cs + (size_t)view * 16;
         const float* Pm = projs + (size_t)view * 16;
-        s->M[threadIdx.x] = Wm[4 * i] * Pm[j] + Wm[4 * i + 1] * Pm[4 + j] + Wm[4 * i + 2] * Pm[8 + j] +
-                            Wm[4 * i + 3] * Pm[12 + j];
-    } else if (threadIdx.x >= 32 && threadIdx.x < 41) {
-        s->sh[threadIdx.x - 32] = sh_coeffs[(size_t)sh_row * 9 + threadIdx.x - 32];
+        s->M[tid] = Wm[4 * i] * Pm[j] + Wm[4 * i + 1] * Pm[4 + j] + Wm[4 * i + 2] * Pm[8 + j] + Wm[4 * i + 3] * Pm[12 + j];
+    } else if (tid >= 32 && tid < 41) {
+        s->sh[tid - 32] = sh_coeffs[(size_t)sh_row * 9 + tid - 32];
     }
 }
 
@@ -171,12 +212,13 @@ __device__ __forceinline__ float3 clip_to_world(const float* M, float gx, float 
 }
 
 __device__ __forceinline__ float block_sum_256(float v, float* sm) {
+    const int tid = tile_tid();
     v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    if ((tid & 31) == 0) sm[tid >> 5] = v;
     __syncthreads();
     float r = 0.0f;
-    if (threadIdx.x < 8) r = sm[threadIdx.x];
-    if (threadIdx.x < 32) {
+    if (tid < 8) r = sm[tid];
+    if (tid < 32) {
         r += __shfl_xor_sync(0xffffffffu, r, 4);
         r += __shfl_xor_sync(0xffffffffu, r, 2);
         r += __shfl_xor_sync(0xffffffffu, r, 1);
@@ -185,47 +227,169 @@ __device__ __forceinline__ float block_sum_256(float v, float* sm) {
     return r;  // valid in thread 0
 }
 
+// One 16x16 tile of one view, as handed out by the work lists.
+struct TileCtx {
+    int n, bx, by, nx, ny;  // view slot, tile coordinates, tiles per row / column
+};
+__device__ __forceinline__ uint32_t tile_encode(int n, int bx, int by) { return ((uint32_t)n << 20) | ((uint32_t)by << 10) | (uint32_t)bx; }
+__device__ __forceinline__ TileCtx tile_decode(uint32_t e, int nx, int ny) {
+    TileCtx tc;
+    tc.n = (int)(e >> 20); tc.by = (int)((e >> 10) & 1023u); tc.bx = (int)(e & 1023u); tc.nx = nx; tc.ny = ny;
+    return tc;
+}
+
+// 32-way spread accumulators
+__device__ __forceinline__ void acc_add(double* acc, int k, float v, const TileCtx& tc) {
+    if (v != 0.0f) atomicAdd(acc + k * 32 + ((tc.bx + tc.by * 7 + tc.n * 13) & 31), (double)v);
+}
+// barrier-free variant: shuffle-reduce inside the warp, one spread fp64 atomic per warp
+__device__ __forceinline__ void warp_acc_add(double* acc, int k, float v, const TileCtx& tc) {
+    v = warp_sum(v);
+    if ((tile_tid() & 31) == 0 && v != 0.0f)
+        atomicAdd(acc + k * 32 + ((tc.bx + tc.by * 7 + tc.n * 13 + (tile_tid() >> 5)) & 31), (double)v);
+}
+__device__ __forceinline__ double acc_total(const double* acc, int k) {
+    double s = 0.0;
+    for (int j = 0; j < 32; j++) s += acc[k * 32 + j];
+    return s;
+}
+__device__ __forceinline__ int tile_index(const TileCtx& tc) { return tc.by * tc.nx + tc.bx; }
+// Appends this tile and its four edge neighbours to the dilated work list (bitmap de-duplicates).
+__device__ __forceinline__ void tile_mark_active(const TileCtx& tc, int tid, uint32_t* __restrict__ abits,
+                                                 uint32_t* __restrict__ alist, int* __restrict__ acount) {
+    int bx = tc.bx, by = tc.by;
+    if (tid == 1) bx -= 1; else if (tid == 2) bx += 1; else if (tid == 3) by -= 1; else if (tid == 4) by += 1;
+    if (tid > 4 || bx < 0 || by < 0 || bx >= tc.nx || by >= tc.ny) return;
+    const int tile = by * tc.nx + bx, words_pv = (tc.nx * tc.ny + 31) >> 5;
+    const uint32_t bit = 1u << (tile & 31);
+    const uint32_t old = atomicOr(abits + (size_t)tc.n * words_pv + (tile >> 5), bit);
+    if (!(old & bit)) alist[atomicAdd(acount, 1)] = tile_encode(tc.n, bx, by);
+}
+
 // Per-vertex accumulator layout in `packed` (12 floats = 3 float4):
 //   A = (photo_pos.xyz, mask_pos.x)  B = (mask_pos.yz, normal.xy)  C = (normal.z, albedo.bgr)
 // photo_* are gradients of the UN-NORMALISED photometric sum  sum |tmp_img - img|, mask_pos of sum (pred - valid)^2 / 2.
 
 // ------------------------------------------------------------------------------------------------
-// shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A)
+// z-buffer key layout after the shade pass (low word): bits 0..27 triangle id, 28..30 silhouette-candidate bits of
+// that triangle in this pixel's frame (aa_triangle_geom), bit 31 "valid" (covered and mask > 0).
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kTriMask = 0x0FFFFFFFu;
+
+struct NbrKeys {
+    int tri;   // -1 empty
+    float zw;
+    int bits;  // silhouette-candidate bits
+    bool valid;
+};
+__device__ __forceinline__ NbrKeys decode_key(unsigned long long key) {
+    NbrKeys k;
+    if (key == ZB_EMPTY) { k.tri = -1; k.zw = 0.0f; k.bits = 0; k.valid = false; }
+    else {
+        const uint32_t lo = (uint32_t)key;
+        k.tri = (int)(lo & kTriMask);
+        k.bits = (int)((lo >> 28) & 7u);
+        k.valid = (lo >> 31) != 0;
+        k.zw = depth_from_key((uint32_t)(key >> 32));
+    }
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pair work queue.  A block is responsible for every horizontally / vertically adjacent pixel pair with at least one
+// pixel in its tile: the two pairs each of its pixels starts (right, down) plus the pairs entering through the tile's
+// left column and top row.  Pairs that can blend (different triangle ids and silhouette bits set on the chosen
+// triangle) are rare (~1 % of pixels), so instead of running the ~400-instruction edge analysis under a 3-lane mask
+// inside every warp, they are queued in shared memory and analysed densely by all 256 threads.
+//   item = (tid << 2) | which,  which: 0 (self,right)  1 (self,down)  2 (left,self)  3 (up,self)
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairQueue = 2 * kTile * kTile + 2 * kTile;
+
+__device__ __forceinline__ bool pair_needs_analysis(const NbrKeys& k0, const NbrKeys& k1) {
+    if (k0.tri == k1.tri) return false;
+    // same triangle choice as aa_analyse; the chosen pixel's silhouette bits come from the identical aa_triangle_geom
+    // call in the shade pass, so skipping bits == 0 is exact
+    const bool from1 = (k0.tri >= 0 && k1.tri >= 0) ? !(k0.zw < k1.zw) : (k0.tri < 0);
+    return (from1 ? k1.bits : k0.bits) != 0;
+}
+
+__device__ __forceinline__ void enqueue_pairs(const unsigned long long* __restrict__ zb, int px, int py, int H, int W,
+                                              const NbrKeys& self, int tid, uint32_t* q_items, int* q_n) {
+    if (px >= W || py >= H) return;
+    const int rem = py * W + px;
+    if (px + 1 < W) {
+        const NbrKeys o = decode_key(zb[rem + 1]);
+        if (pair_needs_analysis(self, o)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 0u;
+    }
+    if (py + 1 < H) {
+        const NbrKeys o = decode_key(zb[rem + W]);
+        if (pair_needs_analysis(self, o)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 1u;
+    }
+    if (threadIdx.x == 0 && px > 0) {
+        const NbrKeys o = decode_key(zb[rem - 1]);
+        if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 2u;
+    }
+    if (threadIdx.y == 0 && py > 0) {
+        const NbrKeys o = decode_key(zb[rem - W]);
+        if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 3u;
+    }
+}
+
+struct PairItem {
+    int qx, qy, d;        // first pixel of the pair and direction
+    int tid0, tid1;       // in-tile thread index of the first / second pixel, -1 when outside this tile
+};
+__device__ __forceinline__ PairItem decode_pair_item(uint32_t item, const TileCtx& tc) {
+    const int tid = (int)(item >> 2), which = (int)(item & 3u);
+    const int lx = tid & (kTile - 1), ly = tid >> 4;
+    const int px = tc.bx * kTile + lx, py = tc.by * kTile + ly;
+    PairItem it;
+    it.d = which & 1;
+    if (which < 2) {
+        it.qx = px; it.qy = py; it.tid0 = tid;
+        const int ox = lx + (1 - it.d), oy = ly + it.d;
+        it.tid1 = (ox < kTile && oy < kTile) ? oy * kTile + ox : -1;
+    } else {
+        it.qx = px - (1 - it.d); it.qy = py - it.d; it.tid0 = -1; it.tid1 = tid;
+    }
+    return it;
+}
+
+// shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A); also tags the key with
+// the silhouette bits / valid flag and resets the OTHER z-buffer slot for the next iteration (no separate clear pass).
 template <int PHASE>
-__global__ void __launch_bounds__(256) ham_shade_kernel(const unsigned long long* __restrict__ zbuf,
-                                                        const float4* __restrict__ pos,
-                                                        const int32_t* __restrict__ tri,
-                                                        const float* __restrict__ normals,
-                                                        const float* __restrict__ albedo,
-                                                        const float* __restrict__ masks,
-                                                        const float* __restrict__ sh_coeffs,
-                                                        const int32_t* __restrict__ view_idx,
-                                                        const int32_t* __restrict__ sh_idx, int V, int H, int W,
-                                                        float4* __restrict__ plane0, float4* __restrict__ plane1,
-                                                        double* __restrict__ acc) {
-    __shared__ float sh[9];
-    __shared__ float red[8];
-    const int n = blockIdx.y;
+__device__ __forceinline__ void shade_tile(const TileCtx tc, unsigned long long* __restrict__ zbuf,
+                                           const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+                                           const int32_t* __restrict__ opp, const float* __restrict__ normals,
+                                           const float* __restrict__ albedo, const float* __restrict__ masks,
+                                           const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx,
+                                           const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
+                                           float4* __restrict__ plane0, float4* __restrict__ plane1,
+                                           double* __restrict__ acc) {
+    const int n = tc.n;
     const int view = __ldg(view_idx + n);
-    if (PHASE == 1 && threadIdx.x < 9) sh[threadIdx.x] = sh_coeffs[(size_t)__ldg(sh_idx + n) * 9 + threadIdx.x];
-    __syncthreads();
+    const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;  // block-uniform address: L1 broadcast
     const int hw = H * W;
-    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+    const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
     float nvalid = 0.0f;
-    if (rem < hw) {
+    if (px < W && py < H) {
+        const int rem = py * W + px;
         const size_t pix = (size_t)n * hw + rem;
         const unsigned long long key = zbuf[pix];
         if (key != ZB_EMPTY) {
-            const int py = rem / W, px = rem - py * W;
-            const int t = (int)(uint32_t)key;
+            const int t = (int)((uint32_t)key & kTriMask);
             const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
+            const float4* Pv = pos + (size_t)n * V;
             PixTri q;
-            load_pixtri(t, px, py, pos + (size_t)n * V, tri, invW, invH, q);
+            load_pixtri(t, px, py, Pv, tri, invW, invH, q);
+            AAGeom g;
+            g.bits = 0;
+            aa_triangle_geom(t, px, py, reinterpret_cast<const float*>(Pv), tri, opp, V, T, H, W, g);
             const float3 m = interp3(normals, q);
             const float3 a = interp3(albedo, q);
             const bool valid = __ldg(masks + (size_t)view * hw + rem) > 0.0f;
             nvalid = valid ? 1.0f : 0.0f;
+            zbuf[pix] = key | ((unsigned long long)(uint32_t)g.bits << 28) | (valid ? 0x80000000ull : 0ull);
             if (PHASE == 1) {
                 float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
@@ -240,103 +404,125 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(const unsigned long long
             }
         }
     }
-    const float s = block_sum_256(nvalid, red);
-    if (threadIdx.x == 0 && s != 0.0f) atomicAdd(acc + 0, (double)s);
+    warp_acc_add(acc, 0, nvalid, tc);
 }
 
-// ------------------------------------------------------------------------------------------------
-// antialias (gather form) + losses
-// ------------------------------------------------------------------------------------------------
-struct NbrKeys {
-    int tri;   // -1 empty
-    float zw;
-};
-__device__ __forceinline__ NbrKeys decode_key(unsigned long long key) {
-    NbrKeys k;
-    if (key == ZB_EMPTY) { k.tri = -1; k.zw = 0.0f; }
-    else { k.tri = (int)(uint32_t)key; k.zw = depth_from_key((uint32_t)(key >> 32)); }
-    return k;
-}
-
-// Visits the (up to) four pixel pairs that contain pixel (px,py).  For every pair whose analysis finds a silhouette
-// crossing, calls f(pair, pix_first, pix_second, d, self_is_first).
-template <typename F>
-__device__ __forceinline__ void for_each_pair(const unsigned long long* __restrict__ zb, int px, int py, int H, int W,
-                                              const float* __restrict__ P, const int32_t* __restrict__ tri,
-                                              const int32_t* __restrict__ opp, int V, int T, NbrKeys self, F f) {
-    const int rem = py * W + px;
-    // d = 0: (self, right) ; d = 1: (self, down) ; then (left, self), (up, self)
-#pragma unroll
-    for (int which = 0; which < 4; which++) {
-        const int d = which & 1;
-        const bool self_first = which < 2;
-        const int qx = self_first ? px : px - (1 - d), qy = self_first ? py : py - d;  // first pixel of the pair
-        const int ox = self_first ? px + (1 - d) : qx, oy = self_first ? py + d : qy;  // the OTHER pixel
-        if (ox < 0 || oy < 0 || ox >= W || oy >= H) continue;
-        const int orem = oy * W + ox;
-        const NbrKeys other = decode_key(zb[orem]);
-        if (other.tri == self.tri) continue;
-        const NbrKeys k0 = self_first ? self : other, k1 = self_first ? other : self;
-        AAPair pr;
-        if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, qx, qy, d, P, tri, opp, V, T, H, W, pr)) continue;
-        f(pr, self_first ? rem : orem, self_first ? orem : rem, d, self_first, qx, qy);
+// shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A); tags every key with the
+// silhouette bits / valid flag, resets the tiles the OTHER z-buffer slot dirtied in the previous iteration (no separate
+// clear pass) and builds the dilated work list for the two passes that follow.  Persistent: grid = SMs x 4.
+template <int PHASE>
+__global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __restrict__ zbuf,
+                                                        unsigned long long* __restrict__ zbuf_next,
+                                                        const uint32_t* __restrict__ tlist, const int* __restrict__ tcount,
+                                                        const uint32_t* __restrict__ tlist_next,
+                                                        const int* __restrict__ tcount_next,
+                                                        uint32_t* __restrict__ abits, uint32_t* __restrict__ alist,
+                                                        int* __restrict__ acount, int tiles_x, int tiles_y,
+                                                        const float4* __restrict__ pos,
+                                                        const int32_t* __restrict__ tri,
+                                                        const int32_t* __restrict__ opp,
+                                                        const float* __restrict__ normals,
+                                                        const float* __restrict__ albedo,
+                                                        const float* __restrict__ masks,
+                                                        const float* __restrict__ sh_coeffs,
+                                                        const int32_t* __restrict__ view_idx,
+                                                        const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
+                                                        float4* __restrict__ plane0, float4* __restrict__ plane1,
+                                                        double* __restrict__ acc) {
+    const int nd = *tcount_next;
+    for (int it = blockIdx.x; it < nd; it += gridDim.x) {
+        const TileCtx tc = tile_decode(tlist_next[it], tiles_x, tiles_y);
+        const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
+        if (px < W && py < H) zbuf_next[((size_t)tc.n * H + py) * W + px] = ZB_EMPTY;
+    }
+    const int nc = *tcount;
+    for (int it = blockIdx.x; it < nc; it += gridDim.x) {
+        const TileCtx tc = tile_decode(tlist[it], tiles_x, tiles_y);
+        tile_mark_active(tc, tile_tid(), abits, alist, acount);
+        shade_tile<PHASE>(tc, zbuf, pos, tri, opp, normals, albedo, masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
+                          plane1, acc);
     }
 }
 
 template <int PHASE>
-__global__ void __launch_bounds__(256) ham_aa_loss_kernel(
-    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+__device__ __forceinline__ void aa_loss_tile(
+    const TileCtx tc, const unsigned long long* __restrict__ zbuf,
+    const float4* __restrict__ pos, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
     float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
-    float* __restrict__ dbg_image, float* __restrict__ dbg_mask) {
-    __shared__ float sh[9];
-    __shared__ float red[8];
-    const int n = blockIdx.y;
+    const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask,
+    uint32_t* q_items, int& q_n, float (*blend)[PHASE == 1 ? 4 : 6]) {
+    constexpr int NC = PHASE == 1 ? 4 : 6;  // blended channels: (b,g,r,coverage) or (normal xyz, albedo bgr)
+    const int n = tc.n;
+    const int tiles = tc.nx * tc.ny;
     const int view = __ldg(view_idx + n);
-    if (PHASE == 0 && threadIdx.x < 9) sh[threadIdx.x] = sh_coeffs[(size_t)__ldg(sh_idx + n) * 9 + threadIdx.x];
-    __syncthreads();
+    const int tid = tile_tid();
+    const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;  // block-uniform address: L1 broadcast
     const int hw = H * W;
-    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+    const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
+    const bool inb = px < W && py < H;
+    const size_t base = (size_t)n * hw;
+    const unsigned long long* zb = zbuf + base;
+    const int rem = py * W + px;
+    NbrKeys self = decode_key(ZB_EMPTY);
+    if (inb) self = decode_key(zb[rem]);
+    enqueue_pairs(zb, px, py, H, W, self, tid, q_items, &q_n);
+    __syncthreads();  // the only barrier of a tile without blend candidates (q_n is double-buffered by the caller)
+    // dense analysis of the queued pairs; the receiver's blend lands in shared memory
+    const int nq = q_n;
+    if (nq > 0) {  // block-uniform
+#pragma unroll
+        for (int c = 0; c < NC; c++) blend[tid][c] = 0.0f;
+        __syncthreads();
+        const float* P = reinterpret_cast<const float*>(pos + (size_t)n * V);
+        for (int e = tid; e < nq; e += kTile * kTile) {
+            const PairItem it = decode_pair_item(q_items[e], tc);
+            const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
+            const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
+            AAPair pr;
+            if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, P, tri, opp, V, T, H, W, pr)) continue;
+            const int recv = pr.alpha > 0.0f ? it.tid0 : it.tid1;
+            if (recv < 0) continue;  // the receiver belongs to the neighbouring tile's block
+            // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
+            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, s0 = f0, s1 = f0;
+            if (k0.tri >= 0) { f0 = plane0[base + r0]; if (PHASE == 0) f1 = plane1[base + r0]; }
+            if (k1.tri >= 0) { s0 = plane0[base + r1]; if (PHASE == 0) s1 = plane1[base + r1]; }
+            atomicAdd(&blend[recv][0], pr.alpha * (s0.x - f0.x));
+            atomicAdd(&blend[recv][1], pr.alpha * (s0.y - f0.y));
+            atomicAdd(&blend[recv][2], pr.alpha * (s0.z - f0.z));
+            if (PHASE == 1) {
+                atomicAdd(&blend[recv][3], pr.alpha * ((k1.tri >= 0 ? 1.0f : 0.0f) - (k0.tri >= 0 ? 1.0f : 0.0f)));
+            } else {
+                atomicAdd(&blend[recv][3], pr.alpha * (s1.x - f1.x));
+                atomicAdd(&blend[recv][4], pr.alpha * (s1.y - f1.y));
+                atomicAdd(&blend[recv][5], pr.alpha * (s1.z - f1.z));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) q_n = 0;  // everyone has read nq; this counter is next used two tiles from now
+    }
     float abs_sum = 0.0f, msk_sum = 0.0f;
     float gc[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) gc[k] = 0.0f;
-    if (rem < hw) {
-        const size_t base = (size_t)n * hw;
+    if (inb) {
         const size_t pix = base + rem;
-        const unsigned long long* zb = zbuf + base;
-        const NbrKeys self = decode_key(zb[rem]);
-        const int py = rem / W, px = rem - py * W;
-        const float* P = reinterpret_cast<const float*>(pos + (size_t)n * V);
         // own (pre-antialias) values; empty pixels are zero in every channel
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (self.tri >= 0) {
             c0 = plane0[pix];
             if (PHASE == 0) c1 = plane1[pix];
         }
-        const float cov_self = self.tri >= 0 ? 1.0f : 0.0f;
-        float4 a0 = c0, a1 = c1;  // antialiased accumulators
-        float amask = cov_self;
-        for_each_pair(zb, px, py, H, W, P, tri, opp, V, T, self,
-                      [&](const AAPair& pr, int r_first, int r_second, int d, bool self_first, int qx, int qy) {
-                          const bool recv_first = pr.alpha > 0.0f;
-                          if (recv_first != self_first) return;  // this pixel is not the receiver
-                          const int orem = self_first ? r_second : r_first;
-                          const bool ocov = decode_key(zb[orem]).tri >= 0;
-                          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-                          if (ocov) {
-                              o0 = plane0[base + orem];
-                              if (PHASE == 0) o1 = plane1[base + orem];
-                          }
-                          // out[recv] += alpha * (color[second] - color[first])
-                          const float sgn = self_first ? pr.alpha : -pr.alpha;  // alpha*(other - self) or alpha*(self - other)
-                          a0.x += sgn * (o0.x - c0.x); a0.y += sgn * (o0.y - c0.y); a0.z += sgn * (o0.z - c0.z);
-                          if (PHASE == 0) { a1.x += sgn * (o1.x - c1.x); a1.y += sgn * (o1.y - c1.y); a1.z += sgn * (o1.z - c1.z); }
-                          if (PHASE == 1) amask += sgn * ((ocov ? 1.0f : 0.0f) - cov_self);
-                      });
-        const bool valid = self.tri >= 0 && c0.w > 0.0f;
+        float4 a0 = c0, a1 = c1;  // antialiased values
+        float amask = self.tri >= 0 ? 1.0f : 0.0f;
+        if (nq > 0) {
+            a0.x += blend[tid][0]; a0.y += blend[tid][1]; a0.z += blend[tid][2];
+            if (PHASE == 1) amask += blend[tid][3];
+            else { a1.x += blend[tid][3]; a1.y += blend[tid][4]; a1.z += blend[tid][5]; }
+        }
+        const bool valid = self.valid;
         const float* img = imgs + ((size_t)view * hw + rem) * 3;
         if (PHASE == 1) {
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -345,7 +531,9 @@ __global__ void __launch_bounds__(256) ham_aa_loss_kernel(
                 abs_sum = fabsf(d0) + fabsf(d1) + fabsf(d2);
                 g.x = (d0 > 0.f) - (d0 < 0.f); g.y = (d1 > 0.f) - (d1 < 0.f); g.z = (d2 > 0.f) - (d2 < 0.f);
             }
-            const float dm = amask - __ldg(valid_masks + (size_t)view * hw + rem);  // mesh_sfs_optim.py:295
+            // mesh_sfs_optim.py:295  mean((pred_mask - valid_mask)^2).  Inactive tiles have pred_mask == 0 and contribute
+            // valid_mask^2, a per-tile constant of the view (buffers.view_vm2): they are never visited.
+            const float dm = amask - __ldg(valid_masks + (size_t)view * hw + rem);
             msk_sum = dm * dm;
             g.w = dm;
             gplane0[pix] = g;
@@ -375,17 +563,44 @@ __global__ void __launch_bounds__(256) ham_aa_loss_kernel(
             if (dbg_image) { dbg_image[pix * 3] = pred.x; dbg_image[pix * 3 + 1] = pred.y; dbg_image[pix * 3 + 2] = pred.z; }
         }
     }
-    float s = block_sum_256(abs_sum, red);
-    if (threadIdx.x == 0 && s != 0.0f) atomicAdd(acc + 1, (double)s);
+    warp_acc_add(acc, 1, abs_sum, tc);
     if (PHASE == 1) {
-        s = block_sum_256(msk_sum, red);
-        if (threadIdx.x == 0 && s != 0.0f) atomicAdd(acc + 2, (double)s);
+        warp_acc_add(acc, 2, msk_sum, tc);
+        // this tile is accounted for explicitly: remove its constant share (exact in fp64)
+        if (tid == 0)
+            atomicAdd(acc + 7 * 32 + ((tc.bx + tc.by * 7 + tc.n * 13) & 31),
+                      view_vm2[(size_t)view * (tiles + 1) + tile_index(tc)]);
     } else {
 #pragma unroll
         for (int k = 0; k < 9; k++) {
-            s = block_sum_256(gc[k], red);
-            if (threadIdx.x == 0 && s != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, s);
+            const float sk = warp_sum(gc[k]);
+            if ((tid & 31) == 0 && sk != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, sk);
         }
+    }
+    if (nq > 0) __syncthreads();  // blend[] / q_items are rewritten by the next tile
+}
+
+// antialias (gather form, dense pair queue) + losses; persistent over the dilated work list
+template <int PHASE>
+__global__ void __launch_bounds__(256) ham_aa_loss_kernel(
+    const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
+    int tiles_x, int tiles_y, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
+    const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
+    int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
+    float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
+    const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask) {
+    __shared__ uint32_t q_items[kPairQueue];
+    __shared__ int q_n[2];  // double-buffered: a fast warp may already enqueue for the next tile
+    __shared__ float blend[kTile * kTile][PHASE == 1 ? 4 : 6];
+    if (tile_tid() < 2) q_n[tile_tid()] = 0;
+    __syncthreads();
+    const int na = *acount;
+    int par = 0;
+    for (int it = blockIdx.x; it < na; it += gridDim.x, par ^= 1) {
+        const TileCtx tc = tile_decode(alist[it], tiles_x, tiles_y);
+        aa_loss_tile<PHASE>(tc, zbuf, pos, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
+                            plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items, q_n[par], blend);
     }
 }
 
@@ -394,72 +609,92 @@ __global__ void __launch_bounds__(256) ham_aa_loss_kernel(
 // interpolate bwd, rasterize bwd; everything lands in the per-vertex world-space accumulators.
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
-__global__ void __launch_bounds__(256) ham_pixel_bwd_kernel(
-    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+__device__ __forceinline__ void pixel_bwd_tile(
+    const TileCtx tc, const unsigned long long* __restrict__ zbuf,
+    const float4* __restrict__ pos, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
     const float* __restrict__ w2cs, const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
     const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
     const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
-    const float4* __restrict__ gplane1, float4* __restrict__ G) {
-    __shared__ ViewCtx ctx;
-    const int n = blockIdx.y;
-    const int view = __ldg(view_idx + n);
-    load_view_ctx(&ctx, w2cs, projs, sh_coeffs, view, __ldg(sh_idx + n));
-    __syncthreads();
+    const float4* __restrict__ gplane1, float4* __restrict__ G, ViewCtx& ctx, uint32_t* q_items, int& q_n,
+    float (*gblend)[3]) {
+    const int n = tc.n;
+    const int tid = tile_tid();
     const int hw = H * W;
-    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rem >= hw) return;
+    const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
+    const bool inb = px < W && py < H;
+    const int rem = py * W + px;
     const size_t base = (size_t)n * hw;
     const size_t pix = base + rem;
     const unsigned long long* zb = zbuf + base;
-    const NbrKeys self = decode_key(zb[rem]);
-    const int py = rem / W, px = rem - py * W;
+    NbrKeys self = decode_key(ZB_EMPTY);
+    if (inb) self = decode_key(zb[rem]);
     const float4* Pv = pos + (size_t)n * V;
     const float* P = reinterpret_cast<const float*>(Pv);
-    const bool covered = self.tri >= 0;
-    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-    if (covered) {
-        c0 = plane0[pix];
-        if (PHASE == 0) c1 = plane1[pix];
+    enqueue_pairs(zb, px, py, H, W, self, tid, q_items, &q_n);
+    __syncthreads();  // the only barrier of a tile without blend candidates (q_n is double-buffered by the caller)
+    const int nq = q_n;
+    if (nq > 0) {  // block-uniform
+        gblend[tid][0] = 0.0f; gblend[tid][1] = 0.0f; gblend[tid][2] = 0.0f;
+        __syncthreads();
     }
-    const float cov_self = covered ? 1.0f : 0.0f;
+    for (int e = tid; e < nq; e += kTile * kTile) {
+        const PairItem it = decode_pair_item(q_items[e], tc);
+        const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
+        const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
+        AAPair pr;
+        if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, P, tri, opp, V, T, H, W, pr)) continue;
+        const int recv = (pr.alpha > 0.0f) ? r0 : r1;
+        // phase B blends the shaded colour (gplane0.xyz) and coverage (gplane0.w); phase A the albedo (gplane1.xyz)
+        const float4 gr = (PHASE == 1) ? gplane0[base + recv] : gplane1[base + recv];
+        // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g
+        if (it.tid0 >= 0) {
+            atomicAdd(&gblend[it.tid0][0], -pr.alpha * gr.x);
+            atomicAdd(&gblend[it.tid0][1], -pr.alpha * gr.y);
+            atomicAdd(&gblend[it.tid0][2], -pr.alpha * gr.z);
+        }
+        if (it.tid1 >= 0) {
+            atomicAdd(&gblend[it.tid1][0], pr.alpha * gr.x);
+            atomicAdd(&gblend[it.tid1][1], pr.alpha * gr.y);
+            atomicAdd(&gblend[it.tid1][2], pr.alpha * gr.z);
+        }
+        if (PHASE == 1 && it.tid0 >= 0 && !pr.clamped) {
+            // position gradient: the block that owns the pair's first pixel scatters it
+            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = f0;
+            if (k0.tri >= 0) f0 = plane0[base + r0];
+            if (k1.tri >= 0) s0 = plane0[base + r1];
+            const float dd_img = gr.x * (s0.x - f0.x) + gr.y * (s0.y - f0.y) + gr.z * (s0.z - f0.z);
+            const float dd_msk = gr.w * ((k1.tri >= 0 ? 1.0f : 0.0f) - (k0.tri >= 0 ? 1.0f : 0.0f));
+            if (dd_img != 0.0f || dd_msk != 0.0f) {
+                float4 e1, e2;
+                aa_pos_grad(pr, it.qx, it.qy, it.d, P, H, W, 1.0f, e1, e2);
+                const float3 w1 = clip_to_world(ctx.M, e1.x, e1.y, e1.w);
+                const float3 w2 = clip_to_world(ctx.M, e2.x, e2.y, e2.w);
+                atomicAdd(G + 3 * (size_t)pr.i1, make_float4(dd_img * w1.x, dd_img * w1.y, dd_img * w1.z, dd_msk * w1.x));
+                atomicAdd(G + 3 * (size_t)pr.i1 + 1, make_float4(dd_msk * w1.y, dd_msk * w1.z, 0.f, 0.f));
+                atomicAdd(G + 3 * (size_t)pr.i2, make_float4(dd_img * w2.x, dd_img * w2.y, dd_img * w2.z, dd_msk * w2.x));
+                atomicAdd(G + 3 * (size_t)pr.i2 + 1, make_float4(dd_msk * w2.y, dd_msk * w2.z, 0.f, 0.f));
+            }
+        }
+    }
+    float3 gb = make_float3(0.f, 0.f, 0.f);
+    if (nq > 0) {
+        __syncthreads();
+        gb = make_float3(gblend[tid][0], gblend[tid][1], gblend[tid][2]);
+        if (tid == 0) q_n = 0;  // everyone has read nq; this counter is next used two tiles from now
+        __syncthreads();        // gblend[] / q_items are rewritten by the next tile
+    }
+    const bool covered = self.tri >= 0;
+    if (!inb || !covered) return;  // empty pixels have no upstream producer
     // gradient w.r.t. this pixel's PRE-antialias values: pass-through + pair terms
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-    if (covered) {  // empty pixels have no upstream producer
+    if (PHASE == 1) {
         g0 = gplane0[pix];
-        if (PHASE == 0) g1 = gplane1[pix];
+        g0.x += gb.x; g0.y += gb.y; g0.z += gb.z;
+    } else {
+        g1 = gplane1[pix];
+        g1.x += gb.x; g1.y += gb.y; g1.z += gb.z;
     }
-    for_each_pair(zb, px, py, H, W, P, tri, opp, V, T, self,
-                  [&](const AAPair& pr, int r_first, int r_second, int d, bool self_first, int qx, int qy) {
-                      const int recv = (pr.alpha > 0.0f) ? r_first : r_second;
-                      const float4 gr0 = gplane0[base + recv];
-                      float4 gr1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                      if (PHASE == 0) gr1 = gplane1[base + recv];
-                      // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g
-                      const float sg = self_first ? -pr.alpha : pr.alpha;
-                      g0.x += sg * gr0.x; g0.y += sg * gr0.y; g0.z += sg * gr0.z;
-                      if (PHASE == 0) { g1.x += sg * gr1.x; g1.y += sg * gr1.y; g1.z += sg * gr1.z; }
-                      if (PHASE == 1 && self_first && !pr.clamped) {
-                          // position gradient: the pair's first pixel owns the scatter
-                          const int orem = r_second;
-                          const bool ocov = decode_key(zb[orem]).tri >= 0;
-                          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                          if (ocov) o0 = plane0[base + orem];
-                          const float dd_img = gr0.x * (o0.x - c0.x) + gr0.y * (o0.y - c0.y) + gr0.z * (o0.z - c0.z);
-                          const float dd_msk = gr0.w * ((ocov ? 1.0f : 0.0f) - cov_self);
-                          if (dd_img != 0.0f || dd_msk != 0.0f) {
-                              float4 e1, e2;
-                              aa_pos_grad(pr, qx, qy, d, P, H, W, 1.0f, e1, e2);
-                              const float3 w1 = clip_to_world(ctx.M, e1.x, e1.y, e1.w);
-                              const float3 w2 = clip_to_world(ctx.M, e2.x, e2.y, e2.w);
-                              atomicAdd(G + 3 * (size_t)pr.i1, make_float4(dd_img * w1.x, dd_img * w1.y, dd_img * w1.z, dd_msk * w1.x));
-                              atomicAdd(G + 3 * (size_t)pr.i1 + 1, make_float4(dd_msk * w1.y, dd_msk * w1.z, 0.f, 0.f));
-                              atomicAdd(G + 3 * (size_t)pr.i2, make_float4(dd_img * w2.x, dd_img * w2.y, dd_img * w2.z, dd_msk * w2.x));
-                              atomicAdd(G + 3 * (size_t)pr.i2 + 1, make_float4(dd_msk * w2.y, dd_msk * w2.z, 0.f, 0.f));
-                          }
-                      }
-                  });
-    if (!covered) return;
     const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
     PixTri q;
     load_pixtri(self.tri, px, py, Pv, tri, invW, invH, q);
@@ -473,7 +708,7 @@ __global__ void __launch_bounds__(256) ham_pixel_bwd_kernel(
         return;
     }
     // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286)
-    if (!(c0.w > 0.0f)) return;
+    if (!self.valid) return;
     if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) return;
     const float3 m = interp3(normals, q);
     const float3 a = interp3(albedo, q);
@@ -535,12 +770,82 @@ __global__ void __launch_bounds__(256) ham_pixel_bwd_kernel(
     atomicAdd(G2 + 2, make_float4(w * gm.z, w * ga.x, w * ga.y, w * ga.z));
 }
 
-__global__ void ham_finalize_scalars_kernel(const double* __restrict__ acc, float* __restrict__ scal) {
+// pixel backward, persistent over the dilated work list
+template <int PHASE>
+__global__ void __launch_bounds__(256) ham_pixel_bwd_kernel(
+    const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
+    int tiles_x, int tiles_y, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
+    const float* __restrict__ w2cs, const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
+    const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
+    const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
+    const float4* __restrict__ gplane1, float4* __restrict__ G) {
+    __shared__ ViewCtx ctx;
+    __shared__ uint32_t q_items[kPairQueue];
+    __shared__ int q_n[2];  // double-buffered: a fast warp may already enqueue for the next tile
+    __shared__ float gblend[kTile * kTile][3];  // pair terms of d(loss)/d(pre-antialias colour | albedo)
+    if (tile_tid() < 2) q_n[tile_tid()] = 0;
+    const int na = *acount;
+    int par = 0, ctx_n = -1;
+    for (int it = blockIdx.x; it < na; it += gridDim.x, par ^= 1) {
+        const TileCtx tc = tile_decode(alist[it], tiles_x, tiles_y);
+        if (tc.n != ctx_n) {  // block-uniform: per-view matrices / SH row change rarely along the list
+            __syncthreads();
+            load_view_ctx(&ctx, w2cs, projs, sh_coeffs, __ldg(view_idx + tc.n), __ldg(sh_idx + tc.n));
+            __syncthreads();
+            ctx_n = tc.n;
+        }
+        pixel_bwd_tile<PHASE>(tc, zbuf, pos, tri, opp, normals, albedo, w2cs, projs, sh_coeffs, view_idx, sh_idx, V, T, H, W,
+                              plane0, plane1, gplane0, gplane1, G, ctx, q_items, q_n[par], gblend);
+    }
+}
+
+__global__ void ham_finalize_scalars_kernel(const double* __restrict__ acc, const double* __restrict__ view_vm2,
+                                            const int32_t* __restrict__ view_idx, int n_views, int tiles, int phase,
+                                            float* __restrict__ scal) {
     if (threadIdx.x == 0) {
-        scal[0] = (float)acc[0];
-        scal[1] = (float)acc[1];
-        scal[2] = (float)acc[2];
+        double vm2 = 0.0;  // sum of valid_mask^2 over the tiles no block visited = view totals - visited tiles
+        if (phase == 1) {
+            for (int n = 0; n < n_views; n++) vm2 += view_vm2[(size_t)view_idx[n] * (tiles + 1) + tiles];
+            vm2 -= acc_total(acc, 7);
+        }
+        scal[0] = (float)acc_total(acc, 0);
+        scal[1] = (float)acc_total(acc, 1);
+        scal[2] = (float)(acc_total(acc, 2) + vm2);
         scal[3] = 0.0f;
+    }
+}
+
+// view_vm2[view][tile] = sum of valid_mask^2 over the 16x16 tile, view_vm2[view][tiles] = sum over the view (constants
+// of the optimisation: valid_masks never change, mesh_sfs_optim.py:163).  The view total is the fp64 sum of the
+// tile sums, so "total - visited tiles" cancels exactly when every non-zero tile is visited.
+__global__ void __launch_bounds__(256) ham_view_vm2_kernel(const float* __restrict__ valid_masks, int H, int W,
+                                                           double* __restrict__ out) {
+    __shared__ double red[8];
+    const int view = blockIdx.z, tiles = gridDim.x * gridDim.y;
+    const int px = blockIdx.x * kTile + threadIdx.x, py = blockIdx.y * kTile + threadIdx.y;
+    double s = 0.0;
+    if (px < W && py < H) {
+        const float x = valid_masks[((size_t)view * H + py) * W + px];
+        s = (double)x * (double)x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int tid = tile_tid();
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        out[(size_t)view * (tiles + 1) + blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+__global__ void ham_view_vm2_total_kernel(int tiles, double* __restrict__ out) {
+    double* row = out + (size_t)blockIdx.x * (tiles + 1);
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < tiles; i++) t += row[i];
+        row[tiles] = t;
     }
 }
 
@@ -555,7 +860,7 @@ __global__ void __launch_bounds__(256) ham_export_rast_kernel(const unsigned lon
     const size_t pix = (size_t)n * hw + rem;
     const unsigned long long key = zbuf[pix];
     if (key == ZB_EMPTY) { rast[pix] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
-    const int t = (int)(uint32_t)key, py = rem / W, px = rem - py * W;
+    const int t = (int)((uint32_t)key & kTriMask), py = rem / W, px = rem - py * W;
     const float4* P = pos + (size_t)n * V;
     const Bary b = bary_at(__ldg(P + __ldg(tri + 3 * t)), __ldg(P + __ldg(tri + 3 * t + 1)),
                            __ldg(P + __ldg(tri + 3 * t + 2)), px, py, xd(1.0f, (float)W), xd(1.0f, (float)H));
@@ -567,39 +872,44 @@ __global__ void __launch_bounds__(256) ham_export_rast_kernel(const unsigned lon
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float3 ldf3(const float* p) { return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 
+// The vertex-domain kernels below use 8 lanes per vertex (kLPV): V is only ~50k, so one thread per vertex leaves the
+// GPU at <0.3 waves of latency-bound gather loops; splitting each vertex's ~6 neighbours / incident faces over 8 lanes
+// (shuffle-reduced) gives 8x the memory-level parallelism.
+constexpr int kLPV = 8;
+__device__ __forceinline__ float sub_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
 // pass 1: Laplacian forward for vertices and albedo, edge/delta losses, projector of the normal backward, Adam scalars
-__global__ void __launch_bounds__(128) ham_update_pass1_kernel(
+__global__ void __launch_bounds__(256) ham_update_pass1_kernel(
     fmhr_ham_config cfg, const float* __restrict__ vertices, const float* __restrict__ delta,
     const float* __restrict__ albedo, const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr,
     const int32_t* __restrict__ v2f_idx, const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx,
     const float* __restrict__ raw, const float* __restrict__ packed, float* __restrict__ yhat_v,
     float* __restrict__ yhat_a, float* __restrict__ gN, double* __restrict__ acc, int32_t* __restrict__ adam_step,
     float* __restrict__ adam_sc) {
-    __shared__ float red[4][4];
+    __shared__ float red[4][8];
     const int V = cfg.V;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
     float lv = 0.f, la = 0.f, le = 0.f, ld = 0.f;
+    float3 sv = make_float3(0.f, 0.f, 0.f), sa = sv, vi = sv;
+    int deg = 0;
     if (i < V) {
         const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
-        float3 sv = make_float3(0.f, 0.f, 0.f), sa = sv;
-        for (int j = b; j < e; j++) {
+        deg = e - b;
+        for (int j = b + sub; j < e; j += kLPV) {
             const size_t nb = 3 * (size_t)__ldg(v2v_idx + j);
             const float3 xv = ldf3(vertices + nb), xa_ = ldf3(albedo + nb);
             sv.x += xv.x; sv.y += xv.y; sv.z += xv.z;
             sa.x += xa_.x; sa.y += xa_.y; sa.z += xa_.z;
         }
-        const float invd = (e > b) ? 1.0f / (float)(e - b) : 0.0f;
-        const float3 vi = ldf3(vertices + 3 * (size_t)i), ai = ldf3(albedo + 3 * (size_t)i);
-        sv = make_float3(sv.x * invd - vi.x, sv.y * invd - vi.y, sv.z * invd - vi.z);
-        sa = make_float3(sa.x * invd - ai.x, sa.y * invd - ai.y, sa.z * invd - ai.z);
-        lv = sqrtf(sv.x * sv.x + sv.y * sv.y + sv.z * sv.z);
-        la = sqrtf(sa.x * sa.x + sa.y * sa.y + sa.z * sa.z);
-        const float iv = lv > 0.f ? 1.0f / lv : 0.f, ia = la > 0.f ? 1.0f / la : 0.f;
-        yhat_v[3 * (size_t)i] = sv.x * iv; yhat_v[3 * (size_t)i + 1] = sv.y * iv; yhat_v[3 * (size_t)i + 2] = sv.z * iv;
-        yhat_a[3 * (size_t)i] = sa.x * ia; yhat_a[3 * (size_t)i + 1] = sa.y * ia; yhat_a[3 * (size_t)i + 2] = sa.z * ia;
+        vi = ldf3(vertices + 3 * (size_t)i);
         // edge hinge (mesh_sfs_optim.py:296-302): every half-edge is seen from both of its endpoints -> weight 1/2
         const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
-        for (int j = fb; j < fe; j++) {
+        for (int j = fb + sub; j < fe; j += kLPV) {
             const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
 #pragma unroll
             for (int s = 1; s <= 2; s++) {
@@ -609,6 +919,19 @@ __global__ void __launch_bounds__(128) ham_update_pass1_kernel(
                 le += 0.5f * fminf(fmaxf(x, 0.0f), 1.0f);
             }
         }
+    }
+    sv.x = sub_sum(sv.x); sv.y = sub_sum(sv.y); sv.z = sub_sum(sv.z);
+    sa.x = sub_sum(sa.x); sa.y = sub_sum(sa.y); sa.z = sub_sum(sa.z);
+    if (i < V && sub == 0) {
+        const float invd = (deg > 0) ? 1.0f / (float)deg : 0.0f;
+        const float3 ai = ldf3(albedo + 3 * (size_t)i);
+        sv = make_float3(sv.x * invd - vi.x, sv.y * invd - vi.y, sv.z * invd - vi.z);
+        sa = make_float3(sa.x * invd - ai.x, sa.y * invd - ai.y, sa.z * invd - ai.z);
+        lv = sqrtf(sv.x * sv.x + sv.y * sv.y + sv.z * sv.z);
+        la = sqrtf(sa.x * sa.x + sa.y * sa.y + sa.z * sa.z);
+        const float iv = lv > 0.f ? 1.0f / lv : 0.f, ia = la > 0.f ? 1.0f / la : 0.f;
+        yhat_v[3 * (size_t)i] = sv.x * iv; yhat_v[3 * (size_t)i + 1] = sv.y * iv; yhat_v[3 * (size_t)i + 2] = sv.z * iv;
+        yhat_a[3 * (size_t)i] = sa.x * ia; yhat_a[3 * (size_t)i + 1] = sa.y * ia; yhat_a[3 * (size_t)i + 2] = sa.z * ia;
         const float3 di = ldf3(delta + 3 * (size_t)i);
         ld = di.x * di.x + di.y * di.y + di.z * di.z;
         // normal backward, step 1: through the normalisation (un-normalised photometric scale; linear, scaled later)
@@ -634,8 +957,10 @@ __global__ void __launch_bounds__(128) ham_update_pass1_kernel(
     }
     __syncthreads();
     if (threadIdx.x < 4) {
-        const float s = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
-        if (s != 0.0f) atomicAdd(acc + 3 + threadIdx.x, (double)s);
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += red[threadIdx.x][w];
+        if (s != 0.0f) atomicAdd(acc + (3 + threadIdx.x) * 32 + (blockIdx.x & 31), (double)s);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // Adam bias corrections (torch.optim.Adam defaults); which parameters step depends on the phase:
@@ -663,8 +988,8 @@ __device__ __forceinline__ float adam_update(float p, float g, float* m, float* 
     return p - step_size * (mm / denom);
 }
 
-// pass 2: gather every gradient term per vertex, then Adam on delta (phase B) and albedo
-__global__ void __launch_bounds__(128) ham_update_pass2_kernel(
+// pass 2: gather every gradient term per vertex (8 lanes each), then Adam on delta (phase B) and albedo
+__global__ void __launch_bounds__(256) ham_update_pass2_kernel(
     fmhr_ham_config cfg, const float* __restrict__ vertices, float* __restrict__ delta, float* __restrict__ albedo,
     const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr, const int32_t* __restrict__ v2f_idx,
     const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed,
@@ -672,7 +997,7 @@ __global__ void __launch_bounds__(128) ham_update_pass2_kernel(
     float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
     const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad) {
     const int V = cfg.V;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
     const float* scal = packed + 12 * (size_t)V;
     const float n_valid = scal[0];
     const float P_global = (float)cfg.n_views_global * (float)cfg.H * (float)cfg.W;
@@ -680,28 +1005,60 @@ __global__ void __launch_bounds__(128) ham_update_pass2_kernel(
     const float s_mask = 2.0f * cfg.mask_weight / P_global;              // F.mse_loss mean over n*H*W
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const float sfs = cfg.sfs_weight * scal[1] / (3.0f * n_valid);
-        const float lap = cfg.lap_weight * (float)(acc[3] / (double)V);
-        const float alb = cfg.albedo_weight * (float)(acc[4] / (double)V);
+        const float lap = cfg.lap_weight * (float)(acc_total(acc, 3) / (double)V);
+        const float alb = cfg.albedo_weight * (float)(acc_total(acc, 4) / (double)V);
         const float msk = cfg.phase == 1 ? cfg.mask_weight * scal[2] / P_global : 0.0f;
-        const float edg = cfg.edge_weight * (float)(acc[5] / (3.0 * (double)cfg.T));
-        const float del = cfg.delta_weight * (float)(acc[6] / (double)V);
+        const float edg = cfg.edge_weight * (float)(acc_total(acc, 5) / (3.0 * (double)cfg.T));
+        const float del = cfg.delta_weight * (float)(acc_total(acc, 6) / (double)V);
         losses[0] = sfs; losses[1] = cfg.phase == 1 ? lap : 0.0f; losses[2] = alb; losses[3] = msk;
         losses[4] = cfg.phase == 1 ? edg : 0.0f; losses[5] = cfg.phase == 1 ? del : 0.0f; losses[6] = n_valid;
         losses[7] = cfg.phase == 1 ? sfs + lap + alb + msk + edg + del : sfs;
     }
-    if (i >= V) return;
-    const float* Gi = packed + 12 * (size_t)i;
-    // Laplacian backward rows (L^T yhat) for vertices and albedo
-    float3 lv = make_float3(0.f, 0.f, 0.f), la = lv;
-    {
+    // Laplacian backward rows (L^T yhat) for vertices and albedo; normal backward + edge hinge over incident faces
+    float3 lv = make_float3(0.f, 0.f, 0.f), la = lv, gnb = lv, ge = lv, vi = lv;
+    if (i < V) {
         const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
-        for (int q = b; q < e; q++) {
+        for (int q = b + sub; q < e; q += kLPV) {
             const int j = __ldg(v2v_idx + q);
             const float invd = 1.0f / (float)(__ldg(v2v_ptr + j + 1) - __ldg(v2v_ptr + j));
-            const float3 yv = ldf3(yhat_v + 3 * (size_t)j), ya = ldf3(yhat_a + 3 * (size_t)j);
-            lv.x += yv.x * invd; lv.y += yv.y * invd; lv.z += yv.z * invd;
+            const float3 ya = ldf3(yhat_a + 3 * (size_t)j);
             la.x += ya.x * invd; la.y += ya.y * invd; la.z += ya.z * invd;
+            if (cfg.phase == 1) {
+                const float3 yv = ldf3(yhat_v + 3 * (size_t)j);
+                lv.x += yv.x * invd; lv.y += yv.y * invd; lv.z += yv.z * invd;
+            }
         }
+        if (cfg.phase == 1) {
+            vi = ldf3(vertices + 3 * (size_t)i);
+            const float3 gi = ldf3(gN + 3 * (size_t)i);
+            const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
+            for (int j = fb + sub; j < fe; j += kLPV) {
+                const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
+                const int ia = __ldg(tri + 3 * t + (k + 1) % 3), ib = __ldg(tri + 3 * t + (k + 2) % 3);
+                const float3 pa = ldf3(vertices + 3 * (size_t)ia), pb = ldf3(vertices + 3 * (size_t)ib);
+                const float3 ka = ldf3(gN + 3 * (size_t)ia), kb = ldf3(gN + 3 * (size_t)ib);
+                const float3 Gs = make_float3(gi.x + ka.x + kb.x, gi.y + ka.y + kb.y, gi.z + ka.z + kb.z);
+                const float3 ed = make_float3(pa.x - pb.x, pa.y - pb.y, pa.z - pb.z);
+                gnb.x += ed.y * Gs.z - ed.z * Gs.y; gnb.y += ed.z * Gs.x - ed.x * Gs.z; gnb.z += ed.x * Gs.y - ed.y * Gs.x;
+                const float3 o[2] = {pa, pb};
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const float dx = vi.x - o[s].x, dy = vi.y - o[s].y, dz = vi.z - o[s].z;
+                    const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
+                    if (x >= 0.0f && x <= 1.0f) { ge.x += 2.0f * dx; ge.y += 2.0f * dy; ge.z += 2.0f * dz; }
+                }
+            }
+        }
+    }
+    la.x = sub_sum(la.x); la.y = sub_sum(la.y); la.z = sub_sum(la.z);
+    if (cfg.phase == 1) {
+        lv.x = sub_sum(lv.x); lv.y = sub_sum(lv.y); lv.z = sub_sum(lv.z);
+        gnb.x = sub_sum(gnb.x); gnb.y = sub_sum(gnb.y); gnb.z = sub_sum(gnb.z);
+        ge.x = sub_sum(ge.x); ge.y = sub_sum(ge.y); ge.z = sub_sum(ge.z);
+    }
+    if (i >= V || sub != 0) return;
+    const float* Gi = packed + 12 * (size_t)i;
+    {
         const float3 yv = ldf3(yhat_v + 3 * (size_t)i), ya = ldf3(yhat_a + 3 * (size_t)i);
         const float iv = 1.0f / (float)V;
         lv = make_float3((lv.x - yv.x) * iv, (lv.y - yv.y) * iv, (lv.z - yv.z) * iv);
@@ -712,27 +1069,6 @@ __global__ void __launch_bounds__(128) ham_update_pass2_kernel(
     if (cfg.phase == 1) { ga.x += cfg.albedo_weight * la.x; ga.y += cfg.albedo_weight * la.y; ga.z += cfg.albedo_weight * la.z; }
     float3 gd = make_float3(0.f, 0.f, 0.f);
     if (cfg.phase == 1) {
-        const float3 vi = ldf3(vertices + 3 * (size_t)i);
-        // normal backward gather + edge hinge gradient over incident faces
-        float3 gnb = make_float3(0.f, 0.f, 0.f), ge = gnb;
-        const float3 gi = ldf3(gN + 3 * (size_t)i);
-        const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
-        for (int j = fb; j < fe; j++) {
-            const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
-            const int ia = __ldg(tri + 3 * t + (k + 1) % 3), ib = __ldg(tri + 3 * t + (k + 2) % 3);
-            const float3 pa = ldf3(vertices + 3 * (size_t)ia), pb = ldf3(vertices + 3 * (size_t)ib);
-            const float3 ka = ldf3(gN + 3 * (size_t)ia), kb = ldf3(gN + 3 * (size_t)ib);
-            const float3 Gs = make_float3(gi.x + ka.x + kb.x, gi.y + ka.y + kb.y, gi.z + ka.z + kb.z);
-            const float3 ed = make_float3(pa.x - pb.x, pa.y - pb.y, pa.z - pb.z);
-            gnb.x += ed.y * Gs.z - ed.z * Gs.y; gnb.y += ed.z * Gs.x - ed.x * Gs.z; gnb.z += ed.x * Gs.y - ed.y * Gs.x;
-            const float3 o[2] = {pa, pb};
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const float dx = vi.x - o[s].x, dy = vi.y - o[s].y, dz = vi.z - o[s].z;
-                const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
-                if (x >= 0.0f && x <= 1.0f) { ge.x += 2.0f * dx; ge.y += 2.0f * dy; ge.z += 2.0f * dz; }
-            }
-        }
         const float s_edge = cfg.edge_weight / (3.0f * (float)cfg.T);
         const float s_delta = 2.0f * cfg.delta_weight / (float)V;
         const float3 di = ldf3(delta + 3 * (size_t)i);
@@ -774,11 +1110,25 @@ __global__ void ham_update_sh_kernel(fmhr_ham_config cfg, const float* __restric
                                adam_sc[5]);
 }
 
+// persistent pixel kernels: 4 resident 256-thread blocks per SM (64 registers / thread)
+static int persistent_blocks() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        n = sms * 4;
+    }
+    return n;
+}
+
 static int check_cfg(const fmhr_ham_config* c) {
     FMHR_CHECK_ARG(c != nullptr);
     FMHR_CHECK_ARG(c->V > 0 && c->T > 0 && c->H > 0 && c->W > 0 && c->n_views > 0 && c->n_views_global >= c->n_views);
     FMHR_CHECK_ARG(c->phase == 0 || c->phase == 1);
     FMHR_CHECK_ARG(c->n_sh_rows >= 1);
+    FMHR_CHECK_ARG(c->zbuf_slot == 0 || c->zbuf_slot == 1);
+    FMHR_CHECK_ARG(c->T < (1 << 28));  // triangle id shares the key's low word with 4 tag bits
+    FMHR_CHECK_ARG(c->n_views < 4096 && c->W <= 16384 && c->H <= 16384);  // work-list entry = view:12 | ty:10 | tx:10
     FMHR_CHECK_ARG((long long)c->H * c->W < (1ll << 31));
     return FMHR_OK;
 }
@@ -801,7 +1151,7 @@ static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers*
     FMHR_CHECK_ARG(b != nullptr);
     FMHR_CHECK_ARG(b->tri && b->opp && b->v2f_ptr && b->v2f_idx && b->v2v_ptr && b->v2v_idx);
     FMHR_CHECK_ARG(b->vertices_tmp && b->delta && b->albedo && b->sh_coeffs && b->adam_m && b->adam_v && b->adam_step);
-    FMHR_CHECK_ARG(b->imgs && b->masks && b->valid_masks && b->w2cs && b->projs && b->view_idx);
+    FMHR_CHECK_ARG(b->imgs && b->masks && b->valid_masks && b->w2cs && b->projs && b->view_idx && b->view_vm2);
     FMHR_CHECK_ARG(b->packed && b->losses && b->workspace);
     FMHR_CHECK_ARG(b->workspace_bytes >= fmhr_ham_workspace_bytes(cfg));
     FMHR_CHECK_ARG(((uintptr_t)b->packed & 15) == 0 && ((uintptr_t)b->workspace & 255) == 0);
@@ -814,11 +1164,15 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     HamWs ws;
     ham_layout(cfg, (char*)b->workspace, &ws);
     const int V = cfg->V, T = cfg->T, H = cfg->H, W = cfg->W, n = cfg->n_views;
-    const size_t P = (size_t)n * H * W;
+    unsigned long long* zcur = ws.zbuf[cfg->zbuf_slot];
+    unsigned long long* znext = ws.zbuf[cfg->zbuf_slot ^ 1];
+    const int cur = cfg->zbuf_slot, nxt = cfg->zbuf_slot ^ 1;
+    const int tiles_x = cdiv(W, kTile), tiles_y = cdiv(H, kTile);
     const int32_t* sh_idx = b->sh_idx ? b->sh_idx : b->view_idx;
     FMHR_CUDA(cudaMemsetAsync(b->packed, 0, fmhr_ham_packed_floats(cfg) * sizeof(float), st));
-    FMHR_CUDA(cudaMemsetAsync(ws.acc, 0, 8 * sizeof(double), st));
-    FMHR_CUDA(cudaMemsetAsync(ws.zbuf, 0xFF, P * 8, st));
+    // zero: loss accumulators + dilated work list (common) and the work list of the slot rasterised this step
+    FMHR_CUDA(cudaMemsetAsync(ws.common_region, 0, ws.common_bytes, st));
+    FMHR_CUDA(cudaMemsetAsync(ws.slot_region[cfg->zbuf_slot], 0, ws.slot_bytes, st));
     if (PHASE == 0) FMHR_CUDA(cudaMemsetAsync(ws.gsh, 0, (size_t)cfg->n_sh_rows * 9 * sizeof(float), st));
     FMHR_STAGE_MARK();  // 0: clears
     ham_vertex_prep_kernel<<<cdiv(3 * V, 256), 256, 0, st>>>(b->vertices_tmp, b->delta, 3 * V, ws.vertices);
@@ -826,34 +1180,64 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     int rc = launch_vertex_normals_fwd(ws.vertices, b->tri, b->v2f_ptr, b->v2f_idx, V, ws.normals, ws.raw, st);
     if (rc) return rc;
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
-    ham_transform_kernel<<<dim3(cdiv(V, 256), n), 256, 0, st>>>(ws.vertices, b->w2cs, b->projs, b->view_idx, V, ws.pos);
+    ham_transform_kernel<<<dim3(cdiv(V, 256), n), 256, 0, st>>>(ws.vertices, b->w2cs, b->projs, b->view_idx, V, H, W,
+                                                                ws.pos, ws.snap);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 2: transform
-    rc = launch_raster_coverage((const float*)ws.pos, b->tri, n, V, T, H, W, ws.zbuf, st);
+    rc = launch_raster_coverage_snapped(ws.pos, ws.snap, b->tri, n, V, T, H, W, zcur, ws.tbits[cur], ws.tlist[cur],
+                                        ws.tcount[cur], tiles_x, tiles_x * tiles_y, st);
     if (rc) return rc;
     FMHR_STAGE_MARK();  // 3: coverage
-    const dim3 pgrid(cdiv((long long)H * W, 256), n);
-    ham_shade_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, ws.normals, b->albedo, b->masks,
-                                                   b->sh_coeffs, b->view_idx, sh_idx, V, H, W, ws.plane[0],
-                                                   ws.plane[1], ws.acc);
+    const dim3 pgrid(persistent_blocks()), pblock(kTile, kTile);
+    ham_shade_kernel<PHASE><<<pgrid, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt],
+                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
+                                                      b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W,
+                                                      ws.plane[0], ws.plane[1], ws.acc);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 4: shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    ham_aa_loss_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, b->opp, b->imgs, b->valid_masks,
+    ham_aa_loss_kernel<PHASE><<<pgrid, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, b->imgs, b->valid_masks,
                                                      b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
-                                                     ws.plane[1], g0, g1, ws.acc, ws.gsh, dbg_image, dbg_mask);
+                                                     ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
-        ham_pixel_bwd_kernel<PHASE><<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
+        ham_pixel_bwd_kernel<PHASE><<<pgrid, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
                                                            b->w2cs, b->projs, b->sh_coeffs, b->view_idx, sh_idx, V, T,
                                                            H, W, ws.plane[0], ws.plane[1], g0, g1, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
     }
-    ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->packed + 12 * (size_t)V);
+    ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,
+                                                  b->packed + 12 * (size_t)V);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(buf && buf->workspace && buf->workspace_bytes >= fmhr_ham_workspace_bytes(cfg));
+    HamWs ws;
+    ham_layout(cfg, (char*)buf->workspace, &ws);
+    const size_t P = (size_t)cfg->n_views * cfg->H * cfg->W;
+    for (int i = 0; i < 2; i++) {
+        FMHR_CUDA(cudaMemsetAsync(ws.zbuf[i], 0xFF, P * 8, (cudaStream_t)stream));
+        FMHR_CUDA(cudaMemsetAsync(ws.slot_region[i], 0, ws.slot_bytes, (cudaStream_t)stream));
+    }
+    FMHR_CUDA(cudaMemsetAsync(ws.common_region, 0, ws.common_bytes, (cudaStream_t)stream));
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_prepare_views(const float* valid_masks, int num, int H, int W, double* view_vm2,
+                                      fmhr_stream_t stream) {
+    FMHR_CHECK_ARG(valid_masks && view_vm2 && num > 0 && H > 0 && W > 0);
+    const int tx = cdiv(W, kTile), ty = cdiv(H, kTile);
+    ham_view_vm2_kernel<<<dim3(tx, ty, num), dim3(kTile, kTile), 0, (cudaStream_t)stream>>>(valid_masks, H, W, view_vm2);
+    FMHR_LAUNCH_CHECK();
+    ham_view_vm2_total_kernel<<<num, 32, 0, (cudaStream_t)stream>>>(tx * ty, view_vm2);
+    FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }
 
@@ -876,12 +1260,12 @@ extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_b
     HamWs ws;
     ham_layout(cfg, (char*)buf->workspace, &ws);
     const int V = cfg->V;
-    ham_update_pass1_kernel<<<cdiv(V, 128), 128, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
+    ham_update_pass1_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
                                                           buf->v2f_ptr, buf->v2f_idx, buf->v2v_ptr, buf->v2v_idx,
                                                           ws.raw, buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, ws.acc,
                                                           buf->adam_step, ws.adam_sc);
     FMHR_LAUNCH_CHECK();
-    ham_update_pass2_kernel<<<cdiv(V, 128), 128, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
+    ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
                                                           buf->v2f_ptr, buf->v2f_idx, buf->v2v_ptr, buf->v2v_idx,
                                                           buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, buf->adam_m,
                                                           buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad);
@@ -938,7 +1322,8 @@ extern "C" int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_
     if (normals) FMHR_CUDA(cudaMemcpyAsync(normals, ws.normals, (size_t)cfg->V * 12, cudaMemcpyDeviceToDevice, st));
     if (rast) {
         const dim3 pgrid(cdiv((long long)cfg->H * cfg->W, 256), cfg->n_views);
-        ham_export_rast_kernel<<<pgrid, 256, 0, st>>>(ws.zbuf, ws.pos, buf->tri, cfg->V, cfg->H, cfg->W, (float4*)rast);
+        ham_export_rast_kernel<<<pgrid, 256, 0, st>>>(ws.zbuf[cfg->zbuf_slot], ws.pos, buf->tri, cfg->V, cfg->H, cfg->W,
+                                                      (float4*)rast);
         FMHR_LAUNCH_CHECK();
     }
     return FMHR_OK;
@@ -960,6 +1345,8 @@ extern "C" int fmhr_ham_step_host(const fmhr_ham_config* cfg, const fmhr_ham_buf
     FMHR_CUDA(cudaMemcpyAsync((void*)buf->valid_masks, valid_masks_host, n * hw * sizeof(float), cudaMemcpyHostToDevice, st));
     FMHR_CUDA(cudaMemcpyAsync((void*)buf->w2cs, w2cs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
     FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = fmhr_ham_prepare_views(buf->valid_masks, (int)n, cfg->H, cfg->W, (double*)buf->view_vm2, stream);
+    if (rc) return rc;
     rc = fmhr_ham_step_render(cfg, buf, stream);
     if (rc) return rc;
     rc = fmhr_ham_step_update(cfg, buf, stream);

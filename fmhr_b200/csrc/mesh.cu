@@ -91,22 +91,32 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
 }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
-__global__ void __launch_bounds__(128) vertex_normals_fwd_kernel(const float* __restrict__ verts,
+// 8 lanes per vertex: each lane takes every 8th incident face, partial sums are shuffle-reduced (V ~ 50k alone would
+// leave the GPU at a fraction of a wave of latency-bound gather loops).
+__global__ void __launch_bounds__(256) vertex_normals_fwd_kernel(const float* __restrict__ verts,
                                                                  const int32_t* __restrict__ tri,
                                                                  const int32_t* __restrict__ v2f_ptr,
                                                                  const int32_t* __restrict__ v2f_idx, int V,
                                                                  float* __restrict__ normals, float* __restrict__ raw) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V) return;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
     float3 acc = make_float3(0.f, 0.f, 0.f);
-    const int b = __ldg(v2f_ptr + i), e = __ldg(v2f_ptr + i + 1);
-    const float3 pk = ld3(verts + 3 * (size_t)i);
-    for (int j = b; j < e; j++) {
-        const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
-        const int ia = __ldg(tri + 3 * t + (k + 1) % 3), ib = __ldg(tri + 3 * t + (k + 2) % 3);
-        // corner-k form of the face normal, models/utils.py:517-543
-        acc = add3(acc, cross3(sub3(ld3(verts + 3 * (size_t)ia), pk), sub3(ld3(verts + 3 * (size_t)ib), pk)));
+    if (i < V) {
+        const int b = __ldg(v2f_ptr + i), e = __ldg(v2f_ptr + i + 1);
+        const float3 pk = ld3(verts + 3 * (size_t)i);
+        for (int j = b + sub; j < e; j += 8) {
+            const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
+            const int ia = __ldg(tri + 3 * t + (k + 1) % 3), ib = __ldg(tri + 3 * t + (k + 2) % 3);
+            // corner-k form of the face normal, models/utils.py:517-543
+            acc = add3(acc, cross3(sub3(ld3(verts + 3 * (size_t)ia), pk), sub3(ld3(verts + 3 * (size_t)ib), pk)));
+        }
     }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    }
+    if (i >= V || sub != 0) return;
     const float len = sqrtf(dot3(acc, acc));
     const float inv = 1.0f / fmaxf(len, 1e-6f);
     if (raw) { raw[3 * (size_t)i] = acc.x; raw[3 * (size_t)i + 1] = acc.y; raw[3 * (size_t)i + 2] = acc.z; }
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(256) ncc_fwd_kernel(const float* __restrict__ 
 // exported to ham.cu
 int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
                               int V, float* normals, float* raw, cudaStream_t st) {
-    vertex_normals_fwd_kernel<<<cdiv(V, 128), 128, 0, st>>>(verts, tri, v2f_ptr, v2f_idx, V, normals, raw);
+    vertex_normals_fwd_kernel<<<cdiv((long long)V * 8, 256), 256, 0, st>>>(verts, tri, v2f_ptr, v2f_idx, V, normals, raw);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

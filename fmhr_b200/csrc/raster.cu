@@ -9,20 +9,6 @@
 
 namespace fmhr {
 
-constexpr float kGuard = 16384.0f;
-
-// clip -> 24.8 fixed-point window coordinates; rejects triangles outside the clip volume / guard band.
-__device__ __forceinline__ bool snap_vertex(const float4 p, float hw, float hh, int& X, int& Y) {
-    if (!(p.w > 0.0f)) return false;
-    if (!(p.z >= -p.w && p.z <= p.w)) return false;
-    float sx = xa(xm(xd(p.x, p.w), hw), hw);
-    float sy = xa(xm(xd(p.y, p.w), hh), hh);
-    if (!(fabsf(sx) <= kGuard) || !(fabsf(sy) <= kGuard)) return false;
-    X = __float2int_rn(xm(sx, 256.0f));
-    Y = __float2int_rn(xm(sy, 256.0f));
-    return true;
-}
-
 __device__ __forceinline__ bool owns_edge(long long dx, long long dy) { return dy > 0 || (dy == 0 && dx > 0); }
 
 template <typename I>
@@ -50,6 +36,139 @@ __device__ __forceinline__ void cover_bbox(int X0, int Y0, int X1, int Y1, int X
             e0 -= dy0 * 256;
             e1 -= dy1 * 256;
             e2 -= dy2 * 256;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coverage for the fused HAM path.
+//  * vertices were snapped once per (view, vertex) by the transform kernel, so the per-triangle work before the
+//    (usually failing) bounding-box test is three 8-byte gathers and integer min/max;
+//  * the nested bounding-box loops only TEST pixel centres; every hit is pushed to a per-warp shared-memory queue and
+//    the expensive part (three float4 position gathers, perspective barycentric depth with two IEEE divides, the 64-bit
+//    atomicMin) then runs once per fragment with the queue spread over all 32 lanes.  With ~0.3 fragments per triangle
+//    the in-loop version executed that ~120-instruction body up to four times per warp at ~10 % lane utilisation;
+//  * tile hits are collected in a per-block shared-memory bitmap; at block end the tiles not yet in the slot's global
+//    bitmap are appended to its work list (a few atomics per block instead of one store per fragment).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFragQueue = 96;  // per-warp capacity; overflowing fragments are resolved in place
+
+__device__ __forceinline__ void resolve_fragment(const float4* __restrict__ P, const int32_t* __restrict__ tri, int t,
+                                                 int px, int py, int W, float invW, float invH,
+                                                 unsigned long long* __restrict__ zb) {
+    const float4 p0 = __ldg(P + __ldg(tri + 3 * t)), p1 = __ldg(P + __ldg(tri + 3 * t + 1)),
+                 p2 = __ldg(P + __ldg(tri + 3 * t + 2));
+    const Bary b = bary_at(p0, p1, p2, px, py, invW, invH);
+    atomicMin(&zb[(size_t)py * W + px], ((unsigned long long)depth_key(b.zw) << 32) | (uint32_t)t);
+}
+
+template <typename I>
+__device__ __forceinline__ void cover_bbox_queue(int X0, int Y0, int X1, int Y1, int X2, int Y2, int px0, int px1,
+                                                 int py0, int py1, const float4* __restrict__ P,
+                                                 const int32_t* __restrict__ tri, int W, float invW, float invH,
+                                                 unsigned long long* __restrict__ zb, unsigned int* tbits, int tiles_x,
+                                                 int t, int* qcount, uint2* queue) {
+    const I dx0 = X2 - X1, dy0 = Y2 - Y1;
+    const I dx1 = X0 - X2, dy1 = Y0 - Y2;
+    const I dx2 = X1 - X0, dy2 = Y1 - Y0;
+    const I b0 = owns_edge(dx0, dy0) ? 1 : 0, b1 = owns_edge(dx1, dy1) ? 1 : 0, b2 = owns_edge(dx2, dy2) ? 1 : 0;
+    const int Cx0 = px0 * 256 + 128;
+    for (int py = py0; py <= py1; py++) {
+        const int Cy = py * 256 + 128;
+        I e0 = dx0 * (I)(Cy - Y1) - dy0 * (I)(Cx0 - X1);
+        I e1 = dx1 * (I)(Cy - Y2) - dy1 * (I)(Cx0 - X2);
+        I e2 = dx2 * (I)(Cy - Y0) - dy2 * (I)(Cx0 - X0);
+        for (int px = px0; px <= px1; px++) {
+            if (e0 + b0 > 0 && e1 + b1 > 0 && e2 + b2 > 0) {
+                const int tile = (py >> 4) * tiles_x + (px >> 4);
+                atomicOr(tbits + (tile >> 5), 1u << (tile & 31));
+                const int slot = atomicAdd(qcount, 1);
+                if (slot < kFragQueue) queue[slot] = make_uint2((uint32_t)t, ((uint32_t)py << 16) | (uint32_t)px);
+                else resolve_fragment(P, tri, t, px, py, W, invW, invH, zb);  // large triangles only
+            }
+            e0 -= dy0 * 256;
+            e1 -= dy1 * 256;
+            e2 -= dy2 * 256;
+        }
+    }
+}
+
+__device__ __forceinline__ void coverage_snapped_one(const float4* __restrict__ P, const int2* __restrict__ S,
+                                                     const int32_t* __restrict__ tri, int V, int H, int W, int t,
+                                                     float invW, float invH, unsigned long long* __restrict__ zb,
+                                                     unsigned int* tbits, int tiles_x, int* qcount, uint2* queue) {
+    const int i0 = __ldg(tri + 3 * t), i1 = __ldg(tri + 3 * t + 1), i2 = __ldg(tri + 3 * t + 2);
+    if ((unsigned)i0 >= (unsigned)V || (unsigned)i1 >= (unsigned)V || (unsigned)i2 >= (unsigned)V) return;
+    const int2 s0 = __ldg(S + i0), s1 = __ldg(S + i1), s2 = __ldg(S + i2);
+    if (s0.x == kSnapRejected || s1.x == kSnapRejected || s2.x == kSnapRejected) return;
+    int X0 = s0.x, Y0 = s0.y, X1 = s1.x, Y1 = s1.y, X2 = s2.x, Y2 = s2.y;
+    const int minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
+    const int minY = min(Y0, min(Y1, Y2)), maxY = max(Y0, max(Y1, Y2));
+    const int px0 = max(0, (minX - 128 + 255) >> 8), px1 = min(W - 1, (maxX - 128) >> 8);
+    const int py0 = max(0, (minY - 128 + 255) >> 8), py1 = min(H - 1, (maxY - 128) >> 8);
+    if (px0 > px1 || py0 > py1) return;  // no pixel centre in the bounding box: the common case
+    const bool small = (maxX - minX) < 32768 && (maxY - minY) < 32768 && px1 < 65536 && py1 < 65536;
+    bool neg;
+    if (small) {
+        const int a = (X1 - X0) * (Y2 - Y0) - (X2 - X0) * (Y1 - Y0);  // |factors| < 2^15: exact in 32 bits
+        if (a == 0) return;
+        neg = a < 0;
+    } else {
+        const long long a = (long long)(X1 - X0) * (Y2 - Y0) - (long long)(X2 - X0) * (Y1 - Y0);
+        if (a == 0) return;
+        neg = a < 0;
+    }
+    if (neg) {  // orient for coverage only; barycentrics keep the original vertex order
+        int tx = X1; X1 = X2; X2 = tx;
+        int ty = Y1; Y1 = Y2; Y2 = ty;
+    }
+    if (small) cover_bbox_queue<int>(X0, Y0, X1, Y1, X2, Y2, px0, px1, py0, py1, P, tri, W, invW, invH, zb, tbits, tiles_x, t, qcount, queue);
+    else cover_bbox_queue<long long>(X0, Y0, X1, Y1, X2, Y2, px0, px1, py0, py1, P, tri, W, invW, invH, zb, tbits, tiles_x, t, qcount, queue);
+}
+
+__global__ void __launch_bounds__(256) raster_coverage_snapped_kernel(const float4* __restrict__ pos,
+                                                                      const int2* __restrict__ snap,
+                                                                      const int32_t* __restrict__ tri, int V, int T,
+                                                                      int H, int W,
+                                                                      unsigned long long* __restrict__ zbuf,
+                                                                      uint32_t* __restrict__ gbits,
+                                                                      uint32_t* __restrict__ glist,
+                                                                      int* __restrict__ gcount, int tiles_x,
+                                                                      int tiles_per_view) {
+    extern __shared__ unsigned int tbits[];  // (tiles_per_view + 31) / 32 words
+    __shared__ uint2 queue[8][kFragQueue];
+    __shared__ int qcount[8];
+    const int words = (tiles_per_view + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) qcount[warp] = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
+    unsigned long long* zb = zbuf + (size_t)n * H * W;
+    const float4* P = pos + (size_t)n * V;
+    if (t < T)
+        coverage_snapped_one(P, snap + (size_t)n * V, tri, V, H, W, t, invW, invH, zb, tbits, tiles_x, &qcount[warp],
+                             queue[warp]);
+    __syncwarp();
+    const int nq = min(qcount[warp], kFragQueue);
+    for (int e = lane; e < nq; e += 32) {
+        const uint2 f = queue[warp][e];
+        resolve_fragment(P, tri, (int)f.x, (int)(f.y & 0xffffu), (int)(f.y >> 16), W, invW, invH, zb);
+    }
+    __syncthreads();
+    // flush: tiles this block touched first (global bitmap de-duplicates) are appended to the slot's work list
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        const unsigned int bits = tbits[w];
+        if (bits == 0) continue;
+        unsigned int fresh = bits & ~atomicOr(gbits + (size_t)n * words + w, bits);
+        while (fresh) {
+            const int bit = __ffs(fresh) - 1;
+            fresh &= fresh - 1;
+            const int tile = (w << 5) + bit;
+            const int by = tile / tiles_x, bx = tile - by * tiles_x;
+            glist[atomicAdd(gcount, 1)] = ((uint32_t)n << 20) | ((uint32_t)by << 10) | (uint32_t)bx;
         }
     }
 }
@@ -182,6 +301,21 @@ int launch_raster_coverage(const float* pos, const int32_t* tri, int N, int V, i
                            unsigned long long* zbuf, cudaStream_t st) {
     dim3 grid(cdiv(T, 256), N);
     raster_coverage_kernel<<<grid, 256, 0, st>>>(pos, tri, V, T, H, W, zbuf);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
+int launch_raster_coverage_snapped(const float4* pos, const int2* snap, const int32_t* tri, int N, int V, int T, int H,
+                                   int W, unsigned long long* zbuf, uint32_t* tbits, uint32_t* tlist, int* tcount,
+                                   int tiles_x, int tiles_per_view, cudaStream_t st) {
+    dim3 grid(cdiv(T, 256), N);
+    const size_t smem = (size_t)((tiles_per_view + 31) / 32) * sizeof(unsigned int);
+    if (smem > 48 * 1024) {
+        set_error("launch_raster_coverage_snapped: %d tiles per view exceed the shared-memory bitmap", tiles_per_view);
+        return FMHR_EUNSUPPORTED;
+    }
+    raster_coverage_snapped_kernel<<<grid, 256, smem, st>>>(pos, snap, tri, V, T, H, W, zbuf, tbits, tlist, tcount,
+                                                            tiles_x, tiles_per_view);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

@@ -45,6 +45,10 @@ class HamOptimizer:
         self.adam_step = torch.zeros(4, dtype=torch.int32, device=dev)
         self.packed = torch.zeros(12 * self.V + 4, dtype=torch.float32, device=dev)
         self.losses = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.n_tiles = ((self.W + 15) // 16) * ((self.H + 15) // 16)
+        self.view_vm2 = torch.zeros(self.num, self.n_tiles + 1, dtype=torch.float64, device=dev)
+        check(self.lib.fmhr_ham_prepare_views(ptr(self.valid_masks), self.num, self.H, self.W, ptr(self.view_vm2), stream()),
+              "ham_prepare_views")
         self.workspace = None
         self.pg = process_group
         self.world = 1
@@ -59,6 +63,8 @@ class HamOptimizer:
         self.use_graphs = bool(use_graphs) and not debug
         self._graphs = {}
         self._struct_cache = {}
+        self._zb_layout = None
+        self._zb_slot = 0
 
     # ------------------------------------------------------------------ reference-shaped accessors
     @property
@@ -81,6 +87,7 @@ class HamOptimizer:
         cfg.n_views_global = self.n_views_global_override or n_views * self.world
         cfg.phase = phase
         cfg.n_sh_rows = self.num
+        cfg.zbuf_slot = 0
         cfg.sfs_weight, cfg.lap_weight = c["sfs_weight"], c["lap_weight"]
         cfg.albedo_weight = c["albedo_weight"] if albedo_weight is None else albedo_weight
         cfg.mask_weight, cfg.edge_weight, cfg.delta_weight = c["mask_weight"], c["edge_weight"], c["delta_weight"]
@@ -89,7 +96,8 @@ class HamOptimizer:
         cfg.edge_length_mean = self.edge_length_mean
         return cfg
 
-    def _buffers(self, cfg, view_idx, imgs=None, masks=None, valid_masks=None, w2cs=None, projs=None, sh_idx=None):
+    def _buffers(self, cfg, view_idx, imgs=None, masks=None, valid_masks=None, w2cs=None, projs=None, sh_idx=None,
+                 view_vm2=None):
         need = self.lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg))
         if need == 0:
             raise RuntimeError("fmhr_b200: invalid HAM configuration")
@@ -106,6 +114,7 @@ class HamOptimizer:
         b.imgs = ptr(self.imgs if imgs is None else imgs)
         b.masks = ptr(self.masks if masks is None else masks)
         b.valid_masks = ptr(self.valid_masks if valid_masks is None else valid_masks)
+        b.view_vm2 = ptr(self.view_vm2 if view_vm2 is None else view_vm2)
         b.w2cs = ptr(self.w2cs if w2cs is None else w2cs)
         b.projs = ptr(self.projs if projs is None else projs)
         b.view_idx = ptr(view_idx)
@@ -117,6 +126,17 @@ class HamOptimizer:
             self.dbg_grad_sh = torch.zeros(self.num, 9, dtype=torch.float32, device=self.device)
         b.dbg_grad_sh = ptr(self.dbg_grad_sh if (self.debug and cfg.phase == 0) else None)
         return b
+
+    def _prepare_zbuf(self, cfg, buf):
+        """The fused step rasterises z-buffer slot `cfg.zbuf_slot` and resets the other one for the next step, so the
+        slot alternates every render; both slots are reset whenever the workspace layout changes."""
+        layout = (cfg.n_views, cfg.phase == 0, self.workspace.data_ptr())
+        if layout != self._zb_layout:
+            check(self.lib.fmhr_ham_reset(ctypes.byref(cfg), ctypes.byref(buf), stream()), "ham_reset")
+            self._zb_layout = layout
+            self._zb_slot = 0
+        cfg.zbuf_slot = self._zb_slot
+        self._zb_slot ^= 1
 
     def _views(self, view_idx):
         if torch.is_tensor(view_idx):
@@ -145,6 +165,7 @@ class HamOptimizer:
         cfg, buf = cb[0], cb[1]
         if torch.cuda.current_device() != self.device.index:
             torch.cuda.set_device(self.device)
+        self._prepare_zbuf(cfg, buf)
         sp = stream()
         check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_render")
         if self.world > 1:
@@ -153,60 +174,75 @@ class HamOptimizer:
         return self.losses
 
     def _step_graph(self, phase, view_idx, albedo_weight):
-        """CUDA-graph replay of the iteration: the ~14 launches + memsets of render/update are captured once per
-        (phase, batch size, albedo_weight) and replayed with one launch; the step's view indices are copied into a
-        persistent device buffer the captured kernels read.  With more than one rank the NCCL all-reduce runs eagerly
-        between the two captured halves."""
+        """CUDA-graph replay of the iteration: the launches + memsets of render/update are captured once per
+        (phase, batch size, albedo_weight, z-buffer slot) and replayed with one launch; the step's view indices are
+        copied into a persistent device buffer the captured kernels read.  With more than one rank the NCCL all-reduce
+        runs eagerly between the two captured halves."""
         n = view_idx.numel() if torch.is_tensor(view_idx) else len(view_idx)
         key = (phase, n, None if albedo_weight is None else float(albedo_weight))
-        g = self._graphs.get(key)
-        if g is None:
-            slot = torch.zeros(n, dtype=torch.int32, device=self.device)
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._capture(phase, n, albedo_weight, view_idx)
+            self._graphs[key] = ent
+        graphs, idx_buf, ws_ptr, cfgs, bufs = ent
+        if self.workspace.data_ptr() != ws_ptr:
+            raise RuntimeError("fmhr_b200: workspace was reallocated after graph capture")
+        layout = (n, phase == 0, ws_ptr)
+        if layout != self._zb_layout:
+            check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), stream()), "ham_reset")
+            self._zb_layout = layout
+            self._zb_slot = 0
+        slot = self._zb_slot
+        self._zb_slot ^= 1
+        vi = self._views(view_idx)
+        if vi.data_ptr() != idx_buf.data_ptr():
+            idx_buf.copy_(vi, non_blocking=True)
+        graphs[slot][0].replay()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.packed, group=self.pg)
+            graphs[slot][1].replay()
+        return self.losses
+
+    def _capture(self, phase, n, albedo_weight, view_idx):
+        idx_buf = torch.zeros(n, dtype=torch.int32, device=self.device)
+        cfgs, bufs = [], []
+        for slot in (0, 1):
             cfg = self._cfg(n, phase, albedo_weight)
-            buf = self._buffers(cfg, slot)
-            ws_ptr = self.workspace.data_ptr()
-            slot.copy_(self._views(view_idx))
-            # state touched by a trial run is restored so that capture does not advance the optimiser
-            saved = [t.clone() for t in (self.delta, self.albedo, self.sh_coeffs, self.adam_m, self.adam_v, self.adam_step)]
-            torch.cuda.synchronize(self.device)
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            graphs = []
-            with torch.cuda.stream(side):
-                sp = _lib.c_p(side.cuda_stream)
-                for fn, name in ((self.lib.fmhr_ham_step_render, "ham_step_render"), (self.lib.fmhr_ham_step_update, "ham_step_update")):
-                    check(fn(ctypes.byref(cfg), ctypes.byref(buf), sp), name)  # warm-up outside capture
-                side.synchronize()
-                if self.world == 1:
+            cfg.zbuf_slot = slot
+            cfgs.append(cfg)
+            bufs.append(self._buffers(cfg, idx_buf))
+        ws_ptr = self.workspace.data_ptr()
+        idx_buf.copy_(self._views(view_idx))
+        state = (self.delta, self.albedo, self.sh_coeffs, self.adam_m, self.adam_v, self.adam_step)
+        saved = [t.clone() for t in state]  # the warm-up runs below must not advance the optimiser
+        calls = ((self.lib.fmhr_ham_step_render, "ham_step_render"), (self.lib.fmhr_ham_step_update, "ham_step_update"))
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        graphs = [[], []]
+        with torch.cuda.stream(side):
+            sp = _lib.c_p(side.cuda_stream)
+            check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), sp), "ham_reset")
+            for slot in (0, 1):  # warm-up outside capture (lazy module loading), slot 0 then 1 keeps the buffers sane
+                for fn, name in calls:
+                    check(fn(ctypes.byref(cfgs[slot]), ctypes.byref(bufs[slot]), sp), name)
+            side.synchronize()
+            for slot in (0, 1):
+                groups = [calls] if self.world == 1 else [calls[:1], calls[1:]]
+                for grp in groups:
                     gr = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gr, stream=side):
                         sp2 = _lib.c_p(torch.cuda.current_stream(self.device).cuda_stream)
-                        check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp2), "ham_step_render")
-                        check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), sp2), "ham_step_update")
-                    graphs = [gr]
-                else:
-                    for fn, name in ((self.lib.fmhr_ham_step_render, "ham_step_render"), (self.lib.fmhr_ham_step_update, "ham_step_update")):
-                        gr = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(gr, stream=side):
-                            sp2 = _lib.c_p(torch.cuda.current_stream(self.device).cuda_stream)
-                            check(fn(ctypes.byref(cfg), ctypes.byref(buf), sp2), name)
-                        graphs.append(gr)
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            for t, sv in zip((self.delta, self.albedo, self.sh_coeffs, self.adam_m, self.adam_v, self.adam_step), saved):
-                t.copy_(sv)
-            g = (graphs, slot, ws_ptr, cfg, buf)
-            self._graphs[key] = g
-        graphs, slot, ws_ptr, _, _ = g
-        if self.workspace.data_ptr() != ws_ptr:
-            raise RuntimeError("fmhr_b200: workspace was reallocated after graph capture")
-        vi = self._views(view_idx)
-        if vi.data_ptr() != slot.data_ptr():
-            slot.copy_(vi, non_blocking=True)
-        graphs[0].replay()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.packed, group=self.pg)
-            graphs[1].replay()
-        return self.losses
+                        for fn, name in grp:
+                            check(fn(ctypes.byref(cfgs[slot]), ctypes.byref(bufs[slot]), sp2), name)
+                    graphs[slot].append(gr)
+            check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), sp), "ham_reset")
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        for t, sv in zip(state, saved):
+            t.copy_(sv)
+        self._zb_layout = (n, phase == 0, ws_ptr)
+        self._zb_slot = 0
+        return graphs, idx_buf, ws_ptr, cfgs, bufs
 
     # ------------------------------------------------------------------ the two loops' bodies
     def step_phase_a(self, view_idx):
@@ -234,6 +270,7 @@ class HamOptimizer:
         acc = [0.0] * len(self.STAGES)
         with torch.cuda.device(self.device):
             for _ in range(repeats):
+                self._prepare_zbuf(cfg, buf)
                 check(self.lib.fmhr_ham_stage_times(ctypes.byref(cfg), ctypes.byref(buf), ms, ctypes.byref(n), stream()),
                       "ham_stage_times")
                 for i in range(min(n.value, len(acc))):
@@ -254,6 +291,7 @@ class HamOptimizer:
         pmask = torch.zeros(n, self.H, self.W, dtype=torch.float32, device=dev)
         normals = torch.empty(self.V, 3, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            self._prepare_zbuf(cfg, buf)
             check(self.lib.fmhr_ham_debug_export(ctypes.byref(cfg), ctypes.byref(buf), ptr(pos), ptr(rast), ptr(image),
                                                  ptr(pmask), ptr(normals), stream()), "ham_debug_export")
         return dict(pos=pos, rast=rast, image=image, pred_mask=pmask, normals=normals)
@@ -274,6 +312,7 @@ class HostStreamingStepper:
         self.d_w2cs = torch.empty(n_views, 4, 4, dtype=torch.float32, device=dev)
         self.d_projs = torch.empty(n_views, 4, 4, dtype=torch.float32, device=dev)
         self.rows = torch.arange(n_views, dtype=torch.int32, device=dev)
+        self.d_vm2 = torch.zeros(n_views, opt.n_tiles + 1, dtype=torch.float64, device=dev)
         self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.h2d_bytes = 4 * (n_views * H * W * 5 + n_views * 32)
         self.d2h_bytes = 32
@@ -287,10 +326,12 @@ class HostStreamingStepper:
         if o.phase != 1:
             o.begin_phase_b()
         cfg = o._cfg(self.n, 1, albedo_weight)
-        buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows)
+        buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows,
+                         self.d_vm2)
         if o.world > 1:
             raise RuntimeError("HostStreamingStepper is single-process; use HamOptimizer under torch.distributed")
         with torch.cuda.device(o.device):
+            o._prepare_zbuf(cfg, buf)
             check(o.lib.fmhr_ham_step_host(ctypes.byref(cfg), ctypes.byref(buf), ptr(h_imgs), ptr(h_masks), ptr(h_valid),
                                            ptr(h_w2cs), ptr(h_projs), ptr(self.losses_host), stream()), "ham_step_host")
         return self.losses_host

@@ -126,6 +126,9 @@ typedef struct fmhr_ham_config {
     int32_t n_views_global;   /* views in the step's batch over all ranks (mask-loss denominator) */
     int32_t phase;            /* 0 = phase A (albedo + SH), 1 = phase B (delta + albedo) */
     int32_t n_sh_rows;        /* rows of sh_coeffs resident on this rank (= its number of views) */
+    int32_t zbuf_slot;        /* 0/1: z-buffer rasterised by THIS step; the step resets the other one, so the caller
+                                 alternates the slot every step (after fmhr_ham_reset) */
+    int32_t reserved;
     float sfs_weight, lap_weight, albedo_weight, mask_weight, edge_weight, delta_weight;
     float lr, albedo_lr, sh_lr;
     float beta1, beta2, eps;
@@ -152,6 +155,7 @@ typedef struct fmhr_ham_buffers {
     const float* imgs;         /* [num,H,W,3] */
     const float* masks;        /* [num,H,W] */
     const float* valid_masks;  /* [num,H,W] */
+    const double* view_vm2;    /* [num, tiles+1] from fmhr_ham_prepare_views, tiles = ceil(W/16)*ceil(H/16) */
     const float* w2cs;         /* [num,4,4] transposed (row-vector) */
     const float* projs;        /* [num,4,4] transposed */
     const int32_t* view_idx;   /* [n_views] rows of the per-view arrays used by this step (the perm slice) */
@@ -170,6 +174,13 @@ typedef struct fmhr_ham_buffers {
 
 size_t fmhr_ham_workspace_bytes(const fmhr_ham_config* cfg);
 size_t fmhr_ham_packed_floats(const fmhr_ham_config* cfg);
+/* Resets both z-buffer slots of `workspace`.  Call once before the first step and whenever the workspace layout
+ * changes (different n_views / phase / workspace pointer). */
+int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
+/* Constants of the mask loss: view_vm2[i][t] = sum of valid_masks[i]^2 over 16x16 tile t (row-major tiles), and
+ * view_vm2[i][tiles] = the view total, tiles = ceil(W/16)*ceil(H/16) (valid_masks are fixed during the optimisation,
+ * mesh_sfs_optim.py:163).  Call once at setup, and again if valid_masks change. */
+int fmhr_ham_prepare_views(const float* valid_masks, int num, int H, int W, double* view_vm2, fmhr_stream_t stream);
 /* forward + pixel backward: fills `packed` with un-normalised gradient accumulators and loss partials. */
 int fmhr_ham_step_render(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
 /* normalises with the (all-reduced) counts, adds the regulariser gradients, applies Adam, writes `losses`. */

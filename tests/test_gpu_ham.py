@@ -238,7 +238,7 @@ def test_graph_replay_matches_eager(scene):
         lb = b.step_phase_b(views).cpu()
         assert torch.allclose(la, lb, rtol=1e-4, atol=1e-6), (la, lb)
     assert torch.allclose(a.delta, b.delta, atol=2e-2 * scene["conf"]["lr"])
-    assert int(b.adam_step[0]) == 4 and len(b._graphs) == 2
+    assert int(b.adam_step[0]) == 4 and len(b._graphs) == 2 and int(a.adam_step[0]) == 4
 
 
 def test_host_streaming_step_matches_resident(scene):

@@ -194,14 +194,14 @@ struct ViewCtx {
 __device__ __forceinline__ void load_view_ctx(ViewCtx* s, const float* __restrict__ w2cs,
                                               const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
                                               int view, int sh_row) {
-    const int tid = tile_tid();
-    if (tid < 12) {
-        const int i = tid >> 2, j = tid & 3;
+    const int lane = tile_tid() & 31;  // called by one warp
+    if (lane < 12) {
+        const int i = lane >> 2, j = lane & 3;
         const float* Wm = w2cs + (size_t)view * 16;
         const float* Pm = projs + (size_t)view * 16;
-        s->M[tid] = Wm[4 * i] * Pm[j] + Wm[4 * i + 1] * Pm[4 + j] + Wm[4 * i + 2] * Pm[8 + j] + Wm[4 * i + 3] * Pm[12 + j];
-    } else if (tid >= 32 && tid < 41) {
-        s->sh[tid - 32] = sh_coeffs[(size_t)sh_row * 9 + tid - 32];
+        s->M[lane] = Wm[4 * i] * Pm[j] + Wm[4 * i + 1] * Pm[4 + j] + Wm[4 * i + 2] * Pm[8 + j] + Wm[4 * i + 3] * Pm[12 + j];
+    } else if (lane >= 16 && lane < 25) {
+        s->sh[lane - 16] = sh_coeffs[(size_t)sh_row * 9 + lane - 16];
     }
 }
 
@@ -296,14 +296,16 @@ __device__ __forceinline__ NbrKeys decode_key(unsigned long long key) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pair work queue.  A block is responsible for every horizontally / vertically adjacent pixel pair with at least one
-// pixel in its tile: the two pairs each of its pixels starts (right, down) plus the pairs entering through the tile's
-// left column and top row.  Pairs that can blend (different triangle ids and silhouette bits set on the chosen
-// triangle) are rare (~1 % of pixels), so instead of running the ~400-instruction edge analysis under a 3-lane mask
-// inside every warp, they are queued in shared memory and analysed densely by all 256 threads.
+// Pair work queue (per warp).  A warp owns a 16x2 strip of its block's tile and is responsible for every horizontally /
+// vertically adjacent pixel pair with at least one pixel in the strip: the two pairs each of its pixels starts (right,
+// down) plus the pairs entering through the strip's top row and the tile's left column.  Pairs that can blend
+// (different triangle ids and silhouette bits set on the chosen triangle) are rare (~1 % of pixels), so instead of
+// running the ~400-instruction edge analysis under a 3-lane mask inside the per-pixel code they are queued in shared
+// memory and analysed afterwards with the queue spread over the lanes.  Everything is warp-synchronous: the pixel passes
+// have NO block-level barrier, so the 32+ resident warps of an SM hide each other's gather latency.
 //   item = (tid << 2) | which,  which: 0 (self,right)  1 (self,down)  2 (left,self)  3 (up,self)
 // ------------------------------------------------------------------------------------------------
-constexpr int kPairQueue = 2 * kTile * kTile + 2 * kTile;
+constexpr int kPairQueue = 96;  // 2*32 own pairs + 16 top-row pairs + 2 left-column pairs
 
 __device__ __forceinline__ bool pair_needs_analysis(const NbrKeys& k0, const NbrKeys& k1) {
     if (k0.tri == k1.tri) return false;
@@ -329,7 +331,7 @@ __device__ __forceinline__ void enqueue_pairs(const unsigned long long* __restri
         const NbrKeys o = decode_key(zb[rem - 1]);
         if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 2u;
     }
-    if (threadIdx.y == 0 && py > 0) {
+    if ((threadIdx.y & 1) == 0 && py > 0) {  // top row of this warp's strip
         const NbrKeys o = decode_key(zb[rem - W]);
         if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 3u;
     }
@@ -337,7 +339,7 @@ __device__ __forceinline__ void enqueue_pairs(const unsigned long long* __restri
 
 struct PairItem {
     int qx, qy, d;        // first pixel of the pair and direction
-    int tid0, tid1;       // in-tile thread index of the first / second pixel, -1 when outside this tile
+    int tid0, tid1;       // in-tile thread index of the first / second pixel, -1 when outside this warp's strip
 };
 __device__ __forceinline__ PairItem decode_pair_item(uint32_t item, const TileCtx& tc) {
     const int tid = (int)(item >> 2), which = (int)(item & 3u);
@@ -348,7 +350,7 @@ __device__ __forceinline__ PairItem decode_pair_item(uint32_t item, const TileCt
     if (which < 2) {
         it.qx = px; it.qy = py; it.tid0 = tid;
         const int ox = lx + (1 - it.d), oy = ly + it.d;
-        it.tid1 = (ox < kTile && oy < kTile) ? oy * kTile + ox : -1;
+        it.tid1 = (ox < kTile && (oy >> 1) == (ly >> 1)) ? oy * kTile + ox : -1;  // same 16x2 strip only
     } else {
         it.qx = px - (1 - it.d); it.qy = py - it.d; it.tid0 = -1; it.tid1 = tid;
     }
@@ -469,22 +471,22 @@ __device__ __forceinline__ void aa_loss_tile(
     NbrKeys self = decode_key(ZB_EMPTY);
     if (inb) self = decode_key(zb[rem]);
     enqueue_pairs(zb, px, py, H, W, self, tid, q_items, &q_n);
-    __syncthreads();  // the only barrier of a tile without blend candidates (q_n is double-buffered by the caller)
-    // dense analysis of the queued pairs; the receiver's blend lands in shared memory
+    __syncwarp();
+    // analysis of the queued pairs spread over the lanes; the receiver's blend lands in shared memory
     const int nq = q_n;
-    if (nq > 0) {  // block-uniform
+    if (nq > 0) {  // warp-uniform
 #pragma unroll
         for (int c = 0; c < NC; c++) blend[tid][c] = 0.0f;
-        __syncthreads();
+        __syncwarp();
         const float* P = reinterpret_cast<const float*>(pos + (size_t)n * V);
-        for (int e = tid; e < nq; e += kTile * kTile) {
+        for (int e = tid & 31; e < nq; e += 32) {
             const PairItem it = decode_pair_item(q_items[e], tc);
             const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
             const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
             AAPair pr;
             if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, P, tri, opp, V, T, H, W, pr)) continue;
             const int recv = pr.alpha > 0.0f ? it.tid0 : it.tid1;
-            if (recv < 0) continue;  // the receiver belongs to the neighbouring tile's block
+            if (recv < 0) continue;  // the receiver belongs to another warp's strip
             // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
             float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, s0 = f0, s1 = f0;
             if (k0.tri >= 0) { f0 = plane0[base + r0]; if (PHASE == 0) f1 = plane1[base + r0]; }
@@ -500,8 +502,8 @@ __device__ __forceinline__ void aa_loss_tile(
                 atomicAdd(&blend[recv][5], pr.alpha * (s1.z - f1.z));
             }
         }
-        __syncthreads();
-        if (tid == 0) q_n = 0;  // everyone has read nq; this counter is next used two tiles from now
+        __syncwarp();
+        if ((tid & 31) == 0) q_n = 0;
     }
     float abs_sum = 0.0f, msk_sum = 0.0f;
     float gc[9];
@@ -577,7 +579,7 @@ __device__ __forceinline__ void aa_loss_tile(
             if ((tid & 31) == 0 && sk != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, sk);
         }
     }
-    if (nq > 0) __syncthreads();  // blend[] / q_items are rewritten by the next tile
+    __syncwarp();  // blend[] / q_items / q_n of this warp are rewritten by its next tile
 }
 
 // antialias (gather form, dense pair queue) + losses; persistent over the dilated work list
@@ -590,17 +592,18 @@ __global__ void __launch_bounds__(256) ham_aa_loss_kernel(
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
     float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
     const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask) {
-    __shared__ uint32_t q_items[kPairQueue];
-    __shared__ int q_n[2];  // double-buffered: a fast warp may already enqueue for the next tile
+    __shared__ uint32_t q_items[8][kPairQueue];
+    __shared__ int q_n[8];
     __shared__ float blend[kTile * kTile][PHASE == 1 ? 4 : 6];
-    if (tile_tid() < 2) q_n[tile_tid()] = 0;
-    __syncthreads();
+    const int warp = tile_tid() >> 5;
+    if ((tile_tid() & 31) == 0) q_n[warp] = 0;
+    __syncwarp();
     const int na = *acount;
-    int par = 0;
-    for (int it = blockIdx.x; it < na; it += gridDim.x, par ^= 1) {
+    for (int it = blockIdx.x; it < na; it += gridDim.x) {
         const TileCtx tc = tile_decode(alist[it], tiles_x, tiles_y);
         aa_loss_tile<PHASE>(tc, zbuf, pos, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
-                            plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items, q_n[par], blend);
+                            plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items[warp], q_n[warp],
+                            blend);
     }
 }
 
@@ -632,13 +635,13 @@ __device__ __forceinline__ void pixel_bwd_tile(
     const float4* Pv = pos + (size_t)n * V;
     const float* P = reinterpret_cast<const float*>(Pv);
     enqueue_pairs(zb, px, py, H, W, self, tid, q_items, &q_n);
-    __syncthreads();  // the only barrier of a tile without blend candidates (q_n is double-buffered by the caller)
+    __syncwarp();
     const int nq = q_n;
-    if (nq > 0) {  // block-uniform
+    if (nq > 0) {  // warp-uniform
         gblend[tid][0] = 0.0f; gblend[tid][1] = 0.0f; gblend[tid][2] = 0.0f;
-        __syncthreads();
+        __syncwarp();
     }
-    for (int e = tid; e < nq; e += kTile * kTile) {
+    for (int e = tid & 31; e < nq; e += 32) {
         const PairItem it = decode_pair_item(q_items[e], tc);
         const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
         const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
@@ -659,7 +662,7 @@ __device__ __forceinline__ void pixel_bwd_tile(
             atomicAdd(&gblend[it.tid1][2], pr.alpha * gr.z);
         }
         if (PHASE == 1 && it.tid0 >= 0 && !pr.clamped) {
-            // position gradient: the block that owns the pair's first pixel scatters it
+            // position gradient: the warp whose strip holds the pair's first pixel scatters it
             float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = f0;
             if (k0.tri >= 0) f0 = plane0[base + r0];
             if (k1.tri >= 0) s0 = plane0[base + r1];
@@ -679,10 +682,10 @@ __device__ __forceinline__ void pixel_bwd_tile(
     }
     float3 gb = make_float3(0.f, 0.f, 0.f);
     if (nq > 0) {
-        __syncthreads();
+        __syncwarp();
         gb = make_float3(gblend[tid][0], gblend[tid][1], gblend[tid][2]);
-        if (tid == 0) q_n = 0;  // everyone has read nq; this counter is next used two tiles from now
-        __syncthreads();        // gblend[] / q_items are rewritten by the next tile
+        if ((tid & 31) == 0) q_n = 0;
+        __syncwarp();  // gblend[] / q_items of this warp are rewritten by its next tile
     }
     const bool covered = self.tri >= 0;
     if (!inb || !covered) return;  // empty pixels have no upstream producer
@@ -780,23 +783,24 @@ __global__ void __launch_bounds__(256) ham_pixel_bwd_kernel(
     const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
     const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
     const float4* __restrict__ gplane1, float4* __restrict__ G) {
-    __shared__ ViewCtx ctx;
-    __shared__ uint32_t q_items[kPairQueue];
-    __shared__ int q_n[2];  // double-buffered: a fast warp may already enqueue for the next tile
+    __shared__ ViewCtx ctx[8];  // per warp: warps of a block drift apart (no block barrier) and may be on different views
+    __shared__ uint32_t q_items[8][kPairQueue];
+    __shared__ int q_n[8];
     __shared__ float gblend[kTile * kTile][3];  // pair terms of d(loss)/d(pre-antialias colour | albedo)
-    if (tile_tid() < 2) q_n[tile_tid()] = 0;
+    const int warp = tile_tid() >> 5;
+    if ((tile_tid() & 31) == 0) q_n[warp] = 0;
     const int na = *acount;
-    int par = 0, ctx_n = -1;
-    for (int it = blockIdx.x; it < na; it += gridDim.x, par ^= 1) {
+    int ctx_n = -1;
+    for (int it = blockIdx.x; it < na; it += gridDim.x) {
         const TileCtx tc = tile_decode(alist[it], tiles_x, tiles_y);
-        if (tc.n != ctx_n) {  // block-uniform: per-view matrices / SH row change rarely along the list
-            __syncthreads();
-            load_view_ctx(&ctx, w2cs, projs, sh_coeffs, __ldg(view_idx + tc.n), __ldg(sh_idx + tc.n));
-            __syncthreads();
+        if (tc.n != ctx_n) {  // warp-uniform: per-view matrices / SH row change rarely along the list
+            __syncwarp();
+            load_view_ctx(&ctx[warp], w2cs, projs, sh_coeffs, __ldg(view_idx + tc.n), __ldg(sh_idx + tc.n));
+            __syncwarp();
             ctx_n = tc.n;
         }
         pixel_bwd_tile<PHASE>(tc, zbuf, pos, tri, opp, normals, albedo, w2cs, projs, sh_coeffs, view_idx, sh_idx, V, T, H, W,
-                              plane0, plane1, gplane0, gplane1, G, ctx, q_items, q_n[par], gblend);
+                              plane0, plane1, gplane0, gplane1, G, ctx[warp], q_items[warp], q_n[warp], gblend);
     }
 }
 
@@ -1110,15 +1114,15 @@ __global__ void ham_update_sh_kernel(fmhr_ham_config cfg, const float* __restric
                                adam_sc[5]);
 }
 
-// persistent pixel kernels: 4 resident 256-thread blocks per SM (64 registers / thread)
-static int persistent_blocks() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n = sms * 4;
-    }
-    return n;
+// Persistent pixel kernels: the grid is exactly the number of co-resident 256-thread blocks (SMs x occupancy), so the
+// static round-robin over the work list is balanced (a grid larger than that runs a second, idle-tailed wave).
+template <typename K>
+static int persistent_blocks(K kernel) {
+    int dev = 0, sms = 148, per_sm = 2;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTile * kTile, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 2;
+    return sms * per_sm;
 }
 
 static int check_cfg(const fmhr_ham_config* c) {
@@ -1188,8 +1192,11 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
                                         ws.tcount[cur], tiles_x, tiles_x * tiles_y, st);
     if (rc) return rc;
     FMHR_STAGE_MARK();  // 3: coverage
-    const dim3 pgrid(persistent_blocks()), pblock(kTile, kTile);
-    ham_shade_kernel<PHASE><<<pgrid, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt],
+    static const int g_shade = persistent_blocks(ham_shade_kernel<PHASE>);
+    static const int g_aa = persistent_blocks(ham_aa_loss_kernel<PHASE>);
+    static const int g_bwd = persistent_blocks(ham_pixel_bwd_kernel<PHASE>);
+    const dim3 pblock(kTile, kTile);
+    ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt],
                                                       ws.tcount[nxt], ws.abits, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
                                                       b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W,
                                                       ws.plane[0], ws.plane[1], ws.acc);
@@ -1197,13 +1204,13 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     FMHR_STAGE_MARK();  // 4: shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    ham_aa_loss_kernel<PHASE><<<pgrid, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, b->imgs, b->valid_masks,
+    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, b->imgs, b->valid_masks,
                                                      b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
                                                      ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
-        ham_pixel_bwd_kernel<PHASE><<<pgrid, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
                                                            b->w2cs, b->projs, b->sh_coeffs, b->view_idx, sh_idx, V, T,
                                                            H, W, ws.plane[0], ws.plane[1], g0, g1, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();

@@ -1,6 +1,6 @@
 // Silhouette-edge analysis of one pixel pair, shared by the stand-alone antialias op (antialias.cu) and the fused
 // HAM kernels (ham.cu).  Semantics follow nvdiffrast's antialias; every decision-relevant
-// operation is an exactly-rounded, un-contracted fp32 op in the same order as oracle/raster_oracle.cpp::aa_analyse,
+// operation is an exactly-rounded, un-contracted fp32 op in the same order as the CPU checker (aa_analyse in the test oracle),
 // so the discrete choices (which triangle, which edge, blend or not) are bit-identical to the oracle's.
 #pragma once
 #include "common.cuh"

@@ -584,7 +584,7 @@ __device__ __forceinline__ void aa_loss_tile(
 
 // antialias (gather form, dense pair queue) + losses; persistent over the dilated work list
 template <int PHASE>
-__global__ void __launch_bounds__(256) ham_aa_loss_kernel(
+__global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
     int tiles_x, int tiles_y, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
@@ -775,7 +775,7 @@ __device__ __forceinline__ void pixel_bwd_tile(
 
 // pixel backward, persistent over the dilated work list
 template <int PHASE>
-__global__ void __launch_bounds__(256) ham_pixel_bwd_kernel(
+__global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
     const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
     int tiles_x, int tiles_y, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,

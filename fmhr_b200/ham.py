@@ -10,6 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import HamBuffers, HamConfig, check, ptr, stream
+from .dist import allreduce_packed
 from .dr import Topology
 
 
@@ -169,7 +170,7 @@ class HamOptimizer:
         sp = stream()
         check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_render")
         if self.world > 1:
-            torch.distributed.all_reduce(self.packed, group=self.pg)  # one NCCL sum per iteration
+            allreduce_packed(self.packed, self.pg)  # one NCCL sum per iteration
         check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_update")
         return self.losses
 
@@ -199,7 +200,7 @@ class HamOptimizer:
             idx_buf.copy_(vi, non_blocking=True)
         graphs[slot][0].replay()
         if self.world > 1:
-            torch.distributed.all_reduce(self.packed, group=self.pg)
+            allreduce_packed(self.packed, self.pg)
             graphs[slot][1].replay()
         return self.losses
 

@@ -52,8 +52,8 @@ class HamOptimizer:
               "ham_prepare_views")
         self.workspace = None
         self.pg = process_group
-        self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        self.world = 1  # process_group=False forces a single-rank optimiser inside a distributed job
+        if process_group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.n_views_global_override = n_views_global
         self.dbg_grad = torch.zeros(self.V, 6, dtype=torch.float32, device=dev) if debug else None

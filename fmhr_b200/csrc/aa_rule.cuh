@@ -24,11 +24,31 @@ __device__ __forceinline__ bool aa_rational_gt(float n0, float d0, float n1, flo
     const bool flip = (d0 < 0.0f) != (d1 < 0.0f);
     return flip ? (l < r) : (l > r);
 }
-__device__ __forceinline__ void aa_project(const float4 p, float xh, float yh, float fx, float fy, float& x, float& y) {
+// Window coordinates of a vertex relative to a pixel centre.  Two sources with bit-identical results:
+//  AAProjClip   - from clip-space positions [V,4] (the stand-alone op): one IEEE divide per vertex;
+//  AAProjScreen - from (x/w*W/2, y/w*H/2) pairs the fused path's transform kernel pre-computed once per (view, vertex)
+//                 with the very same operations (aa_window_xy), leaving two subtractions here.
+__device__ __forceinline__ float2 aa_window_xy(const float4 p, float xh, float yh) {
     const float iw = xd(1.0f, p.w);
-    x = xs(xm(xm(p.x, iw), xh), fx);
-    y = xs(xm(xm(p.y, iw), yh), fy);
+    return make_float2(xm(xm(p.x, iw), xh), xm(xm(p.y, iw), yh));
 }
+struct AAProjClip {
+    const float* P;
+    float xh, yh;
+    __device__ __forceinline__ void operator()(int v, float fx, float fy, float& x, float& y) const {
+        const float2 s = aa_window_xy(ldg4(P + 4 * (size_t)v), xh, yh);
+        x = xs(s.x, fx);
+        y = xs(s.y, fy);
+    }
+};
+struct AAProjScreen {
+    const float2* S;
+    __device__ __forceinline__ void operator()(int v, float fx, float fy, float& x, float& y) const {
+        const float2 s = __ldg(S + v);
+        x = xs(s.x, fx);
+        y = xs(s.y, fy);
+    }
+};
 
 // Projected corners of triangle t relative to the centre of its OWNING pixel (qx,qy), plus the three silhouette-candidate
 // bits: bit k set <=> the wing across the edge facing corner k lies on the same side as the triangle itself (or the
@@ -39,7 +59,8 @@ struct AAGeom {
     int bits;
 };
 
-__device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const float* __restrict__ P,
+template <class Proj>
+__device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const Proj proj,
                                                  const int32_t* __restrict__ tri, const int32_t* __restrict__ opp,
                                                  int V, int T, int H, int W, AAGeom& g) {
     if (t < 0 || t >= T) return false;
@@ -48,14 +69,14 @@ __device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const fl
     const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
     const float fx = xs(xa((float)qx, 0.5f), xh), fy = xs(xa((float)qy, 0.5f), yh);
     float x0, y0, x1, y1, x2, y2;
-    aa_project(ldg4(P + 4 * (size_t)v0), xh, yh, fx, fy, x0, y0);
-    aa_project(ldg4(P + 4 * (size_t)v1), xh, yh, fx, fy, x1, y1);
-    aa_project(ldg4(P + 4 * (size_t)v2), xh, yh, fx, fy, x2, y2);
+    proj(v0, fx, fy, x0, y0);
+    proj(v1, fx, fy, x1, y1);
+    proj(v2, fx, fy, x2, y2);
     const int o0 = __ldg(opp + 3 * t), o1 = __ldg(opp + 3 * t + 1), o2 = __ldg(opp + 3 * t + 2);
     float ox0 = x0, oy0 = y0, ox1 = x1, oy1 = y1, ox2 = x2, oy2 = y2;
-    if ((unsigned)o0 < (unsigned)V) aa_project(ldg4(P + 4 * (size_t)o0), xh, yh, fx, fy, ox0, oy0);
-    if ((unsigned)o1 < (unsigned)V) aa_project(ldg4(P + 4 * (size_t)o1), xh, yh, fx, fy, ox1, oy1);
-    if ((unsigned)o2 < (unsigned)V) aa_project(ldg4(P + 4 * (size_t)o2), xh, yh, fx, fy, ox2, oy2);
+    if ((unsigned)o0 < (unsigned)V) proj(o0, fx, fy, ox0, oy0);
+    if ((unsigned)o1 < (unsigned)V) proj(o1, fx, fy, ox1, oy1);
+    if ((unsigned)o2 < (unsigned)V) proj(o2, fx, fy, ox2, oy2);
     const float bb = xs(xm(xs(x1, x0), xs(y2, y0)), xm(xs(x2, x0), xs(y1, y0)));
     const float a0 = xs(xm(xs(x1, ox0), xs(y2, oy0)), xm(xs(x2, ox0), xs(y1, oy0)));
     const float a1 = xs(xm(xs(x2, ox1), xs(y0, oy1)), xm(xs(x0, ox1), xs(y2, oy1)));
@@ -110,16 +131,17 @@ __device__ __forceinline__ bool aa_select_edge(const AAGeom& g, int t, int d, bo
 }
 
 // (px,py) = first pixel of the pair, d = 0 (right neighbour) or 1 (down neighbour);
-// tri0/z0 and tri1/z1 are triangle id (-1 = empty) and z/w of the two pixels; P = this view's clip positions.
+// tri0/z0 and tri1/z1 are triangle id (-1 = empty) and z/w of the two pixels; proj = this view's vertex projector.
+template <class Proj>
 __device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z1, int px, int py, int d,
-                                           const float* __restrict__ P, const int32_t* __restrict__ tri,
+                                           const Proj proj, const int32_t* __restrict__ tri,
                                            const int32_t* __restrict__ opp, int V, int T, int H, int W, AAPair& out) {
     int t = (tri0 >= 0) ? tri0 : tri1;
     if (tri0 >= 0 && tri1 >= 0) t = (z0 < z1) ? tri0 : tri1;
     const bool from1 = (t == tri1);
     if (from1) { px += 1 - d; py += d; }
     AAGeom g;
-    if (!aa_triangle_geom(t, px, py, P, tri, opp, V, T, H, W, g)) return false;
+    if (!aa_triangle_geom(t, px, py, proj, tri, opp, V, T, H, W, g)) return false;
     return aa_select_edge(g, t, d, from1, out);
 }
 

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) antialias_kernel(const float* __restrict_
         const float4 r1 = __ldg(rast + pix1);
         if (r0.w == r1.w) continue;
         AAPair pr;
-        if (!aa_analyse((int)r0.w - 1, r0.z, (int)r1.w - 1, r1.z, px, py, d, P, tri, opp, V, T, H, W, pr)) continue;
+        const AAProjClip proj{P, 0.5f * (float)W, 0.5f * (float)H};
+        if (!aa_analyse((int)r0.w - 1, r0.z, (int)r1.w - 1, r1.z, px, py, d, proj, tri, opp, V, T, H, W, pr)) continue;
         const float* c0 = color + pix0 * C;
         const float* c1 = color + pix1 * C;
         const size_t recv = (pr.alpha > 0.0f) ? pix0 : pix1;

@@ -25,6 +25,7 @@ struct HamWs {
     float4* plane[4];          // [n,H,W] each
     float4* pos;               // [n,V] clip positions
     int2* snap;                // [n,V] 24.8 fixed-point window coordinates (x == INT_MIN: vertex rejected)
+    float2* scr;               // [n,V] (x/w*W/2, y/w*H/2): the antialias rule's window coordinates, divide done once
     // Active-tile work lists (16x16 tiles).  slot[s]: tiles of z-buffer slot s that received fragments (bitmap for
     // de-duplication + compact list + count, filled by the coverage kernel); act: those tiles dilated by their four
     // edge neighbours (antialias pairs straddle tile edges), filled by the shade pass.  The pixel passes are persistent
@@ -77,6 +78,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     }
     p = take((size_t)c->n_views * V * 16); if (ws) ws->pos = (float4*)p;
     p = take((size_t)c->n_views * V * 8); if (ws) ws->snap = (int2*)p;
+    p = take((size_t)c->n_views * V * 8); if (ws) ws->scr = (float2*)p;
     const size_t tiles_pv = (size_t)((c->W + 15) / 16) * ((c->H + 15) / 16);
     const size_t words = (size_t)c->n_views * ((tiles_pv + 31) / 32);
     const size_t slot_bytes = 256 + align256(words * 4);
@@ -107,11 +109,23 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
 // ------------------------------------------------------------------------------------------------
 // vertex-domain prologue
 // ------------------------------------------------------------------------------------------------
+// vertices = vertices_tmp + delta (mesh_sfs_optim.py:253).  The same launch re-arms the step's accumulators (the packed
+// gradient buffer = 3V float4, loss / work-list scratch, SH gradients) so the iteration has no memset nodes.
 __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __restrict__ vtmp,
                                                               const float* __restrict__ delta, int n3,
-                                                              float* __restrict__ vertices) {
+                                                              float* __restrict__ vertices, float4* __restrict__ packed4,
+                                                              uint32_t* __restrict__ z0, int n0,
+                                                              uint32_t* __restrict__ z1, int n1,
+                                                              uint32_t* __restrict__ z2, int n2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n3) vertices[i] = vtmp[i] + delta[i];  // mesh_sfs_optim.py:253
+    if (i < n3) {
+        vertices[i] = vtmp[i] + delta[i];
+        packed4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (i == 0) packed4[n3] = make_float4(0.f, 0.f, 0.f, 0.f);  // the four scalars behind the 12V floats
+    if (i < n0) z0[i] = 0u;
+    if (i < n1) z1[i] = 0u;
+    if (i < n2) z2[i] = 0u;
 }
 
 // clip = ([v,1] @ w2c) @ proj, both matrices stored transposed (mesh_sfs_optim.py:262-264, get_data.py:96-97); also snaps
@@ -120,7 +134,8 @@ __global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restr
                                                             const float* __restrict__ w2cs,
                                                             const float* __restrict__ projs,
                                                             const int32_t* __restrict__ view_idx, int V, int H, int W,
-                                                            float4* __restrict__ pos, int2* __restrict__ snap) {
+                                                            float4* __restrict__ pos, int2* __restrict__ snap,
+                                                            float2* __restrict__ scr) {
     const int n = blockIdx.y;
     const int view = __ldg(view_idx + n);
     const float* Wm = w2cs + (size_t)view * 16;  // block-uniform addresses: broadcast loads
@@ -139,6 +154,7 @@ __global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restr
     int X = kSnapRejected, Y = 0;
     if (!snap_vertex(p, (float)W * 0.5f, (float)H * 0.5f, X, Y)) X = kSnapRejected;
     snap[(size_t)n * V + i] = make_int2(X, Y);
+    scr[(size_t)n * V + i] = aa_window_xy(p, 0.5f * (float)W, 0.5f * (float)H);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -361,7 +377,8 @@ __device__ __forceinline__ PairItem decode_pair_item(uint32_t item, const TileCt
 // the silhouette bits / valid flag and resets the OTHER z-buffer slot for the next iteration (no separate clear pass).
 template <int PHASE>
 __device__ __forceinline__ void shade_tile(const TileCtx tc, unsigned long long* __restrict__ zbuf,
-                                           const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+                                           const float4* __restrict__ pos, const float2* __restrict__ scr, float invW,
+                                           float invH, const int32_t* __restrict__ tri,
                                            const int32_t* __restrict__ opp, const float* __restrict__ normals,
                                            const float* __restrict__ albedo, const float* __restrict__ masks,
                                            const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx,
@@ -380,13 +397,12 @@ __device__ __forceinline__ void shade_tile(const TileCtx tc, unsigned long long*
         const unsigned long long key = zbuf[pix];
         if (key != ZB_EMPTY) {
             const int t = (int)((uint32_t)key & kTriMask);
-            const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
             const float4* Pv = pos + (size_t)n * V;
             PixTri q;
             load_pixtri(t, px, py, Pv, tri, invW, invH, q);
             AAGeom g;
             g.bits = 0;
-            aa_triangle_geom(t, px, py, reinterpret_cast<const float*>(Pv), tri, opp, V, T, H, W, g);
+            aa_triangle_geom(t, px, py, AAProjScreen{scr + (size_t)n * V}, tri, opp, V, T, H, W, g);
             const float3 m = interp3(normals, q);
             const float3 a = interp3(albedo, q);
             const bool valid = __ldg(masks + (size_t)view * hw + rem) > 0.0f;
@@ -421,6 +437,7 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
                                                         uint32_t* __restrict__ abits, uint32_t* __restrict__ alist,
                                                         int* __restrict__ acount, int tiles_x, int tiles_y,
                                                         const float4* __restrict__ pos,
+                                                        const float2* __restrict__ scr, float invW, float invH,
                                                         const int32_t* __restrict__ tri,
                                                         const int32_t* __restrict__ opp,
                                                         const float* __restrict__ normals,
@@ -441,7 +458,7 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
     for (int it = blockIdx.x; it < nc; it += gridDim.x) {
         const TileCtx tc = tile_decode(tlist[it], tiles_x, tiles_y);
         tile_mark_active(tc, tile_tid(), abits, alist, acount);
-        shade_tile<PHASE>(tc, zbuf, pos, tri, opp, normals, albedo, masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
+        shade_tile<PHASE>(tc, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
                           plane1, acc);
     }
 }
@@ -449,7 +466,7 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
 template <int PHASE>
 __device__ __forceinline__ void aa_loss_tile(
     const TileCtx tc, const unsigned long long* __restrict__ zbuf,
-    const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    const float2* __restrict__ scr, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
@@ -478,13 +495,13 @@ __device__ __forceinline__ void aa_loss_tile(
 #pragma unroll
         for (int c = 0; c < NC; c++) blend[tid][c] = 0.0f;
         __syncwarp();
-        const float* P = reinterpret_cast<const float*>(pos + (size_t)n * V);
+        const AAProjScreen proj{scr + (size_t)n * V};
         for (int e = tid & 31; e < nq; e += 32) {
             const PairItem it = decode_pair_item(q_items[e], tc);
             const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
             const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
             AAPair pr;
-            if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, P, tri, opp, V, T, H, W, pr)) continue;
+            if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, proj, tri, opp, V, T, H, W, pr)) continue;
             const int recv = pr.alpha > 0.0f ? it.tid0 : it.tid1;
             if (recv < 0) continue;  // the receiver belongs to another warp's strip
             // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
@@ -586,7 +603,7 @@ __device__ __forceinline__ void aa_loss_tile(
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
-    int tiles_x, int tiles_y, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    int tiles_x, int tiles_y, const float2* __restrict__ scr, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
@@ -601,7 +618,7 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     const int na = *acount;
     for (int it = blockIdx.x; it < na; it += gridDim.x) {
         const TileCtx tc = tile_decode(alist[it], tiles_x, tiles_y);
-        aa_loss_tile<PHASE>(tc, zbuf, pos, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
+        aa_loss_tile<PHASE>(tc, zbuf, scr, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
                             plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items[warp], q_n[warp],
                             blend);
     }
@@ -614,7 +631,7 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
 template <int PHASE>
 __device__ __forceinline__ void pixel_bwd_tile(
     const TileCtx tc, const unsigned long long* __restrict__ zbuf,
-    const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    const float4* __restrict__ pos, const float2* __restrict__ scr, float invW, float invH, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
     const float* __restrict__ w2cs, const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
     const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
@@ -646,7 +663,7 @@ __device__ __forceinline__ void pixel_bwd_tile(
         const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
         const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
         AAPair pr;
-        if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, P, tri, opp, V, T, H, W, pr)) continue;
+        if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, AAProjScreen{scr + (size_t)n * V}, tri, opp, V, T, H, W, pr)) continue;
         const int recv = (pr.alpha > 0.0f) ? r0 : r1;
         // phase B blends the shaded colour (gplane0.xyz) and coverage (gplane0.w); phase A the albedo (gplane1.xyz)
         const float4 gr = (PHASE == 1) ? gplane0[base + recv] : gplane1[base + recv];
@@ -698,7 +715,6 @@ __device__ __forceinline__ void pixel_bwd_tile(
         g1 = gplane1[pix];
         g1.x += gb.x; g1.y += gb.y; g1.z += gb.z;
     }
-    const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
     PixTri q;
     load_pixtri(self.tri, px, py, Pv, tri, invW, invH, q);
     const float w = 1.0f - q.u - q.v;
@@ -777,7 +793,8 @@ __device__ __forceinline__ void pixel_bwd_tile(
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
     const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
-    int tiles_x, int tiles_y, const float4* __restrict__ pos, const int32_t* __restrict__ tri,
+    int tiles_x, int tiles_y, const float4* __restrict__ pos, const float2* __restrict__ scr, float invW, float invH,
+    const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
     const float* __restrict__ w2cs, const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
     const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
@@ -799,7 +816,7 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
             __syncwarp();
             ctx_n = tc.n;
         }
-        pixel_bwd_tile<PHASE>(tc, zbuf, pos, tri, opp, normals, albedo, w2cs, projs, sh_coeffs, view_idx, sh_idx, V, T, H, W,
+        pixel_bwd_tile<PHASE>(tc, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, w2cs, projs, sh_coeffs, view_idx, sh_idx, V, T, H, W,
                               plane0, plane1, gplane0, gplane1, G, ctx[warp], q_items[warp], q_n[warp], gblend);
     }
 }
@@ -1172,20 +1189,22 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     unsigned long long* znext = ws.zbuf[cfg->zbuf_slot ^ 1];
     const int cur = cfg->zbuf_slot, nxt = cfg->zbuf_slot ^ 1;
     const int tiles_x = cdiv(W, kTile), tiles_y = cdiv(H, kTile);
+    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;  // IEEE single divides, identical to the device's __fdiv_rn
     const int32_t* sh_idx = b->sh_idx ? b->sh_idx : b->view_idx;
-    FMHR_CUDA(cudaMemsetAsync(b->packed, 0, fmhr_ham_packed_floats(cfg) * sizeof(float), st));
-    // zero: loss accumulators + dilated work list (common) and the work list of the slot rasterised this step
-    FMHR_CUDA(cudaMemsetAsync(ws.common_region, 0, ws.common_bytes, st));
-    FMHR_CUDA(cudaMemsetAsync(ws.slot_region[cfg->zbuf_slot], 0, ws.slot_bytes, st));
-    if (PHASE == 0) FMHR_CUDA(cudaMemsetAsync(ws.gsh, 0, (size_t)cfg->n_sh_rows * 9 * sizeof(float), st));
-    FMHR_STAGE_MARK();  // 0: clears
-    ham_vertex_prep_kernel<<<cdiv(3 * V, 256), 256, 0, st>>>(b->vertices_tmp, b->delta, 3 * V, ws.vertices);
+    FMHR_STAGE_MARK();  // 0: (no clear pass any more)
+    // zeroed by the prep kernel: packed, loss accumulators + dilated work list (common), the work list of the slot
+    // rasterised this step, SH gradients (phase A)
+    const int n0 = (int)(ws.common_bytes / 4), n1 = (int)(ws.slot_bytes / 4), n2 = PHASE == 0 ? cfg->n_sh_rows * 9 : 0;
+    const int prep_threads = max(3 * V, max(n0, max(n1, n2)));
+    ham_vertex_prep_kernel<<<cdiv(prep_threads, 256), 256, 0, st>>>(
+        b->vertices_tmp, b->delta, 3 * V, ws.vertices, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
+        (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2);
     FMHR_LAUNCH_CHECK();
     int rc = launch_vertex_normals_fwd(ws.vertices, b->tri, b->v2f_ptr, b->v2f_idx, V, ws.normals, ws.raw, st);
     if (rc) return rc;
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
     ham_transform_kernel<<<dim3(cdiv(V, 256), n), 256, 0, st>>>(ws.vertices, b->w2cs, b->projs, b->view_idx, V, H, W,
-                                                                ws.pos, ws.snap);
+                                                                ws.pos, ws.snap, ws.scr);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 2: transform
     rc = launch_raster_coverage_snapped(ws.pos, ws.snap, b->tri, n, V, T, H, W, zcur, ws.tbits[cur], ws.tlist[cur],
@@ -1197,20 +1216,22 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     static const int g_bwd = persistent_blocks(ham_pixel_bwd_kernel<PHASE>);
     const dim3 pblock(kTile, kTile);
     ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt],
-                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
+                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos,
+                                                      ws.scr, invW, invH, b->tri, b->opp, ws.normals, b->albedo,
                                                       b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W,
                                                       ws.plane[0], ws.plane[1], ws.acc);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 4: shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, b->imgs, b->valid_masks,
+    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.scr, b->tri, b->opp, b->imgs, b->valid_masks,
                                                      b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
                                                      ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos, b->tri, b->opp, ws.normals, b->albedo,
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos,
+                                                              ws.scr, invW, invH, b->tri, b->opp, ws.normals, b->albedo,
                                                            b->w2cs, b->projs, b->sh_coeffs, b->view_idx, sh_idx, V, T,
                                                            H, W, ws.plane[0], ws.plane[1], g0, g1, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();

@@ -9,7 +9,8 @@
 
 namespace fmhr {
 
-__device__ __forceinline__ bool owns_edge(long long dx, long long dy) { return dy > 0 || (dy == 0 && dx > 0); }
+template <typename I>
+__device__ __forceinline__ bool owns_edge(I dx, I dy) { return dy > 0 || (dy == 0 && dx > 0); }
 
 template <typename I>
 __device__ __forceinline__ void cover_bbox(int X0, int Y0, int X1, int Y1, int X2, int Y2, int px0, int px1, int py0,

@@ -20,12 +20,18 @@ int launch_raster_coverage_snapped(const float4* pos, const int2* snap, const in
 int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
                               int V, float* normals, float* raw, cudaStream_t st);
 
+// Per-view constants of the backward pass, written once per step by the transform kernel:
+//   viewM[n][0..11] = rows 0..2 of (w2c @ proj), columns x,y,z,w : d(clip_j)/d(world_i) = M[4i+j]
+constexpr int kViewM = 12;
+
 struct HamWs {
     unsigned long long* zbuf[2];  // [n,H,W] x2: `zbuf_slot` is rasterised this step, the other is reset for the next
     float4* plane[4];          // [n,H,W] each
     float4* pos;               // [n,V] clip positions
     int2* snap;                // [n,V] 24.8 fixed-point window coordinates (x == INT_MIN: vertex rejected)
     float2* scr;               // [n,V] (x/w*W/2, y/w*H/2): the antialias rule's window coordinates, divide done once
+    float* viewM;              // [n,12] d(clip)/d(world) per view
+    int* cursors;              // [8] work cursors of the persistent kernels (inside common_region)
     // Active-tile work lists (16x16 tiles).  slot[s]: tiles of z-buffer slot s that received fragments (bitmap for
     // de-duplication + compact list + count, filled by the coverage kernel); act: those tiles dilated by their four
     // edge neighbours (antialias pairs straddle tile edges), filled by the shade pass.  The pixel passes are persistent
@@ -79,6 +85,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take((size_t)c->n_views * V * 16); if (ws) ws->pos = (float4*)p;
     p = take((size_t)c->n_views * V * 8); if (ws) ws->snap = (int2*)p;
     p = take((size_t)c->n_views * V * 8); if (ws) ws->scr = (float2*)p;
+    p = take((size_t)c->n_views * kViewM * 4); if (ws) ws->viewM = (float*)p;
     const size_t tiles_pv = (size_t)((c->W + 15) / 16) * ((c->H + 15) / 16);
     const size_t words = (size_t)c->n_views * ((tiles_pv + 31) / 32);
     const size_t slot_bytes = 256 + align256(words * 4);
@@ -93,6 +100,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     if (ws) {
         ws->common_region = p; ws->common_bytes = common_bytes; ws->slot_bytes = slot_bytes;
         ws->acc = (double*)p; ws->acount = (int*)(p + 8 * 32 * sizeof(double));
+        ws->cursors = ws->acount + 8;  // same zeroed 256-byte slot
         ws->abits = (uint32_t*)(p + 8 * 32 * sizeof(double) + 256);
     }
     p = take(V * 12); if (ws) ws->vertices = (float*)p;
@@ -135,11 +143,16 @@ __global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restr
                                                             const float* __restrict__ projs,
                                                             const int32_t* __restrict__ view_idx, int V, int H, int W,
                                                             float4* __restrict__ pos, int2* __restrict__ snap,
-                                                            float2* __restrict__ scr) {
+                                                            float2* __restrict__ scr, float* __restrict__ viewM) {
     const int n = blockIdx.y;
     const int view = __ldg(view_idx + n);
     const float* Wm = w2cs + (size_t)view * 16;  // block-uniform addresses: broadcast loads
     const float* Pm = projs + (size_t)view * 16;
+    if (blockIdx.x == 0 && threadIdx.x < kViewM) {
+        const int r = threadIdx.x >> 2, j = threadIdx.x & 3;
+        viewM[n * kViewM + threadIdx.x] = Wm[4 * r] * Pm[j] + Wm[4 * r + 1] * Pm[4 + j] + Wm[4 * r + 2] * Pm[8 + j] +
+                                          Wm[4 * r + 3] * Pm[12 + j];
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float x = vertices[3 * (size_t)i], y = vertices[3 * (size_t)i + 1], z = vertices[3 * (size_t)i + 2];
@@ -202,25 +215,6 @@ __device__ __forceinline__ float sh_radiance(const float* c, float x, float y, f
 constexpr int kTile = 16;
 __device__ __forceinline__ int tile_tid() { return threadIdx.y * kTile + threadIdx.x; }
 
-struct ViewCtx {
-    float M[12];  // rows 0..2 of (w2c @ proj), columns x,y,z,w : d(clip_j)/d(world_i) = M[4i+j]
-    float sh[9];
-};
-
-__device__ __forceinline__ void load_view_ctx(ViewCtx* s, const float* __restrict__ w2cs,
-                                              const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
-                                              int view, int sh_row) {
-    const int lane = tile_tid() & 31;  // called by one warp
-    if (lane < 12) {
-        const int i = lane >> 2, j = lane & 3;
-        const float* Wm = w2cs + (size_t)view * 16;
-        const float* Pm = projs + (size_t)view * 16;
-        s->M[lane] = Wm[4 * i] * Pm[j] + Wm[4 * i + 1] * Pm[4 + j] + Wm[4 * i + 2] * Pm[8 + j] + Wm[4 * i + 3] * Pm[12 + j];
-    } else if (lane >= 16 && lane < 25) {
-        s->sh[lane - 16] = sh_coeffs[(size_t)sh_row * 9 + lane - 16];
-    }
-}
-
 // clip-space gradient (x, y, -, w) -> world-space xyz
 __device__ __forceinline__ float3 clip_to_world(const float* M, float gx, float gy, float gw) {
     return make_float3(M[0] * gx + M[1] * gy + M[3] * gw, M[4] * gx + M[5] * gy + M[7] * gw,
@@ -254,15 +248,40 @@ __device__ __forceinline__ TileCtx tile_decode(uint32_t e, int nx, int ny) {
     return tc;
 }
 
+// Unit of work of the persistent pixel kernels: one warp = one 16x2 strip of a 16x16 tile; warps are independent
+// workers (no block barrier anywhere in the pixel passes).
+struct Strip {
+    TileCtx tc;
+    int lane, wib;   // lane in warp, warp in block
+    int lx, ly;      // pixel position inside the tile
+    int tid;         // ly * 16 + lx = strip * 32 + lane
+    int px, py;      // pixel position in the image
+};
+__device__ __forceinline__ bool next_strip(int& u, const uint32_t* __restrict__ list, int n_tiles, int tiles_x,
+                                           int tiles_y, Strip& st) {
+    // static striding at strip granularity: unit u, u + (grid warps), ...  (a single global cursor serialises ~10^5
+    // same-address atomics per pass; strips of one tile still land on the 8 warps of one block -> shared L1 lines)
+    if (u >= n_tiles * 8) return false;
+    const int lane = threadIdx.x & 31;
+    st.tc = tile_decode(__ldg(list + (u >> 3)), tiles_x, tiles_y);
+    const int strip = u & 7;
+    st.lane = lane; st.wib = threadIdx.x >> 5;
+    st.lx = lane & 15; st.ly = 2 * strip + (lane >> 4);
+    st.tid = strip * 32 + lane;
+    st.px = st.tc.bx * kTile + st.lx; st.py = st.tc.by * kTile + st.ly;
+    u += gridDim.x * 8;
+    return true;
+}
+
 // 32-way spread accumulators
 __device__ __forceinline__ void acc_add(double* acc, int k, float v, const TileCtx& tc) {
     if (v != 0.0f) atomicAdd(acc + k * 32 + ((tc.bx + tc.by * 7 + tc.n * 13) & 31), (double)v);
 }
 // barrier-free variant: shuffle-reduce inside the warp, one spread fp64 atomic per warp
-__device__ __forceinline__ void warp_acc_add(double* acc, int k, float v, const TileCtx& tc) {
+__device__ __forceinline__ void warp_acc_add(double* acc, int k, float v, const Strip& st) {
     v = warp_sum(v);
-    if ((tile_tid() & 31) == 0 && v != 0.0f)
-        atomicAdd(acc + k * 32 + ((tc.bx + tc.by * 7 + tc.n * 13 + (tile_tid() >> 5)) & 31), (double)v);
+    if (st.lane == 0 && v != 0.0f)
+        atomicAdd(acc + k * 32 + ((st.tc.bx + st.tc.by * 7 + st.tc.n * 13 + (st.tid >> 5)) & 31), (double)v);
 }
 __device__ __forceinline__ double acc_total(const double* acc, int k) {
     double s = 0.0;
@@ -331,8 +350,9 @@ __device__ __forceinline__ bool pair_needs_analysis(const NbrKeys& k0, const Nbr
     return (from1 ? k1.bits : k0.bits) != 0;
 }
 
-__device__ __forceinline__ void enqueue_pairs(const unsigned long long* __restrict__ zb, int px, int py, int H, int W,
-                                              const NbrKeys& self, int tid, uint32_t* q_items, int* q_n) {
+__device__ __forceinline__ void enqueue_pairs(const unsigned long long* __restrict__ zb, const Strip& st, int H, int W,
+                                              const NbrKeys& self, uint32_t* q_items, int* q_n) {
+    const int px = st.px, py = st.py, tid = st.tid;
     if (px >= W || py >= H) return;
     const int rem = py * W + px;
     if (px + 1 < W) {
@@ -343,11 +363,11 @@ __device__ __forceinline__ void enqueue_pairs(const unsigned long long* __restri
         const NbrKeys o = decode_key(zb[rem + W]);
         if (pair_needs_analysis(self, o)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 1u;
     }
-    if (threadIdx.x == 0 && px > 0) {
+    if (st.lx == 0 && px > 0) {
         const NbrKeys o = decode_key(zb[rem - 1]);
         if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 2u;
     }
-    if ((threadIdx.y & 1) == 0 && py > 0) {  // top row of this warp's strip
+    if ((st.ly & 1) == 0 && py > 0) {  // top row of this warp's strip
         const NbrKeys o = decode_key(zb[rem - W]);
         if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 3u;
     }
@@ -376,7 +396,7 @@ __device__ __forceinline__ PairItem decode_pair_item(uint32_t item, const TileCt
 // shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A); also tags the key with
 // the silhouette bits / valid flag and resets the OTHER z-buffer slot for the next iteration (no separate clear pass).
 template <int PHASE>
-__device__ __forceinline__ void shade_tile(const TileCtx tc, unsigned long long* __restrict__ zbuf,
+__device__ __forceinline__ void shade_tile(const Strip& st, unsigned long long* __restrict__ zbuf,
                                            const float4* __restrict__ pos, const float2* __restrict__ scr, float invW,
                                            float invH, const int32_t* __restrict__ tri,
                                            const int32_t* __restrict__ opp, const float* __restrict__ normals,
@@ -385,11 +405,12 @@ __device__ __forceinline__ void shade_tile(const TileCtx tc, unsigned long long*
                                            const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
                                            float4* __restrict__ plane0, float4* __restrict__ plane1,
                                            double* __restrict__ acc) {
+    const TileCtx& tc = st.tc;
     const int n = tc.n;
     const int view = __ldg(view_idx + n);
     const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;  // block-uniform address: L1 broadcast
     const int hw = H * W;
-    const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
+    const int px = st.px, py = st.py;
     float nvalid = 0.0f;
     if (px < W && py < H) {
         const int rem = py * W + px;
@@ -422,7 +443,7 @@ __device__ __forceinline__ void shade_tile(const TileCtx tc, unsigned long long*
             }
         }
     }
-    warp_acc_add(acc, 0, nvalid, tc);
+    warp_acc_add(acc, 0, nvalid, st);
 }
 
 // shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A); tags every key with the
@@ -435,7 +456,8 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
                                                         const uint32_t* __restrict__ tlist_next,
                                                         const int* __restrict__ tcount_next,
                                                         uint32_t* __restrict__ abits, uint32_t* __restrict__ alist,
-                                                        int* __restrict__ acount, int tiles_x, int tiles_y,
+                                                        int* __restrict__ acount, int* __restrict__ cursors,
+                                                        int tiles_x, int tiles_y,
                                                         const float4* __restrict__ pos,
                                                         const float2* __restrict__ scr, float invW, float invH,
                                                         const int32_t* __restrict__ tri,
@@ -448,24 +470,25 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
                                                         const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
                                                         float4* __restrict__ plane0, float4* __restrict__ plane1,
                                                         double* __restrict__ acc) {
+    // units = 16x2 strips; two global cursors (reset pass of the other slot, shade pass of this slot)
+    Strip st;
+    const int u0 = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int nd = *tcount_next;
-    for (int it = blockIdx.x; it < nd; it += gridDim.x) {
-        const TileCtx tc = tile_decode(tlist_next[it], tiles_x, tiles_y);
-        const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
-        if (px < W && py < H) zbuf_next[((size_t)tc.n * H + py) * W + px] = ZB_EMPTY;
-    }
+    int u = u0;
+    while (next_strip(u, tlist_next, nd, tiles_x, tiles_y, st))
+        if (st.px < W && st.py < H) zbuf_next[((size_t)st.tc.n * H + st.py) * W + st.px] = ZB_EMPTY;
     const int nc = *tcount;
-    for (int it = blockIdx.x; it < nc; it += gridDim.x) {
-        const TileCtx tc = tile_decode(tlist[it], tiles_x, tiles_y);
-        tile_mark_active(tc, tile_tid(), abits, alist, acount);
-        shade_tile<PHASE>(tc, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
-                          plane1, acc);
+    u = u0;
+    while (next_strip(u, tlist, nc, tiles_x, tiles_y, st)) {
+        if (st.tid < 5) tile_mark_active(st.tc, st.tid, abits, alist, acount);  // strip 0 of the tile dilates it
+        shade_tile<PHASE>(st, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, masks, sh_coeffs, view_idx, sh_idx, V, T, H,
+                          W, plane0, plane1, acc);
     }
 }
 
 template <int PHASE>
 __device__ __forceinline__ void aa_loss_tile(
-    const TileCtx tc, const unsigned long long* __restrict__ zbuf,
+    const Strip& st, const unsigned long long* __restrict__ zbuf,
     const float2* __restrict__ scr, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
@@ -474,36 +497,38 @@ __device__ __forceinline__ void aa_loss_tile(
     const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask,
     uint32_t* q_items, int& q_n, float (*blend)[PHASE == 1 ? 4 : 6]) {
     constexpr int NC = PHASE == 1 ? 4 : 6;  // blended channels: (b,g,r,coverage) or (normal xyz, albedo bgr)
+    const TileCtx& tc = st.tc;
     const int n = tc.n;
     const int tiles = tc.nx * tc.ny;
     const int view = __ldg(view_idx + n);
-    const int tid = tile_tid();
+    const int tid = st.tid, lane = st.lane;  // blend[] is this warp's: indexed by lane
     const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;  // block-uniform address: L1 broadcast
     const int hw = H * W;
-    const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
+    const int px = st.px, py = st.py;
     const bool inb = px < W && py < H;
     const size_t base = (size_t)n * hw;
     const unsigned long long* zb = zbuf + base;
     const int rem = py * W + px;
     NbrKeys self = decode_key(ZB_EMPTY);
     if (inb) self = decode_key(zb[rem]);
-    enqueue_pairs(zb, px, py, H, W, self, tid, q_items, &q_n);
+    enqueue_pairs(zb, st, H, W, self, q_items, &q_n);
     __syncwarp();
     // analysis of the queued pairs spread over the lanes; the receiver's blend lands in shared memory
     const int nq = q_n;
     if (nq > 0) {  // warp-uniform
 #pragma unroll
-        for (int c = 0; c < NC; c++) blend[tid][c] = 0.0f;
+        for (int c = 0; c < NC; c++) blend[lane][c] = 0.0f;
         __syncwarp();
         const AAProjScreen proj{scr + (size_t)n * V};
-        for (int e = tid & 31; e < nq; e += 32) {
+        for (int e = lane; e < nq; e += 32) {
             const PairItem it = decode_pair_item(q_items[e], tc);
             const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
             const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
             AAPair pr;
             if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, proj, tri, opp, V, T, H, W, pr)) continue;
-            const int recv = pr.alpha > 0.0f ? it.tid0 : it.tid1;
-            if (recv < 0) continue;  // the receiver belongs to another warp's strip
+            const int recv_tid = pr.alpha > 0.0f ? it.tid0 : it.tid1;
+            if (recv_tid < 0) continue;  // the receiver belongs to another warp's strip
+            const int recv = recv_tid & 31;
             // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
             float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, s0 = f0, s1 = f0;
             if (k0.tri >= 0) { f0 = plane0[base + r0]; if (PHASE == 0) f1 = plane1[base + r0]; }
@@ -520,7 +545,7 @@ __device__ __forceinline__ void aa_loss_tile(
             }
         }
         __syncwarp();
-        if ((tid & 31) == 0) q_n = 0;
+        if (lane == 0) q_n = 0;
     }
     float abs_sum = 0.0f, msk_sum = 0.0f;
     float gc[9];
@@ -537,9 +562,9 @@ __device__ __forceinline__ void aa_loss_tile(
         float4 a0 = c0, a1 = c1;  // antialiased values
         float amask = self.tri >= 0 ? 1.0f : 0.0f;
         if (nq > 0) {
-            a0.x += blend[tid][0]; a0.y += blend[tid][1]; a0.z += blend[tid][2];
-            if (PHASE == 1) amask += blend[tid][3];
-            else { a1.x += blend[tid][3]; a1.y += blend[tid][4]; a1.z += blend[tid][5]; }
+            a0.x += blend[lane][0]; a0.y += blend[lane][1]; a0.z += blend[lane][2];
+            if (PHASE == 1) amask += blend[lane][3];
+            else { a1.x += blend[lane][3]; a1.y += blend[lane][4]; a1.z += blend[lane][5]; }
         }
         const bool valid = self.valid;
         const float* img = imgs + ((size_t)view * hw + rem) * 3;
@@ -582,18 +607,18 @@ __device__ __forceinline__ void aa_loss_tile(
             if (dbg_image) { dbg_image[pix * 3] = pred.x; dbg_image[pix * 3 + 1] = pred.y; dbg_image[pix * 3 + 2] = pred.z; }
         }
     }
-    warp_acc_add(acc, 1, abs_sum, tc);
+    warp_acc_add(acc, 1, abs_sum, st);
     if (PHASE == 1) {
-        warp_acc_add(acc, 2, msk_sum, tc);
+        warp_acc_add(acc, 2, msk_sum, st);
         // this tile is accounted for explicitly: remove its constant share (exact in fp64)
-        if (tid == 0)
+        if (tid == 0)  // strip 0, lane 0: once per tile
             atomicAdd(acc + 7 * 32 + ((tc.bx + tc.by * 7 + tc.n * 13) & 31),
                       view_vm2[(size_t)view * (tiles + 1) + tile_index(tc)]);
     } else {
 #pragma unroll
         for (int k = 0; k < 9; k++) {
             const float sk = warp_sum(gc[k]);
-            if ((tid & 31) == 0 && sk != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, sk);
+            if (lane == 0 && sk != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, sk);
         }
     }
     __syncwarp();  // blend[] / q_items / q_n of this warp are rewritten by its next tile
@@ -603,7 +628,7 @@ __device__ __forceinline__ void aa_loss_tile(
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
-    int tiles_x, int tiles_y, const float2* __restrict__ scr, const int32_t* __restrict__ tri,
+    int* __restrict__ cursors, int tiles_x, int tiles_y, const float2* __restrict__ scr, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
@@ -611,17 +636,17 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask) {
     __shared__ uint32_t q_items[8][kPairQueue];
     __shared__ int q_n[8];
-    __shared__ float blend[kTile * kTile][PHASE == 1 ? 4 : 6];
-    const int warp = tile_tid() >> 5;
-    if ((tile_tid() & 31) == 0) q_n[warp] = 0;
+    __shared__ float blend[8][32][PHASE == 1 ? 4 : 6];
+    const int wib = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) q_n[wib] = 0;
     __syncwarp();
     const int na = *acount;
-    for (int it = blockIdx.x; it < na; it += gridDim.x) {
-        const TileCtx tc = tile_decode(alist[it], tiles_x, tiles_y);
-        aa_loss_tile<PHASE>(tc, zbuf, scr, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
-                            plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items[warp], q_n[warp],
-                            blend);
-    }
+    Strip st;
+    int u = blockIdx.x * 8 + wib;
+    while (next_strip(u, alist, na, tiles_x, tiles_y, st))
+        aa_loss_tile<PHASE>(st, zbuf, scr, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
+                            plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items[wib], q_n[wib],
+                            blend[wib]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,18 +655,21 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
 __device__ __forceinline__ void pixel_bwd_tile(
-    const TileCtx tc, const unsigned long long* __restrict__ zbuf,
+    const Strip& st, const unsigned long long* __restrict__ zbuf,
     const float4* __restrict__ pos, const float2* __restrict__ scr, float invW, float invH, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
-    const float* __restrict__ w2cs, const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
+    const float* __restrict__ sh_coeffs,
     const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
     const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
-    const float4* __restrict__ gplane1, float4* __restrict__ G, ViewCtx& ctx, uint32_t* q_items, int& q_n,
-    float (*gblend)[3]) {
+    const float4* __restrict__ gplane1, float4* __restrict__ G, const float* __restrict__ viewM, uint32_t* q_items,
+    int& q_n, float (*gblend)[3]) {
+    const TileCtx& tc = st.tc;
     const int n = tc.n;
-    const int tid = tile_tid();
+    const int lane = st.lane;  // gblend[] is this warp's: indexed by lane
+    const float* M = viewM + (size_t)n * kViewM;                                // warp-uniform addresses: L1 broadcast
+    const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
     const int hw = H * W;
-    const int px = tc.bx * kTile + threadIdx.x, py = tc.by * kTile + threadIdx.y;
+    const int px = st.px, py = st.py;
     const bool inb = px < W && py < H;
     const int rem = py * W + px;
     const size_t base = (size_t)n * hw;
@@ -651,14 +679,14 @@ __device__ __forceinline__ void pixel_bwd_tile(
     if (inb) self = decode_key(zb[rem]);
     const float4* Pv = pos + (size_t)n * V;
     const float* P = reinterpret_cast<const float*>(Pv);
-    enqueue_pairs(zb, px, py, H, W, self, tid, q_items, &q_n);
+    enqueue_pairs(zb, st, H, W, self, q_items, &q_n);
     __syncwarp();
     const int nq = q_n;
     if (nq > 0) {  // warp-uniform
-        gblend[tid][0] = 0.0f; gblend[tid][1] = 0.0f; gblend[tid][2] = 0.0f;
+        gblend[lane][0] = 0.0f; gblend[lane][1] = 0.0f; gblend[lane][2] = 0.0f;
         __syncwarp();
     }
-    for (int e = tid & 31; e < nq; e += 32) {
+    for (int e = lane; e < nq; e += 32) {
         const PairItem it = decode_pair_item(q_items[e], tc);
         const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
         const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
@@ -669,14 +697,14 @@ __device__ __forceinline__ void pixel_bwd_tile(
         const float4 gr = (PHASE == 1) ? gplane0[base + recv] : gplane1[base + recv];
         // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g
         if (it.tid0 >= 0) {
-            atomicAdd(&gblend[it.tid0][0], -pr.alpha * gr.x);
-            atomicAdd(&gblend[it.tid0][1], -pr.alpha * gr.y);
-            atomicAdd(&gblend[it.tid0][2], -pr.alpha * gr.z);
+            atomicAdd(&gblend[it.tid0 & 31][0], -pr.alpha * gr.x);
+            atomicAdd(&gblend[it.tid0 & 31][1], -pr.alpha * gr.y);
+            atomicAdd(&gblend[it.tid0 & 31][2], -pr.alpha * gr.z);
         }
         if (it.tid1 >= 0) {
-            atomicAdd(&gblend[it.tid1][0], pr.alpha * gr.x);
-            atomicAdd(&gblend[it.tid1][1], pr.alpha * gr.y);
-            atomicAdd(&gblend[it.tid1][2], pr.alpha * gr.z);
+            atomicAdd(&gblend[it.tid1 & 31][0], pr.alpha * gr.x);
+            atomicAdd(&gblend[it.tid1 & 31][1], pr.alpha * gr.y);
+            atomicAdd(&gblend[it.tid1 & 31][2], pr.alpha * gr.z);
         }
         if (PHASE == 1 && it.tid0 >= 0 && !pr.clamped) {
             // position gradient: the warp whose strip holds the pair's first pixel scatters it
@@ -688,8 +716,8 @@ __device__ __forceinline__ void pixel_bwd_tile(
             if (dd_img != 0.0f || dd_msk != 0.0f) {
                 float4 e1, e2;
                 aa_pos_grad(pr, it.qx, it.qy, it.d, P, H, W, 1.0f, e1, e2);
-                const float3 w1 = clip_to_world(ctx.M, e1.x, e1.y, e1.w);
-                const float3 w2 = clip_to_world(ctx.M, e2.x, e2.y, e2.w);
+                const float3 w1 = clip_to_world(M, e1.x, e1.y, e1.w);
+                const float3 w2 = clip_to_world(M, e2.x, e2.y, e2.w);
                 atomicAdd(G + 3 * (size_t)pr.i1, make_float4(dd_img * w1.x, dd_img * w1.y, dd_img * w1.z, dd_msk * w1.x));
                 atomicAdd(G + 3 * (size_t)pr.i1 + 1, make_float4(dd_msk * w1.y, dd_msk * w1.z, 0.f, 0.f));
                 atomicAdd(G + 3 * (size_t)pr.i2, make_float4(dd_img * w2.x, dd_img * w2.y, dd_img * w2.z, dd_msk * w2.x));
@@ -700,8 +728,8 @@ __device__ __forceinline__ void pixel_bwd_tile(
     float3 gb = make_float3(0.f, 0.f, 0.f);
     if (nq > 0) {
         __syncwarp();
-        gb = make_float3(gblend[tid][0], gblend[tid][1], gblend[tid][2]);
-        if ((tid & 31) == 0) q_n = 0;
+        gb = make_float3(gblend[lane][0], gblend[lane][1], gblend[lane][2]);
+        if (lane == 0) q_n = 0;
         __syncwarp();  // gblend[] / q_items of this warp are rewritten by its next tile
     }
     const bool covered = self.tri >= 0;
@@ -734,7 +762,6 @@ __device__ __forceinline__ void pixel_bwd_tile(
     const float len = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
     const float inv = 1.0f / fmaxf(len, 1e-12f);
     const float nx = m.x * inv, ny = m.y * inv, nz = m.z * inv;
-    const float* c = ctx.sh;
     const float r = sh_radiance(c, nx, ny, nz);
     const float3 ga = make_float3(g0.x * r, g0.y * r, g0.z * r);           // d/d(interpolated albedo)
     const float gr = g0.x * a.x + g0.y * a.y + g0.z * a.z;                 // d/d(radiance)
@@ -774,9 +801,9 @@ __device__ __forceinline__ void pixel_bwd_tile(
     const float g0y = gbb * (q1x - q2x) + gb1 * q2x;
     const float g1y = gbb * (q2x - q0x) - gb0 * q2x;
     const float g2y = gbb * (q0x - q1x) + gb0 * q1x - gb1 * q0x;
-    const float3 w0 = clip_to_world(ctx.M, g0x, g0y, -fx * g0x - fy * g0y);
-    const float3 w1 = clip_to_world(ctx.M, g1x, g1y, -fx * g1x - fy * g1y);
-    const float3 w2 = clip_to_world(ctx.M, g2x, g2y, -fx * g2x - fy * g2y);
+    const float3 w0 = clip_to_world(M, g0x, g0y, -fx * g0x - fy * g0y);
+    const float3 w1 = clip_to_world(M, g1x, g1y, -fx * g1x - fy * g1y);
+    const float3 w2 = clip_to_world(M, g2x, g2y, -fx * g2x - fy * g2y);
     float4* G0 = G + 3 * (size_t)q.i0; float4* G1 = G + 3 * (size_t)q.i1; float4* G2 = G + 3 * (size_t)q.i2;
     atomicAdd(G0, make_float4(w0.x, w0.y, w0.z, 0.f));
     atomicAdd(G0 + 1, make_float4(0.f, 0.f, q.u * gm.x, q.u * gm.y));
@@ -793,32 +820,25 @@ __device__ __forceinline__ void pixel_bwd_tile(
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
     const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
-    int tiles_x, int tiles_y, const float4* __restrict__ pos, const float2* __restrict__ scr, float invW, float invH,
-    const int32_t* __restrict__ tri,
+    int* __restrict__ cursors, int tiles_x, int tiles_y, const float4* __restrict__ pos, const float2* __restrict__ scr,
+    float invW, float invH, const float* __restrict__ viewM, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
-    const float* __restrict__ w2cs, const float* __restrict__ projs, const float* __restrict__ sh_coeffs,
+    const float* __restrict__ sh_coeffs,
     const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
     const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
     const float4* __restrict__ gplane1, float4* __restrict__ G) {
-    __shared__ ViewCtx ctx[8];  // per warp: warps of a block drift apart (no block barrier) and may be on different views
     __shared__ uint32_t q_items[8][kPairQueue];
     __shared__ int q_n[8];
-    __shared__ float gblend[kTile * kTile][3];  // pair terms of d(loss)/d(pre-antialias colour | albedo)
-    const int warp = tile_tid() >> 5;
-    if ((tile_tid() & 31) == 0) q_n[warp] = 0;
+    __shared__ float gblend[8][32][3];  // pair terms of d(loss)/d(pre-antialias colour | albedo), per warp
+    const int wib = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) q_n[wib] = 0;
+    __syncwarp();
     const int na = *acount;
-    int ctx_n = -1;
-    for (int it = blockIdx.x; it < na; it += gridDim.x) {
-        const TileCtx tc = tile_decode(alist[it], tiles_x, tiles_y);
-        if (tc.n != ctx_n) {  // warp-uniform: per-view matrices / SH row change rarely along the list
-            __syncwarp();
-            load_view_ctx(&ctx[warp], w2cs, projs, sh_coeffs, __ldg(view_idx + tc.n), __ldg(sh_idx + tc.n));
-            __syncwarp();
-            ctx_n = tc.n;
-        }
-        pixel_bwd_tile<PHASE>(tc, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, w2cs, projs, sh_coeffs, view_idx, sh_idx, V, T, H, W,
-                              plane0, plane1, gplane0, gplane1, G, ctx[warp], q_items[warp], q_n[warp], gblend);
-    }
+    Strip st;
+    int u = blockIdx.x * 8 + wib;
+    while (next_strip(u, alist, na, tiles_x, tiles_y, st))
+        pixel_bwd_tile<PHASE>(st, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, sh_coeffs, view_idx, sh_idx, V, T, H,
+                              W, plane0, plane1, gplane0, gplane1, G, viewM, q_items[wib], q_n[wib], gblend[wib]);
 }
 
 __global__ void ham_finalize_scalars_kernel(const double* __restrict__ acc, const double* __restrict__ view_vm2,
@@ -1204,7 +1224,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     if (rc) return rc;
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
     ham_transform_kernel<<<dim3(cdiv(V, 256), n), 256, 0, st>>>(ws.vertices, b->w2cs, b->projs, b->view_idx, V, H, W,
-                                                                ws.pos, ws.snap, ws.scr);
+                                                                ws.pos, ws.snap, ws.scr, ws.viewM);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 2: transform
     rc = launch_raster_coverage_snapped(ws.pos, ws.snap, b->tri, n, V, T, H, W, zcur, ws.tbits[cur], ws.tlist[cur],
@@ -1214,9 +1234,9 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     static const int g_shade = persistent_blocks(ham_shade_kernel<PHASE>);
     static const int g_aa = persistent_blocks(ham_aa_loss_kernel<PHASE>);
     static const int g_bwd = persistent_blocks(ham_pixel_bwd_kernel<PHASE>);
-    const dim3 pblock(kTile, kTile);
+    const int pblock = kTile * kTile;  // 8 warps = 8 independent strip workers
     ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt],
-                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos,
+                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.pos,
                                                       ws.scr, invW, invH, b->tri, b->opp, ws.normals, b->albedo,
                                                       b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W,
                                                       ws.plane[0], ws.plane[1], ws.acc);
@@ -1224,15 +1244,15 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     FMHR_STAGE_MARK();  // 4: shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.scr, b->tri, b->opp, b->imgs, b->valid_masks,
+    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.scr, b->tri, b->opp, b->imgs, b->valid_masks,
                                                      b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
                                                      ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(zcur, ws.alist, ws.acount, tiles_x, tiles_y, ws.pos,
-                                                              ws.scr, invW, invH, b->tri, b->opp, ws.normals, b->albedo,
-                                                           b->w2cs, b->projs, b->sh_coeffs, b->view_idx, sh_idx, V, T,
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(zcur, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.pos,
+                                                              ws.scr, invW, invH, ws.viewM, b->tri, b->opp, ws.normals, b->albedo,
+                                                           b->sh_coeffs, b->view_idx, sh_idx, V, T,
                                                            H, W, ws.plane[0], ws.plane[1], g0, g1, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
     }

@@ -18,7 +18,7 @@ int launch_raster_coverage_snapped(const float4* pos, const int2* snap, const in
                                    int W, unsigned long long* zbuf, uint32_t* tbits, uint32_t* tlist, int* tcount,
                                    int tiles_x, int tiles_per_view, cudaStream_t st);
 int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
-                              int V, float* normals, float* raw, cudaStream_t st);
+                              const int32_t* v2f_nbr, int V, float* normals, float* raw, cudaStream_t st);
 
 // Per-view constants of the backward pass, written once per step by the transform kernel:
 //   viewM[n][0..11] = rows 0..2 of (w2c @ proj), columns x,y,z,w : d(clip_j)/d(world_i) = M[4i+j]
@@ -138,36 +138,53 @@ __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __res
 
 // clip = ([v,1] @ w2c) @ proj, both matrices stored transposed (mesh_sfs_optim.py:262-264, get_data.py:96-97); also snaps
 // every vertex to the rasteriser's fixed-point grid once per (view, vertex) instead of once per (view, triangle corner).
+constexpr int kViewsPerBlock = 8;
 __global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restrict__ vertices,
                                                             const float* __restrict__ w2cs,
                                                             const float* __restrict__ projs,
-                                                            const int32_t* __restrict__ view_idx, int V, int H, int W,
-                                                            float4* __restrict__ pos, int2* __restrict__ snap,
-                                                            float2* __restrict__ scr, float* __restrict__ viewM) {
-    const int n = blockIdx.y;
-    const int view = __ldg(view_idx + n);
-    const float* Wm = w2cs + (size_t)view * 16;  // block-uniform addresses: broadcast loads
-    const float* Pm = projs + (size_t)view * 16;
-    if (blockIdx.x == 0 && threadIdx.x < kViewM) {
-        const int r = threadIdx.x >> 2, j = threadIdx.x & 3;
-        viewM[n * kViewM + threadIdx.x] = Wm[4 * r] * Pm[j] + Wm[4 * r + 1] * Pm[4 + j] + Wm[4 * r + 2] * Pm[8 + j] +
-                                          Wm[4 * r + 3] * Pm[12 + j];
+                                                            const int32_t* __restrict__ view_idx, int n_views, int V,
+                                                            int H, int W, float4* __restrict__ pos,
+                                                            int2* __restrict__ snap, float2* __restrict__ scr,
+                                                            float* __restrict__ viewM) {
+    // A block transforms 256 vertices into kViewsPerBlock views: the dependent preamble (view index -> matrix rows) is
+    // paid once per block and hidden behind the vertex load instead of once per (view, vertex) thread - with one view
+    // per block the kernel was 8 waves of blocks that lived for two L2 round trips each.
+    __shared__ float Wm[kViewsPerBlock][16], Pm[kViewsPerBlock][16];
+    const int n0 = blockIdx.y * kViewsPerBlock;
+    const int nv = min(kViewsPerBlock, n_views - n0);
+    {
+        const int slot = threadIdx.x >> 5, e = threadIdx.x & 31;
+        if (slot < nv) {
+            const int view = __ldg(view_idx + n0 + slot);
+            if (e < 16) Wm[slot][e] = w2cs[(size_t)view * 16 + e];
+            else Pm[slot][e - 16] = projs[(size_t)view * 16 + e - 16];
+        }
     }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (i < V) { x = vertices[3 * (size_t)i]; y = vertices[3 * (size_t)i + 1]; z = vertices[3 * (size_t)i + 2]; }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < kViewM * nv) {
+        const int slot = threadIdx.x / kViewM, k = threadIdx.x - slot * kViewM, r = k >> 2, j = k & 3;
+        viewM[(n0 + slot) * kViewM + k] = Wm[slot][4 * r] * Pm[slot][j] + Wm[slot][4 * r + 1] * Pm[slot][4 + j] +
+                                          Wm[slot][4 * r + 2] * Pm[slot][8 + j] + Wm[slot][4 * r + 3] * Pm[slot][12 + j];
+    }
     if (i >= V) return;
-    const float x = vertices[3 * (size_t)i], y = vertices[3 * (size_t)i + 1], z = vertices[3 * (size_t)i + 2];
-    float r[4], c[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) r[j] = x * __ldg(Wm + j) + y * __ldg(Wm + 4 + j) + z * __ldg(Wm + 8 + j) + __ldg(Wm + 12 + j);
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        c[j] = r[0] * __ldg(Pm + j) + r[1] * __ldg(Pm + 4 + j) + r[2] * __ldg(Pm + 8 + j) + r[3] * __ldg(Pm + 12 + j);
-    const float4 p = make_float4(c[0], c[1], c[2], c[3]);
-    pos[(size_t)n * V + i] = p;
-    int X = kSnapRejected, Y = 0;
-    if (!snap_vertex(p, (float)W * 0.5f, (float)H * 0.5f, X, Y)) X = kSnapRejected;
-    snap[(size_t)n * V + i] = make_int2(X, Y);
-    scr[(size_t)n * V + i] = aa_window_xy(p, 0.5f * (float)W, 0.5f * (float)H);
+    const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
+    for (int sl = 0; sl < nv; sl++) {
+        const float* w = Wm[sl];
+        const float* q = Pm[sl];
+        const float r0 = x * w[0] + y * w[4] + z * w[8] + w[12], r1 = x * w[1] + y * w[5] + z * w[9] + w[13];
+        const float r2 = x * w[2] + y * w[6] + z * w[10] + w[14], r3 = x * w[3] + y * w[7] + z * w[11] + w[15];
+        const float4 p = make_float4(r0 * q[0] + r1 * q[4] + r2 * q[8] + r3 * q[12], r0 * q[1] + r1 * q[5] + r2 * q[9] + r3 * q[13],
+                                     r0 * q[2] + r1 * q[6] + r2 * q[10] + r3 * q[14], r0 * q[3] + r1 * q[7] + r2 * q[11] + r3 * q[15]);
+        const size_t o = (size_t)(n0 + sl) * V + i;
+        pos[o] = p;
+        int X = kSnapRejected, Y = 0;
+        if (!snap_vertex(p, hw, hh, X, Y)) X = kSnapRejected;
+        snap[o] = make_int2(X, Y);
+        scr[o] = aa_window_xy(p, hw, hh);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -928,7 +945,7 @@ __device__ __forceinline__ float sub_sum(float v) {
 __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
     fmhr_ham_config cfg, const float* __restrict__ vertices, const float* __restrict__ delta,
     const float* __restrict__ albedo, const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr,
-    const int32_t* __restrict__ v2f_idx, const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx,
+    const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx,
     const float* __restrict__ raw, const float* __restrict__ packed, float* __restrict__ yhat_v,
     float* __restrict__ yhat_a, float* __restrict__ gN, double* __restrict__ acc, int32_t* __restrict__ adam_step,
     float* __restrict__ adam_sc) {
@@ -951,10 +968,10 @@ __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
         // edge hinge (mesh_sfs_optim.py:296-302): every half-edge is seen from both of its endpoints -> weight 1/2
         const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
         for (int j = fb + sub; j < fe; j += kLPV) {
-            const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
+            const int2 nb = __ldg(v2f_nbr + j);
 #pragma unroll
             for (int s = 1; s <= 2; s++) {
-                const float3 o = ldf3(vertices + 3 * (size_t)__ldg(tri + 3 * t + (k + s) % 3));
+                const float3 o = ldf3(vertices + 3 * (size_t)(s == 1 ? nb.x : nb.y));
                 const float dx = vi.x - o.x, dy = vi.y - o.y, dz = vi.z - o.z;
                 const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
                 le += 0.5f * fminf(fmaxf(x, 0.0f), 1.0f);
@@ -1032,8 +1049,9 @@ __device__ __forceinline__ float adam_update(float p, float g, float* m, float* 
 // pass 2: gather every gradient term per vertex (8 lanes each), then Adam on delta (phase B) and albedo
 __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
     fmhr_ham_config cfg, const float* __restrict__ vertices, float* __restrict__ delta, float* __restrict__ albedo,
-    const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr, const int32_t* __restrict__ v2f_idx,
-    const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed,
+    const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr,
+    const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx, const float* __restrict__ inv_deg,
+    const float* __restrict__ packed,
     const float* __restrict__ yhat_v, const float* __restrict__ yhat_a, const float* __restrict__ gN,
     float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
     const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad) {
@@ -1061,7 +1079,7 @@ __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
         const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
         for (int q = b + sub; q < e; q += kLPV) {
             const int j = __ldg(v2v_idx + q);
-            const float invd = 1.0f / (float)(__ldg(v2v_ptr + j + 1) - __ldg(v2v_ptr + j));
+            const float invd = __ldg(inv_deg + j);
             const float3 ya = ldf3(yhat_a + 3 * (size_t)j);
             la.x += ya.x * invd; la.y += ya.y * invd; la.z += ya.z * invd;
             if (cfg.phase == 1) {
@@ -1074,8 +1092,8 @@ __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
             const float3 gi = ldf3(gN + 3 * (size_t)i);
             const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
             for (int j = fb + sub; j < fe; j += kLPV) {
-                const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
-                const int ia = __ldg(tri + 3 * t + (k + 1) % 3), ib = __ldg(tri + 3 * t + (k + 2) % 3);
+                const int2 nb = __ldg(v2f_nbr + j);
+                const int ia = nb.x, ib = nb.y;
                 const float3 pa = ldf3(vertices + 3 * (size_t)ia), pb = ldf3(vertices + 3 * (size_t)ib);
                 const float3 ka = ldf3(gN + 3 * (size_t)ia), kb = ldf3(gN + 3 * (size_t)ib);
                 const float3 Gs = make_float3(gi.x + ka.x + kb.x, gi.y + ka.y + kb.y, gi.z + ka.z + kb.z);
@@ -1190,7 +1208,7 @@ extern "C" size_t fmhr_ham_packed_floats(const fmhr_ham_config* cfg) {
 
 static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b) {
     FMHR_CHECK_ARG(b != nullptr);
-    FMHR_CHECK_ARG(b->tri && b->opp && b->v2f_ptr && b->v2f_idx && b->v2v_ptr && b->v2v_idx);
+    FMHR_CHECK_ARG(b->tri && b->opp && b->v2f_ptr && b->v2f_idx && b->v2v_ptr && b->v2v_idx && b->v2f_nbr && b->inv_deg);
     FMHR_CHECK_ARG(b->vertices_tmp && b->delta && b->albedo && b->sh_coeffs && b->adam_m && b->adam_v && b->adam_step);
     FMHR_CHECK_ARG(b->imgs && b->masks && b->valid_masks && b->w2cs && b->projs && b->view_idx && b->view_vm2);
     FMHR_CHECK_ARG(b->packed && b->losses && b->workspace);
@@ -1220,11 +1238,11 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         b->vertices_tmp, b->delta, 3 * V, ws.vertices, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
         (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2);
     FMHR_LAUNCH_CHECK();
-    int rc = launch_vertex_normals_fwd(ws.vertices, b->tri, b->v2f_ptr, b->v2f_idx, V, ws.normals, ws.raw, st);
+    int rc = launch_vertex_normals_fwd(ws.vertices, b->tri, b->v2f_ptr, b->v2f_idx, b->v2f_nbr, V, ws.normals, ws.raw, st);
     if (rc) return rc;
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
-    ham_transform_kernel<<<dim3(cdiv(V, 256), n), 256, 0, st>>>(ws.vertices, b->w2cs, b->projs, b->view_idx, V, H, W,
-                                                                ws.pos, ws.snap, ws.scr, ws.viewM);
+    ham_transform_kernel<<<dim3(cdiv(V, 256), cdiv(n, kViewsPerBlock)), 256, 0, st>>>(
+        ws.vertices, b->w2cs, b->projs, b->view_idx, n, V, H, W, ws.pos, ws.snap, ws.scr, ws.viewM);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 2: transform
     rc = launch_raster_coverage_snapped(ws.pos, ws.snap, b->tri, n, V, T, H, W, zcur, ws.tbits[cur], ws.tlist[cur],
@@ -1309,13 +1327,13 @@ extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_b
     ham_layout(cfg, (char*)buf->workspace, &ws);
     const int V = cfg->V;
     ham_update_pass1_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
-                                                          buf->v2f_ptr, buf->v2f_idx, buf->v2v_ptr, buf->v2v_idx,
+                                                          buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
                                                           ws.raw, buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, ws.acc,
                                                           buf->adam_step, ws.adam_sc);
     FMHR_LAUNCH_CHECK();
     ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
-                                                          buf->v2f_ptr, buf->v2f_idx, buf->v2v_ptr, buf->v2v_idx,
-                                                          buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, buf->adam_m,
+                                                          buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
+                                                          buf->inv_deg, buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, buf->adam_m,
                                                           buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)

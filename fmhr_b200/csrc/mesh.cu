@@ -80,6 +80,23 @@ __global__ void topo_v2v_finish_kernel(const unsigned long long* __restrict__ un
     }
 }
 
+// Derived adjacency that removes one dependent load from every gather loop of the vertex-domain kernels:
+//   v2f_nbr[j] = the two other corners (cyclic order) of incident face entry j  -> no tri[] lookup
+//   inv_deg[i] = 1 / degree(i) (0 for isolated vertices)                         -> no second row-pointer lookup
+__global__ void topo_derive_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_idx,
+                                   const int32_t* __restrict__ v2v_ptr, int V, int T, int2* __restrict__ v2f_nbr,
+                                   float* __restrict__ inv_deg) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < 3 * T) {
+        const int tk = v2f_idx[j], t = tk >> 2, k = tk & 3;
+        v2f_nbr[j] = make_int2(tri[3 * t + (k + 1) % 3], tri[3 * t + (k + 2) % 3]);
+    }
+    if (j < V) {
+        const int d = v2v_ptr[j + 1] - v2v_ptr[j];
+        inv_deg[j] = d > 0 ? 1.0f / (float)d : 0.0f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // vertex normals
 // ------------------------------------------------------------------------------------------------
@@ -96,7 +113,8 @@ __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a
 __global__ void __launch_bounds__(256) vertex_normals_fwd_kernel(const float* __restrict__ verts,
                                                                  const int32_t* __restrict__ tri,
                                                                  const int32_t* __restrict__ v2f_ptr,
-                                                                 const int32_t* __restrict__ v2f_idx, int V,
+                                                                 const int32_t* __restrict__ v2f_idx,
+                                                                 const int2* __restrict__ v2f_nbr, int V,
                                                                  float* __restrict__ normals, float* __restrict__ raw) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
     float3 acc = make_float3(0.f, 0.f, 0.f);
@@ -104,8 +122,12 @@ __global__ void __launch_bounds__(256) vertex_normals_fwd_kernel(const float* __
         const int b = __ldg(v2f_ptr + i), e = __ldg(v2f_ptr + i + 1);
         const float3 pk = ld3(verts + 3 * (size_t)i);
         for (int j = b + sub; j < e; j += 8) {
-            const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
-            const int ia = __ldg(tri + 3 * t + (k + 1) % 3), ib = __ldg(tri + 3 * t + (k + 2) % 3);
+            int ia, ib;
+            if (v2f_nbr) { const int2 nb = __ldg(v2f_nbr + j); ia = nb.x; ib = nb.y; }
+            else {
+                const int tk = __ldg(v2f_idx + j), t = tk >> 2, k = tk & 3;
+                ia = __ldg(tri + 3 * t + (k + 1) % 3); ib = __ldg(tri + 3 * t + (k + 2) % 3);
+            }
             // corner-k form of the face normal, models/utils.py:517-543
             acc = add3(acc, cross3(sub3(ld3(verts + 3 * (size_t)ia), pk), sub3(ld3(verts + 3 * (size_t)ib), pk)));
         }
@@ -327,8 +349,9 @@ __global__ void __launch_bounds__(256) ncc_fwd_kernel(const float* __restrict__ 
 
 // exported to ham.cu
 int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
-                              int V, float* normals, float* raw, cudaStream_t st) {
-    vertex_normals_fwd_kernel<<<cdiv((long long)V * 8, 256), 256, 0, st>>>(verts, tri, v2f_ptr, v2f_idx, V, normals, raw);
+                              const int32_t* v2f_nbr, int V, float* normals, float* raw, cudaStream_t st) {
+    vertex_normals_fwd_kernel<<<cdiv((long long)V * 8, 256), 256, 0, st>>>(verts, tri, v2f_ptr, v2f_idx,
+                                                                           (const int2*)v2f_nbr, V, normals, raw);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }
@@ -413,11 +436,20 @@ extern "C" int fmhr_mesh_topology_build(const int32_t* tri, int V, int T, int32_
     return FMHR_OK;
 }
 
+extern "C" int fmhr_mesh_topology_derive(const int32_t* tri, const int32_t* v2f_idx, const int32_t* v2v_ptr, int V, int T,
+                                         int32_t* v2f_nbr, float* inv_deg, fmhr_stream_t stream) {
+    FMHR_CHECK_ARG(tri && v2f_idx && v2v_ptr && v2f_nbr && inv_deg && V > 0 && T > 0);
+    topo_derive_kernel<<<cdiv(max(3 * T, V), 256), 256, 0, (cudaStream_t)stream>>>(tri, v2f_idx, v2v_ptr, V, T,
+                                                                                   (int2*)v2f_nbr, inv_deg);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
 extern "C" int fmhr_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr,
                                        const int32_t* v2f_idx, int V, int T, float* normals, float* raw,
                                        fmhr_stream_t stream) {
     FMHR_CHECK_ARG(verts && tri && v2f_ptr && v2f_idx && normals && V > 0 && T > 0);
-    return launch_vertex_normals_fwd(verts, tri, v2f_ptr, v2f_idx, V, normals, raw, (cudaStream_t)stream);
+    return launch_vertex_normals_fwd(verts, tri, v2f_ptr, v2f_idx, nullptr, V, normals, raw, (cudaStream_t)stream);
 }
 
 extern "C" int fmhr_vertex_normals_bwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr,

@@ -52,7 +52,7 @@ __device__ __forceinline__ void cover_bbox(int X0, int Y0, int X1, int Y1, int X
 //  * tile hits are collected in a per-block shared-memory bitmap; at block end the tiles not yet in the slot's global
 //    bitmap are appended to its work list (a few atomics per block instead of one store per fragment).
 // ------------------------------------------------------------------------------------------------
-constexpr int kFragQueue = 96;  // per-warp capacity; overflowing fragments are resolved in place
+constexpr int kFragQueue = 160;  // per-warp capacity (128 triangles per warp); overflowing fragments are resolved in place
 
 __device__ __forceinline__ void resolve_fragment(const float4* __restrict__ P, const int32_t* __restrict__ tri, int t,
                                                  int px, int py, int W, float invW, float invH,
@@ -94,13 +94,14 @@ __device__ __forceinline__ void cover_bbox_queue(int X0, int Y0, int X1, int Y1,
     }
 }
 
-__device__ __forceinline__ void coverage_snapped_one(const float4* __restrict__ P, const int2* __restrict__ S,
-                                                     const int32_t* __restrict__ tri, int V, int H, int W, int t,
-                                                     float invW, float invH, unsigned long long* __restrict__ zb,
-                                                     unsigned int* tbits, int tiles_x, int* qcount, uint2* queue) {
-    const int i0 = __ldg(tri + 3 * t), i1 = __ldg(tri + 3 * t + 1), i2 = __ldg(tri + 3 * t + 2);
-    if ((unsigned)i0 >= (unsigned)V || (unsigned)i1 >= (unsigned)V || (unsigned)i2 >= (unsigned)V) return;
-    const int2 s0 = __ldg(S + i0), s1 = __ldg(S + i1), s2 = __ldg(S + i2);
+constexpr int kTriPerThread = 4;  // triangles per thread: their 12 index loads and 12 snapped-vertex gathers are issued
+                                  // back to back, so a block pays the two dependent L2 round trips once for 1024
+                                  // triangles instead of once for 256 (the kernel's time was waves x block latency)
+
+__device__ __forceinline__ void coverage_snapped_test(int t, int2 s0, int2 s1, int2 s2, const float4* __restrict__ P,
+                                                      const int32_t* __restrict__ tri, int H, int W, float invW,
+                                                      float invH, unsigned long long* __restrict__ zb,
+                                                      unsigned int* tbits, int tiles_x, int* qcount, uint2* queue) {
     if (s0.x == kSnapRejected || s1.x == kSnapRejected || s2.x == kSnapRejected) return;
     int X0 = s0.x, Y0 = s0.y, X1 = s1.x, Y1 = s1.y, X2 = s2.x, Y2 = s2.y;
     const int minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
@@ -130,7 +131,7 @@ __device__ __forceinline__ void coverage_snapped_one(const float4* __restrict__ 
 __global__ void __launch_bounds__(256) raster_coverage_snapped_kernel(const float4* __restrict__ pos,
                                                                       const int2* __restrict__ snap,
                                                                       const int32_t* __restrict__ tri, int V, int T,
-                                                                      int H, int W,
+                                                                      int H, int W, float invW, float invH,
                                                                       unsigned long long* __restrict__ zbuf,
                                                                       uint32_t* __restrict__ gbits,
                                                                       uint32_t* __restrict__ glist,
@@ -143,15 +144,33 @@ __global__ void __launch_bounds__(256) raster_coverage_snapped_kernel(const floa
     for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) qcount[warp] = 0;
-    __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = blockIdx.y;
-    const float invW = xd(1.0f, (float)W), invH = xd(1.0f, (float)H);
+    const int2* S = snap + (size_t)n * V;
+    // ---- batched loads: indices of all kTriPerThread triangles, then their snapped vertices
+    int tt[kTriPerThread], i0[kTriPerThread], i1[kTriPerThread], i2[kTriPerThread];
+#pragma unroll
+    for (int k = 0; k < kTriPerThread; k++) {
+        tt[k] = (blockIdx.x * kTriPerThread + k) * blockDim.x + threadIdx.x;
+        const bool ok = tt[k] < T;
+        i0[k] = ok ? __ldg(tri + 3 * tt[k]) : -1;
+        i1[k] = ok ? __ldg(tri + 3 * tt[k] + 1) : -1;
+        i2[k] = ok ? __ldg(tri + 3 * tt[k] + 2) : -1;
+    }
+    int2 s0[kTriPerThread], s1[kTriPerThread], s2[kTriPerThread];
+#pragma unroll
+    for (int k = 0; k < kTriPerThread; k++) {
+        const bool ok = (unsigned)i0[k] < (unsigned)V && (unsigned)i1[k] < (unsigned)V && (unsigned)i2[k] < (unsigned)V;
+        s0[k] = ok ? __ldg(S + i0[k]) : make_int2(kSnapRejected, 0);
+        s1[k] = ok ? __ldg(S + i1[k]) : make_int2(kSnapRejected, 0);
+        s2[k] = ok ? __ldg(S + i2[k]) : make_int2(kSnapRejected, 0);
+    }
+    __syncthreads();  // tbits / qcount initialised
     unsigned long long* zb = zbuf + (size_t)n * H * W;
     const float4* P = pos + (size_t)n * V;
-    if (t < T)
-        coverage_snapped_one(P, snap + (size_t)n * V, tri, V, H, W, t, invW, invH, zb, tbits, tiles_x, &qcount[warp],
-                             queue[warp]);
+#pragma unroll
+    for (int k = 0; k < kTriPerThread; k++)
+        coverage_snapped_test(tt[k], s0[k], s1[k], s2[k], P, tri, H, W, invW, invH, zb, tbits, tiles_x, &qcount[warp],
+                              queue[warp]);
     __syncwarp();
     const int nq = min(qcount[warp], kFragQueue);
     for (int e = lane; e < nq; e += 32) {
@@ -309,14 +328,14 @@ int launch_raster_coverage(const float* pos, const int32_t* tri, int N, int V, i
 int launch_raster_coverage_snapped(const float4* pos, const int2* snap, const int32_t* tri, int N, int V, int T, int H,
                                    int W, unsigned long long* zbuf, uint32_t* tbits, uint32_t* tlist, int* tcount,
                                    int tiles_x, int tiles_per_view, cudaStream_t st) {
-    dim3 grid(cdiv(T, 256), N);
+    dim3 grid(cdiv(T, 256 * kTriPerThread), N);
     const size_t smem = (size_t)((tiles_per_view + 31) / 32) * sizeof(unsigned int);
     if (smem > 48 * 1024) {
         set_error("launch_raster_coverage_snapped: %d tiles per view exceed the shared-memory bitmap", tiles_per_view);
         return FMHR_EUNSUPPORTED;
     }
-    raster_coverage_snapped_kernel<<<grid, 256, smem, st>>>(pos, snap, tri, V, T, H, W, zbuf, tbits, tlist, tcount,
-                                                            tiles_x, tiles_per_view);
+    raster_coverage_snapped_kernel<<<grid, 256, smem, st>>>(pos, snap, tri, V, T, H, W, 1.0f / (float)W, 1.0f / (float)H,
+                                                            zbuf, tbits, tlist, tcount, tiles_x, tiles_per_view);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

@@ -47,6 +47,11 @@ class Topology:
         self.n_dir_edges = n_dir.value
         self.v2v_idx = v2v_idx[: self.n_dir_edges].clone()
         self.tri = tri
+        self.v2f_nbr = torch.empty(3 * T, 2, dtype=torch.int32, device=dev)
+        self.inv_deg = torch.empty(V, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.fmhr_mesh_topology_derive(ptr(tri), ptr(self.v2f_idx), ptr(self.v2v_ptr), V, T, ptr(self.v2f_nbr),
+                                                ptr(self.inv_deg), stream()), "mesh_topology_derive")
 
 
 _TOPO_CACHE = collections.OrderedDict()

@@ -110,6 +110,7 @@ class HamOptimizer:
         t = self.topo
         b.tri, b.opp = ptr(self.faces), ptr(t.opp)
         b.v2f_ptr, b.v2f_idx, b.v2v_ptr, b.v2v_idx = ptr(t.v2f_ptr), ptr(t.v2f_idx), ptr(t.v2v_ptr), ptr(t.v2v_idx)
+        b.v2f_nbr, b.inv_deg = ptr(t.v2f_nbr), ptr(t.inv_deg)
         b.vertices_tmp, b.delta, b.albedo, b.sh_coeffs = ptr(self.vertices_tmp), ptr(self.delta), ptr(self.albedo), ptr(self.sh_coeffs)
         b.adam_m, b.adam_v, b.adam_step = ptr(self.adam_m), ptr(self.adam_v), ptr(self.adam_step)
         b.imgs = ptr(self.imgs if imgs is None else imgs)

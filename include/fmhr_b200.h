@@ -77,6 +77,11 @@ int fmhr_mesh_topology_build(const int32_t* tri, int V, int T, int32_t* opp, int
                              int32_t* v2v_ptr, int32_t* v2v_idx, int* n_dir_edges_host, void* workspace,
                              size_t workspace_bytes, fmhr_stream_t stream);
 
+/* Derived adjacency for the fused iteration (setup, after fmhr_mesh_topology_build):
+ *   v2f_nbr [3T,2] the two other corners (cyclic order) of each vertex->face entry, inv_deg [V] = 1/degree. */
+int fmhr_mesh_topology_derive(const int32_t* tri, const int32_t* v2f_idx, const int32_t* v2v_ptr, int V, int T,
+                              int32_t* v2f_nbr, float* inv_deg, fmhr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * dr.antialias(color, rast, pos, tri)                [mesh_sfs_optim.py:146-147,217-219,274,287]
  *   color [N,H,W,C], rast [N,H,W,4], pos [N,V,4], tri [T,3], opp [T,3] from fmhr_mesh_topology_build
@@ -143,6 +148,8 @@ typedef struct fmhr_ham_buffers {
     const int32_t* v2f_idx;   /* [3T] */
     const int32_t* v2v_ptr;   /* [V+1] */
     const int32_t* v2v_idx;   /* [2E] */
+    const int32_t* v2f_nbr;   /* [3T,2] from fmhr_mesh_topology_derive */
+    const float* inv_deg;     /* [V]    from fmhr_mesh_topology_derive */
     /* optimisation state */
     const float* vertices_tmp; /* [V,3] */
     float* delta;              /* [V,3] */

@@ -233,6 +233,8 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * 1000.0 / ms_per_step  # 48-view iteration equivalents per second over all ranks
     losses = opt.losses.cpu().tolist()
+    if not all(np.isfinite(losses)) or losses[6] <= 0:
+        raise SystemExit("bench.py: the optimisation state is not finite (losses %s) - refusing to report a number" % losses)
 
     # ---------------------------------------------------------------- end to end (host buffers)
     e2e = None

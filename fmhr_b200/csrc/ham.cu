@@ -152,13 +152,11 @@ __global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restr
     __shared__ float Wm[kViewsPerBlock][16], Pm[kViewsPerBlock][16];
     const int n0 = blockIdx.y * kViewsPerBlock;
     const int nv = min(kViewsPerBlock, n_views - n0);
-    {
-        const int slot = threadIdx.x >> 5, e = threadIdx.x & 31;
-        if (slot < nv) {
-            const int view = __ldg(view_idx + n0 + slot);
-            if (e < 16) Wm[slot][e] = w2cs[(size_t)view * 16 + e];
-            else Pm[slot][e - 16] = projs[(size_t)view * 16 + e - 16];
-        }
+    for (int q = threadIdx.x; q < nv * 32; q += blockDim.x) {
+        const int slot = q >> 5, e = q & 31;
+        const int view = __ldg(view_idx + n0 + slot);
+        if (e < 16) Wm[slot][e] = w2cs[(size_t)view * 16 + e];
+        else Pm[slot][e - 16] = projs[(size_t)view * 16 + e - 16];
     }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float x = 0.f, y = 0.f, z = 0.f;

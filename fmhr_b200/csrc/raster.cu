@@ -128,7 +128,7 @@ __device__ __forceinline__ void coverage_snapped_test(int t, int2 s0, int2 s1, i
     else cover_bbox_queue<long long>(X0, Y0, X1, Y1, X2, Y2, px0, px1, py0, py1, P, tri, W, invW, invH, zb, tbits, tiles_x, t, qcount, queue);
 }
 
-__global__ void __launch_bounds__(256) raster_coverage_snapped_kernel(const float4* __restrict__ pos,
+__global__ void __launch_bounds__(256, 4) raster_coverage_snapped_kernel(const float4* __restrict__ pos,
                                                                       const int2* __restrict__ snap,
                                                                       const int32_t* __restrict__ tri, int V, int T,
                                                                       int H, int W, float invW, float invH,

@@ -58,6 +58,7 @@ _SIGS = {
     "fmhr_sh_radiance_fwd": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p]),
     "fmhr_sh_radiance_bwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p]),
     "fmhr_ncc_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "fmhr_ncc_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_ham_workspace_bytes": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_packed_floats": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_reset": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),

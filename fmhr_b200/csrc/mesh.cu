@@ -347,6 +347,47 @@ __global__ void __launch_bounds__(256) ncc_fwd_kernel(const float* __restrict__ 
     if (lane == 0) ncc[warp] = cv / (sqrtf(vr) * sqrtf(vs));
 }
 
+// d(sum g * ncc)/d(src): three warp passes over the patch (means; variances / covariance; per-pixel gradient)
+__global__ void __launch_bounds__(256) ncc_bwd_kernel(const float* __restrict__ ref, const float* __restrict__ src,
+                                                      const float* __restrict__ mask, const float* __restrict__ gout,
+                                                      int Nv, int Np, int Npx, float* __restrict__ grad_src) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= Nv * Np) return;
+    const int p = warp % Np;
+    const float* r = ref + (size_t)p * Npx;
+    const float* s = src + (size_t)warp * Npx;
+    const float* m = mask + (size_t)warp * Npx;
+    float cnt = 0.f, sr = 0.f, ss = 0.f;
+    for (int k = lane; k < Npx; k += 32) {
+        const float mk = m[k];
+        cnt += mk; sr += r[k] * mk; ss += s[k] * mk;
+    }
+    cnt = warp_sum(cnt); sr = warp_sum(sr); ss = warp_sum(ss);
+    if (cnt == 0.0f) cnt = 1.0f;
+    const float rm = sr / cnt, sm = ss / cnt;
+    float vr = 0.f, vs = 0.f, cv = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int k = lane; k < Npx; k += 32) {
+        const float mk = m[k];
+        const float dr = (r[k] - rm) * mk, dsv = (s[k] - sm) * mk;
+        vr += dr * dr; vs += dsv * dsv; cv += (r[k] - rm) * (s[k] - sm) * mk;
+        s1 += dsv * mk; s2 += dr;
+    }
+    vr = warp_sum(vr) / cnt; vs = warp_sum(vs) / cnt; cv = warp_sum(cv) / cnt;
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (vr == 0.0f) vr = 1.0f;
+    if (vs == 0.0f) vs = 1.0f;
+    const float g = gout[warp];
+    const float ir = rsqrtf(vr), is = rsqrtf(vs);
+    const float c_cv = g * ir * is / cnt;                    // d/d(cov) * 1/cnt
+    const float c_vs = -g * cv * ir * is / vs / cnt;         // d/d(var_s) * 2/cnt  (the 1/2 and the 2 cancel)
+    for (int k = lane; k < Npx; k += 32) {
+        const float mk = m[k];
+        const float dcv = (r[k] - rm) * mk - mk / cnt * s2;
+        const float dvs = (s[k] - sm) * mk * mk - mk / cnt * s1;
+        grad_src[(size_t)warp * Npx + k] = c_cv * dcv + c_vs * dvs;
+    }
+}
+
 // exported to ham.cu
 int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
                               const int32_t* v2f_nbr, int V, float* normals, float* raw, cudaStream_t st) {
@@ -519,6 +560,16 @@ extern "C" int fmhr_sh_radiance_bwd(const float* coeff, int coeff_rows, const fl
     if (n == 0) return FMHR_OK;
     sh_radiance_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(coeff, coeff_rows, normal, grad_radiance, n, grad_coeff,
                                                          grad_normal);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ncc_bwd(const float* ref, const float* src, const float* src_mask, const float* grad_ncc, int Nv,
+                            int Np, int Npx, float* grad_src, fmhr_stream_t stream) {
+    FMHR_CHECK_ARG(ref && src && src_mask && grad_ncc && grad_src && Nv > 0 && Np > 0 && Npx > 0);
+    const long long threads = (long long)Nv * Np * 32;
+    ncc_bwd_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(ref, src, src_mask, grad_ncc, Nv, Np, Npx,
+                                                                         grad_src);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

@@ -173,14 +173,34 @@ def get_radiance(coeff, normal, degree=3):
     return _Radiance.apply(coeff, normal)
 
 
+class _NCC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, src, mask):
+        lib = _lib.load()
+        ref, src, mask = ref.contiguous(), src.contiguous(), mask.contiguous()
+        Nv, Np, Npx = src.shape
+        out = torch.empty(Nv, Np, dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            check(lib.fmhr_ncc_fwd(ptr(ref), ptr(src), ptr(mask), Nv, Np, Npx, ptr(out), stream()), "ncc_fwd")
+        ctx.save_for_backward(ref, src, mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        ref, src, mask = ctx.saved_tensors
+        Nv, Np, Npx = src.shape
+        grad = torch.empty_like(src)
+        dy = dy.contiguous()
+        with torch.cuda.device(src.device):
+            check(lib.fmhr_ncc_bwd(ptr(ref), ptr(src), ptr(mask), ptr(dy), Nv, Np, Npx, ptr(grad), stream()), "ncc_bwd")
+        return None, grad, None
+
+
 def NCC(ref, src, ref_valid_mask, src_valid_mask):
-    """ref [1,Np,Npx], src / src_valid_mask [Nv,Np,Npx] -> ncc [Nv,Np] (forward only; ref_valid_mask is ignored as
-    in the reference)."""
-    lib = _lib.load()
+    """ref [1,Np,Npx], src / src_valid_mask [Nv,Np,Npx] -> ncc [Nv,Np]; differentiable w.r.t. src (ref_valid_mask is
+    ignored as in the reference, models/ncc_utils.py:4-35)."""
     _lib.require_cuda(ref, src, src_valid_mask)
-    Nv, Np, Npx = src.shape
-    out = torch.empty(Nv, Np, dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
-        check(lib.fmhr_ncc_fwd(ptr(ref.contiguous()), ptr(src.contiguous()), ptr(src_valid_mask.contiguous()), Nv, Np,
-                               Npx, ptr(out), stream()), "ncc_fwd")
-    return out.squeeze()
+    if src.dim() != 3 or ref.shape[-2:] != src.shape[-2:]:
+        raise RuntimeError("fmhr_b200.NCC: ref must be [1,Np,Npx] and src [Nv,Np,Npx]")
+    return _NCC.apply(ref, src, src_valid_mask).squeeze()

@@ -119,6 +119,9 @@ int fmhr_sh_radiance_bwd(const float* coeff, int coeff_rows, const float* normal
 /* NCC (models/ncc_utils.py:4-35): ref [1,Np,Npx], src/mask [Nv,Np,Npx] -> ncc [Nv,Np]. */
 int fmhr_ncc_fwd(const float* ref, const float* src, const float* src_mask, int Nv, int Np, int Npx, float* ncc,
                  fmhr_stream_t stream);
+/* grad_src [Nv,Np,Npx] = d(sum grad_ncc * ncc)/d(src) (overwritten). */
+int fmhr_ncc_bwd(const float* ref, const float* src, const float* src_mask, const float* grad_ncc, int Nv, int Np,
+                 int Npx, float* grad_src, fmhr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused HAM iteration (mesh_sfs_optim.py:198-237 phase A, :253-310 phase B).

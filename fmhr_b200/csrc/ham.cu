@@ -31,6 +31,14 @@ struct HamWs {
     int2* snap;                // [n,V] 24.8 fixed-point window coordinates (x == INT_MIN: vertex rejected)
     float2* scr;               // [n,V] (x/w*W/2, y/w*H/2): the antialias rule's window coordinates, divide done once
     float* viewM;              // [n,12] d(clip)/d(world) per view
+    // Compact work lists of the backward pass (built by the forward passes of the same iteration):
+    uint32_t* vlist;           // [P]   pixels that feed the backward shader (phase B: valid, phase A: covered), by shade
+    uint4* plist_a;            // [P/2] blending pixel pairs found by the antialias pass: (pixel0, flags, alpha, i1)
+    uint32_t* plist_b;         // [P/2]                                                    i2
+    float4* gdelta;            // [P]   pair terms of d(loss)/d(pre-antialias value); zero outside an iteration
+    int* vcount;               // inside common_region (zeroed every step)
+    int* pcount;
+    int* status;               // bit 0: pair list overflow
     int* cursors;              // [8] work cursors of the persistent kernels (inside common_region)
     // Active-tile work lists (16x16 tiles).  slot[s]: tiles of z-buffer slot s that received fragments (bitmap for
     // de-duplication + compact list + count, filled by the coverage kernel); act: those tiles dilated by their four
@@ -86,6 +94,10 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take((size_t)c->n_views * V * 8); if (ws) ws->snap = (int2*)p;
     p = take((size_t)c->n_views * V * 8); if (ws) ws->scr = (float2*)p;
     p = take((size_t)c->n_views * kViewM * 4); if (ws) ws->viewM = (float*)p;
+    p = take(P * 4); if (ws) ws->vlist = (uint32_t*)p;
+    p = take((P / 2 + 64) * 16); if (ws) ws->plist_a = (uint4*)p;
+    p = take((P / 2 + 64) * 4); if (ws) ws->plist_b = (uint32_t*)p;
+    p = take(P * 16); if (ws) ws->gdelta = (float4*)p;
     const size_t tiles_pv = (size_t)((c->W + 15) / 16) * ((c->H + 15) / 16);
     const size_t words = (size_t)c->n_views * ((tiles_pv + 31) / 32);
     const size_t slot_bytes = 256 + align256(words * 4);
@@ -101,6 +113,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
         ws->common_region = p; ws->common_bytes = common_bytes; ws->slot_bytes = slot_bytes;
         ws->acc = (double*)p; ws->acount = (int*)(p + 8 * 32 * sizeof(double));
         ws->cursors = ws->acount + 8;  // same zeroed 256-byte slot
+        ws->vcount = ws->acount + 16; ws->pcount = ws->acount + 17; ws->status = ws->acount + 18;
         ws->abits = (uint32_t*)(p + 8 * 32 * sizeof(double) + 256);
     }
     p = take(V * 12); if (ws) ws->vertices = (float*)p;
@@ -419,8 +432,10 @@ __device__ __forceinline__ void shade_tile(const Strip& st, unsigned long long* 
                                            const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx,
                                            const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
                                            float4* __restrict__ plane0, float4* __restrict__ plane1,
-                                           double* __restrict__ acc) {
+                                           double* __restrict__ acc, bool& feeds_backward, uint32_t& pix32) {
     const TileCtx& tc = st.tc;
+    feeds_backward = false;
+    pix32 = 0u;
     const int n = tc.n;
     const int view = __ldg(view_idx + n);
     const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;  // block-uniform address: L1 broadcast
@@ -443,6 +458,8 @@ __device__ __forceinline__ void shade_tile(const Strip& st, unsigned long long* 
             const float3 a = interp3(albedo, q);
             const bool valid = __ldg(masks + (size_t)view * hw + rem) > 0.0f;
             nvalid = valid ? 1.0f : 0.0f;
+            feeds_backward = PHASE == 1 ? valid : true;  // phase A back-propagates through every covered pixel's albedo
+            pix32 = (uint32_t)pix;
             zbuf[pix] = key | ((unsigned long long)(uint32_t)g.bits << 28) | (valid ? 0x80000000ull : 0ull);
             if (PHASE == 1) {
                 float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -484,7 +501,22 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
                                                         const int32_t* __restrict__ view_idx,
                                                         const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
                                                         float4* __restrict__ plane0, float4* __restrict__ plane1,
-                                                        double* __restrict__ acc) {
+                                                        double* __restrict__ acc, uint32_t* __restrict__ vlist,
+                                                        int* __restrict__ vcount) {
+    // Pixels that feed the backward shader are collected per warp in shared memory and appended to the global compact
+    // list with one atomic per ~450 pixels; the backward pass then runs with every lane busy.
+    constexpr int kVBuf = 480;
+    __shared__ uint32_t vbuf[8][kVBuf];
+    int nbuf = 0;  // warp-uniform
+    const int wib_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+    auto flush = [&]() {
+        int base = 0;
+        if (lane_ == 0) base = atomicAdd(vcount, nbuf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane_; i < nbuf; i += 32) vlist[base + i] = vbuf[wib_][i];
+        __syncwarp();
+        nbuf = 0;
+    };
     // units = 16x2 strips; two global cursors (reset pass of the other slot, shade pass of this slot)
     Strip st;
     const int u0 = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -496,9 +528,19 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
     u = u0;
     while (next_strip(u, tlist, nc, tiles_x, tiles_y, st)) {
         if (st.tid < 5) tile_mark_active(st.tc, st.tid, abits, alist, acount);  // strip 0 of the tile dilates it
+        bool fb;
+        uint32_t pix32;
         shade_tile<PHASE>(st, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, masks, sh_coeffs, view_idx, sh_idx, V, T, H,
-                          W, plane0, plane1, acc);
+                          W, plane0, plane1, acc, fb, pix32);
+        const unsigned m = __ballot_sync(0xffffffffu, fb);
+        if (m) {
+            if (fb) vbuf[wib_][nbuf + __popc(m & ((1u << lane_) - 1u))] = pix32;
+            nbuf += __popc(m);
+            __syncwarp();
+            if (nbuf > kVBuf - 32) flush();
+        }
     }
+    if (nbuf > 0) flush();
 }
 
 template <int PHASE>
@@ -510,7 +552,8 @@ __device__ __forceinline__ void aa_loss_tile(
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
     float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
     const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask,
-    uint32_t* q_items, int& q_n, float (*blend)[PHASE == 1 ? 4 : 6]) {
+    uint32_t* q_items, int& q_n, float (*blend)[PHASE == 1 ? 4 : 6], uint4* __restrict__ plist_a,
+    uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap, int* __restrict__ status) {
     constexpr int NC = PHASE == 1 ? 4 : 6;  // blended channels: (b,g,r,coverage) or (normal xyz, albedo bgr)
     const TileCtx& tc = st.tc;
     const int n = tc.n;
@@ -541,6 +584,17 @@ __device__ __forceinline__ void aa_loss_tile(
             const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
             AAPair pr;
             if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, proj, tri, opp, V, T, H, W, pr)) continue;
+            if (it.tid0 >= 0) {  // the warp whose strip holds the pair's first pixel records it for the backward pass
+                const int slot = atomicAdd(pcount, 1);
+                if (slot < pcap) {
+                    const uint32_t flags = (uint32_t)it.d | ((uint32_t)pr.from1 << 1) | ((uint32_t)pr.clamped << 2) |
+                                           ((uint32_t)pr.di << 3);
+                    plist_a[slot] = make_uint4((uint32_t)(base + r0), flags, __float_as_uint(pr.alpha), (uint32_t)pr.i1);
+                    plist_b[slot] = (uint32_t)pr.i2;
+                } else {
+                    atomicOr(status, 1);
+                }
+            }
             const int recv_tid = pr.alpha > 0.0f ? it.tid0 : it.tid1;
             if (recv_tid < 0) continue;  // the receiver belongs to another warp's strip
             const int recv = recv_tid & 31;
@@ -648,7 +702,9 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
     float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
-    const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask) {
+    const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask,
+    uint4* __restrict__ plist_a, uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap,
+    int* __restrict__ status) {
     __shared__ uint32_t q_items[8][kPairQueue];
     __shared__ int q_n[8];
     __shared__ float blend[8][32][PHASE == 1 ? 4 : 6];
@@ -661,76 +717,55 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     while (next_strip(u, alist, na, tiles_x, tiles_y, st))
         aa_loss_tile<PHASE>(st, zbuf, scr, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
                             plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items[wib], q_n[wib],
-                            blend[wib]);
+                            blend[wib], plist_a, plist_b, pcount, pcap, status);
 }
 
 // ------------------------------------------------------------------------------------------------
 // pixel backward: antialias bwd (gather form for colours, owner-scatter for positions), shading bwd,
 // interpolate bwd, rasterize bwd; everything lands in the per-vertex world-space accumulators.
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// backward, part 1: the blending pairs recorded by the antialias pass (a few 10^4 per iteration, one thread each).
+//   * colour / albedo gradient of the two pixels of the pair -> gdelta plane (only pixels the main pass will visit);
+//   * phase B: silhouette position gradient -> world-space accumulators.
+// ------------------------------------------------------------------------------------------------
 template <int PHASE>
-__device__ __forceinline__ void pixel_bwd_tile(
-    const Strip& st, const unsigned long long* __restrict__ zbuf,
-    const float4* __restrict__ pos, const float2* __restrict__ scr, float invW, float invH, const int32_t* __restrict__ tri,
-    const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
-    const float* __restrict__ sh_coeffs,
-    const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
-    const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
-    const float4* __restrict__ gplane1, float4* __restrict__ G, const float* __restrict__ viewM, uint32_t* q_items,
-    int& q_n, float (*gblend)[3]) {
-    const TileCtx& tc = st.tc;
-    const int n = tc.n;
-    const int lane = st.lane;  // gblend[] is this warp's: indexed by lane
-    const float* M = viewM + (size_t)n * kViewM;                                // warp-uniform addresses: L1 broadcast
-    const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
+__global__ void __launch_bounds__(256) ham_pair_bwd_kernel(
+    const uint4* __restrict__ plist_a, const uint32_t* __restrict__ plist_b, const int* __restrict__ pcount, int pcap,
+    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ pos, const float* __restrict__ viewM, int V,
+    int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ gplane0,
+    const float4* __restrict__ gplane1, float4* __restrict__ gdelta, float4* __restrict__ G) {
+    const int np = min(*pcount, pcap);
     const int hw = H * W;
-    const int px = st.px, py = st.py;
-    const bool inb = px < W && py < H;
-    const int rem = py * W + px;
-    const size_t base = (size_t)n * hw;
-    const size_t pix = base + rem;
-    const unsigned long long* zb = zbuf + base;
-    NbrKeys self = decode_key(ZB_EMPTY);
-    if (inb) self = decode_key(zb[rem]);
-    const float4* Pv = pos + (size_t)n * V;
-    const float* P = reinterpret_cast<const float*>(Pv);
-    enqueue_pairs(zb, st, H, W, self, q_items, &q_n);
-    __syncwarp();
-    const int nq = q_n;
-    if (nq > 0) {  // warp-uniform
-        gblend[lane][0] = 0.0f; gblend[lane][1] = 0.0f; gblend[lane][2] = 0.0f;
-        __syncwarp();
-    }
-    for (int e = lane; e < nq; e += 32) {
-        const PairItem it = decode_pair_item(q_items[e], tc);
-        const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
-        const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < np; e += gridDim.x * blockDim.x) {
+        const uint4 a = plist_a[e];
         AAPair pr;
-        if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, AAProjScreen{scr + (size_t)n * V}, tri, opp, V, T, H, W, pr)) continue;
-        const int recv = (pr.alpha > 0.0f) ? r0 : r1;
+        const size_t pix0 = a.x;
+        const int d = (int)(a.y & 1u);
+        pr.from1 = (int)((a.y >> 1) & 1u); pr.clamped = (int)((a.y >> 2) & 1u); pr.di = (int)((a.y >> 3) & 3u);
+        pr.alpha = __uint_as_float(a.z); pr.i1 = (int)a.w; pr.i2 = (int)plist_b[e]; pr.tri = 0;
+        const size_t pix1 = pix0 + (d ? W : 1);
+        const int n = (int)(pix0 / hw);
+        const int rem0 = (int)(pix0 - (size_t)n * hw), qy = rem0 / W, qx = rem0 - qy * W;
+        const NbrKeys k0 = decode_key(zbuf[pix0]), k1 = decode_key(zbuf[pix1]);
+        const size_t recv = pr.alpha > 0.0f ? pix0 : pix1;
         // phase B blends the shaded colour (gplane0.xyz) and coverage (gplane0.w); phase A the albedo (gplane1.xyz)
-        const float4 gr = (PHASE == 1) ? gplane0[base + recv] : gplane1[base + recv];
-        // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g
-        if (it.tid0 >= 0) {
-            atomicAdd(&gblend[it.tid0 & 31][0], -pr.alpha * gr.x);
-            atomicAdd(&gblend[it.tid0 & 31][1], -pr.alpha * gr.y);
-            atomicAdd(&gblend[it.tid0 & 31][2], -pr.alpha * gr.z);
-        }
-        if (it.tid1 >= 0) {
-            atomicAdd(&gblend[it.tid1 & 31][0], pr.alpha * gr.x);
-            atomicAdd(&gblend[it.tid1 & 31][1], pr.alpha * gr.y);
-            atomicAdd(&gblend[it.tid1 & 31][2], pr.alpha * gr.z);
-        }
-        if (PHASE == 1 && it.tid0 >= 0 && !pr.clamped) {
-            // position gradient: the warp whose strip holds the pair's first pixel scatters it
+        const float4 gr = (PHASE == 1) ? gplane0[recv] : gplane1[recv];
+        // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g; only pixels on the
+        // main pass' list consume it (phase B: valid, phase A: covered)
+        const bool t0 = PHASE == 1 ? k0.valid : k0.tri >= 0, t1 = PHASE == 1 ? k1.valid : k1.tri >= 0;
+        if (t0) atomicAdd(gdelta + pix0, make_float4(-pr.alpha * gr.x, -pr.alpha * gr.y, -pr.alpha * gr.z, 0.f));
+        if (t1) atomicAdd(gdelta + pix1, make_float4(pr.alpha * gr.x, pr.alpha * gr.y, pr.alpha * gr.z, 0.f));
+        if (PHASE == 1 && !pr.clamped) {
             float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = f0;
-            if (k0.tri >= 0) f0 = plane0[base + r0];
-            if (k1.tri >= 0) s0 = plane0[base + r1];
+            if (k0.tri >= 0) f0 = plane0[pix0];
+            if (k1.tri >= 0) s0 = plane0[pix1];
             const float dd_img = gr.x * (s0.x - f0.x) + gr.y * (s0.y - f0.y) + gr.z * (s0.z - f0.z);
             const float dd_msk = gr.w * ((k1.tri >= 0 ? 1.0f : 0.0f) - (k0.tri >= 0 ? 1.0f : 0.0f));
             if (dd_img != 0.0f || dd_msk != 0.0f) {
+                const float* M = viewM + (size_t)n * kViewM;
                 float4 e1, e2;
-                aa_pos_grad(pr, it.qx, it.qy, it.d, P, H, W, 1.0f, e1, e2);
+                aa_pos_grad(pr, qx, qy, d, reinterpret_cast<const float*>(pos + (size_t)n * V), H, W, 1.0f, e1, e2);
                 const float3 w1 = clip_to_world(M, e1.x, e1.y, e1.w);
                 const float3 w2 = clip_to_world(M, e2.x, e2.y, e2.w);
                 atomicAdd(G + 3 * (size_t)pr.i1, make_float4(dd_img * w1.x, dd_img * w1.y, dd_img * w1.z, dd_msk * w1.x));
@@ -740,120 +775,113 @@ __device__ __forceinline__ void pixel_bwd_tile(
             }
         }
     }
-    float3 gb = make_float3(0.f, 0.f, 0.f);
-    if (nq > 0) {
-        __syncwarp();
-        gb = make_float3(gblend[lane][0], gblend[lane][1], gblend[lane][2]);
-        if (lane == 0) q_n = 0;
-        __syncwarp();  // gblend[] / q_items of this warp are rewritten by its next tile
-    }
-    const bool covered = self.tri >= 0;
-    if (!inb || !covered) return;  // empty pixels have no upstream producer
-    // gradient w.r.t. this pixel's PRE-antialias values: pass-through + pair terms
-    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-    if (PHASE == 1) {
-        g0 = gplane0[pix];
-        g0.x += gb.x; g0.y += gb.y; g0.z += gb.z;
-    } else {
-        g1 = gplane1[pix];
-        g1.x += gb.x; g1.y += gb.y; g1.z += gb.z;
-    }
-    PixTri q;
-    load_pixtri(self.tri, px, py, Pv, tri, invW, invH, q);
-    const float w = 1.0f - q.u - q.v;
-    if (PHASE == 0) {
-        // only the albedo attribute is trainable: interpolate bwd
-        if (g1.x == 0.0f && g1.y == 0.0f && g1.z == 0.0f) return;
-        atomicAdd(G + 3 * (size_t)q.i0 + 2, make_float4(0.f, q.u * g1.x, q.u * g1.y, q.u * g1.z));
-        atomicAdd(G + 3 * (size_t)q.i1 + 2, make_float4(0.f, q.v * g1.x, q.v * g1.y, q.v * g1.z));
-        atomicAdd(G + 3 * (size_t)q.i2 + 2, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
-        return;
-    }
-    // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286)
-    if (!self.valid) return;
-    if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) return;
-    const float3 m = interp3(normals, q);
-    const float3 a = interp3(albedo, q);
-    const float len = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
-    const float inv = 1.0f / fmaxf(len, 1e-12f);
-    const float nx = m.x * inv, ny = m.y * inv, nz = m.z * inv;
-    const float r = sh_radiance(c, nx, ny, nz);
-    const float3 ga = make_float3(g0.x * r, g0.y * r, g0.z * r);           // d/d(interpolated albedo)
-    const float gr = g0.x * a.x + g0.y * a.y + g0.z * a.z;                 // d/d(radiance)
-    float3 gn = make_float3(gr * (c[3] + c[4] * ny - 2 * c[6] * nx + c[7] * nz + 2 * c[8] * nx),
-                            gr * (c[1] + c[4] * nx + c[5] * nz - 2 * c[6] * ny - 2 * c[8] * ny),
-                            gr * (c[2] + c[5] * ny + 4 * c[6] * nz + c[7] * nx));
-    float3 gm;  // through F.normalize(eps=1e-12), mesh_sfs_optim.py:273
-    if (len > 1e-12f) {
-        const float dt = nx * gn.x + ny * gn.y + nz * gn.z;
-        gm = make_float3((gn.x - nx * dt) * inv, (gn.y - ny * dt) * inv, (gn.z - nz * dt) * inv);
-    } else {
-        gm = make_float3(gn.x * inv, gn.y * inv, gn.z * inv);
-    }
-    // interpolate bwd: d/du, d/dv over the six differentiable attributes
-    const float* n0 = normals + 3 * (size_t)q.i0; const float* n1 = normals + 3 * (size_t)q.i1; const float* n2 = normals + 3 * (size_t)q.i2;
-    const float* b0 = albedo + 3 * (size_t)q.i0; const float* b1 = albedo + 3 * (size_t)q.i1; const float* b2 = albedo + 3 * (size_t)q.i2;
-    const float n2x = __ldg(n2), n2y = __ldg(n2 + 1), n2z = __ldg(n2 + 2);
-    const float b2x = __ldg(b2), b2y = __ldg(b2 + 1), b2z = __ldg(b2 + 2);
-    const float du = gm.x * (__ldg(n0) - n2x) + gm.y * (__ldg(n0 + 1) - n2y) + gm.z * (__ldg(n0 + 2) - n2z) +
-                     ga.x * (__ldg(b0) - b2x) + ga.y * (__ldg(b0 + 1) - b2y) + ga.z * (__ldg(b0 + 2) - b2z);
-    const float dv = gm.x * (__ldg(n1) - n2x) + gm.y * (__ldg(n1 + 1) - n2y) + gm.z * (__ldg(n1 + 2) - n2z) +
-                     ga.x * (__ldg(b1) - b2x) + ga.y * (__ldg(b1 + 1) - b2y) + ga.z * (__ldg(b1 + 2) - b2z);
-    // rasterize bwd
-    const float fx = (float)(2 * px + 1) / (float)W - 1.0f;
-    const float fy = (float)(2 * py + 1) / (float)H - 1.0f;
-    const float q0x = q.p0.x - fx * q.p0.w, q0y = q.p0.y - fy * q.p0.w;
-    const float q1x = q.p1.x - fx * q.p1.w, q1y = q.p1.y - fy * q.p1.w;
-    const float q2x = q.p2.x - fx * q.p2.w, q2y = q.p2.y - fy * q.p2.w;
-    const float e0 = q1x * q2y - q1y * q2x, e1 = q2x * q0y - q2y * q0x, e2 = q0x * q1y - q0y * q1x;
-    const float at = e0 + e1 + e2;
-    const float iw = 1.0f / (at + copysignf(1e-6f, at));
-    const float bb0 = e0 * iw, bb1 = e1 * iw;
-    const float gb0 = du * iw, gb1 = dv * iw, gbb = gb0 * bb0 + gb1 * bb1;
-    const float g0x = gbb * (q2y - q1y) - gb1 * q2y;
-    const float g1x = gbb * (q0y - q2y) + gb0 * q2y;
-    const float g2x = gbb * (q1y - q0y) - gb0 * q1y + gb1 * q0y;
-    const float g0y = gbb * (q1x - q2x) + gb1 * q2x;
-    const float g1y = gbb * (q2x - q0x) - gb0 * q2x;
-    const float g2y = gbb * (q0x - q1x) + gb0 * q1x - gb1 * q0x;
-    const float3 w0 = clip_to_world(M, g0x, g0y, -fx * g0x - fy * g0y);
-    const float3 w1 = clip_to_world(M, g1x, g1y, -fx * g1x - fy * g1y);
-    const float3 w2 = clip_to_world(M, g2x, g2y, -fx * g2x - fy * g2y);
-    float4* G0 = G + 3 * (size_t)q.i0; float4* G1 = G + 3 * (size_t)q.i1; float4* G2 = G + 3 * (size_t)q.i2;
-    atomicAdd(G0, make_float4(w0.x, w0.y, w0.z, 0.f));
-    atomicAdd(G0 + 1, make_float4(0.f, 0.f, q.u * gm.x, q.u * gm.y));
-    atomicAdd(G0 + 2, make_float4(q.u * gm.z, q.u * ga.x, q.u * ga.y, q.u * ga.z));
-    atomicAdd(G1, make_float4(w1.x, w1.y, w1.z, 0.f));
-    atomicAdd(G1 + 1, make_float4(0.f, 0.f, q.v * gm.x, q.v * gm.y));
-    atomicAdd(G1 + 2, make_float4(q.v * gm.z, q.v * ga.x, q.v * ga.y, q.v * ga.z));
-    atomicAdd(G2, make_float4(w2.x, w2.y, w2.z, 0.f));
-    atomicAdd(G2 + 1, make_float4(0.f, 0.f, w * gm.x, w * gm.y));
-    atomicAdd(G2 + 2, make_float4(w * gm.z, w * ga.x, w * ga.y, w * ga.z));
 }
 
-// pixel backward, persistent over the dilated work list
+// ------------------------------------------------------------------------------------------------
+// backward, part 2: one thread per pixel of the compact list (every lane busy): SH / normalise / interpolate /
+// rasterize backward, 9 float4 red.global.add per pixel into the world-space per-vertex accumulators.
+// ------------------------------------------------------------------------------------------------
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
-    const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
-    int* __restrict__ cursors, int tiles_x, int tiles_y, const float4* __restrict__ pos, const float2* __restrict__ scr,
-    float invW, float invH, const float* __restrict__ viewM, const int32_t* __restrict__ tri,
-    const int32_t* __restrict__ opp, const float* __restrict__ normals, const float* __restrict__ albedo,
-    const float* __restrict__ sh_coeffs,
-    const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
-    const float4* __restrict__ plane0, const float4* __restrict__ plane1, const float4* __restrict__ gplane0,
-    const float4* __restrict__ gplane1, float4* __restrict__ G) {
-    __shared__ uint32_t q_items[8][kPairQueue];
-    __shared__ int q_n[8];
-    __shared__ float gblend[8][32][3];  // pair terms of d(loss)/d(pre-antialias colour | albedo), per warp
-    const int wib = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) q_n[wib] = 0;
-    __syncwarp();
-    const int na = *acount;
-    Strip st;
-    int u = blockIdx.x * 8 + wib;
-    while (next_strip(u, alist, na, tiles_x, tiles_y, st))
-        pixel_bwd_tile<PHASE>(st, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, sh_coeffs, view_idx, sh_idx, V, T, H,
-                              W, plane0, plane1, gplane0, gplane1, G, viewM, q_items[wib], q_n[wib], gblend[wib]);
+    const uint32_t* __restrict__ vlist, const int* __restrict__ vcount, const unsigned long long* __restrict__ zbuf,
+    const float4* __restrict__ pos, float invW, float invH, const float* __restrict__ viewM,
+    const int32_t* __restrict__ tri, const float* __restrict__ normals, const float* __restrict__ albedo,
+    const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, int V, int H, int W,
+    const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ gdelta,
+    float4* __restrict__ G) {
+    const int nv = *vcount;
+    const int hw = H * W;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += gridDim.x * blockDim.x) {
+        const size_t pix = vlist[e];
+        const int n = (int)(pix / hw);
+        const int rem = (int)(pix - (size_t)n * hw), py = rem / W, px = rem - py * W;
+        const NbrKeys self = decode_key(zbuf[pix]);
+        const float* M = viewM + (size_t)n * kViewM;
+        const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
+        const float4* Pv = pos + (size_t)n * V;
+        // gradient w.r.t. this pixel's PRE-antialias values: pass-through + pair terms (consumed and re-armed)
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+        const float4 gd = gdelta[pix];
+        if (gd.x != 0.0f || gd.y != 0.0f || gd.z != 0.0f) gdelta[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PHASE == 1) {
+            g0 = gplane0[pix];
+            g0.x += gd.x; g0.y += gd.y; g0.z += gd.z;
+        } else {
+            g1 = gplane1[pix];
+            g1.x += gd.x; g1.y += gd.y; g1.z += gd.z;
+        }
+        PixTri q;
+        load_pixtri(self.tri, px, py, Pv, tri, invW, invH, q);
+        const float w = 1.0f - q.u - q.v;
+        if (PHASE == 0) {
+            // only the albedo attribute is trainable: interpolate bwd
+            if (g1.x == 0.0f && g1.y == 0.0f && g1.z == 0.0f) continue;
+            atomicAdd(G + 3 * (size_t)q.i0 + 2, make_float4(0.f, q.u * g1.x, q.u * g1.y, q.u * g1.z));
+            atomicAdd(G + 3 * (size_t)q.i1 + 2, make_float4(0.f, q.v * g1.x, q.v * g1.y, q.v * g1.z));
+            atomicAdd(G + 3 * (size_t)q.i2 + 2, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
+            continue;
+        }
+        // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286)
+        if (!self.valid) continue;
+        if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) continue;
+        const float3 m = interp3(normals, q);
+        const float3 a = interp3(albedo, q);
+        const float len = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
+        const float inv = 1.0f / fmaxf(len, 1e-12f);
+        const float nx = m.x * inv, ny = m.y * inv, nz = m.z * inv;
+        const float r = sh_radiance(c, nx, ny, nz);
+        const float3 ga = make_float3(g0.x * r, g0.y * r, g0.z * r);           // d/d(interpolated albedo)
+        const float gr = g0.x * a.x + g0.y * a.y + g0.z * a.z;                 // d/d(radiance)
+        float3 gn = make_float3(gr * (c[3] + c[4] * ny - 2 * c[6] * nx + c[7] * nz + 2 * c[8] * nx),
+                                gr * (c[1] + c[4] * nx + c[5] * nz - 2 * c[6] * ny - 2 * c[8] * ny),
+                                gr * (c[2] + c[5] * ny + 4 * c[6] * nz + c[7] * nx));
+        float3 gm;  // through F.normalize(eps=1e-12), mesh_sfs_optim.py:273
+        if (len > 1e-12f) {
+            const float dt = nx * gn.x + ny * gn.y + nz * gn.z;
+            gm = make_float3((gn.x - nx * dt) * inv, (gn.y - ny * dt) * inv, (gn.z - nz * dt) * inv);
+        } else {
+            gm = make_float3(gn.x * inv, gn.y * inv, gn.z * inv);
+        }
+        // interpolate bwd: d/du, d/dv over the six differentiable attributes
+        const float* n0 = normals + 3 * (size_t)q.i0; const float* n1 = normals + 3 * (size_t)q.i1; const float* n2 = normals + 3 * (size_t)q.i2;
+        const float* b0 = albedo + 3 * (size_t)q.i0; const float* b1 = albedo + 3 * (size_t)q.i1; const float* b2 = albedo + 3 * (size_t)q.i2;
+        const float n2x = __ldg(n2), n2y = __ldg(n2 + 1), n2z = __ldg(n2 + 2);
+        const float b2x = __ldg(b2), b2y = __ldg(b2 + 1), b2z = __ldg(b2 + 2);
+        const float du = gm.x * (__ldg(n0) - n2x) + gm.y * (__ldg(n0 + 1) - n2y) + gm.z * (__ldg(n0 + 2) - n2z) +
+                         ga.x * (__ldg(b0) - b2x) + ga.y * (__ldg(b0 + 1) - b2y) + ga.z * (__ldg(b0 + 2) - b2z);
+        const float dv = gm.x * (__ldg(n1) - n2x) + gm.y * (__ldg(n1 + 1) - n2y) + gm.z * (__ldg(n1 + 2) - n2z) +
+                         ga.x * (__ldg(b1) - b2x) + ga.y * (__ldg(b1 + 1) - b2y) + ga.z * (__ldg(b1 + 2) - b2z);
+        // rasterize bwd
+        const float fx = (float)(2 * px + 1) / (float)W - 1.0f;
+        const float fy = (float)(2 * py + 1) / (float)H - 1.0f;
+        const float q0x = q.p0.x - fx * q.p0.w, q0y = q.p0.y - fy * q.p0.w;
+        const float q1x = q.p1.x - fx * q.p1.w, q1y = q.p1.y - fy * q.p1.w;
+        const float q2x = q.p2.x - fx * q.p2.w, q2y = q.p2.y - fy * q.p2.w;
+        const float e0 = q1x * q2y - q1y * q2x, e1 = q2x * q0y - q2y * q0x, e2 = q0x * q1y - q0y * q1x;
+        const float at = e0 + e1 + e2;
+        const float iw = 1.0f / (at + copysignf(1e-6f, at));
+        const float bb0 = e0 * iw, bb1 = e1 * iw;
+        const float gb0 = du * iw, gb1 = dv * iw, gbb = gb0 * bb0 + gb1 * bb1;
+        const float g0x = gbb * (q2y - q1y) - gb1 * q2y;
+        const float g1x = gbb * (q0y - q2y) + gb0 * q2y;
+        const float g2x = gbb * (q1y - q0y) - gb0 * q1y + gb1 * q0y;
+        const float g0y = gbb * (q1x - q2x) + gb1 * q2x;
+        const float g1y = gbb * (q2x - q0x) - gb0 * q2x;
+        const float g2y = gbb * (q0x - q1x) + gb0 * q1x - gb1 * q0x;
+        const float3 w0 = clip_to_world(M, g0x, g0y, -fx * g0x - fy * g0y);
+        const float3 w1 = clip_to_world(M, g1x, g1y, -fx * g1x - fy * g1y);
+        const float3 w2 = clip_to_world(M, g2x, g2y, -fx * g2x - fy * g2y);
+        float4* G0 = G + 3 * (size_t)q.i0; float4* G1 = G + 3 * (size_t)q.i1; float4* G2 = G + 3 * (size_t)q.i2;
+        atomicAdd(G0, make_float4(w0.x, w0.y, w0.z, 0.f));
+        atomicAdd(G0 + 1, make_float4(0.f, 0.f, q.u * gm.x, q.u * gm.y));
+        atomicAdd(G0 + 2, make_float4(q.u * gm.z, q.u * ga.x, q.u * ga.y, q.u * ga.z));
+        atomicAdd(G1, make_float4(w1.x, w1.y, w1.z, 0.f));
+        atomicAdd(G1 + 1, make_float4(0.f, 0.f, q.v * gm.x, q.v * gm.y));
+        atomicAdd(G1 + 2, make_float4(q.v * gm.z, q.v * ga.x, q.v * ga.y, q.v * ga.z));
+        atomicAdd(G2, make_float4(w2.x, w2.y, w2.z, 0.f));
+        atomicAdd(G2 + 1, make_float4(0.f, 0.f, w * gm.x, w * gm.y));
+        atomicAdd(G2 + 2, make_float4(w * gm.z, w * ga.x, w * ga.y, w * ga.z));
+    }
 }
 
 __global__ void ham_finalize_scalars_kernel(const double* __restrict__ acc, const double* __restrict__ view_vm2,
@@ -1052,7 +1080,8 @@ __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
     const float* __restrict__ packed,
     const float* __restrict__ yhat_v, const float* __restrict__ yhat_a, const float* __restrict__ gN,
     float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
-    const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad) {
+    const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad,
+    const int* __restrict__ status) {
     const int V = cfg.V;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
     const float* scal = packed + 12 * (size_t)V;
@@ -1070,6 +1099,7 @@ __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
         losses[0] = sfs; losses[1] = cfg.phase == 1 ? lap : 0.0f; losses[2] = alb; losses[3] = msk;
         losses[4] = cfg.phase == 1 ? edg : 0.0f; losses[5] = cfg.phase == 1 ? del : 0.0f; losses[6] = n_valid;
         losses[7] = cfg.phase == 1 ? sfs + lap + alb + msk + edg + del : sfs;
+        if (status && (*status & 1)) losses[7] = __int_as_float(0x7fc00000);  // pair list overflow: refuse a number
     }
     // Laplacian backward rows (L^T yhat) for vertices and albedo; normal backward + edge hinge over incident faces
     float3 lv = make_float3(0.f, 0.f, 0.f), la = lv, gnb = lv, ge = lv, vi = lv;
@@ -1221,6 +1251,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     HamWs ws;
     ham_layout(cfg, (char*)b->workspace, &ws);
     const int V = cfg->V, T = cfg->T, H = cfg->H, W = cfg->W, n = cfg->n_views;
+    const size_t P = (size_t)n * H * W;
     unsigned long long* zcur = ws.zbuf[cfg->zbuf_slot];
     unsigned long long* znext = ws.zbuf[cfg->zbuf_slot ^ 1];
     const int cur = cfg->zbuf_slot, nxt = cfg->zbuf_slot ^ 1;
@@ -1255,21 +1286,25 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
                                                       ws.tcount[nxt], ws.abits, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.pos,
                                                       ws.scr, invW, invH, b->tri, b->opp, ws.normals, b->albedo,
                                                       b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W,
-                                                      ws.plane[0], ws.plane[1], ws.acc);
+                                                      ws.plane[0], ws.plane[1], ws.acc, ws.vlist, ws.vcount);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 4: shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
     ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.scr, b->tri, b->opp, b->imgs, b->valid_masks,
                                                      b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
-                                                     ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask);
+                                                     ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask,
+                                                     ws.plist_a, ws.plist_b, ws.pcount, (int)(P / 2), ws.status);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(zcur, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.pos,
-                                                              ws.scr, invW, invH, ws.viewM, b->tri, b->opp, ws.normals, b->albedo,
-                                                           b->sh_coeffs, b->view_idx, sh_idx, V, T,
-                                                           H, W, ws.plane[0], ws.plane[1], g0, g1, (float4*)b->packed);
+        ham_pair_bwd_kernel<PHASE><<<64, 256, 0, st>>>(ws.plist_a, ws.plist_b, ws.pcount, (int)(P / 2), zcur, ws.pos,
+                                                       ws.viewM, V, H, W, ws.plane[0], g0, g1, ws.gdelta,
+                                                       (float4*)b->packed);
+        FMHR_LAUNCH_CHECK();
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.vlist, ws.vcount, zcur, ws.pos, invW, invH, ws.viewM, b->tri,
+                                                              ws.normals, b->albedo, b->sh_coeffs, sh_idx, V, H, W, g0, g1,
+                                                              ws.gdelta, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
     }
     ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,
@@ -1291,6 +1326,7 @@ extern "C" int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers
         FMHR_CUDA(cudaMemsetAsync(ws.slot_region[i], 0, ws.slot_bytes, (cudaStream_t)stream));
     }
     FMHR_CUDA(cudaMemsetAsync(ws.common_region, 0, ws.common_bytes, (cudaStream_t)stream));
+    FMHR_CUDA(cudaMemsetAsync(ws.gdelta, 0, P * 16, (cudaStream_t)stream));
     return FMHR_OK;
 }
 
@@ -1332,7 +1368,7 @@ extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_b
     ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
                                                           buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
                                                           buf->inv_deg, buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, buf->adam_m,
-                                                          buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad);
+                                                          buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)
     if (cfg->phase == 0) {

@@ -35,7 +35,10 @@ class HamBuffers(ctypes.Structure):
         "tri", "opp", "v2f_ptr", "v2f_idx", "v2v_ptr", "v2v_idx", "v2f_nbr", "inv_deg",
         "vertices_tmp", "delta", "albedo", "sh_coeffs", "adam_m", "adam_v", "adam_step",
         "imgs", "masks", "valid_masks", "view_vm2", "w2cs", "projs", "view_idx", "sh_idx",
-        "packed", "losses", "workspace")] + [("workspace_bytes", c_sz), ("dbg_grad", c_p), ("dbg_grad_sh", c_p)]
+        "packed", "losses", "workspace")] + [("workspace_bytes", c_sz), ("dbg_grad", c_p), ("dbg_grad_sh", c_p),
+                                             ("ml_vptr", c_p), ("ml_verts", c_p), ("ml_tri2", c_p),
+                                             ("n_meshlets", ctypes.c_int32), ("ml_tris", ctypes.c_int32),
+                                             ("ml_max_verts", ctypes.c_int32), ("ml_reserved", ctypes.c_int32)]
 
 
 _SIGS = {
@@ -49,6 +52,8 @@ _SIGS = {
     "fmhr_mesh_topology_workspace_bytes": (c_sz, [c_i, c_i]),
     "fmhr_mesh_topology_build": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(c_i), c_p, c_sz, c_p]),
     "fmhr_mesh_topology_derive": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
+    "fmhr_meshlets_build_host": (c_i, [c_p, c_p, c_i, c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i),
+                                       ctypes.POINTER(c_i), c_p, c_p, c_p]),
     "fmhr_antialias_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_antialias_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "fmhr_vertex_normals_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),

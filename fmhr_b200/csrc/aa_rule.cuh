@@ -59,12 +59,10 @@ struct AAGeom {
     int bits;
 };
 
+// Core of aa_triangle_geom for callers that already hold the triangle's corners (v*) and opposite-wing vertices (o*).
 template <class Proj>
-__device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const Proj proj,
-                                                 const int32_t* __restrict__ tri, const int32_t* __restrict__ opp,
-                                                 int V, int T, int H, int W, AAGeom& g) {
-    if (t < 0 || t >= T) return false;
-    const int v0 = __ldg(tri + 3 * t), v1 = __ldg(tri + 3 * t + 1), v2 = __ldg(tri + 3 * t + 2);
+__device__ __forceinline__ bool aa_triangle_geom_idx(int v0, int v1, int v2, int o0, int o1, int o2, int qx, int qy,
+                                                     const Proj proj, int V, int H, int W, AAGeom& g) {
     if ((unsigned)v0 >= (unsigned)V || (unsigned)v1 >= (unsigned)V || (unsigned)v2 >= (unsigned)V) return false;
     const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
     const float fx = xs(xa((float)qx, 0.5f), xh), fy = xs(xa((float)qy, 0.5f), yh);
@@ -72,7 +70,6 @@ __device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const Pr
     proj(v0, fx, fy, x0, y0);
     proj(v1, fx, fy, x1, y1);
     proj(v2, fx, fy, x2, y2);
-    const int o0 = __ldg(opp + 3 * t), o1 = __ldg(opp + 3 * t + 1), o2 = __ldg(opp + 3 * t + 2);
     float ox0 = x0, oy0 = y0, ox1 = x1, oy1 = y1, ox2 = x2, oy2 = y2;
     if ((unsigned)o0 < (unsigned)V) proj(o0, fx, fy, ox0, oy0);
     if ((unsigned)o1 < (unsigned)V) proj(o1, fx, fy, ox1, oy1);
@@ -85,6 +82,37 @@ __device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const Pr
     g.x0 = x0; g.y0 = y0; g.x1 = x1; g.y1 = y1; g.x2 = x2; g.y2 = y2;
     g.bits = (aa_same_sign(a0, bb) ? 1 : 0) | (aa_same_sign(a1, bb) ? 2 : 0) | (aa_same_sign(a2, bb) ? 4 : 0);
     return true;
+}
+
+// Same, from absolute window coordinates (aa_window_xy) of the corners (s*) and of the opposite-wing vertices (so*,
+// ignored where the wing does not exist): identical arithmetic to AAProjScreen.
+__device__ __forceinline__ void aa_triangle_geom_win(int v0, int v1, int v2, float2 s0, float2 s1, float2 s2, int o0, int o1,
+                                                     int o2, float2 so0, float2 so1, float2 so2, int qx, int qy, int V,
+                                                     int H, int W, AAGeom& g) {
+    const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
+    const float fx = xs(xa((float)qx, 0.5f), xh), fy = xs(xa((float)qy, 0.5f), yh);
+    const float x0 = xs(s0.x, fx), y0 = xs(s0.y, fy), x1 = xs(s1.x, fx), y1 = xs(s1.y, fy), x2 = xs(s2.x, fx), y2 = xs(s2.y, fy);
+    float ox0 = x0, oy0 = y0, ox1 = x1, oy1 = y1, ox2 = x2, oy2 = y2;
+    if ((unsigned)o0 < (unsigned)V) { ox0 = xs(so0.x, fx); oy0 = xs(so0.y, fy); }
+    if ((unsigned)o1 < (unsigned)V) { ox1 = xs(so1.x, fx); oy1 = xs(so1.y, fy); }
+    if ((unsigned)o2 < (unsigned)V) { ox2 = xs(so2.x, fx); oy2 = xs(so2.y, fy); }
+    const float bb = xs(xm(xs(x1, x0), xs(y2, y0)), xm(xs(x2, x0), xs(y1, y0)));
+    const float a0 = xs(xm(xs(x1, ox0), xs(y2, oy0)), xm(xs(x2, ox0), xs(y1, oy0)));
+    const float a1 = xs(xm(xs(x2, ox1), xs(y0, oy1)), xm(xs(x0, ox1), xs(y2, oy1)));
+    const float a2 = xs(xm(xs(x0, ox2), xs(y1, oy2)), xm(xs(x1, ox2), xs(y0, oy2)));
+    g.v0 = v0; g.v1 = v1; g.v2 = v2;
+    g.x0 = x0; g.y0 = y0; g.x1 = x1; g.y1 = y1; g.x2 = x2; g.y2 = y2;
+    g.bits = (aa_same_sign(a0, bb) ? 1 : 0) | (aa_same_sign(a1, bb) ? 2 : 0) | (aa_same_sign(a2, bb) ? 4 : 0);
+}
+
+template <class Proj>
+__device__ __forceinline__ bool aa_triangle_geom(int t, int qx, int qy, const Proj proj,
+                                                 const int32_t* __restrict__ tri, const int32_t* __restrict__ opp,
+                                                 int V, int T, int H, int W, AAGeom& g) {
+    if (t < 0 || t >= T) return false;
+    const int v0 = __ldg(tri + 3 * t), v1 = __ldg(tri + 3 * t + 1), v2 = __ldg(tri + 3 * t + 2);
+    const int o0 = __ldg(opp + 3 * t), o1 = __ldg(opp + 3 * t + 1), o2 = __ldg(opp + 3 * t + 2);
+    return aa_triangle_geom_idx(v0, v1, v2, o0, o1, o2, qx, qy, proj, V, H, W, g);
 }
 
 // Edge selection for the pair whose chosen triangle has geometry g (d = 0 right / 1 down neighbour, from1 = the chosen
@@ -146,13 +174,13 @@ __device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z
 }
 
 // d(alpha)/d(clip position) of the two edge vertices, scaled by `dd` = d(loss)/d(alpha).
-// (px,py) is the pair's FIRST pixel.  Returns the two float4 gradients (x, y, 0, w).
-__device__ __forceinline__ void aa_pos_grad(const AAPair& pr, int px, int py, int d, const float* __restrict__ P, int H,
-                                            int W, float dd, float4& g1, float4& g2) {
+// (px,py) is the pair's FIRST pixel, p1 / p2 the clip positions of the edge's vertices pr.i1 / pr.i2.  Returns the two
+// float4 gradients (x, y, 0, w).
+__device__ __forceinline__ void aa_pos_grad(const AAPair& pr, int px, int py, int d, const float4 p1, const float4 p2,
+                                            int H, int W, float dd, float4& g1, float4& g2) {
     const int qx = px + (pr.from1 ? 1 - d : 0), qy = py + (pr.from1 ? d : 0);
     const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
     const float fx = (float)qx + 0.5f - xh, fy = (float)qy + 0.5f - yh;
-    const float4 p1 = ldg4(P + 4 * (size_t)pr.i1), p2 = ldg4(P + 4 * (size_t)pr.i2);
     const float iw1 = 1.0f / p1.w, iw2 = 1.0f / p2.w;
     float x1 = p1.x * iw1 * xh - fx, y1 = p1.y * iw1 * yh - fy;
     float x2 = p2.x * iw2 * xh - fx, y2 = p2.y * iw2 * yh - fy;

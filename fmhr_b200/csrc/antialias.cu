@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) antialias_kernel(const float* __restrict_
             }
             if (dd == 0.0f || pr.clamped || grad_pos == nullptr) continue;
             float4 g1, g2;
-            aa_pos_grad(pr, px, py, d, P, H, W, dd, g1, g2);
+            aa_pos_grad(pr, px, py, d, ldg4(P + 4 * (size_t)pr.i1), ldg4(P + 4 * (size_t)pr.i2), H, W, dd, g1, g2);
             float4* G = reinterpret_cast<float4*>(grad_pos + (size_t)n * V * 4);
             atomicAdd(G + pr.i1, g1);
             atomicAdd(G + pr.i2, g2);

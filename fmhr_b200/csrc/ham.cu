@@ -14,23 +14,17 @@
 
 namespace fmhr {
 
-int launch_raster_coverage_snapped(const float4* pos, const int2* snap, const int32_t* tri, int N, int V, int T, int H,
-                                   int W, unsigned long long* zbuf, uint32_t* tbits, uint32_t* tlist, int* tcount,
-                                   int tiles_x, int tiles_per_view, cudaStream_t st);
-int launch_vertex_normals_fwd(const float* verts, const int32_t* tri, const int32_t* v2f_ptr, const int32_t* v2f_idx,
-                              const int32_t* v2f_nbr, int V, float* normals, float* raw, cudaStream_t st);
-
-// Per-view constants of the backward pass, written once per step by the transform kernel:
-//   viewM[n][0..11] = rows 0..2 of (w2c @ proj), columns x,y,z,w : d(clip_j)/d(world_i) = M[4i+j]
-constexpr int kViewM = 12;
+// Per-view combined matrix, written once per step by the prep kernel (row-vector convention of get_data.py:96-97):
+//   viewM[n][4i+j] = (w2c @ proj)[i][j],  clip_j = sum_i world_i * M[4i+j] + M[12+j]  (mesh_sfs_optim.py:262-264);
+// the same 16 floats are d(clip_j)/d(world_i) for the backward pass.  Every kernel derives clip positions from the
+// world-space vertex and this matrix with clip_from_world() (fixed FMA order -> bit-identical everywhere), so no
+// [n,V] position array exists in HBM.
+constexpr int kViewM = 16;
 
 struct HamWs {
     unsigned long long* zbuf[2];  // [n,H,W] x2: `zbuf_slot` is rasterised this step, the other is reset for the next
     float4* plane[4];          // [n,H,W] each
-    float4* pos;               // [n,V] clip positions
-    int2* snap;                // [n,V] 24.8 fixed-point window coordinates (x == INT_MIN: vertex rejected)
-    float2* scr;               // [n,V] (x/w*W/2, y/w*H/2): the antialias rule's window coordinates, divide done once
-    float* viewM;              // [n,12] d(clip)/d(world) per view
+    float* viewM;              // [n,16] combined world->clip matrix per view
     // Compact work lists of the backward pass (built by the forward passes of the same iteration):
     uint32_t* vlist;           // [P]   pixels that feed the backward shader (phase B: valid, phase A: covered), by shade
     uint4* plist_a;            // [P/2] blending pixel pairs found by the antialias pass: (pixel0, flags, alpha, i1)
@@ -54,12 +48,13 @@ struct HamWs {
     int* acount;
     uint32_t* abits;
     uint32_t* alist;
-    float* vertices;           // [V,3]
-    float* normals;            // [V,3] normalised
-    float* raw;                // [V,3] un-normalised normal sums
-    float* gN;                 // [V,3]
-    float* yhat_v;             // [V,3]
-    float* yhat_a;             // [V,3]
+    // Vertex-domain records (every gather of the pixel / update kernels is a 128- or 256-bit load of one 32-byte sector):
+    float4* vg;                // [V,2]  vg[2i] = (x, y, z, 0) current vertex,   vg[2i+1] = d(loss)/d(raw normal) (update pass 1)
+    float4* vattr;             // [V,2]  vattr[2i] = (unit normal, degenerate flag), vattr[2i+1] = (albedo b,g,r, 0)
+    float4* raw4;              // [V]    (un-normalised normal sum N, |N|)
+    float4* ys;                // [V,2]  ys[2i] = (yhat_v / deg, deg), ys[2i+1] = (yhat_a / deg, 0): Laplacian backward rows
+    int4* tri4;                // [T] (i0, i1, i2, -) padded copies of tri / opp, rebuilt by the prep kernel every step
+    int4* opp4;                // [T]
     float* gsh;                // [n_sh_rows,9] un-normalised SH gradients by SH row (phase A)
     double* acc;               // [8][32] (32-way spread against same-address atomics):
                                // 0 n_valid, 1 abs_sum, 2 mask_sq correction, 3 lap_v, 4 lap_a, 5 edge, 6 delta
@@ -90,9 +85,6 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
         p = (i < nplanes) ? take(P * 16) : nullptr;
         if (ws) ws->plane[i] = (float4*)p;
     }
-    p = take((size_t)c->n_views * V * 16); if (ws) ws->pos = (float4*)p;
-    p = take((size_t)c->n_views * V * 8); if (ws) ws->snap = (int2*)p;
-    p = take((size_t)c->n_views * V * 8); if (ws) ws->scr = (float2*)p;
     p = take((size_t)c->n_views * kViewM * 4); if (ws) ws->viewM = (float*)p;
     p = take(P * 4); if (ws) ws->vlist = (uint32_t*)p;
     p = take((P / 2 + 64) * 16); if (ws) ws->plist_a = (uint4*)p;
@@ -116,12 +108,12 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
         ws->vcount = ws->acount + 16; ws->pcount = ws->acount + 17; ws->status = ws->acount + 18;
         ws->abits = (uint32_t*)(p + 8 * 32 * sizeof(double) + 256);
     }
-    p = take(V * 12); if (ws) ws->vertices = (float*)p;
-    p = take(V * 12); if (ws) ws->normals = (float*)p;
-    p = take(V * 12); if (ws) ws->raw = (float*)p;
-    p = take(V * 12); if (ws) ws->gN = (float*)p;
-    p = take(V * 12); if (ws) ws->yhat_v = (float*)p;
-    p = take(V * 12); if (ws) ws->yhat_a = (float*)p;
+    p = take(V * 32); if (ws) ws->vg = (float4*)p;
+    p = take(V * 32); if (ws) ws->vattr = (float4*)p;
+    p = take(V * 16); if (ws) ws->raw4 = (float4*)p;
+    p = take(V * 32); if (ws) ws->ys = (float4*)p;
+    p = take((size_t)c->T * 16); if (ws) ws->tri4 = (int4*)p;
+    p = take((size_t)c->T * 16); if (ws) ws->opp4 = (int4*)p;
     p = take((size_t)c->n_sh_rows * 9 * 4); if (ws) ws->gsh = (float*)p;
     p = take(8 * sizeof(float)); if (ws) ws->adam_sc = (float*)p;
     return off;
@@ -130,71 +122,264 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
 // ------------------------------------------------------------------------------------------------
 // vertex-domain prologue
 // ------------------------------------------------------------------------------------------------
+// 256-bit gather of one 32-byte record (LDG.E.256, sm_100+): one L1 wavefront instead of two.
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const float4* p) {
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+// same, for records written earlier in the SAME kernel launch sequence but read through the coherent path
+__device__ __forceinline__ F8 ld256(const float4* p) {
+    F8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+
 // vertices = vertices_tmp + delta (mesh_sfs_optim.py:253).  The same launch re-arms the step's accumulators (the packed
-// gradient buffer = 3V float4, loss / work-list scratch, SH gradients) so the iteration has no memset nodes.
+// gradient buffer = 3V float4, loss / work-list scratch, SH gradients) so the iteration has no memset nodes, and
+// rebuilds the padded int4 copies of tri / opp that the pixel passes gather with one 128-bit load.
 __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __restrict__ vtmp,
-                                                              const float* __restrict__ delta, int n3,
-                                                              float* __restrict__ vertices, float4* __restrict__ packed4,
+                                                              const float* __restrict__ delta, int V,
+                                                              float4* __restrict__ vg, float4* __restrict__ packed4,
                                                               uint32_t* __restrict__ z0, int n0,
                                                               uint32_t* __restrict__ z1, int n1,
-                                                              uint32_t* __restrict__ z2, int n2) {
+                                                              uint32_t* __restrict__ z2, int n2,
+                                                              const int32_t* __restrict__ tri,
+                                                              const int32_t* __restrict__ opp, int T,
+                                                              int4* __restrict__ tri4, int4* __restrict__ opp4,
+                                                              const float* __restrict__ w2cs,
+                                                              const float* __restrict__ projs,
+                                                              const int32_t* __restrict__ view_idx, int n_views,
+                                                              float* __restrict__ viewM) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n3) {
-        vertices[i] = vtmp[i] + delta[i];
-        packed4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_views * kViewM) {
+        const int n = i >> 4, r = (i >> 2) & 3, j = i & 3;
+        const float* Wm = w2cs + (size_t)view_idx[n] * 16;
+        const float* Pm = projs + (size_t)view_idx[n] * 16;
+        viewM[i] = __fmaf_rn(Wm[4 * r + 3], Pm[12 + j], __fmaf_rn(Wm[4 * r + 2], Pm[8 + j],
+                             __fmaf_rn(Wm[4 * r + 1], Pm[4 + j], __fmul_rn(Wm[4 * r], Pm[j]))));
     }
-    if (i == 0) packed4[n3] = make_float4(0.f, 0.f, 0.f, 0.f);  // the four scalars behind the 12V floats
+    if (i < T) {
+        tri4[i] = make_int4(tri[3 * (size_t)i], tri[3 * (size_t)i + 1], tri[3 * (size_t)i + 2], 0);
+        opp4[i] = make_int4(opp[3 * (size_t)i], opp[3 * (size_t)i + 1], opp[3 * (size_t)i + 2], 0);
+    }
+    if (i < V) {
+        const size_t k = 3 * (size_t)i;
+        vg[2 * (size_t)i] = make_float4(vtmp[k] + delta[k], vtmp[k + 1] + delta[k + 1], vtmp[k + 2] + delta[k + 2], 0.f);
+    }
+    if (i <= 3 * V) packed4[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // 3V accumulator float4 + the four scalars behind them
     if (i < n0) z0[i] = 0u;
     if (i < n1) z1[i] = 0u;
     if (i < n2) z2[i] = 0u;
 }
 
-// clip = ([v,1] @ w2c) @ proj, both matrices stored transposed (mesh_sfs_optim.py:262-264, get_data.py:96-97); also snaps
-// every vertex to the rasteriser's fixed-point grid once per (view, vertex) instead of once per (view, triangle corner).
-constexpr int kViewsPerBlock = 8;
-__global__ void __launch_bounds__(256) ham_transform_kernel(const float* __restrict__ vertices,
-                                                            const float* __restrict__ w2cs,
-                                                            const float* __restrict__ projs,
-                                                            const int32_t* __restrict__ view_idx, int n_views, int V,
-                                                            int H, int W, float4* __restrict__ pos,
-                                                            int2* __restrict__ snap, float2* __restrict__ scr,
-                                                            float* __restrict__ viewM) {
-    // A block transforms 256 vertices into kViewsPerBlock views: the dependent preamble (view index -> matrix rows) is
-    // paid once per block and hidden behind the vertex load instead of once per (view, vertex) thread - with one view
-    // per block the kernel was 8 waves of blocks that lived for two L2 round trips each.
-    __shared__ float Wm[kViewsPerBlock][16], Pm[kViewsPerBlock][16];
-    const int n0 = blockIdx.y * kViewsPerBlock;
-    const int nv = min(kViewsPerBlock, n_views - n0);
-    for (int q = threadIdx.x; q < nv * 32; q += blockDim.x) {
-        const int slot = q >> 5, e = q & 31;
-        const int view = __ldg(view_idx + n0 + slot);
-        if (e < 16) Wm[slot][e] = w2cs[(size_t)view * 16 + e];
-        else Pm[slot][e - 16] = projs[(size_t)view * 16 + e - 16];
+// Area-weighted vertex normals (models/utils.py:508-548, corner form of the face normal), 8 lanes per vertex over the
+// vertex->face CSR; writes the packed attribute records of the pixel passes.
+__global__ void __launch_bounds__(256) ham_normals_kernel(const float4* __restrict__ vg, const float* __restrict__ albedo,
+                                                          const int32_t* __restrict__ v2f_ptr,
+                                                          const int2* __restrict__ v2f_nbr, int V,
+                                                          float4* __restrict__ vattr, float4* __restrict__ raw4) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (i < V) {
+        const int b = __ldg(v2f_ptr + i), e = __ldg(v2f_ptr + i + 1);
+        const float4 pk = vg[2 * (size_t)i];
+        for (int j = b + sub; j < e; j += 8) {
+            const int2 nb = __ldg(v2f_nbr + j);
+            const float4 pa = vg[2 * (size_t)nb.x], pb = vg[2 * (size_t)nb.y];
+            const float ux = pa.x - pk.x, uy = pa.y - pk.y, uz = pa.z - pk.z;
+            const float wx = pb.x - pk.x, wy = pb.y - pk.y, wz = pb.z - pk.z;
+            ax += uy * wz - uz * wy; ay += uz * wx - ux * wz; az += ux * wy - uy * wx;
+        }
     }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (i < V) { x = vertices[3 * (size_t)i]; y = vertices[3 * (size_t)i + 1]; z = vertices[3 * (size_t)i + 2]; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+    }
+    if (i >= V || sub != 0) return;
+    const float len = sqrtf(ax * ax + ay * ay + az * az);
+    const float inv = 1.0f / fmaxf(len, 1e-6f);
+    raw4[i] = make_float4(ax, ay, az, len);
+    // flag: the normalisation backward of this vertex does not project (models/utils.py:547 clamps the norm at 1e-6)
+    vattr[2 * (size_t)i] = make_float4(ax * inv, ay * inv, az * inv, len > 1e-6f ? 0.0f : 1.0f);
+    const float* a = albedo + 3 * (size_t)i;
+    vattr[2 * (size_t)i + 1] = make_float4(a[0], a[1], a[2], 0.0f);
+}
+
+struct ViewM { float m[16]; };
+__device__ __forceinline__ ViewM load_viewM(const float* __restrict__ g) {
+    ViewM M;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 r = __ldg(g4 + k);
+        M.m[4 * k] = r.x; M.m[4 * k + 1] = r.y; M.m[4 * k + 2] = r.z; M.m[4 * k + 3] = r.w;
+    }
+    return M;
+}
+// clip = [v,1] @ (w2c @ proj); fixed FMA order, shared by every kernel that needs a clip position
+__device__ __forceinline__ float4 clip_from_world(const float* M, const float4 v) {
+    return make_float4(__fmaf_rn(v.z, M[8], __fmaf_rn(v.y, M[4], __fmaf_rn(v.x, M[0], M[12]))),
+                       __fmaf_rn(v.z, M[9], __fmaf_rn(v.y, M[5], __fmaf_rn(v.x, M[1], M[13]))),
+                       __fmaf_rn(v.z, M[10], __fmaf_rn(v.y, M[6], __fmaf_rn(v.x, M[2], M[14]))),
+                       __fmaf_rn(v.z, M[11], __fmaf_rn(v.y, M[7], __fmaf_rn(v.x, M[3], M[15]))));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coverage (replaces dr.rasterize's visibility, mesh_sfs_optim.py:267): one block = one meshlet in one view.
+//  1. the meshlet's <= 1024 vertices are gathered (16 B each, from the 1.6 MB vertex record array), transformed to clip
+//     space and snapped to the rasteriser's 24.8 grid into SHARED memory - once per (view, meshlet vertex) instead of a
+//     [n,V] array in HBM written by a transform kernel and gathered three times per triangle;
+//  2. every thread tests kTPT triangles against integer bounding boxes / edge functions on the shared snapped
+//     coordinates; hits go to a per-warp fragment queue;
+//  3. the queue is resolved densely (perspective barycentric depth from the shared clip positions, 64-bit atomicMin on
+//     depth | ORIGINAL triangle id), touched 16x16 tiles are collected in a shared bitmap and appended to the slot's
+//     global work list at block end.
+// Rule and arithmetic are those of raster.cu and of the CPU checker (bit-exact ids and depth).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFragQueue = 160;  // per-warp capacity; overflowing fragments (large triangles) are resolved in place
+
+template <typename I>
+__device__ __forceinline__ bool ml_owns_edge(I dx, I dy) { return dy > 0 || (dy == 0 && dx > 0); }
+
+__device__ __forceinline__ void ml_resolve(const float4* pos_s, uint32_t packed, uint32_t tid_orig, int px, int py, int W,
+                                           float invW, float invH, unsigned long long* __restrict__ zb) {
+    const float4 p0 = pos_s[packed & 1023u], p1 = pos_s[(packed >> 10) & 1023u], p2 = pos_s[(packed >> 20) & 1023u];
+    const Bary b = bary_at(p0, p1, p2, px, py, invW, invH);
+    atomicMin(&zb[(size_t)py * W + px], ((unsigned long long)depth_key(b.zw) << 32) | tid_orig);
+}
+
+template <typename I>
+__device__ __forceinline__ void ml_cover(int X0, int Y0, int X1, int Y1, int X2, int Y2, int px0, int px1, int py0, int py1,
+                                         const float4* pos_s, uint2 rec, uint32_t slot, int W, float invW, float invH,
+                                         unsigned long long* __restrict__ zb, unsigned int* tbits, int tiles_x,
+                                         int* qcount, uint2* queue) {
+    const I dx0 = X2 - X1, dy0 = Y2 - Y1;
+    const I dx1 = X0 - X2, dy1 = Y0 - Y2;
+    const I dx2 = X1 - X0, dy2 = Y1 - Y0;
+    // bias folds the tie rule into a strict comparison: inside <=> e + bias > 0
+    const I b0 = ml_owns_edge(dx0, dy0) ? 1 : 0, b1 = ml_owns_edge(dx1, dy1) ? 1 : 0, b2 = ml_owns_edge(dx2, dy2) ? 1 : 0;
+    const int Cx0 = px0 * 256 + 128;
+    for (int py = py0; py <= py1; py++) {
+        const int Cy = py * 256 + 128;
+        I e0 = dx0 * (I)(Cy - Y1) - dy0 * (I)(Cx0 - X1);
+        I e1 = dx1 * (I)(Cy - Y2) - dy1 * (I)(Cx0 - X2);
+        I e2 = dx2 * (I)(Cy - Y0) - dy2 * (I)(Cx0 - X0);
+        for (int px = px0; px <= px1; px++) {
+            if (e0 + b0 > 0 && e1 + b1 > 0 && e2 + b2 > 0) {
+                const int tile = (py >> 4) * tiles_x + (px >> 4);
+                atomicOr(tbits + (tile >> 5), 1u << (tile & 31));
+                const int q = atomicAdd(qcount, 1);
+                if (q < kFragQueue) queue[q] = make_uint2(slot, ((uint32_t)py << 16) | (uint32_t)px);
+                else ml_resolve(pos_s, rec.x, rec.y, px, py, W, invW, invH, zb);
+            }
+            e0 -= dy0 * 256;
+            e1 -= dy1 * 256;
+            e2 -= dy2 * 256;
+        }
+    }
+}
+
+__device__ __forceinline__ void ml_test(uint2 rec, uint32_t slot, const float4* pos_s, const int2* snap_s, int H, int W,
+                                        float invW, float invH, unsigned long long* __restrict__ zb, unsigned int* tbits,
+                                        int tiles_x, int* qcount, uint2* queue) {
+    if (rec.x == 0xffffffffu) return;  // padding
+    const int2 s0 = snap_s[rec.x & 1023u], s1 = snap_s[(rec.x >> 10) & 1023u], s2 = snap_s[(rec.x >> 20) & 1023u];
+    if (s0.x == kSnapRejected || s1.x == kSnapRejected || s2.x == kSnapRejected) return;
+    int X0 = s0.x, Y0 = s0.y, X1 = s1.x, Y1 = s1.y, X2 = s2.x, Y2 = s2.y;
+    const int minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
+    const int minY = min(Y0, min(Y1, Y2)), maxY = max(Y0, max(Y1, Y2));
+    // pixel centres (px*256+128) inside [min,max]
+    const int px0 = max(0, (minX - 128 + 255) >> 8), px1 = min(W - 1, (maxX - 128) >> 8);
+    const int py0 = max(0, (minY - 128 + 255) >> 8), py1 = min(H - 1, (maxY - 128) >> 8);
+    if (px0 > px1 || py0 > py1) return;  // no pixel centre in the bounding box: the common case
+    const bool small = (maxX - minX) < 32768 && (maxY - minY) < 32768 && px1 < 65536 && py1 < 65536;
+    bool neg;
+    if (small) {
+        const int a = (X1 - X0) * (Y2 - Y0) - (X2 - X0) * (Y1 - Y0);  // |factors| < 2^15: exact in 32 bits
+        if (a == 0) return;
+        neg = a < 0;
+    } else {
+        const long long a = (long long)(X1 - X0) * (Y2 - Y0) - (long long)(X2 - X0) * (Y1 - Y0);
+        if (a == 0) return;
+        neg = a < 0;
+    }
+    if (neg) {  // orient for coverage only; barycentrics keep the original vertex order
+        int tx = X1; X1 = X2; X2 = tx;
+        int ty = Y1; Y1 = Y2; Y2 = ty;
+    }
+    if (small) ml_cover<int>(X0, Y0, X1, Y1, X2, Y2, px0, px1, py0, py1, pos_s, rec, slot, W, invW, invH, zb, tbits, tiles_x, qcount, queue);
+    else ml_cover<long long>(X0, Y0, X1, Y1, X2, Y2, px0, px1, py0, py1, pos_s, rec, slot, W, invW, invH, zb, tbits, tiles_x, qcount, queue);
+}
+
+template <int TPT>
+__global__ void __launch_bounds__(256, 4) ham_coverage_meshlet_kernel(
+    const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ ml_vptr,
+    const int32_t* __restrict__ ml_verts, const uint2* __restrict__ ml_tri2, int max_verts, int H, int W, float invW,
+    float invH, unsigned long long* __restrict__ zbuf, uint32_t* __restrict__ gbits, uint32_t* __restrict__ glist,
+    int* __restrict__ gcount, int tiles_x, int tiles_per_view) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float4* pos_s = reinterpret_cast<float4*>(dyn_smem);
+    int2* snap_s = reinterpret_cast<int2*>(pos_s + max_verts);
+    unsigned int* tbits = reinterpret_cast<unsigned int*>(snap_s + max_verts);  // (tiles_per_view + 31) / 32 words
+    __shared__ uint2 queue[8][kFragQueue];
+    __shared__ int qcount[8];
+    __shared__ float Ms[kViewM];
+    const int m = blockIdx.x, n = blockIdx.y;
+    const int words = (tiles_per_view + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) qcount[warp] = 0;
+    if (threadIdx.x < kViewM) Ms[threadIdx.x] = viewM[(size_t)n * kViewM + threadIdx.x];
+    // triangle records of this thread: issued before the vertex phase so their latency hides behind it
+    uint2 rec[TPT];
+    const uint2* recs = ml_tri2 + (size_t)m * (TPT * 256);
+#pragma unroll
+    for (int k = 0; k < TPT; k++) rec[k] = __ldg(recs + k * 256 + threadIdx.x);
+    const int vb = __ldg(ml_vptr + m), nv = __ldg(ml_vptr + m + 1) - vb;
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x < kViewM * nv) {
-        const int slot = threadIdx.x / kViewM, k = threadIdx.x - slot * kViewM, r = k >> 2, j = k & 3;
-        viewM[(n0 + slot) * kViewM + k] = Wm[slot][4 * r] * Pm[slot][j] + Wm[slot][4 * r + 1] * Pm[slot][4 + j] +
-                                          Wm[slot][4 * r + 2] * Pm[slot][8 + j] + Wm[slot][4 * r + 3] * Pm[slot][12 + j];
-    }
-    if (i >= V) return;
     const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
-    for (int sl = 0; sl < nv; sl++) {
-        const float* w = Wm[sl];
-        const float* q = Pm[sl];
-        const float r0 = x * w[0] + y * w[4] + z * w[8] + w[12], r1 = x * w[1] + y * w[5] + z * w[9] + w[13];
-        const float r2 = x * w[2] + y * w[6] + z * w[10] + w[14], r3 = x * w[3] + y * w[7] + z * w[11] + w[15];
-        const float4 p = make_float4(r0 * q[0] + r1 * q[4] + r2 * q[8] + r3 * q[12], r0 * q[1] + r1 * q[5] + r2 * q[9] + r3 * q[13],
-                                     r0 * q[2] + r1 * q[6] + r2 * q[10] + r3 * q[14], r0 * q[3] + r1 * q[7] + r2 * q[11] + r3 * q[15]);
-        const size_t o = (size_t)(n0 + sl) * V + i;
-        pos[o] = p;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const float4 v = __ldg(vg + 2 * (size_t)__ldg(ml_verts + vb + i));
+        const float4 p = clip_from_world(Ms, v);
+        pos_s[i] = p;
         int X = kSnapRejected, Y = 0;
         if (!snap_vertex(p, hw, hh, X, Y)) X = kSnapRejected;
-        snap[o] = make_int2(X, Y);
-        scr[o] = aa_window_xy(p, hw, hh);
+        snap_s[i] = make_int2(X, Y);
+    }
+    __syncthreads();
+    unsigned long long* zb = zbuf + (size_t)n * H * W;
+#pragma unroll
+    for (int k = 0; k < TPT; k++)
+        ml_test(rec[k], (uint32_t)(k * 256 + threadIdx.x), pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x,
+                &qcount[warp], queue[warp]);
+    __syncwarp();
+    const int nq = min(qcount[warp], kFragQueue);
+    for (int e = lane; e < nq; e += 32) {
+        const uint2 f = queue[warp][e];
+        const uint2 r = __ldg(recs + f.x);
+        ml_resolve(pos_s, r.x, r.y, (int)(f.y & 0xffffu), (int)(f.y >> 16), W, invW, invH, zb);
+    }
+    __syncthreads();
+    // flush: tiles this block touched first (global bitmap de-duplicates) are appended to the slot's work list
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        const unsigned int bits = tbits[w];
+        if (bits == 0) continue;
+        unsigned int fresh = bits & ~atomicOr(gbits + (size_t)n * words + w, bits);
+        while (fresh) {
+            const int bit = __ffs(fresh) - 1;
+            fresh &= fresh - 1;
+            const int tile = (w << 5) + bit;
+            const int by = tile / tiles_x, bx = tile - by * tiles_x;
+            glist[atomicAdd(gcount, 1)] = ((uint32_t)n << 20) | ((uint32_t)by << 10) | (uint32_t)bx;
+        }
     }
 }
 
@@ -205,25 +390,63 @@ struct PixTri {
     int i0, i1, i2;
     float4 p0, p1, p2;
     float u, v;
+    float3 n0, n1, n2;  // vertex normals
+    float3 b0, b1, b2;  // vertex albedo
+    float d0, d1, d2;   // degenerate-normal flags
 };
 
-__device__ __forceinline__ void load_pixtri(int t, int px, int py, const float4* __restrict__ P,
-                                            const int32_t* __restrict__ tri, float invW, float invH, PixTri& q) {
-    q.i0 = __ldg(tri + 3 * t); q.i1 = __ldg(tri + 3 * t + 1); q.i2 = __ldg(tri + 3 * t + 2);
-    q.p0 = __ldg(P + q.i0); q.p1 = __ldg(P + q.i1); q.p2 = __ldg(P + q.i2);
+// Every per-pixel gather is a 128- or 256-bit load: the triangle's corners come from the padded int4 copy of `tri`,
+// world-space vertices are float4 (clip positions are recomputed from them), and normal + albedo of a vertex are one 32-byte record (vattr).  With 12-byte records each
+// of these was three scalar gathers, i.e. 32 L1 wavefronts per warp instruction, and the pixel passes are bound by the
+// number of L1 wavefronts (distinct sectors per warp instruction), not by DRAM.
+__device__ __forceinline__ void load_pixtri(int t, int px, int py, const float4* __restrict__ vg, const float* M,
+                                            const int4* __restrict__ tri4, const float4* __restrict__ vattr, float invW,
+                                            float invH, PixTri& q) {
+    const int4 ix = __ldg(tri4 + t);
+    q.i0 = ix.x; q.i1 = ix.y; q.i2 = ix.z;
+    q.p0 = clip_from_world(M, __ldg(vg + 2 * (size_t)q.i0));
+    q.p1 = clip_from_world(M, __ldg(vg + 2 * (size_t)q.i1));
+    q.p2 = clip_from_world(M, __ldg(vg + 2 * (size_t)q.i2));
+    const F8 a0 = ldg256(vattr + 2 * (size_t)q.i0), a1 = ldg256(vattr + 2 * (size_t)q.i1),
+             a2 = ldg256(vattr + 2 * (size_t)q.i2);
+    q.n0 = make_float3(a0.a.x, a0.a.y, a0.a.z); q.b0 = make_float3(a0.b.x, a0.b.y, a0.b.z);
+    q.n1 = make_float3(a1.a.x, a1.a.y, a1.a.z); q.b1 = make_float3(a1.b.x, a1.b.y, a1.b.z);
+    q.n2 = make_float3(a2.a.x, a2.a.y, a2.a.z); q.b2 = make_float3(a2.b.x, a2.b.y, a2.b.z);
+    q.d0 = a0.a.w; q.d1 = a1.a.w; q.d2 = a2.a.w;
     const Bary b = bary_at(q.p0, q.p1, q.p2, px, py, invW, invH);
     q.u = b.u; q.v = b.v;
 }
 
-__device__ __forceinline__ float3 interp3(const float* __restrict__ a, const PixTri& q) {
+__device__ __forceinline__ float3 interp3(const float3 a0, const float3 a1, const float3 a2, const PixTri& q) {
     const float w = 1.0f - q.u - q.v;
-    const float* a0 = a + 3 * (size_t)q.i0;
-    const float* a1 = a + 3 * (size_t)q.i1;
-    const float* a2 = a + 3 * (size_t)q.i2;
-    return make_float3(q.u * __ldg(a0) + q.v * __ldg(a1) + w * __ldg(a2),
-                       q.u * __ldg(a0 + 1) + q.v * __ldg(a1 + 1) + w * __ldg(a2 + 1),
-                       q.u * __ldg(a0 + 2) + q.v * __ldg(a1 + 2) + w * __ldg(a2 + 2));
+    return make_float3(q.u * a0.x + q.v * a1.x + w * a2.x, q.u * a0.y + q.v * a1.y + w * a2.y,
+                       q.u * a0.z + q.v * a1.z + w * a2.z);
 }
+
+// Tangent frame of a unit normal (branchless orthonormal basis, Duff et al. 2017).  The normalisation backward of a
+// vertex normal only keeps the tangential part of its gradient (models/utils.py:547 F.normalize), so the pixel
+// backward accumulates the two tangential components (t1.g, t2.g) instead of three Cartesian ones and the update pass
+// rebuilds g_tangential = t1 (t1.g) + t2 (t2.g) from the identical frame: 8 floats = ONE 32-byte sector per vertex.
+__device__ __forceinline__ void tangent_frame(const float3 n, float3& t1, float3& t2) {
+    const float sg = copysignf(1.0f, n.z);
+    const float a = -1.0f / (sg + n.z);
+    const float b = n.x * n.y * a;
+    t1 = make_float3(1.0f + sg * n.x * n.x * a, sg * b, -sg * n.x);
+    t2 = make_float3(b, sg + n.y * n.y * a, -n.y);
+}
+
+// Window coordinates for the antialias rule straight from the world-space vertex (same arithmetic as aa_window_xy on
+// the clip position every other kernel derives).
+struct AAProjWorld {
+    const float4* vg;
+    const float* M;
+    float xh, yh;
+    __device__ __forceinline__ void operator()(int v, float fx, float fy, float& x, float& y) const {
+        const float2 s = aa_window_xy(clip_from_world(M, __ldg(vg + 2 * (size_t)v)), xh, yh);
+        x = xs(s.x, fx);
+        y = xs(s.y, fy);
+    }
+};
 
 // models/utils.py:208-226, same term order
 __device__ __forceinline__ float sh_radiance(const float* c, float x, float y, float z) {
@@ -329,9 +552,12 @@ __device__ __forceinline__ void tile_mark_active(const TileCtx& tc, int tid, uin
     if (!(old & bit)) alist[atomicAdd(acount, 1)] = tile_encode(tc.n, bx, by);
 }
 
-// Per-vertex accumulator layout in `packed` (12 floats = 3 float4):
-//   A = (photo_pos.xyz, mask_pos.x)  B = (mask_pos.yz, normal.xy)  C = (normal.z, albedo.bgr)
-// photo_* are gradients of the UN-NORMALISED photometric sum  sum |tmp_img - img|, mask_pos of sum (pred - valid)^2 / 2.
+// Per-vertex accumulator layout in `packed` (12V floats, viewed as 3V float4):
+//   G8[2i]   = (photo_pos.xyz, normal.t1)   G8[2i+1] = (normal.t2, albedo.bgr)    one 32-byte sector per vertex, the
+//                                                                                   only record the pixel backward hits
+//   Gm[i] = packed4[2V + i] = (mask_pos.xyz, normal.z of degenerate vertices)       silhouette pairs only
+// photo_* are gradients of the UN-NORMALISED photometric sum  sum |tmp_img - img|, mask_pos of sum (pred - valid)^2 / 2;
+// normal.t1/t2 are the components of the vertex-normal gradient in tangent_frame(normal) (x, y for degenerate normals).
 
 // ------------------------------------------------------------------------------------------------
 // z-buffer key layout after the shade pass (low word): bits 0..27 triangle id, 28..30 silhouette-candidate bits of
@@ -425,10 +651,10 @@ __device__ __forceinline__ PairItem decode_pair_item(uint32_t item, const TileCt
 // the silhouette bits / valid flag and resets the OTHER z-buffer slot for the next iteration (no separate clear pass).
 template <int PHASE>
 __device__ __forceinline__ void shade_tile(const Strip& st, unsigned long long* __restrict__ zbuf,
-                                           const float4* __restrict__ pos, const float2* __restrict__ scr, float invW,
-                                           float invH, const int32_t* __restrict__ tri,
-                                           const int32_t* __restrict__ opp, const float* __restrict__ normals,
-                                           const float* __restrict__ albedo, const float* __restrict__ masks,
+                                           const float4* __restrict__ vg, const float* __restrict__ viewM, float invW,
+                                           float invH, const int4* __restrict__ tri4, const int4* __restrict__ opp4,
+                                           const float4* __restrict__ vattr,
+                                           const float* __restrict__ masks,
                                            const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx,
                                            const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
                                            float4* __restrict__ plane0, float4* __restrict__ plane1,
@@ -448,14 +674,25 @@ __device__ __forceinline__ void shade_tile(const Strip& st, unsigned long long* 
         const unsigned long long key = zbuf[pix];
         if (key != ZB_EMPTY) {
             const int t = (int)((uint32_t)key & kTriMask);
-            const float4* Pv = pos + (size_t)n * V;
+            const ViewM Mv = load_viewM(viewM + (size_t)n * kViewM);
             PixTri q;
-            load_pixtri(t, px, py, Pv, tri, invW, invH, q);
+            load_pixtri(t, px, py, vg, Mv.m, tri4, vattr, invW, invH, q);
             AAGeom g;
             g.bits = 0;
-            aa_triangle_geom(t, px, py, AAProjScreen{scr + (size_t)n * V}, tri, opp, V, T, H, W, g);
-            const float3 m = interp3(normals, q);
-            const float3 a = interp3(albedo, q);
+            {
+                // silhouette-candidate bits of this triangle in this pixel's frame; window coordinates of the corners
+                // come from the clip positions already in registers, those of the three wing vertices are gathered
+                const int4 ox = __ldg(opp4 + t);
+                const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
+                float2 so0 = make_float2(0.f, 0.f), so1 = so0, so2 = so0;
+                if ((unsigned)ox.x < (unsigned)V) so0 = aa_window_xy(clip_from_world(Mv.m, __ldg(vg + 2 * (size_t)ox.x)), xh, yh);
+                if ((unsigned)ox.y < (unsigned)V) so1 = aa_window_xy(clip_from_world(Mv.m, __ldg(vg + 2 * (size_t)ox.y)), xh, yh);
+                if ((unsigned)ox.z < (unsigned)V) so2 = aa_window_xy(clip_from_world(Mv.m, __ldg(vg + 2 * (size_t)ox.z)), xh, yh);
+                aa_triangle_geom_win(q.i0, q.i1, q.i2, aa_window_xy(q.p0, xh, yh), aa_window_xy(q.p1, xh, yh),
+                                     aa_window_xy(q.p2, xh, yh), ox.x, ox.y, ox.z, so0, so1, so2, px, py, V, H, W, g);
+            }
+            const float3 m = interp3(q.n0, q.n1, q.n2, q);
+            const float3 a = interp3(q.b0, q.b1, q.b2, q);
             const bool valid = __ldg(masks + (size_t)view * hw + rem) > 0.0f;
             nvalid = valid ? 1.0f : 0.0f;
             feeds_backward = PHASE == 1 ? valid : true;  // phase A back-propagates through every covered pixel's albedo
@@ -490,12 +727,11 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
                                                         uint32_t* __restrict__ abits, uint32_t* __restrict__ alist,
                                                         int* __restrict__ acount, int* __restrict__ cursors,
                                                         int tiles_x, int tiles_y,
-                                                        const float4* __restrict__ pos,
-                                                        const float2* __restrict__ scr, float invW, float invH,
-                                                        const int32_t* __restrict__ tri,
-                                                        const int32_t* __restrict__ opp,
-                                                        const float* __restrict__ normals,
-                                                        const float* __restrict__ albedo,
+                                                        const float4* __restrict__ vg,
+                                                        const float* __restrict__ viewM, float invW, float invH,
+                                                        const int4* __restrict__ tri4,
+                                                        const int4* __restrict__ opp4,
+                                                        const float4* __restrict__ vattr,
                                                         const float* __restrict__ masks,
                                                         const float* __restrict__ sh_coeffs,
                                                         const int32_t* __restrict__ view_idx,
@@ -530,7 +766,7 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
         if (st.tid < 5) tile_mark_active(st.tc, st.tid, abits, alist, acount);  // strip 0 of the tile dilates it
         bool fb;
         uint32_t pix32;
-        shade_tile<PHASE>(st, zbuf, pos, scr, invW, invH, tri, opp, normals, albedo, masks, sh_coeffs, view_idx, sh_idx, V, T, H,
+        shade_tile<PHASE>(st, zbuf, vg, viewM, invW, invH, tri4, opp4, vattr, masks, sh_coeffs, view_idx, sh_idx, V, T, H,
                           W, plane0, plane1, acc, fb, pix32);
         const unsigned m = __ballot_sync(0xffffffffu, fb);
         if (m) {
@@ -546,7 +782,7 @@ __global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __re
 template <int PHASE>
 __device__ __forceinline__ void aa_loss_tile(
     const Strip& st, const unsigned long long* __restrict__ zbuf,
-    const float2* __restrict__ scr, const int32_t* __restrict__ tri,
+    const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
@@ -577,7 +813,7 @@ __device__ __forceinline__ void aa_loss_tile(
 #pragma unroll
         for (int c = 0; c < NC; c++) blend[lane][c] = 0.0f;
         __syncwarp();
-        const AAProjScreen proj{scr + (size_t)n * V};
+        const AAProjWorld proj{vg, viewM + (size_t)n * kViewM, 0.5f * (float)W, 0.5f * (float)H};
         for (int e = lane; e < nq; e += 32) {
             const PairItem it = decode_pair_item(q_items[e], tc);
             const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
@@ -697,7 +933,8 @@ __device__ __forceinline__ void aa_loss_tile(
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
-    int* __restrict__ cursors, int tiles_x, int tiles_y, const float2* __restrict__ scr, const int32_t* __restrict__ tri,
+    int* __restrict__ cursors, int tiles_x, int tiles_y, const float4* __restrict__ vg,
+    const float* __restrict__ viewM, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
@@ -715,7 +952,7 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     Strip st;
     int u = blockIdx.x * 8 + wib;
     while (next_strip(u, alist, na, tiles_x, tiles_y, st))
-        aa_loss_tile<PHASE>(st, zbuf, scr, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
+        aa_loss_tile<PHASE>(st, zbuf, vg, viewM, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
                             plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items[wib], q_n[wib],
                             blend[wib], plist_a, plist_b, pcount, pcap, status);
 }
@@ -730,9 +967,9 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
 //   * phase B: silhouette position gradient -> world-space accumulators.
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
-__global__ void __launch_bounds__(256) ham_pair_bwd_kernel(
+__global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
     const uint4* __restrict__ plist_a, const uint32_t* __restrict__ plist_b, const int* __restrict__ pcount, int pcap,
-    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ pos, const float* __restrict__ viewM, int V,
+    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ vg, const float* __restrict__ viewM, int V,
     int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ gplane0,
     const float4* __restrict__ gplane1, float4* __restrict__ gdelta, float4* __restrict__ G) {
     const int np = min(*pcount, pcap);
@@ -765,13 +1002,19 @@ __global__ void __launch_bounds__(256) ham_pair_bwd_kernel(
             if (dd_img != 0.0f || dd_msk != 0.0f) {
                 const float* M = viewM + (size_t)n * kViewM;
                 float4 e1, e2;
-                aa_pos_grad(pr, qx, qy, d, reinterpret_cast<const float*>(pos + (size_t)n * V), H, W, 1.0f, e1, e2);
+                aa_pos_grad(pr, qx, qy, d, clip_from_world(M, __ldg(vg + 2 * (size_t)pr.i1)),
+                            clip_from_world(M, __ldg(vg + 2 * (size_t)pr.i2)), H, W, 1.0f, e1, e2);
                 const float3 w1 = clip_to_world(M, e1.x, e1.y, e1.w);
                 const float3 w2 = clip_to_world(M, e2.x, e2.y, e2.w);
-                atomicAdd(G + 3 * (size_t)pr.i1, make_float4(dd_img * w1.x, dd_img * w1.y, dd_img * w1.z, dd_msk * w1.x));
-                atomicAdd(G + 3 * (size_t)pr.i1 + 1, make_float4(dd_msk * w1.y, dd_msk * w1.z, 0.f, 0.f));
-                atomicAdd(G + 3 * (size_t)pr.i2, make_float4(dd_img * w2.x, dd_img * w2.y, dd_img * w2.z, dd_msk * w2.x));
-                atomicAdd(G + 3 * (size_t)pr.i2 + 1, make_float4(dd_msk * w2.y, dd_msk * w2.z, 0.f, 0.f));
+                float4* Gm = G + 2 * (size_t)V;
+                if (dd_img != 0.0f) {
+                    atomicAdd(G + 2 * (size_t)pr.i1, make_float4(dd_img * w1.x, dd_img * w1.y, dd_img * w1.z, 0.f));
+                    atomicAdd(G + 2 * (size_t)pr.i2, make_float4(dd_img * w2.x, dd_img * w2.y, dd_img * w2.z, 0.f));
+                }
+                if (dd_msk != 0.0f) {
+                    atomicAdd(Gm + pr.i1, make_float4(dd_msk * w1.x, dd_msk * w1.y, dd_msk * w1.z, 0.f));
+                    atomicAdd(Gm + pr.i2, make_float4(dd_msk * w2.x, dd_msk * w2.y, dd_msk * w2.z, 0.f));
+                }
             }
         }
     }
@@ -784,8 +1027,8 @@ __global__ void __launch_bounds__(256) ham_pair_bwd_kernel(
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
     const uint32_t* __restrict__ vlist, const int* __restrict__ vcount, const unsigned long long* __restrict__ zbuf,
-    const float4* __restrict__ pos, float invW, float invH, const float* __restrict__ viewM,
-    const int32_t* __restrict__ tri, const float* __restrict__ normals, const float* __restrict__ albedo,
+    const float4* __restrict__ vg, float invW, float invH, const float* __restrict__ viewM,
+    const int4* __restrict__ tri4, const float4* __restrict__ vattr,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, int V, int H, int W,
     const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ gdelta,
     float4* __restrict__ G) {
@@ -798,7 +1041,6 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
         const NbrKeys self = decode_key(zbuf[pix]);
         const float* M = viewM + (size_t)n * kViewM;
         const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
-        const float4* Pv = pos + (size_t)n * V;
         // gradient w.r.t. this pixel's PRE-antialias values: pass-through + pair terms (consumed and re-armed)
         float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
         const float4 gd = gdelta[pix];
@@ -811,21 +1053,21 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
             g1.x += gd.x; g1.y += gd.y; g1.z += gd.z;
         }
         PixTri q;
-        load_pixtri(self.tri, px, py, Pv, tri, invW, invH, q);
+        load_pixtri(self.tri, px, py, vg, M, tri4, vattr, invW, invH, q);
         const float w = 1.0f - q.u - q.v;
         if (PHASE == 0) {
             // only the albedo attribute is trainable: interpolate bwd
             if (g1.x == 0.0f && g1.y == 0.0f && g1.z == 0.0f) continue;
-            atomicAdd(G + 3 * (size_t)q.i0 + 2, make_float4(0.f, q.u * g1.x, q.u * g1.y, q.u * g1.z));
-            atomicAdd(G + 3 * (size_t)q.i1 + 2, make_float4(0.f, q.v * g1.x, q.v * g1.y, q.v * g1.z));
-            atomicAdd(G + 3 * (size_t)q.i2 + 2, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
+            atomicAdd(G + 2 * (size_t)q.i0 + 1, make_float4(0.f, q.u * g1.x, q.u * g1.y, q.u * g1.z));
+            atomicAdd(G + 2 * (size_t)q.i1 + 1, make_float4(0.f, q.v * g1.x, q.v * g1.y, q.v * g1.z));
+            atomicAdd(G + 2 * (size_t)q.i2 + 1, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
             continue;
         }
         // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286)
         if (!self.valid) continue;
         if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) continue;
-        const float3 m = interp3(normals, q);
-        const float3 a = interp3(albedo, q);
+        const float3 m = interp3(q.n0, q.n1, q.n2, q);
+        const float3 a = interp3(q.b0, q.b1, q.b2, q);
         const float len = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
         const float inv = 1.0f / fmaxf(len, 1e-12f);
         const float nx = m.x * inv, ny = m.y * inv, nz = m.z * inv;
@@ -843,14 +1085,10 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
             gm = make_float3(gn.x * inv, gn.y * inv, gn.z * inv);
         }
         // interpolate bwd: d/du, d/dv over the six differentiable attributes
-        const float* n0 = normals + 3 * (size_t)q.i0; const float* n1 = normals + 3 * (size_t)q.i1; const float* n2 = normals + 3 * (size_t)q.i2;
-        const float* b0 = albedo + 3 * (size_t)q.i0; const float* b1 = albedo + 3 * (size_t)q.i1; const float* b2 = albedo + 3 * (size_t)q.i2;
-        const float n2x = __ldg(n2), n2y = __ldg(n2 + 1), n2z = __ldg(n2 + 2);
-        const float b2x = __ldg(b2), b2y = __ldg(b2 + 1), b2z = __ldg(b2 + 2);
-        const float du = gm.x * (__ldg(n0) - n2x) + gm.y * (__ldg(n0 + 1) - n2y) + gm.z * (__ldg(n0 + 2) - n2z) +
-                         ga.x * (__ldg(b0) - b2x) + ga.y * (__ldg(b0 + 1) - b2y) + ga.z * (__ldg(b0 + 2) - b2z);
-        const float dv = gm.x * (__ldg(n1) - n2x) + gm.y * (__ldg(n1 + 1) - n2y) + gm.z * (__ldg(n1 + 2) - n2z) +
-                         ga.x * (__ldg(b1) - b2x) + ga.y * (__ldg(b1 + 1) - b2y) + ga.z * (__ldg(b1 + 2) - b2z);
+        const float du = gm.x * (q.n0.x - q.n2.x) + gm.y * (q.n0.y - q.n2.y) + gm.z * (q.n0.z - q.n2.z) +
+                         ga.x * (q.b0.x - q.b2.x) + ga.y * (q.b0.y - q.b2.y) + ga.z * (q.b0.z - q.b2.z);
+        const float dv = gm.x * (q.n1.x - q.n2.x) + gm.y * (q.n1.y - q.n2.y) + gm.z * (q.n1.z - q.n2.z) +
+                         ga.x * (q.b1.x - q.b2.x) + ga.y * (q.b1.y - q.b2.y) + ga.z * (q.b1.z - q.b2.z);
         // rasterize bwd
         const float fx = (float)(2 * px + 1) / (float)W - 1.0f;
         const float fy = (float)(2 * py + 1) / (float)H - 1.0f;
@@ -871,31 +1109,53 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
         const float3 w0 = clip_to_world(M, g0x, g0y, -fx * g0x - fy * g0y);
         const float3 w1 = clip_to_world(M, g1x, g1y, -fx * g1x - fy * g1y);
         const float3 w2 = clip_to_world(M, g2x, g2y, -fx * g2x - fy * g2y);
-        float4* G0 = G + 3 * (size_t)q.i0; float4* G1 = G + 3 * (size_t)q.i1; float4* G2 = G + 3 * (size_t)q.i2;
-        atomicAdd(G0, make_float4(w0.x, w0.y, w0.z, 0.f));
-        atomicAdd(G0 + 1, make_float4(0.f, 0.f, q.u * gm.x, q.u * gm.y));
-        atomicAdd(G0 + 2, make_float4(q.u * gm.z, q.u * ga.x, q.u * ga.y, q.u * ga.z));
-        atomicAdd(G1, make_float4(w1.x, w1.y, w1.z, 0.f));
-        atomicAdd(G1 + 1, make_float4(0.f, 0.f, q.v * gm.x, q.v * gm.y));
-        atomicAdd(G1 + 2, make_float4(q.v * gm.z, q.v * ga.x, q.v * ga.y, q.v * ga.z));
-        atomicAdd(G2, make_float4(w2.x, w2.y, w2.z, 0.f));
-        atomicAdd(G2 + 1, make_float4(0.f, 0.f, w * gm.x, w * gm.y));
-        atomicAdd(G2 + 2, make_float4(w * gm.z, w * ga.x, w * ga.y, w * ga.z));
+        const int vi[3] = {q.i0, q.i1, q.i2};
+        const float wt[3] = {q.u, q.v, w};
+        const float3 wp[3] = {w0, w1, w2};
+        const float3 nn[3] = {q.n0, q.n1, q.n2};
+        const float dg[3] = {q.d0, q.d1, q.d2};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float3 gk = make_float3(wt[k] * gm.x, wt[k] * gm.y, wt[k] * gm.z);  // d/d(vertex normal attribute)
+            float a1, a2;
+            if (dg[k] == 0.0f) {
+                float3 t1, t2;
+                tangent_frame(nn[k], t1, t2);
+                a1 = t1.x * gk.x + t1.y * gk.y + t1.z * gk.z;
+                a2 = t2.x * gk.x + t2.y * gk.y + t2.z * gk.z;
+            } else {  // |N| <= 1e-6: the normalisation does not project, keep all three components
+                a1 = gk.x; a2 = gk.y;
+                atomicAdd(reinterpret_cast<float*>(G + 2 * (size_t)V + vi[k]) + 3, gk.z);
+            }
+            float4* Gk = G + 2 * (size_t)vi[k];
+            atomicAdd(Gk, make_float4(wp[k].x, wp[k].y, wp[k].z, a1));
+            atomicAdd(Gk + 1, make_float4(a2, wt[k] * ga.x, wt[k] * ga.y, wt[k] * ga.z));
+        }
     }
 }
 
-__global__ void ham_finalize_scalars_kernel(const double* __restrict__ acc, const double* __restrict__ view_vm2,
-                                            const int32_t* __restrict__ view_idx, int n_views, int tiles, int phase,
-                                            float* __restrict__ scal) {
-    if (threadIdx.x == 0) {
-        double vm2 = 0.0;  // sum of valid_mask^2 over the tiles no block visited = view totals - visited tiles
-        if (phase == 1) {
-            for (int n = 0; n < n_views; n++) vm2 += view_vm2[(size_t)view_idx[n] * (tiles + 1) + tiles];
-            vm2 -= acc_total(acc, 7);
-        }
-        scal[0] = (float)acc_total(acc, 0);
-        scal[1] = (float)acc_total(acc, 1);
-        scal[2] = (float)(acc_total(acc, 2) + vm2);
+// One warp: lane j owns spread slot j of every accumulator (fp64 shuffles), view totals are strided over the lanes.
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(32) ham_finalize_scalars_kernel(const double* __restrict__ acc,
+                                                                  const double* __restrict__ view_vm2,
+                                                                  const int32_t* __restrict__ view_idx, int n_views,
+                                                                  int tiles, int phase, float* __restrict__ scal) {
+    const int lane = threadIdx.x;
+    double vm2 = 0.0;  // sum of valid_mask^2 over the tiles no block visited = view totals - visited tiles
+    if (phase == 1) {
+        for (int n = lane; n < n_views; n += 32) vm2 += view_vm2[(size_t)view_idx[n] * (tiles + 1) + tiles];
+        vm2 -= acc[7 * 32 + lane];
+    }
+    const double a0 = warp_sum_f64(acc[0 * 32 + lane]), a1 = warp_sum_f64(acc[1 * 32 + lane]);
+    const double a2 = warp_sum_f64(acc[2 * 32 + lane] + vm2);
+    if (lane == 0) {
+        scal[0] = (float)a0;
+        scal[1] = (float)a1;
+        scal[2] = (float)a2;
         scal[3] = 0.0f;
     }
 }
@@ -935,7 +1195,8 @@ __global__ void ham_view_vm2_total_kernel(int tiles, double* __restrict__ out) {
 
 // zbuf -> rast_out for fmhr_ham_debug_export
 __global__ void __launch_bounds__(256) ham_export_rast_kernel(const unsigned long long* __restrict__ zbuf,
-                                                              const float4* __restrict__ pos,
+                                                              const float4* __restrict__ vg,
+                                                              const float* __restrict__ viewM,
                                                               const int32_t* __restrict__ tri, int V, int H, int W,
                                                               float4* __restrict__ rast) {
     const int n = blockIdx.y, hw = H * W;
@@ -945,23 +1206,29 @@ __global__ void __launch_bounds__(256) ham_export_rast_kernel(const unsigned lon
     const unsigned long long key = zbuf[pix];
     if (key == ZB_EMPTY) { rast[pix] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
     const int t = (int)((uint32_t)key & kTriMask), py = rem / W, px = rem - py * W;
-    const float4* P = pos + (size_t)n * V;
-    const Bary b = bary_at(__ldg(P + __ldg(tri + 3 * t)), __ldg(P + __ldg(tri + 3 * t + 1)),
-                           __ldg(P + __ldg(tri + 3 * t + 2)), px, py, xd(1.0f, (float)W), xd(1.0f, (float)H));
+    const float* M = viewM + (size_t)n * kViewM;
+    const Bary b = bary_at(clip_from_world(M, __ldg(vg + 2 * (size_t)__ldg(tri + 3 * t))),
+                           clip_from_world(M, __ldg(vg + 2 * (size_t)__ldg(tri + 3 * t + 1))),
+                           clip_from_world(M, __ldg(vg + 2 * (size_t)__ldg(tri + 3 * t + 2))), px, py,
+                           xd(1.0f, (float)W), xd(1.0f, (float)H));
     rast[pix] = make_float4(b.u, b.v, b.zw, (float)(t + 1));
+}
+// clip positions [n,V,4] for fmhr_ham_debug_export (the iteration itself never materialises them)
+__global__ void __launch_bounds__(256) ham_export_pos_kernel(const float4* __restrict__ vg, const float* __restrict__ viewM,
+                                                             int V, float4* __restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+    if (i < V) pos[(size_t)n * V + i] = clip_from_world(viewM + (size_t)n * kViewM, __ldg(vg + 2 * (size_t)i));
 }
 
 // ------------------------------------------------------------------------------------------------
 // update: regularisers, normal backward, normalisation, Adam
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float3 ldf3(const float* p) { return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
-
-// The vertex-domain kernels below use 8 lanes per vertex (kLPV): V is only ~50k, so one thread per vertex leaves the
-// GPU at <0.3 waves of latency-bound gather loops; splitting each vertex's ~6 neighbours / incident faces over 8 lanes
-// (shuffle-reduced) gives 8x the memory-level parallelism.
-constexpr int kLPV = 8;
+// The vertex-domain kernels below use 4 lanes per vertex (kLPV): V is only ~50k, so one thread per vertex leaves the
+// GPU at <0.3 waves of latency-bound gather loops; splitting each vertex's ~6 neighbours / incident faces over 4 lanes
+// (shuffle-reduced) keeps the whole mesh in ONE wave of resident warps (8 lanes needed 1.3 waves: the tail wave
+// doubled the kernel's latency-bound run time).  Every neighbour gather is one 128/256-bit record load.
+constexpr int kLPV = 4;
 __device__ __forceinline__ float sub_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
@@ -969,12 +1236,10 @@ __device__ __forceinline__ float sub_sum(float v) {
 
 // pass 1: Laplacian forward for vertices and albedo, edge/delta losses, projector of the normal backward, Adam scalars
 __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
-    fmhr_ham_config cfg, const float* __restrict__ vertices, const float* __restrict__ delta,
-    const float* __restrict__ albedo, const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr,
-    const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx,
-    const float* __restrict__ raw, const float* __restrict__ packed, float* __restrict__ yhat_v,
-    float* __restrict__ yhat_a, float* __restrict__ gN, double* __restrict__ acc, int32_t* __restrict__ adam_step,
-    float* __restrict__ adam_sc) {
+    fmhr_ham_config cfg, float4* __restrict__ vg, const float* __restrict__ delta, const float4* __restrict__ vattr,
+    const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
+    const int32_t* __restrict__ v2v_idx, const float4* __restrict__ raw4, const float4* __restrict__ packed4,
+    float4* __restrict__ ys, double* __restrict__ acc, int32_t* __restrict__ adam_step, float* __restrict__ adam_sc) {
     __shared__ float red[4][8];
     const int V = cfg.V;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
@@ -985,19 +1250,20 @@ __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
         const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
         deg = e - b;
         for (int j = b + sub; j < e; j += kLPV) {
-            const size_t nb = 3 * (size_t)__ldg(v2v_idx + j);
-            const float3 xv = ldf3(vertices + nb), xa_ = ldf3(albedo + nb);
+            const size_t nb = 2 * (size_t)__ldg(v2v_idx + j);
+            const float4 xv = vg[nb], xa_ = __ldg(vattr + nb + 1);
             sv.x += xv.x; sv.y += xv.y; sv.z += xv.z;
             sa.x += xa_.x; sa.y += xa_.y; sa.z += xa_.z;
         }
-        vi = ldf3(vertices + 3 * (size_t)i);
+        const float4 v4 = vg[2 * (size_t)i];
+        vi = make_float3(v4.x, v4.y, v4.z);
         // edge hinge (mesh_sfs_optim.py:296-302): every half-edge is seen from both of its endpoints -> weight 1/2
         const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
         for (int j = fb + sub; j < fe; j += kLPV) {
             const int2 nb = __ldg(v2f_nbr + j);
 #pragma unroll
             for (int s = 1; s <= 2; s++) {
-                const float3 o = ldf3(vertices + 3 * (size_t)(s == 1 ? nb.x : nb.y));
+                const float4 o = vg[2 * (size_t)(s == 1 ? nb.x : nb.y)];
                 const float dx = vi.x - o.x, dy = vi.y - o.y, dz = vi.z - o.z;
                 const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
                 le += 0.5f * fminf(fmaxf(x, 0.0f), 1.0f);
@@ -1008,31 +1274,32 @@ __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
     sa.x = sub_sum(sa.x); sa.y = sub_sum(sa.y); sa.z = sub_sum(sa.z);
     if (i < V && sub == 0) {
         const float invd = (deg > 0) ? 1.0f / (float)deg : 0.0f;
-        const float3 ai = ldf3(albedo + 3 * (size_t)i);
+        const float4 at = __ldg(vattr + 2 * (size_t)i + 1), nrm = __ldg(vattr + 2 * (size_t)i);
         sv = make_float3(sv.x * invd - vi.x, sv.y * invd - vi.y, sv.z * invd - vi.z);
-        sa = make_float3(sa.x * invd - ai.x, sa.y * invd - ai.y, sa.z * invd - ai.z);
+        sa = make_float3(sa.x * invd - at.x, sa.y * invd - at.y, sa.z * invd - at.z);
         lv = sqrtf(sv.x * sv.x + sv.y * sv.y + sv.z * sv.z);
         la = sqrtf(sa.x * sa.x + sa.y * sa.y + sa.z * sa.z);
-        const float iv = lv > 0.f ? 1.0f / lv : 0.f, ia = la > 0.f ? 1.0f / la : 0.f;
-        yhat_v[3 * (size_t)i] = sv.x * iv; yhat_v[3 * (size_t)i + 1] = sv.y * iv; yhat_v[3 * (size_t)i + 2] = sv.z * iv;
-        yhat_a[3 * (size_t)i] = sa.x * ia; yhat_a[3 * (size_t)i + 1] = sa.y * ia; yhat_a[3 * (size_t)i + 2] = sa.z * ia;
-        const float3 di = ldf3(delta + 3 * (size_t)i);
-        ld = di.x * di.x + di.y * di.y + di.z * di.z;
+        // rows of the Laplacian backward: L^T yhat = sum_j yhat_j / deg_j - yhat_i
+        const float iv = lv > 0.f ? invd / lv : 0.f, ia = la > 0.f ? invd / la : 0.f;
+        ys[2 * (size_t)i] = make_float4(sv.x * iv, sv.y * iv, sv.z * iv, (float)deg);
+        ys[2 * (size_t)i + 1] = make_float4(sa.x * ia, sa.y * ia, sa.z * ia, 0.f);
+        const float* dp = delta + 3 * (size_t)i;
+        ld = dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2];
         // normal backward, step 1: through the normalisation (un-normalised photometric scale; linear, scaled later)
-        const float* Gi = packed + 12 * (size_t)i;
-        const float3 g = make_float3(Gi[6], Gi[7], Gi[8]);
-        const float3 N = ldf3(raw + 3 * (size_t)i);
-        const float len = sqrtf(N.x * N.x + N.y * N.y + N.z * N.z);
+        const float4 ga = packed4[2 * (size_t)i], gb = packed4[2 * (size_t)i + 1];
+        const float4 N = raw4[i];
         float3 r;
-        if (len > 1e-6f) {
-            const float inv = 1.0f / len;
-            const float3 nh = make_float3(N.x * inv, N.y * inv, N.z * inv);
-            const float d = nh.x * g.x + nh.y * g.y + nh.z * g.z;
-            r = make_float3((g.x - nh.x * d) * inv, (g.y - nh.y * d) * inv, (g.z - nh.z * d) * inv);
+        if (nrm.w == 0.0f) {  // |N| > 1e-6: tangential part of the gradient / |N|
+            float3 t1, t2;
+            tangent_frame(make_float3(nrm.x, nrm.y, nrm.z), t1, t2);
+            const float inv = 1.0f / N.w;
+            r = make_float3((t1.x * ga.w + t2.x * gb.x) * inv, (t1.y * ga.w + t2.y * gb.x) * inv,
+                            (t1.z * ga.w + t2.z * gb.x) * inv);
         } else {
-            r = make_float3(g.x * 1e6f, g.y * 1e6f, g.z * 1e6f);
+            const float gz = packed4[2 * (size_t)V + i].w;
+            r = make_float3(ga.w * 1e6f, gb.x * 1e6f, gz * 1e6f);
         }
-        gN[3 * (size_t)i] = r.x; gN[3 * (size_t)i + 1] = r.y; gN[3 * (size_t)i + 2] = r.z;
+        vg[2 * (size_t)i + 1] = make_float4(r.x, r.y, r.z, 0.f);
     }
     lv = warp_sum(lv); la = warp_sum(la); le = warp_sum(le); ld = warp_sum(ld);
     if ((threadIdx.x & 31) == 0) {
@@ -1046,19 +1313,18 @@ __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
         for (int w = 0; w < 8; w++) s += red[threadIdx.x][w];
         if (s != 0.0f) atomicAdd(acc + (3 + threadIdx.x) * 32 + (blockIdx.x & 31), (double)s);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= 64 && threadIdx.x < 70) {
         // Adam bias corrections (torch.optim.Adam defaults); which parameters step depends on the phase:
         //   phase A: albedo, sh   (mesh_sfs_optim.py:193)     phase B: delta, albedo   (:242-244, sh has no grad)
-        const int steps[3] = {cfg.phase == 1, 1, cfg.phase == 0};
-        const float lrs[3] = {cfg.lr, cfg.albedo_lr, cfg.sh_lr};
-        for (int k = 0; k < 3; k++) {
-            const int t = adam_step[k] + steps[k];
-            adam_step[k] = t;
-            const double b1 = 1.0 - pow((double)cfg.beta1, (double)max(t, 1));
-            const double b2 = 1.0 - pow((double)cfg.beta2, (double)max(t, 1));
-            adam_sc[2 * k] = (float)((double)lrs[k] / b1);
-            adam_sc[2 * k + 1] = (float)sqrt(b2);
-        }
+        // six fp64 pow() calls, one per lane (a single thread doing all six was a ~6 us serial tail)
+        const int q = threadIdx.x - 64, k = q >> 1;
+        const int step = k == 0 ? (cfg.phase == 1) : (k == 1 ? 1 : (cfg.phase == 0));
+        const float lr = k == 0 ? cfg.lr : (k == 1 ? cfg.albedo_lr : cfg.sh_lr);
+        const int t = adam_step[k] + step;
+        const double bc = 1.0 - pow((double)((q & 1) ? cfg.beta2 : cfg.beta1), (double)max(t, 1));
+        adam_sc[q] = (q & 1) ? (float)sqrt(bc) : (float)((double)lr / bc);
+        __syncwarp(0x3fu);  // both lanes of a parameter have read the counter before it advances
+        if ((q & 1) == 0) adam_step[k] = t;
     }
 }
 
@@ -1072,13 +1338,14 @@ __device__ __forceinline__ float adam_update(float p, float g, float* m, float* 
     return p - step_size * (mm / denom);
 }
 
-// pass 2: gather every gradient term per vertex (8 lanes each), then Adam on delta (phase B) and albedo
+__device__ __forceinline__ float pick3(const float3 v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
+
+// pass 2: gather every gradient term per vertex (kLPV lanes each), then Adam on delta (phase B) and albedo with the
+// components of the vertex spread over lanes 0..2 (coalesced Adam state traffic)
 __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
-    fmhr_ham_config cfg, const float* __restrict__ vertices, float* __restrict__ delta, float* __restrict__ albedo,
-    const int32_t* __restrict__ tri, const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr,
-    const int32_t* __restrict__ v2v_ptr, const int32_t* __restrict__ v2v_idx, const float* __restrict__ inv_deg,
-    const float* __restrict__ packed,
-    const float* __restrict__ yhat_v, const float* __restrict__ yhat_a, const float* __restrict__ gN,
+    fmhr_ham_config cfg, const float4* __restrict__ vg, float* __restrict__ delta, float* __restrict__ albedo,
+    const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
+    const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed, const float4* __restrict__ ys,
     float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
     const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad,
     const int* __restrict__ status) {
@@ -1102,32 +1369,25 @@ __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
         if (status && (*status & 1)) losses[7] = __int_as_float(0x7fc00000);  // pair list overflow: refuse a number
     }
     // Laplacian backward rows (L^T yhat) for vertices and albedo; normal backward + edge hinge over incident faces
-    float3 lv = make_float3(0.f, 0.f, 0.f), la = lv, gnb = lv, ge = lv, vi = lv;
+    float3 lv = make_float3(0.f, 0.f, 0.f), la = lv, gnb = lv, ge = lv;
     if (i < V) {
         const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
         for (int q = b + sub; q < e; q += kLPV) {
-            const int j = __ldg(v2v_idx + q);
-            const float invd = __ldg(inv_deg + j);
-            const float3 ya = ldf3(yhat_a + 3 * (size_t)j);
-            la.x += ya.x * invd; la.y += ya.y * invd; la.z += ya.z * invd;
-            if (cfg.phase == 1) {
-                const float3 yv = ldf3(yhat_v + 3 * (size_t)j);
-                lv.x += yv.x * invd; lv.y += yv.y * invd; lv.z += yv.z * invd;
-            }
+            const F8 y = ldg256(ys + 2 * (size_t)__ldg(v2v_idx + q));
+            la.x += y.b.x; la.y += y.b.y; la.z += y.b.z;
+            lv.x += y.a.x; lv.y += y.a.y; lv.z += y.a.z;
         }
         if (cfg.phase == 1) {
-            vi = ldf3(vertices + 3 * (size_t)i);
-            const float3 gi = ldf3(gN + 3 * (size_t)i);
+            const F8 self = ldg256(vg + 2 * (size_t)i);
+            const float3 vi = make_float3(self.a.x, self.a.y, self.a.z), gi = make_float3(self.b.x, self.b.y, self.b.z);
             const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
             for (int j = fb + sub; j < fe; j += kLPV) {
                 const int2 nb = __ldg(v2f_nbr + j);
-                const int ia = nb.x, ib = nb.y;
-                const float3 pa = ldf3(vertices + 3 * (size_t)ia), pb = ldf3(vertices + 3 * (size_t)ib);
-                const float3 ka = ldf3(gN + 3 * (size_t)ia), kb = ldf3(gN + 3 * (size_t)ib);
-                const float3 Gs = make_float3(gi.x + ka.x + kb.x, gi.y + ka.y + kb.y, gi.z + ka.z + kb.z);
-                const float3 ed = make_float3(pa.x - pb.x, pa.y - pb.y, pa.z - pb.z);
+                const F8 A = ldg256(vg + 2 * (size_t)nb.x), B = ldg256(vg + 2 * (size_t)nb.y);
+                const float3 Gs = make_float3(gi.x + A.b.x + B.b.x, gi.y + A.b.y + B.b.y, gi.z + A.b.z + B.b.z);
+                const float3 ed = make_float3(A.a.x - B.a.x, A.a.y - B.a.y, A.a.z - B.a.z);
                 gnb.x += ed.y * Gs.z - ed.z * Gs.y; gnb.y += ed.z * Gs.x - ed.x * Gs.z; gnb.z += ed.x * Gs.y - ed.y * Gs.x;
-                const float3 o[2] = {pa, pb};
+                const float4 o[2] = {A.a, B.a};
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     const float dx = vi.x - o[s].x, dy = vi.y - o[s].y, dz = vi.z - o[s].z;
@@ -1137,47 +1397,37 @@ __global__ void __launch_bounds__(256) ham_update_pass2_kernel(
             }
         }
     }
+    // butterfly sums: every lane of the vertex's group ends up with the totals
     la.x = sub_sum(la.x); la.y = sub_sum(la.y); la.z = sub_sum(la.z);
     if (cfg.phase == 1) {
         lv.x = sub_sum(lv.x); lv.y = sub_sum(lv.y); lv.z = sub_sum(lv.z);
         gnb.x = sub_sum(gnb.x); gnb.y = sub_sum(gnb.y); gnb.z = sub_sum(gnb.z);
         ge.x = sub_sum(ge.x); ge.y = sub_sum(ge.y); ge.z = sub_sum(ge.z);
     }
-    if (i >= V || sub != 0) return;
-    const float* Gi = packed + 12 * (size_t)i;
-    {
-        const float3 yv = ldf3(yhat_v + 3 * (size_t)i), ya = ldf3(yhat_a + 3 * (size_t)i);
-        const float iv = 1.0f / (float)V;
-        lv = make_float3((lv.x - yv.x) * iv, (lv.y - yv.y) * iv, (lv.z - yv.z) * iv);
-        la = make_float3((la.x - ya.x) * iv, (la.y - ya.y) * iv, (la.z - ya.z) * iv);
-    }
+    if (i >= V || sub >= 3) return;
+    // lane c of the vertex's group owns component c of delta and of albedo
+    const int c = sub;
+    const float iv = 1.0f / (float)V;
+    const F8 yself = ldg256(ys + 2 * (size_t)i);
+    const float deg = yself.a.w;  // yhat_i = (yhat_i / deg_i) * deg_i
+    const size_t k = 3 * (size_t)i + c;
     // albedo gradient (phase A: photometric only, mesh_sfs_optim.py:233; phase B adds the albedo Laplacian)
-    float3 ga = make_float3(s_photo * Gi[9], s_photo * Gi[10], s_photo * Gi[11]);
-    if (cfg.phase == 1) { ga.x += cfg.albedo_weight * la.x; ga.y += cfg.albedo_weight * la.y; ga.z += cfg.albedo_weight * la.z; }
-    float3 gd = make_float3(0.f, 0.f, 0.f);
+    float ga = s_photo * packed[8 * (size_t)i + 5 + c];
+    if (cfg.phase == 1)
+        ga += cfg.albedo_weight * ((pick3(la, c) - pick3(make_float3(yself.b.x, yself.b.y, yself.b.z), c) * deg) * iv);
+    float gd = 0.0f;
     if (cfg.phase == 1) {
         const float s_edge = cfg.edge_weight / (3.0f * (float)cfg.T);
         const float s_delta = 2.0f * cfg.delta_weight / (float)V;
-        const float3 di = ldf3(delta + 3 * (size_t)i);
-        gd.x = s_photo * (Gi[0] + gnb.x) + s_mask * Gi[3] + cfg.lap_weight * lv.x + s_edge * ge.x + s_delta * di.x;
-        gd.y = s_photo * (Gi[1] + gnb.y) + s_mask * Gi[4] + cfg.lap_weight * lv.y + s_edge * ge.y + s_delta * di.y;
-        gd.z = s_photo * (Gi[2] + gnb.z) + s_mask * Gi[5] + cfg.lap_weight * lv.z + s_edge * ge.z + s_delta * di.z;
+        const float lap = (pick3(lv, c) - pick3(make_float3(yself.a.x, yself.a.y, yself.a.z), c) * deg) * iv;
+        gd = s_photo * (packed[8 * (size_t)i + c] + pick3(gnb, c)) + s_mask * packed[8 * (size_t)V + 4 * (size_t)i + c] +
+             cfg.lap_weight * lap + s_edge * pick3(ge, c) + s_delta * delta[k];
     }
-    if (dbg_grad) {
-        dbg_grad[6 * (size_t)i] = gd.x; dbg_grad[6 * (size_t)i + 1] = gd.y; dbg_grad[6 * (size_t)i + 2] = gd.z;
-        dbg_grad[6 * (size_t)i + 3] = ga.x; dbg_grad[6 * (size_t)i + 4] = ga.y; dbg_grad[6 * (size_t)i + 5] = ga.z;
-    }
-    const float gds[3] = {gd.x, gd.y, gd.z}, gas[3] = {ga.x, ga.y, ga.z};
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const size_t k = 3 * (size_t)i + c;
-        if (cfg.phase == 1)
-            delta[k] = adam_update(delta[k], gds[c], adam_m + k, adam_v + k, cfg.beta1, cfg.beta2, cfg.eps, adam_sc[0],
-                                   adam_sc[1]);
-        const size_t ka = 3 * (size_t)V + k;
-        albedo[k] = adam_update(albedo[k], gas[c], adam_m + ka, adam_v + ka, cfg.beta1, cfg.beta2, cfg.eps, adam_sc[2],
-                                adam_sc[3]);
-    }
+    if (dbg_grad) { dbg_grad[6 * (size_t)i + c] = gd; dbg_grad[6 * (size_t)i + 3 + c] = ga; }
+    if (cfg.phase == 1)
+        delta[k] = adam_update(delta[k], gd, adam_m + k, adam_v + k, cfg.beta1, cfg.beta2, cfg.eps, adam_sc[0], adam_sc[1]);
+    const size_t ka = 3 * (size_t)V + k;
+    albedo[k] = adam_update(albedo[k], ga, adam_m + ka, adam_v + ka, cfg.beta1, cfg.beta2, cfg.eps, adam_sc[2], adam_sc[3]);
 }
 
 // phase A: Adam on sh_coeffs.  torch.optim.Adam steps the WHOLE [num,9] tensor every iteration (rows of views outside
@@ -1240,6 +1490,8 @@ static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers*
     FMHR_CHECK_ARG(b->vertices_tmp && b->delta && b->albedo && b->sh_coeffs && b->adam_m && b->adam_v && b->adam_step);
     FMHR_CHECK_ARG(b->imgs && b->masks && b->valid_masks && b->w2cs && b->projs && b->view_idx && b->view_vm2);
     FMHR_CHECK_ARG(b->packed && b->losses && b->workspace);
+    FMHR_CHECK_ARG(b->ml_vptr && b->ml_verts && b->ml_tri2 && b->n_meshlets > 0);
+    FMHR_CHECK_ARG((b->ml_tris == 256 || b->ml_tris == 512 || b->ml_tris == 1024) && b->ml_max_verts > 0 && b->ml_max_verts <= 1024);
     FMHR_CHECK_ARG(b->workspace_bytes >= fmhr_ham_workspace_bytes(cfg));
     FMHR_CHECK_ARG(((uintptr_t)b->packed & 15) == 0 && ((uintptr_t)b->workspace & 255) == 0);
     return FMHR_OK;
@@ -1262,48 +1514,67 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     // zeroed by the prep kernel: packed, loss accumulators + dilated work list (common), the work list of the slot
     // rasterised this step, SH gradients (phase A)
     const int n0 = (int)(ws.common_bytes / 4), n1 = (int)(ws.slot_bytes / 4), n2 = PHASE == 0 ? cfg->n_sh_rows * 9 : 0;
-    const int prep_threads = max(3 * V, max(n0, max(n1, n2)));
+    const int prep_threads = max(max(max(3 * V + 1, T), n * kViewM), max(n0, max(n1, n2)));
     ham_vertex_prep_kernel<<<cdiv(prep_threads, 256), 256, 0, st>>>(
-        b->vertices_tmp, b->delta, 3 * V, ws.vertices, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
-        (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2);
+        b->vertices_tmp, b->delta, V, ws.vg, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
+        (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->tri, b->opp, T, ws.tri4, ws.opp4,
+        b->w2cs, b->projs, b->view_idx, n, ws.viewM);
     FMHR_LAUNCH_CHECK();
-    int rc = launch_vertex_normals_fwd(ws.vertices, b->tri, b->v2f_ptr, b->v2f_idx, b->v2f_nbr, V, ws.normals, ws.raw, st);
-    if (rc) return rc;
+    ham_normals_kernel<<<cdiv((long long)V * 8, 256), 256, 0, st>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
+                                                                    ws.vattr, ws.raw4);
+    FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
-    ham_transform_kernel<<<dim3(cdiv(V, 256), cdiv(n, kViewsPerBlock)), 256, 0, st>>>(
-        ws.vertices, b->w2cs, b->projs, b->view_idx, n, V, H, W, ws.pos, ws.snap, ws.scr, ws.viewM);
-    FMHR_LAUNCH_CHECK();
-    FMHR_STAGE_MARK();  // 2: transform
-    rc = launch_raster_coverage_snapped(ws.pos, ws.snap, b->tri, n, V, T, H, W, zcur, ws.tbits[cur], ws.tlist[cur],
-                                        ws.tcount[cur], tiles_x, tiles_x * tiles_y, st);
-    if (rc) return rc;
-    FMHR_STAGE_MARK();  // 3: coverage
+    FMHR_STAGE_MARK();  // 2: (the clip transform is fused into the coverage kernel)
+    {
+        const int tiles_pv = tiles_x * tiles_y;
+        const size_t smem = (size_t)b->ml_max_verts * 24 + (size_t)((tiles_pv + 31) / 32) * sizeof(unsigned int);
+        const dim3 grid(b->n_meshlets, n);
+        const uint2* tri2 = (const uint2*)b->ml_tri2;
+#define FMHR_COVERAGE(TPT)                                                                                             \
+        do {                                                                                                           \
+            static bool attr_set = false;                                                                              \
+            if (!attr_set) {                                                                                           \
+                FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT>,                                       \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));              \
+                attr_set = true;                                                                                       \
+            }                                                                                                          \
+            ham_coverage_meshlet_kernel<TPT><<<grid, 256, smem, st>>>(                                                 \
+                ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,               \
+                ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv);                                      \
+        } while (0)
+        if (b->ml_tris == 1024) FMHR_COVERAGE(4);
+        else if (b->ml_tris == 512) FMHR_COVERAGE(2);
+        else FMHR_COVERAGE(1);
+#undef FMHR_COVERAGE
+        FMHR_LAUNCH_CHECK();
+    }
+    FMHR_STAGE_MARK();  // 3: coverage (transform + visibility)
     static const int g_shade = persistent_blocks(ham_shade_kernel<PHASE>);
     static const int g_aa = persistent_blocks(ham_aa_loss_kernel<PHASE>);
     static const int g_bwd = persistent_blocks(ham_pixel_bwd_kernel<PHASE>);
     const int pblock = kTile * kTile;  // 8 warps = 8 independent strip workers
     ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt],
-                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.pos,
-                                                      ws.scr, invW, invH, b->tri, b->opp, ws.normals, b->albedo,
+                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.vg,
+                                                      ws.viewM, invW, invH, ws.tri4, ws.opp4, ws.vattr,
                                                       b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W,
                                                       ws.plane[0], ws.plane[1], ws.acc, ws.vlist, ws.vcount);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 4: shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.scr, b->tri, b->opp, b->imgs, b->valid_masks,
+    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.vg, ws.viewM, b->tri, b->opp, b->imgs, b->valid_masks,
                                                      b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
                                                      ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask,
                                                      ws.plist_a, ws.plist_b, ws.pcount, (int)(P / 2), ws.status);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
-        ham_pair_bwd_kernel<PHASE><<<64, 256, 0, st>>>(ws.plist_a, ws.plist_b, ws.pcount, (int)(P / 2), zcur, ws.pos,
+        ham_pair_bwd_kernel<PHASE><<<296, 128, 0, st>>>(ws.plist_a, ws.plist_b, ws.pcount, (int)(P / 2), zcur, ws.vg,
                                                        ws.viewM, V, H, W, ws.plane[0], g0, g1, ws.gdelta,
                                                        (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.vlist, ws.vcount, zcur, ws.pos, invW, invH, ws.viewM, b->tri,
-                                                              ws.normals, b->albedo, b->sh_coeffs, sh_idx, V, H, W, g0, g1,
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.vlist, ws.vcount, zcur, ws.vg, invW, invH, ws.viewM, ws.tri4,
+                                                              ws.vattr, b->sh_coeffs, sh_idx, V, H, W, g0, g1,
                                                               ws.gdelta, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
     }
@@ -1360,15 +1631,13 @@ extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_b
     HamWs ws;
     ham_layout(cfg, (char*)buf->workspace, &ws);
     const int V = cfg->V;
-    ham_update_pass1_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
-                                                          buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
-                                                          ws.raw, buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, ws.acc,
-                                                          buf->adam_step, ws.adam_sc);
+    ham_update_pass1_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
+        *cfg, ws.vg, buf->delta, ws.vattr, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx, ws.raw4,
+        (const float4*)buf->packed, ws.ys, ws.acc, buf->adam_step, ws.adam_sc);
     FMHR_LAUNCH_CHECK();
-    ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(*cfg, ws.vertices, buf->delta, buf->albedo, buf->tri,
-                                                          buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
-                                                          buf->inv_deg, buf->packed, ws.yhat_v, ws.yhat_a, ws.gN, buf->adam_m,
-                                                          buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status);
+    ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
+        *cfg, ws.vg, buf->delta, buf->albedo, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
+        buf->packed, ws.ys, buf->adam_m, buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)
     if (cfg->phase == 0) {
@@ -1417,12 +1686,14 @@ extern "C" int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_
     if (rc) return rc;
     HamWs ws;
     ham_layout(cfg, (char*)buf->workspace, &ws);
-    const size_t nV = (size_t)cfg->n_views * cfg->V;
-    if (pos) FMHR_CUDA(cudaMemcpyAsync(pos, ws.pos, nV * 16, cudaMemcpyDeviceToDevice, st));
-    if (normals) FMHR_CUDA(cudaMemcpyAsync(normals, ws.normals, (size_t)cfg->V * 12, cudaMemcpyDeviceToDevice, st));
+    if (pos) {
+        ham_export_pos_kernel<<<dim3(cdiv(cfg->V, 256), cfg->n_views), 256, 0, st>>>(ws.vg, ws.viewM, cfg->V, (float4*)pos);
+        FMHR_LAUNCH_CHECK();
+    }
+    if (normals) FMHR_CUDA(cudaMemcpy2DAsync(normals, 12, ws.vattr, 32, 12, (size_t)cfg->V, cudaMemcpyDeviceToDevice, st));
     if (rast) {
         const dim3 pgrid(cdiv((long long)cfg->H * cfg->W, 256), cfg->n_views);
-        ham_export_rast_kernel<<<pgrid, 256, 0, st>>>(ws.zbuf[cfg->zbuf_slot], ws.pos, buf->tri, cfg->V, cfg->H, cfg->W,
+        ham_export_rast_kernel<<<pgrid, 256, 0, st>>>(ws.zbuf[cfg->zbuf_slot], ws.vg, ws.viewM, buf->tri, cfg->V, cfg->H, cfg->W,
                                                       (float4*)rast);
         FMHR_LAUNCH_CHECK();
     }

@@ -36,6 +36,7 @@ class HamOptimizer:
         self.delta = torch.zeros_like(self.vertices_tmp)
         self.conf = dict(conf)
         self.topo = Topology(self.faces, self.V)
+        self._build_meshlets()
         # mesh_sfs_optim.py:184-188: mean of squared lengths of the 3F half-edges of the initial mesh
         v, f = self.vertices_tmp, self.faces.long()
         a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
@@ -66,6 +67,29 @@ class HamOptimizer:
         self._struct_cache = {}
         self._zb_layout = None
         self._zb_slot = 0
+
+    MESHLET_TRIS = 1024
+
+    def _build_meshlets(self):
+        """Setup: Morton-ordered meshlets for the coverage kernel (fmhr_meshlets_build_host, host-side, once per mesh)."""
+        import numpy as np
+        tri = np.ascontiguousarray(self.faces.cpu().numpy(), dtype=np.int32)
+        verts = np.ascontiguousarray(self.vertices_tmp.cpu().numpy(), dtype=np.float32)
+        hp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+        nm, nr, mv = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        call = lambda a, b, c: check(self.lib.fmhr_meshlets_build_host(
+            hp(tri), hp(verts), self.V, self.T, self.MESHLET_TRIS, ctypes.byref(nm), ctypes.byref(nr), ctypes.byref(mv),
+            hp(a), hp(b), hp(c)), "meshlets_build_host")
+        call(None, None, None)
+        vptr = np.zeros(nm.value + 1, dtype=np.int32)
+        vrefs = np.zeros(max(nr.value, 1), dtype=np.int32)
+        tri2 = np.zeros((nm.value * self.MESHLET_TRIS, 2), dtype=np.uint32)
+        call(vptr, vrefs, tri2)
+        dev = self.device
+        self.ml_vptr = torch.from_numpy(vptr).to(dev)
+        self.ml_verts = torch.from_numpy(vrefs).to(dev)
+        self.ml_tri2 = torch.from_numpy(tri2.view(np.int32)).to(dev)
+        self.n_meshlets, self.ml_max_verts = nm.value, mv.value
 
     # ------------------------------------------------------------------ reference-shaped accessors
     @property
@@ -111,6 +135,8 @@ class HamOptimizer:
         b.tri, b.opp = ptr(self.faces), ptr(t.opp)
         b.v2f_ptr, b.v2f_idx, b.v2v_ptr, b.v2v_idx = ptr(t.v2f_ptr), ptr(t.v2f_idx), ptr(t.v2v_ptr), ptr(t.v2v_idx)
         b.v2f_nbr, b.inv_deg = ptr(t.v2f_nbr), ptr(t.inv_deg)
+        b.ml_vptr, b.ml_verts, b.ml_tri2 = ptr(self.ml_vptr), ptr(self.ml_verts), ptr(self.ml_tri2)
+        b.n_meshlets, b.ml_tris, b.ml_max_verts = self.n_meshlets, self.MESHLET_TRIS, self.ml_max_verts
         b.vertices_tmp, b.delta, b.albedo, b.sh_coeffs = ptr(self.vertices_tmp), ptr(self.delta), ptr(self.albedo), ptr(self.sh_coeffs)
         b.adam_m, b.adam_v, b.adam_step = ptr(self.adam_m), ptr(self.adam_v), ptr(self.adam_step)
         b.imgs = ptr(self.imgs if imgs is None else imgs)

@@ -82,6 +82,15 @@ int fmhr_mesh_topology_build(const int32_t* tri, int V, int T, int32_t* opp, int
 int fmhr_mesh_topology_derive(const int32_t* tri, const int32_t* v2f_idx, const int32_t* v2v_ptr, int V, int T,
                               int32_t* v2f_nbr, float* inv_deg, fmhr_stream_t stream);
 
+/* Meshlets for the fused iteration's coverage kernel (setup, HOST pointers): faces are ordered along a Morton curve of
+ * their centroids (verts [V,3]; NULL keeps the input order) and cut into groups of at most tris_per_meshlet (multiple of
+ * 32, <= 1024) triangles and 1024 distinct vertices.  Call once with ml_vptr = ml_verts = ml_tri2 = NULL to obtain
+ * the counts, allocate ml_vptr [*n_meshlets+1], ml_verts [*n_vert_refs], ml_tri2 [*n_meshlets*tris_per_meshlet*2] and
+ * call again.  The z-buffer keeps ORIGINAL triangle ids, so results do not depend on the meshlet order. */
+int fmhr_meshlets_build_host(const int32_t* tri, const float* verts, int V, int T, int tris_per_meshlet,
+                             int* n_meshlets, int* n_vert_refs, int* max_verts, int32_t* ml_vptr, int32_t* ml_verts,
+                             uint32_t* ml_tri2);
+
 /* ---------------------------------------------------------------------------------------------
  * dr.antialias(color, rast, pos, tri)                [mesh_sfs_optim.py:146-147,217-219,274,287]
  *   color [N,H,W,C], rast [N,H,W,4], pos [N,V,4], tri [T,3], opp [T,3] from fmhr_mesh_topology_build
@@ -180,6 +189,14 @@ typedef struct fmhr_ham_buffers {
     /* optional inspection outputs for parity tests (NULL in production): the gradients Adam consumed */
     float* dbg_grad;           /* [V,6] = (d loss/d delta xyz, d loss/d albedo bgr) */
     float* dbg_grad_sh;        /* [n_sh_rows,9] (phase A) */
+    /* meshlets of the coverage kernel (static, from fmhr_meshlets_build_host, uploaded to the device) */
+    const int32_t* ml_vptr;    /* [n_meshlets+1] */
+    const int32_t* ml_verts;   /* [ml_vptr[n_meshlets]] global vertex id of each meshlet-local vertex */
+    const uint32_t* ml_tri2;   /* [n_meshlets*ml_tris,2] (l0 | l1<<10 | l2<<20, original triangle id); padding = ~0 */
+    int32_t n_meshlets;
+    int32_t ml_tris;           /* triangles per meshlet (multiple of 256, <= 1024) */
+    int32_t ml_max_verts;      /* largest meshlet vertex count (<= 1024) */
+    int32_t ml_reserved;
 } fmhr_ham_buffers;
 
 size_t fmhr_ham_workspace_bytes(const fmhr_ham_config* cfg);

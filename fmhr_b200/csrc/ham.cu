@@ -25,29 +25,26 @@ struct HamWs {
     unsigned long long* zbuf[2];  // [n,H,W] x2: `zbuf_slot` is rasterised this step, the other is reset for the next
     float4* plane[4];          // [n,H,W] each
     float* viewM;              // [n,16] combined world->clip matrix per view
-    // Compact work lists of the backward pass (built by the forward passes of the same iteration):
-    uint32_t* vlist;           // [P]   pixels that feed the backward shader (phase B: valid, phase A: covered), by shade
+    // Compact work lists (rebuilt every iteration):
+    uint2* clist;              // [P]   covered pixels (pixel index, triangle | valid << 31), by the scan / shade passes
+    uint32_t* rlist;           // [P/2] empty pixels touching a covered one (antialias receivers), by the scan pass
+    uint32_t* ringbits;        // [P/32] de-duplication bitmap of rlist; zero outside an iteration
     uint4* plist_a;            // [P/2] blending pixel pairs found by the antialias pass: (pixel0, flags, alpha, i1)
     uint32_t* plist_b;         // [P/2]                                                    i2
     float4* gdelta;            // [P]   pair terms of d(loss)/d(pre-antialias value); zero outside an iteration
-    int* vcount;               // inside common_region (zeroed every step)
+    int* ccount;               // inside common_region (zeroed every step)
+    int* rcount;
     int* pcount;
-    int* status;               // bit 0: pair list overflow
-    int* cursors;              // [8] work cursors of the persistent kernels (inside common_region)
-    // Active-tile work lists (16x16 tiles).  slot[s]: tiles of z-buffer slot s that received fragments (bitmap for
-    // de-duplication + compact list + count, filled by the coverage kernel); act: those tiles dilated by their four
-    // edge neighbours (antialias pairs straddle tile edges), filled by the shade pass.  The pixel passes are persistent
-    // kernels that walk these lists, so idle tiles cost nothing (launching a block per tile spent ~80 us per pass on
-    // ~25k blocks whose only instruction was a flag load).
+    int* status;               // bit 0: pair list overflow, bit 1: ring list overflow
+    // Tile work lists (16x16 tiles).  slot[s]: tiles of z-buffer slot s that received fragments (bitmap for
+    // de-duplication + compact list + count, filled by the coverage kernel).  The scan pass walks the list of the slot
+    // rasterised this step (idle tiles cost nothing) and resets the tiles of the other slot.
     char* slot_region[2];        // [count (256 B) | bitmap] zeroed together when the slot is reused
     int* tcount[2];
     uint32_t* tbits[2];          // [n, words_per_view]
     uint32_t* tlist[2];          // [n * tiles_per_view]
-    char* common_region;         // [acc | acount | abits] zeroed every step
+    char* common_region;         // [acc | counters] zeroed every step
     size_t common_bytes, slot_bytes;
-    int* acount;
-    uint32_t* abits;
-    uint32_t* alist;
     // Vertex-domain records (every gather of the pixel / update kernels is a 128- or 256-bit load of one 32-byte sector):
     float4* vg;                // [V,2]  vg[2i] = (x, y, z, 0) current vertex,   vg[2i+1] = d(loss)/d(raw normal) (update pass 1)
     float4* vattr;             // [V,2]  vattr[2i] = (unit normal, degenerate flag), vattr[2i+1] = (albedo b,g,r, 0)
@@ -86,7 +83,9 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
         if (ws) ws->plane[i] = (float4*)p;
     }
     p = take((size_t)c->n_views * kViewM * 4); if (ws) ws->viewM = (float*)p;
-    p = take(P * 4); if (ws) ws->vlist = (uint32_t*)p;
+    p = take(P * 8); if (ws) ws->clist = (uint2*)p;
+    p = take((P / 2 + 64) * 4); if (ws) ws->rlist = (uint32_t*)p;
+    p = take((P / 32 + 64) * 4); if (ws) ws->ringbits = (uint32_t*)p;
     p = take((P / 2 + 64) * 16); if (ws) ws->plist_a = (uint4*)p;
     p = take((P / 2 + 64) * 4); if (ws) ws->plist_b = (uint32_t*)p;
     p = take(P * 16); if (ws) ws->gdelta = (float4*)p;
@@ -98,15 +97,13 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
         if (ws) { ws->slot_region[i] = p; ws->tcount[i] = (int*)p; ws->tbits[i] = (uint32_t*)(p + 256); }
         p = take((size_t)c->n_views * tiles_pv * 4); if (ws) ws->tlist[i] = (uint32_t*)p;
     }
-    p = take((size_t)c->n_views * tiles_pv * 4); if (ws) ws->alist = (uint32_t*)p;
-    const size_t common_bytes = 8 * 32 * sizeof(double) + 256 + align256(words * 4);
+    const size_t common_bytes = 8 * 32 * sizeof(double) + 256;
     p = take(common_bytes);
     if (ws) {
         ws->common_region = p; ws->common_bytes = common_bytes; ws->slot_bytes = slot_bytes;
-        ws->acc = (double*)p; ws->acount = (int*)(p + 8 * 32 * sizeof(double));
-        ws->cursors = ws->acount + 8;  // same zeroed 256-byte slot
-        ws->vcount = ws->acount + 16; ws->pcount = ws->acount + 17; ws->status = ws->acount + 18;
-        ws->abits = (uint32_t*)(p + 8 * 32 * sizeof(double) + 256);
+        ws->acc = (double*)p;
+        int* cnt = (int*)(p + 8 * 32 * sizeof(double));
+        ws->ccount = cnt; ws->rcount = cnt + 1; ws->pcount = cnt + 2; ws->status = cnt + 3;
     }
     p = take(V * 32); if (ws) ws->vg = (float4*)p;
     p = take(V * 32); if (ws) ws->vattr = (float4*)p;
@@ -237,28 +234,31 @@ __device__ __forceinline__ float4 clip_from_world(const float* M, const float4 v
 //  1. the meshlet's <= 1024 vertices are gathered (16 B each, from the 1.6 MB vertex record array), transformed to clip
 //     space and snapped to the rasteriser's 24.8 grid into SHARED memory - once per (view, meshlet vertex) instead of a
 //     [n,V] array in HBM written by a transform kernel and gathered three times per triangle;
-//  2. every thread tests kTPT triangles against integer bounding boxes / edge functions on the shared snapped
-//     coordinates; hits go to a per-warp fragment queue;
-//  3. the queue is resolved densely (perspective barycentric depth from the shared clip positions, 64-bit atomicMin on
-//     depth | ORIGINAL triangle id), touched 16x16 tiles are collected in a shared bitmap and appended to the slot's
-//     global work list at block end.
+//  2. every thread tests TPT triangles against their integer pixel-centre bounding box on the shared snapped coordinates
+//     (micropolygons: ~60 % contain no pixel centre); the survivors are compacted per warp;
+//  3. the survivors are processed with all lanes busy: integer edge functions; covered pixel centres go to a per-warp
+//     queue and are then depth-resolved densely (perspective barycentric depth from the shared clip positions, 64-bit
+//     atomicMin on depth | ORIGINAL triangle id); touched 16x16 tiles are collected in a shared bitmap and appended to
+//     the slot's global work list at block end.
 // Rule and arithmetic are those of raster.cu and of the CPU checker (bit-exact ids and depth).
 // ------------------------------------------------------------------------------------------------
-constexpr int kFragQueue = 160;  // per-warp capacity; overflowing fragments (large triangles) are resolved in place
-
 template <typename I>
 __device__ __forceinline__ bool ml_owns_edge(I dx, I dy) { return dy > 0 || (dy == 0 && dx > 0); }
 
-__device__ __forceinline__ void ml_resolve(const float4* pos_s, uint32_t packed, uint32_t tid_orig, int px, int py, int W,
-                                           float invW, float invH, unsigned long long* __restrict__ zb) {
-    const float4 p0 = pos_s[packed & 1023u], p1 = pos_s[(packed >> 10) & 1023u], p2 = pos_s[(packed >> 20) & 1023u];
+// Coverage of one candidate triangle (its bounding box holds at least one pixel centre): integer edge functions on the
+// snapped corners, every covered pixel is depth-resolved in place from the shared clip positions.
+constexpr int kFragQueue = 160;  // per-warp capacity; overflowing fragments (large triangles) are resolved in place
+
+__device__ __forceinline__ void ml_resolve(const float4* pos_s, uint2 rec, int px, int py, int W, float invW, float invH,
+                                           unsigned long long* __restrict__ zb) {
+    const float4 p0 = pos_s[rec.x & 1023u], p1 = pos_s[(rec.x >> 10) & 1023u], p2 = pos_s[(rec.x >> 20) & 1023u];
     const Bary b = bary_at(p0, p1, p2, px, py, invW, invH);
-    atomicMin(&zb[(size_t)py * W + px], ((unsigned long long)depth_key(b.zw) << 32) | tid_orig);
+    atomicMin(&zb[(size_t)py * W + px], ((unsigned long long)depth_key(b.zw) << 32) | rec.y);
 }
 
 template <typename I>
 __device__ __forceinline__ void ml_cover(int X0, int Y0, int X1, int Y1, int X2, int Y2, int px0, int px1, int py0, int py1,
-                                         const float4* pos_s, uint2 rec, uint32_t slot, int W, float invW, float invH,
+                                         const float4* pos_s, uint2 rec, int e, int W, float invW, float invH,
                                          unsigned long long* __restrict__ zb, unsigned int* tbits, int tiles_x,
                                          int* qcount, uint2* queue) {
     const I dx0 = X2 - X1, dy0 = Y2 - Y1;
@@ -276,9 +276,10 @@ __device__ __forceinline__ void ml_cover(int X0, int Y0, int X1, int Y1, int X2,
             if (e0 + b0 > 0 && e1 + b1 > 0 && e2 + b2 > 0) {
                 const int tile = (py >> 4) * tiles_x + (px >> 4);
                 atomicOr(tbits + (tile >> 5), 1u << (tile & 31));
+                // the ~150-instruction depth resolve runs afterwards with the hits spread over all lanes
                 const int q = atomicAdd(qcount, 1);
-                if (q < kFragQueue) queue[q] = make_uint2(slot, ((uint32_t)py << 16) | (uint32_t)px);
-                else ml_resolve(pos_s, rec.x, rec.y, px, py, W, invW, invH, zb);
+                if (q < kFragQueue) queue[q] = make_uint2((uint32_t)e, ((uint32_t)py << 16) | (uint32_t)px);
+                else ml_resolve(pos_s, rec, px, py, W, invW, invH, zb);
             }
             e0 -= dy0 * 256;
             e1 -= dy1 * 256;
@@ -287,22 +288,29 @@ __device__ __forceinline__ void ml_cover(int X0, int Y0, int X1, int Y1, int X2,
     }
 }
 
-__device__ __forceinline__ void ml_test(uint2 rec, uint32_t slot, const float4* pos_s, const int2* snap_s, int H, int W,
-                                        float invW, float invH, unsigned long long* __restrict__ zb, unsigned int* tbits,
-                                        int tiles_x, int* qcount, uint2* queue) {
-    if (rec.x == 0xffffffffu) return;  // padding
-    const int2 s0 = snap_s[rec.x & 1023u], s1 = snap_s[(rec.x >> 10) & 1023u], s2 = snap_s[(rec.x >> 20) & 1023u];
-    if (s0.x == kSnapRejected || s1.x == kSnapRejected || s2.x == kSnapRejected) return;
-    int X0 = s0.x, Y0 = s0.y, X1 = s1.x, Y1 = s1.y, X2 = s2.x, Y2 = s2.y;
-    const int minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
-    const int minY = min(Y0, min(Y1, Y2)), maxY = max(Y0, max(Y1, Y2));
+// Pixel-centre bounding box of a triangle from its snapped corners; false when a corner was rejected or no pixel centre
+// lies inside (the common case for micropolygons).
+struct MlBox { int px0, px1, py0, py1; bool small; };
+__device__ __forceinline__ bool ml_bbox(const int2 s0, const int2 s1, const int2 s2, int H, int W, MlBox& bx) {
+    if (s0.x == kSnapRejected || s1.x == kSnapRejected || s2.x == kSnapRejected) return false;
+    const int minX = min(s0.x, min(s1.x, s2.x)), maxX = max(s0.x, max(s1.x, s2.x));
+    const int minY = min(s0.y, min(s1.y, s2.y)), maxY = max(s0.y, max(s1.y, s2.y));
     // pixel centres (px*256+128) inside [min,max]
-    const int px0 = max(0, (minX - 128 + 255) >> 8), px1 = min(W - 1, (maxX - 128) >> 8);
-    const int py0 = max(0, (minY - 128 + 255) >> 8), py1 = min(H - 1, (maxY - 128) >> 8);
-    if (px0 > px1 || py0 > py1) return;  // no pixel centre in the bounding box: the common case
-    const bool small = (maxX - minX) < 32768 && (maxY - minY) < 32768 && px1 < 65536 && py1 < 65536;
+    bx.px0 = max(0, (minX - 128 + 255) >> 8); bx.px1 = min(W - 1, (maxX - 128) >> 8);
+    bx.py0 = max(0, (minY - 128 + 255) >> 8); bx.py1 = min(H - 1, (maxY - 128) >> 8);
+    bx.small = (maxX - minX) < 32768 && (maxY - minY) < 32768 && bx.px1 < 65536 && bx.py1 < 65536;
+    return bx.px0 <= bx.px1 && bx.py0 <= bx.py1;
+}
+
+__device__ __forceinline__ void ml_candidate(uint2 rec, int e, const float4* pos_s, const int2* snap_s, int H, int W,
+                                             float invW, float invH, unsigned long long* __restrict__ zb,
+                                             unsigned int* tbits, int tiles_x, int* qcount, uint2* queue) {
+    const int2 s0 = snap_s[rec.x & 1023u], s1 = snap_s[(rec.x >> 10) & 1023u], s2 = snap_s[(rec.x >> 20) & 1023u];
+    MlBox bx;
+    if (!ml_bbox(s0, s1, s2, H, W, bx)) return;
+    int X0 = s0.x, Y0 = s0.y, X1 = s1.x, Y1 = s1.y, X2 = s2.x, Y2 = s2.y;
     bool neg;
-    if (small) {
+    if (bx.small) {
         const int a = (X1 - X0) * (Y2 - Y0) - (X2 - X0) * (Y1 - Y0);  // |factors| < 2^15: exact in 32 bits
         if (a == 0) return;
         neg = a < 0;
@@ -315,8 +323,8 @@ __device__ __forceinline__ void ml_test(uint2 rec, uint32_t slot, const float4* 
         int tx = X1; X1 = X2; X2 = tx;
         int ty = Y1; Y1 = Y2; Y2 = ty;
     }
-    if (small) ml_cover<int>(X0, Y0, X1, Y1, X2, Y2, px0, px1, py0, py1, pos_s, rec, slot, W, invW, invH, zb, tbits, tiles_x, qcount, queue);
-    else ml_cover<long long>(X0, Y0, X1, Y1, X2, Y2, px0, px1, py0, py1, pos_s, rec, slot, W, invW, invH, zb, tbits, tiles_x, qcount, queue);
+    if (bx.small) ml_cover<int>(X0, Y0, X1, Y1, X2, Y2, bx.px0, bx.px1, bx.py0, bx.py1, pos_s, rec, e, W, invW, invH, zb, tbits, tiles_x, qcount, queue);
+    else ml_cover<long long>(X0, Y0, X1, Y1, X2, Y2, bx.px0, bx.px1, bx.py0, bx.py1, pos_s, rec, e, W, invW, invH, zb, tbits, tiles_x, qcount, queue);
 }
 
 template <int TPT>
@@ -329,7 +337,8 @@ __global__ void __launch_bounds__(256, 4) ham_coverage_meshlet_kernel(
     float4* pos_s = reinterpret_cast<float4*>(dyn_smem);
     int2* snap_s = reinterpret_cast<int2*>(pos_s + max_verts);
     unsigned int* tbits = reinterpret_cast<unsigned int*>(snap_s + max_verts);  // (tiles_per_view + 31) / 32 words
-    __shared__ uint2 queue[8][kFragQueue];
+    __shared__ uint2 cand[8][TPT * 32];  // per warp: the triangles whose bounding box holds a pixel centre
+    __shared__ uint2 queue[8][kFragQueue];  // per warp: covered pixel centres (candidate index, py << 16 | px)
     __shared__ int qcount[8];
     __shared__ float Ms[kViewM];
     const int m = blockIdx.x, n = blockIdx.y;
@@ -355,17 +364,30 @@ __global__ void __launch_bounds__(256, 4) ham_coverage_meshlet_kernel(
         snap_s[i] = make_int2(X, Y);
     }
     __syncthreads();
-    unsigned long long* zb = zbuf + (size_t)n * H * W;
+    // stage A: cheap bounding-box test of every triangle (all lanes busy), survivors compacted per warp
+    int nc = 0;  // warp-uniform
 #pragma unroll
-    for (int k = 0; k < TPT; k++)
-        ml_test(rec[k], (uint32_t)(k * 256 + threadIdx.x), pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x,
-                &qcount[warp], queue[warp]);
+    for (int k = 0; k < TPT; k++) {
+        bool pass = false;
+        if (rec[k].x != 0xffffffffu) {  // padding
+            MlBox bx;
+            pass = ml_bbox(snap_s[rec[k].x & 1023u], snap_s[(rec[k].x >> 10) & 1023u], snap_s[(rec[k].x >> 20) & 1023u], H, W, bx);
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, pass);
+        if (pass) cand[warp][nc + __popc(mk & ((1u << lane) - 1u))] = rec[k];
+        nc += __popc(mk);
+    }
     __syncwarp();
+    // stage B: edge functions of the survivors, spread densely over the lanes; hits go to the fragment queue
+    unsigned long long* zb = zbuf + (size_t)n * H * W;
+    for (int e = lane; e < nc; e += 32)
+        ml_candidate(cand[warp][e], e, pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x, &qcount[warp], queue[warp]);
+    __syncwarp();
+    // stage C: depth resolve of the hits, again with all lanes busy
     const int nq = min(qcount[warp], kFragQueue);
-    for (int e = lane; e < nq; e += 32) {
-        const uint2 f = queue[warp][e];
-        const uint2 r = __ldg(recs + f.x);
-        ml_resolve(pos_s, r.x, r.y, (int)(f.y & 0xffffu), (int)(f.y >> 16), W, invW, invH, zb);
+    for (int f = lane; f < nq; f += 32) {
+        const uint2 fr = queue[warp][f];
+        ml_resolve(pos_s, cand[warp][fr.x], (int)(fr.y & 0xffffu), (int)(fr.y >> 16), W, invW, invH, zb);
     }
     __syncthreads();
     // flush: tiles this block touched first (global bitmap de-duplicates) are appended to the slot's work list
@@ -462,9 +484,9 @@ __device__ __forceinline__ float sh_radiance(const float* c, float x, float y, f
     return r;
 }
 
-// pixel kernels run 16x16 tiles: 2-D locality keeps the hand's pixels in few, densely active blocks
+// The scan pass walks 16x16 tiles (2-D locality keeps the hand's pixels in few, densely populated tiles); every later
+// pixel pass walks the compact pixel lists the scan pass builds.
 constexpr int kTile = 16;
-__device__ __forceinline__ int tile_tid() { return threadIdx.y * kTile + threadIdx.x; }
 
 // clip-space gradient (x, y, -, w) -> world-space xyz
 __device__ __forceinline__ float3 clip_to_world(const float* M, float gx, float gy, float gw) {
@@ -472,84 +494,60 @@ __device__ __forceinline__ float3 clip_to_world(const float* M, float gx, float 
                        M[8] * gx + M[9] * gy + M[11] * gw);
 }
 
-__device__ __forceinline__ float block_sum_256(float v, float* sm) {
-    const int tid = tile_tid();
-    v = warp_sum(v);
-    if ((tid & 31) == 0) sm[tid >> 5] = v;
-    __syncthreads();
-    float r = 0.0f;
-    if (tid < 8) r = sm[tid];
-    if (tid < 32) {
-        r += __shfl_xor_sync(0xffffffffu, r, 4);
-        r += __shfl_xor_sync(0xffffffffu, r, 2);
-        r += __shfl_xor_sync(0xffffffffu, r, 1);
-    }
-    __syncthreads();
-    return r;  // valid in thread 0
-}
-
 // One 16x16 tile of one view, as handed out by the work lists.
 struct TileCtx {
     int n, bx, by, nx, ny;  // view slot, tile coordinates, tiles per row / column
 };
-__device__ __forceinline__ uint32_t tile_encode(int n, int bx, int by) { return ((uint32_t)n << 20) | ((uint32_t)by << 10) | (uint32_t)bx; }
 __device__ __forceinline__ TileCtx tile_decode(uint32_t e, int nx, int ny) {
     TileCtx tc;
     tc.n = (int)(e >> 20); tc.by = (int)((e >> 10) & 1023u); tc.bx = (int)(e & 1023u); tc.nx = nx; tc.ny = ny;
     return tc;
 }
 
-// Unit of work of the persistent pixel kernels: one warp = one 16x2 strip of a 16x16 tile; warps are independent
-// workers (no block barrier anywhere in the pixel passes).
+// Unit of work of the scan pass: one warp = one 16x2 strip of a 16x16 tile; warps are independent workers (no block
+// barrier anywhere in the pixel passes).
 struct Strip {
     TileCtx tc;
-    int lane, wib;   // lane in warp, warp in block
-    int lx, ly;      // pixel position inside the tile
-    int tid;         // ly * 16 + lx = strip * 32 + lane
     int px, py;      // pixel position in the image
 };
 __device__ __forceinline__ bool next_strip(int& u, const uint32_t* __restrict__ list, int n_tiles, int tiles_x,
                                            int tiles_y, Strip& st) {
-    // static striding at strip granularity: unit u, u + (grid warps), ...  (a single global cursor serialises ~10^5
-    // same-address atomics per pass; strips of one tile still land on the 8 warps of one block -> shared L1 lines)
+    // static striding at strip granularity: unit u, u + (grid warps), ...
     if (u >= n_tiles * 8) return false;
     const int lane = threadIdx.x & 31;
     st.tc = tile_decode(__ldg(list + (u >> 3)), tiles_x, tiles_y);
     const int strip = u & 7;
-    st.lane = lane; st.wib = threadIdx.x >> 5;
-    st.lx = lane & 15; st.ly = 2 * strip + (lane >> 4);
-    st.tid = strip * 32 + lane;
-    st.px = st.tc.bx * kTile + st.lx; st.py = st.tc.by * kTile + st.ly;
+    st.px = st.tc.bx * kTile + (lane & 15); st.py = st.tc.by * kTile + 2 * strip + (lane >> 4);
     u += gridDim.x * 8;
     return true;
 }
 
-// 32-way spread accumulators
-__device__ __forceinline__ void acc_add(double* acc, int k, float v, const TileCtx& tc) {
-    if (v != 0.0f) atomicAdd(acc + k * 32 + ((tc.bx + tc.by * 7 + tc.n * 13) & 31), (double)v);
-}
-// barrier-free variant: shuffle-reduce inside the warp, one spread fp64 atomic per warp
-__device__ __forceinline__ void warp_acc_add(double* acc, int k, float v, const Strip& st) {
+// 32-way spread fp64 accumulators: shuffle-reduce inside the warp, one spread atomic per warp
+__device__ __forceinline__ void warp_acc_add(double* acc, int k, float v) {
     v = warp_sum(v);
-    if (st.lane == 0 && v != 0.0f)
-        atomicAdd(acc + k * 32 + ((st.tc.bx + st.tc.by * 7 + st.tc.n * 13 + (st.tid >> 5)) & 31), (double)v);
+    if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(acc + k * 32 + ((blockIdx.x * 8 + (threadIdx.x >> 5)) & 31), (double)v);
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 __device__ __forceinline__ double acc_total(const double* acc, int k) {
     double s = 0.0;
     for (int j = 0; j < 32; j++) s += acc[k * 32 + j];
     return s;
 }
-__device__ __forceinline__ int tile_index(const TileCtx& tc) { return tc.by * tc.nx + tc.bx; }
-// Appends this tile and its four edge neighbours to the dilated work list (bitmap de-duplicates).
-__device__ __forceinline__ void tile_mark_active(const TileCtx& tc, int tid, uint32_t* __restrict__ abits,
-                                                 uint32_t* __restrict__ alist, int* __restrict__ acount) {
-    int bx = tc.bx, by = tc.by;
-    if (tid == 1) bx -= 1; else if (tid == 2) bx += 1; else if (tid == 3) by -= 1; else if (tid == 4) by += 1;
-    if (tid > 4 || bx < 0 || by < 0 || bx >= tc.nx || by >= tc.ny) return;
-    const int tile = by * tc.nx + bx, words_pv = (tc.nx * tc.ny + 31) >> 5;
-    const uint32_t bit = 1u << (tile & 31);
-    const uint32_t old = atomicOr(abits + (size_t)tc.n * words_pv + (tile >> 5), bit);
-    if (!(old & bit)) alist[atomicAdd(acount, 1)] = tile_encode(tc.n, bx, by);
+
+// global pixel index -> view slot, coordinates
+struct PixAddr { int n, px, py, rem; };
+__device__ __forceinline__ PixAddr pix_decode(uint32_t pix, int H, int W) {
+    PixAddr a;
+    const uint32_t hw = (uint32_t)(H * W);
+    a.n = (int)(pix / hw);
+    a.rem = (int)(pix - (uint32_t)a.n * hw);
+    a.py = a.rem / W;
+    a.px = a.rem - a.py * W;
+    return a;
 }
 
 // Per-vertex accumulator layout in `packed` (12V floats, viewed as 3V float4):
@@ -585,376 +583,354 @@ __device__ __forceinline__ NbrKeys decode_key(unsigned long long key) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pair work queue (per warp).  A warp owns a 16x2 strip of its block's tile and is responsible for every horizontally /
-// vertically adjacent pixel pair with at least one pixel in the strip: the two pairs each of its pixels starts (right,
-// down) plus the pairs entering through the strip's top row and the tile's left column.  Pairs that can blend
-// (different triangle ids and silhouette bits set on the chosen triangle) are rare (~1 % of pixels), so instead of
-// running the ~400-instruction edge analysis under a 3-lane mask inside the per-pixel code they are queued in shared
-// memory and analysed afterwards with the queue spread over the lanes.  Everything is warp-synchronous: the pixel passes
-// have NO block-level barrier, so the 32+ resident warps of an SM hide each other's gather latency.
-//   item = (tid << 2) | which,  which: 0 (self,right)  1 (self,down)  2 (left,self)  3 (up,self)
+// scan: z-buffer tiles -> compact pixel lists.  Persistent over the tile list of the slot the coverage kernel just
+// filled; each warp walks 16x2 strips with coalesced key loads and
+//   * appends every covered pixel as (pixel index, triangle id) to `clist` (per-warp shared buffer, one global atomic per
+//     ~200 pixels): the shade / antialias / backward passes then run with every lane busy and perfectly balanced;
+//   * appends every EMPTY pixel that touches a covered one to `rlist` (the only empty pixels antialiasing can blend
+//     into; a self-cleaning bitmap de-duplicates);
+//   * resets the tiles the OTHER z-buffer slot dirtied in the previous iteration (no separate clear pass).
 // ------------------------------------------------------------------------------------------------
-constexpr int kPairQueue = 96;  // 2*32 own pairs + 16 top-row pairs + 2 left-column pairs
-
-__device__ __forceinline__ bool pair_needs_analysis(const NbrKeys& k0, const NbrKeys& k1) {
-    if (k0.tri == k1.tri) return false;
-    // same triangle choice as aa_analyse; the chosen pixel's silhouette bits come from the identical aa_triangle_geom
-    // call in the shade pass, so skipping bits == 0 is exact
-    const bool from1 = (k0.tri >= 0 && k1.tri >= 0) ? !(k0.zw < k1.zw) : (k0.tri < 0);
-    return (from1 ? k1.bits : k0.bits) != 0;
-}
-
-__device__ __forceinline__ void enqueue_pairs(const unsigned long long* __restrict__ zb, const Strip& st, int H, int W,
-                                              const NbrKeys& self, uint32_t* q_items, int* q_n) {
-    const int px = st.px, py = st.py, tid = st.tid;
-    if (px >= W || py >= H) return;
-    const int rem = py * W + px;
-    if (px + 1 < W) {
-        const NbrKeys o = decode_key(zb[rem + 1]);
-        if (pair_needs_analysis(self, o)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 0u;
-    }
-    if (py + 1 < H) {
-        const NbrKeys o = decode_key(zb[rem + W]);
-        if (pair_needs_analysis(self, o)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 1u;
-    }
-    if (st.lx == 0 && px > 0) {
-        const NbrKeys o = decode_key(zb[rem - 1]);
-        if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 2u;
-    }
-    if ((st.ly & 1) == 0 && py > 0) {  // top row of this warp's strip
-        const NbrKeys o = decode_key(zb[rem - W]);
-        if (pair_needs_analysis(o, self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)tid << 2) | 3u;
-    }
-}
-
-struct PairItem {
-    int qx, qy, d;        // first pixel of the pair and direction
-    int tid0, tid1;       // in-tile thread index of the first / second pixel, -1 when outside this warp's strip
-};
-__device__ __forceinline__ PairItem decode_pair_item(uint32_t item, const TileCtx& tc) {
-    const int tid = (int)(item >> 2), which = (int)(item & 3u);
-    const int lx = tid & (kTile - 1), ly = tid >> 4;
-    const int px = tc.bx * kTile + lx, py = tc.by * kTile + ly;
-    PairItem it;
-    it.d = which & 1;
-    if (which < 2) {
-        it.qx = px; it.qy = py; it.tid0 = tid;
-        const int ox = lx + (1 - it.d), oy = ly + it.d;
-        it.tid1 = (ox < kTile && (oy >> 1) == (ly >> 1)) ? oy * kTile + ox : -1;  // same 16x2 strip only
-    } else {
-        it.qx = px - (1 - it.d); it.qy = py - it.d; it.tid0 = -1; it.tid1 = tid;
-    }
-    return it;
-}
-
-// shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A); also tags the key with
-// the silhouette bits / valid flag and resets the OTHER z-buffer slot for the next iteration (no separate clear pass).
-template <int PHASE>
-__device__ __forceinline__ void shade_tile(const Strip& st, unsigned long long* __restrict__ zbuf,
-                                           const float4* __restrict__ vg, const float* __restrict__ viewM, float invW,
-                                           float invH, const int4* __restrict__ tri4, const int4* __restrict__ opp4,
-                                           const float4* __restrict__ vattr,
-                                           const float* __restrict__ masks,
-                                           const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx,
-                                           const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
-                                           float4* __restrict__ plane0, float4* __restrict__ plane1,
-                                           double* __restrict__ acc, bool& feeds_backward, uint32_t& pix32) {
-    const TileCtx& tc = st.tc;
-    feeds_backward = false;
-    pix32 = 0u;
-    const int n = tc.n;
-    const int view = __ldg(view_idx + n);
-    const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;  // block-uniform address: L1 broadcast
-    const int hw = H * W;
-    const int px = st.px, py = st.py;
-    float nvalid = 0.0f;
-    if (px < W && py < H) {
-        const int rem = py * W + px;
-        const size_t pix = (size_t)n * hw + rem;
-        const unsigned long long key = zbuf[pix];
-        if (key != ZB_EMPTY) {
-            const int t = (int)((uint32_t)key & kTriMask);
-            const ViewM Mv = load_viewM(viewM + (size_t)n * kViewM);
-            PixTri q;
-            load_pixtri(t, px, py, vg, Mv.m, tri4, vattr, invW, invH, q);
-            AAGeom g;
-            g.bits = 0;
-            {
-                // silhouette-candidate bits of this triangle in this pixel's frame; window coordinates of the corners
-                // come from the clip positions already in registers, those of the three wing vertices are gathered
-                const int4 ox = __ldg(opp4 + t);
-                const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
-                float2 so0 = make_float2(0.f, 0.f), so1 = so0, so2 = so0;
-                if ((unsigned)ox.x < (unsigned)V) so0 = aa_window_xy(clip_from_world(Mv.m, __ldg(vg + 2 * (size_t)ox.x)), xh, yh);
-                if ((unsigned)ox.y < (unsigned)V) so1 = aa_window_xy(clip_from_world(Mv.m, __ldg(vg + 2 * (size_t)ox.y)), xh, yh);
-                if ((unsigned)ox.z < (unsigned)V) so2 = aa_window_xy(clip_from_world(Mv.m, __ldg(vg + 2 * (size_t)ox.z)), xh, yh);
-                aa_triangle_geom_win(q.i0, q.i1, q.i2, aa_window_xy(q.p0, xh, yh), aa_window_xy(q.p1, xh, yh),
-                                     aa_window_xy(q.p2, xh, yh), ox.x, ox.y, ox.z, so0, so1, so2, px, py, V, H, W, g);
-            }
-            const float3 m = interp3(q.n0, q.n1, q.n2, q);
-            const float3 a = interp3(q.b0, q.b1, q.b2, q);
-            const bool valid = __ldg(masks + (size_t)view * hw + rem) > 0.0f;
-            nvalid = valid ? 1.0f : 0.0f;
-            feeds_backward = PHASE == 1 ? valid : true;  // phase A back-propagates through every covered pixel's albedo
-            pix32 = (uint32_t)pix;
-            zbuf[pix] = key | ((unsigned long long)(uint32_t)g.bits << 28) | (valid ? 0x80000000ull : 0ull);
-            if (PHASE == 1) {
-                float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    const float inv = 1.0f / fmaxf(sqrtf(m.x * m.x + m.y * m.y + m.z * m.z), 1e-12f);
-                    const float r = sh_radiance(sh, m.x * inv, m.y * inv, m.z * inv);
-                    col = make_float4(r * a.x, r * a.y, r * a.z, 1.0f);
-                }
-                plane0[pix] = col;
-            } else {
-                plane0[pix] = make_float4(m.x, m.y, m.z, nvalid);
-                plane1[pix] = make_float4(a.x, a.y, a.z, 0.0f);
-            }
-        }
-    }
-    warp_acc_add(acc, 0, nvalid, st);
-}
-
-// shade:  z-buffer -> shaded colour (phase B) or interpolated normals + albedo (phase A); tags every key with the
-// silhouette bits / valid flag, resets the tiles the OTHER z-buffer slot dirtied in the previous iteration (no separate
-// clear pass) and builds the dilated work list for the two passes that follow.  Persistent: grid = SMs x 4.
-template <int PHASE>
-__global__ void __launch_bounds__(256) ham_shade_kernel(unsigned long long* __restrict__ zbuf,
-                                                        unsigned long long* __restrict__ zbuf_next,
-                                                        const uint32_t* __restrict__ tlist, const int* __restrict__ tcount,
-                                                        const uint32_t* __restrict__ tlist_next,
-                                                        const int* __restrict__ tcount_next,
-                                                        uint32_t* __restrict__ abits, uint32_t* __restrict__ alist,
-                                                        int* __restrict__ acount, int* __restrict__ cursors,
-                                                        int tiles_x, int tiles_y,
-                                                        const float4* __restrict__ vg,
-                                                        const float* __restrict__ viewM, float invW, float invH,
-                                                        const int4* __restrict__ tri4,
-                                                        const int4* __restrict__ opp4,
-                                                        const float4* __restrict__ vattr,
-                                                        const float* __restrict__ masks,
-                                                        const float* __restrict__ sh_coeffs,
-                                                        const int32_t* __restrict__ view_idx,
-                                                        const int32_t* __restrict__ sh_idx, int V, int T, int H, int W,
-                                                        float4* __restrict__ plane0, float4* __restrict__ plane1,
-                                                        double* __restrict__ acc, uint32_t* __restrict__ vlist,
-                                                        int* __restrict__ vcount) {
-    // Pixels that feed the backward shader are collected per warp in shared memory and appended to the global compact
-    // list with one atomic per ~450 pixels; the backward pass then runs with every lane busy.
-    constexpr int kVBuf = 480;
-    __shared__ uint32_t vbuf[8][kVBuf];
+__global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long* __restrict__ zbuf,
+                                                       unsigned long long* __restrict__ zbuf_next,
+                                                       const uint32_t* __restrict__ tlist, const int* __restrict__ tcount,
+                                                       const uint32_t* __restrict__ tlist_next,
+                                                       const int* __restrict__ tcount_next, int tiles_x, int tiles_y,
+                                                       int H, int W, uint2* __restrict__ clist, int* __restrict__ ccount,
+                                                       uint32_t* __restrict__ ringbits, uint32_t* __restrict__ rlist,
+                                                       int* __restrict__ rcount, int rcap, int* __restrict__ status) {
+    constexpr int kBuf = 224;
+    __shared__ uint2 cbuf[8][kBuf];
     int nbuf = 0;  // warp-uniform
-    const int wib_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     auto flush = [&]() {
         int base = 0;
-        if (lane_ == 0) base = atomicAdd(vcount, nbuf);
+        if (lane == 0) base = atomicAdd(ccount, nbuf);
         base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane_; i < nbuf; i += 32) vlist[base + i] = vbuf[wib_][i];
+        for (int i = lane; i < nbuf; i += 32) clist[base + i] = cbuf[wib][i];
         __syncwarp();
         nbuf = 0;
     };
-    // units = 16x2 strips; two global cursors (reset pass of the other slot, shade pass of this slot)
     Strip st;
-    const int u0 = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int u0 = blockIdx.x * 8 + wib;
     const int nd = *tcount_next;
     int u = u0;
     while (next_strip(u, tlist_next, nd, tiles_x, tiles_y, st))
         if (st.px < W && st.py < H) zbuf_next[((size_t)st.tc.n * H + st.py) * W + st.px] = ZB_EMPTY;
-    const int nc = *tcount;
+    const int nt = *tcount;
     u = u0;
-    while (next_strip(u, tlist, nc, tiles_x, tiles_y, st)) {
-        if (st.tid < 5) tile_mark_active(st.tc, st.tid, abits, alist, acount);  // strip 0 of the tile dilates it
-        bool fb;
-        uint32_t pix32;
-        shade_tile<PHASE>(st, zbuf, vg, viewM, invW, invH, tri4, opp4, vattr, masks, sh_coeffs, view_idx, sh_idx, V, T, H,
-                          W, plane0, plane1, acc, fb, pix32);
-        const unsigned m = __ballot_sync(0xffffffffu, fb);
-        if (m) {
-            if (fb) vbuf[wib_][nbuf + __popc(m & ((1u << lane_) - 1u))] = pix32;
-            nbuf += __popc(m);
-            __syncwarp();
-            if (nbuf > kVBuf - 32) flush();
+    while (next_strip(u, tlist, nt, tiles_x, tiles_y, st)) {
+        const bool inb = st.px < W && st.py < H;
+        const size_t pix = ((size_t)st.tc.n * H + st.py) * W + st.px;
+        unsigned long long key = ZB_EMPTY;
+        if (inb) key = zbuf[pix];
+        const bool covered = key != ZB_EMPTY;
+        const unsigned m = __ballot_sync(0xffffffffu, covered);
+        if (m == 0u) continue;
+        if (covered) {
+            cbuf[wib][nbuf + __popc(m & lt)] = make_uint2((uint32_t)pix, (uint32_t)key & kTriMask);
+            // empty 4-neighbours of a covered pixel: the ring antialiasing can blend into
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                const int dx = d == 0 ? 1 : (d == 1 ? -1 : 0), dy = d == 2 ? 1 : (d == 3 ? -1 : 0);
+                const int qx = st.px + dx, qy = st.py + dy;
+                if (qx < 0 || qy < 0 || qx >= W || qy >= H) continue;
+                const size_t q = pix + dx + (long long)dy * W;
+                if (zbuf[q] != ZB_EMPTY) continue;
+                const uint32_t bit = 1u << (q & 31);
+                const uint32_t old = atomicOr(ringbits + (q >> 5), bit);
+                if (!(old & bit)) {
+                    const int slot = atomicAdd(rcount, 1);
+                    if (slot < rcap) rlist[slot] = (uint32_t)q;
+                    else atomicOr(status, 2);
+                }
+            }
         }
+        nbuf += __popc(m);
+        __syncwarp();
+        if (nbuf > kBuf - 32) flush();
     }
     if (nbuf > 0) flush();
 }
 
+// ------------------------------------------------------------------------------------------------
+// shade: one covered pixel per thread over the compact list (grid-stride, every lane busy): triangle -> world-space
+// corners -> clip positions, perspective barycentrics, interpolated normal / albedo, SH radiance * albedo (phase B) or
+// normals + albedo planes (phase A); tags the z-buffer key with the triangle's silhouette-candidate bits and the valid
+// flag (one 32-bit RED), and records the valid flag in the list entry for the backward pass.
+// ------------------------------------------------------------------------------------------------
 template <int PHASE>
-__device__ __forceinline__ void aa_loss_tile(
-    const Strip& st, const unsigned long long* __restrict__ zbuf,
+__global__ void __launch_bounds__(256, 4) ham_shade_kernel(uint2* __restrict__ clist, const int* __restrict__ ccount,
+                                                        unsigned long long* __restrict__ zbuf,
+                                                        const float4* __restrict__ vg, const float* __restrict__ viewM,
+                                                        float invW, float invH, const int4* __restrict__ tri4,
+                                                        const int4* __restrict__ opp4, const float4* __restrict__ vattr,
+                                                        const float* __restrict__ masks,
+                                                        const float* __restrict__ sh_coeffs,
+                                                        const int32_t* __restrict__ view_idx,
+                                                        const int32_t* __restrict__ sh_idx, int V, int H, int W,
+                                                        float4* __restrict__ plane0, float4* __restrict__ plane1,
+                                                        double* __restrict__ acc) {
+    const int nc = *ccount;
+    const int hw = H * W;
+    const int lane = threadIdx.x & 31;
+    float nvalid = 0.0f;
+    for (int e0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; e0 < nc; e0 += gridDim.x * blockDim.x) {
+        const int e = e0 + lane;
+        if (e >= nc) continue;
+        const uint2 ent = clist[e];
+        const size_t pix = ent.x;
+        const int t = (int)ent.y;
+        const PixAddr pa = pix_decode(ent.x, H, W);
+        const int n = pa.n, px = pa.px, py = pa.py;
+        const float* Mv = viewM + (size_t)n * kViewM;
+        const int view = __ldg(view_idx + n);
+        const bool valid = __ldg(masks + (size_t)view * hw + pa.rem) > 0.0f;
+        PixTri q;
+        load_pixtri(t, px, py, vg, Mv, tri4, vattr, invW, invH, q);
+        AAGeom g;
+        g.bits = 0;
+        {
+            // silhouette-candidate bits of this triangle in this pixel's frame; window coordinates of the corners come
+            // from the clip positions already in registers, those of the three wing vertices are gathered
+            const int4 ox = __ldg(opp4 + t);
+            const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
+            float2 so0 = make_float2(0.f, 0.f), so1 = so0, so2 = so0;
+            if ((unsigned)ox.x < (unsigned)V) so0 = aa_window_xy(clip_from_world(Mv, __ldg(vg + 2 * (size_t)ox.x)), xh, yh);
+            if ((unsigned)ox.y < (unsigned)V) so1 = aa_window_xy(clip_from_world(Mv, __ldg(vg + 2 * (size_t)ox.y)), xh, yh);
+            if ((unsigned)ox.z < (unsigned)V) so2 = aa_window_xy(clip_from_world(Mv, __ldg(vg + 2 * (size_t)ox.z)), xh, yh);
+            aa_triangle_geom_win(q.i0, q.i1, q.i2, aa_window_xy(q.p0, xh, yh), aa_window_xy(q.p1, xh, yh),
+                                 aa_window_xy(q.p2, xh, yh), ox.x, ox.y, ox.z, so0, so1, so2, px, py, V, H, W, g);
+        }
+        const float3 m = interp3(q.n0, q.n1, q.n2, q);
+        const float3 a = interp3(q.b0, q.b1, q.b2, q);
+        if (valid) nvalid += 1.0f;
+        const uint32_t tag = ((uint32_t)g.bits << 28) | (valid ? 0x80000000u : 0u);
+        if (tag) atomicOr(reinterpret_cast<unsigned int*>(zbuf + pix), tag);  // low word of the little-endian key
+        clist[e].y = ent.y | (valid ? 0x80000000u : 0u);
+        if (PHASE == 1) {
+            float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
+                const float inv = 1.0f / fmaxf(sqrtf(m.x * m.x + m.y * m.y + m.z * m.z), 1e-12f);
+                const float r = sh_radiance(sh, m.x * inv, m.y * inv, m.z * inv);
+                col = make_float4(r * a.x, r * a.y, r * a.z, 1.0f);
+            }
+            plane0[pix] = col;
+        } else {
+            plane0[pix] = make_float4(m.x, m.y, m.z, valid ? 1.0f : 0.0f);
+            plane1[pix] = make_float4(a.x, a.y, a.z, 0.0f);
+        }
+    }
+    warp_acc_add(acc, 0, nvalid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// antialias (gather form) + losses over the compact lists: covered pixels, then the ring of empty pixels around them.
+// Each pixel inspects its four pixel pairs (self,right) (self,down) (left,self) (up,self).  Pairs that can blend
+// (different triangle ids and silhouette bits set on the chosen triangle - exact, the bits come from the identical
+// geometry call in the shade pass) are rare (~1 % of pixels), so instead of running the ~400-instruction edge analysis
+// under a 1-3 lane mask they are queued per warp in shared memory and analysed with the queue spread over the lanes;
+// a pair is analysed from both of its pixels and each takes the blend only if it is the receiver
+// (out[alpha > 0 ? first : second] += alpha * (color[second] - color[first])), the pair's first pixel records it for
+// the backward pass.  Everything is warp-synchronous.
+//   item = (lane << 2) | which,  which: 0 (self,right)  1 (self,down)  2 (left,self)  3 (up,self)
+// The mask loss sum_pixels (pred_mask - valid_mask)^2 is accumulated as a correction (pred - valid)^2 - valid^2 over the
+// listed pixels; every other pixel has pred_mask == 0 and contributes valid_mask^2, whose total per view is a constant
+// of the optimisation (buffers.view_vm2).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_needs_analysis(const NbrKeys& k0, const NbrKeys& k1) {
+    if (k0.tri == k1.tri) return false;
+    // same triangle choice as aa_analyse
+    const bool from1 = (k0.tri >= 0 && k1.tri >= 0) ? !(k0.zw < k1.zw) : (k0.tri < 0);
+    return (from1 ? k1.bits : k0.bits) != 0;
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
+    const uint2* __restrict__ clist, const int* __restrict__ ccount, const uint32_t* __restrict__ rlist,
+    const int* __restrict__ rcount, int rcap, uint32_t* __restrict__ ringbits, const unsigned long long* __restrict__ zbuf,
     const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ tri,
     const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
     float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
-    const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask,
-    uint32_t* q_items, int& q_n, float (*blend)[PHASE == 1 ? 4 : 6], uint4* __restrict__ plist_a,
+    float* __restrict__ dbg_image, float* __restrict__ dbg_mask, uint4* __restrict__ plist_a,
     uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap, int* __restrict__ status) {
     constexpr int NC = PHASE == 1 ? 4 : 6;  // blended channels: (b,g,r,coverage) or (normal xyz, albedo bgr)
-    const TileCtx& tc = st.tc;
-    const int n = tc.n;
-    const int tiles = tc.nx * tc.ny;
-    const int view = __ldg(view_idx + n);
-    const int tid = st.tid, lane = st.lane;  // blend[] is this warp's: indexed by lane
-    const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;  // block-uniform address: L1 broadcast
+    __shared__ uint32_t q_items_s[8][128];
+    __shared__ int q_n_s[8];
+    __shared__ float blend_s[8][32][NC];
+    __shared__ uint32_t spix_s[8][32];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* q_items = q_items_s[wib];
+    int* q_n = &q_n_s[wib];
+    float (*blend)[NC] = blend_s[wib];
+    uint32_t* spix = spix_s[wib];
+    const int nc = *ccount, total = nc + min(*rcount, rcap);
     const int hw = H * W;
-    const int px = st.px, py = st.py;
-    const bool inb = px < W && py < H;
-    const size_t base = (size_t)n * hw;
-    const unsigned long long* zb = zbuf + base;
-    const int rem = py * W + px;
-    NbrKeys self = decode_key(ZB_EMPTY);
-    if (inb) self = decode_key(zb[rem]);
-    enqueue_pairs(zb, st, H, W, self, q_items, &q_n);
-    __syncwarp();
-    // analysis of the queued pairs spread over the lanes; the receiver's blend lands in shared memory
-    const int nq = q_n;
-    if (nq > 0) {  // warp-uniform
-#pragma unroll
-        for (int c = 0; c < NC; c++) blend[lane][c] = 0.0f;
+    float abs_acc = 0.0f;
+    double msk_acc = 0.0;  // fp64: the corrections cancel against the fp64 view totals (exactly 0 when pred == valid)
+    for (int e0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; e0 < total; e0 += gridDim.x * blockDim.x) {
+        const int e = e0 + lane;
+        const bool active = e < total;
+        uint32_t pix32 = 0u;
+        if (active) {
+            if (e < nc) pix32 = clist[e].x;
+            else {
+                pix32 = rlist[e - nc];
+                atomicAnd(ringbits + (pix32 >> 5), ~(1u << (pix32 & 31)));  // the bitmap cleans itself for the next step
+            }
+        }
+        const PixAddr pa = pix_decode(pix32, H, W);
+        const int n = pa.n, px = pa.px, py = pa.py, rem = pa.rem;
+        const size_t base = (size_t)n * hw;
+        const unsigned long long* zb = zbuf + base;
+        NbrKeys self = decode_key(ZB_EMPTY);
+        if (lane == 0) *q_n = 0;
+        spix[lane] = pix32;
         __syncwarp();
-        const AAProjWorld proj{vg, viewM + (size_t)n * kViewM, 0.5f * (float)W, 0.5f * (float)H};
-        for (int e = lane; e < nq; e += 32) {
-            const PairItem it = decode_pair_item(q_items[e], tc);
-            const int r0 = it.qy * W + it.qx, r1 = r0 + (it.d ? W : 1);
-            const NbrKeys k0 = decode_key(zb[r0]), k1 = decode_key(zb[r1]);
-            AAPair pr;
-            if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, it.qx, it.qy, it.d, proj, tri, opp, V, T, H, W, pr)) continue;
-            if (it.tid0 >= 0) {  // the warp whose strip holds the pair's first pixel records it for the backward pass
-                const int slot = atomicAdd(pcount, 1);
-                if (slot < pcap) {
-                    const uint32_t flags = (uint32_t)it.d | ((uint32_t)pr.from1 << 1) | ((uint32_t)pr.clamped << 2) |
-                                           ((uint32_t)pr.di << 3);
-                    plist_a[slot] = make_uint4((uint32_t)(base + r0), flags, __float_as_uint(pr.alpha), (uint32_t)pr.i1);
-                    plist_b[slot] = (uint32_t)pr.i2;
+        if (active) {
+            self = decode_key(zb[rem]);
+            if (px + 1 < W && pair_needs_analysis(self, decode_key(zb[rem + 1]))) q_items[atomicAdd(q_n, 1)] = ((uint32_t)lane << 2) | 0u;
+            if (py + 1 < H && pair_needs_analysis(self, decode_key(zb[rem + W]))) q_items[atomicAdd(q_n, 1)] = ((uint32_t)lane << 2) | 1u;
+            if (px > 0 && pair_needs_analysis(decode_key(zb[rem - 1]), self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)lane << 2) | 2u;
+            if (py > 0 && pair_needs_analysis(decode_key(zb[rem - W]), self)) q_items[atomicAdd(q_n, 1)] = ((uint32_t)lane << 2) | 3u;
+        }
+        __syncwarp();
+        // analysis of the queued pairs spread over the lanes; the receiver's blend lands in shared memory
+        const int nq = *q_n;
+        if (nq > 0) {  // warp-uniform
+#pragma unroll
+            for (int c = 0; c < NC; c++) blend[lane][c] = 0.0f;
+            __syncwarp();
+            for (int x = lane; x < nq; x += 32) {
+                const uint32_t item = q_items[x];
+                const int L = (int)(item >> 2), which = (int)(item & 3u), d = which & 1;
+                const PixAddr qa = pix_decode(spix[L], H, W);
+                // first pixel of the pair
+                const int qx = which < 2 ? qa.px : qa.px - (1 - d), qy = which < 2 ? qa.py : qa.py - d;
+                const size_t qbase = (size_t)qa.n * hw;
+                const int r0 = qy * W + qx, r1 = r0 + (d ? W : 1);
+                const NbrKeys k0 = decode_key(zbuf[qbase + r0]), k1 = decode_key(zbuf[qbase + r1]);
+                const AAProjWorld proj{vg, viewM + (size_t)qa.n * kViewM, 0.5f * (float)W, 0.5f * (float)H};
+                AAPair pr;
+                if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, qx, qy, d, proj, tri, opp, V, T, H, W, pr)) continue;
+                if (which < 2) {  // seen from the pair's first pixel: record it for the backward pass
+                    const int slot = atomicAdd(pcount, 1);
+                    if (slot < pcap) {
+                        const uint32_t flags = (uint32_t)d | ((uint32_t)pr.from1 << 1) | ((uint32_t)pr.clamped << 2) |
+                                               ((uint32_t)pr.di << 3);
+                        plist_a[slot] = make_uint4((uint32_t)(qbase + r0), flags, __float_as_uint(pr.alpha), (uint32_t)pr.i1);
+                        plist_b[slot] = (uint32_t)pr.i2;
+                    } else {
+                        atomicOr(status, 1);
+                    }
+                }
+                const bool recv_is_self = (which < 2) == (pr.alpha > 0.0f);
+                if (!recv_is_self) continue;  // the other pixel's own item delivers it
+                // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
+                float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, s0 = f0, s1 = f0;
+                if (k0.tri >= 0) { f0 = plane0[qbase + r0]; if (PHASE == 0) f1 = plane1[qbase + r0]; }
+                if (k1.tri >= 0) { s0 = plane0[qbase + r1]; if (PHASE == 0) s1 = plane1[qbase + r1]; }
+                atomicAdd(&blend[L][0], pr.alpha * (s0.x - f0.x));
+                atomicAdd(&blend[L][1], pr.alpha * (s0.y - f0.y));
+                atomicAdd(&blend[L][2], pr.alpha * (s0.z - f0.z));
+                if (PHASE == 1) {
+                    atomicAdd(&blend[L][3], pr.alpha * ((k1.tri >= 0 ? 1.0f : 0.0f) - (k0.tri >= 0 ? 1.0f : 0.0f)));
                 } else {
-                    atomicOr(status, 1);
+                    atomicAdd(&blend[L][3], pr.alpha * (s1.x - f1.x));
+                    atomicAdd(&blend[L][4], pr.alpha * (s1.y - f1.y));
+                    atomicAdd(&blend[L][5], pr.alpha * (s1.z - f1.z));
                 }
             }
-            const int recv_tid = pr.alpha > 0.0f ? it.tid0 : it.tid1;
-            if (recv_tid < 0) continue;  // the receiver belongs to another warp's strip
-            const int recv = recv_tid & 31;
-            // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
-            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, s0 = f0, s1 = f0;
-            if (k0.tri >= 0) { f0 = plane0[base + r0]; if (PHASE == 0) f1 = plane1[base + r0]; }
-            if (k1.tri >= 0) { s0 = plane0[base + r1]; if (PHASE == 0) s1 = plane1[base + r1]; }
-            atomicAdd(&blend[recv][0], pr.alpha * (s0.x - f0.x));
-            atomicAdd(&blend[recv][1], pr.alpha * (s0.y - f0.y));
-            atomicAdd(&blend[recv][2], pr.alpha * (s0.z - f0.z));
+            __syncwarp();
+        }
+        float gc[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) gc[k] = 0.0f;
+        if (active) {
+            const size_t pix = pix32;
+            const int view = __ldg(view_idx + n);
+            // own (pre-antialias) values; empty pixels are zero in every channel
+            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (self.tri >= 0) {
+                c0 = plane0[pix];
+                if (PHASE == 0) c1 = plane1[pix];
+            }
+            float4 a0 = c0, a1 = c1;  // antialiased values
+            float amask = self.tri >= 0 ? 1.0f : 0.0f;
+            if (nq > 0) {
+                a0.x += blend[lane][0]; a0.y += blend[lane][1]; a0.z += blend[lane][2];
+                if (PHASE == 1) amask += blend[lane][3];
+                else { a1.x += blend[lane][3]; a1.y += blend[lane][4]; a1.z += blend[lane][5]; }
+            }
+            const bool valid = self.valid;
+            const float* img = imgs + ((size_t)view * hw + rem) * 3;
             if (PHASE == 1) {
-                atomicAdd(&blend[recv][3], pr.alpha * ((k1.tri >= 0 ? 1.0f : 0.0f) - (k0.tri >= 0 ? 1.0f : 0.0f)));
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {  // mesh_sfs_optim.py:289  l1 over tmp_img[valid_idx]
+                    const float d0 = a0.x - __ldg(img), d1 = a0.y - __ldg(img + 1), d2 = a0.z - __ldg(img + 2);
+                    abs_acc += fabsf(d0) + fabsf(d1) + fabsf(d2);
+                    g.x = (d0 > 0.f) - (d0 < 0.f); g.y = (d1 > 0.f) - (d1 < 0.f); g.z = (d2 > 0.f) - (d2 < 0.f);
+                }
+                // mesh_sfs_optim.py:295  mean((pred_mask - valid_mask)^2), as a correction to sum valid_mask^2
+                const float vm = __ldg(valid_masks + (size_t)view * hw + rem);
+                const float dm = amask - vm;
+                msk_acc += (double)dm * (double)dm - (double)vm * (double)vm;
+                g.w = dm;
+                gplane0[pix] = g;
+                if (dbg_image) { dbg_image[pix * 3] = a0.x; dbg_image[pix * 3 + 1] = a0.y; dbg_image[pix * 3 + 2] = a0.z; }
+                if (dbg_mask) dbg_mask[pix] = amask;
             } else {
-                atomicAdd(&blend[recv][3], pr.alpha * (s1.x - f1.x));
-                atomicAdd(&blend[recv][4], pr.alpha * (s1.y - f1.y));
-                atomicAdd(&blend[recv][5], pr.alpha * (s1.z - f1.z));
+                // phase A (mesh_sfs_optim.py:217-230): a0 = antialiased normals, a1 = antialiased albedo
+                float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+                float3 pred = make_float3(0.f, 0.f, 0.f);
+                if (valid) {
+                    const float* sh = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
+                    const float len = sqrtf(a0.x * a0.x + a0.y * a0.y + a0.z * a0.z);
+                    const float inv = 1.0f / fmaxf(len, 1e-12f);
+                    const float nx = a0.x * inv, ny = a0.y * inv, nz = a0.z * inv;
+                    const float r = sh_radiance(sh, nx, ny, nz);
+                    pred = make_float3(r * a1.x, r * a1.y, r * a1.z);
+                    const float d0 = pred.x - __ldg(img), d1 = pred.y - __ldg(img + 1), d2 = pred.z - __ldg(img + 2);
+                    abs_acc += fabsf(d0) + fabsf(d1) + fabsf(d2);
+                    const float s0 = (d0 > 0.f) - (d0 < 0.f), s1 = (d1 > 0.f) - (d1 < 0.f), s2 = (d2 > 0.f) - (d2 < 0.f);
+                    g1 = make_float4(s0 * r, s1 * r, s2 * r, 0.0f);  // d/d(albedo_aa)
+                    const float gr = s0 * a1.x + s1 * a1.y + s2 * a1.z;
+                    gc[0] = gr; gc[1] = gr * ny; gc[2] = gr * nz; gc[3] = gr * nx; gc[4] = gr * nx * ny; gc[5] = gr * ny * nz;
+                    gc[6] = gr * (2 * nz * nz - nx * nx - ny * ny); gc[7] = gr * nz * nx; gc[8] = gr * (nx * nx - ny * ny);
+                    // normals are not trainable in phase A (vertices detached, mesh_sfs_optim.py:191,196): g0 stays 0
+                }
+                gplane0[pix] = g0;
+                gplane1[pix] = g1;
+                if (dbg_image) { dbg_image[pix * 3] = pred.x; dbg_image[pix * 3 + 1] = pred.y; dbg_image[pix * 3 + 2] = pred.z; }
             }
         }
-        __syncwarp();
-        if (lane == 0) q_n = 0;
-    }
-    float abs_sum = 0.0f, msk_sum = 0.0f;
-    float gc[9];
+        if (PHASE == 0) {
+            // SH gradient rows: a warp's 32 list entries almost always belong to one view
+            const int n0 = __shfl_sync(0xffffffffu, n, 0);
+            const bool uniform = __all_sync(0xffffffffu, !active || n == n0);
+            if (uniform) {
 #pragma unroll
-    for (int k = 0; k < 9; k++) gc[k] = 0.0f;
-    if (inb) {
-        const size_t pix = base + rem;
-        // own (pre-antialias) values; empty pixels are zero in every channel
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (self.tri >= 0) {
-            c0 = plane0[pix];
-            if (PHASE == 0) c1 = plane1[pix];
-        }
-        float4 a0 = c0, a1 = c1;  // antialiased values
-        float amask = self.tri >= 0 ? 1.0f : 0.0f;
-        if (nq > 0) {
-            a0.x += blend[lane][0]; a0.y += blend[lane][1]; a0.z += blend[lane][2];
-            if (PHASE == 1) amask += blend[lane][3];
-            else { a1.x += blend[lane][3]; a1.y += blend[lane][4]; a1.z += blend[lane][5]; }
-        }
-        const bool valid = self.valid;
-        const float* img = imgs + ((size_t)view * hw + rem) * 3;
-        if (PHASE == 1) {
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {  // mesh_sfs_optim.py:289  l1 over tmp_img[valid_idx]
-                const float d0 = a0.x - __ldg(img), d1 = a0.y - __ldg(img + 1), d2 = a0.z - __ldg(img + 2);
-                abs_sum = fabsf(d0) + fabsf(d1) + fabsf(d2);
-                g.x = (d0 > 0.f) - (d0 < 0.f); g.y = (d1 > 0.f) - (d1 < 0.f); g.z = (d2 > 0.f) - (d2 < 0.f);
+                for (int k = 0; k < 9; k++) {
+                    const float sk = warp_sum(gc[k]);
+                    if (lane == 0 && sk != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n0) * 9 + k, sk);
+                }
+            } else if (active) {
+#pragma unroll
+                for (int k = 0; k < 9; k++)
+                    if (gc[k] != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, gc[k]);
             }
-            // mesh_sfs_optim.py:295  mean((pred_mask - valid_mask)^2).  Inactive tiles have pred_mask == 0 and contribute
-            // valid_mask^2, a per-tile constant of the view (buffers.view_vm2): they are never visited.
-            const float dm = amask - __ldg(valid_masks + (size_t)view * hw + rem);
-            msk_sum = dm * dm;
-            g.w = dm;
-            gplane0[pix] = g;
-            if (dbg_image) { dbg_image[pix * 3] = a0.x; dbg_image[pix * 3 + 1] = a0.y; dbg_image[pix * 3 + 2] = a0.z; }
-            if (dbg_mask) dbg_mask[pix] = amask;
-        } else {
-            // phase A (mesh_sfs_optim.py:217-230): a0 = antialiased normals, a1 = antialiased albedo
-            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-            float3 pred = make_float3(0.f, 0.f, 0.f);
-            if (valid) {
-                const float len = sqrtf(a0.x * a0.x + a0.y * a0.y + a0.z * a0.z);
-                const float inv = 1.0f / fmaxf(len, 1e-12f);
-                const float nx = a0.x * inv, ny = a0.y * inv, nz = a0.z * inv;
-                const float r = sh_radiance(sh, nx, ny, nz);
-                pred = make_float3(r * a1.x, r * a1.y, r * a1.z);
-                const float d0 = pred.x - __ldg(img), d1 = pred.y - __ldg(img + 1), d2 = pred.z - __ldg(img + 2);
-                abs_sum = fabsf(d0) + fabsf(d1) + fabsf(d2);
-                const float s0 = (d0 > 0.f) - (d0 < 0.f), s1 = (d1 > 0.f) - (d1 < 0.f), s2 = (d2 > 0.f) - (d2 < 0.f);
-                g1 = make_float4(s0 * r, s1 * r, s2 * r, 0.0f);  // d/d(albedo_aa)
-                const float gr = s0 * a1.x + s1 * a1.y + s2 * a1.z;
-                gc[0] = gr; gc[1] = gr * ny; gc[2] = gr * nz; gc[3] = gr * nx; gc[4] = gr * nx * ny; gc[5] = gr * ny * nz;
-                gc[6] = gr * (2 * nz * nz - nx * nx - ny * ny); gc[7] = gr * nz * nx; gc[8] = gr * (nx * nx - ny * ny);
-                // normals are not trainable in phase A (vertices detached, mesh_sfs_optim.py:191,196): g0 stays 0
-            }
-            gplane0[pix] = g0;
-            gplane1[pix] = g1;
-            if (dbg_image) { dbg_image[pix * 3] = pred.x; dbg_image[pix * 3 + 1] = pred.y; dbg_image[pix * 3 + 2] = pred.z; }
         }
+        __syncwarp();  // blend[] / q_items / q_n / spix of this warp are rewritten by its next batch
     }
-    warp_acc_add(acc, 1, abs_sum, st);
+    warp_acc_add(acc, 1, abs_acc);
     if (PHASE == 1) {
-        warp_acc_add(acc, 2, msk_sum, st);
-        // this tile is accounted for explicitly: remove its constant share (exact in fp64)
-        if (tid == 0)  // strip 0, lane 0: once per tile
-            atomicAdd(acc + 7 * 32 + ((tc.bx + tc.by * 7 + tc.n * 13) & 31),
-                      view_vm2[(size_t)view * (tiles + 1) + tile_index(tc)]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const float sk = warp_sum(gc[k]);
-            if (lane == 0 && sk != 0.0f) atomicAdd(gsh + (size_t)__ldg(sh_idx + n) * 9 + k, sk);
-        }
+        msk_acc = warp_sum_f64(msk_acc);
+        if (lane == 0 && msk_acc != 0.0) atomicAdd(acc + 2 * 32 + ((blockIdx.x * 8 + wib) & 31), msk_acc);
     }
-    __syncwarp();  // blend[] / q_items / q_n of this warp are rewritten by its next tile
-}
-
-// antialias (gather form, dense pair queue) + losses; persistent over the dilated work list
-template <int PHASE>
-__global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
-    const unsigned long long* __restrict__ zbuf, const uint32_t* __restrict__ alist, const int* __restrict__ acount,
-    int* __restrict__ cursors, int tiles_x, int tiles_y, const float4* __restrict__ vg,
-    const float* __restrict__ viewM, const int32_t* __restrict__ tri,
-    const int32_t* __restrict__ opp, const float* __restrict__ imgs, const float* __restrict__ valid_masks,
-    const float* __restrict__ sh_coeffs, const int32_t* __restrict__ view_idx, const int32_t* __restrict__ sh_idx,
-    int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
-    float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
-    const double* __restrict__ view_vm2, float* __restrict__ dbg_image, float* __restrict__ dbg_mask,
-    uint4* __restrict__ plist_a, uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap,
-    int* __restrict__ status) {
-    __shared__ uint32_t q_items[8][kPairQueue];
-    __shared__ int q_n[8];
-    __shared__ float blend[8][32][PHASE == 1 ? 4 : 6];
-    const int wib = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) q_n[wib] = 0;
-    __syncwarp();
-    const int na = *acount;
-    Strip st;
-    int u = blockIdx.x * 8 + wib;
-    while (next_strip(u, alist, na, tiles_x, tiles_y, st))
-        aa_loss_tile<PHASE>(st, zbuf, vg, viewM, tri, opp, imgs, valid_masks, sh_coeffs, view_idx, sh_idx, V, T, H, W, plane0,
-                            plane1, gplane0, gplane1, acc, gsh, view_vm2, dbg_image, dbg_mask, q_items[wib], q_n[wib],
-                            blend[wib], plist_a, plist_b, pcount, pcap, status);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1021,24 +997,27 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, part 2: one thread per pixel of the compact list (every lane busy): SH / normalise / interpolate /
+// backward, part 2: one thread per covered pixel of the compact list (every lane busy): SH / normalise / interpolate /
 // rasterize backward, 9 float4 red.global.add per pixel into the world-space per-vertex accumulators.
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
-    const uint32_t* __restrict__ vlist, const int* __restrict__ vcount, const unsigned long long* __restrict__ zbuf,
+    const uint2* __restrict__ clist, const int* __restrict__ ccount,
     const float4* __restrict__ vg, float invW, float invH, const float* __restrict__ viewM,
     const int4* __restrict__ tri4, const float4* __restrict__ vattr,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, int V, int H, int W,
     const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ gdelta,
     float4* __restrict__ G) {
-    const int nv = *vcount;
-    const int hw = H * W;
+    const int nv = *ccount;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += gridDim.x * blockDim.x) {
-        const size_t pix = vlist[e];
-        const int n = (int)(pix / hw);
-        const int rem = (int)(pix - (size_t)n * hw), py = rem / W, px = rem - py * W;
-        const NbrKeys self = decode_key(zbuf[pix]);
+        const uint2 ent = clist[e];  // (pixel, triangle | valid << 31) from the scan / shade passes
+        // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286);
+        // phase A back-propagates through every covered pixel's albedo
+        if (PHASE == 1 && !(ent.y >> 31)) continue;
+        const size_t pix = ent.x;
+        const int tself = (int)(ent.y & kTriMask);
+        const PixAddr pa = pix_decode(ent.x, H, W);
+        const int n = pa.n, px = pa.px, py = pa.py;
         const float* M = viewM + (size_t)n * kViewM;
         const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
         // gradient w.r.t. this pixel's PRE-antialias values: pass-through + pair terms (consumed and re-armed)
@@ -1053,7 +1032,7 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
             g1.x += gd.x; g1.y += gd.y; g1.z += gd.z;
         }
         PixTri q;
-        load_pixtri(self.tri, px, py, vg, M, tri4, vattr, invW, invH, q);
+        load_pixtri(tself, px, py, vg, M, tri4, vattr, invW, invH, q);
         const float w = 1.0f - q.u - q.v;
         if (PHASE == 0) {
             // only the albedo attribute is trainable: interpolate bwd
@@ -1063,8 +1042,6 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
             atomicAdd(G + 2 * (size_t)q.i2 + 1, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
             continue;
         }
-        // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286)
-        if (!self.valid) continue;
         if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) continue;
         const float3 m = interp3(q.n0, q.n1, q.n2, q);
         const float3 a = interp3(q.b0, q.b1, q.b2, q);
@@ -1135,21 +1112,14 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
 }
 
 // One warp: lane j owns spread slot j of every accumulator (fp64 shuffles), view totals are strided over the lanes.
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 __global__ void __launch_bounds__(32) ham_finalize_scalars_kernel(const double* __restrict__ acc,
                                                                   const double* __restrict__ view_vm2,
                                                                   const int32_t* __restrict__ view_idx, int n_views,
                                                                   int tiles, int phase, float* __restrict__ scal) {
     const int lane = threadIdx.x;
-    double vm2 = 0.0;  // sum of valid_mask^2 over the tiles no block visited = view totals - visited tiles
-    if (phase == 1) {
+    double vm2 = 0.0;  // sum of valid_mask^2 over the batch's views; acc[2] holds the listed pixels' corrections
+    if (phase == 1)
         for (int n = lane; n < n_views; n += 32) vm2 += view_vm2[(size_t)view_idx[n] * (tiles + 1) + tiles];
-        vm2 -= acc[7 * 32 + lane];
-    }
     const double a0 = warp_sum_f64(acc[0 * 32 + lane]), a1 = warp_sum_f64(acc[1 * 32 + lane]);
     const double a2 = warp_sum_f64(acc[2 * 32 + lane] + vm2);
     if (lane == 0) {
@@ -1161,8 +1131,7 @@ __global__ void __launch_bounds__(32) ham_finalize_scalars_kernel(const double* 
 }
 
 // view_vm2[view][tile] = sum of valid_mask^2 over the 16x16 tile, view_vm2[view][tiles] = sum over the view (constants
-// of the optimisation: valid_masks never change, mesh_sfs_optim.py:163).  The view total is the fp64 sum of the
-// tile sums, so "total - visited tiles" cancels exactly when every non-zero tile is visited.
+// of the optimisation: valid_masks never change, mesh_sfs_optim.py:163); the iteration only uses the view totals.
 __global__ void __launch_bounds__(256) ham_view_vm2_kernel(const float* __restrict__ valid_masks, int H, int W,
                                                            double* __restrict__ out) {
     __shared__ double red[8];
@@ -1175,7 +1144,7 @@ __global__ void __launch_bounds__(256) ham_view_vm2_kernel(const float* __restri
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const int tid = tile_tid();
+    const int tid = threadIdx.y * kTile + threadIdx.x;
     if ((tid & 31) == 0) red[tid >> 5] = s;
     __syncthreads();
     if (tid == 0) {
@@ -1184,13 +1153,13 @@ __global__ void __launch_bounds__(256) ham_view_vm2_kernel(const float* __restri
         out[(size_t)view * (tiles + 1) + blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
 }
-__global__ void ham_view_vm2_total_kernel(int tiles, double* __restrict__ out) {
+__global__ void __launch_bounds__(32) ham_view_vm2_total_kernel(int tiles, double* __restrict__ out) {
     double* row = out + (size_t)blockIdx.x * (tiles + 1);
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < tiles; i++) t += row[i];
-        row[tiles] = t;
-    }
+    double t = 0.0;
+    for (int i = threadIdx.x; i < tiles; i += 32) t += row[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) row[tiles] = t;
 }
 
 // zbuf -> rast_out for fmhr_ham_debug_export
@@ -1549,31 +1518,35 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         FMHR_LAUNCH_CHECK();
     }
     FMHR_STAGE_MARK();  // 3: coverage (transform + visibility)
+    static const int g_scan = persistent_blocks(ham_scan_kernel);
     static const int g_shade = persistent_blocks(ham_shade_kernel<PHASE>);
     static const int g_aa = persistent_blocks(ham_aa_loss_kernel<PHASE>);
     static const int g_bwd = persistent_blocks(ham_pixel_bwd_kernel<PHASE>);
-    const int pblock = kTile * kTile;  // 8 warps = 8 independent strip workers
-    ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt],
-                                                      ws.tcount[nxt], ws.abits, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.vg,
-                                                      ws.viewM, invW, invH, ws.tri4, ws.opp4, ws.vattr,
-                                                      b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W,
-                                                      ws.plane[0], ws.plane[1], ws.acc, ws.vlist, ws.vcount);
+    const int pblock = 256;  // 8 warps = 8 independent workers (no block barrier in the pixel passes)
+    const int rcap = (int)(P / 2), pcap = (int)(P / 2);
+    ham_scan_kernel<<<g_scan, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt], ws.tcount[nxt],
+                                               tiles_x, tiles_y, H, W, ws.clist, ws.ccount, ws.ringbits, ws.rlist,
+                                               ws.rcount, rcap, ws.status);
     FMHR_LAUNCH_CHECK();
-    FMHR_STAGE_MARK();  // 4: shade
+    ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH, ws.tri4,
+                                                      ws.opp4, ws.vattr, b->masks, b->sh_coeffs, b->view_idx, sh_idx, V,
+                                                      H, W, ws.plane[0], ws.plane[1], ws.acc);
+    FMHR_LAUNCH_CHECK();
+    FMHR_STAGE_MARK();  // 4: scan + shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(zcur, ws.alist, ws.acount, ws.cursors, tiles_x, tiles_y, ws.vg, ws.viewM, b->tri, b->opp, b->imgs, b->valid_masks,
-                                                     b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0],
-                                                     ws.plane[1], g0, g1, ws.acc, ws.gsh, b->view_vm2, dbg_image, dbg_mask,
-                                                     ws.plist_a, ws.plist_b, ws.pcount, (int)(P / 2), ws.status);
+    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(
+        ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp, b->imgs,
+        b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1, ws.acc, ws.gsh,
+        dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     if (!forward_only) {
-        ham_pair_bwd_kernel<PHASE><<<296, 128, 0, st>>>(ws.plist_a, ws.plist_b, ws.pcount, (int)(P / 2), zcur, ws.vg,
+        ham_pair_bwd_kernel<PHASE><<<296, 128, 0, st>>>(ws.plist_a, ws.plist_b, ws.pcount, pcap, zcur, ws.vg,
                                                        ws.viewM, V, H, W, ws.plane[0], g0, g1, ws.gdelta,
                                                        (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.vlist, ws.vcount, zcur, ws.vg, invW, invH, ws.viewM, ws.tri4,
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, ws.vg, invW, invH, ws.viewM, ws.tri4,
                                                               ws.vattr, b->sh_coeffs, sh_idx, V, H, W, g0, g1,
                                                               ws.gdelta, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
@@ -1597,6 +1570,7 @@ extern "C" int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers
         FMHR_CUDA(cudaMemsetAsync(ws.slot_region[i], 0, ws.slot_bytes, (cudaStream_t)stream));
     }
     FMHR_CUDA(cudaMemsetAsync(ws.common_region, 0, ws.common_bytes, (cudaStream_t)stream));
+    FMHR_CUDA(cudaMemsetAsync(ws.ringbits, 0, (P / 32 + 64) * 4, (cudaStream_t)stream));
     FMHR_CUDA(cudaMemsetAsync(ws.gdelta, 0, P * 16, (cudaStream_t)stream));
     return FMHR_OK;
 }
@@ -1680,7 +1654,13 @@ extern "C" int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_
     rc = ham_check_buffers(cfg, buf);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    // re-run the forward with export pointers (leaves `packed` holding forward-only partials)
+    // re-run the forward with export pointers (leaves `packed` holding forward-only partials); the antialias pass only
+    // visits covered pixels and their ring, every other pixel of the exported planes is zero
+    {
+        const size_t P = (size_t)cfg->n_views * cfg->H * cfg->W;
+        if (image) FMHR_CUDA(cudaMemsetAsync(image, 0, P * 3 * sizeof(float), st));
+        if (pred_mask) FMHR_CUDA(cudaMemsetAsync(pred_mask, 0, P * sizeof(float), st));
+    }
     rc = cfg->phase == 0 ? ham_render_impl<0>(cfg, buf, st, image, pred_mask, true)
                          : ham_render_impl<1>(cfg, buf, st, image, pred_mask, true);
     if (rc) return rc;

@@ -173,6 +173,31 @@ __device__ __forceinline__ bool aa_analyse(int tri0, float z0, int tri1, float z
     return aa_select_edge(g, t, d, from1, out);
 }
 
+// aa_analyse for callers that already know the chosen triangle's silhouette-candidate bits in its owning pixel's frame
+// (the fused path stores them in the z-buffer key during shading): only the three corners are projected, the three
+// wing vertices (three more gathers and IEEE divides) are not needed.  Decisions are identical to aa_analyse.
+template <class Proj>
+__device__ __forceinline__ bool aa_analyse_bits(int tri0, float z0, int bits0, int tri1, float z1, int bits1, int px, int py,
+                                                int d, const Proj proj, const int32_t* __restrict__ tri, int V, int T,
+                                                int H, int W, AAPair& out) {
+    int t = (tri0 >= 0) ? tri0 : tri1;
+    if (tri0 >= 0 && tri1 >= 0) t = (z0 < z1) ? tri0 : tri1;
+    const bool from1 = (t == tri1);
+    if (from1) { px += 1 - d; py += d; }
+    if (t < 0 || t >= T) return false;
+    AAGeom g;
+    g.bits = from1 ? bits1 : bits0;
+    if (g.bits == 0) return false;
+    g.v0 = __ldg(tri + 3 * t); g.v1 = __ldg(tri + 3 * t + 1); g.v2 = __ldg(tri + 3 * t + 2);
+    if ((unsigned)g.v0 >= (unsigned)V || (unsigned)g.v1 >= (unsigned)V || (unsigned)g.v2 >= (unsigned)V) return false;
+    const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
+    const float fx = xs(xa((float)px, 0.5f), xh), fy = xs(xa((float)py, 0.5f), yh);
+    proj(g.v0, fx, fy, g.x0, g.y0);
+    proj(g.v1, fx, fy, g.x1, g.y1);
+    proj(g.v2, fx, fy, g.x2, g.y2);
+    return aa_select_edge(g, t, d, from1, out);
+}
+
 // d(alpha)/d(clip position) of the two edge vertices, scaled by `dd` = d(loss)/d(alpha).
 // (px,py) is the pair's FIRST pixel, p1 / p2 the clip positions of the edge's vertices pr.i1 / pr.i2.  Returns the two
 // float4 gradients (x, y, 0, w).

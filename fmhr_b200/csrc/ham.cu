@@ -50,8 +50,7 @@ struct HamWs {
     float4* vattr;             // [V,2]  vattr[2i] = (unit normal, degenerate flag), vattr[2i+1] = (albedo b,g,r, 0)
     float4* raw4;              // [V]    (un-normalised normal sum N, |N|)
     float4* ys;                // [V,2]  ys[2i] = (yhat_v / deg, deg), ys[2i+1] = (yhat_a / deg, 0): Laplacian backward rows
-    int4* tri4;                // [T] (i0, i1, i2, -) padded copies of tri / opp, rebuilt by the prep kernel every step
-    int4* opp4;                // [T]
+    float4* trirec;            // [T,10] per-triangle record of the pixel passes (kTriRec floats), rebuilt every step
     float* gsh;                // [n_sh_rows,9] un-normalised SH gradients by SH row (phase A)
     double* acc;               // [8][32] (32-way spread against same-address atomics):
                                // 0 n_valid, 1 abs_sum, 2 mask_sq correction, 3 lap_v, 4 lap_a, 5 edge, 6 delta
@@ -109,8 +108,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take(V * 32); if (ws) ws->vattr = (float4*)p;
     p = take(V * 16); if (ws) ws->raw4 = (float4*)p;
     p = take(V * 32); if (ws) ws->ys = (float4*)p;
-    p = take((size_t)c->T * 16); if (ws) ws->tri4 = (int4*)p;
-    p = take((size_t)c->T * 16); if (ws) ws->opp4 = (int4*)p;
+    p = take((size_t)c->T * 160); if (ws) ws->trirec = (float4*)p;
     p = take((size_t)c->n_sh_rows * 9 * 4); if (ws) ws->gsh = (float*)p;
     p = take(8 * sizeof(float)); if (ws) ws->adam_sc = (float*)p;
     return off;
@@ -139,16 +137,13 @@ __device__ __forceinline__ F8 ld256(const float4* p) {
 
 // vertices = vertices_tmp + delta (mesh_sfs_optim.py:253).  The same launch re-arms the step's accumulators (the packed
 // gradient buffer = 3V float4, loss / work-list scratch, SH gradients) so the iteration has no memset nodes, and
-// rebuilds the padded int4 copies of tri / opp that the pixel passes gather with one 128-bit load.
+// computes the per-view combined world->clip matrices.
 __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __restrict__ vtmp,
                                                               const float* __restrict__ delta, int V,
                                                               float4* __restrict__ vg, float4* __restrict__ packed4,
                                                               uint32_t* __restrict__ z0, int n0,
                                                               uint32_t* __restrict__ z1, int n1,
                                                               uint32_t* __restrict__ z2, int n2,
-                                                              const int32_t* __restrict__ tri,
-                                                              const int32_t* __restrict__ opp, int T,
-                                                              int4* __restrict__ tri4, int4* __restrict__ opp4,
                                                               const float* __restrict__ w2cs,
                                                               const float* __restrict__ projs,
                                                               const int32_t* __restrict__ view_idx, int n_views,
@@ -160,10 +155,6 @@ __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __res
         const float* Pm = projs + (size_t)view_idx[n] * 16;
         viewM[i] = __fmaf_rn(Wm[4 * r + 3], Pm[12 + j], __fmaf_rn(Wm[4 * r + 2], Pm[8 + j],
                              __fmaf_rn(Wm[4 * r + 1], Pm[4 + j], __fmul_rn(Wm[4 * r], Pm[j]))));
-    }
-    if (i < T) {
-        tri4[i] = make_int4(tri[3 * (size_t)i], tri[3 * (size_t)i + 1], tri[3 * (size_t)i + 2], 0);
-        opp4[i] = make_int4(opp[3 * (size_t)i], opp[3 * (size_t)i + 1], opp[3 * (size_t)i + 2], 0);
     }
     if (i < V) {
         const size_t k = 3 * (size_t)i;
@@ -336,28 +327,26 @@ __global__ void __launch_bounds__(256, 4) ham_coverage_meshlet_kernel(
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4* pos_s = reinterpret_cast<float4*>(dyn_smem);
     int2* snap_s = reinterpret_cast<int2*>(pos_s + max_verts);
-    unsigned int* tbits = reinterpret_cast<unsigned int*>(snap_s + max_verts);  // (tiles_per_view + 31) / 32 words
+    const int words = (tiles_per_view + 31) >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int* tbits = reinterpret_cast<unsigned int*>(snap_s + max_verts);  // block-wide tile bitmap
     __shared__ uint2 cand[8][TPT * 32];  // per warp: the triangles whose bounding box holds a pixel centre
     __shared__ uint2 queue[8][kFragQueue];  // per warp: covered pixel centres (candidate index, py << 16 | px)
     __shared__ int qcount[8];
-    __shared__ float Ms[kViewM];
     const int m = blockIdx.x, n = blockIdx.y;
-    const int words = (tiles_per_view + 31) >> 5;
-    for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;  // visible after the vertex-phase barrier
     if (lane == 0) qcount[warp] = 0;
-    if (threadIdx.x < kViewM) Ms[threadIdx.x] = viewM[(size_t)n * kViewM + threadIdx.x];
+    const ViewM Mv = load_viewM(viewM + (size_t)n * kViewM);  // uniform loads: L1 broadcast
     // triangle records of this thread: issued before the vertex phase so their latency hides behind it
     uint2 rec[TPT];
     const uint2* recs = ml_tri2 + (size_t)m * (TPT * 256);
 #pragma unroll
     for (int k = 0; k < TPT; k++) rec[k] = __ldg(recs + k * 256 + threadIdx.x);
     const int vb = __ldg(ml_vptr + m), nv = __ldg(ml_vptr + m + 1) - vb;
-    __syncthreads();
     const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
         const float4 v = __ldg(vg + 2 * (size_t)__ldg(ml_verts + vb + i));
-        const float4 p = clip_from_world(Ms, v);
+        const float4 p = clip_from_world(Mv.m, v);
         pos_s[i] = p;
         int X = kSnapRejected, Y = 0;
         if (!snap_vertex(p, hw, hh, X, Y)) X = kSnapRejected;
@@ -408,33 +397,71 @@ __global__ void __launch_bounds__(256, 4) ham_coverage_meshlet_kernel(
 // ------------------------------------------------------------------------------------------------
 // pixel-domain helpers
 // ------------------------------------------------------------------------------------------------
+// Per-triangle record of the pixel passes (kTriRec floats = 160 B = five 32-byte sectors, rebuilt every iteration by
+// ham_trirec_kernel after the normals): everything a pixel of triangle t needs sits in ONE contiguous record, so the
+// shade pass issues 5 and the backward pass 4 independent 256-bit loads per pixel instead of 13 / 7 scattered sector
+// gathers through vertex indices (these passes are bound by L1 wavefronts, not by DRAM).
+//   [0..3]   i0, i1, i2 (int bits), flags (bit k: corner k has a degenerate normal; bit 4+k: wing k exists)
+//   [4..12]  world positions of the corners      [13..21] unit normals       [22..30] albedo (b,g,r)
+//   [31..39] world positions of the three opposite-wing vertices (antialias silhouette test; shade pass only)
+constexpr int kTriRec = 40;
+__global__ void __launch_bounds__(128) ham_trirec_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ opp,
+                                                         const float4* __restrict__ vg, const float4* __restrict__ vattr,
+                                                         int V, int T, float4* __restrict__ trirec) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    int iv[3], ov[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { iv[k] = __ldg(tri + 3 * (size_t)t + k); ov[k] = __ldg(opp + 3 * (size_t)t + k); }
+    float r[kTriRec];
+    int flags = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const bool ok = (unsigned)iv[k] < (unsigned)V;
+        const float4 p = ok ? vg[2 * (size_t)iv[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        F8 a;
+        a.a = make_float4(0.f, 0.f, 0.f, 0.f); a.b = a.a;
+        if (ok) a = ldg256(vattr + 2 * (size_t)iv[k]);
+        r[4 + 3 * k] = p.x; r[5 + 3 * k] = p.y; r[6 + 3 * k] = p.z;
+        r[13 + 3 * k] = a.a.x; r[14 + 3 * k] = a.a.y; r[15 + 3 * k] = a.a.z;
+        r[22 + 3 * k] = a.b.x; r[23 + 3 * k] = a.b.y; r[24 + 3 * k] = a.b.z;
+        if (a.a.w != 0.0f) flags |= 1 << k;
+        const bool wing = (unsigned)ov[k] < (unsigned)V;
+        const float4 w = wing ? vg[2 * (size_t)ov[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        r[31 + 3 * k] = w.x; r[32 + 3 * k] = w.y; r[33 + 3 * k] = w.z;
+        if (wing) flags |= 16 << k;
+    }
+    r[0] = __int_as_float(iv[0]); r[1] = __int_as_float(iv[1]); r[2] = __int_as_float(iv[2]); r[3] = __int_as_float(flags);
+    float4* out = trirec + (size_t)t * (kTriRec / 4);
+#pragma unroll
+    for (int k = 0; k < kTriRec / 4; k++) out[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+}
+
 struct PixTri {
-    int i0, i1, i2;
-    float4 p0, p1, p2;
+    int i0, i1, i2, flags;
+    float4 p0, p1, p2;  // clip positions
     float u, v;
     float3 n0, n1, n2;  // vertex normals
     float3 b0, b1, b2;  // vertex albedo
-    float d0, d1, d2;   // degenerate-normal flags
+    float w0x;          // first float of the wing block (lives in the record's fourth sector)
 };
 
-// Every per-pixel gather is a 128- or 256-bit load: the triangle's corners come from the padded int4 copy of `tri`,
-// world-space vertices are float4 (clip positions are recomputed from them), and normal + albedo of a vertex are one 32-byte record (vattr).  With 12-byte records each
-// of these was three scalar gathers, i.e. 32 L1 wavefronts per warp instruction, and the pixel passes are bound by the
-// number of L1 wavefronts (distinct sectors per warp instruction), not by DRAM.
-__device__ __forceinline__ void load_pixtri(int t, int px, int py, const float4* __restrict__ vg, const float* M,
-                                            const int4* __restrict__ tri4, const float4* __restrict__ vattr, float invW,
-                                            float invH, PixTri& q) {
-    const int4 ix = __ldg(tri4 + t);
-    q.i0 = ix.x; q.i1 = ix.y; q.i2 = ix.z;
-    q.p0 = clip_from_world(M, __ldg(vg + 2 * (size_t)q.i0));
-    q.p1 = clip_from_world(M, __ldg(vg + 2 * (size_t)q.i1));
-    q.p2 = clip_from_world(M, __ldg(vg + 2 * (size_t)q.i2));
-    const F8 a0 = ldg256(vattr + 2 * (size_t)q.i0), a1 = ldg256(vattr + 2 * (size_t)q.i1),
-             a2 = ldg256(vattr + 2 * (size_t)q.i2);
-    q.n0 = make_float3(a0.a.x, a0.a.y, a0.a.z); q.b0 = make_float3(a0.b.x, a0.b.y, a0.b.z);
-    q.n1 = make_float3(a1.a.x, a1.a.y, a1.a.z); q.b1 = make_float3(a1.b.x, a1.b.y, a1.b.z);
-    q.n2 = make_float3(a2.a.x, a2.a.y, a2.a.z); q.b2 = make_float3(a2.b.x, a2.b.y, a2.b.z);
-    q.d0 = a0.a.w; q.d1 = a1.a.w; q.d2 = a2.a.w;
+__device__ __forceinline__ void load_pixtri(int t, int px, int py, const float4* __restrict__ trirec, const float* M,
+                                            float invW, float invH, PixTri& q) {
+    const float4* rp = trirec + (size_t)t * (kTriRec / 4);
+    const F8 r0 = ldg256(rp), r1 = ldg256(rp + 2), r2 = ldg256(rp + 4), r3 = ldg256(rp + 6);
+    q.i0 = __float_as_int(r0.a.x); q.i1 = __float_as_int(r0.a.y); q.i2 = __float_as_int(r0.a.z);
+    q.flags = __float_as_int(r0.a.w);
+    q.p0 = clip_from_world(M, make_float4(r0.b.x, r0.b.y, r0.b.z, 0.f));
+    q.p1 = clip_from_world(M, make_float4(r0.b.w, r1.a.x, r1.a.y, 0.f));
+    q.p2 = clip_from_world(M, make_float4(r1.a.z, r1.a.w, r1.b.x, 0.f));
+    q.n0 = make_float3(r1.b.y, r1.b.z, r1.b.w);
+    q.n1 = make_float3(r2.a.x, r2.a.y, r2.a.z);
+    q.n2 = make_float3(r2.a.w, r2.b.x, r2.b.y);
+    q.b0 = make_float3(r2.b.z, r2.b.w, r3.a.x);
+    q.b1 = make_float3(r3.a.y, r3.a.z, r3.a.w);
+    q.b2 = make_float3(r3.b.x, r3.b.y, r3.b.z);
+    q.w0x = r3.b.w;
     const Bary b = bary_at(q.p0, q.p1, q.p2, px, py, invW, invH);
     q.u = b.u; q.v = b.v;
 }
@@ -504,24 +531,6 @@ __device__ __forceinline__ TileCtx tile_decode(uint32_t e, int nx, int ny) {
     return tc;
 }
 
-// Unit of work of the scan pass: one warp = one 16x2 strip of a 16x16 tile; warps are independent workers (no block
-// barrier anywhere in the pixel passes).
-struct Strip {
-    TileCtx tc;
-    int px, py;      // pixel position in the image
-};
-__device__ __forceinline__ bool next_strip(int& u, const uint32_t* __restrict__ list, int n_tiles, int tiles_x,
-                                           int tiles_y, Strip& st) {
-    // static striding at strip granularity: unit u, u + (grid warps), ...
-    if (u >= n_tiles * 8) return false;
-    const int lane = threadIdx.x & 31;
-    st.tc = tile_decode(__ldg(list + (u >> 3)), tiles_x, tiles_y);
-    const int strip = u & 7;
-    st.px = st.tc.bx * kTile + (lane & 15); st.py = st.tc.by * kTile + 2 * strip + (lane >> 4);
-    u += gridDim.x * 8;
-    return true;
-}
-
 // 32-way spread fp64 accumulators: shuffle-reduce inside the warp, one spread atomic per warp
 __device__ __forceinline__ void warp_acc_add(double* acc, int k, float v) {
     v = warp_sum(v);
@@ -584,7 +593,7 @@ __device__ __forceinline__ NbrKeys decode_key(unsigned long long key) {
 
 // ------------------------------------------------------------------------------------------------
 // scan: z-buffer tiles -> compact pixel lists.  Persistent over the tile list of the slot the coverage kernel just
-// filled; each warp walks 16x2 strips with coalesced key loads and
+// filled; each warp walks half tiles (16 x 8 pixels) with coalesced key loads and
 //   * appends every covered pixel as (pixel index, triangle id) to `clist` (per-warp shared buffer, one global atomic per
 //     ~200 pixels): the shade / antialias / backward passes then run with every lane busy and perfectly balanced;
 //   * appends every EMPTY pixel that touches a covered one to `rlist` (the only empty pixels antialiasing can blend
@@ -599,9 +608,13 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
                                                        int H, int W, uint2* __restrict__ clist, int* __restrict__ ccount,
                                                        uint32_t* __restrict__ ringbits, uint32_t* __restrict__ rlist,
                                                        int* __restrict__ rcount, int rcap, int* __restrict__ status) {
-    constexpr int kBuf = 224;
+    // unit of work = half a tile (16 x 8 pixels): a lane owns column (lane & 15) of rows (lane >> 4) + 2k, k = 0..3, so
+    // the four key loads (and then the sixteen neighbour-key loads) of a unit are independent and issued back to back
+    constexpr int kBuf = 288, kRBuf = 96;
     __shared__ uint2 cbuf[8][kBuf];
-    int nbuf = 0;  // warp-uniform
+    __shared__ uint32_t rbuf[8][kRBuf];  // ring pixels: appended to rlist with ONE global atomic per ~64 entries (a
+                                         // same-address atomicAdd per ring pixel serialised the kernel at the L2 slice)
+    int nbuf = 0, nring = 0;  // warp-uniform
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     auto flush = [&]() {
@@ -612,46 +625,92 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
         __syncwarp();
         nbuf = 0;
     };
-    Strip st;
-    const int u0 = blockIdx.x * 8 + wib;
+    auto flush_ring = [&]() {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(rcount, nring);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < nring; i += 32) {
+            if (base + i < rcap) rlist[base + i] = rbuf[wib][i];
+            else atomicOr(status, 2);
+        }
+        __syncwarp();
+        nring = 0;
+    };
+    const int u0 = blockIdx.x * 8 + wib, ustride = gridDim.x * 8;
+    const int lx = lane & 15, ly = lane >> 4;
     const int nd = *tcount_next;
-    int u = u0;
-    while (next_strip(u, tlist_next, nd, tiles_x, tiles_y, st))
-        if (st.px < W && st.py < H) zbuf_next[((size_t)st.tc.n * H + st.py) * W + st.px] = ZB_EMPTY;
+    for (int u = u0; u < 2 * nd; u += ustride) {
+        const TileCtx tc = tile_decode(__ldg(tlist_next + (u >> 1)), tiles_x, tiles_y);
+        const int px = tc.bx * kTile + lx, py0 = tc.by * kTile + (u & 1) * 8 + ly;
+        if (px < W) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (py0 + 2 * k < H) zbuf_next[((size_t)tc.n * H + py0 + 2 * k) * W + px] = ZB_EMPTY;
+        }
+    }
     const int nt = *tcount;
-    u = u0;
-    while (next_strip(u, tlist, nt, tiles_x, tiles_y, st)) {
-        const bool inb = st.px < W && st.py < H;
-        const size_t pix = ((size_t)st.tc.n * H + st.py) * W + st.px;
-        unsigned long long key = ZB_EMPTY;
-        if (inb) key = zbuf[pix];
-        const bool covered = key != ZB_EMPTY;
-        const unsigned m = __ballot_sync(0xffffffffu, covered);
-        if (m == 0u) continue;
-        if (covered) {
-            cbuf[wib][nbuf + __popc(m & lt)] = make_uint2((uint32_t)pix, (uint32_t)key & kTriMask);
-            // empty 4-neighbours of a covered pixel: the ring antialiasing can blend into
+    for (int u = u0; u < 2 * nt; u += ustride) {
+        const TileCtx tc = tile_decode(__ldg(tlist + (u >> 1)), tiles_x, tiles_y);
+        const int px = tc.bx * kTile + lx, py0 = tc.by * kTile + (u & 1) * 8 + ly;
+        const unsigned long long* zb = zbuf + (size_t)tc.n * H * W;
+        unsigned long long key[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int py = py0 + 2 * k;
+            key[k] = (px < W && py < H) ? zb[(size_t)py * W + px] : ZB_EMPTY;
+        }
+        unsigned m[4];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, key[k] != ZB_EMPTY); total += __popc(m[k]); }
+        if (total == 0) continue;
+        // neighbour keys of the covered pixels (a non-empty dummy where the neighbour is outside the view)
+        unsigned long long nk[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int py = py0 + 2 * k;
+            const bool cov = key[k] != ZB_EMPTY;
 #pragma unroll
             for (int d = 0; d < 4; d++) {
-                const int dx = d == 0 ? 1 : (d == 1 ? -1 : 0), dy = d == 2 ? 1 : (d == 3 ? -1 : 0);
-                const int qx = st.px + dx, qy = st.py + dy;
-                if (qx < 0 || qy < 0 || qx >= W || qy >= H) continue;
-                const size_t q = pix + dx + (long long)dy * W;
-                if (zbuf[q] != ZB_EMPTY) continue;
-                const uint32_t bit = 1u << (q & 31);
-                const uint32_t old = atomicOr(ringbits + (q >> 5), bit);
-                if (!(old & bit)) {
-                    const int slot = atomicAdd(rcount, 1);
-                    if (slot < rcap) rlist[slot] = (uint32_t)q;
-                    else atomicOr(status, 2);
+                const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py + (d == 2 ? 1 : (d == 3 ? -1 : 0));
+                nk[k][d] = (cov && qx >= 0 && qy >= 0 && qx < W && qy < H) ? zb[(size_t)qy * W + qx] : 0ull;
+            }
+        }
+        int off = nbuf;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int py = py0 + 2 * k;
+            if (key[k] != ZB_EMPTY) {
+                const uint32_t pix = (uint32_t)(((size_t)tc.n * H + py) * W + px);
+                cbuf[wib][off + __popc(m[k] & lt)] = make_uint2(pix, (uint32_t)key[k] & kTriMask);
+            }
+            off += __popc(m[k]);
+            // empty 4-neighbours of a covered pixel: the ring antialiasing can blend into (bitmap de-duplicates)
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                bool fresh = false;
+                uint32_t q = 0u;
+                if (nk[k][d] == ZB_EMPTY) {
+                    const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py + (d == 2 ? 1 : (d == 3 ? -1 : 0));
+                    q = (uint32_t)(((size_t)tc.n * H + qy) * W + qx);
+                    const uint32_t bit = 1u << (q & 31);
+                    fresh = !(atomicOr(ringbits + (q >> 5), bit) & bit);
+                }
+                const unsigned mr = __ballot_sync(0xffffffffu, fresh);
+                if (mr) {
+                    if (fresh) rbuf[wib][nring + __popc(mr & lt)] = q;
+                    nring += __popc(mr);
+                    __syncwarp();
+                    if (nring > kRBuf - 32) flush_ring();
                 }
             }
         }
-        nbuf += __popc(m);
+        nbuf = off;
         __syncwarp();
-        if (nbuf > kBuf - 32) flush();
+        if (nbuf > kBuf - 128) flush();
     }
     if (nbuf > 0) flush();
+    if (nring > 0) flush_ring();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -664,8 +723,7 @@ template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_shade_kernel(uint2* __restrict__ clist, const int* __restrict__ ccount,
                                                         unsigned long long* __restrict__ zbuf,
                                                         const float4* __restrict__ vg, const float* __restrict__ viewM,
-                                                        float invW, float invH, const int4* __restrict__ tri4,
-                                                        const int4* __restrict__ opp4, const float4* __restrict__ vattr,
+                                                        float invW, float invH, const float4* __restrict__ trirec,
                                                         const float* __restrict__ masks,
                                                         const float* __restrict__ sh_coeffs,
                                                         const int32_t* __restrict__ view_idx,
@@ -688,20 +746,21 @@ __global__ void __launch_bounds__(256, 4) ham_shade_kernel(uint2* __restrict__ c
         const int view = __ldg(view_idx + n);
         const bool valid = __ldg(masks + (size_t)view * hw + pa.rem) > 0.0f;
         PixTri q;
-        load_pixtri(t, px, py, vg, Mv, tri4, vattr, invW, invH, q);
+        load_pixtri(t, px, py, trirec, Mv, invW, invH, q);
         AAGeom g;
         g.bits = 0;
         {
-            // silhouette-candidate bits of this triangle in this pixel's frame; window coordinates of the corners come
-            // from the clip positions already in registers, those of the three wing vertices are gathered
-            const int4 ox = __ldg(opp4 + t);
+            // silhouette-candidate bits of this triangle in this pixel's frame: window coordinates of the corners come
+            // from the clip positions already in registers, the three wing vertices from the record's last sector
+            const F8 r4 = ldg256(trirec + (size_t)t * (kTriRec / 4) + 8);
             const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
-            float2 so0 = make_float2(0.f, 0.f), so1 = so0, so2 = so0;
-            if ((unsigned)ox.x < (unsigned)V) so0 = aa_window_xy(clip_from_world(Mv, __ldg(vg + 2 * (size_t)ox.x)), xh, yh);
-            if ((unsigned)ox.y < (unsigned)V) so1 = aa_window_xy(clip_from_world(Mv, __ldg(vg + 2 * (size_t)ox.y)), xh, yh);
-            if ((unsigned)ox.z < (unsigned)V) so2 = aa_window_xy(clip_from_world(Mv, __ldg(vg + 2 * (size_t)ox.z)), xh, yh);
+            const float2 so0 = aa_window_xy(clip_from_world(Mv, make_float4(q.w0x, r4.a.x, r4.a.y, 0.f)), xh, yh);
+            const float2 so1 = aa_window_xy(clip_from_world(Mv, make_float4(r4.a.z, r4.a.w, r4.b.x, 0.f)), xh, yh);
+            const float2 so2 = aa_window_xy(clip_from_world(Mv, make_float4(r4.b.y, r4.b.z, r4.b.w, 0.f)), xh, yh);
+            // aa_triangle_geom_win ignores a wing whose vertex id is outside [0, V)
+            const int o0 = (q.flags & 16) ? 0 : -1, o1 = (q.flags & 32) ? 0 : -1, o2 = (q.flags & 64) ? 0 : -1;
             aa_triangle_geom_win(q.i0, q.i1, q.i2, aa_window_xy(q.p0, xh, yh), aa_window_xy(q.p1, xh, yh),
-                                 aa_window_xy(q.p2, xh, yh), ox.x, ox.y, ox.z, so0, so1, so2, px, py, V, H, W, g);
+                                 aa_window_xy(q.p2, xh, yh), o0, o1, o2, so0, so1, so2, px, py, V, H, W, g);
         }
         const float3 m = interp3(q.n0, q.n1, q.n2, q);
         const float3 a = interp3(q.b0, q.b1, q.b2, q);
@@ -763,7 +822,25 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
     __shared__ int q_n_s[8];
     __shared__ float blend_s[8][32][NC];
     __shared__ uint32_t spix_s[8][32];
+    // recorded pairs wait in shared memory and reach plist with ONE global atomic per >= 32 records (a same-address
+    // atomicAdd per pair serialised the kernel at the L2 slice)
+    constexpr int kPBuf = 64;
+    __shared__ uint4 pbuf_a[8][kPBuf];
+    __shared__ uint32_t pbuf_b[8][kPBuf];
+    int npb = 0;  // warp-uniform
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    auto flush_pairs = [&]() {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(pcount, npb);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < npb; i += 32) {
+            if (base + i < pcap) { plist_a[base + i] = pbuf_a[wib][i]; plist_b[base + i] = pbuf_b[wib][i]; }
+            else atomicOr(status, 1);
+        }
+        __syncwarp();
+        npb = 0;
+    };
     uint32_t* q_items = q_items_s[wib];
     int* q_n = &q_n_s[wib];
     float (*blend)[NC] = blend_s[wib];
@@ -805,29 +882,40 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
 #pragma unroll
             for (int c = 0; c < NC; c++) blend[lane][c] = 0.0f;
             __syncwarp();
-            for (int x = lane; x < nq; x += 32) {
-                const uint32_t item = q_items[x];
-                const int L = (int)(item >> 2), which = (int)(item & 3u), d = which & 1;
-                const PixAddr qa = pix_decode(spix[L], H, W);
-                // first pixel of the pair
-                const int qx = which < 2 ? qa.px : qa.px - (1 - d), qy = which < 2 ? qa.py : qa.py - d;
-                const size_t qbase = (size_t)qa.n * hw;
-                const int r0 = qy * W + qx, r1 = r0 + (d ? W : 1);
-                const NbrKeys k0 = decode_key(zbuf[qbase + r0]), k1 = decode_key(zbuf[qbase + r1]);
-                const AAProjWorld proj{vg, viewM + (size_t)qa.n * kViewM, 0.5f * (float)W, 0.5f * (float)H};
+            for (int x0 = 0; x0 < nq; x0 += 32) {  // warp-uniform trip count: the record buffer is appended by ballot
+                const int x = x0 + lane;
+                bool found = false, record = false;
                 AAPair pr;
-                if (!aa_analyse(k0.tri, k0.zw, k1.tri, k1.zw, qx, qy, d, proj, tri, opp, V, T, H, W, pr)) continue;
-                if (which < 2) {  // seen from the pair's first pixel: record it for the backward pass
-                    const int slot = atomicAdd(pcount, 1);
-                    if (slot < pcap) {
+                int L = 0, which = 0, d = 0, r0 = 0, r1 = 0;
+                size_t qbase = 0;
+                NbrKeys k0 = decode_key(ZB_EMPTY), k1 = k0;
+                if (x < nq) {
+                    const uint32_t item = q_items[x];
+                    L = (int)(item >> 2); which = (int)(item & 3u); d = which & 1;
+                    const PixAddr qa = pix_decode(spix[L], H, W);
+                    // first pixel of the pair
+                    const int qx = which < 2 ? qa.px : qa.px - (1 - d), qy = which < 2 ? qa.py : qa.py - d;
+                    qbase = (size_t)qa.n * hw;
+                    r0 = qy * W + qx; r1 = r0 + (d ? W : 1);
+                    k0 = decode_key(zbuf[qbase + r0]); k1 = decode_key(zbuf[qbase + r1]);
+                    const AAProjWorld proj{vg, viewM + (size_t)qa.n * kViewM, 0.5f * (float)W, 0.5f * (float)H};
+                    found = aa_analyse_bits(k0.tri, k0.zw, k0.bits, k1.tri, k1.zw, k1.bits, qx, qy, d, proj, tri, V, T, H, W, pr);
+                    record = found && which < 2;  // seen from the pair's first pixel: record it for the backward pass
+                }
+                const unsigned mrec = __ballot_sync(0xffffffffu, record);
+                if (mrec) {
+                    if (record) {
+                        const int slot = npb + __popc(mrec & lt);
                         const uint32_t flags = (uint32_t)d | ((uint32_t)pr.from1 << 1) | ((uint32_t)pr.clamped << 2) |
                                                ((uint32_t)pr.di << 3);
-                        plist_a[slot] = make_uint4((uint32_t)(qbase + r0), flags, __float_as_uint(pr.alpha), (uint32_t)pr.i1);
-                        plist_b[slot] = (uint32_t)pr.i2;
-                    } else {
-                        atomicOr(status, 1);
+                        pbuf_a[wib][slot] = make_uint4((uint32_t)(qbase + r0), flags, __float_as_uint(pr.alpha), (uint32_t)pr.i1);
+                        pbuf_b[wib][slot] = (uint32_t)pr.i2;
                     }
+                    npb += __popc(mrec);
+                    __syncwarp();
+                    if (npb > kPBuf - 32) flush_pairs();
                 }
+                if (!found) continue;
                 const bool recv_is_self = (which < 2) == (pr.alpha > 0.0f);
                 if (!recv_is_self) continue;  // the other pixel's own item delivers it
                 // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
@@ -926,6 +1014,7 @@ __global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
         }
         __syncwarp();  // blend[] / q_items / q_n / spix of this warp are rewritten by its next batch
     }
+    if (npb > 0) flush_pairs();
     warp_acc_add(acc, 1, abs_acc);
     if (PHASE == 1) {
         msk_acc = warp_sum_f64(msk_acc);
@@ -1003,8 +1092,7 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
 template <int PHASE>
 __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
     const uint2* __restrict__ clist, const int* __restrict__ ccount,
-    const float4* __restrict__ vg, float invW, float invH, const float* __restrict__ viewM,
-    const int4* __restrict__ tri4, const float4* __restrict__ vattr,
+    const float4* __restrict__ trirec, float invW, float invH, const float* __restrict__ viewM,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, int V, int H, int W,
     const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ gdelta,
     float4* __restrict__ G) {
@@ -1032,7 +1120,7 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
             g1.x += gd.x; g1.y += gd.y; g1.z += gd.z;
         }
         PixTri q;
-        load_pixtri(tself, px, py, vg, M, tri4, vattr, invW, invH, q);
+        load_pixtri(tself, px, py, trirec, M, invW, invH, q);
         const float w = 1.0f - q.u - q.v;
         if (PHASE == 0) {
             // only the albedo attribute is trainable: interpolate bwd
@@ -1090,12 +1178,12 @@ __global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
         const float wt[3] = {q.u, q.v, w};
         const float3 wp[3] = {w0, w1, w2};
         const float3 nn[3] = {q.n0, q.n1, q.n2};
-        const float dg[3] = {q.d0, q.d1, q.d2};
+        const bool dg[3] = {(q.flags & 1) != 0, (q.flags & 2) != 0, (q.flags & 4) != 0};
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const float3 gk = make_float3(wt[k] * gm.x, wt[k] * gm.y, wt[k] * gm.z);  // d/d(vertex normal attribute)
             float a1, a2;
-            if (dg[k] == 0.0f) {
+            if (!dg[k]) {
                 float3 t1, t2;
                 tangent_frame(nn[k], t1, t2);
                 a1 = t1.x * gk.x + t1.y * gk.y + t1.z * gk.z;
@@ -1483,20 +1571,25 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     // zeroed by the prep kernel: packed, loss accumulators + dilated work list (common), the work list of the slot
     // rasterised this step, SH gradients (phase A)
     const int n0 = (int)(ws.common_bytes / 4), n1 = (int)(ws.slot_bytes / 4), n2 = PHASE == 0 ? cfg->n_sh_rows * 9 : 0;
-    const int prep_threads = max(max(max(3 * V + 1, T), n * kViewM), max(n0, max(n1, n2)));
+    const int prep_threads = max(max(3 * V + 1, n * kViewM), max(n0, max(n1, n2)));
     ham_vertex_prep_kernel<<<cdiv(prep_threads, 256), 256, 0, st>>>(
         b->vertices_tmp, b->delta, V, ws.vg, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
-        (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->tri, b->opp, T, ws.tri4, ws.opp4,
-        b->w2cs, b->projs, b->view_idx, n, ws.viewM);
+        (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->w2cs, b->projs, b->view_idx, n, ws.viewM);
     FMHR_LAUNCH_CHECK();
     ham_normals_kernel<<<cdiv((long long)V * 8, 256), 256, 0, st>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
                                                                     ws.vattr, ws.raw4);
+    FMHR_LAUNCH_CHECK();
+    ham_trirec_kernel<<<cdiv(T, 128), 128, 0, st>>>(b->tri, b->opp, ws.vg, ws.vattr, V, T, ws.trirec);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
     FMHR_STAGE_MARK();  // 2: (the clip transform is fused into the coverage kernel)
     {
         const int tiles_pv = tiles_x * tiles_y;
         const size_t smem = (size_t)b->ml_max_verts * 24 + (size_t)((tiles_pv + 31) / 32) * sizeof(unsigned int);
+        if (smem > 96 * 1024) {
+            set_error("fmhr_ham_step_render: %d tiles per view exceed the coverage kernel's shared-memory bitmaps", tiles_pv);
+            return FMHR_EUNSUPPORTED;
+        }
         const dim3 grid(b->n_meshlets, n);
         const uint2* tri2 = (const uint2*)b->ml_tri2;
 #define FMHR_COVERAGE(TPT)                                                                                             \
@@ -1528,9 +1621,9 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
                                                tiles_x, tiles_y, H, W, ws.clist, ws.ccount, ws.ringbits, ws.rlist,
                                                ws.rcount, rcap, ws.status);
     FMHR_LAUNCH_CHECK();
-    ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH, ws.tri4,
-                                                      ws.opp4, ws.vattr, b->masks, b->sh_coeffs, b->view_idx, sh_idx, V,
-                                                      H, W, ws.plane[0], ws.plane[1], ws.acc);
+    ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH, ws.trirec,
+                                                      b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, H, W, ws.plane[0],
+                                                      ws.plane[1], ws.acc);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 4: scan + shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
@@ -1546,9 +1639,9 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
                                                        ws.viewM, V, H, W, ws.plane[0], g0, g1, ws.gdelta,
                                                        (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, ws.vg, invW, invH, ws.viewM, ws.tri4,
-                                                              ws.vattr, b->sh_coeffs, sh_idx, V, H, W, g0, g1,
-                                                              ws.gdelta, (float4*)b->packed);
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, ws.trirec, invW, invH, ws.viewM,
+                                                              b->sh_coeffs, sh_idx, V, H, W, g0, g1, ws.gdelta,
+                                                              (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
     }
     ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,

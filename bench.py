@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "HAM iters/sec (fwd+bwd, views x res)"
 UNIT = "iters/s"
-KERNELS_PER_STEP = 11  # prep, normals, coverage, scan, shade, antialias_loss, pair_bwd, pixel_bwd, finalize, update x2
+KERNELS_PER_STEP = 13  # prep, normals, regulariser, trirec, coverage, scan, shade, antialias_loss, pair_bwd, pixel_bwd, finalize, normal_grad, adam
 
 
 def b_alg_bytes(n, H, W, V, F, E):

@@ -127,6 +127,11 @@ __device__ __forceinline__ F8 ldg256(const float4* p) {
     return r;
 }
 // same, for records written earlier in the SAME kernel launch sequence but read through the coherent path
+__device__ __forceinline__ void st256(float4* p, const float* r) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]),
+                 "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ F8 ld256(const float4* p) {
     F8 r;
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(128) ham_trirec_kernel(const int32_t* __restri
     r[0] = __int_as_float(iv[0]); r[1] = __int_as_float(iv[1]); r[2] = __int_as_float(iv[2]); r[3] = __int_as_float(flags);
     float4* out = trirec + (size_t)t * (kTriRec / 4);
 #pragma unroll
-    for (int k = 0; k < kTriRec / 4; k++) out[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+    for (int k = 0; k < kTriRec / 8; k++) st256(out + 2 * k, r + 8 * k);  // five full-sector stores
 }
 
 struct PixTri {
@@ -1291,12 +1296,14 @@ __device__ __forceinline__ float sub_sum(float v) {
     return v;
 }
 
-// pass 1: Laplacian forward for vertices and albedo, edge/delta losses, projector of the normal backward, Adam scalars
-__global__ void __launch_bounds__(256) ham_update_pass1_kernel(
-    fmhr_ham_config cfg, float4* __restrict__ vg, const float* __restrict__ delta, const float4* __restrict__ vattr,
+// Regulariser forward (Laplacian for vertices and albedo, edge / delta losses) and the step's Adam scalars.  Depends only
+// on the vertices and albedo, not on the rendering: fmhr_ham_step_render runs it on a side stream, concurrently with the
+// coverage kernel, so it is off the iteration's critical path.
+__global__ void __launch_bounds__(256) ham_regulariser_kernel(
+    fmhr_ham_config cfg, const float4* __restrict__ vg, const float* __restrict__ delta, const float4* __restrict__ vattr,
     const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
-    const int32_t* __restrict__ v2v_idx, const float4* __restrict__ raw4, const float4* __restrict__ packed4,
-    float4* __restrict__ ys, double* __restrict__ acc, int32_t* __restrict__ adam_step, float* __restrict__ adam_sc) {
+    const int32_t* __restrict__ v2v_idx, float4* __restrict__ ys, double* __restrict__ acc,
+    int32_t* __restrict__ adam_step, float* __restrict__ adam_sc) {
     __shared__ float red[4][8];
     const int V = cfg.V;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
@@ -1331,7 +1338,7 @@ __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
     sa.x = sub_sum(sa.x); sa.y = sub_sum(sa.y); sa.z = sub_sum(sa.z);
     if (i < V && sub == 0) {
         const float invd = (deg > 0) ? 1.0f / (float)deg : 0.0f;
-        const float4 at = __ldg(vattr + 2 * (size_t)i + 1), nrm = __ldg(vattr + 2 * (size_t)i);
+        const float4 at = __ldg(vattr + 2 * (size_t)i + 1);
         sv = make_float3(sv.x * invd - vi.x, sv.y * invd - vi.y, sv.z * invd - vi.z);
         sa = make_float3(sa.x * invd - at.x, sa.y * invd - at.y, sa.z * invd - at.z);
         lv = sqrtf(sv.x * sv.x + sv.y * sv.y + sv.z * sv.z);
@@ -1342,21 +1349,6 @@ __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
         ys[2 * (size_t)i + 1] = make_float4(sa.x * ia, sa.y * ia, sa.z * ia, 0.f);
         const float* dp = delta + 3 * (size_t)i;
         ld = dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2];
-        // normal backward, step 1: through the normalisation (un-normalised photometric scale; linear, scaled later)
-        const float4 ga = packed4[2 * (size_t)i], gb = packed4[2 * (size_t)i + 1];
-        const float4 N = raw4[i];
-        float3 r;
-        if (nrm.w == 0.0f) {  // |N| > 1e-6: tangential part of the gradient / |N|
-            float3 t1, t2;
-            tangent_frame(make_float3(nrm.x, nrm.y, nrm.z), t1, t2);
-            const float inv = 1.0f / N.w;
-            r = make_float3((t1.x * ga.w + t2.x * gb.x) * inv, (t1.y * ga.w + t2.y * gb.x) * inv,
-                            (t1.z * ga.w + t2.z * gb.x) * inv);
-        } else {
-            const float gz = packed4[2 * (size_t)V + i].w;
-            r = make_float3(ga.w * 1e6f, gb.x * 1e6f, gz * 1e6f);
-        }
-        vg[2 * (size_t)i + 1] = make_float4(r.x, r.y, r.z, 0.f);
     }
     lv = warp_sum(lv); la = warp_sum(la); le = warp_sum(le); ld = warp_sum(ld);
     if ((threadIdx.x & 31) == 0) {
@@ -1383,6 +1375,31 @@ __global__ void __launch_bounds__(256) ham_update_pass1_kernel(
         __syncwarp(0x3fu);  // both lanes of a parameter have read the counter before it advances
         if ((q & 1) == 0) adam_step[k] = t;
     }
+}
+
+// Normal backward, step 1: gradient through the per-vertex normalisation (un-normalised photometric scale; linear, scaled
+// in the Adam pass), from the (all-reduced) tangential accumulators.  One thread per vertex.
+__global__ void __launch_bounds__(256) ham_normal_grad_kernel(int V, float4* __restrict__ vg,
+                                                              const float4* __restrict__ vattr,
+                                                              const float4* __restrict__ raw4,
+                                                              const float4* __restrict__ packed4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const float4 ga = packed4[2 * (size_t)i], gb = packed4[2 * (size_t)i + 1];
+    const float4 nrm = __ldg(vattr + 2 * (size_t)i);
+    const float4 N = raw4[i];
+    float3 r;
+    if (nrm.w == 0.0f) {  // |N| > 1e-6: tangential part of the gradient / |N|
+        float3 t1, t2;
+        tangent_frame(make_float3(nrm.x, nrm.y, nrm.z), t1, t2);
+        const float inv = 1.0f / N.w;
+        r = make_float3((t1.x * ga.w + t2.x * gb.x) * inv, (t1.y * ga.w + t2.y * gb.x) * inv,
+                        (t1.z * ga.w + t2.z * gb.x) * inv);
+    } else {
+        const float gz = packed4[2 * (size_t)V + i].w;
+        r = make_float3(ga.w * 1e6f, gb.x * 1e6f, gz * 1e6f);
+    }
+    vg[2 * (size_t)i + 1] = make_float4(r.x, r.y, r.z, 0.f);
 }
 
 __device__ __forceinline__ float adam_update(float p, float g, float* m, float* v, float b1, float b2, float eps,
@@ -1554,6 +1571,29 @@ static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers*
     return FMHR_OK;
 }
 
+// Side stream for work that is independent of the rendering chain (forked / joined with events, so it is captured into
+// the same CUDA graph when the caller's stream is being captured).
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int dev = -1;
+};
+static int side_stream(SideStream** out) {
+    static SideStream side[64];
+    int dev = 0;
+    FMHR_CUDA(cudaGetDevice(&dev));
+    FMHR_CHECK_ARG(dev >= 0 && dev < 64);
+    SideStream& s = side[dev];
+    if (s.dev != dev) {
+        FMHR_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        s.dev = dev;
+    }
+    *out = &s;
+    return FMHR_OK;
+}
+
 template <int PHASE>
 static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b, cudaStream_t st, float* dbg_image,
                            float* dbg_mask, bool forward_only) {
@@ -1579,6 +1619,24 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     ham_normals_kernel<<<cdiv((long long)V * 8, 256), 256, 0, st>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
                                                                     ws.vattr, ws.raw4);
     FMHR_LAUNCH_CHECK();
+    // regulariser forward + Adam scalars: independent of the rendering -> side stream, joined at the end of this call
+    // (inline when the stages are being timed, skipped by the forward-only inspection path: it advances the step counters)
+    SideStream* side = nullptr;
+    if (!forward_only) {
+        cudaStream_t rs = st;
+        if (!g_timer) {
+            int rc_ = side_stream(&side);
+            if (rc_) return rc_;
+            FMHR_CUDA(cudaEventRecord(side->fork, st));
+            FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+            rs = side->st;
+        }
+        ham_regulariser_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, rs>>>(
+            *cfg, ws.vg, b->delta, ws.vattr, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.acc,
+            b->adam_step, ws.adam_sc);
+        FMHR_LAUNCH_CHECK();
+        if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
+    }
     ham_trirec_kernel<<<cdiv(T, 128), 128, 0, st>>>(b->tri, b->opp, ws.vg, ws.vattr, V, T, ws.trirec);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
@@ -1647,6 +1705,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,
                                                   b->packed + 12 * (size_t)V);
     FMHR_LAUNCH_CHECK();
+    if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
     return FMHR_OK;
 }
@@ -1698,9 +1757,7 @@ extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_b
     HamWs ws;
     ham_layout(cfg, (char*)buf->workspace, &ws);
     const int V = cfg->V;
-    ham_update_pass1_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
-        *cfg, ws.vg, buf->delta, ws.vattr, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx, ws.raw4,
-        (const float4*)buf->packed, ws.ys, ws.acc, buf->adam_step, ws.adam_sc);
+    ham_normal_grad_kernel<<<cdiv(V, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, (const float4*)buf->packed);
     FMHR_LAUNCH_CHECK();
     ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
         *cfg, ws.vg, buf->delta, buf->albedo, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,

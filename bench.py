@@ -40,19 +40,30 @@ def b_alg_bytes(n, H, W, V, F, E):
     return 68 * P + 204 * V + 12 * F + 8 * (2 * E + V) + 4 * (V + 1) + 164 * n
 
 
-# Algorithmic HBM bytes per launch of each fused kernel (DESIGN.md "Kernels"): per pixel P, per vertex V, per view n
+# Algorithmic HBM bytes per launch of each stage of the fused iteration (DESIGN.md "Kernels"), dense model of SURVEY.md
+# 8(d): per pixel P, per vertex V, per view n.  (The kernels only touch covered pixels, so their DRAM traffic is lower.)
 def stage_bytes(stage, n, H, W, V, F):
     P = n * H * W
     return {
-        "clears": 8 * P,                                   # z-buffer reset
-        "vertex_normals": 36 * V + 12 * F + 24 * V,        # read vtmp, delta, faces; write vertices, normals
-        "clip_transform": 12 * V + 16 * n * V,             # write [n,V,4]
-        "coverage": 16 * n * V + 12 * F,                   # read clip positions + faces (atomics hit L2)
+        "clears": 0,                                       # no clear pass: the scan kernel resets dirty tiles
+        "vertex_normals": 36 * V + 12 * F + 24 * V + 160 * F,   # vertices, normals, per-triangle records
+        "clip_transform": 0,                               # fused into the coverage kernel
+        "coverage": 16 * n * V + 12 * F + 8 * P,           # vertices per view + faces + z-buffer keys
         "shade": 8 * P + 4 * P + 16 * P,                   # read z-buffer + mask, write colour plane
         "antialias_loss": 8 * P + 16 * P + 12 * P + 4 * P + 16 * P,  # zbuf, colour, img, valid_mask, write pixel grads
         "pixel_backward": 8 * P + 16 * P + 16 * P,         # zbuf, colour, pixel grads (vertex atomics hit L2)
         "update_adam": 204 * V + 12 * F,
     }[stage]
+
+
+def measured_traffic():
+    """DRAM bytes per iteration (dram__bytes_read.sum + dram__bytes_write.sum over the iteration's kernels) from the
+    committed ncu capture of this command, profiles/r1_traffic.json (written by tools/ncu_launch_table.py)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -278,20 +289,30 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0, N=1 timing)
+    # ---------------------------------------------------------------- roofline (rank 0)
+    # the unit of the path is one whole iteration (one CUDA-graph launch of 13 kernels) and its
+    # algorithmic bytes B_alg are the single figure for roofline.achieved; the dominant kernel is reported beside it.
     peak, peak_src = measured_peak_gbs()
-    roof = None
-    stages = None
+    balg = b_alg_bytes(n, H, W, V, F, E)
+    iter_ach = balg / (ms_per_step * 1e-3) / 1e9
+    traffic = measured_traffic()
+    roof = {"bound": "hbm", "kernel": "fused HAM iteration (%d kernels, one graph launch)" % KERNELS_PER_STEP,
+            "achieved": iter_ach, "peak": peak, "unit": "GB/s", "frac": iter_ach / peak,
+            "traffic": traffic["iteration_bytes"] if traffic else None, "algorithmic_bytes": balg,
+            "iter_ms": ms_per_step, "peak_source": peak_src,
+            "note": "SURVEY.md 8(d): B_alg / t_iter; B_alg is the dense model (68 B per pixel of every view), the kernels "
+                    "only visit covered pixels so measured DRAM traffic is far below it - the iteration is bound by "
+                    "instruction issue (coverage) and gather latency (pixel passes), not by HBM"}
     if world == 1:
         stages = opt.stage_times(views, repeats=10)
         top = max(stages, key=lambda k: stages[k])
         byts = stage_bytes(top, n, H, W, V, F)
         ach = byts / (stages[top] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes": byts, "kernel_ms": stages[top], "peak_source": peak_src,
-                "stage_ms": stages}
-    balg = b_alg_bytes(n, H, W, V, F, E)
-    iter_ach = balg / (ms_per_step * 1e-3) / 1e9
+        roof["dominant_kernel"] = {"kernel": top, "kernel_ms": stages[top], "algorithmic_bytes": byts, "achieved": ach,
+                                   "frac": ach / peak,
+                                   "traffic": (traffic or {}).get("kernels", {}).get(top),
+                                   "share_of_step": stages[top] / sum(stages.values())}
+        roof["stage_ms"] = stages
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -316,8 +337,6 @@ def main():
         "clocks": clocks,
         "e2e": e2e,
         "roofline": roof,
-        "roofline_iteration": {"algorithmic_bytes": balg, "achieved": iter_ach, "peak": peak, "unit": "GB/s",
-                               "frac": iter_ach / peak, "note": "SURVEY.md 8(d) B_alg / t_iter (north-star figure)"},
         "cpu_baseline": cpu,
         "losses_last": {k: v for k, v in zip(["sfs", "lap", "albedo", "mask", "edge", "delta", "n_valid", "total"], losses)},
     }

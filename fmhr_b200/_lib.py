@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libfmhr_b200.so")
+SO_PATH = os.environ.get("FMHR_B200_LIB") or os.path.join(_HERE, "libfmhr_b200.so")  # override: tuning builds only
 _lib = None
 
 c_p = ctypes.c_void_p

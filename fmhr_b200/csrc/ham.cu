@@ -12,6 +12,21 @@
 // shaded colour and one float4 pixel-gradient (two of each in phase A, where 6 channels are antialiased).
 #include "aa_rule.cuh"
 
+// resident 256-thread blocks per SM the pixel / coverage kernels are compiled for (register budget = 65536 / 256 / N);
+// measured on B200 (tools/run_variants.sh): shade and backward are faster spill-free at 3, coverage at 5
+#ifndef FMHR_LB_COVERAGE
+#define FMHR_LB_COVERAGE 5
+#endif
+#ifndef FMHR_LB_SHADE
+#define FMHR_LB_SHADE 3
+#endif
+#ifndef FMHR_LB_AA
+#define FMHR_LB_AA 4
+#endif
+#ifndef FMHR_LB_BWD
+#define FMHR_LB_BWD 3
+#endif
+
 namespace fmhr {
 
 // Per-view combined matrix, written once per step by the prep kernel (row-vector convention of get_data.py:96-97):
@@ -324,7 +339,7 @@ __device__ __forceinline__ void ml_candidate(uint2 rec, int e, const float4* pos
 }
 
 template <int TPT>
-__global__ void __launch_bounds__(256, 4) ham_coverage_meshlet_kernel(
+__global__ void __launch_bounds__(256, FMHR_LB_COVERAGE) ham_coverage_meshlet_kernel(
     const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ ml_vptr,
     const int32_t* __restrict__ ml_verts, const uint2* __restrict__ ml_tri2, int max_verts, int H, int W, float invW,
     float invH, unsigned long long* __restrict__ zbuf, uint32_t* __restrict__ gbits, uint32_t* __restrict__ glist,
@@ -725,7 +740,7 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
 // flag (one 32-bit RED), and records the valid flag in the list entry for the backward pass.
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
-__global__ void __launch_bounds__(256, 4) ham_shade_kernel(uint2* __restrict__ clist, const int* __restrict__ ccount,
+__global__ void __launch_bounds__(256, FMHR_LB_SHADE) ham_shade_kernel(uint2* __restrict__ clist, const int* __restrict__ ccount,
                                                         unsigned long long* __restrict__ zbuf,
                                                         const float4* __restrict__ vg, const float* __restrict__ viewM,
                                                         float invW, float invH, const float4* __restrict__ trirec,
@@ -812,7 +827,7 @@ __device__ __forceinline__ bool pair_needs_analysis(const NbrKeys& k0, const Nbr
 }
 
 template <int PHASE>
-__global__ void __launch_bounds__(256, 4) ham_aa_loss_kernel(
+__global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     const uint2* __restrict__ clist, const int* __restrict__ ccount, const uint32_t* __restrict__ rlist,
     const int* __restrict__ rcount, int rcap, uint32_t* __restrict__ ringbits, const unsigned long long* __restrict__ zbuf,
     const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ tri,
@@ -1095,7 +1110,7 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
 // rasterize backward, 9 float4 red.global.add per pixel into the world-space per-vertex accumulators.
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
-__global__ void __launch_bounds__(256, 4) ham_pixel_bwd_kernel(
+__global__ void __launch_bounds__(256, FMHR_LB_BWD) ham_pixel_bwd_kernel(
     const uint2* __restrict__ clist, const int* __restrict__ ccount,
     const float4* __restrict__ trirec, float invW, float invH, const float* __restrict__ viewM,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, int V, int H, int W,

@@ -5,6 +5,7 @@ NCCL all-reduce of the packed gradient buffer between them (views shard across r
 State names follow the reference: vertices_tmp, delta, albedo [1,V,3], sh_coeffs [num,9], valid_masks, ...
 """
 import ctypes
+import os
 
 import torch
 
@@ -68,7 +69,7 @@ class HamOptimizer:
         self._zb_layout = None
         self._zb_slot = 0
 
-    MESHLET_TRIS = 1024
+    MESHLET_TRIS = int(os.environ.get("FMHR_MESHLET_TRIS", "1024"))  # 256 / 512 / 1024 (tuning override)
 
     def _build_meshlets(self):
         """Setup: Morton-ordered meshlets for the coverage kernel (fmhr_meshlets_build_host, host-side, once per mesh)."""

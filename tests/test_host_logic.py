@@ -107,3 +107,66 @@ def test_two_rank_gloo_reduction_matches_single_process(tmp_path):
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
     assert rel(got["g_delta"], st.delta.grad) < 1e-4
     assert rel(got["g_albedo"], st.albedo.grad[0]) < 1e-4
+
+
+def _build_meshlets(tri, verts, tpm, V):
+    import ctypes
+    import numpy as np
+    from fmhr_b200 import _build, _lib
+    _build.build()
+    lib = _lib.load()
+    hp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+    T = tri.shape[0]
+    nm, nr, mv = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    call = lambda a, b, c: lib.fmhr_meshlets_build_host(hp(tri), hp(verts), V, T, tpm, ctypes.byref(nm), ctypes.byref(nr),
+                                                         ctypes.byref(mv), hp(a), hp(b), hp(c))
+    assert call(None, None, None) == 0
+    vptr = np.zeros(nm.value + 1, dtype=np.int32)
+    vrefs = np.zeros(nr.value, dtype=np.int32)
+    tri2 = np.zeros((nm.value * tpm, 2), dtype=np.uint32)
+    assert call(vptr, vrefs, tri2) == 0
+    return nm.value, mv.value, vptr, vrefs, tri2
+
+
+@pytest.mark.parametrize("tpm", [256, 1024])
+def test_meshlets_partition_the_mesh(tpm):
+    """fmhr_meshlets_build_host (host-side setup of the coverage kernel): every triangle appears in exactly one meshlet,
+    its 10-bit local indices decode to its own vertices in the original corner order, no meshlet exceeds 1024 vertices,
+    and the result does not depend on whether vertex positions (Morton order) are supplied."""
+    import numpy as np
+    from fmhr_b200 import synth
+    v, f = synth.base_hand_mesh()
+    v, f = synth.subdivide_loop(v, f, 2)
+    tri = np.ascontiguousarray(f, dtype=np.int32)
+    verts = np.ascontiguousarray(v, dtype=np.float32)
+    for use_pos in (True, False):
+        M, mx, vptr, vrefs, tri2 = _build_meshlets(tri, verts if use_pos else None, tpm, verts.shape[0])
+        assert 0 < mx <= 1024 and vptr[0] == 0 and vptr[-1] == vrefs.shape[0]
+        assert M >= (tri.shape[0] + tpm - 1) // tpm
+        seen = np.zeros(tri.shape[0], dtype=np.int64)
+        for m in range(M):
+            loc = vrefs[vptr[m]:vptr[m + 1]]
+            assert loc.shape[0] <= 1024 and np.unique(loc).shape[0] == loc.shape[0]
+            rec = tri2[m * tpm:(m + 1) * tpm]
+            real = rec[:, 0] != 0xFFFFFFFF
+            assert np.all(rec[~real, 1] == 0xFFFFFFFF)      # padding is all ones
+            tid = rec[real, 1].astype(np.int64)
+            seen[tid] += 1
+            packed = rec[real, 0]
+            corners = np.stack([packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023], axis=1).astype(np.int64)
+            assert corners.max() < loc.shape[0]
+            assert np.array_equal(loc[corners], tri[tid])
+        assert np.all(seen == 1)
+
+
+def test_meshlets_reject_bad_input():
+    import ctypes
+    import numpy as np
+    from fmhr_b200 import _build, _lib
+    _build.build()
+    lib = _lib.load()
+    tri = np.array([[0, 1, 5]], dtype=np.int32)   # vertex 5 out of range for V = 3
+    nm, nr, mv = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.fmhr_meshlets_build_host(ctypes.c_void_p(tri.ctypes.data), None, 3, 1, 1024, ctypes.byref(nm), ctypes.byref(nr),
+                                      ctypes.byref(mv), None, None, None)
+    assert rc == -1 and b"invalid argument" in lib.fmhr_last_error_string()

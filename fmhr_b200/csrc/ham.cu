@@ -1586,13 +1586,38 @@ static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers*
     return FMHR_OK;
 }
 
+// 8-bit host batch -> the float planes the kernels read: img = u8 / 255 (one IEEE divide, bit-identical to the loader's
+// `img.astype(float32) / 255`, get_data.py:77-90), mask = u8 > 127 (get_data.py:78-79).  Four bytes per thread.
+__global__ void __launch_bounds__(256) ham_u8_to_f32_kernel(const uchar4* __restrict__ src, size_t n_img4, size_t n_all4,
+                                                            float4* __restrict__ imgs, float4* __restrict__ masks) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_all4) return;
+    const uchar4 b = src[i];
+    if (i < n_img4) {
+        imgs[i] = make_float4(__fdiv_rn((float)b.x, 255.0f), __fdiv_rn((float)b.y, 255.0f), __fdiv_rn((float)b.z, 255.0f),
+                              __fdiv_rn((float)b.w, 255.0f));
+    } else {
+        masks[i - n_img4] = make_float4(b.x > 127 ? 1.0f : 0.0f, b.y > 127 ? 1.0f : 0.0f, b.z > 127 ? 1.0f : 0.0f,
+                                        b.w > 127 ? 1.0f : 0.0f);
+    }
+}
+
 // Side stream for work that is independent of the rendering chain (forked / joined with events, so it is captured into
 // the same CUDA graph when the caller's stream is being captured).
 struct SideStream {
     cudaStream_t st = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t copy = nullptr;              // host-batch uploads of fmhr_ham_step_host_u8
+    cudaEvent_t copy_fork = nullptr, ready = nullptr;
     int dev = -1;
 };
+// Host batch in flight (fmhr_ham_step_host_u8): the render chain converts it right before the first kernel that reads
+// images / masks, so the PCIe transfer overlaps vertex prep, coverage and scan.
+struct PendingInputs {
+    const uint8_t* staging = nullptr;  // device: [n*H*W*3 image bytes | n*H*W mask bytes]
+    cudaEvent_t ready = nullptr;
+};
+static thread_local PendingInputs g_pending;
 static int side_stream(SideStream** out) {
     static SideStream side[64];
     int dev = 0;
@@ -1603,6 +1628,9 @@ static int side_stream(SideStream** out) {
         FMHR_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        FMHR_CUDA(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.copy_fork, cudaEventDisableTiming));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
         s.dev = dev;
     }
     *out = &s;
@@ -1684,6 +1712,14 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         FMHR_LAUNCH_CHECK();
     }
     FMHR_STAGE_MARK();  // 3: coverage (transform + visibility)
+    if (g_pending.staging) {  // host batch of fmhr_ham_step_host_u8: first use of images / masks is the shade pass
+        FMHR_CUDA(cudaStreamWaitEvent(st, g_pending.ready, 0));
+        const size_t n_img4 = P * 3 / 4, n_all4 = n_img4 + P / 4;
+        ham_u8_to_f32_kernel<<<cdiv((long long)n_all4, 256), 256, 0, st>>>((const uchar4*)g_pending.staging, n_img4, n_all4,
+                                                                          (float4*)b->imgs, (float4*)b->masks);
+        FMHR_LAUNCH_CHECK();
+        g_pending.staging = nullptr;
+    }
     static const int g_scan = persistent_blocks(ham_scan_kernel);
     static const int g_shade = persistent_blocks(ham_shade_kernel<PHASE>);
     static const int g_aa = persistent_blocks(ham_aa_loss_kernel<PHASE>);
@@ -1864,6 +1900,46 @@ extern "C" int fmhr_ham_step_host(const fmhr_ham_config* cfg, const fmhr_ham_buf
     rc = fmhr_ham_prepare_views(buf->valid_masks, (int)n, cfg->H, cfg->W, (double*)buf->view_vm2, stream);
     if (rc) return rc;
     rc = fmhr_ham_step_render(cfg, buf, stream);
+    if (rc) return rc;
+    rc = fmhr_ham_step_update(cfg, buf, stream);
+    if (rc) return rc;
+    FMHR_CUDA(cudaMemcpyAsync(losses_host, buf->losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return FMHR_OK;
+}
+
+extern "C" size_t fmhr_ham_host_u8_staging_bytes(const fmhr_ham_config* cfg) {
+    if (!cfg || check_cfg(cfg) != FMHR_OK) return 0;
+    return (size_t)cfg->n_views * cfg->H * cfg->W * 4;
+}
+
+extern "C" int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const uint8_t* imgs_host,
+                                     const uint8_t* masks_host, const float* w2cs_host, const float* projs_host,
+                                     void* staging, float* losses_host, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(imgs_host && masks_host && w2cs_host && projs_host && staging && losses_host);
+    const size_t P = (size_t)cfg->n_views * cfg->H * cfg->W;
+    FMHR_CHECK_ARG(P % 4 == 0 && ((uintptr_t)staging & 15) == 0 && ((uintptr_t)buf->imgs & 15) == 0 &&
+                   ((uintptr_t)buf->masks & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    SideStream* side = nullptr;
+    rc = side_stream(&side);
+    if (rc) return rc;
+    // image / mask bytes travel on the copy stream while the geometry half of the iteration runs on `st`
+    FMHR_CUDA(cudaEventRecord(side->copy_fork, st));  // earlier work on `st` may still read the staging buffer
+    FMHR_CUDA(cudaStreamWaitEvent(side->copy, side->copy_fork, 0));
+    FMHR_CUDA(cudaMemcpyAsync(staging, imgs_host, P * 3, cudaMemcpyHostToDevice, side->copy));
+    FMHR_CUDA(cudaMemcpyAsync((char*)staging + P * 3, masks_host, P, cudaMemcpyHostToDevice, side->copy));
+    FMHR_CUDA(cudaEventRecord(side->ready, side->copy));
+    const size_t n = cfg->n_views;
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->w2cs, w2cs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    g_pending.staging = (const uint8_t*)staging;
+    g_pending.ready = side->ready;
+    rc = fmhr_ham_step_render(cfg, buf, stream);
+    g_pending.staging = nullptr;
     if (rc) return rc;
     rc = fmhr_ham_step_update(cfg, buf, stream);
     if (rc) return rc;

@@ -345,6 +345,8 @@ class HostStreamingStepper:
         self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.h2d_bytes = 4 * (n_views * H * W * 5 + n_views * 32)
         self.d2h_bytes = 32
+        self.staging = None
+        self.h2d_bytes_u8 = n_views * H * W * 4 + 4 * n_views * 32
 
     def step_phase_b(self, h_imgs, h_masks, h_valid, h_w2cs, h_projs, sh_rows, albedo_weight=None):
         """h_* are pinned host tensors holding this step's n_views rows; sh_rows = int32 device tensor of SH rows."""
@@ -363,4 +365,38 @@ class HostStreamingStepper:
             o._prepare_zbuf(cfg, buf)
             check(o.lib.fmhr_ham_step_host(ctypes.byref(cfg), ctypes.byref(buf), ptr(h_imgs), ptr(h_masks), ptr(h_valid),
                                            ptr(h_w2cs), ptr(h_projs), ptr(self.losses_host), stream()), "ham_step_host")
+        return self.losses_host
+
+    def set_resident_valid_masks(self, valid_masks):
+        """valid_masks of the step's views stay on the device for the u8 path (the reference derives them on the GPU,
+        mesh_sfs_optim.py:146-163); also prepares their mask-loss constants."""
+        o = self.opt
+        self.d_valid.copy_(valid_masks)
+        with torch.cuda.device(o.device):
+            check(o.lib.fmhr_ham_prepare_views(ptr(self.d_valid), self.n, o.H, o.W, ptr(self.d_vm2), stream()),
+                  "ham_prepare_views")
+
+    def step_phase_b_u8(self, h_imgs_u8, h_masks_u8, h_w2cs, h_projs, sh_rows, albedo_weight=None):
+        """Host batch in its native 8-bit form: h_imgs_u8 [n,H,W,3] uint8 (img = u8/255), h_masks_u8 [n,H,W] uint8
+        (mask = u8 > 127), cameras float32 - all pinned; valid_masks resident (set_resident_valid_masks)."""
+        o = self.opt
+        for t, dt in ((h_imgs_u8, torch.uint8), (h_masks_u8, torch.uint8), (h_w2cs, torch.float32), (h_projs, torch.float32)):
+            if t.is_cuda or not t.is_contiguous() or t.dtype != dt or not t.is_pinned():
+                raise RuntimeError("HostStreamingStepper: host batches must be pinned, contiguous CPU tensors (uint8 images / "
+                                   "masks, float32 cameras)")
+        if o.phase != 1:
+            o.begin_phase_b()
+        if o.world > 1:
+            raise RuntimeError("HostStreamingStepper is single-process; use HamOptimizer under torch.distributed")
+        cfg = o._cfg(self.n, 1, albedo_weight)
+        buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows,
+                         self.d_vm2)
+        if self.staging is None:
+            self.staging = torch.empty(o.lib.fmhr_ham_host_u8_staging_bytes(ctypes.byref(cfg)), dtype=torch.uint8,
+                                       device=o.device)
+        with torch.cuda.device(o.device):
+            o._prepare_zbuf(cfg, buf)
+            check(o.lib.fmhr_ham_step_host_u8(ctypes.byref(cfg), ctypes.byref(buf), ptr(h_imgs_u8), ptr(h_masks_u8),
+                                              ptr(h_w2cs), ptr(h_projs), ptr(self.staging), ptr(self.losses_host),
+                                              stream()), "ham_step_host_u8")
         return self.losses_host

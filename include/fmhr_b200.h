@@ -229,6 +229,17 @@ int fmhr_ham_step_host(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, 
                        const float* masks_host, const float* valid_masks_host, const float* w2cs_host,
                        const float* projs_host, float* losses_host, fmhr_stream_t stream);
 
+/* Same, with the batch in its native 8-bit form (what the reference's loader reads from disk, get_data.py:77-90):
+ * imgs_host [n,H,W,3] uint8 (BGR, img = u8 / 255), masks_host [n,H,W] uint8 (mask = u8 > 127), pinned HOST memory;
+ * `staging` = fmhr_ham_host_u8_staging_bytes(cfg) bytes of DEVICE memory.  The bytes travel on an internal copy stream
+ * while vertex prep / coverage / scan run, are converted into buf->imgs / buf->masks right before the shade pass, and
+ * the 8-float loss record is copied back to losses_host.  valid_masks / view_vm2 stay resident (the reference derives
+ * valid_masks on the device, mesh_sfs_optim.py:146-163).  Requires n*H*W % 4 == 0. */
+size_t fmhr_ham_host_u8_staging_bytes(const fmhr_ham_config* cfg);
+int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const uint8_t* imgs_host,
+                          const uint8_t* masks_host, const float* w2cs_host, const float* projs_host, void* staging,
+                          float* losses_host, fmhr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -264,6 +264,41 @@ def test_host_streaming_step_matches_resident(scene):
         stepper.step_phase_b(h[0], h[1], h[2], h[3].transpose(1, 2), h[4], views)
 
 
+def test_host_streaming_u8_step_matches_resident(scene):
+    """fmhr_ham_step_host_u8: 8-bit host images / masks uploaded on the copy stream while the geometry kernels run,
+    converted on the device (img = u8 / 255 exactly as the loader's float32 division, mask = u8 > 127); must equal
+    the resident path fed with the same quantised images."""
+    import copy
+    from fmhr_b200.ham import HostStreamingStepper
+    n, H, W = scene["imgs"].shape[0], scene["imgs"].shape[1], scene["imgs"].shape[2]
+    if (n * H * W) % 4:
+        pytest.skip("u8 path needs n*H*W % 4 == 0")
+    img_u8 = np.clip(np.rint(np.asarray(scene["imgs"], dtype=np.float64) * 255.0), 0, 255).astype(np.uint8)
+    msk_u8 = (np.asarray(scene["masks"]) > 0).astype(np.uint8) * 255
+    q = copy.copy(scene)
+    q["imgs"] = img_u8.astype(np.float32) / np.float32(255.0)
+    q["masks"] = (msk_u8 > 127).astype(np.float32)
+    a = _make_opt(q, debug=False)
+    b = _make_opt(q, debug=False)
+    views = torch.arange(n, dtype=torch.int32, device="cuda")
+    stepper = HostStreamingStepper(b, n)
+    stepper.set_resident_valid_masks(b.valid_masks)
+    stepper.d_imgs.fill_(7.0)   # poison: the step must overwrite the staging planes
+    stepper.d_masks.fill_(7.0)
+    pin = lambda x, dt: torch.tensor(x, dtype=dt).contiguous().pin_memory()
+    h = [pin(img_u8, torch.uint8), pin(msk_u8, torch.uint8), pin(scene["w2cs"], torch.float32), pin(scene["projs"], torch.float32)]
+    for _ in range(3):
+        la = a.step_phase_b(views).cpu()
+        stepper.step_phase_b_u8(*h, views)
+        torch.cuda.synchronize()
+        assert torch.allclose(la, stepper.losses_host, rtol=1e-4, atol=1e-6), (la, stepper.losses_host)
+    assert torch.equal(stepper.d_imgs.cpu(), torch.tensor(q["imgs"]))
+    assert torch.equal(stepper.d_masks.cpu(), torch.tensor(q["masks"]))
+    assert torch.allclose(a.delta, b.delta, atol=2e-2 * scene["conf"]["lr"])
+    with pytest.raises(RuntimeError):
+        stepper.step_phase_b_u8(h[0].float().pin_memory(), h[1], h[2], h[3], views)
+
+
 def test_two_hands_and_full_size_properties():
     """BASELINE.json configs 2 and 4 at their full shapes, through size-independent properties: the fused path's
     coverage equals the stand-alone rasterize op on the same clip positions (bit-exact, GPU vs GPU), is deterministic

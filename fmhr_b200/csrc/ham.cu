@@ -752,12 +752,13 @@ __global__ void __launch_bounds__(256, FMHR_LB_SHADE) ham_shade_kernel(uint2* __
                                                         double* __restrict__ acc) {
     const int nc = *ccount;
     const int hw = H * W;
-    const int lane = threadIdx.x & 31;
     float nvalid = 0.0f;
-    for (int e0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; e0 < nc; e0 += gridDim.x * blockDim.x) {
-        const int e = e0 + lane;
-        if (e >= nc) continue;
-        const uint2 ent = clist[e];
+    // the NEXT list entry is loaded before this entry's gather chain starts (one dependent level less per iteration)
+    const int e_first = blockIdx.x * blockDim.x + threadIdx.x, e_stride = gridDim.x * blockDim.x;
+    uint2 ent_next = e_first < nc ? clist[e_first] : make_uint2(0u, 0u);
+    for (int e = e_first; e < nc; e += e_stride) {
+        const uint2 ent = ent_next;
+        if (e + e_stride < nc) ent_next = clist[e + e_stride];
         const size_t pix = ent.x;
         const int t = (int)ent.y;
         const PixAddr pa = pix_decode(ent.x, H, W);
@@ -869,17 +870,16 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     const int hw = H * W;
     float abs_acc = 0.0f;
     double msk_acc = 0.0;  // fp64: the corrections cancel against the fp64 view totals (exactly 0 when pred == valid)
-    for (int e0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; e0 < total; e0 += gridDim.x * blockDim.x) {
+    auto list_pixel = [&](int e) -> uint32_t { return e < nc ? clist[e].x : rlist[e - nc]; };
+    const int e_stride = gridDim.x * blockDim.x;
+    uint32_t pix_next = 0u;  // the NEXT list entry is loaded before this batch's key / analysis chain starts
+    if ((int)(blockIdx.x * blockDim.x + threadIdx.x) < total) pix_next = list_pixel(blockIdx.x * blockDim.x + threadIdx.x);
+    for (int e0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; e0 < total; e0 += e_stride) {
         const int e = e0 + lane;
         const bool active = e < total;
-        uint32_t pix32 = 0u;
-        if (active) {
-            if (e < nc) pix32 = clist[e].x;
-            else {
-                pix32 = rlist[e - nc];
-                atomicAnd(ringbits + (pix32 >> 5), ~(1u << (pix32 & 31)));  // the bitmap cleans itself for the next step
-            }
-        }
+        const uint32_t pix32 = active ? pix_next : 0u;
+        if (e + e_stride < total) pix_next = list_pixel(e + e_stride);
+        if (active && e >= nc) atomicAnd(ringbits + (pix32 >> 5), ~(1u << (pix32 & 31)));  // the bitmap cleans itself
         const PixAddr pa = pix_decode(pix32, H, W);
         const int n = pa.n, px = pa.px, py = pa.py, rem = pa.rem;
         const size_t base = (size_t)n * hw;
@@ -1117,8 +1117,11 @@ __global__ void __launch_bounds__(256, FMHR_LB_BWD) ham_pixel_bwd_kernel(
     const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ gdelta,
     float4* __restrict__ G) {
     const int nv = *ccount;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += gridDim.x * blockDim.x) {
-        const uint2 ent = clist[e];  // (pixel, triangle | valid << 31) from the scan / shade passes
+    const int e_first = blockIdx.x * blockDim.x + threadIdx.x, e_stride = gridDim.x * blockDim.x;
+    uint2 ent_next = e_first < nv ? clist[e_first] : make_uint2(0u, 0u);
+    for (int e = e_first; e < nv; e += e_stride) {
+        const uint2 ent = ent_next;  // (pixel, triangle | valid << 31) from the scan / shade passes; next one prefetched
+        if (e + e_stride < nv) ent_next = clist[e + e_stride];
         // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286);
         // phase A back-propagates through every covered pixel's albedo
         if (PHASE == 1 && !(ent.y >> 31)) continue;

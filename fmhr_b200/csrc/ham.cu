@@ -186,18 +186,18 @@ __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __res
     if (i < n2) z2[i] = 0u;
 }
 
-// Area-weighted vertex normals (models/utils.py:508-548, corner form of the face normal), 8 lanes per vertex over the
+// Area-weighted vertex normals (models/utils.py:508-548, corner form of the face normal), 4 lanes per vertex over the
 // vertex->face CSR; writes the packed attribute records of the pixel passes.
-__global__ void __launch_bounds__(256) ham_normals_kernel(const float4* __restrict__ vg, const float* __restrict__ albedo,
+__global__ void __launch_bounds__(256, 6) ham_normals_kernel(const float4* __restrict__ vg, const float* __restrict__ albedo,
                                                           const int32_t* __restrict__ v2f_ptr,
                                                           const int2* __restrict__ v2f_nbr, int V,
                                                           float4* __restrict__ vattr, float4* __restrict__ raw4) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, sub = threadIdx.x & 3;  // 4 lanes per vertex: ONE wave of blocks
     float ax = 0.f, ay = 0.f, az = 0.f;
     if (i < V) {
         const int b = __ldg(v2f_ptr + i), e = __ldg(v2f_ptr + i + 1);
         const float4 pk = vg[2 * (size_t)i];
-        for (int j = b + sub; j < e; j += 8) {
+        for (int j = b + sub; j < e; j += 4) {
             const int2 nb = __ldg(v2f_nbr + j);
             const float4 pa = vg[2 * (size_t)nb.x], pb = vg[2 * (size_t)nb.y];
             const float ux = pa.x - pk.x, uy = pa.y - pk.y, uz = pa.z - pk.z;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) ham_normals_kernel(const float4* __restri
         }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = 2; o > 0; o >>= 1) {
         ax += __shfl_xor_sync(0xffffffffu, ax, o);
         ay += __shfl_xor_sync(0xffffffffu, ay, o);
         az += __shfl_xor_sync(0xffffffffu, az, o);
@@ -1317,7 +1317,7 @@ __device__ __forceinline__ float sub_sum(float v) {
 // Regulariser forward (Laplacian for vertices and albedo, edge / delta losses) and the step's Adam scalars.  Depends only
 // on the vertices and albedo, not on the rendering: fmhr_ham_step_render runs it on a side stream, concurrently with the
 // coverage kernel, so it is off the iteration's critical path.
-__global__ void __launch_bounds__(256) ham_regulariser_kernel(
+__global__ void __launch_bounds__(256, 6) ham_regulariser_kernel(
     fmhr_ham_config cfg, const float4* __restrict__ vg, const float* __restrict__ delta, const float4* __restrict__ vattr,
     const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
     const int32_t* __restrict__ v2v_idx, float4* __restrict__ ys, double* __restrict__ acc,
@@ -1434,7 +1434,7 @@ __device__ __forceinline__ float pick3(const float3 v, int c) { return c == 0 ? 
 
 // pass 2: gather every gradient term per vertex (kLPV lanes each), then Adam on delta (phase B) and albedo with the
 // components of the vertex spread over lanes 0..2 (coalesced Adam state traffic)
-__global__ void __launch_bounds__(256) ham_update_pass2_kernel(
+__global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
     fmhr_ham_config cfg, const float4* __restrict__ vg, float* __restrict__ delta, float* __restrict__ albedo,
     const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
     const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed, const float4* __restrict__ ys,
@@ -1662,7 +1662,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         b->vertices_tmp, b->delta, V, ws.vg, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
         (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->w2cs, b->projs, b->view_idx, n, ws.viewM);
     FMHR_LAUNCH_CHECK();
-    ham_normals_kernel<<<cdiv((long long)V * 8, 256), 256, 0, st>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
+    ham_normals_kernel<<<cdiv((long long)V * 4, 256), 256, 0, st>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
                                                                     ws.vattr, ws.raw4);
     FMHR_LAUNCH_CHECK();
     // regulariser forward + Adam scalars: independent of the rendering -> side stream, joined at the end of this call

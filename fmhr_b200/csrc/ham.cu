@@ -556,6 +556,23 @@ __device__ __forceinline__ void warp_acc_add(double* acc, int k, float v) {
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(acc + k * 32 + ((blockIdx.x * 8 + (threadIdx.x >> 5)) & 31), (double)v);
 }
+// Final flush of per-warp work-list buffers: the 8 warps of a block reserve their slots with ONE global atomic (every
+// warp of the grid reaching its last flush at the same time meant ~5,000 same-address atomics queued at one L2 slice).
+// Must be called by all threads of the block; returns this warp's base slot.
+__device__ __forceinline__ int block_reserve(int* counter, int n_warp, int* s_cnt /* [10] shared */) {
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) s_cnt[wib] = n_warp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+        s_cnt[8] = tot > 0 ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    const int base = s_cnt[8] + s_cnt[wib];
+    __syncthreads();  // s_cnt may be reused by the next reservation
+    return base;
+}
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -729,8 +746,18 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
         __syncwarp();
         if (nbuf > kBuf - 128) flush();
     }
-    if (nbuf > 0) flush();
-    if (nring > 0) flush_ring();
+    __shared__ int s_cnt[10];
+    {
+        const int base = block_reserve(ccount, nbuf, s_cnt);
+        for (int i = lane; i < nbuf; i += 32) clist[base + i] = cbuf[wib][i];
+    }
+    {
+        const int base = block_reserve(rcount, nring, s_cnt);
+        for (int i = lane; i < nring; i += 32) {
+            if (base + i < rcap) rlist[base + i] = rbuf[wib][i];
+            else atomicOr(status, 2);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1034,7 +1061,14 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
         }
         __syncwarp();  // blend[] / q_items / q_n / spix of this warp are rewritten by its next batch
     }
-    if (npb > 0) flush_pairs();
+    {
+        __shared__ int s_cnt[10];
+        const int base = block_reserve(pcount, npb, s_cnt);
+        for (int i = lane; i < npb; i += 32) {
+            if (base + i < pcap) { plist_a[base + i] = pbuf_a[wib][i]; plist_b[base + i] = pbuf_b[wib][i]; }
+            else atomicOr(status, 1);
+        }
+    }
     warp_acc_add(acc, 1, abs_acc);
     if (PHASE == 1) {
         msk_acc = warp_sum_f64(msk_acc);

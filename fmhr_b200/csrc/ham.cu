@@ -1643,7 +1643,7 @@ __global__ void __launch_bounds__(256) ham_u8_to_f32_kernel(const uchar4* __rest
 // the same CUDA graph when the caller's stream is being captured).
 struct SideStream {
     cudaStream_t st = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, records = nullptr;
     cudaStream_t copy = nullptr;              // host-batch uploads of fmhr_ham_step_host_u8
     cudaEvent_t copy_fork = nullptr, ready = nullptr;
     int dev = -1;
@@ -1665,6 +1665,7 @@ static int side_stream(SideStream** out) {
         FMHR_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.records, cudaEventDisableTiming));
         FMHR_CUDA(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.copy_fork, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
@@ -1696,29 +1697,32 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         b->vertices_tmp, b->delta, V, ws.vg, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
         (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->w2cs, b->projs, b->view_idx, n, ws.viewM);
     FMHR_LAUNCH_CHECK();
-    ham_normals_kernel<<<cdiv((long long)V * 4, 256), 256, 0, st>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
+    // The coverage + scan kernels only need the vertices and the view matrices (prep).  Normals -> per-triangle records
+    // (needed from the shade pass on) and the regulariser forward + Adam scalars (needed by the update) run on a side
+    // stream concurrently with them: latency-bound vertex kernels under the issue-bound coverage kernel.  Inline when the
+    // stages are being timed; the regulariser is skipped by the forward-only inspection path (it advances the counters).
+    SideStream* side = nullptr;
+    cudaStream_t vs = st;
+    if (!g_timer) {
+        int rc_ = side_stream(&side);
+        if (rc_) return rc_;
+        FMHR_CUDA(cudaEventRecord(side->fork, st));
+        FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+        vs = side->st;
+    }
+    ham_normals_kernel<<<cdiv((long long)V * 4, 256), 256, 0, vs>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
                                                                     ws.vattr, ws.raw4);
     FMHR_LAUNCH_CHECK();
-    // regulariser forward + Adam scalars: independent of the rendering -> side stream, joined at the end of this call
-    // (inline when the stages are being timed, skipped by the forward-only inspection path: it advances the step counters)
-    SideStream* side = nullptr;
+    ham_trirec_kernel<<<cdiv(T, 128), 128, 0, vs>>>(b->tri, b->opp, ws.vg, ws.vattr, V, T, ws.trirec);
+    FMHR_LAUNCH_CHECK();
+    if (side) FMHR_CUDA(cudaEventRecord(side->records, side->st));
     if (!forward_only) {
-        cudaStream_t rs = st;
-        if (!g_timer) {
-            int rc_ = side_stream(&side);
-            if (rc_) return rc_;
-            FMHR_CUDA(cudaEventRecord(side->fork, st));
-            FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
-            rs = side->st;
-        }
-        ham_regulariser_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, rs>>>(
+        ham_regulariser_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, vs>>>(
             *cfg, ws.vg, b->delta, ws.vattr, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.acc,
             b->adam_step, ws.adam_sc);
         FMHR_LAUNCH_CHECK();
-        if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
     }
-    ham_trirec_kernel<<<cdiv(T, 128), 128, 0, st>>>(b->tri, b->opp, ws.vg, ws.vattr, V, T, ws.trirec);
-    FMHR_LAUNCH_CHECK();
+    if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
     FMHR_STAGE_MARK();  // 2: (the clip transform is fused into the coverage kernel)
     {
@@ -1767,6 +1771,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
                                                tiles_x, tiles_y, H, W, ws.clist, ws.ccount, ws.ringbits, ws.rlist,
                                                ws.rcount, rcap, ws.status);
     FMHR_LAUNCH_CHECK();
+    if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->records, 0));  // normals + triangle records are ready
     ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH, ws.trirec,
                                                       b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, H, W, ws.plane[0],
                                                       ws.plane[1], ws.acc);

@@ -46,7 +46,6 @@ struct HamWs {
     uint32_t* ringbits;        // [P/32] de-duplication bitmap of rlist; zero outside an iteration
     uint4* plist_a;            // [P/2] blending pixel pairs found by the antialias pass: (pixel0, flags, alpha, i1)
     uint32_t* plist_b;         // [P/2]                                                    i2
-    float4* gdelta;            // [P]   pair terms of d(loss)/d(pre-antialias value); zero outside an iteration
     int* ccount;               // inside common_region (zeroed every step)
     int* rcount;
     int* pcount;
@@ -102,7 +101,6 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take((P / 32 + 64) * 4); if (ws) ws->ringbits = (uint32_t*)p;
     p = take((P / 2 + 64) * 16); if (ws) ws->plist_a = (uint4*)p;
     p = take((P / 2 + 64) * 4); if (ws) ws->plist_b = (uint32_t*)p;
-    p = take(P * 16); if (ws) ws->gdelta = (float4*)p;
     const size_t tiles_pv = (size_t)((c->W + 15) / 16) * ((c->H + 15) / 16);
     const size_t words = (size_t)c->n_views * ((tiles_pv + 31) / 32);
     const size_t slot_bytes = 256 + align256(words * 4);
@@ -1080,9 +1078,105 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
 // pixel backward: antialias bwd (gather form for colours, owner-scatter for positions), shading bwd,
 // interpolate bwd, rasterize bwd; everything lands in the per-vertex world-space accumulators.
 // ------------------------------------------------------------------------------------------------
+// Shading backward of ONE covered pixel for an incoming gradient g w.r.t. its pre-antialias value (phase B: shaded
+// colour b,g,r; phase A: albedo): SH / normalise / interpolate / rasterize backward from the triangle record, two
+// red.global.add.v4.f32 per corner into the world-space vertex accumulators.  LINEAR in g, so the pass-through gradient
+// (pixel kernel) and the antialias pair terms (pair kernel) are back-propagated independently.
+template <int PHASE>
+__device__ __forceinline__ void pixel_backward(uint32_t pix32, int tself, float4 gin, const float4* __restrict__ trirec,
+                                               float invW, float invH, const float* __restrict__ viewM,
+                                               const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx,
+                                               int V, int H, int W, float4* __restrict__ G) {
+    const PixAddr pa = pix_decode(pix32, H, W);
+    const int n = pa.n, px = pa.px, py = pa.py;
+    const float* M = viewM + (size_t)n * kViewM;
+    const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
+    const float4 g0 = gin, g1 = gin;
+    if (gin.x == 0.0f && gin.y == 0.0f && gin.z == 0.0f) return;
+    PixTri q;
+    load_pixtri(tself, px, py, trirec, M, invW, invH, q);
+    const float w = 1.0f - q.u - q.v;
+    if (PHASE == 0) {
+        // only the albedo attribute is trainable: interpolate bwd
+        if (g1.x == 0.0f && g1.y == 0.0f && g1.z == 0.0f) return;
+        atomicAdd(G + 2 * (size_t)q.i0 + 1, make_float4(0.f, q.u * g1.x, q.u * g1.y, q.u * g1.z));
+        atomicAdd(G + 2 * (size_t)q.i1 + 1, make_float4(0.f, q.v * g1.x, q.v * g1.y, q.v * g1.z));
+        atomicAdd(G + 2 * (size_t)q.i2 + 1, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
+        return;
+    }
+    if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) return;
+    const float3 m = interp3(q.n0, q.n1, q.n2, q);
+    const float3 a = interp3(q.b0, q.b1, q.b2, q);
+    const float len = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
+    const float inv = 1.0f / fmaxf(len, 1e-12f);
+    const float nx = m.x * inv, ny = m.y * inv, nz = m.z * inv;
+    const float r = sh_radiance(c, nx, ny, nz);
+    const float3 ga = make_float3(g0.x * r, g0.y * r, g0.z * r);           // d/d(interpolated albedo)
+    const float gr = g0.x * a.x + g0.y * a.y + g0.z * a.z;                 // d/d(radiance)
+    float3 gn = make_float3(gr * (c[3] + c[4] * ny - 2 * c[6] * nx + c[7] * nz + 2 * c[8] * nx),
+                            gr * (c[1] + c[4] * nx + c[5] * nz - 2 * c[6] * ny - 2 * c[8] * ny),
+                            gr * (c[2] + c[5] * ny + 4 * c[6] * nz + c[7] * nx));
+    float3 gm;  // through F.normalize(eps=1e-12), mesh_sfs_optim.py:273
+    if (len > 1e-12f) {
+        const float dt = nx * gn.x + ny * gn.y + nz * gn.z;
+        gm = make_float3((gn.x - nx * dt) * inv, (gn.y - ny * dt) * inv, (gn.z - nz * dt) * inv);
+    } else {
+        gm = make_float3(gn.x * inv, gn.y * inv, gn.z * inv);
+    }
+    // interpolate bwd: d/du, d/dv over the six differentiable attributes
+    const float du = gm.x * (q.n0.x - q.n2.x) + gm.y * (q.n0.y - q.n2.y) + gm.z * (q.n0.z - q.n2.z) +
+                     ga.x * (q.b0.x - q.b2.x) + ga.y * (q.b0.y - q.b2.y) + ga.z * (q.b0.z - q.b2.z);
+    const float dv = gm.x * (q.n1.x - q.n2.x) + gm.y * (q.n1.y - q.n2.y) + gm.z * (q.n1.z - q.n2.z) +
+                     ga.x * (q.b1.x - q.b2.x) + ga.y * (q.b1.y - q.b2.y) + ga.z * (q.b1.z - q.b2.z);
+    // rasterize bwd
+    const float fx = (float)(2 * px + 1) / (float)W - 1.0f;
+    const float fy = (float)(2 * py + 1) / (float)H - 1.0f;
+    const float q0x = q.p0.x - fx * q.p0.w, q0y = q.p0.y - fy * q.p0.w;
+    const float q1x = q.p1.x - fx * q.p1.w, q1y = q.p1.y - fy * q.p1.w;
+    const float q2x = q.p2.x - fx * q.p2.w, q2y = q.p2.y - fy * q.p2.w;
+    const float e0 = q1x * q2y - q1y * q2x, e1 = q2x * q0y - q2y * q0x, e2 = q0x * q1y - q0y * q1x;
+    const float at = e0 + e1 + e2;
+    const float iw = 1.0f / (at + copysignf(1e-6f, at));
+    const float bb0 = e0 * iw, bb1 = e1 * iw;
+    const float gb0 = du * iw, gb1 = dv * iw, gbb = gb0 * bb0 + gb1 * bb1;
+    const float g0x = gbb * (q2y - q1y) - gb1 * q2y;
+    const float g1x = gbb * (q0y - q2y) + gb0 * q2y;
+    const float g2x = gbb * (q1y - q0y) - gb0 * q1y + gb1 * q0y;
+    const float g0y = gbb * (q1x - q2x) + gb1 * q2x;
+    const float g1y = gbb * (q2x - q0x) - gb0 * q2x;
+    const float g2y = gbb * (q0x - q1x) + gb0 * q1x - gb1 * q0x;
+    const float3 w0 = clip_to_world(M, g0x, g0y, -fx * g0x - fy * g0y);
+    const float3 w1 = clip_to_world(M, g1x, g1y, -fx * g1x - fy * g1y);
+    const float3 w2 = clip_to_world(M, g2x, g2y, -fx * g2x - fy * g2y);
+    const int vi[3] = {q.i0, q.i1, q.i2};
+    const float wt[3] = {q.u, q.v, w};
+    const float3 wp[3] = {w0, w1, w2};
+    const float3 nn[3] = {q.n0, q.n1, q.n2};
+    const bool dg[3] = {(q.flags & 1) != 0, (q.flags & 2) != 0, (q.flags & 4) != 0};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float3 gk = make_float3(wt[k] * gm.x, wt[k] * gm.y, wt[k] * gm.z);  // d/d(vertex normal attribute)
+        float a1, a2;
+        if (!dg[k]) {
+            float3 t1, t2;
+            tangent_frame(nn[k], t1, t2);
+            a1 = t1.x * gk.x + t1.y * gk.y + t1.z * gk.z;
+            a2 = t2.x * gk.x + t2.y * gk.y + t2.z * gk.z;
+        } else {  // |N| <= 1e-6: the normalisation does not project, keep all three components
+            a1 = gk.x; a2 = gk.y;
+            atomicAdd(reinterpret_cast<float*>(G + 2 * (size_t)V + vi[k]) + 3, gk.z);
+        }
+        float4* Gk = G + 2 * (size_t)vi[k];
+        atomicAdd(Gk, make_float4(wp[k].x, wp[k].y, wp[k].z, a1));
+        atomicAdd(Gk + 1, make_float4(a2, wt[k] * ga.x, wt[k] * ga.y, wt[k] * ga.z));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward, part 1: the blending pairs recorded by the antialias pass (a few 10^4 per iteration, one thread each).
-//   * colour / albedo gradient of the two pixels of the pair -> gdelta plane (only pixels the main pass will visit);
+//   * colour / albedo gradient of the two pixels of the pair (-alpha g_recv, +alpha g_recv), back-propagated through each
+//     pixel's shading chain right here (pixel_backward is linear in its input, so no per-pixel delta plane is needed
+//     and this kernel is independent of the pixel kernel);
 //   * phase B: silhouette position gradient -> world-space accumulators.
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
@@ -1090,7 +1184,8 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
     const uint4* __restrict__ plist_a, const uint32_t* __restrict__ plist_b, const int* __restrict__ pcount, int pcap,
     const unsigned long long* __restrict__ zbuf, const float4* __restrict__ vg, const float* __restrict__ viewM, int V,
     int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ gplane0,
-    const float4* __restrict__ gplane1, float4* __restrict__ gdelta, float4* __restrict__ G) {
+    const float4* __restrict__ gplane1, const float4* __restrict__ trirec, float invW, float invH,
+    const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, float4* __restrict__ G) {
     const int np = min(*pcount, pcap);
     const int hw = H * W;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < np; e += gridDim.x * blockDim.x) {
@@ -1110,8 +1205,12 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
         // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g; only pixels on the
         // main pass' list consume it (phase B: valid, phase A: covered)
         const bool t0 = PHASE == 1 ? k0.valid : k0.tri >= 0, t1 = PHASE == 1 ? k1.valid : k1.tri >= 0;
-        if (t0) atomicAdd(gdelta + pix0, make_float4(-pr.alpha * gr.x, -pr.alpha * gr.y, -pr.alpha * gr.z, 0.f));
-        if (t1) atomicAdd(gdelta + pix1, make_float4(pr.alpha * gr.x, pr.alpha * gr.y, pr.alpha * gr.z, 0.f));
+        if (t0)
+            pixel_backward<PHASE>((uint32_t)pix0, k0.tri, make_float4(-pr.alpha * gr.x, -pr.alpha * gr.y, -pr.alpha * gr.z, 0.f),
+                                  trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
+        if (t1)
+            pixel_backward<PHASE>((uint32_t)pix1, k1.tri, make_float4(pr.alpha * gr.x, pr.alpha * gr.y, pr.alpha * gr.z, 0.f),
+                                  trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
         if (PHASE == 1 && !pr.clamped) {
             float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = f0;
             if (k0.tri >= 0) f0 = plane0[pix0];
@@ -1140,16 +1239,15 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, part 2: one thread per covered pixel of the compact list (every lane busy): SH / normalise / interpolate /
-// rasterize backward, 9 float4 red.global.add per pixel into the world-space per-vertex accumulators.
+// backward, part 2: one thread per covered pixel of the compact list (every lane busy), pass-through gradient of the
+// pixel's own loss term.  Runs concurrently with the pair kernel (both only add into the vertex accumulators).
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
 __global__ void __launch_bounds__(256, FMHR_LB_BWD) ham_pixel_bwd_kernel(
     const uint2* __restrict__ clist, const int* __restrict__ ccount,
     const float4* __restrict__ trirec, float invW, float invH, const float* __restrict__ viewM,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, int V, int H, int W,
-    const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ gdelta,
-    float4* __restrict__ G) {
+    const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ G) {
     const int nv = *ccount;
     const int e_first = blockIdx.x * blockDim.x + threadIdx.x, e_stride = gridDim.x * blockDim.x;
     uint2 ent_next = e_first < nv ? clist[e_first] : make_uint2(0u, 0u);
@@ -1159,100 +1257,8 @@ __global__ void __launch_bounds__(256, FMHR_LB_BWD) ham_pixel_bwd_kernel(
         // phase B: tmp_img[valid_idx] = pred_img -> only valid pixels feed the shader (mesh_sfs_optim.py:285-286);
         // phase A back-propagates through every covered pixel's albedo
         if (PHASE == 1 && !(ent.y >> 31)) continue;
-        const size_t pix = ent.x;
-        const int tself = (int)(ent.y & kTriMask);
-        const PixAddr pa = pix_decode(ent.x, H, W);
-        const int n = pa.n, px = pa.px, py = pa.py;
-        const float* M = viewM + (size_t)n * kViewM;
-        const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
-        // gradient w.r.t. this pixel's PRE-antialias values: pass-through + pair terms (consumed and re-armed)
-        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-        const float4 gd = gdelta[pix];
-        if (gd.x != 0.0f || gd.y != 0.0f || gd.z != 0.0f) gdelta[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (PHASE == 1) {
-            g0 = gplane0[pix];
-            g0.x += gd.x; g0.y += gd.y; g0.z += gd.z;
-        } else {
-            g1 = gplane1[pix];
-            g1.x += gd.x; g1.y += gd.y; g1.z += gd.z;
-        }
-        PixTri q;
-        load_pixtri(tself, px, py, trirec, M, invW, invH, q);
-        const float w = 1.0f - q.u - q.v;
-        if (PHASE == 0) {
-            // only the albedo attribute is trainable: interpolate bwd
-            if (g1.x == 0.0f && g1.y == 0.0f && g1.z == 0.0f) continue;
-            atomicAdd(G + 2 * (size_t)q.i0 + 1, make_float4(0.f, q.u * g1.x, q.u * g1.y, q.u * g1.z));
-            atomicAdd(G + 2 * (size_t)q.i1 + 1, make_float4(0.f, q.v * g1.x, q.v * g1.y, q.v * g1.z));
-            atomicAdd(G + 2 * (size_t)q.i2 + 1, make_float4(0.f, w * g1.x, w * g1.y, w * g1.z));
-            continue;
-        }
-        if (g0.x == 0.0f && g0.y == 0.0f && g0.z == 0.0f) continue;
-        const float3 m = interp3(q.n0, q.n1, q.n2, q);
-        const float3 a = interp3(q.b0, q.b1, q.b2, q);
-        const float len = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
-        const float inv = 1.0f / fmaxf(len, 1e-12f);
-        const float nx = m.x * inv, ny = m.y * inv, nz = m.z * inv;
-        const float r = sh_radiance(c, nx, ny, nz);
-        const float3 ga = make_float3(g0.x * r, g0.y * r, g0.z * r);           // d/d(interpolated albedo)
-        const float gr = g0.x * a.x + g0.y * a.y + g0.z * a.z;                 // d/d(radiance)
-        float3 gn = make_float3(gr * (c[3] + c[4] * ny - 2 * c[6] * nx + c[7] * nz + 2 * c[8] * nx),
-                                gr * (c[1] + c[4] * nx + c[5] * nz - 2 * c[6] * ny - 2 * c[8] * ny),
-                                gr * (c[2] + c[5] * ny + 4 * c[6] * nz + c[7] * nx));
-        float3 gm;  // through F.normalize(eps=1e-12), mesh_sfs_optim.py:273
-        if (len > 1e-12f) {
-            const float dt = nx * gn.x + ny * gn.y + nz * gn.z;
-            gm = make_float3((gn.x - nx * dt) * inv, (gn.y - ny * dt) * inv, (gn.z - nz * dt) * inv);
-        } else {
-            gm = make_float3(gn.x * inv, gn.y * inv, gn.z * inv);
-        }
-        // interpolate bwd: d/du, d/dv over the six differentiable attributes
-        const float du = gm.x * (q.n0.x - q.n2.x) + gm.y * (q.n0.y - q.n2.y) + gm.z * (q.n0.z - q.n2.z) +
-                         ga.x * (q.b0.x - q.b2.x) + ga.y * (q.b0.y - q.b2.y) + ga.z * (q.b0.z - q.b2.z);
-        const float dv = gm.x * (q.n1.x - q.n2.x) + gm.y * (q.n1.y - q.n2.y) + gm.z * (q.n1.z - q.n2.z) +
-                         ga.x * (q.b1.x - q.b2.x) + ga.y * (q.b1.y - q.b2.y) + ga.z * (q.b1.z - q.b2.z);
-        // rasterize bwd
-        const float fx = (float)(2 * px + 1) / (float)W - 1.0f;
-        const float fy = (float)(2 * py + 1) / (float)H - 1.0f;
-        const float q0x = q.p0.x - fx * q.p0.w, q0y = q.p0.y - fy * q.p0.w;
-        const float q1x = q.p1.x - fx * q.p1.w, q1y = q.p1.y - fy * q.p1.w;
-        const float q2x = q.p2.x - fx * q.p2.w, q2y = q.p2.y - fy * q.p2.w;
-        const float e0 = q1x * q2y - q1y * q2x, e1 = q2x * q0y - q2y * q0x, e2 = q0x * q1y - q0y * q1x;
-        const float at = e0 + e1 + e2;
-        const float iw = 1.0f / (at + copysignf(1e-6f, at));
-        const float bb0 = e0 * iw, bb1 = e1 * iw;
-        const float gb0 = du * iw, gb1 = dv * iw, gbb = gb0 * bb0 + gb1 * bb1;
-        const float g0x = gbb * (q2y - q1y) - gb1 * q2y;
-        const float g1x = gbb * (q0y - q2y) + gb0 * q2y;
-        const float g2x = gbb * (q1y - q0y) - gb0 * q1y + gb1 * q0y;
-        const float g0y = gbb * (q1x - q2x) + gb1 * q2x;
-        const float g1y = gbb * (q2x - q0x) - gb0 * q2x;
-        const float g2y = gbb * (q0x - q1x) + gb0 * q1x - gb1 * q0x;
-        const float3 w0 = clip_to_world(M, g0x, g0y, -fx * g0x - fy * g0y);
-        const float3 w1 = clip_to_world(M, g1x, g1y, -fx * g1x - fy * g1y);
-        const float3 w2 = clip_to_world(M, g2x, g2y, -fx * g2x - fy * g2y);
-        const int vi[3] = {q.i0, q.i1, q.i2};
-        const float wt[3] = {q.u, q.v, w};
-        const float3 wp[3] = {w0, w1, w2};
-        const float3 nn[3] = {q.n0, q.n1, q.n2};
-        const bool dg[3] = {(q.flags & 1) != 0, (q.flags & 2) != 0, (q.flags & 4) != 0};
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float3 gk = make_float3(wt[k] * gm.x, wt[k] * gm.y, wt[k] * gm.z);  // d/d(vertex normal attribute)
-            float a1, a2;
-            if (!dg[k]) {
-                float3 t1, t2;
-                tangent_frame(nn[k], t1, t2);
-                a1 = t1.x * gk.x + t1.y * gk.y + t1.z * gk.z;
-                a2 = t2.x * gk.x + t2.y * gk.y + t2.z * gk.z;
-            } else {  // |N| <= 1e-6: the normalisation does not project, keep all three components
-                a1 = gk.x; a2 = gk.y;
-                atomicAdd(reinterpret_cast<float*>(G + 2 * (size_t)V + vi[k]) + 3, gk.z);
-            }
-            float4* Gk = G + 2 * (size_t)vi[k];
-            atomicAdd(Gk, make_float4(wp[k].x, wp[k].y, wp[k].z, a1));
-            atomicAdd(Gk + 1, make_float4(a2, wt[k] * ga.x, wt[k] * ga.y, wt[k] * ga.z));
-        }
+        const float4 g = PHASE == 1 ? gplane0[ent.x] : gplane1[ent.x];
+        pixel_backward<PHASE>(ent.x, (int)(ent.y & kTriMask), g, trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
     }
 }
 
@@ -1785,19 +1791,29 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
+    // After the antialias pass three independent kernels remain: the pair backward and the loss-scalar finalize go to the
+    // side stream, the pixel backward stays on the caller's stream (all three only ADD into `packed`).
+    cudaStream_t ps = st;
+    if (side) {
+        FMHR_CUDA(cudaEventRecord(side->fork, st));
+        FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+        ps = side->st;
+    }
     if (!forward_only) {
-        ham_pair_bwd_kernel<PHASE><<<296, 128, 0, st>>>(ws.plist_a, ws.plist_b, ws.pcount, pcap, zcur, ws.vg,
-                                                       ws.viewM, V, H, W, ws.plane[0], g0, g1, ws.gdelta,
+        ham_pair_bwd_kernel<PHASE><<<296, 128, 0, ps>>>(ws.plist_a, ws.plist_b, ws.pcount, pcap, zcur, ws.vg, ws.viewM, V, H,
+                                                       W, ws.plane[0], g0, g1, ws.trirec, invW, invH, b->sh_coeffs, sh_idx,
                                                        (float4*)b->packed);
         FMHR_LAUNCH_CHECK();
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, ws.trirec, invW, invH, ws.viewM,
-                                                              b->sh_coeffs, sh_idx, V, H, W, g0, g1, ws.gdelta,
-                                                              (float4*)b->packed);
-        FMHR_LAUNCH_CHECK();
     }
-    ham_finalize_scalars_kernel<<<1, 32, 0, st>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,
+    ham_finalize_scalars_kernel<<<1, 32, 0, ps>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,
                                                   b->packed + 12 * (size_t)V);
     FMHR_LAUNCH_CHECK();
+    if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
+    if (!forward_only) {
+        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, ws.trirec, invW, invH, ws.viewM,
+                                                              b->sh_coeffs, sh_idx, V, H, W, g0, g1, (float4*)b->packed);
+        FMHR_LAUNCH_CHECK();
+    }
     if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
     return FMHR_OK;
@@ -1816,7 +1832,6 @@ extern "C" int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers
     }
     FMHR_CUDA(cudaMemsetAsync(ws.common_region, 0, ws.common_bytes, (cudaStream_t)stream));
     FMHR_CUDA(cudaMemsetAsync(ws.ringbits, 0, (P / 32 + 64) * 4, (cudaStream_t)stream));
-    FMHR_CUDA(cudaMemsetAsync(ws.gdelta, 0, P * 16, (cudaStream_t)stream));
     return FMHR_OK;
 }
 

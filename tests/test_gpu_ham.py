@@ -326,3 +326,49 @@ def test_two_hands_and_full_size_properties():
         assert 0.02 < float(cov) < 0.4
         # the initial mesh renders its own valid_masks: the mask loss of the first iteration is ~0
         assert float(rec[3]) < 1e-3  # a few pixels differ: valid_masks came from einsum-built positions (1-ulp apart)
+
+
+def test_capture_room_and_stress_shapes():
+    """BASELINE.json configs 3 and 5 at their per-view shapes (1024x1024 sub3, 2048x2048 sub4 = 393,728 faces; fewer views
+    so the test stays short): bit-exact coverage vs the stand-alone rasterize op on the fused path's own clip positions,
+    run-to-run determinism, exact N_valid, a finite optimiser step, graph replay == eager; plus masked NCC at config 3's
+    sizes (50,000 points x 121-pixel patches, 15 source views) against the reference formula in fp64."""
+    from fmhr_b200 import dr as fdr
+    from fmhr_b200 import utils as futils
+    from fmhr_b200.ham import HamOptimizer
+    from fmhr_b200.render import render_views
+    dev = torch.device("cuda")
+    for workload, nv in (("capture_16x1024x1024", 3), ("stress_128x2048x2048", 2)):
+        wl = dict(synth.WORKLOADS[workload])
+        scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), n_views=nv)
+        c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt, device=dev)
+        mk = lambda g: HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
+                                    c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=g)
+        opt = mk(False)
+        assert opt.T == (98432 if wl["subdiv"] == 3 else 393728)
+        views = list(range(nv))
+        ex1 = opt.export(views)
+        ex2 = opt.export(views)
+        assert torch.equal(ex1["rast"], ex2["rast"])
+        ref, _ = fdr.rasterize(fdr.RasterizeGLContext(), ex1["pos"], opt.faces, resolution=(opt.H, opt.W), grad_db=False)
+        assert torch.equal(ex1["rast"], ref)
+        n_valid = int(((ex1["rast"][..., 3] > 0) & (opt.masks[:nv] > 0)).sum())
+        rec = opt.step_phase_b(views).cpu()
+        assert int(rec[6]) == n_valid and bool(torch.isfinite(rec).all())
+        gopt = mk(True)
+        grec = gopt.step_phase_b(views).cpu()
+        assert torch.allclose(rec, grec, rtol=1e-4, atol=1e-6)
+        del opt, gopt, ex1, ex2, ref
+        torch.cuda.empty_cache()
+    # NCC (models/ncc_utils.py:4-35) at config 3's sizes; 1/4 of the points keeps the fp64 check light
+    g = torch.Generator(device="cpu").manual_seed(5)
+    Nv, Np, Npx = 15, 12500, 121
+    ref_p = torch.rand(1, Np, Npx, generator=g)
+    src_p = (0.6 * ref_p + 0.4 * torch.rand(Nv, Np, Npx, generator=g))
+    msk = (torch.rand(Nv, Np, Npx, generator=g) > 0.2).float()
+    msk[0, :7] = 0.0                       # points with no valid source pixel: src_valid_num == 0 -> 1
+    src_p[1, 7:14] = 0.5                   # constant patches: zero variance -> var + 1
+    out = futils.NCC(ref_p.cuda(), src_p.cuda(), None, msk.cuda()).cpu()
+    from oracle import refmath
+    want = refmath.NCC(ref_p.double(), src_p.double(), None, msk.double())
+    assert out.shape == (Nv, Np) and float((out.double() - want).abs().max()) < 2e-5

@@ -127,6 +127,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def quantise_targets(scene):
+    """Target images in their native 8-bit form (get_data.py:77-90 reads PNGs and divides by 255): every leg of the
+    bench (device-resident, e2e, CPU reference) optimises against img = u8 / 255; the e2e leg uploads the u8 bytes."""
+    img_u8 = np.clip(np.rint(np.asarray(scene["imgs"], dtype=np.float64) * 255.0), 0, 255).astype(np.uint8)
+    msk_u8 = (np.asarray(scene["masks"]) > 0).astype(np.uint8) * 255
+    scene["imgs"] = img_u8.astype(np.float32) / np.float32(255.0)
+    scene["masks"] = (msk_u8 > 127).astype(np.float32)
+    return img_u8, msk_u8
+
+
 def cpu_reference_step_rate(scene, steps, warmup, threads):
     """Times the oracle (restated reference loop, PyTorch-CPU + C++ reference rasteriser) on the host cores."""
     import torch
@@ -156,6 +166,7 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     wl = dict(synth.WORKLOADS[args.workload])
     scene = synth.build_scene(wl, oham.render_views)
+    quantise_targets(scene)
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     rate = cpu_reference_step_rate(scene, steps, warm, threads)
     sample = "full workload, %d timed iteration(s) after %d warm-up" % (steps, warm)
@@ -205,12 +216,7 @@ def main():
 
     wl = dict(synth.WORKLOADS[args.workload])
     scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), camera_seed=1 + rank)
-    # target images in their native 8-bit form (get_data.py:77-90 reads PNGs and divides by 255): both legs of the
-    # bench optimise against img = u8 / 255, the e2e leg uploads the u8 bytes every step
-    img_u8 = np.clip(np.rint(np.asarray(scene["imgs"], dtype=np.float64) * 255.0), 0, 255).astype(np.uint8)
-    msk_u8 = (np.asarray(scene["masks"]) > 0).astype(np.uint8) * 255
-    scene["imgs"] = img_u8.astype(np.float32) / np.float32(255.0)
-    scene["masks"] = (msk_u8 > 127).astype(np.float32)
+    img_u8, msk_u8 = quantise_targets(scene)
     n, H, W = scene["imgs"].shape[0], scene["H"], scene["W"]
     c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt, device=dev)
     opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),

@@ -862,8 +862,12 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     int V, int T, int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ plane1,
     float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
     float* __restrict__ dbg_image, float* __restrict__ dbg_mask, uint4* __restrict__ plist_a,
-    uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap, int* __restrict__ status) {
-    constexpr int NC = PHASE == 1 ? 4 : 6;  // blended channels: (b,g,r,coverage) or (normal xyz, albedo bgr)
+    uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap, int* __restrict__ status,
+    double* __restrict__ init_acc) {
+    // PHASE 2 = HAM initialisation (mesh_sfs_optim.py:124-163): plane0 holds interpolated NORMALS, they and the coverage
+    // are antialiased like phase B's colour + coverage; `imgs` is the gray image [num,H,W]; outputs: antialiased coverage
+    // (dbg_mask), unit antialiased normal (gplane0) and the per-view normal equations of the SH fit (init_acc).
+    constexpr int NC = PHASE != 0 ? 4 : 6;  // blended channels: (b,g,r | normal, coverage) or (normal xyz, albedo bgr)
     __shared__ uint32_t q_items_s[8][128];
     __shared__ int q_n_s[8];
     __shared__ float blend_s[8][32][NC];
@@ -945,7 +949,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                     k0 = decode_key(zbuf[qbase + r0]); k1 = decode_key(zbuf[qbase + r1]);
                     const AAProjWorld proj{vg, viewM + (size_t)qa.n * kViewM, 0.5f * (float)W, 0.5f * (float)H};
                     found = aa_analyse_bits(k0.tri, k0.zw, k0.bits, k1.tri, k1.zw, k1.bits, qx, qy, d, proj, tri, V, T, H, W, pr);
-                    record = found && which < 2;  // seen from the pair's first pixel: record it for the backward pass
+                    record = found && which < 2 && PHASE != 2;  // seen from the pair's first pixel: record it for the backward pass
                 }
                 const unsigned mrec = __ballot_sync(0xffffffffu, record);
                 if (mrec) {
@@ -970,7 +974,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                 atomicAdd(&blend[L][0], pr.alpha * (s0.x - f0.x));
                 atomicAdd(&blend[L][1], pr.alpha * (s0.y - f0.y));
                 atomicAdd(&blend[L][2], pr.alpha * (s0.z - f0.z));
-                if (PHASE == 1) {
+                if (PHASE != 0) {
                     atomicAdd(&blend[L][3], pr.alpha * ((k1.tri >= 0 ? 1.0f : 0.0f) - (k0.tri >= 0 ? 1.0f : 0.0f)));
                 } else {
                     atomicAdd(&blend[L][3], pr.alpha * (s1.x - f1.x));
@@ -983,6 +987,8 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
         float gc[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) gc[k] = 0.0f;
+        float init_y = 0.0f;  // PHASE 2: gc = SH basis row of this valid pixel, init_y = its gray value
+        bool init_valid = false;
         if (active) {
             const size_t pix = pix32;
             const int view = __ldg(view_idx + n);
@@ -996,12 +1002,26 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
             float amask = self.tri >= 0 ? 1.0f : 0.0f;
             if (nq > 0) {
                 a0.x += blend[lane][0]; a0.y += blend[lane][1]; a0.z += blend[lane][2];
-                if (PHASE == 1) amask += blend[lane][3];
+                if (PHASE != 0) amask += blend[lane][3];
                 else { a1.x += blend[lane][3]; a1.y += blend[lane][4]; a1.z += blend[lane][5]; }
             }
             const bool valid = self.valid;
             const float* img = imgs + ((size_t)view * hw + rem) * 3;
-            if (PHASE == 1) {
+            if (PHASE == 2) {
+                float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {  // mesh_sfs_optim.py:148-153: F.normalize of the antialiased normals, get_matrix row
+                    const float len = sqrtf(a0.x * a0.x + a0.y * a0.y + a0.z * a0.z);
+                    const float inv = 1.0f / fmaxf(len, 1e-12f);
+                    const float nx = a0.x * inv, ny = a0.y * inv, nz = a0.z * inv;
+                    nrm = make_float4(nx, ny, nz, 1.0f);
+                    gc[0] = 1.0f; gc[1] = ny; gc[2] = nz; gc[3] = nx; gc[4] = nx * ny; gc[5] = ny * nz;
+                    gc[6] = 2 * nz * nz - nx * nx - ny * ny; gc[7] = nz * nx; gc[8] = nx * nx - ny * ny;
+                    init_y = __ldg(imgs + (size_t)view * hw + rem);
+                    init_valid = true;
+                }
+                gplane0[pix] = nrm;
+                if (dbg_mask) dbg_mask[pix] = amask;
+            } else if (PHASE == 1) {
                 float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {  // mesh_sfs_optim.py:289  l1 over tmp_img[valid_idx]
                     const float d0 = a0.x - __ldg(img), d1 = a0.y - __ldg(img + 1), d2 = a0.z - __ldg(img + 2);
@@ -1039,6 +1059,34 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                 gplane0[pix] = g0;
                 gplane1[pix] = g1;
                 if (dbg_image) { dbg_image[pix * 3] = pred.x; dbg_image[pix * 3 + 1] = pred.y; dbg_image[pix * 3 + 2] = pred.z; }
+            }
+        }
+        if (PHASE == 2) {
+            // normal equations of the per-view least-squares SH fit: upper triangle of A^T A (45) + A^T y (9) + count,
+            // fp64, warp-reduced when the batch belongs to one view (almost always)
+            const int n0 = __shfl_sync(0xffffffffu, n, 0);
+            const bool uniform = __all_sync(0xffffffffu, !active || n == n0);
+            double* row = init_acc + (size_t)__ldg(view_idx + (uniform ? n0 : n)) * 56;
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+#pragma unroll
+                for (int j = i; j <= 9; j++, k++) {  // j == 9: the right-hand side
+                    const double v = init_valid ? (double)gc[i] * (double)(j < 9 ? gc[j] : init_y) : 0.0;
+                    if (uniform) {
+                        const double sv = warp_sum_f64(v);
+                        if (lane == 0 && sv != 0.0) atomicAdd(row + k, sv);
+                    } else if (v != 0.0) {
+                        atomicAdd(row + k, v);
+                    }
+                }
+            }
+            const double cv = init_valid ? 1.0 : 0.0;
+            if (uniform) {
+                const double sc = warp_sum_f64(cv);
+                if (lane == 0 && sc != 0.0) atomicAdd(row + 54, sc);
+            } else if (init_valid) {
+                atomicAdd(row + 54, 1.0);
             }
         }
         if (PHASE == 0) {
@@ -1260,6 +1308,92 @@ __global__ void __launch_bounds__(256, FMHR_LB_BWD) ham_pixel_bwd_kernel(
         const float4 g = PHASE == 1 ? gplane0[ent.x] : gplane1[ent.x];
         pixel_backward<PHASE>(ent.x, (int)(ent.y & kTriMask), g, trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
     }
+}
+
+// HAM initialisation, part 2: per-view and global least-squares SH lighting from the accumulated normal equations
+// (np.linalg.lstsq in the reference, mesh_sfs_optim.py:153,166).  Block v < num solves view v, block num the sum over
+// all views.  9x9 Cholesky in fp64 by one thread; a view without enough valid normals (non-positive pivot) gets zeros
+// in the dependent components (lstsq returns the minimum-norm solution there - outside the reference's use).
+// init_acc rows: [45 upper-triangle (i <= j, with the rhs as column 9 interleaved per row) ...] laid out per row i as
+// (A_ii .. A_i8, b_i), then [54] = number of valid pixels.
+__global__ void ham_init_solve_kernel(const double* __restrict__ init_acc, int num, float* __restrict__ sh_coeffs,
+                                      float* __restrict__ sh_global, double* __restrict__ global_row) {
+    if (threadIdx.x != 0) return;
+    const int v = blockIdx.x;
+    double A[9][9], b[9];
+    for (int i = 0; i < 9; i++) { b[i] = 0.0; for (int j = 0; j < 9; j++) A[i][j] = 0.0; }
+    const int r0 = v < num ? v : 0, r1 = v < num ? v + 1 : num;
+    double count = 0.0;
+    for (int r = r0; r < r1; r++) {
+        const double* row = init_acc + (size_t)r * 56;
+        int k = 0;
+        for (int i = 0; i < 9; i++)
+            for (int j = i; j <= 9; j++, k++) {
+                if (j < 9) A[i][j] += row[k]; else b[i] += row[k];
+            }
+        count += row[54];
+    }
+    // Cholesky A = L L^T (lower triangle stored in A[j][i], i <= j)
+    double L[9][9];
+    bool ok[9];
+    for (int i = 0; i < 9; i++) {
+        for (int j = 0; j <= i; j++) {
+            double sum = A[j][i];
+            for (int k = 0; k < j; k++) sum -= L[i][k] * L[j][k];
+            if (i == j) {
+                ok[i] = sum > 1e-12 * (A[i][i] > 0.0 ? A[i][i] : 1.0);
+                L[i][i] = ok[i] ? sqrt(sum) : 1.0;
+            } else {
+                L[i][j] = ok[j] ? sum / L[j][j] : 0.0;
+            }
+        }
+    }
+    double y[9], x[9];
+    for (int i = 0; i < 9; i++) {
+        double sum = b[i];
+        for (int k = 0; k < i; k++) sum -= L[i][k] * y[k];
+        y[i] = ok[i] ? sum / L[i][i] : 0.0;
+    }
+    for (int i = 8; i >= 0; i--) {
+        double sum = y[i];
+        for (int k = i + 1; k < 9; k++) sum -= L[k][i] * x[k];
+        x[i] = ok[i] ? sum / L[i][i] : 0.0;
+    }
+    float* out = v < num ? sh_coeffs + (size_t)v * 9 : sh_global;
+    for (int i = 0; i < 9; i++) out[i] = (float)x[i];
+    if (v == num) { global_row[54] = count; for (int i = 0; i < 4; i++) global_row[i] = 0.0; }
+}
+
+// HAM initialisation, part 3: albedo_mean = mean over the valid pixels of img / radiance(global SH, normal)
+// (mesh_sfs_optim.py:173-174); the unit antialiased normals were left in `nplane` by the antialias pass.
+__global__ void __launch_bounds__(256) ham_init_albedo_kernel(const uint2* __restrict__ clist, const int* __restrict__ ccount,
+                                                              const float4* __restrict__ nplane,
+                                                              const float* __restrict__ imgs,
+                                                              const int32_t* __restrict__ view_idx, int H, int W,
+                                                              const float* __restrict__ sh_global,
+                                                              double* __restrict__ global_row) {
+    const int nv = *ccount;
+    const int hw = H * W;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += gridDim.x * blockDim.x) {
+        const uint2 ent = clist[e];
+        if (!(ent.y >> 31)) continue;
+        const float4 nr = nplane[ent.x];
+        if (nr.w == 0.0f) continue;
+        const PixAddr pa = pix_decode(ent.x, H, W);
+        const float r = sh_radiance(sh_global, nr.x, nr.y, nr.z);
+        const float* img = imgs + ((size_t)__ldg(view_idx + pa.n) * hw + pa.rem) * 3;
+        s0 += (double)(__ldg(img) / r); s1 += (double)(__ldg(img + 1) / r); s2 += (double)(__ldg(img + 2) / r);
+    }
+    s0 = warp_sum_f64(s0); s1 = warp_sum_f64(s1); s2 = warp_sum_f64(s2);
+    if ((threadIdx.x & 31) == 0) {
+        if (s0 != 0.0) atomicAdd(global_row + 0, s0);
+        if (s1 != 0.0) atomicAdd(global_row + 1, s1);
+        if (s2 != 0.0) atomicAdd(global_row + 2, s2);
+    }
+}
+__global__ void ham_init_albedo_mean_kernel(const double* __restrict__ global_row, float* __restrict__ albedo_mean) {
+    if (threadIdx.x < 3) albedo_mean[threadIdx.x] = (float)(global_row[threadIdx.x] / global_row[54]);
 }
 
 // One warp: lane j owns spread slot j of every accumulator (fp64 shuffles), view totals are strided over the lanes.
@@ -1681,9 +1815,15 @@ static int side_stream(SideStream** out) {
     return FMHR_OK;
 }
 
+// fmhr_ham_init: the forward chain up to the antialias pass runs in its initialisation mode (PHASE 2 kernel)
+struct InitArgs {
+    const float* grayimgs;  // [num,H,W]
+    double* init_acc;       // [(num + 1) * 56]
+};
+
 template <int PHASE>
 static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b, cudaStream_t st, float* dbg_image,
-                           float* dbg_mask, bool forward_only) {
+                           float* dbg_mask, bool forward_only, const InitArgs* init = nullptr) {
     HamWs ws;
     ham_layout(cfg, (char*)b->workspace, &ws);
     const int V = cfg->V, T = cfg->T, H = cfg->H, W = cfg->W, n = cfg->n_views;
@@ -1785,10 +1925,18 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     FMHR_STAGE_MARK();  // 4: scan + shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
     float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(
-        ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp, b->imgs,
-        b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1, ws.acc, ws.gsh,
-        dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status);
+    if (init) {  // initialisation mode: normals + coverage antialiased, SH normal equations accumulated
+        static const int g_init = persistent_blocks(ham_aa_loss_kernel<2>);
+        ham_aa_loss_kernel<2><<<g_init, pblock, 0, st>>>(
+            ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp,
+            init->grayimgs, b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1,
+            ws.acc, ws.gsh, dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, init->init_acc);
+    } else {
+        ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(
+            ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp, b->imgs,
+            b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1, ws.acc, ws.gsh,
+            dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, nullptr);
+    }
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
     // After the antialias pass three independent kernels remain: the pair backward and the loss-scalar finalize go to the
@@ -2001,5 +2149,43 @@ extern "C" int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_
     rc = fmhr_ham_step_update(cfg, buf, stream);
     if (rc) return rc;
     FMHR_CUDA(cudaMemcpyAsync(losses_host, buf->losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return FMHR_OK;
+}
+
+
+extern "C" size_t fmhr_ham_init_scratch_bytes(int num) { return num > 0 ? (size_t)(num + 1) * 56 * sizeof(double) : 0; }
+
+extern "C" int fmhr_ham_init(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* grayimgs,
+                             float* valid_masks_out, float* sh_coeffs_out, float* sh_global_out, float* albedo_mean_out,
+                             void* scratch, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(cfg->phase == 0);  // the phase-A workspace layout (normals / albedo planes) is the one used here
+    FMHR_CHECK_ARG(buf && grayimgs && valid_masks_out && sh_coeffs_out && sh_global_out && albedo_mean_out && scratch);
+    // valid_masks / view_vm2 are OUTPUTS of the initialisation: the checks below only need them non-null
+    fmhr_ham_buffers b = *buf;
+    if (!b.valid_masks) b.valid_masks = valid_masks_out;
+    if (!b.view_vm2) b.view_vm2 = (const double*)scratch;
+    rc = ham_check_buffers(cfg, &b);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int num = cfg->n_views;  // the reference initialises from ALL views (mesh_sfs_optim.py:130)
+    const size_t P = (size_t)num * cfg->H * cfg->W;
+    double* init_acc = (double*)scratch;
+    FMHR_CUDA(cudaMemsetAsync(init_acc, 0, fmhr_ham_init_scratch_bytes(num), st));
+    FMHR_CUDA(cudaMemsetAsync(valid_masks_out, 0, P * sizeof(float), st));
+    InitArgs ia{grayimgs, init_acc};
+    rc = ham_render_impl<0>(cfg, &b, st, nullptr, valid_masks_out, true, &ia);
+    if (rc) return rc;
+    HamWs ws;
+    ham_layout(cfg, (char*)b.workspace, &ws);
+    double* global_row = init_acc + (size_t)num * 56;
+    ham_init_solve_kernel<<<num + 1, 32, 0, st>>>(init_acc, num, sh_coeffs_out, sh_global_out, global_row);
+    FMHR_LAUNCH_CHECK();
+    ham_init_albedo_kernel<<<296, 256, 0, st>>>(ws.clist, ws.ccount, ws.plane[2], b.imgs, b.view_idx, cfg->H, cfg->W,
+                                                sh_global_out, global_row);
+    FMHR_LAUNCH_CHECK();
+    ham_init_albedo_mean_kernel<<<1, 32, 0, st>>>(global_row, albedo_mean_out);
+    FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

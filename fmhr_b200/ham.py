@@ -92,6 +92,37 @@ class HamOptimizer:
         self.ml_tri2 = torch.from_numpy(tri2.view(np.int32)).to(dev)
         self.n_meshlets, self.ml_max_verts = nm.value, mv.value
 
+    # ------------------------------------------------------------------ initialisation (mesh_sfs_optim.py:124-177)
+    def initialise(self, grayimgs):
+        """HAM initialisation on the fused forward chain (fmhr_ham_init): renders every view of the INITIAL mesh once and
+        sets, exactly as the reference does before its loops, `valid_masks` (antialiased coverage, :146,163), `sh_coeffs`
+        (per-view least-squares SH lighting, :152-159), and `albedo` (img / radiance of the global SH fit, averaged over
+        the valid pixels, broadcast to every vertex, :165-176).  Returns dict(sh_coeff=global [9], albedo_mean=[3])."""
+        dev = self.device
+        gray = grayimgs.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if gray.shape != self.masks.shape:
+            raise RuntimeError("fmhr_b200: grayimgs must be [num,H,W]")
+        views = torch.arange(self.num, dtype=torch.int32, device=dev)
+        cfg = self._cfg(self.num, 0, None)
+        buf = self._buffers(cfg, views)
+        valid = torch.empty_like(self.masks)
+        sh = torch.empty(self.num, 9, dtype=torch.float32, device=dev)
+        sh_g = torch.empty(9, dtype=torch.float32, device=dev)
+        alb = torch.empty(3, dtype=torch.float32, device=dev)
+        scratch = torch.empty(self.lib.fmhr_ham_init_scratch_bytes(self.num), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            self._prepare_zbuf(cfg, buf)
+            check(self.lib.fmhr_ham_init(ctypes.byref(cfg), ctypes.byref(buf), ptr(gray), ptr(valid), ptr(sh), ptr(sh_g),
+                                         ptr(alb), ptr(scratch), stream()), "ham_init")
+            self.valid_masks = valid
+            self.sh_coeffs.copy_(sh)
+            self.albedo.copy_(alb[None].expand(self.V, 3))
+            check(self.lib.fmhr_ham_prepare_views(ptr(self.valid_masks), self.num, self.H, self.W, ptr(self.view_vm2),
+                                                  stream()), "ham_prepare_views")
+        self._struct_cache.clear()
+        self._graphs = {}
+        return dict(sh_coeff=sh_g, albedo_mean=alb)
+
     # ------------------------------------------------------------------ reference-shaped accessors
     @property
     def vertices(self):

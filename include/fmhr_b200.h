@@ -240,6 +240,19 @@ int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_buffers* bu
                           const uint8_t* masks_host, const float* w2cs_host, const float* projs_host, void* staging,
                           float* losses_host, fmhr_stream_t stream);
 
+/* HAM initialisation (mesh_sfs_optim.py:124-177) on the same fused forward chain: every view of the batch is rendered
+ * once (n_views rows of view_idx, normally all views), normals and coverage are antialiased, and
+ *   valid_masks_out [n_views,H,W] = antialiased coverage of the initial mesh (:146,163; indexed by view SLOT),
+ *   sh_coeffs_out   [n_views,9]   = per-view least-squares SH lighting of the re-normalised normals onto grayimgs (:152-153),
+ *   sh_global_out   [9]           = the same fit over all views (:165-166),
+ *   albedo_mean_out [3]           = mean over the valid pixels of img / radiance(global SH) (:173-174).
+ * grayimgs [num,H,W] (rows addressed through view_idx like imgs).  cfg->phase must be 0 (workspace layout), `scratch` =
+ * fmhr_ham_init_scratch_bytes(n_views) bytes of device memory; buf->valid_masks / view_vm2 / sh_coeffs are not read.
+ * The normal equations are accumulated and solved in fp64 (9x9 Cholesky) instead of the reference's SVD least squares. */
+size_t fmhr_ham_init_scratch_bytes(int num);
+int fmhr_ham_init(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* grayimgs, float* valid_masks_out,
+                  float* sh_coeffs_out, float* sh_global_out, float* albedo_mean_out, void* scratch, fmhr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,3 +195,53 @@ def phase_a_step(st, view_idx, keep=None):
         keep.update(grad_albedo=st.albedo.grad.detach().clone(), grad_sh=st.sh_coeffs.grad.detach().clone())
     opt.step()
     return dict(sfs=float(sfs_loss), albedo=float(albedo_loss), n_valid=valid_idx[0].numel())
+
+
+def ham_init(vertices, faces, imgs, grayimgs, masks, w2cs, projs, H, W, degree=3):
+    """HAM initialisation, mesh_sfs_optim.py:124-177 line for line (oracle.raster for nvdiffrast, numpy lstsq as in the
+    reference): per view the antialiased coverage of the initial mesh (`valid_masks`, :146,163) and the least-squares SH
+    lighting of the antialiased, re-normalised normals onto the gray image (:152-153); then the global SH fit over all
+    views (:165-166) and the mean albedo img / radiance over the valid pixels (:173-174).
+    Returns dict(valid_masks [num,H,W], sh_coeffs [num,9], sh_coeff [9], albedo_mean [3], n_valid [num])."""
+    from .refmath import get_matrix
+    vertices = torch.as_tensor(vertices, dtype=torch.float32)
+    faces = torch.as_tensor(faces, dtype=torch.int32)
+    imgs, grayimgs, masks = (torch.as_tensor(a, dtype=torch.float32) for a in (imgs, grayimgs, masks))
+    w2cs, projs = torch.as_tensor(w2cs, dtype=torch.float32), torch.as_tensor(projs, dtype=torch.float32)
+    glctx = dr.RasterizeGLContext()
+    num = imgs.shape[0]
+    with torch.no_grad():
+        valid_normals, valid_grayimgs, valid_masks, valid_imgs, sh_coeffs, counts = [], [], [], [], [], []
+        for k in range(num):
+            w2c, proj = w2cs[k:k + 1], projs[k:k + 1]
+            mask, img, grayimg = masks[k:k + 1], imgs[k:k + 1], grayimgs[k:k + 1]
+            vertsw, proj_verts = _clip_positions(vertices, w2c, proj)
+            normals = get_normals(vertsw[:, :, :3], faces.long())
+            rast_out, _ = dr.rasterize(glctx, proj_verts, faces, resolution=(H, W))
+            feat, _ = dr.interpolate(torch.cat([normals, torch.ones_like(vertsw[:, :, :1])], 2), rast_out, faces)
+            pred_normals = feat[:, :, :, :3].contiguous()
+            pred_mask = feat[:, :, :, 3:4].contiguous()
+            pred_mask = dr.antialias(pred_mask, rast_out, proj_verts, faces).squeeze(-1)
+            pred_normals = dr.antialias(pred_normals, rast_out, proj_verts, faces)
+            pred_normals = F.normalize(pred_normals, p=2, dim=3)
+            valid_idx = (mask > 0) & (rast_out[:, :, :, 3] > 0)
+            valid_normal = pred_normals[valid_idx].numpy()
+            valid_grayimg = grayimg[valid_idx].numpy()
+            matrix = get_matrix(torch.from_numpy(valid_normal), degree).numpy()
+            sh_coeff = np.linalg.lstsq(matrix, valid_grayimg, rcond=None)[0]
+            valid_normals.append(valid_normal)
+            valid_imgs.append(img[valid_idx])
+            valid_grayimgs.append(valid_grayimg)
+            valid_masks.append(pred_mask)
+            sh_coeffs.append(torch.from_numpy(sh_coeff.astype(np.float32)).unsqueeze(0))
+            counts.append(int(valid_idx.sum()))
+        valid_normals = np.concatenate(valid_normals, axis=0)
+        valid_imgs = torch.cat(valid_imgs, 0)
+        valid_grayimgs = np.concatenate(valid_grayimgs, axis=0)
+        valid_masks = torch.cat(valid_masks, 0)
+        matrix = get_matrix(torch.from_numpy(valid_normals), degree).numpy()
+        sh_coeff = torch.from_numpy(np.linalg.lstsq(matrix, valid_grayimgs, rcond=None)[0].astype(np.float32))
+        radiance = get_radiance(sh_coeff, torch.from_numpy(valid_normals), degree).unsqueeze(-1)
+        albedo_mean = (valid_imgs / radiance).mean(0)
+    return dict(valid_masks=valid_masks, sh_coeffs=torch.cat(sh_coeffs, 0), sh_coeff=sh_coeff, albedo_mean=albedo_mean,
+                n_valid=counts)

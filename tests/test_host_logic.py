@@ -170,3 +170,25 @@ def test_meshlets_reject_bad_input():
     rc = lib.fmhr_meshlets_build_host(ctypes.c_void_p(tri.ctypes.data), None, 3, 1, 1024, ctypes.byref(nm), ctypes.byref(nr),
                                       ctypes.byref(mv), None, None, None)
     assert rc == -1 and b"invalid argument" in lib.fmhr_last_error_string()
+
+
+def test_result_files_follow_the_reference_formats(tmp_path):
+    """fmhr_b200.export: <scan>.pt / <scan>.obj / <scan>_c.obj as mesh_sfs_optim.py:19-28,321-337 writes them (the files
+    neural_render.py:90-96 loads): tensor shapes, vertex / face order, BGR->RGB colour clamp(0.5*albedo), flipped winding."""
+    from fmhr_b200 import export
+    rng = np.random.default_rng(0)
+    V, F, num = 7, 5, 3
+    verts = rng.normal(size=(V, 3)).astype(np.float32)
+    faces = rng.integers(0, V, size=(F, 3)).astype(np.int32)
+    albedo = rng.uniform(0, 3, size=(V, 3)).astype(np.float32)   # some entries clamp at 1
+    sh = rng.normal(size=(num, 9)).astype(np.float32)
+    export.save_ham_results(str(tmp_path), 4, verts, faces, albedo, sh)
+    pt = torch.load(str(tmp_path / "4.pt"))
+    assert set(pt) == {"sh_coeff", "albedo"} and tuple(pt["albedo"].shape) == (1, V, 3) and tuple(pt["sh_coeff"].shape) == (num, 9)
+    assert torch.equal(pt["albedo"][0], torch.tensor(albedo)) and torch.equal(pt["sh_coeff"], torch.tensor(sh))
+    v, c, f = export.load_obj(str(tmp_path / "4.obj"))
+    assert c is None and np.allclose(v, verts, atol=1e-6) and np.array_equal(f, faces)
+    v, c, f = export.load_obj(str(tmp_path / "4_c.obj"))
+    assert np.allclose(v, verts, atol=1e-4)
+    assert np.array_equal(f, faces[:, [0, 2, 1]])                                   # flipped winding
+    assert np.allclose(c, np.clip(0.5 * albedo, 0, 1)[:, ::-1], atol=1e-4)          # BGR -> RGB

@@ -341,6 +341,13 @@ def main():
                                    "traffic": (traffic or {}).get("kernels", {}).get(top),
                                    "share_of_step": stages[top] / sum(stages.values())}
         roof["stage_ms"] = stages
+        # second half of BASELINE.json's metric: "rasterize GB/s vs HBM peak" (B_rast = 16nV + 12F + 16P
+        # over the visibility pass alone; the fused path's coverage kernel also does the clip transform)
+        b_rast = 16 * n * V + 12 * F + 16 * n * H * W
+        roof["rasterize"] = {"algorithmic_bytes": b_rast, "kernel_ms": stages["coverage"],
+                             "achieved": b_rast / (stages["coverage"] * 1e-3) / 1e9,
+                             "frac": b_rast / (stages["coverage"] * 1e-3) / 1e9 / peak,
+                             "mtri_per_s": n * F / (stages["coverage"] * 1e-3) / 1e6}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

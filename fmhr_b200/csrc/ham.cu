@@ -336,8 +336,12 @@ __device__ __forceinline__ void ml_candidate(uint2 rec, int e, const float4* pos
     else ml_cover<long long>(X0, Y0, X1, Y1, X2, Y2, bx.px0, bx.px1, bx.py0, bx.py1, pos_s, rec, e, W, invW, invH, zb, tbits, tiles_x, qcount, queue);
 }
 
+#ifndef FMHR_COV_THREADS
+#define FMHR_COV_THREADS 256  // threads per coverage block (tuning: 128 gives smaller barrier domains, more blocks per SM)
+#endif
+constexpr int kCovThreads = FMHR_COV_THREADS;
 template <int TPT>
-__global__ void __launch_bounds__(256, FMHR_LB_COVERAGE) ham_coverage_meshlet_kernel(
+__global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThreads)) ham_coverage_meshlet_kernel(
     const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ ml_vptr,
     const int32_t* __restrict__ ml_verts, const uint2* __restrict__ ml_tri2, int max_verts, int H, int W, float invW,
     float invH, unsigned long long* __restrict__ zbuf, uint32_t* __restrict__ gbits, uint32_t* __restrict__ glist,
@@ -348,18 +352,18 @@ __global__ void __launch_bounds__(256, FMHR_LB_COVERAGE) ham_coverage_meshlet_ke
     const int words = (tiles_per_view + 31) >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned int* tbits = reinterpret_cast<unsigned int*>(snap_s + max_verts);  // block-wide tile bitmap
-    __shared__ uint2 cand[8][TPT * 32];  // per warp: the triangles whose bounding box holds a pixel centre
-    __shared__ uint2 queue[8][kFragQueue];  // per warp: covered pixel centres (candidate index, py << 16 | px)
-    __shared__ int qcount[8];
+    __shared__ uint2 cand[kCovThreads / 32][TPT * 32];  // per warp: the triangles whose bounding box holds a pixel centre
+    __shared__ uint2 queue[kCovThreads / 32][kFragQueue];  // per warp: covered pixel centres (candidate index, py << 16 | px)
+    __shared__ int qcount[kCovThreads / 32];
     const int m = blockIdx.x, n = blockIdx.y;
     for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;  // visible after the vertex-phase barrier
     if (lane == 0) qcount[warp] = 0;
     const ViewM Mv = load_viewM(viewM + (size_t)n * kViewM);  // uniform loads: L1 broadcast
     // triangle records of this thread: issued before the vertex phase so their latency hides behind it
     uint2 rec[TPT];
-    const uint2* recs = ml_tri2 + (size_t)m * (TPT * 256);
+    const uint2* recs = ml_tri2 + (size_t)m * (TPT * kCovThreads);
 #pragma unroll
-    for (int k = 0; k < TPT; k++) rec[k] = __ldg(recs + k * 256 + threadIdx.x);
+    for (int k = 0; k < TPT; k++) rec[k] = __ldg(recs + k * kCovThreads + threadIdx.x);
     const int vb = __ldg(ml_vptr + m), nv = __ldg(ml_vptr + m + 1) - vb;
     const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
@@ -1888,13 +1892,13 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));              \
                 attr_set = true;                                                                                       \
             }                                                                                                          \
-            ham_coverage_meshlet_kernel<TPT><<<grid, 256, smem, st>>>(                                                 \
+            ham_coverage_meshlet_kernel<TPT><<<grid, kCovThreads, smem, st>>>(                                         \
                 ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,               \
                 ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv);                                      \
         } while (0)
-        if (b->ml_tris == 1024) FMHR_COVERAGE(4);
-        else if (b->ml_tris == 512) FMHR_COVERAGE(2);
-        else FMHR_COVERAGE(1);
+        if (b->ml_tris == 1024) FMHR_COVERAGE(1024 / kCovThreads);
+        else if (b->ml_tris == 512) FMHR_COVERAGE(512 / kCovThreads);
+        else FMHR_COVERAGE(256 / kCovThreads);
 #undef FMHR_COVERAGE
         FMHR_LAUNCH_CHECK();
     }

@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
                                                        uint32_t* __restrict__ ringbits, uint32_t* __restrict__ rlist,
                                                        int* __restrict__ rcount, int rcap, int* __restrict__ status) {
     // unit of work = half a tile (16 x 8 pixels): a lane owns column (lane & 15) of rows (lane >> 4) + 2k, k = 0..3, so
-    // the four key loads (and then the sixteen neighbour-key loads) of a unit are independent and issued back to back
+    // the four key loads of a unit are independent and issued back to back
     constexpr int kBuf = 288, kRBuf = 96;
     __shared__ uint2 cbuf[8][kBuf];
     __shared__ uint32_t rbuf[8][kRBuf];  // ring pixels: appended to rlist with ONE global atomic per ~64 entries (a
@@ -703,18 +703,37 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
 #pragma unroll
         for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, key[k] != ZB_EMPTY); total += __popc(m[k]); }
         if (total == 0) continue;
-        // neighbour keys of the covered pixels (a non-empty dummy where the neighbour is outside the view)
-        unsigned long long nk[4][4];
+        // Emptiness of the 4-neighbours of the covered pixels.  Inside the 16x8 unit it is in the ballot words (bit lx +
+        // 16 * (row & 1) of m[row >> 1]); only the unit's border needs keys from memory: ONE load for the rows above /
+        // below (lanes 0-15 / 16-31) and ONE for the columns left / right (lanes 0-7 / 8-15) instead of 16 per lane.
+        const int uy0 = tc.by * kTile + (u & 1) * 8;  // first row of the unit
+        unsigned e_tb, e_lr;
+        {
+            const int qy = ly == 0 ? uy0 - 1 : uy0 + 8;
+            const bool in = px < W && qy >= 0 && qy < H;
+            const unsigned long long kq = in ? zb[(size_t)qy * W + px] : 0ull;
+            e_tb = __ballot_sync(0xffffffffu, in && kq == ZB_EMPTY);
+            const int qx = lane < 8 ? tc.bx * kTile - 1 : tc.bx * kTile + 16, qr = uy0 + (lane & 7);
+            const bool in2 = lane < 16 && qx >= 0 && qx < W && qr < H;
+            const unsigned long long kq2 = in2 ? zb[(size_t)qr * W + qx] : 0ull;
+            e_lr = __ballot_sync(0xffffffffu, in2 && kq2 == ZB_EMPTY);
+        }
+        unsigned emask = 0u;  // bit 4k + d: neighbour d (right, left, down, up) of this lane's pixel in row 2k + ly is empty
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int py = py0 + 2 * k;
-            const bool cov = key[k] != ZB_EMPTY;
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py + (d == 2 ? 1 : (d == 3 ? -1 : 0));
-                nk[k][d] = (cov && qx >= 0 && qy >= 0 && qx < W && qy < H) ? zb[(size_t)qy * W + qx] : 0ull;
-            }
+            if (key[k] == ZB_EMPTY) continue;
+            const int r = 2 * k + ly, py = py0 + 2 * k;
+            const unsigned row = m[k] >> (16 * ly);                       // coverage bits of this pixel's row
+            // row below / above inside the unit: other half of m[k], or the neighbouring word
+            const unsigned below = ly == 0 ? (m[k] >> 16) : (k < 3 ? m[k < 3 ? k + 1 : 3] : 0u);
+            const unsigned above = ly == 1 ? m[k] : (k > 0 ? (m[k > 0 ? k - 1 : 0] >> 16) : 0u);
+            const bool er = lx < 15 ? (!((row >> (lx + 1)) & 1u) && px + 1 < W) : ((e_lr >> (8 + r)) & 1u);
+            const bool el = lx > 0 ? !((row >> (lx - 1)) & 1u) : ((e_lr >> r) & 1u);
+            const bool ed = r < 7 ? (!((below >> lx) & 1u) && py + 1 < H) : ((e_tb >> (16 + lx)) & 1u);
+            const bool eu = r > 0 ? !((above >> lx) & 1u) : ((e_tb >> lx) & 1u);
+            emask |= ((er ? 1u : 0u) | (el ? 2u : 0u) | (ed ? 4u : 0u) | (eu ? 8u : 0u)) << (4 * k);
         }
+        const bool any_ring = __any_sync(0xffffffffu, emask != 0u);
         int off = nbuf;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -724,12 +743,13 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
                 cbuf[wib][off + __popc(m[k] & lt)] = make_uint2(pix, (uint32_t)key[k] & kTriMask);
             }
             off += __popc(m[k]);
+            if (!any_ring) continue;  // interior unit: no empty pixel touches a covered one
             // empty 4-neighbours of a covered pixel: the ring antialiasing can blend into (bitmap de-duplicates)
 #pragma unroll
             for (int d = 0; d < 4; d++) {
                 bool fresh = false;
                 uint32_t q = 0u;
-                if (nk[k][d] == ZB_EMPTY) {
+                if ((emask >> (4 * k + d)) & 1u) {
                     const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py + (d == 2 ? 1 : (d == 3 ? -1 : 0));
                     q = (uint32_t)(((size_t)tc.n * H + qy) * W + qx);
                     const uint32_t bit = 1u << (q & 31);

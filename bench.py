@@ -153,6 +153,16 @@ def cpu_reference_step_rate(scene, steps, warmup, threads):
     return steps / (time.time() - t)
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """The one JSON line of the run, on the process's ORIGINAL stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, line)
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's own CPU implementation of the path = the oracle port (nvdiffrast has no
     CPU build and is not vendored, so rasterize/interpolate/antialias are the plain C++ reference rasteriser)."""
@@ -170,7 +180,7 @@ def run_reference(args, rank, world):
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     rate = cpu_reference_step_rate(scene, steps, warm, threads)
     sample = "full workload, %d timed iteration(s) after %d warm-up" % (steps, warm)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1000.0 / rate, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -178,7 +188,7 @@ def run_reference(args, rank, world):
                    "verts": int(scene["vertices"].shape[0]), "faces": int(scene["faces"].shape[0])},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -191,7 +201,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused NVLink peer-memory exchange inside the update kernel, or one NCCL all-reduce")
     args = ap.parse_args()
+    # Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout, so everything but the
+    # final line is sent to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,7 +238,9 @@ def main():
     n, H, W = scene["imgs"].shape[0], scene["H"], scene["W"]
     c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt, device=dev)
     opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
-                       c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs)
+                       c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs,
+                       exchange=args.exchange if world > 1 else None)
+    exchange = "NVLink peer-memory gather fused into the update kernel" if opt.peer is not None else "1 NCCL all-reduce/iter"
     V, F = opt.V, opt.T
     E = opt.topo.n_dir_edges // 2
     views = torch.arange(n, dtype=torch.int32, device=dev)
@@ -367,7 +387,7 @@ def main():
                    "launch": "eager" if args.no_graphs else "cuda-graph replay",
                    "l2": "per-iteration working set %.0f MB > 126 MB L2 (no flush needed)" % (
                        (8 + 32 + 20) * n * H * W / 1e6),
-                   "parallelism": "views x%d (weak), 1 NCCL all-reduce/iter" % world if world > 1 else "single GPU"},
+                   "parallelism": "views x%d (weak), %s" % (world, exchange) if world > 1 else "single GPU"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clocks,
         "e2e": e2e,
@@ -375,7 +395,7 @@ def main():
         "cpu_baseline": cpu,
         "losses_last": {k: v for k, v in zip(["sfs", "lap", "albedo", "mask", "edge", "delta", "n_valid", "total"], losses)},
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

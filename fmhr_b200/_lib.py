@@ -41,6 +41,15 @@ class HamBuffers(ctypes.Structure):
                                              ("ml_max_verts", ctypes.c_int32), ("ml_reserved", ctypes.c_int32)]
 
 
+MAX_PEERS = 16
+
+
+class HamPeers(ctypes.Structure):
+    """struct fmhr_ham_peers"""
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("packed", c_p * MAX_PEERS),
+                ("flags", c_p * MAX_PEERS), ("epoch", c_p), ("reduced", c_p)]
+
+
 _SIGS = {
     "fmhr_version": (c_i, []),
     "fmhr_last_error_string": (ctypes.c_char_p, []),
@@ -70,6 +79,11 @@ _SIGS = {
     "fmhr_ham_prepare_views": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_ham_step_render": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
     "fmhr_ham_step_update": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
+    "fmhr_ham_step_update_peer": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), ctypes.POINTER(HamPeers), c_p]),
+    "fmhr_peer_alloc": (c_i, [c_sz, ctypes.POINTER(c_p), c_p]),
+    "fmhr_peer_open": (c_i, [c_p, ctypes.POINTER(c_p)]),
+    "fmhr_peer_close": (c_i, [c_p]),
+    "fmhr_peer_free": (c_i, [c_p]),
     "fmhr_ham_stage_times": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), ctypes.POINTER(c_f),
                                    ctypes.POINTER(c_i), c_p]),
     "fmhr_ham_debug_export": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p]),

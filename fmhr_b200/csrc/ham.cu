@@ -1618,6 +1618,90 @@ __global__ void __launch_bounds__(256) ham_normal_grad_kernel(int V, float4* __r
     vg[2 * (size_t)i + 1] = make_float4(r.x, r.y, r.z, 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-GPU exchange over NVLink peer memory, fused into the first kernel of the update (the one exchange of
+// the path is the sum of `packed` over the ranks).  Every rank's `packed` lives in a cudaIpc-shared allocation; this
+// kernel (a) tells every peer that this rank's accumulators of the step are complete, (b) waits for the same word from
+// every peer, then (c) each thread sums ITS vertex's three accumulator float4s straight out of every rank's buffer (one-shot
+// gather in rank order, so all replicas get bit-identical sums), stores the sums into the local `reduced` buffer the Adam
+// pass reads, and does the normal-gradient step of that vertex on them.  `packed` alternates between two buffers per step
+// (the z-buffer slot parity), so a rank never re-arms a buffer a slower peer may still be reading: before it can reach the
+// prep kernel two steps later it has waited for that peer's flag of the step in between.
+struct HamPeerArgs {
+    const float4* packed[FMHR_MAX_PEERS];  // this step's packed buffer of every rank (own rank included)
+    uint32_t* signal[FMHR_MAX_PEERS];      // word [rank] of every rank's flag array: where this rank posts its step count
+    const uint32_t* flags;                 // this rank's flag array [FMHR_MAX_PEERS], word r is posted by rank r
+    const uint32_t* epoch;                 // steps this rank has completed (device counter, bumped by the Adam pass)
+    float4* reduced;                       // [3V + 1] sums over the ranks
+    int world;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer(const float4* p) {  // peer lines must never be served from this SM's L1
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+constexpr long long kPeerTimeoutCycles = 6000000000ll;  // ~3 s at 1.97 GHz: a lost peer flags the step instead of hanging
+
+__global__ void __launch_bounds__(256) ham_peer_reduce_normal_grad_kernel(int V, float4* __restrict__ vg,
+                                                                          const float4* __restrict__ vattr,
+                                                                          const float4* __restrict__ raw4, HamPeerArgs pa,
+                                                                          int* __restrict__ status) {
+    const uint32_t want = *pa.epoch + 1u;
+    if (threadIdx.x < pa.world) {
+        // every block posts the (idempotent) word, so no block ever waits on another block of this grid
+        __threadfence_system();
+        st_release_sys(pa.signal[threadIdx.x], want);
+        const uint32_t* f = pa.flags + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
+            if (clock64() - t0 > kPeerTimeoutCycles) { atomicOr(status, 4); break; }
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > V) return;
+    if (i == V) {  // the four loss scalars behind the accumulators
+        float4 s = ld_peer(pa.packed[0] + 3 * (size_t)V);
+        for (int r = 1; r < pa.world; r++) s = add4(s, ld_peer(pa.packed[r] + 3 * (size_t)V));
+        pa.reduced[3 * (size_t)V] = s;
+        return;
+    }
+    float4 ga = ld_peer(pa.packed[0] + 2 * (size_t)i), gb = ld_peer(pa.packed[0] + 2 * (size_t)i + 1),
+           gm = ld_peer(pa.packed[0] + 2 * (size_t)V + i);
+    for (int r = 1; r < pa.world; r++) {
+        const float4 a = ld_peer(pa.packed[r] + 2 * (size_t)i), b = ld_peer(pa.packed[r] + 2 * (size_t)i + 1),
+                     m = ld_peer(pa.packed[r] + 2 * (size_t)V + i);
+        ga = add4(ga, a); gb = add4(gb, b); gm = add4(gm, m);
+    }
+    pa.reduced[2 * (size_t)i] = ga;
+    pa.reduced[2 * (size_t)i + 1] = gb;
+    pa.reduced[2 * (size_t)V + i] = gm;
+    const float4 nrm = __ldg(vattr + 2 * (size_t)i);
+    const float4 N = raw4[i];
+    float3 r;
+    if (nrm.w == 0.0f) {
+        float3 t1, t2;
+        tangent_frame(make_float3(nrm.x, nrm.y, nrm.z), t1, t2);
+        const float inv = 1.0f / N.w;
+        r = make_float3((t1.x * ga.w + t2.x * gb.x) * inv, (t1.y * ga.w + t2.y * gb.x) * inv,
+                        (t1.z * ga.w + t2.z * gb.x) * inv);
+    } else {
+        r = make_float3(ga.w * 1e6f, gb.x * 1e6f, gm.w * 1e6f);
+    }
+    vg[2 * (size_t)i + 1] = make_float4(r.x, r.y, r.z, 0.f);
+}
+
 __device__ __forceinline__ float adam_update(float p, float g, float* m, float* v, float b1, float b2, float eps,
                                              float step_size, float bias2_sqrt) {
     const float mm = *m + (g - *m) * (1.0f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
@@ -1638,7 +1722,7 @@ __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
     const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed, const float4* __restrict__ ys,
     float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
     const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad,
-    const int* __restrict__ status) {
+    const int* __restrict__ status, uint32_t* __restrict__ epoch_bump) {
     const int V = cfg.V;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
     const float* scal = packed + 12 * (size_t)V;
@@ -1656,7 +1740,9 @@ __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
         losses[0] = sfs; losses[1] = cfg.phase == 1 ? lap : 0.0f; losses[2] = alb; losses[3] = msk;
         losses[4] = cfg.phase == 1 ? edg : 0.0f; losses[5] = cfg.phase == 1 ? del : 0.0f; losses[6] = n_valid;
         losses[7] = cfg.phase == 1 ? sfs + lap + alb + msk + edg + del : sfs;
-        if (status && (*status & 1)) losses[7] = __int_as_float(0x7fc00000);  // pair list overflow: refuse a number
+        // pair list overflow (bit 0) or a peer that never posted its step (bit 2): refuse a number
+        if (status && (*status & 5)) losses[7] = __int_as_float(0x7fc00000);
+        if (epoch_bump) *epoch_bump += 1u;  // peer exchange: this rank has consumed the step's buffers
     }
     // Laplacian backward rows (L^T yhat) for vertices and albedo; normal backward + edge hinge over incident faces
     float3 lv = make_float3(0.f, 0.f, 0.f), la = lv, gnb = lv, ge = lv;
@@ -2028,28 +2114,105 @@ extern "C" int fmhr_ham_step_render(const fmhr_ham_config* cfg, const fmhr_ham_b
                            : ham_render_impl<1>(cfg, buf, st, nullptr, nullptr, false);
 }
 
+static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const fmhr_ham_peers* peers,
+                           cudaStream_t st) {
+    HamWs ws;
+    ham_layout(cfg, (char*)buf->workspace, &ws);
+    const int V = cfg->V;
+    const float* packed = buf->packed;
+    uint32_t* bump = nullptr;
+    if (peers) {
+        HamPeerArgs pa;
+        for (int r = 0; r < FMHR_MAX_PEERS; r++) {
+            pa.packed[r] = r < peers->world ? (const float4*)peers->packed[r] : nullptr;
+            pa.signal[r] = r < peers->world ? peers->flags[r] + peers->rank : nullptr;
+        }
+        pa.flags = peers->flags[peers->rank];
+        pa.epoch = peers->epoch;
+        pa.reduced = (float4*)peers->reduced;
+        pa.world = peers->world;
+        ham_peer_reduce_normal_grad_kernel<<<cdiv(V + 1, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, pa, ws.status);
+        packed = peers->reduced;
+        bump = peers->epoch;
+    } else {
+        ham_normal_grad_kernel<<<cdiv(V, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, (const float4*)buf->packed);
+    }
+    FMHR_LAUNCH_CHECK();
+    ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
+        *cfg, ws.vg, buf->delta, buf->albedo, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
+        packed, ws.ys, buf->adam_m, buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status, bump);
+    FMHR_LAUNCH_CHECK();
+    FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)
+    if (cfg->phase == 0) {
+        ham_update_sh_kernel<<<cdiv(cfg->n_sh_rows * 9, 128), 128, 0, st>>>(*cfg, ws.gsh, packed, buf->sh_coeffs,
+                                                                            buf->adam_m, buf->adam_v, ws.adam_sc,
+                                                                            buf->dbg_grad_sh);
+        FMHR_LAUNCH_CHECK();
+    }
+    return FMHR_OK;
+}
+
 extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     rc = ham_check_buffers(cfg, buf);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    HamWs ws;
-    ham_layout(cfg, (char*)buf->workspace, &ws);
-    const int V = cfg->V;
-    ham_normal_grad_kernel<<<cdiv(V, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, (const float4*)buf->packed);
-    FMHR_LAUNCH_CHECK();
-    ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
-        *cfg, ws.vg, buf->delta, buf->albedo, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
-        buf->packed, ws.ys, buf->adam_m, buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status);
-    FMHR_LAUNCH_CHECK();
-    FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)
-    if (cfg->phase == 0) {
-        ham_update_sh_kernel<<<cdiv(cfg->n_sh_rows * 9, 128), 128, 0, st>>>(*cfg, ws.gsh, buf->packed, buf->sh_coeffs,
-                                                                            buf->adam_m, buf->adam_v, ws.adam_sc,
-                                                                            buf->dbg_grad_sh);
-        FMHR_LAUNCH_CHECK();
+    return ham_update_impl(cfg, buf, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int fmhr_ham_step_update_peer(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf,
+                                         const fmhr_ham_peers* peers, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(peers && peers->world >= 1 && peers->world <= FMHR_MAX_PEERS && peers->rank >= 0 &&
+                   peers->rank < peers->world && peers->epoch && peers->reduced);
+    FMHR_CHECK_ARG(((uintptr_t)peers->reduced & 15) == 0);
+    for (int r = 0; r < peers->world; r++)
+        FMHR_CHECK_ARG(peers->packed[r] && peers->flags[r] && ((uintptr_t)peers->packed[r] & 15) == 0);
+    FMHR_CHECK_ARG(peers->packed[peers->rank] == buf->packed);  // the render pass accumulated into the shared buffer
+    return ham_update_impl(cfg, buf, peers, (cudaStream_t)stream);
+}
+
+// cudaIpc plumbing of the peer exchange: one allocation per rank (both packed buffers + the flag words), exported as a
+// 64-byte handle the host exchanges out of band (torch.distributed) and the peers map into their address space.
+extern "C" int fmhr_peer_alloc(size_t bytes, void** dev_ptr, void* handle64) {
+    FMHR_CHECK_ARG(bytes > 0 && dev_ptr && handle64);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    void* p = nullptr;
+    FMHR_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("fmhr_peer_alloc: %s", cudaGetErrorString(e));
+        return FMHR_ECUDA;
     }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_peer_open(const void* handle64, void** dev_ptr) {
+    FMHR_CHECK_ARG(handle64 && dev_ptr);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    FMHR_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_peer_close(void* dev_ptr) {
+    FMHR_CHECK_ARG(dev_ptr);
+    FMHR_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_peer_free(void* dev_ptr) {
+    FMHR_CHECK_ARG(dev_ptr);
+    FMHR_CUDA(cudaFree(dev_ptr));
     return FMHR_OK;
 }
 

@@ -1,6 +1,7 @@
 """Native HAM optimiser: the reference's two loops (mesh_sfs_optim.py:193-240 phase A, :242-317 phase B) with every
 iteration executed by two C-ABI calls (fmhr_ham_step_render / fmhr_ham_step_update) and, on more than one GPU, one
-NCCL all-reduce of the packed gradient buffer between them (views shard across ranks).
+exchange of the packed gradient buffer (views shard across ranks): fused into the update over NVLink peer
+memory (fmhr_ham_step_update_peer), or one NCCL all-reduce between the two calls.
 
 State names follow the reference: vertices_tmp, delta, albedo [1,V,3], sh_coeffs [num,9], valid_masks, ...
 """
@@ -11,13 +12,13 @@ import torch
 
 from . import _lib
 from ._lib import HamBuffers, HamConfig, check, ptr, stream
-from .dist import allreduce_packed
+from .dist import PeerExchange, allreduce_packed
 from .dr import Topology
 
 
 class HamOptimizer:
     def __init__(self, vertices, faces, imgs, masks, valid_masks, w2cs, projs, sh_coeffs, albedo, conf,
-                 process_group=None, n_views_global=None, debug=False, use_graphs=False):
+                 process_group=None, n_views_global=None, debug=False, use_graphs=False, exchange=None):
         """All tensors CUDA.  vertices [V,3], faces [F,3] int32, imgs [num,H,W,3], masks/valid_masks [num,H,W],
         w2cs/projs [num,4,4] (transposed, get_data.py:96-97), sh_coeffs [num,9], albedo [1,V,3] or [V,3];
         conf: dict with the weights and learning rates of conf/*.conf."""
@@ -57,6 +58,19 @@ class HamOptimizer:
         self.world = 1  # process_group=False forces a single-rank optimiser inside a distributed job
         if process_group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        # The one exchange of the path (sum of `packed` over the ranks): by default fused into the update's first kernel
+        # over NVLink peer memory (fmhr_ham_step_update_peer); exchange="nccl" (or FMHR_EXCHANGE=nccl, or peers that cannot
+        # be mapped) keeps one NCCL all-reduce between the two halves of the step.
+        self.peer = None
+        forced = exchange == "peer"  # an explicit "peer" also runs the exchange kernel on a single rank (tests)
+        exchange = exchange or os.environ.get("FMHR_EXCHANGE", "peer")
+        if exchange not in ("peer", "nccl"):
+            raise RuntimeError("fmhr_b200: exchange must be 'peer' or 'nccl'")
+        if exchange == "peer" and (self.world > 1 or forced):
+            px = PeerExchange(12 * self.V + 4, dev, process_group)
+            if forced and not px.ok:
+                raise RuntimeError("fmhr_b200: peer exchange requested but the ranks' buffers could not be mapped")
+            self.peer = px if px.ok else None
         self.n_views_global_override = n_views_global
         self.dbg_grad = torch.zeros(self.V, 6, dtype=torch.float32, device=dev) if debug else None
         self.dbg_grad_sh = None
@@ -226,18 +240,31 @@ class HamOptimizer:
         if torch.cuda.current_device() != self.device.index:
             torch.cuda.set_device(self.device)
         self._prepare_zbuf(cfg, buf)
-        sp = stream()
-        check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_render")
-        if self.world > 1:
-            allreduce_packed(self.packed, self.pg)  # one NCCL sum per iteration
-        check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_update")
+        self._run_step(cfg, buf, stream())
         return self.losses
+
+    def _run_step(self, cfg, buf, sp, part=None):
+        """The C-ABI calls of one iteration on stream `sp` (part: None = all, 0 = render, 1 = update)."""
+        if self.peer is not None:
+            buf.packed = self.peer.packed[cfg.zbuf_slot].data_ptr()  # the buffer alternates with the z-buffer slot
+        if part in (None, 0):
+            check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_render")
+        if part is None and self.world > 1 and self.peer is None:
+            allreduce_packed(self.packed, self.pg)  # one NCCL sum per iteration
+        if part in (None, 1):
+            if self.peer is not None:
+                check(self.lib.fmhr_ham_step_update_peer(ctypes.byref(cfg), ctypes.byref(buf),
+                                                         ctypes.byref(self.peer.structs[cfg.zbuf_slot]), sp),
+                      "ham_step_update_peer")
+            else:
+                check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_update")
 
     def _step_graph(self, phase, view_idx, albedo_weight):
         """CUDA-graph replay of the iteration: the launches + memsets of render/update are captured once per
         (phase, batch size, albedo_weight, z-buffer slot) and replayed with one launch; the step's view indices are
-        copied into a persistent device buffer the captured kernels read.  With more than one rank the NCCL all-reduce
-        runs eagerly between the two captured halves."""
+        copied into a persistent device buffer the captured kernels read.  With more than one rank the peer exchange is
+        part of the captured update (still one launch per iteration); the NCCL variant runs its all-reduce eagerly between
+        the two captured halves."""
         n = view_idx.numel() if torch.is_tensor(view_idx) else len(view_idx)
         key = (phase, n, None if albedo_weight is None else float(albedo_weight))
         ent = self._graphs.get(key)
@@ -258,7 +285,7 @@ class HamOptimizer:
         if vi.data_ptr() != idx_buf.data_ptr():
             idx_buf.copy_(vi, non_blocking=True)
         graphs[slot][0].replay()
-        if self.world > 1:
+        if len(graphs[slot]) > 1:
             allreduce_packed(self.packed, self.pg)
             graphs[slot][1].replay()
         return self.losses
@@ -275,7 +302,7 @@ class HamOptimizer:
         idx_buf.copy_(self._views(view_idx))
         state = (self.delta, self.albedo, self.sh_coeffs, self.adam_m, self.adam_v, self.adam_step)
         saved = [t.clone() for t in state]  # the warm-up runs below must not advance the optimiser
-        calls = ((self.lib.fmhr_ham_step_render, "ham_step_render"), (self.lib.fmhr_ham_step_update, "ham_step_update"))
+        split = self.world > 1 and self.peer is None  # NCCL variant: the all-reduce sits between two graphs
         torch.cuda.synchronize(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -284,17 +311,14 @@ class HamOptimizer:
             sp = _lib.c_p(side.cuda_stream)
             check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), sp), "ham_reset")
             for slot in (0, 1):  # warm-up outside capture (lazy module loading), slot 0 then 1 keeps the buffers sane
-                for fn, name in calls:
-                    check(fn(ctypes.byref(cfgs[slot]), ctypes.byref(bufs[slot]), sp), name)
+                self._run_step(cfgs[slot], bufs[slot], sp)
             side.synchronize()
             for slot in (0, 1):
-                groups = [calls] if self.world == 1 else [calls[:1], calls[1:]]
-                for grp in groups:
+                for part in ((0, 1) if split else (None,)):
                     gr = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gr, stream=side):
                         sp2 = _lib.c_p(torch.cuda.current_stream(self.device).cuda_stream)
-                        for fn, name in grp:
-                            check(fn(ctypes.byref(cfgs[slot]), ctypes.byref(bufs[slot]), sp2), name)
+                        self._run_step(cfgs[slot], bufs[slot], sp2, part)
                     graphs[slot].append(gr)
             check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), sp), "ham_reset")
         torch.cuda.current_stream(self.device).wait_stream(side)

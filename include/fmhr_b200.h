@@ -212,6 +212,33 @@ int fmhr_ham_prepare_views(const float* valid_masks, int num, int H, int W, doub
 int fmhr_ham_step_render(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
 /* normalises with the (all-reduced) counts, adds the regulariser gradients, applies Adam, writes `losses`. */
 int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
+/* ---- multi-GPU exchange over NVLink peer memory (replaces the ncclAllReduce of `packed` the reference
+ * design would place between loss.backward() and optimizer.step(), mesh_sfs_optim.py:309-310, when views shard) ----
+ * Every rank allocates its exchange memory with fmhr_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; zero-filled), the
+ * host exchanges the 64-byte handles out of band (torch.distributed) and maps the peers' allocations with
+ * fmhr_peer_open.  fmhr_ham_step_update_peer is fmhr_ham_step_update with the all-reduce fused into its first kernel:
+ * it posts this rank's step count into every peer's flag array, waits for all peers, sums the ranks' `packed` buffers
+ * in rank order over NVLink (bit-identical on every rank) into `reduced` and carries on with the update.  Contract:
+ *  - packed[r] = rank r's packed buffer of THIS step as mapped on this device, packed[rank] == buf->packed;
+ *  - consecutive steps must alternate between two packed buffers per rank (a peer may still read the previous one);
+ *  - flags[r]  = rank r's flag array, FMHR_MAX_PEERS uint32 words, zero before the first step;
+ *  - epoch     = one zero-initialised uint32 in local device memory (steps completed; advanced by the call);
+ *  - every rank makes the same sequence of calls.  A peer that does not arrive within ~3 s sets losses[7] = NaN
+ *    instead of hanging the device. */
+#define FMHR_MAX_PEERS 16
+typedef struct fmhr_ham_peers {
+    int32_t rank, world;
+    const float* packed[FMHR_MAX_PEERS];
+    uint32_t* flags[FMHR_MAX_PEERS];
+    uint32_t* epoch;
+    float* reduced;            /* [fmhr_ham_packed_floats] local sums, 16-byte aligned */
+} fmhr_ham_peers;
+int fmhr_peer_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int fmhr_peer_open(const void* handle64, void** dev_ptr);
+int fmhr_peer_close(void* dev_ptr);
+int fmhr_peer_free(void* dev_ptr);
+int fmhr_ham_step_update_peer(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const fmhr_ham_peers* peers,
+                              fmhr_stream_t stream);
 /* Inspection for parity tests: copies internal planes of the last fmhr_ham_step_render into caller buffers
  * (any may be NULL): pos [n,V,4], rast [n,H,W,4], image [n,H,W,3] (antialiased), pred_mask [n,H,W],
  * normals [V,3]. */

@@ -3,7 +3,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/multi_gpu_check.py
 
-Views are sharded round-robin over the ranks, each rank renders its shard, `packed` is all-reduced once per iteration;
+Views are sharded round-robin over the ranks, each rank renders its shard, `packed` is summed once per iteration (NCCL all-reduce, or the
+NVLink peer-memory gather fused into the update kernel, which must also leave every rank with bit-identical state);
 the result must equal a single-rank optimiser that renders all views in one batch.
 """
 import os
@@ -32,10 +33,13 @@ def main():
     c = lambda k, dt=torch.float32, sel=None: torch.tensor(scene[k] if sel is None else scene[k][sel], dtype=dt, device=dev)
     mine = shard_views(num, rank, world)
     ok = True
-    for graphs in (False, True):
+    for exchange, graphs in (("nccl", False), ("nccl", True), ("peer", False), ("peer", True)):
         sharded = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs", sel=mine), c("masks", sel=mine),
                                c("valid_masks", sel=mine), c("w2cs", sel=mine), c("projs", sel=mine),
-                               c("sh_coeffs", sel=mine), c("albedo"), scene["conf"], n_views_global=num, use_graphs=graphs)
+                               c("sh_coeffs", sel=mine), c("albedo"), scene["conf"], n_views_global=num, use_graphs=graphs,
+                               exchange=exchange)
+        if exchange == "peer" and sharded.peer is None:
+            raise SystemExit("peer exchange could not be set up")
         full = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
                             c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], process_group=False)
         for it in range(3):
@@ -45,10 +49,15 @@ def main():
             dd = float((sharded.delta - full.delta).abs().max()) / scene["conf"]["lr"]
             da = float((sharded.albedo - full.albedo).abs().max()) / scene["conf"]["albedo_lr"]
             good = good and dd < 0.05 and da < 0.05
+            if it == 0:  # replicas started from identical state: the exchange must leave them bit-identical
+                mine_state = torch.cat([sharded.delta.flatten(), sharded.albedo.flatten()])
+                states = [torch.empty_like(mine_state) for _ in range(world)]
+                dist.all_gather(states, mine_state)
+                good = good and all(torch.equal(states[0], s) for s in states[1:])
             ok = ok and good
             if rank == 0:
-                print("graphs=%s it=%d losses sharded %s full %s  |ddelta|/lr %.2e |dalbedo|/lr %.2e %s" % (
-                    graphs, it, [round(x, 5) for x in ls.tolist()[:6]], [round(x, 5) for x in lf.tolist()[:6]], dd, da,
+                print("exchange=%s graphs=%s it=%d losses sharded %s full %s  |ddelta|/lr %.2e |dalbedo|/lr %.2e %s" % (
+                    exchange, graphs, it, [round(x, 5) for x in ls.tolist()[:6]], [round(x, 5) for x in lf.tolist()[:6]], dd, da,
                     "OK" if good else "MISMATCH"))
             # keep the two trajectories on identical state (kinks of the hinge / L1 amplify 1e-7 differences)
             sharded.delta.copy_(full.delta); sharded.albedo.copy_(full.albedo)

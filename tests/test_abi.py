@@ -38,22 +38,26 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_struct_layout_matches_header(tmp_path):
-    from fmhr_b200._lib import HamBuffers, HamConfig
+    from fmhr_b200._lib import HamBuffers, HamConfig, HamPeers
     prog = tmp_path / "layout.c"
     fields_c = [f for f, _ in HamConfig._fields_]
     fields_b = [f for f, _ in HamBuffers._fields_]
+    fields_p = [f for f, _ in HamPeers._fields_]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fmhr_b200.h"', 'int main(void){',
-             'printf("%zu %zu\\n", sizeof(fmhr_ham_config), sizeof(fmhr_ham_buffers));']
+             'printf("%zu %zu %zu\\n", sizeof(fmhr_ham_config), sizeof(fmhr_ham_buffers), sizeof(fmhr_ham_peers));']
     lines += ['printf("%%zu\\n", offsetof(fmhr_ham_config, %s));' % f for f in fields_c]
     lines += ['printf("%%zu\\n", offsetof(fmhr_ham_buffers, %s));' % f for f in fields_b]
+    lines += ['printf("%%zu\\n", offsetof(fmhr_ham_peers, %s));' % f for f in fields_p]
     lines += ['return 0;}']
     prog.write_text("\n".join(lines))
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True).split()
     assert int(out[0]) == ctypes.sizeof(HamConfig) and int(out[1]) == ctypes.sizeof(HamBuffers)
-    offs = [int(x) for x in out[2:]]
-    want = [getattr(HamConfig, f).offset for f in fields_c] + [getattr(HamBuffers, f).offset for f in fields_b]
+    assert int(out[2]) == ctypes.sizeof(HamPeers)
+    offs = [int(x) for x in out[3:]]
+    want = [getattr(HamConfig, f).offset for f in fields_c] + [getattr(HamBuffers, f).offset for f in fields_b] + \
+           [getattr(HamPeers, f).offset for f in fields_p]
     assert offs == want
 
 

@@ -244,6 +244,30 @@ def test_graph_replay_matches_eager(scene):
     assert int(b.adam_step[0]) == 4 and len(b._graphs) == 2 and int(a.adam_step[0]) == 4
 
 
+def test_peer_exchange_single_rank_matches_plain(scene):
+    """fmhr_ham_step_update_peer with a world of one (the rank exchanges with itself through the cudaIpc-allocated,
+    slot-alternating packed buffers, flag words and step counter) follows the plain update, eager and graph replay;
+    the 2-rank case over NVLink is tests/multi_gpu_check.py."""
+    from fmhr_b200.ham import HamOptimizer
+    c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt).cuda()
+    mk = lambda **kw: HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"),
+                                   c("w2cs"), c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"],
+                                   process_group=False, **kw)
+    plain, eager, graph = mk(), mk(exchange="peer"), mk(exchange="peer", use_graphs=True)
+    assert eager.peer is not None and graph.peer is not None
+    n = scene["imgs"].shape[0]
+    for it, views in enumerate(([0, 1, 2], [3, 1, 0], list(range(n)), [2, 0, 1])):
+        lp = plain.step_phase_b(views).cpu()
+        for o in (eager, graph):
+            lo = o.step_phase_b(views).cpu()
+            assert torch.allclose(lp, lo, rtol=1e-4, atol=1e-6), (it, lp, lo)
+    for o in (eager, graph):
+        assert torch.allclose(plain.delta, o.delta, atol=2e-2 * scene["conf"]["lr"])
+        assert torch.allclose(plain.albedo, o.albedo, atol=2e-2 * scene["conf"]["albedo_lr"])
+    assert int(eager.peer.epoch) == 4       # one count per step
+    assert int(graph.peer.epoch) >= 4 + 4   # + two warm-up steps per graph capture (two batch sizes, re-captured on growth)
+
+
 def test_host_streaming_step_matches_resident(scene):
     """fmhr_ham_step_host (pinned host batch -> H2D -> render+update -> D2H loss record), the bench's e2e path."""
     from fmhr_b200.ham import HostStreamingStepper

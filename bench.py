@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-oneshot", "peer-twoshot", "nccl"],
                     help="N > 1: fused NVLink peer-memory exchange inside the update kernel, or one NCCL all-reduce")
     args = ap.parse_args()
     # Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout, so everything but the
@@ -240,7 +240,10 @@ def main():
     opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
                        c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs,
                        exchange=args.exchange if world > 1 else None)
-    exchange = "NVLink peer-memory gather fused into the update kernel" if opt.peer is not None else "1 NCCL all-reduce/iter"
+    exchange = "1 NCCL all-reduce/iter"
+    if opt.peer is not None:
+        exchange = "NVLink peer-memory exchange fused into the update kernels (%s)" % (
+            "two-shot reduce-scatter" if opt.peer.mode == 2 or (opt.peer.mode == 0 and world > 2) else "one-shot gather")
     V, F = opt.V, opt.T
     E = opt.topo.n_dir_edges // 2
     views = torch.arange(n, dtype=torch.int32, device=dev)

@@ -46,8 +46,9 @@ MAX_PEERS = 16
 
 class HamPeers(ctypes.Structure):
     """struct fmhr_ham_peers"""
-    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("packed", c_p * MAX_PEERS),
-                ("flags", c_p * MAX_PEERS), ("epoch", c_p), ("reduced", c_p)]
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("mode", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("packed", c_p * MAX_PEERS), ("flags", c_p * MAX_PEERS),
+                ("reduced", c_p * MAX_PEERS), ("epoch", c_p)]
 
 
 _SIGS = {

@@ -1632,8 +1632,13 @@ struct HamPeerArgs {
     uint32_t* signal[FMHR_MAX_PEERS];      // word [rank] of every rank's flag array: where this rank posts its step count
     const uint32_t* flags;                 // this rank's flag array [FMHR_MAX_PEERS], word r is posted by rank r
     const uint32_t* epoch;                 // steps this rank has completed (device counter, bumped by the Adam pass)
-    float4* reduced;                       // [3V + 1] sums over the ranks
+    float4* reduced;                       // [3V + 1] sums over the ranks (this rank's copy)
     int world;
+    // two-shot form (more than two ranks): rank k sums chunk k of the vertices and stores it into every rank's `reduced`
+    float4* reduced_all[FMHR_MAX_PEERS];
+    uint32_t* signal_b[FMHR_MAX_PEERS];    // second flag word per rank pair: "my chunk has landed in your `reduced`"
+    const uint32_t* flags_b;
+    int rank, chunk;                       // chunk = ceil(V / world) vertices per rank
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -1653,22 +1658,95 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 
 constexpr long long kPeerTimeoutCycles = 6000000000ll;  // ~3 s at 1.97 GHz: a lost peer flags the step instead of hanging
 
-__global__ void __launch_bounds__(256) ham_peer_reduce_normal_grad_kernel(int V, float4* __restrict__ vg,
-                                                                          const float4* __restrict__ vattr,
-                                                                          const float4* __restrict__ raw4, HamPeerArgs pa,
-                                                                          int* __restrict__ status) {
-    const uint32_t want = *pa.epoch + 1u;
-    if (threadIdx.x < pa.world) {
-        // every block posts the (idempotent) word, so no block ever waits on another block of this grid
+__device__ __forceinline__ void st_peer(float4* p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Block-level rendezvous with every peer: lanes 0..world-1 post this rank's step count into the peers' flag arrays and
+// wait for theirs.  Every block posts the (idempotent) word, so no block ever waits on another block of its own grid;
+// everything this rank wrote in earlier kernels of the stream is visible to a peer that has seen the word.
+__device__ __forceinline__ void peer_rendezvous(uint32_t* const* signal, const uint32_t* flags, int world, uint32_t want,
+                                                int* status) {
+    if (threadIdx.x < world) {
         __threadfence_system();
-        st_release_sys(pa.signal[threadIdx.x], want);
-        const uint32_t* f = pa.flags + threadIdx.x;
+        st_release_sys(signal[threadIdx.x], want);
+        const uint32_t* f = flags + threadIdx.x;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
             if (clock64() - t0 > kPeerTimeoutCycles) { atomicOr(status, 4); break; }
         }
     }
     __syncthreads();
+}
+
+// Two-shot exchange, kernel 1 (reduce-scatter + all-gather by peer stores): after the rendezvous thread j sums vertex
+// rank*chunk + j over every rank's `packed` (rank order) and stores the three sums into EVERY rank's `reduced`.
+__global__ void __launch_bounds__(256) ham_peer_reduce_scatter_kernel(int V, HamPeerArgs pa, int* __restrict__ status) {
+    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == pa.chunk) {  // the four loss scalars: rank 0
+        if (pa.rank != 0) return;
+        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < pa.world; r++) sc = add4(sc, ld_peer(pa.packed[r] + 3 * (size_t)V));
+        for (int r = 0; r < pa.world; r++) st_peer(pa.reduced_all[r] + 3 * (size_t)V, sc);
+        return;
+    }
+    const int i = pa.rank * pa.chunk + j;
+    if (j > pa.chunk || i >= V) return;
+    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, gm = ga;
+    for (int r0 = 0; r0 < pa.world; r0 += 4) {
+        float4 a[4], b[4], m[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (r0 + k < pa.world) {
+                const float4* p = pa.packed[r0 + k];
+                a[k] = ld_peer(p + 2 * (size_t)i);
+                b[k] = ld_peer(p + 2 * (size_t)i + 1);
+                m[k] = ld_peer(p + 2 * (size_t)V + i);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (r0 + k < pa.world) { ga = add4(ga, a[k]); gb = add4(gb, b[k]); gm = add4(gm, m[k]); }
+    }
+    for (int r = 0; r < pa.world; r++) {
+        float4* q = pa.reduced_all[r];
+        st_peer(q + 2 * (size_t)i, ga);
+        st_peer(q + 2 * (size_t)i + 1, gb);
+        st_peer(q + 2 * (size_t)V + i, gm);
+    }
+}
+
+// Two-shot exchange, kernel 2: second rendezvous (this rank's chunk is complete - the kernel boundary - and so is every
+// peer's), then the normal-gradient step from the local `reduced`.
+__global__ void __launch_bounds__(256) ham_peer_normal_grad_kernel(int V, float4* __restrict__ vg,
+                                                                   const float4* __restrict__ vattr,
+                                                                   const float4* __restrict__ raw4, HamPeerArgs pa,
+                                                                   int* __restrict__ status) {
+    peer_rendezvous(pa.signal_b, pa.flags_b, pa.world, *pa.epoch + 1u, status);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const float4 ga = ld_peer(pa.reduced + 2 * (size_t)i), gb = ld_peer(pa.reduced + 2 * (size_t)i + 1);
+    const float4 nrm = __ldg(vattr + 2 * (size_t)i);
+    const float4 N = raw4[i];
+    float3 r;
+    if (nrm.w == 0.0f) {
+        float3 t1, t2;
+        tangent_frame(make_float3(nrm.x, nrm.y, nrm.z), t1, t2);
+        const float inv = 1.0f / N.w;
+        r = make_float3((t1.x * ga.w + t2.x * gb.x) * inv, (t1.y * ga.w + t2.y * gb.x) * inv,
+                        (t1.z * ga.w + t2.z * gb.x) * inv);
+    } else {
+        const float gz = ld_peer(pa.reduced + 2 * (size_t)V + i).w;
+        r = make_float3(ga.w * 1e6f, gb.x * 1e6f, gz * 1e6f);
+    }
+    vg[2 * (size_t)i + 1] = make_float4(r.x, r.y, r.z, 0.f);
+}
+
+__global__ void __launch_bounds__(256) ham_peer_reduce_normal_grad_kernel(int V, float4* __restrict__ vg,
+                                                                          const float4* __restrict__ vattr,
+                                                                          const float4* __restrict__ raw4, HamPeerArgs pa,
+                                                                          int* __restrict__ status) {
+    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > V) return;
     if (i == V) {  // the four loss scalars behind the accumulators
@@ -1677,12 +1755,21 @@ __global__ void __launch_bounds__(256) ham_peer_reduce_normal_grad_kernel(int V,
         pa.reduced[3 * (size_t)V] = s;
         return;
     }
-    float4 ga = ld_peer(pa.packed[0] + 2 * (size_t)i), gb = ld_peer(pa.packed[0] + 2 * (size_t)i + 1),
-           gm = ld_peer(pa.packed[0] + 2 * (size_t)V + i);
-    for (int r = 1; r < pa.world; r++) {
-        const float4 a = ld_peer(pa.packed[r] + 2 * (size_t)i), b = ld_peer(pa.packed[r] + 2 * (size_t)i + 1),
-                     m = ld_peer(pa.packed[r] + 2 * (size_t)V + i);
-        ga = add4(ga, a); gb = add4(gb, b); gm = add4(gm, m);
+    // four ranks' lines in flight per round trip; the sums run in rank order on every rank
+    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, gm = ga;
+    for (int r0 = 0; r0 < pa.world; r0 += 4) {
+        float4 a[4], b[4], m[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (r0 + k < pa.world) {
+                const float4* p = pa.packed[r0 + k];
+                a[k] = ld_peer(p + 2 * (size_t)i);
+                b[k] = ld_peer(p + 2 * (size_t)i + 1);
+                m[k] = ld_peer(p + 2 * (size_t)V + i);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (r0 + k < pa.world) { ga = add4(ga, a[k]); gb = add4(gb, b[k]); gm = add4(gm, m[k]); }
     }
     pa.reduced[2 * (size_t)i] = ga;
     pa.reduced[2 * (size_t)i + 1] = gb;
@@ -2127,12 +2214,28 @@ static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
             pa.packed[r] = r < peers->world ? (const float4*)peers->packed[r] : nullptr;
             pa.signal[r] = r < peers->world ? peers->flags[r] + peers->rank : nullptr;
         }
+        for (int r = 0; r < FMHR_MAX_PEERS; r++) {
+            pa.reduced_all[r] = r < peers->world ? (float4*)peers->reduced[r] : nullptr;
+            pa.signal_b[r] = r < peers->world ? peers->flags[r] + FMHR_MAX_PEERS + peers->rank : nullptr;
+        }
         pa.flags = peers->flags[peers->rank];
+        pa.flags_b = peers->flags[peers->rank] + FMHR_MAX_PEERS;
         pa.epoch = peers->epoch;
-        pa.reduced = (float4*)peers->reduced;
+        pa.reduced = (float4*)peers->reduced[peers->rank];
         pa.world = peers->world;
-        ham_peer_reduce_normal_grad_kernel<<<cdiv(V + 1, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, pa, ws.status);
-        packed = peers->reduced;
+        pa.rank = peers->rank;
+        pa.chunk = cdiv(V, peers->world);
+        const bool two_shot = peers->mode == 2 || (peers->mode == 0 && peers->world > 2);
+        if (two_shot) {
+            // one-shot pulls world x 48 B per vertex into every rank; beyond two ranks the reduce-scatter form moves
+            // 1/world of that in and the same out (8 ranks: 16.6 MB -> 2 x 2.1 MB per rank and step)
+            ham_peer_reduce_scatter_kernel<<<cdiv(pa.chunk + 1, 256), 256, 0, st>>>(V, pa, ws.status);
+            FMHR_LAUNCH_CHECK();
+            ham_peer_normal_grad_kernel<<<cdiv(V, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, pa, ws.status);
+        } else {
+            ham_peer_reduce_normal_grad_kernel<<<cdiv(V + 1, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, pa, ws.status);
+        }
+        packed = peers->reduced[peers->rank];
         bump = peers->epoch;
     } else {
         ham_normal_grad_kernel<<<cdiv(V, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, (const float4*)buf->packed);
@@ -2167,10 +2270,10 @@ extern "C" int fmhr_ham_step_update_peer(const fmhr_ham_config* cfg, const fmhr_
     rc = ham_check_buffers(cfg, buf);
     if (rc) return rc;
     FMHR_CHECK_ARG(peers && peers->world >= 1 && peers->world <= FMHR_MAX_PEERS && peers->rank >= 0 &&
-                   peers->rank < peers->world && peers->epoch && peers->reduced);
-    FMHR_CHECK_ARG(((uintptr_t)peers->reduced & 15) == 0);
+                   peers->rank < peers->world && peers->epoch && peers->mode >= 0 && peers->mode <= 2);
     for (int r = 0; r < peers->world; r++)
-        FMHR_CHECK_ARG(peers->packed[r] && peers->flags[r] && ((uintptr_t)peers->packed[r] & 15) == 0);
+        FMHR_CHECK_ARG(peers->packed[r] && peers->flags[r] && peers->reduced[r] &&
+                       ((uintptr_t)peers->packed[r] & 15) == 0 && ((uintptr_t)peers->reduced[r] & 15) == 0);
     FMHR_CHECK_ARG(peers->packed[peers->rank] == buf->packed);  // the render pass accumulated into the shared buffer
     return ham_update_impl(cfg, buf, peers, (cudaStream_t)stream);
 }

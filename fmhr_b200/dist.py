@@ -42,13 +42,15 @@ class _RawCuda:
 class PeerExchange:
     """NVLink peer-memory exchange of the packed buffer (include/fmhr_b200.h, fmhr_ham_step_update_peer).
 
-    Each rank owns ONE cudaIpc-shared allocation [packed slot 0 | packed slot 1 | flag words]; the 64-byte handles travel
+    Each rank owns ONE cudaIpc-shared allocation [packed slot 0 | packed slot 1 | reduced | flag words]; the 64-byte handles travel
     through torch.distributed once at setup, after which an iteration needs no host-side collective at all: the update's
     first kernel posts / awaits the ranks' step counters and gathers the peers' accumulators itself.  Construction is
     collective (every rank of `group` must call it); `ok` is False on every rank if any rank could not map a peer, in
     which case the caller keeps the NCCL all-reduce."""
 
-    def __init__(self, n_floats, device, group=None):
+    MODES = {"auto": 0, "oneshot": 1, "twoshot": 2}
+
+    def __init__(self, n_floats, device, group=None, mode=None):
         from ._lib import MAX_PEERS, HamPeers, c_p, check, load
         dist = torch.distributed
         self.lib = load()
@@ -65,7 +67,7 @@ class PeerExchange:
         base = c_p()
         with torch.cuda.device(device):
             try:
-                check(self.lib.fmhr_peer_alloc(2 * self.slot_bytes + 4 * MAX_PEERS * 4, ctypes.byref(base), handle),
+                check(self.lib.fmhr_peer_alloc(3 * self.slot_bytes + 4 * MAX_PEERS * 4, ctypes.byref(base), handle),
                       "peer_alloc")
                 self.base = base.value
             except RuntimeError:
@@ -97,16 +99,19 @@ class PeerExchange:
             self.close()
             return
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
-        self.reduced = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.reduced = torch.as_tensor(_RawCuda(self.base + 2 * self.slot_bytes, n_floats), device=device)
+        import os
+        self.mode = self.MODES[mode or os.environ.get("FMHR_PEER_MODE", "auto")]
         self.packed = [torch.as_tensor(_RawCuda(self.base + s * self.slot_bytes, n_floats), device=device) for s in (0, 1)]
         self.structs = []
         for s in (0, 1):
             st = HamPeers()
-            st.rank, st.world = self.rank, self.world
+            st.rank, st.world, st.mode = self.rank, self.world, self.mode
             for r in range(self.world):
                 st.packed[r] = bases[r] + s * self.slot_bytes
-                st.flags[r] = bases[r] + 2 * self.slot_bytes
-            st.epoch, st.reduced = self.epoch.data_ptr(), self.reduced.data_ptr()
+                st.reduced[r] = bases[r] + 2 * self.slot_bytes
+                st.flags[r] = bases[r] + 3 * self.slot_bytes
+            st.epoch = self.epoch.data_ptr()
             self.structs.append(st)
 
     def close(self):

@@ -62,12 +62,12 @@ class HamOptimizer:
         # over NVLink peer memory (fmhr_ham_step_update_peer); exchange="nccl" (or FMHR_EXCHANGE=nccl, or peers that cannot
         # be mapped) keeps one NCCL all-reduce between the two halves of the step.
         self.peer = None
-        forced = exchange == "peer"  # an explicit "peer" also runs the exchange kernel on a single rank (tests)
+        forced = exchange is not None and exchange.startswith("peer")  # explicit: also on a single rank (tests)
         exchange = exchange or os.environ.get("FMHR_EXCHANGE", "peer")
-        if exchange not in ("peer", "nccl"):
-            raise RuntimeError("fmhr_b200: exchange must be 'peer' or 'nccl'")
-        if exchange == "peer" and (self.world > 1 or forced):
-            px = PeerExchange(12 * self.V + 4, dev, process_group)
+        if exchange not in ("peer", "peer-oneshot", "peer-twoshot", "nccl"):
+            raise RuntimeError("fmhr_b200: exchange must be 'peer', 'peer-oneshot', 'peer-twoshot' or 'nccl'")
+        if exchange.startswith("peer") and (self.world > 1 or forced):
+            px = PeerExchange(12 * self.V + 4, dev, process_group, mode=exchange[5:] or None)
             if forced and not px.ok:
                 raise RuntimeError("fmhr_b200: peer exchange requested but the ranks' buffers could not be mapped")
             self.peer = px if px.ok else None

@@ -218,20 +218,26 @@ int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf
  * host exchanges the 64-byte handles out of band (torch.distributed) and maps the peers' allocations with
  * fmhr_peer_open.  fmhr_ham_step_update_peer is fmhr_ham_step_update with the all-reduce fused into its first kernel:
  * it posts this rank's step count into every peer's flag array, waits for all peers, sums the ranks' `packed` buffers
- * in rank order over NVLink (bit-identical on every rank) into `reduced` and carries on with the update.  Contract:
+ * in rank order over NVLink (bit-identical on every rank) into `reduced` and carries on with the update.  Up to two
+ * ranks every rank gathers all accumulators itself (one kernel); beyond that rank k sums vertex chunk k and stores it
+ * into every rank's `reduced`, and a second rendezvous opens the normal-gradient kernel (two kernels).  Contract:
  *  - packed[r] = rank r's packed buffer of THIS step as mapped on this device, packed[rank] == buf->packed;
  *  - consecutive steps must alternate between two packed buffers per rank (a peer may still read the previous one);
- *  - flags[r]  = rank r's flag array, FMHR_MAX_PEERS uint32 words, zero before the first step;
+ *  - flags[r]  = rank r's flag array, 2 * FMHR_MAX_PEERS uint32 words, zero before the first step;
+ *  - reduced[r] = rank r's sum buffer (one per rank is enough: a peer can only store into it again after this rank
+ *    has posted the next step);
  *  - epoch     = one zero-initialised uint32 in local device memory (steps completed; advanced by the call);
  *  - every rank makes the same sequence of calls.  A peer that does not arrive within ~3 s sets losses[7] = NaN
  *    instead of hanging the device. */
 #define FMHR_MAX_PEERS 16
 typedef struct fmhr_ham_peers {
     int32_t rank, world;
+    int32_t mode;              /* 0 = by world size, 1 = one-shot gather, 2 = two-shot (reduce-scatter + peer stores) */
+    int32_t reserved;
     const float* packed[FMHR_MAX_PEERS];
     uint32_t* flags[FMHR_MAX_PEERS];
+    float* reduced[FMHR_MAX_PEERS]; /* every rank's [fmhr_ham_packed_floats] sum buffer (in its shared allocation) */
     uint32_t* epoch;
-    float* reduced;            /* [fmhr_ham_packed_floats] local sums, 16-byte aligned */
 } fmhr_ham_peers;
 int fmhr_peer_alloc(size_t bytes, void** dev_ptr, void* handle64);
 int fmhr_peer_open(const void* handle64, void** dev_ptr);

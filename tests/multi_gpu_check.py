@@ -33,12 +33,13 @@ def main():
     c = lambda k, dt=torch.float32, sel=None: torch.tensor(scene[k] if sel is None else scene[k][sel], dtype=dt, device=dev)
     mine = shard_views(num, rank, world)
     ok = True
-    for exchange, graphs in (("nccl", False), ("nccl", True), ("peer", False), ("peer", True)):
+    for exchange, graphs in (("nccl", False), ("nccl", True), ("peer-oneshot", False), ("peer-oneshot", True),
+                             ("peer-twoshot", False), ("peer-twoshot", True)):
         sharded = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs", sel=mine), c("masks", sel=mine),
                                c("valid_masks", sel=mine), c("w2cs", sel=mine), c("projs", sel=mine),
                                c("sh_coeffs", sel=mine), c("albedo"), scene["conf"], n_views_global=num, use_graphs=graphs,
                                exchange=exchange)
-        if exchange == "peer" and sharded.peer is None:
+        if exchange != "nccl" and sharded.peer is None:
             raise SystemExit("peer exchange could not be set up")
         full = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
                             c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], process_group=False)

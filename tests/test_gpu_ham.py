@@ -254,14 +254,15 @@ def test_peer_exchange_single_rank_matches_plain(scene):
                                    c("w2cs"), c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"],
                                    process_group=False, **kw)
     plain, eager, graph = mk(), mk(exchange="peer"), mk(exchange="peer", use_graphs=True)
-    assert eager.peer is not None and graph.peer is not None
+    two = mk(exchange="peer-twoshot", use_graphs=True)  # the reduce-scatter form used beyond two ranks
+    assert eager.peer is not None and graph.peer is not None and two.peer.mode == 2
     n = scene["imgs"].shape[0]
     for it, views in enumerate(([0, 1, 2], [3, 1, 0], list(range(n)), [2, 0, 1])):
         lp = plain.step_phase_b(views).cpu()
-        for o in (eager, graph):
+        for o in (eager, graph, two):
             lo = o.step_phase_b(views).cpu()
             assert torch.allclose(lp, lo, rtol=1e-4, atol=1e-6), (it, lp, lo)
-    for o in (eager, graph):
+    for o in (eager, graph, two):
         assert torch.allclose(plain.delta, o.delta, atol=2e-2 * scene["conf"]["lr"])
         assert torch.allclose(plain.albedo, o.albedo, atol=2e-2 * scene["conf"]["albedo_lr"])
     assert int(eager.peer.epoch) == 4       # one count per step

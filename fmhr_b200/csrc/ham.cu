@@ -1983,6 +1983,10 @@ struct SideStream {
     cudaEvent_t fork = nullptr, join = nullptr, records = nullptr;
     cudaStream_t copy = nullptr;              // host-batch uploads of fmhr_ham_step_host_u8
     cudaEvent_t copy_fork = nullptr, ready = nullptr;
+    // pipelined host batches (fmhr_ham_host_u8_submit): two staging slots in flight
+    const void* slot_ptr[2] = {nullptr, nullptr};
+    cudaEvent_t slot_ready[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
     int dev = -1;
 };
 // Host batch in flight (fmhr_ham_step_host_u8): the render chain converts it right before the first kernel that reads
@@ -1990,6 +1994,7 @@ struct SideStream {
 struct PendingInputs {
     const uint8_t* staging = nullptr;  // device: [n*H*W*3 image bytes | n*H*W mask bytes]
     cudaEvent_t ready = nullptr;
+    cudaEvent_t consumed = nullptr;    // recorded after the conversion kernel (pipelined form: the slot may be refilled)
 };
 static thread_local PendingInputs g_pending;
 static int side_stream(SideStream** out) {
@@ -2006,6 +2011,10 @@ static int side_stream(SideStream** out) {
         FMHR_CUDA(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.copy_fork, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            FMHR_CUDA(cudaEventCreateWithFlags(&s.slot_ready[i], cudaEventDisableTiming));
+            FMHR_CUDA(cudaEventCreateWithFlags(&s.slot_free[i], cudaEventDisableTiming));
+        }
         s.dev = dev;
     }
     *out = &s;
@@ -2102,6 +2111,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         ham_u8_to_f32_kernel<<<cdiv((long long)n_all4, 256), 256, 0, st>>>((const uchar4*)g_pending.staging, n_img4, n_all4,
                                                                           (float4*)b->imgs, (float4*)b->masks);
         FMHR_LAUNCH_CHECK();
+        if (g_pending.consumed) FMHR_CUDA(cudaEventRecord(g_pending.consumed, st));
         g_pending.staging = nullptr;
     }
     static const int g_scan = persistent_blocks(ham_scan_kernel);
@@ -2433,6 +2443,7 @@ extern "C" int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_
     FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
     g_pending.staging = (const uint8_t*)staging;
     g_pending.ready = side->ready;
+    g_pending.consumed = nullptr;
     rc = fmhr_ham_step_render(cfg, buf, stream);
     g_pending.staging = nullptr;
     if (rc) return rc;
@@ -2442,6 +2453,70 @@ extern "C" int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_
     return FMHR_OK;
 }
 
+
+// Pipelined form of the host-batch step: the NEXT step's batch is uploaded while the current step computes, so a
+// PCIe-bound loop runs at the transfer rate instead of transfer + the post-upload half of the iteration.
+extern "C" int fmhr_ham_host_u8_submit(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
+                                       void* staging) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(imgs_host && masks_host && staging && ((uintptr_t)staging & 15) == 0);
+    const size_t P = (size_t)cfg->n_views * cfg->H * cfg->W;
+    FMHR_CHECK_ARG(P % 4 == 0);
+    SideStream* side = nullptr;
+    rc = side_stream(&side);
+    if (rc) return rc;
+    int slot = side->slot_ptr[0] == staging ? 0 : (side->slot_ptr[1] == staging ? 1 : -1);
+    if (slot < 0) slot = side->slot_ptr[0] == nullptr ? 0 : (side->slot_ptr[1] == nullptr ? 1 : -1);
+    if (slot < 0) slot = side->slot_used[0] ? 0 : (side->slot_used[1] ? 1 : -1);  // a consumed buffer gives way to a new one
+    if (slot < 0) {
+        set_error("fmhr_ham_host_u8_submit: two submitted batches are already waiting for their steps on this device");
+        return FMHR_EINVAL;
+    }
+    if (side->slot_ptr[slot] == staging && side->slot_used[slot])  // the conversion of its previous batch has been issued
+        FMHR_CUDA(cudaStreamWaitEvent(side->copy, side->slot_free[slot], 0));
+    side->slot_ptr[slot] = staging;
+    side->slot_used[slot] = false;
+    FMHR_CUDA(cudaMemcpyAsync(staging, imgs_host, P * 3, cudaMemcpyHostToDevice, side->copy));
+    FMHR_CUDA(cudaMemcpyAsync((char*)staging + P * 3, masks_host, P, cudaMemcpyHostToDevice, side->copy));
+    FMHR_CUDA(cudaEventRecord(side->slot_ready[slot], side->copy));
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf,
+                                               const float* w2cs_host, const float* projs_host, void* staging,
+                                               float* losses_host, fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(w2cs_host && projs_host && staging && losses_host);
+    FMHR_CHECK_ARG(((uintptr_t)buf->imgs & 15) == 0 && ((uintptr_t)buf->masks & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    SideStream* side = nullptr;
+    rc = side_stream(&side);
+    if (rc) return rc;
+    const int slot = side->slot_ptr[0] == staging ? 0 : (side->slot_ptr[1] == staging ? 1 : -1);
+    if (slot < 0 || side->slot_used[slot]) {
+        set_error("fmhr_ham_step_host_u8_submitted: no batch was submitted into this staging buffer");
+        return FMHR_EINVAL;
+    }
+    const size_t n = cfg->n_views;
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->w2cs, w2cs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    g_pending.staging = (const uint8_t*)staging;
+    g_pending.ready = side->slot_ready[slot];
+    g_pending.consumed = side->slot_free[slot];
+    rc = fmhr_ham_step_render(cfg, buf, stream);
+    g_pending.staging = nullptr;
+    g_pending.consumed = nullptr;
+    if (rc) return rc;
+    side->slot_used[slot] = true;
+    rc = fmhr_ham_step_update(cfg, buf, stream);
+    if (rc) return rc;
+    FMHR_CUDA(cudaMemcpyAsync(losses_host, buf->losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return FMHR_OK;
+}
 
 extern "C" size_t fmhr_ham_init_scratch_bytes(int num) { return num > 0 ? (size_t)(num + 1) * 56 * sizeof(double) : 0; }
 

@@ -455,3 +455,43 @@ class HostStreamingStepper:
                                               ptr(h_w2cs), ptr(h_projs), ptr(self.staging), ptr(self.losses_host),
                                               stream()), "ham_step_host_u8")
         return self.losses_host
+
+    # ---- pipelined form: the next step's batch travels while the current step computes
+    def submit_u8(self, h_imgs_u8, h_masks_u8):
+        """Start the upload of a host batch (pinned uint8 images [n,H,W,3] / masks [n,H,W]) into the next free staging
+        buffer; returns a ticket for step_submitted_u8.  At most two batches may be in flight."""
+        o = self.opt
+        for t in (h_imgs_u8, h_masks_u8):
+            if t.is_cuda or not t.is_contiguous() or t.dtype != torch.uint8 or not t.is_pinned():
+                raise RuntimeError("HostStreamingStepper: host batches must be pinned, contiguous uint8 CPU tensors")
+        cfg = o._cfg(self.n, 1, None)
+        if getattr(self, "_stagings", None) is None:
+            nbytes = o.lib.fmhr_ham_host_u8_staging_bytes(ctypes.byref(cfg))
+            self._stagings = [torch.empty(nbytes, dtype=torch.uint8, device=o.device) for _ in range(2)]
+            self._next_slot = 0
+        slot = self._next_slot
+        self._next_slot ^= 1
+        with torch.cuda.device(o.device):
+            check(o.lib.fmhr_ham_host_u8_submit(ctypes.byref(cfg), ptr(h_imgs_u8), ptr(h_masks_u8),
+                                                ptr(self._stagings[slot])), "ham_host_u8_submit")
+        return slot
+
+    def step_submitted_u8(self, ticket, h_w2cs, h_projs, sh_rows, albedo_weight=None):
+        """The iteration on the batch submitted under `ticket` (cameras: pinned float32 [n,4,4])."""
+        o = self.opt
+        for t in (h_w2cs, h_projs):
+            if t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or not t.is_pinned():
+                raise RuntimeError("HostStreamingStepper: cameras must be pinned, contiguous float32 CPU tensors")
+        if o.phase != 1:
+            o.begin_phase_b()
+        if o.world > 1:
+            raise RuntimeError("HostStreamingStepper is single-process; use HamOptimizer under torch.distributed")
+        cfg = o._cfg(self.n, 1, albedo_weight)
+        buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows,
+                         self.d_vm2)
+        with torch.cuda.device(o.device):
+            o._prepare_zbuf(cfg, buf)
+            check(o.lib.fmhr_ham_step_host_u8_submitted(ctypes.byref(cfg), ctypes.byref(buf), ptr(h_w2cs), ptr(h_projs),
+                                                        ptr(self._stagings[ticket]), ptr(self.losses_host), stream()),
+                  "ham_step_host_u8_submitted")
+        return self.losses_host

@@ -273,6 +273,15 @@ int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_buffers* bu
                           const uint8_t* masks_host, const float* w2cs_host, const float* projs_host, void* staging,
                           float* losses_host, fmhr_stream_t stream);
 
+/* Pipelined form of the same step (a loader thread decodes batch i+1 while step i runs): fmhr_ham_host_u8_submit starts
+ * the upload of a batch into `staging` on the internal copy stream and returns at once; up to two staging buffers may be
+ * in flight per device, and a buffer is only overwritten after the conversion kernel of its previous batch.
+ * fmhr_ham_step_host_u8_submitted runs the iteration on the batch last submitted into `staging`. */
+int fmhr_ham_host_u8_submit(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
+                            void* staging);
+int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* w2cs_host,
+                                    const float* projs_host, void* staging, float* losses_host, fmhr_stream_t stream);
+
 /* HAM initialisation (mesh_sfs_optim.py:124-177) on the same fused forward chain: every view of the batch is rendered
  * once (n_views rows of view_idx, normally all views), normals and coverage are antialiased, and
  *   valid_masks_out [n_views,H,W] = antialiased coverage of the initial mesh (:146,163; indexed by view SLOT),

@@ -324,6 +324,46 @@ def test_host_streaming_u8_step_matches_resident(scene):
         stepper.step_phase_b_u8(h[0].float().pin_memory(), h[1], h[2], h[3], views)
 
 
+def test_host_streaming_u8_pipelined_matches_resident(scene):
+    """fmhr_ham_host_u8_submit / fmhr_ham_step_host_u8_submitted: the batch of step i+1 is uploaded while step i runs, two
+    staging buffers in flight.  Two DIFFERENT batches alternate, so consuming the wrong slot (or a slot refilled too
+    early) changes the losses; must equal the resident path fed with the same quantised images step by step."""
+    import copy
+    from fmhr_b200.ham import HostStreamingStepper
+    n, H, W = scene["imgs"].shape[0], scene["imgs"].shape[1], scene["imgs"].shape[2]
+    if (n * H * W) % 4:
+        pytest.skip("u8 path needs n*H*W % 4 == 0")
+    img_a = np.clip(np.rint(np.asarray(scene["imgs"], dtype=np.float64) * 255.0), 0, 255).astype(np.uint8)
+    img_b = (img_a // 2 + 17).astype(np.uint8)
+    msk_u8 = (np.asarray(scene["masks"]) > 0).astype(np.uint8) * 255
+    q = copy.copy(scene)
+    q["imgs"] = img_a.astype(np.float32) / np.float32(255.0)
+    q["masks"] = (msk_u8 > 127).astype(np.float32)
+    a = _make_opt(q, debug=False)
+    b = _make_opt(q, debug=False)
+    f_imgs = [torch.tensor(x.astype(np.float32) / np.float32(255.0)).cuda() for x in (img_a, img_b)]
+    views = torch.arange(n, dtype=torch.int32, device="cuda")
+    stepper = HostStreamingStepper(b, n)
+    stepper.set_resident_valid_masks(b.valid_masks)
+    pin = lambda x, dt: torch.tensor(x, dtype=dt).contiguous().pin_memory()
+    h_imgs = [pin(img_a, torch.uint8), pin(img_b, torch.uint8)]
+    h_msk, h_w2c, h_proj = pin(msk_u8, torch.uint8), pin(scene["w2cs"], torch.float32), pin(scene["projs"], torch.float32)
+    steps = 5
+    ticket = stepper.submit_u8(h_imgs[0], h_msk)
+    for i in range(steps):
+        nxt = stepper.submit_u8(h_imgs[(i + 1) % 2], h_msk) if i + 1 < steps else None
+        a.imgs.copy_(f_imgs[i % 2])
+        la = a.step_phase_b(views).cpu()
+        stepper.step_submitted_u8(ticket, h_w2c, h_proj, views)
+        torch.cuda.synchronize()
+        assert torch.allclose(la, stepper.losses_host, rtol=1e-4, atol=1e-6), (i, la, stepper.losses_host)
+        assert torch.equal(stepper.d_imgs, f_imgs[i % 2])
+        ticket = nxt
+    assert torch.allclose(a.delta, b.delta, atol=2e-2 * scene["conf"]["lr"])
+    with pytest.raises(RuntimeError):  # nothing submitted into that slot any more
+        stepper.step_submitted_u8(0, h_w2c, h_proj, views)
+
+
 def test_two_hands_and_full_size_properties():
     """BASELINE.json configs 2 and 4 at their full shapes, through size-independent properties: the fused path's
     coverage equals the stand-alone rasterize op on the same clip positions (bit-exact, GPU vs GPU), is deterministic

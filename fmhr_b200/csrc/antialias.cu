@@ -6,20 +6,19 @@
 
 namespace fmhr {
 
+constexpr int kAARow = 128;  // threads per row segment
 template <bool BWD>
-__global__ void __launch_bounds__(256) antialias_kernel(const float* __restrict__ color,
+__global__ void __launch_bounds__(kAARow) antialias_kernel(const float* __restrict__ color,
                                                         const float4* __restrict__ rast,
                                                         const float* __restrict__ pos, const int32_t* __restrict__ tri,
                                                         const int32_t* __restrict__ opp,
                                                         const float* __restrict__ dy, int H, int W, int C, int V, int T,
                                                         size_t npix, float* __restrict__ out,
                                                         float* __restrict__ grad_pos) {
-    const size_t pix0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix0 >= npix) return;
-    const size_t hw = (size_t)H * W;
-    const int n = (int)(pix0 / hw);
-    const int rem = (int)(pix0 - (size_t)n * hw);
-    const int py = rem / W, px = rem - py * W;
+    // grid = (row segments, rows, views): no per-thread index divisions in a kernel that is otherwise a stream
+    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y, n = blockIdx.z;
+    if (px >= W) return;
+    const size_t pix0 = ((size_t)n * H + py) * W + px;
     const float4 r0 = __ldg(rast + pix0);
     const float* P = pos + (size_t)n * V * 4;
 #pragma unroll
@@ -69,7 +68,8 @@ extern "C" int fmhr_antialias_fwd(const float* color, const float* rast, const f
     cudaStream_t st = (cudaStream_t)stream;
     const size_t npix = (size_t)N * H * W;
     FMHR_CUDA(cudaMemcpyAsync(out, color, npix * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    antialias_kernel<false><<<cdiv(npix, 256), 256, 0, st>>>(color, (const float4*)rast, pos, tri, opp, nullptr, H, W,
+    FMHR_CHECK_ARG(H <= 65535 && N <= 65535);
+    antialias_kernel<false><<<dim3(cdiv(W, kAARow), H, N), kAARow, 0, st>>>(color, (const float4*)rast, pos, tri, opp, nullptr, H, W,
                                                              C, V, T, npix, out, nullptr);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
@@ -84,7 +84,8 @@ extern "C" int fmhr_antialias_bwd(const float* color, const float* rast, const f
     const size_t npix = (size_t)N * H * W;
     FMHR_CUDA(cudaMemcpyAsync(grad_color, dy, npix * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (grad_pos) FMHR_CUDA(cudaMemsetAsync(grad_pos, 0, (size_t)N * V * 4 * sizeof(float), st));
-    antialias_kernel<true><<<cdiv(npix, 256), 256, 0, st>>>(color, (const float4*)rast, pos, tri, opp, dy, H, W, C, V,
+    FMHR_CHECK_ARG(H <= 65535 && N <= 65535);
+    antialias_kernel<true><<<dim3(cdiv(W, kAARow), H, N), kAARow, 0, st>>>(color, (const float4*)rast, pos, tri, opp, dy, H, W, C, V,
                                                             T, npix, grad_color, grad_pos);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;

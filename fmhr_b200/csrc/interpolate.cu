@@ -4,29 +4,55 @@
 
 namespace fmhr {
 
-// One thread per OUTPUT ELEMENT (pixel, channel): stores are perfectly coalesced for any A (A=7 rows are 28 B,
-// not vectorisable per pixel), the 16-byte rast texel is a warp-broadcast L1 hit, attribute gathers are
-// contiguous in the channel index.
+// One thread per OUTPUT float4: a row of A floats is not 16-byte aligned for A = 7 / 6 / 30, but the output plane as a
+// whole is, so thread q produces elements 4q .. 4q+3 of the flat [P*A] array (they straddle at most two pixels for
+// A >= 4) with one coalesced 128-bit store.  The kernel is a stream: 92 % of the pixels of the HAM workloads are
+// empty, so the common case is "read the id word of one or two rast texels, store a zero float4"; A is a template
+// parameter for the widths the reference uses (the divisions become multiply-shift), 0 = run-time width.
+template <int AT>
 __global__ void __launch_bounds__(256) interpolate_fwd_kernel(const float* __restrict__ attr,
                                                               const float4* __restrict__ rast,
                                                               const int32_t* __restrict__ tri, int NA, int V, int T,
-                                                              size_t hw, int A, size_t nelem, float* __restrict__ out) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nelem) return;
-    const size_t pix = e / A;
-    const int k = (int)(e - pix * A);
-    const float4 r = __ldg(rast + pix);
-    const int t = (int)r.w - 1;
-    float o = 0.0f;
-    if (t >= 0 && t < T) {
-        const int n = (int)(pix / hw);
-        const float* At = attr + (NA == 1 ? 0 : (size_t)n * V * A);
-        const float a0 = __ldg(At + (size_t)__ldg(tri + 3 * t) * A + k);
-        const float a1 = __ldg(At + (size_t)__ldg(tri + 3 * t + 1) * A + k);
-        const float a2 = __ldg(At + (size_t)__ldg(tri + 3 * t + 2) * A + k);
-        o = r.x * a0 + r.y * a1 + (1.0f - r.x - r.y) * a2;
+                                                              unsigned hw, int A_rt, size_t nquads, size_t nelem,
+                                                              float* __restrict__ out) {
+    const int A = AT > 0 ? AT : A_rt;
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nquads) return;
+    const size_t e0 = 4 * q;
+    const size_t pix0 = e0 / (unsigned)A;  // one 64-bit division per thread (by a constant for the templated widths)
+    unsigned k = (unsigned)(e0 - pix0 * (unsigned)A);
+    size_t pix = pix0;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    float u = 0.f, v = 0.f;
+    const float *A0 = nullptr, *A1 = nullptr, *A2 = nullptr;
+    bool have = false, covered = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (e0 + j < nelem) {
+            if (!have) {  // first element of a pixel handled by this thread: fetch its texel
+                have = true;
+                const float idw = __ldg(reinterpret_cast<const float*>(rast + pix) + 3);
+                const int t = (int)idw - 1;
+                covered = t >= 0 && t < T;
+                if (covered) {
+                    const float4 r = __ldg(rast + pix);
+                    u = r.x; v = r.y;
+                    const unsigned n = (unsigned)(pix / hw);
+                    const float* At = attr + (NA == 1 ? 0 : (size_t)n * V * A);
+                    A0 = At + (size_t)__ldg(tri + 3 * t) * A;
+                    A1 = At + (size_t)__ldg(tri + 3 * t + 1) * A;
+                    A2 = At + (size_t)__ldg(tri + 3 * t + 2) * A;
+                }
+            }
+            if (covered) o[j] = u * __ldg(A0 + k) + v * __ldg(A1 + k) + (1.0f - u - v) * __ldg(A2 + k);
+            if (++k == (unsigned)A) { k = 0; pix++; have = false; }
+        }
     }
-    out[e] = o;
+    if (e0 + 3 < nelem) {
+        reinterpret_cast<float4*>(out)[q] = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int j = 0; j < 4 && e0 + j < nelem; j++) out[e0 + j] = o[j];
+    }
 }
 
 // One thread per pixel; covered pixels scatter u/v/w-weighted dy to the three vertices and reduce d/du, d/dv.
@@ -75,8 +101,24 @@ extern "C" int fmhr_interpolate_fwd(const float* attr, const float* rast, const 
     FMHR_CHECK_ARG(N > 0 && V > 0 && T >= 0 && H > 0 && W > 0 && A > 0);
     FMHR_CHECK_ARG(NA == N || NA == 1);
     const size_t nelem = (size_t)N * H * W * A;
-    interpolate_fwd_kernel<<<cdiv(nelem, 256), 256, 0, (cudaStream_t)stream>>>(attr, (const float4*)rast, tri, NA, V,
-                                                                               T, (size_t)H * W, A, nelem, out);
+    const size_t nquads = (nelem + 3) / 4;
+    FMHR_CHECK_ARG(((uintptr_t)out & 15) == 0 && ((uintptr_t)rast & 15) == 0);
+    const unsigned hw = (unsigned)((size_t)H * W);
+    const dim3 grid((unsigned)cdiv(nquads, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+#define FMHR_INTERP(AT)                                                                                              \
+    interpolate_fwd_kernel<AT><<<grid, 256, 0, st>>>(attr, (const float4*)rast, tri, NA, V, T, hw, A, nquads, nelem, out)
+    switch (A) {  // the widths of the reference's call sites
+        case 1: FMHR_INTERP(1); break;
+        case 3: FMHR_INTERP(3); break;
+        case 4: FMHR_INTERP(4); break;
+        case 6: FMHR_INTERP(6); break;
+        case 7: FMHR_INTERP(7); break;
+        case 10: FMHR_INTERP(10); break;
+        case 30: FMHR_INTERP(30); break;
+        default: FMHR_INTERP(0); break;
+    }
+#undef FMHR_INTERP
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

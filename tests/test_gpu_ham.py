@@ -175,6 +175,50 @@ def test_fused_phase_b_step(scene):
         _sync_oracle(st, opt, phase_b=True)
 
 
+def test_fused_step_with_empty_and_clipped_views():
+    """Edge cases of the view batch: one camera that sees nothing (the hand is behind it: every triangle is discarded by
+    the w <= 0 rule, so the view only contributes its valid_mask to the mask loss) and one whose frame cuts the hand
+    (coverage up to the image border: the antialias pairs and the ring list must stop at the edge)."""
+    import copy
+    base = synth.build_scene("small", oham.render_views)
+    scene = copy.copy(base)
+    w2cs = np.array(base["w2cs"], dtype=np.float32, copy=True)
+    w2cs[1, :, 2] *= -1.0          # row-vector convention: negate camera z of view 1 -> the mesh lies behind it
+    scene["w2cs"] = w2cs
+    n = scene["imgs"].shape[0]
+    probe = _make_opt(scene)
+    tx0 = float(w2cs[2, 3, 0])
+    for shift in np.arange(0.04, 1.0, 0.02):  # slide view 2 sideways until the frame cuts the hand
+        probe.w2cs[2, 3, 0] = tx0 + float(shift)
+        ids2 = probe.export([2])["rast"][0, :, :, 3]
+        if bool((ids2[:, 0] > 0).any() or (ids2[:, -1] > 0).any()):
+            break
+    w2cs[2, 3, 0] = tx0 + float(shift)
+    opt = _make_opt(scene)
+    st = oham.HamState(scene)
+    ids = opt.export(list(range(n)))["rast"][..., 3]
+    assert int((ids[1] > 0).sum()) == 0, "view 1 must be empty"
+    assert int((ids[2] > 0).sum()) > 0 and bool((ids[2][:, 0] > 0).any() or (ids[2][:, -1] > 0).any()), \
+        "view 2 must be cut by the image border"
+    for it, views in enumerate([list(range(n)), [2, 1, 0], [1]]):
+        keep = {}
+        if views == [1]:
+            # no valid pixel at all: the reference's F.l1_loss over an empty selection is NaN (SURVEY.md App. B a8);
+            # the fused path reports n_valid = 0 and a non-finite photometric loss as well, and must not crash
+            rec = opt.step_phase_b(views).cpu().tolist()
+            assert rec[6] == 0.0 and not np.isfinite(rec[0])
+            break
+        ref = oham.phase_b_step(st, views, keep=keep)
+        rec = opt.step_phase_b(views).cpu().tolist()
+        for k, name in enumerate(["sfs", "lap", "albedo", "mask", "edge", "delta"]):
+            assert abs(rec[k] - ref[name]) <= 2e-5 * abs(ref[name]) + 1e-7, (it, name, rec[k], ref[name])
+        assert rec[6] == ref["n_valid"], (rec[6], ref["n_valid"])
+        g = opt.dbg_grad.cpu()
+        assert _rel(g[:, :3], keep["grad_delta"]) < 2e-4, it
+        assert _rel(g[:, 3:], keep["grad_albedo"][0]) < 2e-4, it
+        _sync_oracle(st, opt, phase_b=True)
+
+
 def test_fused_phase_a_step(scene):
     opt = _make_opt(scene)
     st = oham.HamState(scene)

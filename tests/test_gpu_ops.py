@@ -108,7 +108,8 @@ def test_rasterize_backward(dr):
     assert _rel(p.grad.cpu(), ref) < 1e-4
 
 
-@pytest.mark.parametrize("A,bcast", [(1, False), (4, False), (6, True), (7, False), (7, True), (10, False), (30, True)])
+@pytest.mark.parametrize("A,bcast", [(1, False), (3, False), (4, False), (5, True), (6, True), (7, False), (7, True),
+                                     (10, False), (13, False), (30, True)])
 def test_interpolate(dr, A, bcast):
     pos, tri, H, W = _scene("tiny")
     N, V, _ = pos.shape
@@ -127,6 +128,26 @@ def test_interpolate(dr, A, bcast):
     assert _rel(a.grad.cpu(), ref_ga) < 1e-4
     assert _rel(r.grad.cpu(), ref_gr) < 1e-4
     assert torch.equal(r.grad[..., 2:].cpu(), torch.zeros(N, H, W, 2))
+
+
+@pytest.mark.parametrize("A", [1, 3, 7, 30])
+def test_interpolate_ragged_tail(dr, A):
+    """The forward writes one float4 of the flat [N*H*W*A] output per thread: a plane whose element count is not a
+    multiple of four (odd crop of one view) exercises the scalar tail, and quads that straddle pixel boundaries."""
+    pos, tri, H, W = _scene("tiny")
+    rast, _, _ = orc.rasterize_fwd(pos, tri, (H, W))
+    covered = (rast[0, :, :, 3] > 0).nonzero()
+    y0, x0 = [int(v) for v in covered[len(covered) // 2]]
+    y0, x0 = max(0, min(y0 - 2, H - 5)), max(0, min(x0 - 3, W - 7))
+    crop = rast[:1, y0:y0 + 5, x0:x0 + 7].contiguous()  # 35 pixels, some covered
+    assert (crop[..., 3] > 0).any() and (35 * A) % 4 != 0
+    attr = torch.randn(1, pos.shape[1], A, generator=torch.Generator().manual_seed(100 + A))
+    ref = orc.interpolate_fwd(attr, crop, tri)
+    out, _ = dr.interpolate(attr.cuda(), crop.cuda(), tri.cuda())
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-6)
+    empty = torch.zeros(1, 3, 3, 4)
+    out0, _ = dr.interpolate(attr.cuda(), empty.cuda(), tri.cuda())
+    assert torch.equal(out0.cpu(), torch.zeros(1, 3, 3, A))
 
 
 def test_topology_matches_oracle(dr):

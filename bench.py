@@ -293,7 +293,7 @@ def main():
         h_masks8 = torch.tensor(msk_u8).contiguous().pin_memory()
         h_w2cs, h_projs = pinf("w2cs"), pinf("projs")
         k_e2e = max(3, min(args.steps, 100))
-        if world == 1:
+        if world == 1 or opt.peer is not None:
             stepper = HostStreamingStepper(opt, n)
             stepper.set_resident_valid_masks(opt.valid_masks)
             h2d, d2h = stepper.h2d_bytes_u8, stepper.d2h_bytes
@@ -349,7 +349,7 @@ def main():
                "inputs": "8-bit image batch + 8-bit masks + cameras from pinned host memory every step "
                          "(%s), loss record read back every step" % (
                              "fmhr_ham_host_u8_submit + fmhr_ham_step_host_u8_submitted, next batch in flight during "
-                             "the step" if world == 1 else "torch copies + HamOptimizer.step_phase_b")}
+                             "the step" if (world == 1 or opt.peer is not None) else "torch copies + HamOptimizer.step_phase_b")}
 
     if rank != 0:
         if world > 1:

@@ -2485,7 +2485,7 @@ extern "C" int fmhr_ham_host_u8_submit(const fmhr_ham_config* cfg, const uint8_t
 
 extern "C" int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf,
                                                const float* w2cs_host, const float* projs_host, void* staging,
-                                               float* losses_host, fmhr_stream_t stream) {
+                                               float* losses_host, const fmhr_ham_peers* peers, fmhr_stream_t stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     rc = ham_check_buffers(cfg, buf);
@@ -2512,7 +2512,7 @@ extern "C" int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const
     g_pending.consumed = nullptr;
     if (rc) return rc;
     side->slot_used[slot] = true;
-    rc = fmhr_ham_step_update(cfg, buf, stream);
+    rc = peers ? fmhr_ham_step_update_peer(cfg, buf, peers, stream) : fmhr_ham_step_update(cfg, buf, stream);
     if (rc) return rc;
     FMHR_CUDA(cudaMemcpyAsync(losses_host, buf->losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return FMHR_OK;

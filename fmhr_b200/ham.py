@@ -125,7 +125,7 @@ class HamOptimizer:
         alb = torch.empty(3, dtype=torch.float32, device=dev)
         scratch = torch.empty(self.lib.fmhr_ham_init_scratch_bytes(self.num), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            self._prepare_zbuf(cfg, buf)
+            self._prepare_zbuf_local(cfg, buf)
             check(self.lib.fmhr_ham_init(ctypes.byref(cfg), ctypes.byref(buf), ptr(gray), ptr(valid), ptr(sh), ptr(sh_g),
                                          ptr(alb), ptr(scratch), stream()), "ham_init")
             self.valid_masks = valid
@@ -201,14 +201,24 @@ class HamOptimizer:
         b.dbg_grad_sh = ptr(self.dbg_grad_sh if (self.debug and cfg.phase == 0) else None)
         return b
 
+    def _prepare_zbuf_local(self, cfg, buf):
+        """_prepare_zbuf for rank-local helpers (initialise / stage_times / export): with the peer exchange the slot
+        parity selects the shared `packed` buffer and must only advance on steps EVERY rank makes, so these helpers
+        put the parity back and force a z-buffer reset before the next real step."""
+        if self.peer is None:
+            return self._prepare_zbuf(cfg, buf)
+        slot = self._zb_slot
+        self._prepare_zbuf(cfg, buf)
+        self._zb_slot = slot
+        self._zb_layout = None
+
     def _prepare_zbuf(self, cfg, buf):
         """The fused step rasterises z-buffer slot `cfg.zbuf_slot` and resets the other one for the next step, so the
         slot alternates every render; both slots are reset whenever the workspace layout changes."""
         layout = (cfg.n_views, cfg.phase == 0, self.workspace.data_ptr())
         if layout != self._zb_layout:
             check(self.lib.fmhr_ham_reset(ctypes.byref(cfg), ctypes.byref(buf), stream()), "ham_reset")
-            self._zb_layout = layout
-            self._zb_slot = 0
+            self._zb_layout = layout  # both slots are clean now: the parity simply carries on (see _run_step)
         cfg.zbuf_slot = self._zb_slot
         self._zb_slot ^= 1
 
@@ -246,7 +256,9 @@ class HamOptimizer:
     def _run_step(self, cfg, buf, sp, part=None):
         """The C-ABI calls of one iteration on stream `sp` (part: None = all, 0 = render, 1 = update)."""
         if self.peer is not None:
-            buf.packed = self.peer.packed[cfg.zbuf_slot].data_ptr()  # the buffer alternates with the z-buffer slot
+            # the shared buffer alternates with the z-buffer slot, which flips on EVERY step of this optimiser (eager,
+            # graph replay, host-streaming, workspace resets included): a peer may still be reading the previous one
+            buf.packed = self.peer.packed[cfg.zbuf_slot].data_ptr()
         if part in (None, 0):
             check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_render")
         if part is None and self.world > 1 and self.peer is None:
@@ -278,7 +290,6 @@ class HamOptimizer:
         if layout != self._zb_layout:
             check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), stream()), "ham_reset")
             self._zb_layout = layout
-            self._zb_slot = 0
         slot = self._zb_slot
         self._zb_slot ^= 1
         vi = self._views(view_idx)
@@ -310,7 +321,9 @@ class HamOptimizer:
         with torch.cuda.stream(side):
             sp = _lib.c_p(side.cuda_stream)
             check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), sp), "ham_reset")
-            for slot in (0, 1):  # warm-up outside capture (lazy module loading), slot 0 then 1 keeps the buffers sane
+            # warm-up outside capture (lazy module loading): two steps continuing the slot parity of the steps before
+            # (the peer exchange relies on `packed` alternating on EVERY step, resets included)
+            for slot in (self._zb_slot, self._zb_slot ^ 1):
                 self._run_step(cfgs[slot], bufs[slot], sp)
             side.synchronize()
             for slot in (0, 1):
@@ -324,8 +337,7 @@ class HamOptimizer:
         torch.cuda.current_stream(self.device).wait_stream(side)
         for t, sv in zip(state, saved):
             t.copy_(sv)
-        self._zb_layout = (n, phase == 0, ws_ptr)
-        self._zb_slot = 0
+        self._zb_layout = (n, phase == 0, ws_ptr)  # two warm-up steps: the parity is where it was
         return graphs, idx_buf, ws_ptr, cfgs, bufs
 
     # ------------------------------------------------------------------ the two loops' bodies
@@ -354,7 +366,7 @@ class HamOptimizer:
         acc = [0.0] * len(self.STAGES)
         with torch.cuda.device(self.device):
             for _ in range(repeats):
-                self._prepare_zbuf(cfg, buf)
+                self._prepare_zbuf_local(cfg, buf)
                 check(self.lib.fmhr_ham_stage_times(ctypes.byref(cfg), ctypes.byref(buf), ms, ctypes.byref(n), stream()),
                       "ham_stage_times")
                 for i in range(min(n.value, len(acc))):
@@ -375,7 +387,7 @@ class HamOptimizer:
         pmask = torch.zeros(n, self.H, self.W, dtype=torch.float32, device=dev)
         normals = torch.empty(self.V, 3, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            self._prepare_zbuf(cfg, buf)
+            self._prepare_zbuf_local(cfg, buf)
             check(self.lib.fmhr_ham_debug_export(ctypes.byref(cfg), ctypes.byref(buf), ptr(pos), ptr(rast), ptr(image),
                                                  ptr(pmask), ptr(normals), stream()), "ham_debug_export")
         return dict(pos=pos, rast=rast, image=image, pred_mask=pmask, normals=normals)
@@ -484,14 +496,19 @@ class HostStreamingStepper:
                 raise RuntimeError("HostStreamingStepper: cameras must be pinned, contiguous float32 CPU tensors")
         if o.phase != 1:
             o.begin_phase_b()
-        if o.world > 1:
-            raise RuntimeError("HostStreamingStepper is single-process; use HamOptimizer under torch.distributed")
+        if o.world > 1 and o.peer is None:
+            raise RuntimeError("HostStreamingStepper needs the peer-memory exchange on more than one rank")
         cfg = o._cfg(self.n, 1, albedo_weight)
         buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows,
                          self.d_vm2)
         with torch.cuda.device(o.device):
             o._prepare_zbuf(cfg, buf)
+            peers = None
+            if o.peer is not None:  # the exchange is part of the update kernels: still one call per iteration
+                buf.packed = o.peer.packed[cfg.zbuf_slot].data_ptr()
+                peers = ctypes.byref(o.peer.structs[cfg.zbuf_slot])
             check(o.lib.fmhr_ham_step_host_u8_submitted(ctypes.byref(cfg), ctypes.byref(buf), ptr(h_w2cs), ptr(h_projs),
-                                                        ptr(self._stagings[ticket]), ptr(self.losses_host), stream()),
+                                                        ptr(self._stagings[ticket]), ptr(self.losses_host), peers,
+                                                        stream()),
                   "ham_step_host_u8_submitted")
         return self.losses_host

@@ -276,11 +276,14 @@ int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_buffers* bu
 /* Pipelined form of the same step (a loader thread decodes batch i+1 while step i runs): fmhr_ham_host_u8_submit starts
  * the upload of a batch into `staging` on the internal copy stream and returns at once; up to two staging buffers may be
  * in flight per device, and a buffer is only overwritten after the conversion kernel of its previous batch.
- * fmhr_ham_step_host_u8_submitted runs the iteration on the batch last submitted into `staging`. */
+ * fmhr_ham_step_host_u8_submitted runs the iteration on the batch last submitted into `staging`; `peers` = NULL on a single
+ * rank, else the update is fmhr_ham_step_update_peer (buf->packed must be peers->packed[rank], see below). */
 int fmhr_ham_host_u8_submit(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
                             void* staging);
+struct fmhr_ham_peers;
 int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* w2cs_host,
-                                    const float* projs_host, void* staging, float* losses_host, fmhr_stream_t stream);
+                                    const float* projs_host, void* staging, float* losses_host,
+                                    const struct fmhr_ham_peers* peers, fmhr_stream_t stream);
 
 /* HAM initialisation (mesh_sfs_optim.py:124-177) on the same fused forward chain: every view of the batch is rendered
  * once (n_views rows of view_idx, normally all views), normals and coverage are antialiased, and

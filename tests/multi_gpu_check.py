@@ -23,6 +23,59 @@ from fmhr_b200.ham import HamOptimizer
 from fmhr_b200.render import render_views
 
 
+def extra_checks(scene, c, mine, num, rank, dev):
+    """(1) batches of alternating size (the workspace layout is reset on every step: the shared `packed` buffers must keep
+    alternating); (2) the pipelined host-batch step (HostStreamingStepper) with the peer exchange in its update."""
+    import numpy as np
+    from fmhr_b200.ham import HostStreamingStepper
+    ok = True
+    mk = lambda **kw: HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs", sel=mine), c("masks", sel=mine),
+                                   c("valid_masks", sel=mine), c("w2cs", sel=mine), c("projs", sel=mine),
+                                   c("sh_coeffs", sel=mine), c("albedo"), scene["conf"], **kw)
+    nm = len(mine)
+    if nm >= 2:
+        a = mk(use_graphs=True, exchange="peer")
+        b = mk(use_graphs=False, exchange="nccl")
+        for it in range(6):
+            views = list(range(nm)) if it % 2 == 0 else list(range(nm - 1))
+            la, lb = a.step_phase_b(views).cpu(), b.step_phase_b(views).cpu()
+            good = torch.allclose(la, lb, rtol=2e-4, atol=1e-6)
+            ok = ok and good
+            if rank == 0:
+                print("alternating batch sizes it=%d peer %s nccl %s %s" % (
+                    it, [round(x, 5) for x in la.tolist()[:4]], [round(x, 5) for x in lb.tolist()[:4]],
+                    "OK" if good else "MISMATCH"))
+            a.delta.copy_(b.delta); a.albedo.copy_(b.albedo)
+    H, W = scene["H"], scene["W"]
+    if (nm * H * W) % 4 == 0:
+        img_u8 = np.clip(np.rint(np.asarray(scene["imgs"], dtype=np.float64)[mine] * 255.0), 0, 255).astype(np.uint8)
+        msk_u8 = (np.asarray(scene["masks"])[mine] > 0).astype(np.uint8) * 255
+        q = lambda x, dt: torch.tensor(x, dtype=dt).contiguous().pin_memory()
+        res, hst = mk(exchange="peer"), mk(exchange="peer")
+        for o in (res, hst):
+            o.imgs.copy_(torch.tensor(img_u8.astype(np.float32) / np.float32(255.0)))
+            o.masks.copy_(torch.tensor((msk_u8 > 127).astype(np.float32)))
+        stepper = HostStreamingStepper(hst, nm)
+        stepper.set_resident_valid_masks(hst.valid_masks)
+        h = (q(img_u8, torch.uint8), q(msk_u8, torch.uint8), q(scene["w2cs"][mine], torch.float32),
+             q(scene["projs"][mine], torch.float32))
+        views = torch.arange(nm, dtype=torch.int32, device=dev)
+        ticket = stepper.submit_u8(h[0], h[1])
+        for it in range(4):
+            nxt = stepper.submit_u8(h[0], h[1]) if it < 3 else None
+            lr = res.step_phase_b(views).cpu()
+            stepper.step_submitted_u8(ticket, h[2], h[3], views)
+            torch.cuda.synchronize()
+            good = torch.allclose(lr, stepper.losses_host, rtol=2e-4, atol=1e-6)
+            ok = ok and good
+            if rank == 0:
+                print("host-batch step with peer exchange it=%d resident %s host %s %s" % (
+                    it, [round(x, 5) for x in lr.tolist()[:4]], [round(x, 5) for x in stepper.losses_host.tolist()[:4]],
+                    "OK" if good else "MISMATCH"))
+            ticket = nxt
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -63,6 +116,7 @@ def main():
             # keep the two trajectories on identical state (kinks of the hinge / L1 amplify 1e-7 differences)
             sharded.delta.copy_(full.delta); sharded.albedo.copy_(full.albedo)
             sharded.adam_m.copy_(full.adam_m[: sharded.adam_m.numel()]) if False else None
+    ok = extra_checks(scene, c, mine, num, rank, dev) and ok
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="interhand_48x512x334")
+    ap.add_argument("--views", type=int, default=None,
+                    help="keep only the first N views of the workload (e.g. 16 = one rank's shard of stress_128x2048x2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
@@ -233,7 +235,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     wl = dict(synth.WORKLOADS[args.workload])
-    scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), camera_seed=1 + rank)
+    scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), n_views=args.views, camera_seed=1 + rank)
     img_u8, msk_u8 = quantise_targets(scene)
     n, H, W = scene["imgs"].shape[0], scene["H"], scene["W"]
     c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt, device=dev)

@@ -243,7 +243,10 @@ def main():
                        c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs,
                        exchange=args.exchange if world > 1 else None)
     exchange = "1 NCCL all-reduce/iter"
+    kernels_per_step = KERNELS_PER_STEP  # own kernels per iteration (NCCL's all-reduce kernel is not counted)
     if opt.peer is not None:
+        # one-shot: the exchange IS the normal-gradient kernel; two-shot: one extra reduce-scatter kernel in front of it
+        kernels_per_step += 1 if (opt.peer.mode == 2 or (opt.peer.mode == 0 and world > 2)) else 0
         exchange = "NVLink peer-memory exchange fused into the update kernels (%s)" % (
             "two-shot reduce-scatter" if opt.peer.mode == 2 or (opt.peer.mode == 0 and world > 2) else "one-shot gather")
     V, F = opt.V, opt.T
@@ -366,7 +369,7 @@ def main():
     balg = b_alg_bytes(n, H, W, V, F, E)
     iter_ach = balg / (ms_per_step * 1e-3) / 1e9
     traffic = measured_traffic()
-    roof = {"bound": "hbm", "kernel": "fused HAM iteration (%d kernels, one graph launch)" % KERNELS_PER_STEP,
+    roof = {"bound": "hbm", "kernel": "fused HAM iteration (%d kernels, one graph launch)" % kernels_per_step,
             "achieved": iter_ach, "peak": peak, "unit": "GB/s", "frac": iter_ach / peak,
             "traffic": traffic["iteration_bytes"] if traffic else None, "algorithmic_bytes": balg,
             "iter_ms": ms_per_step, "peak_source": peak_src,
@@ -410,7 +413,7 @@ def main():
                    "l2": "per-iteration working set %.0f MB > 126 MB L2 (no flush needed)" % (
                        (8 + 32 + 20) * n * H * W / 1e6),
                    "parallelism": "views x%d (weak), %s" % (world, exchange) if world > 1 else "single GPU"},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "gpu_launches": kernels_per_step * args.steps,
         "clocks": clocks,
         "e2e": e2e,
         "roofline": roof,

@@ -56,6 +56,9 @@ _SIGS = {
     "fmhr_last_error_string": (ctypes.c_char_p, []),
     "fmhr_rasterize_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "fmhr_rasterize_fwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    "fmhr_rasterize_tile_words": (c_sz, [c_i, c_i, c_i]),
+    "fmhr_rasterize_fwd_meshlets": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p,
+                                          c_sz, c_i, c_p, c_p]),
     "fmhr_rasterize_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_interpolate_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_interpolate_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),

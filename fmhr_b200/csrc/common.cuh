@@ -41,6 +41,7 @@ __device__ __forceinline__ float xs(float a, float b) { return __fsub_rn(a, b); 
 __device__ __forceinline__ float xd(float a, float b) { return __fdiv_rn(a, b); }
 
 constexpr unsigned long long ZB_EMPTY = ~0ull;
+constexpr int kTile = 16;  // screen tile edge of the coverage kernels' dirty-tile bitmaps (ham.cu, raster.cu)
 
 __device__ __forceinline__ uint32_t depth_key(float zw) {
     uint32_t b = __float_as_uint(zw);

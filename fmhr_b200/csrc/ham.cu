@@ -340,12 +340,14 @@ __device__ __forceinline__ void ml_candidate(uint2 rec, int e, const float4* pos
 #define FMHR_COV_THREADS 256  // threads per coverage block (tuning: 128 gives smaller barrier domains, more blocks per SM)
 #endif
 constexpr int kCovThreads = FMHR_COV_THREADS;
-template <int TPT>
+// CLIP = true: stand-alone dr.rasterize (fmhr_rasterize_fwd_meshlets): `vg` is the caller's clip-space pos [N,clipV] (float4),
+// no transform, and only the tile bitmap is produced (glist / gcount are NULL).
+template <int TPT, bool CLIP = false>
 __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThreads)) ham_coverage_meshlet_kernel(
     const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ ml_vptr,
     const int32_t* __restrict__ ml_verts, const uint2* __restrict__ ml_tri2, int max_verts, int H, int W, float invW,
     float invH, unsigned long long* __restrict__ zbuf, uint32_t* __restrict__ gbits, uint32_t* __restrict__ glist,
-    int* __restrict__ gcount, int tiles_x, int tiles_per_view) {
+    int* __restrict__ gcount, int tiles_x, int tiles_per_view, int clipV) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4* pos_s = reinterpret_cast<float4*>(dyn_smem);
     int2* snap_s = reinterpret_cast<int2*>(pos_s + max_verts);
@@ -358,7 +360,8 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
     const int m = blockIdx.x, n = blockIdx.y;
     for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;  // visible after the vertex-phase barrier
     if (lane == 0) qcount[warp] = 0;
-    const ViewM Mv = load_viewM(viewM + (size_t)n * kViewM);  // uniform loads: L1 broadcast
+    ViewM Mv;
+    if (!CLIP) Mv = load_viewM(viewM + (size_t)n * kViewM);  // uniform loads: L1 broadcast
     // triangle records of this thread: issued before the vertex phase so their latency hides behind it
     uint2 rec[TPT];
     const uint2* recs = ml_tri2 + (size_t)m * (TPT * kCovThreads);
@@ -367,8 +370,8 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
     const int vb = __ldg(ml_vptr + m), nv = __ldg(ml_vptr + m + 1) - vb;
     const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-        const float4 v = __ldg(vg + 2 * (size_t)__ldg(ml_verts + vb + i));
-        const float4 p = clip_from_world(Mv.m, v);
+        const size_t gi = (size_t)__ldg(ml_verts + vb + i);
+        const float4 p = CLIP ? __ldg(vg + (size_t)n * clipV + gi) : clip_from_world(Mv.m, __ldg(vg + 2 * gi));
         pos_s[i] = p;
         int X = kSnapRejected, Y = 0;
         if (!snap_vertex(p, hw, hh, X, Y)) X = kSnapRejected;
@@ -406,6 +409,7 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
         const unsigned int bits = tbits[w];
         if (bits == 0) continue;
         unsigned int fresh = bits & ~atomicOr(gbits + (size_t)n * words + w, bits);
+        if (CLIP) continue;  // the stand-alone resolve pass walks the bitmap
         while (fresh) {
             const int bit = __ffs(fresh) - 1;
             fresh &= fresh - 1;
@@ -534,8 +538,7 @@ __device__ __forceinline__ float sh_radiance(const float* c, float x, float y, f
 }
 
 // The scan pass walks 16x16 tiles (2-D locality keeps the hand's pixels in few, densely populated tiles); every later
-// pixel pass walks the compact pixel lists the scan pass builds.
-constexpr int kTile = 16;
+// pixel pass walks the compact pixel lists the scan pass builds.  (kTile = 16 lives in common.cuh.)
 
 // clip-space gradient (x, y, -, w) -> world-space xyz
 __device__ __forceinline__ float3 clip_to_world(const float* M, float gx, float gy, float gw) {
@@ -2096,7 +2099,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
             }                                                                                                          \
             ham_coverage_meshlet_kernel<TPT><<<grid, kCovThreads, smem, st>>>(                                         \
                 ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,               \
-                ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv);                                      \
+                ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv, 0);                                   \
         } while (0)
         if (b->ml_tris == 1024) FMHR_COVERAGE(1024 / kCovThreads);
         else if (b->ml_tris == 512) FMHR_COVERAGE(512 / kCovThreads);
@@ -2173,6 +2176,41 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
     return FMHR_OK;
 }
+
+// Coverage launch of the stand-alone rasteriser (raster.cu, fmhr_rasterize_fwd_meshlets): the fused path's meshlet kernel
+// on caller-provided clip-space positions.
+namespace fmhr {
+int launch_meshlet_coverage_clip(const float* pos, int N, int V, int H, int W, const int32_t* ml_vptr,
+                                 const int32_t* ml_verts, const uint32_t* ml_tri2, int n_meshlets, int ml_tris,
+                                 int ml_max_verts, unsigned long long* zbuf, uint32_t* tile_bits, cudaStream_t st) {
+    const int tiles_x = cdiv(W, kTile), tiles_pv = tiles_x * cdiv(H, kTile);
+    const size_t smem = (size_t)ml_max_verts * 24 + (size_t)((tiles_pv + 31) / 32) * sizeof(unsigned int);
+    if (smem > 96 * 1024 || (ml_tris != 256 && ml_tris != 512 && ml_tris != 1024) || ml_max_verts > 1024) {
+        set_error("fmhr_rasterize_fwd_meshlets: unsupported meshlet / tile configuration");
+        return FMHR_EUNSUPPORTED;
+    }
+    const dim3 grid(n_meshlets, N);
+    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+#define FMHR_COVERAGE_CLIP(TPT)                                                                                        \
+    do {                                                                                                               \
+        static bool attr_set = false;                                                                                  \
+        if (!attr_set) {                                                                                               \
+            FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT, true>,                                     \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));                  \
+            attr_set = true;                                                                                           \
+        }                                                                                                              \
+        ham_coverage_meshlet_kernel<TPT, true><<<grid, kCovThreads, smem, st>>>(                                       \
+            (const float4*)pos, nullptr, ml_vptr, ml_verts, (const uint2*)ml_tri2, ml_max_verts, H, W, invW, invH,     \
+            zbuf, tile_bits, nullptr, nullptr, tiles_x, tiles_pv, V);                                                  \
+    } while (0)
+    if (ml_tris == 1024) FMHR_COVERAGE_CLIP(1024 / kCovThreads);
+    else if (ml_tris == 512) FMHR_COVERAGE_CLIP(512 / kCovThreads);
+    else FMHR_COVERAGE_CLIP(256 / kCovThreads);
+#undef FMHR_COVERAGE_CLIP
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+}  // namespace fmhr
 
 extern "C" int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream) {
     int rc = check_cfg(cfg);

@@ -230,24 +230,10 @@ __global__ void __launch_bounds__(256) raster_coverage_kernel(const float* __res
     }
 }
 
-// zbuf -> rast_out (+ optional rast_db).  One thread per pixel, float4 stores.
-__global__ void __launch_bounds__(256) raster_resolve_kernel(const float* __restrict__ pos,
-                                                             const int32_t* __restrict__ tri, int V, int H, int W,
-                                                             size_t npix,
-                                                             const unsigned long long* __restrict__ zbuf,
-                                                             float4* __restrict__ rast, float4* __restrict__ rast_db) {
-    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const unsigned long long key = zbuf[pix];
-    if (key == ZB_EMPTY) {
-        rast[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rast_db) rast_db[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
-    const size_t hw_ = (size_t)H * W;
-    const int n = (int)(pix / hw_);
-    const int rem = (int)(pix - (size_t)n * hw_);
-    const int py = rem / W, px = rem - py * W;
+// zbuf key -> rast_out texel (+ optional rast_db) of pixel (n, py, px).
+__device__ __forceinline__ void resolve_pixel(unsigned long long key, const float* __restrict__ pos,
+                                              const int32_t* __restrict__ tri, int V, int H, int W, int n, int py, int px,
+                                              size_t pix, float4* __restrict__ rast, float4* __restrict__ rast_db) {
     const int t = (int)(uint32_t)key;
     const float* P = pos + (size_t)n * V * 4;
     const float4 p0 = ldg4(P + 4 * (size_t)__ldg(tri + 3 * t));
@@ -273,6 +259,54 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(const float* __rest
         rast_db[pix] = make_float4((da0x - u * datx) * iw * sx, (da0y - u * daty) * iw * sy,
                                    (da1x - v * datx) * iw * sx, (da1y - v * daty) * iw * sy);
     }
+}
+
+// zbuf -> rast_out (+ optional rast_db).  One thread per pixel, float4 stores.
+__global__ void __launch_bounds__(256) raster_resolve_kernel(const float* __restrict__ pos,
+                                                             const int32_t* __restrict__ tri, int V, int H, int W,
+                                                             size_t npix,
+                                                             const unsigned long long* __restrict__ zbuf,
+                                                             float4* __restrict__ rast, float4* __restrict__ rast_db) {
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const unsigned long long key = zbuf[pix];
+    if (key == ZB_EMPTY) {
+        rast[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rast_db) rast_db[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const size_t hw_ = (size_t)H * W;
+    const int n = (int)(pix / hw_);
+    const int rem = (int)(pix - (size_t)n * hw_);
+    const int py = rem / W, px = rem - py * W;
+    resolve_pixel(key, pos, tri, V, H, W, n, py, px, pix, rast, rast_db);
+}
+
+// Tile form of the resolve pass (fmhr_rasterize_fwd_meshlets): one block per 16x16 screen tile.  A tile the coverage
+// kernel never touched (bitmap bit clear: ~90 % of the frame in the HAM workloads) is zero-filled without reading the
+// z-buffer; a dirty tile resolves its winners and puts the keys it consumed back to EMPTY, so the z-buffer is clean again
+// when the call returns and the next call needs no 8-byte-per-pixel clear pass.
+__global__ void __launch_bounds__(kTile * kTile) raster_resolve_tiles_kernel(
+    const float* __restrict__ pos, const int32_t* __restrict__ tri, int V, int H, int W, int tiles_x, int words,
+    const uint32_t* __restrict__ tile_bits, unsigned long long* __restrict__ zbuf, float4* __restrict__ rast,
+    float4* __restrict__ rast_db) {
+    const int tile = blockIdx.x, n = blockIdx.y;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int px = tx * kTile + (threadIdx.x & (kTile - 1)), py = ty * kTile + (threadIdx.x / kTile);
+    if (px >= W || py >= H) return;
+    const size_t pix = ((size_t)n * H + py) * W + px;
+    const bool dirty = (__ldg(tile_bits + (size_t)n * words + (tile >> 5)) >> (tile & 31)) & 1u;
+    unsigned long long key = ZB_EMPTY;
+    if (dirty) {
+        key = zbuf[pix];
+        if (key != ZB_EMPTY) zbuf[pix] = ZB_EMPTY;
+    }
+    if (key == ZB_EMPTY) {
+        rast[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rast_db) rast_db[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    resolve_pixel(key, pos, tri, V, H, W, n, py, px, pix, rast, rast_db);
 }
 
 // d(u,v)/d(pos) scattered to the three vertices (SURVEY.md Appendix A "rasterize bwd").
@@ -365,6 +399,41 @@ extern "C" int fmhr_rasterize_fwd(const float* pos, const int32_t* tri, int N, i
     }
     raster_resolve_kernel<<<cdiv(npix, 256), 256, 0, st>>>(pos, tri, V, H, W, npix, zbuf, (float4*)rast,
                                                            (float4*)rast_db);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
+namespace fmhr {
+int launch_meshlet_coverage_clip(const float* pos, int N, int V, int H, int W, const int32_t* ml_vptr,
+                                 const int32_t* ml_verts, const uint32_t* ml_tri2, int n_meshlets, int ml_tris,
+                                 int ml_max_verts, unsigned long long* zbuf, uint32_t* tile_bits, cudaStream_t st);
+}
+
+extern "C" size_t fmhr_rasterize_tile_words(int N, int H, int W) {
+    if (N <= 0 || H <= 0 || W <= 0) return 0;
+    return (size_t)N * (size_t)((cdiv(W, kTile) * cdiv(H, kTile) + 31) / 32);
+}
+
+extern "C" int fmhr_rasterize_fwd_meshlets(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
+                                           float* rast, float* rast_db, const int32_t* ml_vptr, const int32_t* ml_verts,
+                                           const uint32_t* ml_tri2, int n_meshlets, int ml_tris, int ml_max_verts,
+                                           void* zbuf_ws, size_t zbuf_bytes, int zbuf_is_clean, uint32_t* tile_bits,
+                                           fmhr_stream_t stream) {
+    FMHR_CHECK_ARG(pos && tri && rast && zbuf_ws && tile_bits && ml_vptr && ml_verts && ml_tri2);
+    FMHR_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0 && n_meshlets > 0);
+    FMHR_CHECK_ARG(zbuf_bytes >= fmhr_rasterize_workspace_bytes(N, H, W));
+    FMHR_CHECK_ARG(T < (1 << 24) && N <= 65535);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* zbuf = (unsigned long long*)zbuf_ws;
+    const size_t npix = (size_t)N * H * W;
+    if (!zbuf_is_clean) FMHR_CUDA(cudaMemsetAsync(zbuf, 0xFF, npix * sizeof(unsigned long long), st));
+    const int tiles_x = cdiv(W, kTile), tiles_pv = tiles_x * cdiv(H, kTile), words = (tiles_pv + 31) / 32;
+    FMHR_CUDA(cudaMemsetAsync(tile_bits, 0, (size_t)N * words * sizeof(uint32_t), st));
+    int rc = launch_meshlet_coverage_clip(pos, N, V, H, W, ml_vptr, ml_verts, ml_tri2, n_meshlets, ml_tris, ml_max_verts,
+                                          zbuf, tile_bits, st);
+    if (rc) return rc;
+    raster_resolve_tiles_kernel<<<dim3(tiles_pv, N), kTile * kTile, 0, st>>>(pos, tri, V, H, W, tiles_x, words, tile_bits,
+                                                                            zbuf, (float4*)rast, (float4*)rast_db);
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

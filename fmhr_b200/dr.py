@@ -8,6 +8,7 @@ backward are one C-ABI call; the repo-root package `nvdiffrast/` re-exports this
 scripts run unchanged.  Keyword signatures follow upstream.
 """
 import collections
+import os
 
 import torch
 
@@ -70,6 +71,64 @@ def get_topology(tri, n_verts):
     return topo
 
 
+class Meshlets:
+    """Meshlets of one triangle tensor for the stand-alone rasteriser (fmhr_rasterize_fwd_meshlets): faces ordered along a
+    Morton curve of their centroids in the NDC of the first view, cut into groups of <= 1024 triangles / 1024 distinct
+    vertices (fmhr_meshlets_build_host, once per mesh).  `ok` is False for meshes the builder cannot take (indices outside
+    [0,V), no triangles): rasterize then uses the one-thread-per-triangle kernel, which skips such triangles."""
+    TRIS = 1024
+
+    def __init__(self, tri, n_verts, pos0):
+        import ctypes
+
+        import numpy as np
+        lib = _lib.load()
+        self.ok = False
+        self.tri = tri  # keeps the storage alive: the cache key (data_ptr, version) cannot be recycled by the allocator
+        T, V = tri.shape[0], int(n_verts)
+        if T == 0:
+            return
+        tri_h = np.ascontiguousarray(tri.detach().cpu().numpy(), dtype=np.int32)
+        if tri_h.min() < 0 or tri_h.max() >= V:
+            return
+        w = pos0[:, 3:4]
+        ndc = torch.nan_to_num(pos0[:, :3] / torch.where(w.abs() > 1e-12, w, torch.ones_like(w)), 0.0, 0.0, 0.0)
+        verts = np.ascontiguousarray(ndc.clamp(-4.0, 4.0).detach().cpu().numpy(), dtype=np.float32)
+        hp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+        nm, nr, mv = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        call = lambda a, b, c: lib.fmhr_meshlets_build_host(hp(tri_h), hp(verts), V, T, self.TRIS, ctypes.byref(nm),
+                                                            ctypes.byref(nr), ctypes.byref(mv), hp(a), hp(b), hp(c))
+        if call(None, None, None) != 0 or nm.value <= 0:
+            return
+        vptr = np.zeros(nm.value + 1, dtype=np.int32)
+        vrefs = np.zeros(max(nr.value, 1), dtype=np.int32)
+        tri2 = np.zeros((nm.value * self.TRIS, 2), dtype=np.uint32)
+        if call(vptr, vrefs, tri2) != 0:
+            return
+        dev = tri.device
+        self.vptr = torch.from_numpy(vptr).to(dev)
+        self.verts = torch.from_numpy(vrefs).to(dev)
+        self.tri2 = torch.from_numpy(tri2.view(np.int32)).to(dev)
+        self.n, self.max_verts = nm.value, mv.value
+        self.ok = True
+
+
+_MESHLET_CACHE = collections.OrderedDict()
+
+
+def get_meshlets(tri, n_verts, pos):
+    key = (tri.data_ptr(), tri._version, tuple(tri.shape), int(n_verts), str(tri.device))
+    ml = _MESHLET_CACHE.get(key)
+    if ml is None:
+        ml = Meshlets(tri, n_verts, pos[0].detach())
+        _MESHLET_CACHE[key] = ml
+        while len(_MESHLET_CACHE) > 8:
+            _MESHLET_CACHE.popitem(last=False)
+    else:
+        _MESHLET_CACHE.move_to_end(key)
+    return ml
+
+
 # ------------------------------------------------------------------------------------------------
 # contexts
 # ------------------------------------------------------------------------------------------------
@@ -82,11 +141,25 @@ class RasterizeCudaContext:
         _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._ws = None
+        self._ws_clean = False   # every byte 0xFF: the meshlet rasteriser then needs no clear pass and leaves it so
+        self._tile_bits = None
+        self.use_meshlets = os.environ.get("FMHR_RASTER", "meshlets") != "v1"
 
-    def workspace(self, nbytes, device):
+    def workspace(self, nbytes, device, clean=False):
+        """The z-buffer scratch.  clean=True: make sure it is all-0xFF (filled once at allocation; the meshlet rasteriser
+        restores that state itself); clean=False: the caller clears / dirties it."""
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws_clean = False
+        if clean and not self._ws_clean:
+            self._ws.fill_(255)
+        self._ws_clean = clean
         return self._ws
+
+    def tile_bits(self, words, device):
+        if self._tile_bits is None or self._tile_bits.numel() < words or self._tile_bits.device != device:
+            self._tile_bits = torch.empty(max(words, 1), dtype=torch.int32, device=device)
+        return self._tile_bits
 
 
 class RasterizeGLContext(RasterizeCudaContext):
@@ -126,10 +199,20 @@ class _RasterizeFunc(torch.autograd.Function):
         rast = torch.empty(N, H, W, 4, dtype=torch.float32, device=pos.device)
         rast_db = torch.empty(N, H, W, 4, dtype=torch.float32, device=pos.device) if grad_db else None
         nbytes = lib.fmhr_rasterize_workspace_bytes(N, H, W)
-        ws = glctx.workspace(nbytes, pos.device)
+        ml = get_meshlets(tri, V, pos) if (glctx.use_meshlets and N <= 65535) else None
         with torch.cuda.device(pos.device):
-            check(lib.fmhr_rasterize_fwd(ptr(pos), ptr(tri), N, V, tri.shape[0], H, W, ptr(rast), ptr(rast_db), ptr(ws),
-                                         ws.numel(), stream()), "rasterize_fwd")
+            if ml is not None and ml.ok:
+                ws = glctx.workspace(nbytes, pos.device, clean=True)
+                bits = glctx.tile_bits(lib.fmhr_rasterize_tile_words(N, H, W), pos.device)
+                glctx._ws_clean = False  # until the call below has been issued successfully
+                check(lib.fmhr_rasterize_fwd_meshlets(ptr(pos), ptr(tri), N, V, tri.shape[0], H, W, ptr(rast), ptr(rast_db),
+                                                      ptr(ml.vptr), ptr(ml.verts), ptr(ml.tri2), ml.n, ml.TRIS, ml.max_verts,
+                                                      ptr(ws), ws.numel(), 1, ptr(bits), stream()), "rasterize_fwd_meshlets")
+                glctx._ws_clean = True
+            else:
+                ws = glctx.workspace(nbytes, pos.device)
+                check(lib.fmhr_rasterize_fwd(ptr(pos), ptr(tri), N, V, tri.shape[0], H, W, ptr(rast), ptr(rast_db), ptr(ws),
+                                             ws.numel(), stream()), "rasterize_fwd")
         ctx.save_for_backward(pos, tri, rast)
         if rast_db is None:
             rast_db = torch.zeros(N, H, W, 0, dtype=torch.float32, device=pos.device)

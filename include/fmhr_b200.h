@@ -46,6 +46,18 @@ const char* fmhr_last_error_string(void);
 size_t fmhr_rasterize_workspace_bytes(int N, int H, int W);
 int fmhr_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                        float* rast, float* rast_db, void* workspace, size_t workspace_bytes, fmhr_stream_t stream);
+/* Same result (bit-exact) on the fused path's meshlet coverage kernel: the meshlet-local vertices are snapped once into
+ * shared memory instead of three times per triangle, a dirty-tile bitmap lets the resolve pass zero-fill untouched 16x16
+ * tiles without reading the z-buffer, and the resolve pass puts the keys it consumed back to "empty" - so when
+ * `zbuf_is_clean` (every byte of zbuf_ws 0xFF on entry: freshly filled, or left by a previous successful call of this
+ * function with any N/H/W) no clear pass runs at all.  ml_* from fmhr_meshlets_build_host (any vertex positions, e.g.
+ * one view's NDC, or NULL for the input order; tris_per_meshlet 256 / 512 / 1024), uploaded to the device; every index
+ * of `tri` must be in [0,V).  tile_bits = fmhr_rasterize_tile_words(N,H,W) uint32 of scratch. */
+size_t fmhr_rasterize_tile_words(int N, int H, int W);
+int fmhr_rasterize_fwd_meshlets(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W, float* rast,
+                                float* rast_db, const int32_t* ml_vptr, const int32_t* ml_verts, const uint32_t* ml_tri2,
+                                int n_meshlets, int ml_tris, int ml_max_verts, void* zbuf_ws, size_t zbuf_bytes,
+                                int zbuf_is_clean, uint32_t* tile_bits, fmhr_stream_t stream);
 /* grad_pos [N,V,4] is overwritten with d(sum dy.rast)/d(pos); only the u,v channels of dy carry gradient. */
 int fmhr_rasterize_bwd(const float* pos, const int32_t* tri, const float* rast, const float* dy,
                        int N, int V, int T, int H, int W, float* grad_pos, fmhr_stream_t stream);

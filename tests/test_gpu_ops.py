@@ -48,6 +48,33 @@ def test_rasterize_bit_exact(dr, workload):
     assert torch.allclose(db, ref_db, rtol=1e-3, atol=1e-4)
 
 
+def test_rasterize_meshlet_and_v1_paths_agree(dr):
+    """dr.rasterize runs on the meshlet coverage kernel with a self-cleaning z-buffer (fmhr_rasterize_fwd_meshlets);
+    the first-generation kernel (fmhr_rasterize_fwd) stays as the fallback for meshes the meshlet builder rejects.
+    Both must give the oracle's result bit for bit - also on REPEATED calls with changing sizes on one context (the
+    z-buffer is only cleared once, every call has to leave it clean) and after a v1 call dirtied the shared scratch."""
+    ctx = dr.RasterizeGLContext()
+    v1 = dr.RasterizeGLContext()
+    v1.use_meshlets = False
+    assert ctx.use_meshlets
+    for workload in ("small", "tiny", "small", "coarse"):
+        pos, tri, H, W = _scene(workload)
+        ref, _, _ = orc.rasterize_fwd(pos, tri, (H, W), want_db=False)
+        for rep in range(2):
+            a, _ = dr.rasterize(ctx, pos.cuda(), tri.cuda(), resolution=(H, W))
+            assert torch.equal(a.cpu(), ref), (workload, rep)
+        b, _ = dr.rasterize(v1, pos.cuda(), tri.cuda(), resolution=(H, W), grad_db=False)
+        assert torch.equal(b.cpu(), ref)
+        assert ctx._ws_clean and bool((ctx._ws == 255).all()), "the meshlet path must leave the z-buffer clean"
+    # a context that alternates between the two kernels
+    pos, tri, H, W = _scene("tiny")
+    ref, _, _ = orc.rasterize_fwd(pos, tri, (H, W), want_db=False)
+    for use in (False, True, False, True, True):
+        ctx.use_meshlets = use
+        a, _ = dr.rasterize(ctx, pos.cuda(), tri.cuda(), resolution=(H, W))
+        assert torch.equal(a.cpu(), ref), use
+
+
 def test_rasterize_odd_sizes_and_culling(dr):
     # W=334 is not a multiple of 8 (SURVEY.md F8); some triangles behind the near plane / off-screen / degenerate
     g = torch.Generator().manual_seed(3)

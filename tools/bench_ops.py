@@ -66,7 +66,14 @@ def main():
     row("rasterize fwd (+rast_db)", ms, 16 * n * V + 12 * F + 32 * P, "%.0f Mtri/s" % (n * F / ms / 1e3))
     ms = timed(lambda: dr.rasterize(glctx, pos, faces, resolution=(H, W), grad_db=False))
     row("rasterize fwd (grad_db=False)", ms, 16 * n * V + 12 * F + 16 * P, "%.0f Mtri/s" % (n * F / ms / 1e3))
+    g1 = dr.RasterizeGLContext()
+    g1.use_meshlets = False
+    ms = timed(lambda: dr.rasterize(g1, pos, faces, resolution=(H, W)))
+    row("rasterize fwd (+rast_db), v1 kernel", ms, 16 * n * V + 12 * F + 32 * P,
+        "one thread per triangle + clear + dense resolve (fmhr_rasterize_fwd)")
     rast, _ = dr.rasterize(glctx, pos, faces, resolution=(H, W))
+    r1, _ = dr.rasterize(g1, pos, faces, resolution=(H, W))
+    assert torch.equal(rast, r1), "meshlet and v1 rasterisers must agree bit for bit"
     covered = int((rast[..., 3] > 0).sum())
 
     # ---- interpolate, A = 7 (normals | albedo | 1, :268) and A = 30 (train_mlp.py:180-184)

@@ -469,9 +469,23 @@ class HostStreamingStepper:
         return self.losses_host
 
     # ---- pipelined form: the next step's batch travels while the current step computes
-    def submit_u8(self, h_imgs_u8, h_masks_u8):
+    @staticmethod
+    def mask_boxes(masks_u8):
+        """Loader metadata for submit_u8(boxes=...): per view the half-open rectangle (y0, y1, x0, x1) that contains every
+        pixel with mask byte > 127 ((0,0,0,0) for an empty mask).  masks_u8: [n,H,W] uint8 (CPU tensor or array)."""
+        import numpy as np
+        m = np.asarray(masks_u8) > 127
+        out = np.zeros((m.shape[0], 4), dtype=np.int32)
+        for v in range(m.shape[0]):
+            ys, xs = np.flatnonzero(m[v].any(axis=1)), np.flatnonzero(m[v].any(axis=0))
+            if ys.size:
+                out[v] = (ys[0], ys[-1] + 1, xs[0], xs[-1] + 1)
+        return torch.from_numpy(out)
+
+    def submit_u8(self, h_imgs_u8, h_masks_u8, boxes=None):
         """Start the upload of a host batch (pinned uint8 images [n,H,W,3] / masks [n,H,W]) into the next free staging
-        buffer; returns a ticket for step_submitted_u8.  At most two batches may be in flight."""
+        buffer; returns a ticket for step_submitted_u8.  At most two batches may be in flight.  boxes (mask_boxes(): int32
+        CPU tensor [n,4]) restricts the transfer to the rectangle of every view that holds its segmentation."""
         o = self.opt
         for t in (h_imgs_u8, h_masks_u8):
             if t.is_cuda or not t.is_contiguous() or t.dtype != torch.uint8 or not t.is_pinned():
@@ -484,8 +498,18 @@ class HostStreamingStepper:
         slot = self._next_slot
         self._next_slot ^= 1
         with torch.cuda.device(o.device):
-            check(o.lib.fmhr_ham_host_u8_submit(ctypes.byref(cfg), ptr(h_imgs_u8), ptr(h_masks_u8),
-                                                ptr(self._stagings[slot])), "ham_host_u8_submit")
+            if boxes is None:
+                check(o.lib.fmhr_ham_host_u8_submit(ctypes.byref(cfg), ptr(h_imgs_u8), ptr(h_masks_u8),
+                                                    ptr(self._stagings[slot])), "ham_host_u8_submit")
+                self.last_submit_bytes = self.h2d_bytes_u8 - 4 * self.n * 32
+            else:
+                if boxes.is_cuda or boxes.dtype != torch.int32 or tuple(boxes.shape) != (self.n, 4) or not boxes.is_contiguous():
+                    raise RuntimeError("HostStreamingStepper: boxes must be a contiguous int32 CPU tensor [n,4]")
+                nb = _lib.c_sz(0)
+                check(o.lib.fmhr_ham_host_u8_submit_boxes(ctypes.byref(cfg), ptr(h_imgs_u8), ptr(h_masks_u8), ptr(boxes),
+                                                          ptr(self._stagings[slot]), ctypes.byref(nb)),
+                      "ham_host_u8_submit_boxes")
+                self.last_submit_bytes = int(nb.value)
         return slot
 
     def step_submitted_u8(self, ticket, h_w2cs, h_projs, sh_rows, albedo_weight=None):

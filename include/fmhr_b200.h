@@ -292,6 +292,13 @@ int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_buffers* bu
  * rank, else the update is fmhr_ham_step_update_peer (buf->packed must be peers->packed[rank], see below). */
 int fmhr_ham_host_u8_submit(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
                             void* staging);
+/* fmhr_ham_host_u8_submit that only moves what can matter: boxes_host [n_views,4] int32 = (y0, y1, x0, x1), half-open, per
+ * view SLOT a rectangle containing every pixel whose mask byte is > 127 (loader metadata: the bounding box of the
+ * segmentation).  Outside it mask = 0, so no pixel is valid (mesh_sfs_optim.py:276-281) and no image byte is read; the mask
+ * staging plane is zero-filled on the device and the rectangles travel as row-pitched 2-D copies.  *h2d_bytes (optional)
+ * receives the bytes queued (4 per pixel of the rectangles). */
+int fmhr_ham_host_u8_submit_boxes(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
+                                  const int32_t* boxes_host, void* staging, size_t* h2d_bytes);
 struct fmhr_ham_peers;
 int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* w2cs_host,
                                     const float* projs_host, void* staging, float* losses_host,

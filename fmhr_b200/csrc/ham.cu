@@ -10,6 +10,8 @@
 // Nothing here materialises rast_out, the [n,V,7] attribute tensor, the [n,H,W,7] interpolated plane or the
 // [n,F,3,3] face-vertex gather of the reference; per pixel the only HBM planes are the 8-byte z-buffer, one float4
 // shaded colour and one float4 pixel-gradient (two of each in phase A, where 6 channels are antialiased).
+#include <stdlib.h>
+
 #include "aa_rule.cuh"
 
 // resident 256-thread blocks per SM the pixel / coverage kernels are compiled for (register budget = 65536 / 256 / N);
@@ -1979,6 +1981,34 @@ __global__ void __launch_bounds__(256) ham_u8_to_f32_kernel(const uchar4* __rest
     }
 }
 
+// Box rows of a pinned host batch -> device staging, read by the SMs straight from host memory (zero-copy) with 16-byte
+// loads: one warp per (view, row), lane l takes 16-byte chunk l, l + 32, ... of the row segment (aligned down / up to 16
+// bytes; the few extra bytes are genuine neighbours of the same planes).  tools/ubench/hostread_bench.cu: such a kernel
+// reads 270-450-byte row segments at 38-43 GB/s and contiguous memory at the DMA engines' rate, while ~100 separate
+// row-pitched cudaMemcpy2DAsync operations per step cost ~4 us of copy-engine time EACH.
+__device__ __forceinline__ uint4 ld_host16(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) ham_pull_boxes_kernel(const uint8_t* __restrict__ imgs_host,
+                                                             const uint8_t* __restrict__ masks_host,
+                                                             const int4* __restrict__ boxes, int H, int W,
+                                                             uint8_t* __restrict__ st_img, uint8_t* __restrict__ st_msk) {
+    const int v = blockIdx.y;
+    const int4 b = boxes[v];  // y0, y1, x0, x1
+    if (b.y <= b.x || b.w <= b.z) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    for (int r = b.x + warp; r < b.y; r += nw) {
+        const size_t p0 = ((size_t)v * H + r) * W + b.z, p1 = p0 + (size_t)(b.w - b.z);
+        for (size_t c = ((3 * p0) & ~(size_t)15) + 16 * (size_t)lane; c < 3 * p1; c += 512)
+            *reinterpret_cast<uint4*>(st_img + c) = ld_host16(imgs_host + c);
+        for (size_t c = (p0 & ~(size_t)15) + 16 * (size_t)lane; c < p1; c += 512)
+            *reinterpret_cast<uint4*>(st_msk + c) = ld_host16(masks_host + c);
+    }
+}
+
 // Side stream for work that is independent of the rendering chain (forked / joined with events, so it is captured into
 // the same CUDA graph when the caller's stream is being captured).
 struct BoxGraph {
@@ -1998,6 +2028,8 @@ struct SideStream {
     cudaEvent_t slot_ready[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
     BoxGraph box_graph[2];  // captured copy lists of fmhr_ham_host_u8_submit_boxes, one per staging slot
+    int4* box_dev[2] = {nullptr, nullptr};  // device copies of the box tables (pull-kernel form)
+    int box_cap[2] = {0, 0};
     int dev = -1;
 };
 // Host batch in flight (fmhr_ham_step_host_u8): the render chain converts it right before the first kernel that reads
@@ -2117,7 +2149,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     }
     FMHR_STAGE_MARK();  // 3: coverage (transform + visibility)
     if (g_pending.staging) {  // host batch of fmhr_ham_step_host_u8: first use of images / masks is the shade pass
-        FMHR_CUDA(cudaStreamWaitEvent(st, g_pending.ready, 0));
+        if (g_pending.ready) FMHR_CUDA(cudaStreamWaitEvent(st, g_pending.ready, 0));
         const size_t n_img4 = P * 3 / 4, n_all4 = n_img4 + P / 4;
         ham_u8_to_f32_kernel<<<cdiv((long long)n_all4, 256), 256, 0, st>>>((const uchar4*)g_pending.staging, n_img4, n_all4,
                                                                           (float4*)b->imgs, (float4*)b->masks);
@@ -2568,6 +2600,31 @@ extern "C" int fmhr_ham_host_u8_submit_boxes(const fmhr_ham_config* cfg, const u
         const int32_t* b = boxes_host + 4 * v;
         if (b[1] > b[0] && b[3] > b[2]) bytes += (size_t)(b[1] - b[0]) * (size_t)(b[3] - b[2]) * 4;
     }
+    // Preferred form: ONE kernel pulls every box row out of the mapped host buffers (needs device-visible, 16-byte aligned
+    // pinned memory and planes whose byte counts are multiples of 16); otherwise the rectangles go as 2-D DMA copies.
+    void *d_imgs = nullptr, *d_masks = nullptr;
+    const char* force_dma = getenv("FMHR_BOX_DMA");  // test hook: exercise the 2-D copy form
+    const bool can_pull = !(force_dma && force_dma[0] == '1') && (P % 16 == 0) &&
+                          (((uintptr_t)imgs_host | (uintptr_t)masks_host) & 15) == 0 &&
+                          cudaHostGetDevicePointer(&d_imgs, (void*)imgs_host, 0) == cudaSuccess &&
+                          cudaHostGetDevicePointer(&d_masks, (void*)masks_host, 0) == cudaSuccess;
+    if (!can_pull) cudaGetLastError();
+    if (can_pull) {
+        if (side->box_cap[slot] < n) {
+            if (side->box_dev[slot]) FMHR_CUDA(cudaFree(side->box_dev[slot]));
+            side->box_dev[slot] = nullptr;
+            FMHR_CUDA(cudaMalloc(&side->box_dev[slot], (size_t)n * sizeof(int4)));
+            side->box_cap[slot] = n;
+        }
+        FMHR_CUDA(cudaMemcpyAsync(side->box_dev[slot], boxes_host, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, side->copy));
+        FMHR_CUDA(cudaMemsetAsync(st_msk, 0, P, side->copy));
+        ham_pull_boxes_kernel<<<dim3(8, n), 256, 0, side->copy>>>((const uint8_t*)d_imgs, (const uint8_t*)d_masks,
+                                                                  side->box_dev[slot], H, W, st_img, st_msk);
+        FMHR_LAUNCH_CHECK();
+        FMHR_CUDA(cudaEventRecord(side->slot_ready[slot], side->copy));
+        if (h2d_bytes) *h2d_bytes = bytes;
+        return FMHR_OK;
+    }
     // A loader cycles through a few pinned buffers, so the same (host batch, boxes, staging) triple comes back: the second
     // time it is seen its 1 + 2 n copy operations are captured into a CUDA graph, afterwards one graph launch replaces
     // ~100 driver calls per step (the submission was host-bound: 0.3 ms of API time for 0.15 ms of transfer).
@@ -2617,39 +2674,74 @@ extern "C" int fmhr_ham_host_u8_submit_boxes(const fmhr_ham_config* cfg, const u
     return FMHR_OK;
 }
 
-extern "C" int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf,
-                                               const float* w2cs_host, const float* projs_host, void* staging,
-                                               float* losses_host, const fmhr_ham_peers* peers, fmhr_stream_t stream) {
+// The submitted-batch step in three parts, so that a host can capture the device work (body) into a CUDA graph while the
+// cross-stream handshakes with the copy stream (acquire / release) stay ordinary stream operations around the replay.
+static int submitted_slot(SideStream* side, const void* staging, const char* who) {
+    const int slot = side->slot_ptr[0] == staging ? 0 : (side->slot_ptr[1] == staging ? 1 : -1);
+    if (slot < 0 || side->slot_used[slot]) {
+        set_error("%s: no batch was submitted into this staging buffer", who);
+        return -1;
+    }
+    return slot;
+}
+
+extern "C" int fmhr_ham_step_host_u8_acquire(void* staging, fmhr_stream_t stream) {
+    FMHR_CHECK_ARG(staging);
+    SideStream* side = nullptr;
+    int rc = side_stream(&side);
+    if (rc) return rc;
+    const int slot = submitted_slot(side, staging, "fmhr_ham_step_host_u8_acquire");
+    if (slot < 0) return FMHR_EINVAL;
+    FMHR_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, side->slot_ready[slot], 0));
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_step_host_u8_body(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* w2cs_host,
+                                          const float* projs_host, const void* staging, float* losses_host,
+                                          const fmhr_ham_peers* peers, fmhr_stream_t stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     rc = ham_check_buffers(cfg, buf);
     if (rc) return rc;
     FMHR_CHECK_ARG(w2cs_host && projs_host && staging && losses_host);
     FMHR_CHECK_ARG(((uintptr_t)buf->imgs & 15) == 0 && ((uintptr_t)buf->masks & 15) == 0);
+    FMHR_CHECK_ARG(((size_t)cfg->n_views * cfg->H * cfg->W) % 4 == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    SideStream* side = nullptr;
-    rc = side_stream(&side);
-    if (rc) return rc;
-    const int slot = side->slot_ptr[0] == staging ? 0 : (side->slot_ptr[1] == staging ? 1 : -1);
-    if (slot < 0 || side->slot_used[slot]) {
-        set_error("fmhr_ham_step_host_u8_submitted: no batch was submitted into this staging buffer");
-        return FMHR_EINVAL;
-    }
     const size_t n = cfg->n_views;
     FMHR_CUDA(cudaMemcpyAsync((void*)buf->w2cs, w2cs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
     FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
     g_pending.staging = (const uint8_t*)staging;
-    g_pending.ready = side->slot_ready[slot];
-    g_pending.consumed = side->slot_free[slot];
+    g_pending.ready = nullptr;     // acquire ordered the stream behind the upload
+    g_pending.consumed = nullptr;  // release frees the buffer
     rc = fmhr_ham_step_render(cfg, buf, stream);
     g_pending.staging = nullptr;
-    g_pending.consumed = nullptr;
     if (rc) return rc;
-    side->slot_used[slot] = true;
     rc = peers ? fmhr_ham_step_update_peer(cfg, buf, peers, stream) : fmhr_ham_step_update(cfg, buf, stream);
     if (rc) return rc;
     FMHR_CUDA(cudaMemcpyAsync(losses_host, buf->losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_step_host_u8_release(void* staging, fmhr_stream_t stream) {
+    FMHR_CHECK_ARG(staging);
+    SideStream* side = nullptr;
+    int rc = side_stream(&side);
+    if (rc) return rc;
+    const int slot = submitted_slot(side, staging, "fmhr_ham_step_host_u8_release");
+    if (slot < 0) return FMHR_EINVAL;
+    FMHR_CUDA(cudaEventRecord(side->slot_free[slot], (cudaStream_t)stream));
+    side->slot_used[slot] = true;
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf,
+                                               const float* w2cs_host, const float* projs_host, void* staging,
+                                               float* losses_host, const fmhr_ham_peers* peers, fmhr_stream_t stream) {
+    int rc = fmhr_ham_step_host_u8_acquire(staging, stream);
+    if (rc) return rc;
+    rc = fmhr_ham_step_host_u8_body(cfg, buf, w2cs_host, projs_host, staging, losses_host, peers, stream);
+    if (rc) return rc;
+    return fmhr_ham_step_host_u8_release(staging, stream);
 }
 
 extern "C" size_t fmhr_ham_init_scratch_bytes(int num) { return num > 0 ? (size_t)(num + 1) * 56 * sizeof(double) : 0; }

@@ -490,7 +490,9 @@ class HostStreamingStepper:
         for t in (h_imgs_u8, h_masks_u8):
             if t.is_cuda or not t.is_contiguous() or t.dtype != torch.uint8 or not t.is_pinned():
                 raise RuntimeError("HostStreamingStepper: host batches must be pinned, contiguous uint8 CPU tensors")
-        cfg = o._cfg(self.n, 1, None)
+        cfg = self.__dict__.get("_submit_cfg")
+        if cfg is None:
+            cfg = self._submit_cfg = o._cfg(self.n, 1, None)
         if getattr(self, "_stagings", None) is None:
             nbytes = o.lib.fmhr_ham_host_u8_staging_bytes(ctypes.byref(cfg))
             self._stagings = [torch.empty(nbytes, dtype=torch.uint8, device=o.device) for _ in range(2)]
@@ -513,7 +515,10 @@ class HostStreamingStepper:
         return slot
 
     def step_submitted_u8(self, ticket, h_w2cs, h_projs, sh_rows, albedo_weight=None):
-        """The iteration on the batch submitted under `ticket` (cameras: pinned float32 [n,4,4])."""
+        """The iteration on the batch submitted under `ticket` (cameras: pinned float32 [n,4,4]).  With use_graphs (the
+        optimiser's setting) the device work - camera upload, conversion, render, update, loss read-back - is captured
+        once per (staging buffer, z-buffer slot, host pointers) and replayed with one launch; the handshakes with the copy
+        stream stay outside the graph (fmhr_ham_step_host_u8_acquire / _release)."""
         o = self.opt
         for t in (h_w2cs, h_projs):
             if t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or not t.is_pinned():
@@ -522,17 +527,49 @@ class HostStreamingStepper:
             o.begin_phase_b()
         if o.world > 1 and o.peer is None:
             raise RuntimeError("HostStreamingStepper needs the peer-memory exchange on more than one rank")
-        cfg = o._cfg(self.n, 1, albedo_weight)
-        buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows,
-                         self.d_vm2)
+        # the per-step Python work is on the critical path (the loss record is read back after every step): the
+        # configuration / buffer structs are built once per (albedo_weight, SH rows, workspace)
+        ckey = (None if albedo_weight is None else float(albedo_weight), sh_rows.data_ptr(),
+                0 if o.workspace is None else o.workspace.data_ptr())
+        cache = self.__dict__.setdefault("_struct_cache", {})
+        cb = cache.get(ckey)
+        if cb is None or cb[2] != (0 if o.workspace is None else o.workspace.data_ptr()):
+            cfg = o._cfg(self.n, 1, albedo_weight)
+            buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows,
+                             self.d_vm2)
+            if len(cache) > 32:
+                cache.clear()
+            cb = cache[(ckey[0], ckey[1], o.workspace.data_ptr())] = (cfg, buf, o.workspace.data_ptr(), sh_rows)
+        cfg, buf = cb[0], cb[1]
+        staging = self._stagings[ticket]
         with torch.cuda.device(o.device):
             o._prepare_zbuf(cfg, buf)
             peers = None
             if o.peer is not None:  # the exchange is part of the update kernels: still one call per iteration
                 buf.packed = o.peer.packed[cfg.zbuf_slot].data_ptr()
                 peers = ctypes.byref(o.peer.structs[cfg.zbuf_slot])
-            check(o.lib.fmhr_ham_step_host_u8_submitted(ctypes.byref(cfg), ctypes.byref(buf), ptr(h_w2cs), ptr(h_projs),
-                                                        ptr(self._stagings[ticket]), ptr(self.losses_host), peers,
-                                                        stream()),
-                  "ham_step_host_u8_submitted")
+            body = lambda sp: check(o.lib.fmhr_ham_step_host_u8_body(
+                ctypes.byref(cfg), ctypes.byref(buf), ptr(h_w2cs), ptr(h_projs), ptr(staging), ptr(self.losses_host), peers,
+                sp), "ham_step_host_u8_body")
+            check(o.lib.fmhr_ham_step_host_u8_acquire(ptr(staging), stream()), "ham_step_host_u8_acquire")
+            if not o.use_graphs:
+                body(stream())
+            else:
+                key = (ticket, cfg.zbuf_slot, h_w2cs.data_ptr(), h_projs.data_ptr(), sh_rows.data_ptr(),
+                       None if albedo_weight is None else float(albedo_weight), o.workspace.data_ptr())
+                graphs = self.__dict__.setdefault("_step_graphs", {})
+                gr = graphs.get(key)
+                if gr is None:
+                    if len(graphs) >= 16:
+                        graphs.clear()
+                    cur = torch.cuda.current_stream(o.device)
+                    side = torch.cuda.Stream(device=o.device)
+                    side.wait_stream(cur)
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, stream=side):  # capture only: nothing runs, the optimiser does not advance
+                        body(_lib.c_p(torch.cuda.current_stream(o.device).cuda_stream))
+                    cur.wait_stream(side)
+                    graphs[key] = gr
+                gr.replay()
+            check(o.lib.fmhr_ham_step_host_u8_release(ptr(staging), stream()), "ham_step_host_u8_release")
         return self.losses_host

@@ -292,6 +292,15 @@ int fmhr_ham_step_host_u8(const fmhr_ham_config* cfg, const fmhr_ham_buffers* bu
  * rank, else the update is fmhr_ham_step_update_peer (buf->packed must be peers->packed[rank], see below). */
 int fmhr_ham_host_u8_submit(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
                             void* staging);
+struct fmhr_ham_peers;
+/* fmhr_ham_step_host_u8_submitted == acquire + body + release.  A host that replays the device work from a CUDA graph
+ * captures `body` once per (staging buffer, z-buffer slot) and brackets every replay with acquire (orders `stream` behind
+ * the upload of the batch) and release (lets the copy stream refill the staging buffer once the step has consumed it). */
+int fmhr_ham_step_host_u8_acquire(void* staging, fmhr_stream_t stream);
+int fmhr_ham_step_host_u8_body(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* w2cs_host,
+                               const float* projs_host, const void* staging, float* losses_host,
+                               const struct fmhr_ham_peers* peers, fmhr_stream_t stream);
+int fmhr_ham_step_host_u8_release(void* staging, fmhr_stream_t stream);
 /* fmhr_ham_host_u8_submit that only moves what can matter: boxes_host [n_views,4] int32 = (y0, y1, x0, x1), half-open, per
  * view SLOT a rectangle containing every pixel whose mask byte is > 127 (loader metadata: the bounding box of the
  * segmentation).  Outside it mask = 0, so no pixel is valid (mesh_sfs_optim.py:276-281) and no image byte is read; the mask
@@ -299,7 +308,6 @@ int fmhr_ham_host_u8_submit(const fmhr_ham_config* cfg, const uint8_t* imgs_host
  * receives the bytes queued (4 per pixel of the rectangles). */
 int fmhr_ham_host_u8_submit_boxes(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
                                   const int32_t* boxes_host, void* staging, size_t* h2d_bytes);
-struct fmhr_ham_peers;
 int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* w2cs_host,
                                     const float* projs_host, void* staging, float* losses_host,
                                     const struct fmhr_ham_peers* peers, fmhr_stream_t stream);

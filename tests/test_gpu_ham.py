@@ -368,13 +368,15 @@ def test_host_streaming_u8_step_matches_resident(scene):
         stepper.step_phase_b_u8(h[0].float().pin_memory(), h[1], h[2], h[3], views)
 
 
-@pytest.mark.parametrize("use_boxes", [False, True])
-def test_host_streaming_u8_pipelined_matches_resident(scene, use_boxes):
+@pytest.mark.parametrize("use_boxes", [False, "pull", "dma"])
+def test_host_streaming_u8_pipelined_matches_resident(scene, use_boxes, monkeypatch):
     """fmhr_ham_host_u8_submit / fmhr_ham_step_host_u8_submitted: the batch of step i+1 is uploaded while step i runs, two
     staging buffers in flight.  Two DIFFERENT batches alternate, so consuming the wrong slot (or a slot refilled too
     early) changes the losses; must equal the resident path fed with the same quantised images step by step.
-    use_boxes: only the bounding box of every view's segmentation travels (fmhr_ham_host_u8_submit_boxes); the staging
+    use_boxes: only the bounding box of every view's segmentation travels (fmhr_ham_host_u8_submit_boxes: "pull" = one
+    kernel reading the box rows from the mapped host buffers, "dma" = row-pitched 2-D copies, the fallback); the staging
     buffers are poisoned with 0xFF first, so a mask byte that is neither copied nor zero-filled would read as "set"."""
+    monkeypatch.setenv("FMHR_BOX_DMA", "1" if use_boxes == "dma" else "0")
     import copy
     from fmhr_b200.ham import HostStreamingStepper
     n, H, W = scene["imgs"].shape[0], scene["imgs"].shape[1], scene["imgs"].shape[2]
@@ -390,6 +392,7 @@ def test_host_streaming_u8_pipelined_matches_resident(scene, use_boxes):
     b = _make_opt(q, debug=False)
     f_imgs = [torch.tensor(x.astype(np.float32) / np.float32(255.0)).cuda() for x in (img_a, img_b)]
     views = torch.arange(n, dtype=torch.int32, device="cuda")
+    b.use_graphs = use_boxes == "pull"  # this variant also replays the step's device work from CUDA graphs
     stepper = HostStreamingStepper(b, n)
     stepper.set_resident_valid_masks(b.valid_masks)
     pin = lambda x, dt: torch.tensor(x, dtype=dt).contiguous().pin_memory()

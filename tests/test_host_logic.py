@@ -192,3 +192,30 @@ def test_result_files_follow_the_reference_formats(tmp_path):
     assert np.allclose(v, verts, atol=1e-4)
     assert np.array_equal(f, faces[:, [0, 2, 1]])                                   # flipped winding
     assert np.allclose(c, np.clip(0.5 * albedo, 0, 1)[:, ::-1], atol=1e-4)          # BGR -> RGB
+
+
+def test_mask_boxes_contain_every_set_pixel():
+    """Loader metadata of the host-batch path (fmhr_ham_host_u8_submit_boxes): the half-open rectangle of every view must
+    contain every pixel with mask byte > 127 - outside it nothing is uploaded - and be tight; an empty mask gives (0,0,0,0)."""
+    import numpy as np
+    from fmhr_b200.ham import HostStreamingStepper
+    rng = np.random.default_rng(0)
+    m = np.zeros((5, 40, 56), dtype=np.uint8)
+    m[0, 3:17, 10:31] = 255
+    m[1, 0, 0] = 200            # a single pixel in the corner
+    m[2, 39, 55] = 128          # ... and in the opposite one
+    m[3] = (rng.random((40, 56)) > 0.97) * 255
+    m[3, 5, 7] = 127            # not set: the loader's rule is > 127
+    boxes = HostStreamingStepper.mask_boxes(m)
+    assert boxes.dtype == torch.int32 and tuple(boxes.shape) == (5, 4)
+    assert boxes[0].tolist() == [3, 17, 10, 31] and boxes[1].tolist() == [0, 1, 0, 1] and boxes[2].tolist() == [39, 40, 55, 56]
+    assert boxes[4].tolist() == [0, 0, 0, 0]
+    for v in range(5):
+        y0, y1, x0, x1 = boxes[v].tolist()
+        inside = np.zeros((40, 56), dtype=bool)
+        inside[y0:y1, x0:x1] = True
+        assert not ((m[v] > 127) & ~inside).any()
+        if y1 > y0:
+            s = m[v] > 127
+            assert s[y0].any() and s[y1 - 1].any() and s[:, x0].any() and s[:, x1 - 1].any()
+    assert torch.equal(HostStreamingStepper.mask_boxes(torch.from_numpy(m)), boxes)

@@ -344,7 +344,9 @@ __device__ __forceinline__ void ml_candidate(uint2 rec, int e, const float4* pos
 constexpr int kCovThreads = FMHR_COV_THREADS;
 // CLIP = true: stand-alone dr.rasterize (fmhr_rasterize_fwd_meshlets): `vg` is the caller's clip-space pos [N,clipV] (float4),
 // no transform, and only the tile bitmap is produced (glist / gcount are NULL).
-template <int TPT, bool CLIP = false>
+// DRAIN = true: variant for triangles of several pixels (chosen by the launcher when the frame has more than four pixels per
+// triangle): the fragment queue is drained between candidate rounds instead of overflowing into the in-place resolve.
+template <int TPT, bool CLIP = false, bool DRAIN = false>
 __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThreads)) ham_coverage_meshlet_kernel(
     const float4* __restrict__ vg, const float* __restrict__ viewM, const int32_t* __restrict__ ml_vptr,
     const int32_t* __restrict__ ml_verts, const uint2* __restrict__ ml_tri2, int max_verts, int H, int W, float invW,
@@ -396,9 +398,33 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
     __syncwarp();
     // stage B: edge functions of the survivors, spread densely over the lanes; hits go to the fragment queue
     unsigned long long* zb = zbuf + (size_t)n * H * W;
-    for (int e = lane; e < nc; e += 32)
-        ml_candidate(cand[warp][e], e, pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x, &qcount[warp], queue[warp]);
-    __syncwarp();
+    if (!DRAIN || nc <= 64) {
+        // micropolygons (config 2: ~40 % of a warp's 128 triangles are candidates, ~60 fragments): the queue cannot overflow
+        // by much, no drain logic in the loop
+        for (int e = lane; e < nc; e += 32)
+            ml_candidate(cand[warp][e], e, pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x, &qcount[warp], queue[warp]);
+        __syncwarp();
+    } else {
+        // Triangles of a few pixels (configs 1, 3, 5: nearly every triangle is a candidate) fill the queue long before the
+        // candidates run out, and what does not fit is resolved in place at one or two active lanes: drain the queue
+        // between rounds whenever the next round might not fit.
+        for (int e0 = 0; e0 < nc; e0 += 32) {  // warp-uniform trip count
+            const int e = e0 + lane;
+            if (e < nc)
+                ml_candidate(cand[warp][e], e, pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x, &qcount[warp], queue[warp]);
+            __syncwarp();
+            if (e0 + 32 < nc && qcount[warp] > kFragQueue - 96) {
+                const int nq0 = min(qcount[warp], kFragQueue);
+                for (int f = lane; f < nq0; f += 32) {
+                    const uint2 fr = queue[warp][f];
+                    ml_resolve(pos_s, cand[warp][fr.x], (int)(fr.y & 0xffffu), (int)(fr.y >> 16), W, invW, invH, zb);
+                }
+                __syncwarp();
+                if (lane == 0) qcount[warp] = 0;
+                __syncwarp();
+            }
+        }
+    }
     // stage C: depth resolve of the hits, again with all lanes busy
     const int nq = min(qcount[warp], kFragQueue);
     for (int f = lane; f < nq; f += 32) {
@@ -2129,17 +2155,26 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         }
         const dim3 grid(b->n_meshlets, n);
         const uint2* tri2 = (const uint2*)b->ml_tri2;
+        // more than four frame pixels per triangle (configs 1, 3, 5): triangles span several pixels, use the draining variant
+        const bool drain = (long long)H * W > 4ll * T;
 #define FMHR_COVERAGE(TPT)                                                                                             \
         do {                                                                                                           \
             static bool attr_set = false;                                                                              \
             if (!attr_set) {                                                                                           \
                 FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT>,                                       \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));              \
+                FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT, false, true>,                          \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));              \
                 attr_set = true;                                                                                       \
             }                                                                                                          \
-            ham_coverage_meshlet_kernel<TPT><<<grid, kCovThreads, smem, st>>>(                                         \
-                ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,               \
-                ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv, 0);                                   \
+            if (drain)                                                                                                 \
+                ham_coverage_meshlet_kernel<TPT, false, true><<<grid, kCovThreads, smem, st>>>(                        \
+                    ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,           \
+                    ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv, 0);                               \
+            else                                                                                                       \
+                ham_coverage_meshlet_kernel<TPT><<<grid, kCovThreads, smem, st>>>(                                     \
+                    ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,           \
+                    ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv, 0);                               \
         } while (0)
         if (b->ml_tris == 1024) FMHR_COVERAGE(1024 / kCovThreads);
         else if (b->ml_tris == 512) FMHR_COVERAGE(512 / kCovThreads);

@@ -2266,17 +2266,25 @@ int launch_meshlet_coverage_clip(const float* pos, int N, int V, int H, int W, c
     }
     const dim3 grid(n_meshlets, N);
     const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+    const bool drain = (long long)H * W > 4ll * (long long)n_meshlets * ml_tris;  // as in the fused path
 #define FMHR_COVERAGE_CLIP(TPT)                                                                                        \
     do {                                                                                                               \
         static bool attr_set = false;                                                                                  \
         if (!attr_set) {                                                                                               \
-            FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT, true>,                                     \
+            FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT, true, false>,                              \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));                  \
+            FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT, true, true>,                               \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));                  \
             attr_set = true;                                                                                           \
         }                                                                                                              \
-        ham_coverage_meshlet_kernel<TPT, true><<<grid, kCovThreads, smem, st>>>(                                       \
-            (const float4*)pos, nullptr, ml_vptr, ml_verts, (const uint2*)ml_tri2, ml_max_verts, H, W, invW, invH,     \
-            zbuf, tile_bits, nullptr, nullptr, tiles_x, tiles_pv, V);                                                  \
+        if (drain)                                                                                                     \
+            ham_coverage_meshlet_kernel<TPT, true, true><<<grid, kCovThreads, smem, st>>>(                             \
+                (const float4*)pos, nullptr, ml_vptr, ml_verts, (const uint2*)ml_tri2, ml_max_verts, H, W, invW, invH, \
+                zbuf, tile_bits, nullptr, nullptr, tiles_x, tiles_pv, V);                                              \
+        else                                                                                                           \
+            ham_coverage_meshlet_kernel<TPT, true, false><<<grid, kCovThreads, smem, st>>>(                            \
+                (const float4*)pos, nullptr, ml_vptr, ml_verts, (const uint2*)ml_tri2, ml_max_verts, H, W, invW, invH, \
+                zbuf, tile_bits, nullptr, nullptr, tiles_x, tiles_pv, V);                                              \
     } while (0)
     if (ml_tris == 1024) FMHR_COVERAGE_CLIP(1024 / kCovThreads);
     else if (ml_tris == 512) FMHR_COVERAGE_CLIP(512 / kCovThreads);

@@ -83,6 +83,20 @@ def test_bad_arguments_return_codes_not_crashes(lib):
     assert rc == -1 and b"invalid argument" in lib.fmhr_last_error_string()
     rc = lib.fmhr_interpolate_fwd(None, None, None, 1, 1, 1, 1, 8, 8, 3, None, None)
     assert rc == -1
+    # entry points added for the meshlet rasteriser, the peer exchange and the host-batch pipeline
+    assert lib.fmhr_rasterize_tile_words(2, 33, 17) == 2 * 1      # 3 x 2 tiles of 16 x 16 -> one 32-bit word per view
+    assert lib.fmhr_rasterize_tile_words(3, 512, 334) == 3 * 21   # 32 x 21 = 672 tiles -> 21 words
+    assert lib.fmhr_rasterize_tile_words(0, 8, 8) == 0
+    rc = lib.fmhr_rasterize_fwd_meshlets(None, None, 1, 1, 1, 8, 8, None, None, None, None, None, 1, 1024, 1, None, 0, 0,
+                                         None, None)
+    assert rc == -1
+    assert lib.fmhr_peer_alloc(0, None, None) == -1 and lib.fmhr_peer_open(None, None) == -1
+    assert lib.fmhr_peer_close(None) == -1 and lib.fmhr_peer_free(None) == -1
+    assert lib.fmhr_ham_step_update_peer(None, None, None, None) == -1
+    assert lib.fmhr_ham_host_u8_submit(None, None, None, None) == -1
+    assert lib.fmhr_ham_host_u8_submit_boxes(None, None, None, None, None, None) == -1
+    assert lib.fmhr_ham_step_host_u8_acquire(None, None) == -1 and lib.fmhr_ham_step_host_u8_release(None, None) == -1
+    assert lib.fmhr_ham_step_host_u8_body(None, None, None, None, None, None, None, None) == -1
 
 
 def test_product_never_touches_the_oracle():

@@ -535,3 +535,20 @@ def test_capture_room_and_stress_shapes():
     from oracle import refmath
     want = refmath.NCC(ref_p.double(), src_p.double(), None, msk.double())
     assert out.shape == (Nv, Np) and float((out.double() - want).abs().max()) < 2e-5
+
+
+def test_two_rank_exchange_on_two_gpus():
+    """The N > 1 path on real devices (skipped on a single-GPU box; the gloo test in test_host_logic.py covers the
+    reduction algebra on CPU): tests/multi_gpu_check.py under torchrun with two ranks - NCCL all-reduce, one-shot and
+    two-shot peer-memory exchange, eager and graph replay, alternating batch sizes, the host-batch step - each against a
+    single-rank optimiser that renders all views, and bit-identical replicas after the exchange."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])

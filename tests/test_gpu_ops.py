@@ -241,3 +241,48 @@ def test_reference_import_path():
     from fmhr_b200 import dr as fdr
     assert ndr.rasterize is fdr.rasterize and ndr.antialias is fdr.antialias
     assert ndr.RasterizeGLContext is fdr.RasterizeGLContext
+
+
+def test_mlp_forward_geometry_stage_on_the_shim(dr):
+    """the rendering half of train_mlp.mlp_forward (:165-185) - per-view camera-space normals (get_normals
+    on a batch of DISTINCT meshes), rasterize, ONE interpolate of the 30-wide feature stack [1 | normals | albedo | uniform
+    | vertex_feat.expand], mask = first channel - line for line on the CUDA shim and on the CPU oracle: same coverage,
+    features <= 1e-5, and the gradient that trains the per-vertex features (summed over the expanded batch) <= 1e-4."""
+    from fmhr_b200 import utils as futils
+    from oracle import refmath
+    wl = synth.WORKLOADS["tiny"]
+    v, f = synth.hand_mesh(wl["subdiv"], 1, seed=0)
+    w2c, proj = synth.make_cameras(wl["n"], wl["H"], wl["W"], v.mean(0).astype(np.float64),
+                                   extent=float(v[:, 1].max() - v[:, 1].min()))
+    B, H, W, V = wl["n"], wl["H"], wl["W"], v.shape[0]
+    g = torch.Generator().manual_seed(5)
+    vertices = torch.tensor(v)[None].expand(B, -1, -1).contiguous()
+    faces = torch.tensor(f)
+    albedo = torch.rand(B, V, 3, generator=g)
+    uni_vertices = torch.rand(B, V, 3, generator=g)      # vertices.clone().uniform_(0, 1) in the reference
+    vertex_feat0 = torch.randn(V, 20, generator=g)
+    wts = torch.randn(B, H, W, 30, generator=g)
+    # the two einsums run once on the CPU so that both sides rasterise bit-identical clip positions
+    vertsw = torch.cat([vertices, torch.ones_like(vertices[:, :, 0:1])], 2)
+    rot_verts = torch.einsum('ijk,ikl->ijl', vertsw, torch.tensor(w2c))
+    proj_verts = torch.einsum('ijk,ikl->ijl', rot_verts, torch.tensor(proj)).contiguous()
+
+    def stage(drmod, get_normals, dev):
+        to = lambda t: t.to(dev)
+        vertex_feat = to(vertex_feat0).clone().requires_grad_(True)
+        normals = get_normals(to(rot_verts)[:, :, :3], to(faces).long())
+        rast_out, _ = drmod.rasterize(drmod.RasterizeGLContext(), to(proj_verts), to(faces), resolution=(H, W))
+        feat = torch.cat([torch.ones_like(to(vertsw)[:, :, :1]), normals, to(albedo), to(uni_vertices),
+                          vertex_feat.unsqueeze(0).expand(B, -1, -1)], 2)
+        feat, _ = drmod.interpolate(feat, rast_out, to(faces))
+        masks = feat[:, :, :, :1].contiguous()
+        (feat * to(wts)).sum().backward()
+        return rast_out.detach().cpu(), feat.detach().cpu(), masks.detach().cpu(), vertex_feat.grad.cpu()
+
+    r_ref, f_ref, m_ref, g_ref = stage(orc, refmath.get_normals, "cpu")
+    r_gpu, f_gpu, m_gpu, g_gpu = stage(dr, futils.get_normals, "cuda")
+    assert f_gpu.shape == (B, H, W, 30)
+    assert torch.equal(r_gpu[..., 3], r_ref[..., 3]) and (r_ref[..., 3] > 0).any()
+    assert torch.equal(m_gpu[..., 0] > 0, r_ref[..., 3] > 0), "the reference selects pixels with masks[..., 0] > 0"
+    assert torch.allclose(f_gpu, f_ref, rtol=1e-5, atol=2e-6)
+    assert _rel(g_gpu, g_ref) < 1e-4

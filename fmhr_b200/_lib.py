@@ -47,7 +47,7 @@ MAX_PEERS = 16
 class HamPeers(ctypes.Structure):
     """struct fmhr_ham_peers"""
     _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("mode", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("packed", c_p * MAX_PEERS), ("flags", c_p * MAX_PEERS),
+                ("timeout_s", ctypes.c_int32), ("packed", c_p * MAX_PEERS), ("flags", c_p * MAX_PEERS),
                 ("reduced", c_p * MAX_PEERS), ("epoch", c_p)]
 
 
@@ -90,6 +90,7 @@ _SIGS = {
     "fmhr_peer_free": (c_i, [c_p]),
     "fmhr_ham_stage_times": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), ctypes.POINTER(c_f),
                                    ctypes.POINTER(c_i), c_p]),
+    "fmhr_trace_read": (c_i, [c_p, c_i, c_i]),
     "fmhr_ham_debug_export": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p]),
     "fmhr_ham_step_host": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "fmhr_ham_init_scratch_bytes": (c_sz, [c_i]),

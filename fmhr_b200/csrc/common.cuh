@@ -95,6 +95,40 @@ __device__ __forceinline__ bool snap_vertex(const float4 p, float hw, float hh, 
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Timeline tracing (diagnostic builds only, -DFMHR_TRACE; tools/trace_timeline.py): every kernel of the fused iteration
+// records the %globaltimer of its first block entry (atomicMin) and of its last warp exit (atomicMax) into slot `id`, so
+// the real schedule of a CUDA-graph replay - overlaps, fill / tail bubbles between kernels - can be read back.  The
+// product build compiles the scope to nothing.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTraceSlots = 64;
+#ifdef FMHR_TRACE
+static __device__ unsigned long long g_trace[kTraceSlots][2];  // only ham.cu's copy is used / read back
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct TraceScope {
+    int id;
+    __device__ __forceinline__ explicit TraceScope(int i) : id(i) {
+        if (threadIdx.x == 0) atomicMin(&g_trace[id][0], trace_now());
+    }
+    __device__ __forceinline__ ~TraceScope() {
+        if ((threadIdx.x & 31) == 0) atomicMax(&g_trace[id][1], trace_now());
+    }
+};
+__device__ __forceinline__ void trace_stamp_min(int id, int k) { atomicMin(&g_trace[id][k], trace_now()); }
+__device__ __forceinline__ void trace_stamp_max(int id, int k) { atomicMax(&g_trace[id][k], trace_now()); }
+#define FMHR_TRACE_SCOPE(id) fmhr::TraceScope trace_scope_(id)
+#define FMHR_TRACE_MIN(id, k) do { if (threadIdx.x == 0) fmhr::trace_stamp_min(id, k); } while (0)
+#define FMHR_TRACE_MAX(id, k) do { if (threadIdx.x == 0) fmhr::trace_stamp_max(id, k); } while (0)
+#else
+#define FMHR_TRACE_SCOPE(id)
+#define FMHR_TRACE_MIN(id, k)
+#define FMHR_TRACE_MAX(id, k)
+#endif
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // warp / block reductions

@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __res
                                                               const float* __restrict__ projs,
                                                               const int32_t* __restrict__ view_idx, int n_views,
                                                               float* __restrict__ viewM) {
+    FMHR_TRACE_SCOPE(0);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_views * kViewM) {
         const int n = i >> 4, r = (i >> 2) & 3, j = i & 3;
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(256, 6) ham_normals_kernel(const float4* __res
                                                           const int32_t* __restrict__ v2f_ptr,
                                                           const int2* __restrict__ v2f_nbr, int V,
                                                           float4* __restrict__ vattr, float4* __restrict__ raw4) {
+    FMHR_TRACE_SCOPE(1);
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, sub = threadIdx.x & 3;  // 4 lanes per vertex: ONE wave of blocks
     float ax = 0.f, ay = 0.f, az = 0.f;
     if (i < V) {
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
     const int32_t* __restrict__ ml_verts, const uint2* __restrict__ ml_tri2, int max_verts, int H, int W, float invW,
     float invH, unsigned long long* __restrict__ zbuf, uint32_t* __restrict__ gbits, uint32_t* __restrict__ glist,
     int* __restrict__ gcount, int tiles_x, int tiles_per_view, int clipV) {
+    FMHR_TRACE_SCOPE(4);
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4* pos_s = reinterpret_cast<float4*>(dyn_smem);
     int2* snap_s = reinterpret_cast<int2*>(pos_s + max_verts);
@@ -462,6 +465,7 @@ constexpr int kTriRec = 40;
 __global__ void __launch_bounds__(128) ham_trirec_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ opp,
                                                          const float4* __restrict__ vg, const float4* __restrict__ vattr,
                                                          int V, int T, float4* __restrict__ trirec) {
+    FMHR_TRACE_SCOPE(2);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     int iv[3], ov[3];
@@ -678,6 +682,7 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
                                                        int H, int W, uint2* __restrict__ clist, int* __restrict__ ccount,
                                                        uint32_t* __restrict__ ringbits, uint32_t* __restrict__ rlist,
                                                        int* __restrict__ rcount, int rcap, int* __restrict__ status) {
+    FMHR_TRACE_SCOPE(5);
     // unit of work = half a tile (16 x 8 pixels): a lane owns column (lane & 15) of rows (lane >> 4) + 2k, k = 0..3, so
     // the four key loads of a unit are independent and issued back to back
     constexpr int kBuf = 288, kRBuf = 96;
@@ -830,6 +835,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_SHADE) ham_shade_kernel(uint2* __
                                                         const int32_t* __restrict__ sh_idx, int V, int H, int W,
                                                         float4* __restrict__ plane0, float4* __restrict__ plane1,
                                                         double* __restrict__ acc) {
+    FMHR_TRACE_SCOPE(6);
     const int nc = *ccount;
     const int hw = H * W;
     float nvalid = 0.0f;
@@ -919,6 +925,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     float* __restrict__ dbg_image, float* __restrict__ dbg_mask, uint4* __restrict__ plist_a,
     uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap, int* __restrict__ status,
     double* __restrict__ init_acc) {
+    FMHR_TRACE_SCOPE(7);
     // PHASE 2 = HAM initialisation (mesh_sfs_optim.py:124-163): plane0 holds interpolated NORMALS, they and the coverage
     // are antialiased like phase B's colour + coverage; `imgs` is the gray image [num,H,W]; outputs: antialiased coverage
     // (dbg_mask), unit antialiased normal (gplane0) and the per-view normal equations of the SH fit (init_acc).
@@ -1289,6 +1296,7 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
     int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ gplane0,
     const float4* __restrict__ gplane1, const float4* __restrict__ trirec, float invW, float invH,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, float4* __restrict__ G) {
+    FMHR_TRACE_SCOPE(8);
     const int np = min(*pcount, pcap);
     const int hw = H * W;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < np; e += gridDim.x * blockDim.x) {
@@ -1351,6 +1359,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_BWD) ham_pixel_bwd_kernel(
     const float4* __restrict__ trirec, float invW, float invH, const float* __restrict__ viewM,
     const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, int V, int H, int W,
     const float4* __restrict__ gplane0, const float4* __restrict__ gplane1, float4* __restrict__ G) {
+    FMHR_TRACE_SCOPE(9);
     const int nv = *ccount;
     const int e_first = blockIdx.x * blockDim.x + threadIdx.x, e_stride = gridDim.x * blockDim.x;
     uint2 ent_next = e_first < nv ? clist[e_first] : make_uint2(0u, 0u);
@@ -1456,6 +1465,7 @@ __global__ void __launch_bounds__(32) ham_finalize_scalars_kernel(const double* 
                                                                   const double* __restrict__ view_vm2,
                                                                   const int32_t* __restrict__ view_idx, int n_views,
                                                                   int tiles, int phase, float* __restrict__ scal) {
+    FMHR_TRACE_SCOPE(10);
     const int lane = threadIdx.x;
     double vm2 = 0.0;  // sum of valid_mask^2 over the batch's views; acc[2] holds the listed pixels' corrections
     if (phase == 1)
@@ -1551,6 +1561,7 @@ __global__ void __launch_bounds__(256, 6) ham_regulariser_kernel(
     const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
     const int32_t* __restrict__ v2v_idx, float4* __restrict__ ys, double* __restrict__ acc,
     int32_t* __restrict__ adam_step, float* __restrict__ adam_sc) {
+    FMHR_TRACE_SCOPE(3);
     __shared__ float red[4][8];
     const int V = cfg.V;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
@@ -1630,6 +1641,7 @@ __global__ void __launch_bounds__(256) ham_normal_grad_kernel(int V, float4* __r
                                                               const float4* __restrict__ vattr,
                                                               const float4* __restrict__ raw4,
                                                               const float4* __restrict__ packed4) {
+    FMHR_TRACE_SCOPE(11);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float4 ga = packed4[2 * (size_t)i], gb = packed4[2 * (size_t)i + 1];
@@ -1670,6 +1682,7 @@ struct HamPeerArgs {
     uint32_t* signal_b[FMHR_MAX_PEERS];    // second flag word per rank pair: "my chunk has landed in your `reduced`"
     const uint32_t* flags_b;
     int rank, chunk;                       // chunk = ceil(V / world) vertices per rank
+    long long timeout_cycles;              // rendezvous give-up time (SM cycles)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -1687,7 +1700,13 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {  // peer lines must
 }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-constexpr long long kPeerTimeoutCycles = 6000000000ll;  // ~3 s at 1.97 GHz: a lost peer flags the step instead of hanging
+// A peer that never posts its step must not hang the device: after `timeout_cycles` SM cycles (fmhr_ham_peers.timeout_s,
+// default 30 s) the rendezvous gives up and raises status bit 2.  That is FATAL and non-destructive: the update kernels
+// then leave parameters, Adam state and the step counters untouched, poison the loss record with NaN and latch
+// adam_step[3] (sticky across steps: every later update refuses as well) until the host has seen it
+// (HamOptimizer.check_health raises).
+constexpr long long kPeerCyclesPerSecond = 2000000000ll;
+constexpr int kPeerDefaultTimeoutS = 30;
 
 __device__ __forceinline__ void st_peer(float4* p, float4 v) {
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -1697,23 +1716,27 @@ __device__ __forceinline__ void st_peer(float4* p, float4 v) {
 // wait for theirs.  Every block posts the (idempotent) word, so no block ever waits on another block of its own grid;
 // everything this rank wrote in earlier kernels of the stream is visible to a peer that has seen the word.
 __device__ __forceinline__ void peer_rendezvous(uint32_t* const* signal, const uint32_t* flags, int world, uint32_t want,
-                                                int* status) {
+                                                int* status, long long timeout_cycles, int trace_slot) {
+    FMHR_TRACE_MIN(trace_slot, 0);  // first block of this rank posts
     if (threadIdx.x < world) {
         __threadfence_system();
         st_release_sys(signal[threadIdx.x], want);
         const uint32_t* f = flags + threadIdx.x;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
-            if (clock64() - t0 > kPeerTimeoutCycles) { atomicOr(status, 4); break; }
+            if (clock64() - t0 > timeout_cycles) { atomicOr(status, 4); break; }
         }
     }
     __syncthreads();
+    FMHR_TRACE_MIN(trace_slot + 1, 0);  // first block that has seen every peer
+    FMHR_TRACE_MAX(trace_slot, 1);      // last block that has seen every peer
 }
 
 // Two-shot exchange, kernel 1 (reduce-scatter + all-gather by peer stores): after the rendezvous thread j sums vertex
 // rank*chunk + j over every rank's `packed` (rank order) and stores the three sums into EVERY rank's `reduced`.
 __global__ void __launch_bounds__(256) ham_peer_reduce_scatter_kernel(int V, HamPeerArgs pa, int* __restrict__ status) {
-    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status);
+    FMHR_TRACE_SCOPE(13);
+    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 20);
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == pa.chunk) {  // the four loss scalars: rank 0
         if (pa.rank != 0) return;
@@ -1753,7 +1776,8 @@ __global__ void __launch_bounds__(256) ham_peer_normal_grad_kernel(int V, float4
                                                                    const float4* __restrict__ vattr,
                                                                    const float4* __restrict__ raw4, HamPeerArgs pa,
                                                                    int* __restrict__ status) {
-    peer_rendezvous(pa.signal_b, pa.flags_b, pa.world, *pa.epoch + 1u, status);
+    FMHR_TRACE_SCOPE(14);
+    peer_rendezvous(pa.signal_b, pa.flags_b, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 22);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float4 ga = ld_peer(pa.reduced + 2 * (size_t)i), gb = ld_peer(pa.reduced + 2 * (size_t)i + 1);
@@ -1777,7 +1801,8 @@ __global__ void __launch_bounds__(256) ham_peer_reduce_normal_grad_kernel(int V,
                                                                           const float4* __restrict__ vattr,
                                                                           const float4* __restrict__ raw4, HamPeerArgs pa,
                                                                           int* __restrict__ status) {
-    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status);
+    FMHR_TRACE_SCOPE(15);
+    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 20);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > V) return;
     if (i == V) {  // the four loss scalars behind the accumulators
@@ -1840,8 +1865,21 @@ __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
     const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed, const float4* __restrict__ ys,
     float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
     const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad,
-    const int* __restrict__ status, uint32_t* __restrict__ epoch_bump) {
+    const int* __restrict__ status, uint32_t* __restrict__ epoch_bump, int32_t* __restrict__ adam_step) {
+    FMHR_TRACE_SCOPE(12);
     const int V = cfg.V;
+    // a peer never arrived (this step, or latched by an earlier one): the summed gradients are incomplete - refuse the
+    // whole update (parameters, Adam moments and step counters stay as they were) and poison the loss record
+    const bool fatal = (status && (*status & 4)) || adam_step[3] != 0;
+    if (fatal) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            for (int k = 0; k < 8; k++) losses[k] = __int_as_float(0x7fc00000);
+            // the regulariser kernel advanced the counters of the parameters that step in this phase: take that back
+            adam_step[0] -= (cfg.phase == 1); adam_step[1] -= 1; adam_step[2] -= (cfg.phase == 0);
+            adam_step[3] = 1;
+        }
+        return;
+    }
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
     const float* scal = packed + 12 * (size_t)V;
     const float n_valid = scal[0];
@@ -1858,8 +1896,8 @@ __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
         losses[0] = sfs; losses[1] = cfg.phase == 1 ? lap : 0.0f; losses[2] = alb; losses[3] = msk;
         losses[4] = cfg.phase == 1 ? edg : 0.0f; losses[5] = cfg.phase == 1 ? del : 0.0f; losses[6] = n_valid;
         losses[7] = cfg.phase == 1 ? sfs + lap + alb + msk + edg + del : sfs;
-        // pair list overflow (bit 0) or a peer that never posted its step (bit 2): refuse a number
-        if (status && (*status & 5)) losses[7] = __int_as_float(0x7fc00000);
+        // pair list (bit 0) or ring list (bit 1) overflow: pixels were dropped, refuse a number
+        if (status && (*status & 3)) losses[7] = __int_as_float(0x7fc00000);
         if (epoch_bump) *epoch_bump += 1u;  // peer exchange: this rank has consumed the step's buffers
     }
     // Laplacian backward rows (L^T yhat) for vertices and albedo; normal backward + edge hinge over incident faces
@@ -1930,7 +1968,10 @@ __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
 __global__ void ham_update_sh_kernel(fmhr_ham_config cfg, const float* __restrict__ gsh,
                                      const float* __restrict__ packed, float* __restrict__ sh_coeffs,
                                      float* __restrict__ adam_m, float* __restrict__ adam_v,
-                                     const float* __restrict__ adam_sc, float* __restrict__ dbg_grad_sh) {
+                                     const float* __restrict__ adam_sc, float* __restrict__ dbg_grad_sh,
+                                     const int32_t* __restrict__ adam_step) {
+    FMHR_TRACE_SCOPE(17);
+    if (adam_step[3] != 0) return;  // latched by ham_update_pass2_kernel (same stream, earlier): a peer never arrived
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cfg.n_sh_rows * 9) return;
     const float n_valid = packed[12 * (size_t)cfg.V];
@@ -1995,6 +2036,7 @@ static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers*
 // `img.astype(float32) / 255`, get_data.py:77-90), mask = u8 > 127 (get_data.py:78-79).  Four bytes per thread.
 __global__ void __launch_bounds__(256) ham_u8_to_f32_kernel(const uchar4* __restrict__ src, size_t n_img4, size_t n_all4,
                                                             float4* __restrict__ imgs, float4* __restrict__ masks) {
+    FMHR_TRACE_SCOPE(16);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_all4) return;
     const uchar4 b = src[i];
@@ -2356,6 +2398,7 @@ static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         pa.world = peers->world;
         pa.rank = peers->rank;
         pa.chunk = cdiv(V, peers->world);
+        pa.timeout_cycles = (long long)(peers->timeout_s > 0 ? peers->timeout_s : kPeerDefaultTimeoutS) * kPeerCyclesPerSecond;
         const bool two_shot = peers->mode == 2 || (peers->mode == 0 && peers->world > 2);
         if (two_shot) {
             // one-shot pulls world x 48 B per vertex into every rank; beyond two ranks the reduce-scatter form moves
@@ -2374,13 +2417,14 @@ static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     FMHR_LAUNCH_CHECK();
     ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
         *cfg, ws.vg, buf->delta, buf->albedo, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
-        packed, ws.ys, buf->adam_m, buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status, bump);
+        packed, ws.ys, buf->adam_m, buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status, bump,
+        buf->adam_step);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)
     if (cfg->phase == 0) {
         ham_update_sh_kernel<<<cdiv(cfg->n_sh_rows * 9, 128), 128, 0, st>>>(*cfg, ws.gsh, packed, buf->sh_coeffs,
                                                                             buf->adam_m, buf->adam_v, ws.adam_sc,
-                                                                            buf->dbg_grad_sh);
+                                                                            buf->dbg_grad_sh, buf->adam_step);
         FMHR_LAUNCH_CHECK();
     }
     return FMHR_OK;
@@ -2472,6 +2516,27 @@ extern "C" int fmhr_ham_stage_times(const fmhr_ham_config* cfg, const fmhr_ham_b
     }
     for (int i = 0; i <= kMaxStages; i++) cudaEventDestroy(tm.ev[i]);
     return rc;
+}
+
+// Diagnostic builds (-DFMHR_TRACE): first-entry / last-exit %globaltimer stamps (ns) of every kernel slot since the last
+// reset; the product build returns FMHR_EUNSUPPORTED.  Synchronises the device.
+extern "C" int fmhr_trace_read(unsigned long long* stamps_host, int n_slots, int reset) {
+#ifdef FMHR_TRACE
+    FMHR_CHECK_ARG(n_slots >= 0 && n_slots <= kTraceSlots && (stamps_host || n_slots == 0));
+    FMHR_CUDA(cudaDeviceSynchronize());
+    if (n_slots > 0)
+        FMHR_CUDA(cudaMemcpyFromSymbol(stamps_host, g_trace, (size_t)n_slots * 2 * sizeof(unsigned long long)));
+    if (reset) {
+        unsigned long long init[kTraceSlots][2];
+        for (int i = 0; i < kTraceSlots; i++) { init[i][0] = ~0ull; init[i][1] = 0ull; }
+        FMHR_CUDA(cudaMemcpyToSymbol(g_trace, init, sizeof(init)));
+    }
+    return FMHR_OK;
+#else
+    (void)stamps_host; (void)n_slots; (void)reset;
+    set_error("fmhr_trace_read: this build has no timeline tracing (compile with -DFMHR_TRACE)");
+    return FMHR_EUNSUPPORTED;
+#endif
 }
 
 extern "C" int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* pos, float* rast,

@@ -107,6 +107,7 @@ class PeerExchange:
         for s in (0, 1):
             st = HamPeers()
             st.rank, st.world, st.mode = self.rank, self.world, self.mode
+            st.timeout_s = int(os.environ.get("FMHR_PEER_TIMEOUT_S", "0"))  # 0 = the library's default (30 s)
             for r in range(self.world):
                 st.packed[r] = bases[r] + s * self.slot_bytes
                 st.reduced[r] = bases[r] + 2 * self.slot_bytes

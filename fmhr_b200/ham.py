@@ -72,6 +72,14 @@ class HamOptimizer:
                 raise RuntimeError("fmhr_b200: peer exchange requested but the ranks' buffers could not be mapped")
             self.peer = px if px.ok else None
         self.n_views_global_override = n_views_global
+        # The loss is a mean over the GLOBAL batch, so every rank must normalise by the same n_views_global.  The default
+        # (local batch x world) is only right when every rank holds the same number of views in every step: checked once
+        # here (collective); uneven shards (num_views % world != 0, short last batches) must pass n_views_global.
+        self._uneven_shards = False
+        if self.world > 1:
+            nums = [None] * self.world
+            torch.distributed.all_gather_object(nums, int(self.num), group=process_group)
+            self._uneven_shards = len(set(nums)) > 1
         self.dbg_grad = torch.zeros(self.V, 6, dtype=torch.float32, device=dev) if debug else None
         self.dbg_grad_sh = None
         self.debug = debug
@@ -146,16 +154,20 @@ class HamOptimizer:
         """mesh_sfs_optim.py:242-244: a fresh Adam over (delta, albedo, sh_coeffs) -> moments and steps restart."""
         self.adam_m.zero_()
         self.adam_v.zero_()
-        self.adam_step.zero_()
+        self.adam_step[:3].zero_()  # [3] is the latched fatal flag of the peer exchange (check_health)
         self.phase = 1
 
     # ------------------------------------------------------------------ plumbing
-    def _cfg(self, n_views, phase, albedo_weight):
+    def _cfg(self, n_views, phase, albedo_weight, n_views_global=None):
         c = self.conf
         cfg = HamConfig()
         cfg.V, cfg.T, cfg.H, cfg.W = self.V, self.T, self.H, self.W
         cfg.n_views = n_views
-        cfg.n_views_global = self.n_views_global_override or n_views * self.world
+        nvg = n_views_global or self.n_views_global_override
+        if nvg is None and self._uneven_shards:
+            raise RuntimeError("fmhr_b200: the ranks hold different numbers of views - pass n_views_global (the size of the "
+                               "global batch of the step) so that every rank normalises the mask loss identically")
+        cfg.n_views_global = int(nvg) if nvg else n_views * self.world
         cfg.phase = phase
         cfg.n_sh_rows = self.num
         cfg.zbuf_slot = 0
@@ -233,14 +245,14 @@ class HamOptimizer:
                 self._view_idx_cache[key] = t
         return t
 
-    def _step(self, phase, view_idx, albedo_weight=None):
+    def _step(self, phase, view_idx, albedo_weight=None, n_views_global=None):
         if self.use_graphs:
-            return self._step_graph(phase, view_idx, albedo_weight)
+            return self._step_graph(phase, view_idx, albedo_weight, n_views_global)
         vi = self._views(view_idx)
-        key = (phase, vi.data_ptr(), vi.numel(), albedo_weight)
+        key = (phase, vi.data_ptr(), vi.numel(), albedo_weight, n_views_global)
         cb = self._struct_cache.get(key)
         if cb is None or cb[2] != (self.workspace.data_ptr() if self.workspace is not None else 0):
-            cfg = self._cfg(vi.numel(), phase, albedo_weight)
+            cfg = self._cfg(vi.numel(), phase, albedo_weight, n_views_global)
             buf = self._buffers(cfg, vi)
             cb = (cfg, buf, self.workspace.data_ptr(), vi)
             if len(self._struct_cache) > 256:
@@ -271,17 +283,17 @@ class HamOptimizer:
             else:
                 check(self.lib.fmhr_ham_step_update(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_update")
 
-    def _step_graph(self, phase, view_idx, albedo_weight):
+    def _step_graph(self, phase, view_idx, albedo_weight, n_views_global=None):
         """CUDA-graph replay of the iteration: the launches + memsets of render/update are captured once per
         (phase, batch size, albedo_weight, z-buffer slot) and replayed with one launch; the step's view indices are
         copied into a persistent device buffer the captured kernels read.  With more than one rank the peer exchange is
         part of the captured update (still one launch per iteration); the NCCL variant runs its all-reduce eagerly between
         the two captured halves."""
         n = view_idx.numel() if torch.is_tensor(view_idx) else len(view_idx)
-        key = (phase, n, None if albedo_weight is None else float(albedo_weight))
+        key = (phase, n, None if albedo_weight is None else float(albedo_weight), n_views_global)
         ent = self._graphs.get(key)
         if ent is None:
-            ent = self._capture(phase, n, albedo_weight, view_idx)
+            ent = self._capture(phase, n, albedo_weight, view_idx, n_views_global)
             self._graphs[key] = ent
         graphs, idx_buf, ws_ptr, cfgs, bufs = ent
         if self.workspace.data_ptr() != ws_ptr:
@@ -301,11 +313,11 @@ class HamOptimizer:
             graphs[slot][1].replay()
         return self.losses
 
-    def _capture(self, phase, n, albedo_weight, view_idx):
+    def _capture(self, phase, n, albedo_weight, view_idx, n_views_global=None):
         idx_buf = torch.zeros(n, dtype=torch.int32, device=self.device)
         cfgs, bufs = [], []
         for slot in (0, 1):
-            cfg = self._cfg(n, phase, albedo_weight)
+            cfg = self._cfg(n, phase, albedo_weight, n_views_global)
             cfg.zbuf_slot = slot
             cfgs.append(cfg)
             bufs.append(self._buffers(cfg, idx_buf))
@@ -341,17 +353,26 @@ class HamOptimizer:
         return graphs, idx_buf, ws_ptr, cfgs, bufs
 
     # ------------------------------------------------------------------ the two loops' bodies
-    def step_phase_a(self, view_idx):
+    def step_phase_a(self, view_idx, n_views_global=None):
         """One iteration of mesh_sfs_optim.py:198-237 (albedo + SH warm-up).  Returns the device loss record
         [sfs, 0, albedo(display), 0, 0, 0, n_valid, total]; no host sync."""
-        return self._step(0, view_idx)
+        return self._step(0, view_idx, None, n_views_global)
 
-    def step_phase_b(self, view_idx, albedo_weight=None):
+    def step_phase_b(self, view_idx, albedo_weight=None, n_views_global=None):
         """One iteration of mesh_sfs_optim.py:253-310.  Returns the device loss record
-        [sfs, lap, albedo, mask, edge, delta, n_valid, total]; no host sync."""
+        [sfs, lap, albedo, mask, edge, delta, n_valid, total]; no host sync.  n_views_global: size of the step's GLOBAL
+        batch when the ranks' shards are uneven (default: local batch x world)."""
         if self.phase != 1:
             self.begin_phase_b()
-        return self._step(1, view_idx, albedo_weight)
+        return self._step(1, view_idx, albedo_weight, n_views_global)
+
+    def check_health(self):
+        """Raises if the peer exchange gave up on a rank (fmhr_ham_step_update_peer latched adam_step[3]): the update of
+        that step and of every later one was refused on this rank - parameters are intact, but the replicas are no longer
+        in step, so the job must stop.  Host sync; call it wherever the loss record is read."""
+        if int(self.adam_step[3].item()) != 0:
+            raise RuntimeError("fmhr_b200: a peer did not reach the gradient exchange within the timeout "
+                               "(FMHR_PEER_TIMEOUT_S); this rank refused the update - parameters are untouched, abort the job")
 
     STAGES = ("clears", "vertex_normals", "clip_transform", "coverage", "shade", "antialias_loss", "pixel_backward",
               "update_adam")

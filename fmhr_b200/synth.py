@@ -287,3 +287,92 @@ def build_scene(workload, render_fn, n_views=None, view_offset=0, view_stride=1,
     conf = dict(CONF[wl["conf"]])
     return dict(vertices=verts, faces=faces, w2cs=w2cs, projs=projs, imgs=img, masks=cov, valid_masks=valid_mask,
                 albedo=alb0, sh_coeffs=sh0, H=H, W=W, conf=conf, n_total=n_all, workload=wl)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0]: the reference's demo capture (demo_data/1) through the loader convention
+# ------------------------------------------------------------------------------------------------
+def demo_cameras(world_mats, scale_mats, cap_res=(1280, 1024)):
+    """The camera convention of get_demo_data (get_data.py:62-76,96-97) without OpenCV: P = world_mat @ scale_mat is
+    split into K [R | t] (RQ decomposition, what cv2.decomposeProjectionMatrix does inside load_K_Rt_from_P,
+    models/utils.py:29-47), K is normalised by K[2,2], w2c = inverse of the camera-to-world pose, and the projection is
+    rewritten to the reference's clip convention (x, y scaled to NDC at the capture resolution, z_clip = -0.1,
+    w_clip = z_cam).  Returns (w2cs[n,4,4], projs[n,4,4]) float32, TRANSPOSED for row-vector use."""
+    w2cs, projs = [], []
+    for Wm, Sm in zip(np.asarray(world_mats, dtype=np.float32), np.asarray(scale_mats, dtype=np.float32)):
+        P = (Wm @ Sm)[:3].astype(np.float64)
+        M = P[:, :3]
+        # RQ decomposition M = K R with K upper triangular, positive diagonal
+        flip = np.flipud(np.eye(3))
+        q, r = np.linalg.qr((flip @ M).T)
+        K = flip @ r.T @ flip
+        R = flip @ q.T
+        sgn = np.diag(np.sign(np.diag(K)))
+        K, R = K @ sgn, sgn @ R
+        if np.linalg.det(R) < 0:
+            R = -R
+            K = -K  # cancels in K / K[2,2] below except for the overall sign of P, which is projective
+        c = -np.linalg.solve(M, P[:, 3])  # camera centre: P [c, 1]^T = 0
+        K = K / K[2, 2]
+        pose = np.eye(4, dtype=np.float32)
+        pose[:3, :3] = R.T
+        pose[:3, 3] = c
+        w2c = np.linalg.inv(pose)
+        proj = np.eye(4)
+        proj[:3, :3] = K
+        proj[0, 0] = proj[0, 0] / (cap_res[0] / 2.)
+        proj[0, 2] = proj[0, 2] / (cap_res[0] / 2.) - 1.
+        proj[1, 1] = proj[1, 1] / (cap_res[1] / 2.)
+        proj[1, 2] = proj[1, 2] / (cap_res[1] / 2.) - 1.
+        proj[2, 2] = 0.
+        proj[2, 3] = -0.1
+        proj[3, 2] = 1.
+        proj[3, 3] = 0.
+        w2cs.append(w2c.astype(np.float32).T)
+        projs.append(proj.astype(np.float32).T)
+    return (np.ascontiguousarray(np.stack(w2cs), dtype=np.float32),
+            np.ascontiguousarray(np.stack(projs), dtype=np.float32))
+
+
+def fit_hand_to_keypoints(kp, subdiv=3, seed=0, noise=2e-4):
+    """The synthetic right-hand mesh posed on 21 triangulated keypoints (MediaPipe order: 0 wrist, 5 / 9 / 17 index /
+    middle / little knuckle, 12 middle finger tip): wrist -> middle finger tip is the long axis, the knuckle line gives
+    the palm plane.  Stands in for the demo's MANO fit, which is not shipped."""
+    kp = np.asarray(kp, dtype=np.float64)
+    v, f = base_hand_mesh()
+    v, f = subdivide_loop(v, f, subdiv)
+    wrist, tip = kp[0], kp[12]
+    ay = tip - wrist
+    length = np.linalg.norm(ay)
+    ay = ay / length
+    ax = kp[5] - kp[17]
+    ax = ax - ay * float(ax @ ay)
+    ax = ax / np.linalg.norm(ax)
+    az = np.cross(ax, ay)
+    s = length / 0.4  # the base mesh spans y in [-0.2, 0.2]
+    local = v + np.array([0.0, 0.2, 0.0])
+    world = wrist[None] + s * (local[:, 0:1] * ax[None] + local[:, 1:2] * ay[None] + local[:, 2:3] * az[None])
+    rng = np.random.default_rng(seed)
+    world = world + rng.normal(0.0, noise, world.shape)
+    return world.astype(np.float32), f.astype(np.int32)
+
+
+def demo_scene(fixture, hand="right", subdiv=3):
+    """Config 1 on the real demo capture: `fixture` = tests/golden/demo1_320x256.npz (or the dict loaded from it; made
+    by the committed fixture generator from the reference's demo_data/1).  Images / masks / gray images as the loader
+    returns them (uint8 / 255, BGR, zero outside the mask; mask = byte > 127), cameras in the loader's transposed
+    clip convention, the synthetic hand posed on the capture's 3-D keypoints, conf/demo_sfs.conf weights.
+    valid_masks, sh_coeffs and albedo are the job of the HAM initialisation (mesh_sfs_optim.py:124-177); placeholders
+    (segmentation mask, zero lighting, grey albedo) are returned so the dict has the usual keys."""
+    fx = np.load(fixture) if isinstance(fixture, str) else fixture
+    kp = np.asarray(fx["keypoints_3d"])
+    verts, faces = fit_hand_to_keypoints(kp[21:42] if hand == "right" else kp[0:21], subdiv)
+    imgs = fx["imgs_u8"].astype(np.float32) / np.float32(255.0)
+    gray = fx["gray_u8"].astype(np.float32) / np.float32(255.0)
+    masks = (fx["masks_u8"] > 127).astype(np.float32)
+    n, H, W = masks.shape
+    w2cs, projs = demo_cameras(fx["world_mats"], fx["scale_mats"], tuple(int(x) for x in fx["cap_res"]))
+    return dict(vertices=verts, faces=faces, w2cs=w2cs, projs=projs, imgs=imgs, grayimgs=gray, masks=masks,
+                valid_masks=masks.copy(), albedo=np.full((verts.shape[0], 3), 0.5, dtype=np.float32),
+                sh_coeffs=np.zeros((n, 9), dtype=np.float32), H=H, W=W, conf=dict(CONF["demo_sfs"]), n_total=n,
+                workload=dict(n=n, H=H, W=W, subdiv=subdiv, hands=1, conf="demo_sfs"))

@@ -181,7 +181,7 @@ typedef struct fmhr_ham_buffers {
     float* sh_coeffs;          /* [n_sh_rows,9] */
     float* adam_m;             /* [6V + 9*n_sh_rows]  (delta | albedo | sh) */
     float* adam_v;             /* same layout */
-    int32_t* adam_step;        /* [3] step counters (delta, albedo, sh) */
+    int32_t* adam_step;        /* [4] step counters (delta, albedo, sh) + [3] latched fatal flag (fmhr_ham_step_update_peer) */
     /* per-view data of all views resident on this rank */
     const float* imgs;         /* [num,H,W,3] */
     const float* masks;        /* [num,H,W] */
@@ -239,13 +239,15 @@ int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf
  *  - reduced[r] = rank r's sum buffer (one per rank is enough: a peer can only store into it again after this rank
  *    has posted the next step);
  *  - epoch     = one zero-initialised uint32 in local device memory (steps completed; advanced by the call);
- *  - every rank makes the same sequence of calls.  A peer that does not arrive within ~3 s sets losses[7] = NaN
- *    instead of hanging the device. */
+ *  - every rank makes the same sequence of calls.  A peer that does not arrive within timeout_s does not hang the
+ *    device: the update is REFUSED (delta / albedo / sh_coeffs, Adam moments and step counters stay untouched), the
+ *    whole loss record becomes NaN and adam_step[3] is latched to 1 so that every later update refuses as well - the
+ *    host must treat adam_step[3] != 0 as fatal (HamOptimizer.check_health raises). */
 #define FMHR_MAX_PEERS 16
 typedef struct fmhr_ham_peers {
     int32_t rank, world;
     int32_t mode;              /* 0 = by world size, 1 = one-shot gather, 2 = two-shot (reduce-scatter + peer stores) */
-    int32_t reserved;
+    int32_t timeout_s;         /* rendezvous give-up time in seconds (0 = default, 30 s) */
     const float* packed[FMHR_MAX_PEERS];
     uint32_t* flags[FMHR_MAX_PEERS];
     float* reduced[FMHR_MAX_PEERS]; /* every rank's [fmhr_ham_packed_floats] sum buffer (in its shared allocation) */
@@ -267,6 +269,10 @@ int fmhr_ham_debug_export(const fmhr_ham_config* cfg, const fmhr_ham_buffers* bu
  * 5 antialias + losses, 6 pixel backward, 7 update/Adam.  Synchronises the stream; advances the optimiser one step. */
 int fmhr_ham_stage_times(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, float* ms_host, int* n_stages_host,
                          fmhr_stream_t stream);
+/* Diagnostic builds only (-DFMHR_TRACE, tools/trace_timeline.py): per-kernel (first block entry, last warp exit)
+ * %globaltimer stamps in ns since the last reset, stamps_host[2 * slot + {0,1}]; slot numbering in csrc/ham.cu.
+ * Synchronises the device.  The product build returns FMHR_EUNSUPPORTED. */
+int fmhr_trace_read(unsigned long long* stamps_host, int n_slots, int reset);
 /* Host-buffer variant (end-to-end measurement path): copies this step's view batch (img/mask/valid_mask/w2c/proj
  * rows, all HOST pinned pointers, n_views rows each) into the device staging planes named by `buf`, runs
  * render+update, and copies the 8-float loss record back to losses_host. */

@@ -219,3 +219,25 @@ def test_mask_boxes_contain_every_set_pixel():
             s = m[v] > 127
             assert s[y0].any() and s[y1 - 1].any() and s[:, x0].any() and s[:, x1 - 1].any()
     assert torch.equal(HostStreamingStepper.mask_boxes(torch.from_numpy(m)), boxes)
+
+
+def test_demo_camera_convention_matches_the_reference_loader():
+    """synth.demo_cameras (RQ decomposition + clip fix-up, get_data.py:62-76,96-97) against the matrices the reference's
+    own load_K_Rt_from_P produced for the 16 demo cameras (fixture made by oracle/gen_demo_fixture.py)."""
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demo1_320x256.npz"))
+    w2cs, projs = synth.demo_cameras(fx["world_mats"], fx["scale_mats"], tuple(int(x) for x in fx["cap_res"]))
+    assert w2cs.shape == (16, 4, 4) and w2cs.dtype == np.float32
+    assert np.abs(w2cs - fx["w2cs"]).max() < 1e-5 and np.abs(projs - fx["projs"]).max() < 1e-5
+    assert np.all(projs[:, 3, 2] == -0.1) and np.all(projs[:, 2, 3] == 1.0)  # z_clip = -0.1, w_clip = z_cam
+    scene = synth.demo_scene(fx)
+    assert scene["vertices"].shape == (49281, 3) and scene["faces"].shape == (98432, 3)
+    # the posed hand is in front of every camera and lands on the segmentation
+    vh = np.concatenate([scene["vertices"], np.ones((49281, 1), np.float32)], 1)
+    inside = []
+    for i in range(16):
+        clip = vh @ scene["w2cs"][i] @ scene["projs"][i]
+        assert clip[:, 3].min() > 0.5
+        px = ((clip[:, 0] / clip[:, 3] + 1) * 0.5 * scene["W"]).astype(int).clip(0, scene["W"] - 1)
+        py = ((clip[:, 1] / clip[:, 3] + 1) * 0.5 * scene["H"]).astype(int).clip(0, scene["H"] - 1)
+        inside.append(float(scene["masks"][i][py, px].mean()))
+    assert np.mean(inside) > 0.2 and min(inside) > 0.0  # (some cameras see the hand mostly outside their frame)

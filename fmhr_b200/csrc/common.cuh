@@ -97,7 +97,7 @@ __device__ __forceinline__ bool snap_vertex(const float4 p, float hw, float hh, 
 
 // ------------------------------------------------------------------------------------------------
 // Timeline tracing (diagnostic builds only, -DFMHR_TRACE; tools/trace_timeline.py): every kernel of the fused iteration
-// records the %globaltimer of its first block entry (atomicMin) and of its last warp exit (atomicMax) into slot `id`, so
+// records the %globaltimer of its first block entry (atomicMin) and of its last block exit (atomicMax) into slot `id`, so
 // the real schedule of a CUDA-graph replay - overlaps, fill / tail bubbles between kernels - can be read back.  The
 // product build compiles the scope to nothing.
 // ------------------------------------------------------------------------------------------------
@@ -115,7 +115,7 @@ struct TraceScope {
         if (threadIdx.x == 0) atomicMin(&g_trace[id][0], trace_now());
     }
     __device__ __forceinline__ ~TraceScope() {
-        if ((threadIdx.x & 31) == 0) atomicMax(&g_trace[id][1], trace_now());
+        if (threadIdx.x == 0) atomicMax(&g_trace[id][1], trace_now());  // (thread 0's exit stands for the block's)
     }
 };
 __device__ __forceinline__ void trace_stamp_min(int id, int k) { atomicMin(&g_trace[id][k], trace_now()); }

@@ -22,6 +22,9 @@
 #ifndef FMHR_LB_SHADE
 #define FMHR_LB_SHADE 3
 #endif
+#ifndef FMHR_LB_SHADE_BWD
+#define FMHR_LB_SHADE_BWD 2  // shade pass with the speculative backward fused in (phase B training step)
+#endif
 #ifndef FMHR_LB_AA
 #define FMHR_LB_AA 4
 #endif
@@ -51,7 +54,9 @@ struct HamWs {
     int* ccount;               // inside common_region (zeroed every step)
     int* rcount;
     int* pcount;
-    int* status;               // bit 0: pair list overflow, bit 1: ring list overflow
+    uint2* qlist;              // [P/4] phase B: pixels whose antialiased L1 sign differs from the shade pass' speculation
+    int* qcount;               //        (pixel, packed sign deltas), back-propagated by the pair kernel
+    int* status;               // bit 0: pair / correction list overflow, bit 1: ring list overflow, bit 2: a peer never arrived
     // Tile work lists (16x16 tiles).  slot[s]: tiles of z-buffer slot s that received fragments (bitmap for
     // de-duplication + compact list + count, filled by the coverage kernel).  The scan pass walks the list of the slot
     // rasterised this step (idle tiles cost nothing) and resets the tiles of the other slot.
@@ -103,6 +108,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take((P / 32 + 64) * 4); if (ws) ws->ringbits = (uint32_t*)p;
     p = take((P / 2 + 64) * 16); if (ws) ws->plist_a = (uint4*)p;
     p = take((P / 2 + 64) * 4); if (ws) ws->plist_b = (uint32_t*)p;
+    p = take((P / 4 + 64) * 8); if (ws) ws->qlist = (uint2*)p;
     const size_t tiles_pv = (size_t)((c->W + 15) / 16) * ((c->H + 15) / 16);
     const size_t words = (size_t)c->n_views * ((tiles_pv + 31) / 32);
     const size_t slot_bytes = 256 + align256(words * 4);
@@ -117,7 +123,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
         ws->common_region = p; ws->common_bytes = common_bytes; ws->slot_bytes = slot_bytes;
         ws->acc = (double*)p;
         int* cnt = (int*)(p + 8 * 32 * sizeof(double));
-        ws->ccount = cnt; ws->rcount = cnt + 1; ws->pcount = cnt + 2; ws->status = cnt + 3;
+        ws->ccount = cnt; ws->rcount = cnt + 1; ws->pcount = cnt + 2; ws->status = cnt + 3; ws->qcount = cnt + 4;
     }
     p = take(V * 32); if (ws) ws->vg = (float4*)p;
     p = take(V * 32); if (ws) ws->vattr = (float4*)p;
@@ -779,24 +785,36 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
                 cbuf[wib][off + __popc(m[k] & lt)] = make_uint2(pix, (uint32_t)key[k] & kTriMask);
             }
             off += __popc(m[k]);
-            if (!any_ring) continue;  // interior unit: no empty pixel touches a covered one
-            // empty 4-neighbours of a covered pixel: the ring antialiasing can blend into (bitmap de-duplicates)
+        }
+        if (any_ring) {  // boundary unit: empty 4-neighbours of covered pixels = the ring antialiasing can blend into
+            // the bitmap de-duplicates; all (up to 16) atomics of a lane are issued before the first result is consumed
+            // (one after the other they were 16 dependent L2 round trips per unit)
+            unsigned fresh = 0u;
 #pragma unroll
-            for (int d = 0; d < 4; d++) {
-                bool fresh = false;
-                uint32_t q = 0u;
-                if ((emask >> (4 * k + d)) & 1u) {
-                    const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py + (d == 2 ? 1 : (d == 3 ? -1 : 0));
-                    q = (uint32_t)(((size_t)tc.n * H + qy) * W + qx);
+            for (int j = 0; j < 16; j++) {
+                if ((emask >> j) & 1u) {
+                    const int k = j >> 2, d = j & 3;
+                    const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py0 + 2 * k + (d == 2 ? 1 : (d == 3 ? -1 : 0));
+                    const uint32_t q = (uint32_t)(((size_t)tc.n * H + qy) * W + qx);
                     const uint32_t bit = 1u << (q & 31);
-                    fresh = !(atomicOr(ringbits + (q >> 5), bit) & bit);
+                    if (!(atomicOr(ringbits + (q >> 5), bit) & bit)) fresh |= 1u << j;
                 }
-                const unsigned mr = __ballot_sync(0xffffffffu, fresh);
-                if (mr) {
-                    if (fresh) rbuf[wib][nring + __popc(mr & lt)] = q;
-                    nring += __popc(mr);
-                    __syncwarp();
-                    if (nring > kRBuf - 32) flush_ring();
+            }
+            if (__any_sync(0xffffffffu, fresh != 0u)) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const bool f = (fresh >> j) & 1u;
+                    const unsigned mr = __ballot_sync(0xffffffffu, f);
+                    if (mr) {
+                        if (f) {
+                            const int k = j >> 2, d = j & 3;
+                            const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py0 + 2 * k + (d == 2 ? 1 : (d == 3 ? -1 : 0));
+                            rbuf[wib][nring + __popc(mr & lt)] = (uint32_t)(((size_t)tc.n * H + qy) * W + qx);
+                        }
+                        nring += __popc(mr);
+                        __syncwarp();
+                        if (nring > kRBuf - 32) flush_ring();
+                    }
                 }
             }
         }
@@ -825,7 +843,21 @@ __global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long*
 // flag (one 32-bit RED), and records the valid flag in the list entry for the backward pass.
 // ------------------------------------------------------------------------------------------------
 template <int PHASE>
-__global__ void __launch_bounds__(256, FMHR_LB_SHADE) ham_shade_kernel(uint2* __restrict__ clist, const int* __restrict__ ccount,
+__device__ __forceinline__ void pixel_backward_q(const PixTri& q, int px, int py, float4 gin, const float* __restrict__ M,
+                                                 const float* __restrict__ c, int V, int H, int W, float4* __restrict__ G);
+
+// BWD (phase B training step): the pixel's own loss gradient is known right here for every pixel that does not RECEIVE an
+// antialias blend - tmp_img == pred_img there, so d|tmp - img| = sign(pred - img) - and those are > 95 % of the pixels.
+// The pass therefore speculates sign(pred - img) for every valid pixel, back-propagates it immediately while the
+// triangle record, barycentrics and shading terms are still in registers (no second gather of the record, no pixel
+// backward pass), and leaves the three signs in the colour plane's w channel; the antialias pass compares them with the
+// signs of the antialiased image and queues the few pixels that differ for a linear correction (pair kernel).
+__device__ __forceinline__ float sgnf(float d) { return (float)((d > 0.f) - (d < 0.f)); }
+__device__ __forceinline__ uint32_t pack_signs(float s0, float s1, float s2) {  // 2 bits per channel + a marker bit
+    return (uint32_t)((int)s0 + 1) | ((uint32_t)((int)s1 + 1) << 2) | ((uint32_t)((int)s2 + 1) << 4) | 0x40u;
+}
+template <int PHASE, bool BWD = false>
+__global__ void __launch_bounds__(256, BWD ? FMHR_LB_SHADE_BWD : FMHR_LB_SHADE) ham_shade_kernel(uint2* __restrict__ clist, const int* __restrict__ ccount,
                                                         unsigned long long* __restrict__ zbuf,
                                                         const float4* __restrict__ vg, const float* __restrict__ viewM,
                                                         float invW, float invH, const float4* __restrict__ trirec,
@@ -834,7 +866,8 @@ __global__ void __launch_bounds__(256, FMHR_LB_SHADE) ham_shade_kernel(uint2* __
                                                         const int32_t* __restrict__ view_idx,
                                                         const int32_t* __restrict__ sh_idx, int V, int H, int W,
                                                         float4* __restrict__ plane0, float4* __restrict__ plane1,
-                                                        double* __restrict__ acc) {
+                                                        double* __restrict__ acc, const float* __restrict__ imgs,
+                                                        float4* __restrict__ G) {
     FMHR_TRACE_SCOPE(6);
     const int nc = *ccount;
     const int hw = H * W;
@@ -874,7 +907,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_SHADE) ham_shade_kernel(uint2* __
         if (valid) nvalid += 1.0f;
         const uint32_t tag = ((uint32_t)g.bits << 28) | (valid ? 0x80000000u : 0u);
         if (tag) atomicOr(reinterpret_cast<unsigned int*>(zbuf + pix), tag);  // low word of the little-endian key
-        clist[e].y = ent.y | (valid ? 0x80000000u : 0u);
+        if (!BWD) clist[e].y = ent.y | (valid ? 0x80000000u : 0u);  // (the separate backward pass reads the flag)
         if (PHASE == 1) {
             float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
@@ -882,6 +915,12 @@ __global__ void __launch_bounds__(256, FMHR_LB_SHADE) ham_shade_kernel(uint2* __
                 const float inv = 1.0f / fmaxf(sqrtf(m.x * m.x + m.y * m.y + m.z * m.z), 1e-12f);
                 const float r = sh_radiance(sh, m.x * inv, m.y * inv, m.z * inv);
                 col = make_float4(r * a.x, r * a.y, r * a.z, 1.0f);
+                if (BWD) {
+                    const float* img = imgs + ((size_t)view * hw + pa.rem) * 3;
+                    const float s0 = sgnf(col.x - __ldg(img)), s1 = sgnf(col.y - __ldg(img + 1)), s2 = sgnf(col.z - __ldg(img + 2));
+                    col.w = __uint_as_float(pack_signs(s0, s1, s2));
+                    pixel_backward_q<1>(q, px, py, make_float4(s0, s1, s2, 0.f), Mv, sh, V, H, W, G);
+                }
             }
             plane0[pix] = col;
         } else {
@@ -913,7 +952,10 @@ __device__ __forceinline__ bool pair_needs_analysis(const NbrKeys& k0, const Nbr
     return (from1 ? k1.bits : k0.bits) != 0;
 }
 
-template <int PHASE>
+// SPEC (phase B training step): the shade pass already back-propagated sign(pred - img) of every valid pixel (packed in
+// plane0.w); this pass only queues the pixels whose antialiased sign differs (qlist) and writes the pixel-gradient plane
+// for the pixels that received a blend (the only entries the pair kernel reads).
+template <int PHASE, bool SPEC = false>
 __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     const uint2* __restrict__ clist, const int* __restrict__ ccount, const uint32_t* __restrict__ rlist,
     const int* __restrict__ rcount, int rcap, uint32_t* __restrict__ ringbits, const unsigned long long* __restrict__ zbuf,
@@ -924,7 +966,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     float4* __restrict__ gplane0, float4* __restrict__ gplane1, double* __restrict__ acc, float* __restrict__ gsh,
     float* __restrict__ dbg_image, float* __restrict__ dbg_mask, uint4* __restrict__ plist_a,
     uint32_t* __restrict__ plist_b, int* __restrict__ pcount, int pcap, int* __restrict__ status,
-    double* __restrict__ init_acc) {
+    double* __restrict__ init_acc, uint2* __restrict__ qlist, int* __restrict__ qcount, int qcap) {
     FMHR_TRACE_SCOPE(7);
     // PHASE 2 = HAM initialisation (mesh_sfs_optim.py:124-163): plane0 holds interpolated NORMALS, they and the coverage
     // are antialiased like phase B's colour + coverage; `imgs` is the gray image [num,H,W]; outputs: antialiased coverage
@@ -934,6 +976,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     __shared__ int q_n_s[8];
     __shared__ float blend_s[8][32][NC];
     __shared__ uint32_t spix_s[8][32];
+    __shared__ uint32_t recv_s[8];  // SPEC: bit L = lane L's pixel received a blend in this batch
     // recorded pairs wait in shared memory and reach plist with ONE global atomic per >= 32 records (a same-address
     // atomicAdd per pair serialised the kernel at the L2 slice)
     constexpr int kPBuf = 64;
@@ -976,7 +1019,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
         const size_t base = (size_t)n * hw;
         const unsigned long long* zb = zbuf + base;
         NbrKeys self = decode_key(ZB_EMPTY);
-        if (lane == 0) *q_n = 0;
+        if (lane == 0) { *q_n = 0; if (SPEC) recv_s[wib] = 0u; }
         spix[lane] = pix32;
         __syncwarp();
         if (active) {
@@ -1029,6 +1072,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                 if (!found) continue;
                 const bool recv_is_self = (which < 2) == (pr.alpha > 0.0f);
                 if (!recv_is_self) continue;  // the other pixel's own item delivers it
+                if (SPEC) atomicOr(&recv_s[wib], 1u << L);
                 // out[recv] += alpha * (color[second] - color[first]); empty pixels are zero in every channel
                 float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, s0 = f0, s1 = f0;
                 if (k0.tri >= 0) { f0 = plane0[qbase + r0]; if (PHASE == 0) f1 = plane1[qbase + r0]; }
@@ -1051,6 +1095,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
         for (int k = 0; k < 9; k++) gc[k] = 0.0f;
         float init_y = 0.0f;  // PHASE 2: gc = SH basis row of this valid pixel, init_y = its gray value
         bool init_valid = false;
+        uint32_t corr_pack = 0u;  // SPEC: sign deltas of this pixel against the shade pass' speculation (0 = none)
         if (active) {
             const size_t pix = pix32;
             const int view = __ldg(view_idx + n);
@@ -1089,13 +1134,26 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                     const float d0 = a0.x - __ldg(img), d1 = a0.y - __ldg(img + 1), d2 = a0.z - __ldg(img + 2);
                     abs_acc += fabsf(d0) + fabsf(d1) + fabsf(d2);
                     g.x = (d0 > 0.f) - (d0 < 0.f); g.y = (d1 > 0.f) - (d1 < 0.f); g.z = (d2 > 0.f) - (d2 < 0.f);
+                    if (SPEC) {
+                        // signs the shade pass speculated (and already back-propagated) vs the antialiased image's
+                        const uint32_t now = pack_signs(g.x, g.y, g.z), was = __float_as_uint(c0.w);
+                        if (now != was) {
+                            // per channel (now - was) in -2..2, stored + 2 in 3 bits
+                            corr_pack = 0x200u;
+#pragma unroll
+                            for (int ch = 0; ch < 3; ch++) {
+                                const int dlt = (int)((now >> (2 * ch)) & 3u) - (int)((was >> (2 * ch)) & 3u);
+                                corr_pack |= (uint32_t)(dlt + 2) << (3 * ch);
+                            }
+                        }
+                    }
                 }
                 // mesh_sfs_optim.py:295  mean((pred_mask - valid_mask)^2), as a correction to sum valid_mask^2
                 const float vm = __ldg(valid_masks + (size_t)view * hw + rem);
                 const float dm = amask - vm;
                 msk_acc += (double)dm * (double)dm - (double)vm * (double)vm;
                 g.w = dm;
-                gplane0[pix] = g;
+                if (!SPEC || (nq > 0 && ((recv_s[wib] >> lane) & 1u))) gplane0[pix] = g;
                 if (dbg_image) { dbg_image[pix * 3] = a0.x; dbg_image[pix * 3 + 1] = a0.y; dbg_image[pix * 3 + 2] = a0.z; }
                 if (dbg_mask) dbg_mask[pix] = amask;
             } else {
@@ -1121,6 +1179,20 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                 gplane0[pix] = g0;
                 gplane1[pix] = g1;
                 if (dbg_image) { dbg_image[pix * 3] = pred.x; dbg_image[pix * 3 + 1] = pred.y; dbg_image[pix * 3 + 2] = pred.z; }
+            }
+        }
+        if (SPEC) {
+            const unsigned mc = __ballot_sync(0xffffffffu, corr_pack != 0u);
+            if (mc) {  // rare (a few 10^3 pixels per iteration): one global atomic per warp batch that has any
+                const int leader = __ffs(mc) - 1;
+                int qb = 0;
+                if (lane == leader) qb = atomicAdd(qcount, __popc(mc));
+                qb = __shfl_sync(0xffffffffu, qb, leader);
+                if (corr_pack != 0u) {
+                    const int slot = qb + __popc(mc & lt);
+                    if (slot < qcap) qlist[slot] = make_uint2(pix32, corr_pack);
+                    else atomicOr(status, 1);
+                }
             }
         }
         if (PHASE == 2) {
@@ -1192,19 +1264,13 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
 // colour b,g,r; phase A: albedo): SH / normalise / interpolate / rasterize backward from the triangle record, two
 // red.global.add.v4.f32 per corner into the world-space vertex accumulators.  LINEAR in g, so the pass-through gradient
 // (pixel kernel) and the antialias pair terms (pair kernel) are back-propagated independently.
+// Core of the shading backward for a pixel whose triangle record `q` (clip positions, barycentrics, attributes) is
+// already in registers: the shade pass calls it right after the forward (phase B), pixel_backward() loads the record first.
 template <int PHASE>
-__device__ __forceinline__ void pixel_backward(uint32_t pix32, int tself, float4 gin, const float4* __restrict__ trirec,
-                                               float invW, float invH, const float* __restrict__ viewM,
-                                               const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx,
-                                               int V, int H, int W, float4* __restrict__ G) {
-    const PixAddr pa = pix_decode(pix32, H, W);
-    const int n = pa.n, px = pa.px, py = pa.py;
-    const float* M = viewM + (size_t)n * kViewM;
-    const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
+__device__ __forceinline__ void pixel_backward_q(const PixTri& q, int px, int py, float4 gin, const float* __restrict__ M,
+                                                 const float* __restrict__ c, int V, int H, int W,
+                                                 float4* __restrict__ G) {
     const float4 g0 = gin, g1 = gin;
-    if (gin.x == 0.0f && gin.y == 0.0f && gin.z == 0.0f) return;
-    PixTri q;
-    load_pixtri(tself, px, py, trirec, M, invW, invH, q);
     const float w = 1.0f - q.u - q.v;
     if (PHASE == 0) {
         // only the albedo attribute is trainable: interpolate bwd
@@ -1282,6 +1348,21 @@ __device__ __forceinline__ void pixel_backward(uint32_t pix32, int tself, float4
     }
 }
 
+template <int PHASE>
+__device__ __forceinline__ void pixel_backward(uint32_t pix32, int tself, float4 gin, const float4* __restrict__ trirec,
+                                               float invW, float invH, const float* __restrict__ viewM,
+                                               const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx,
+                                               int V, int H, int W, float4* __restrict__ G) {
+    if (gin.x == 0.0f && gin.y == 0.0f && gin.z == 0.0f) return;
+    const PixAddr pa = pix_decode(pix32, H, W);
+    const int n = pa.n, px = pa.px, py = pa.py;
+    const float* M = viewM + (size_t)n * kViewM;
+    const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
+    PixTri q;
+    load_pixtri(tself, px, py, trirec, M, invW, invH, q);
+    pixel_backward_q<PHASE>(q, px, py, gin, M, c, V, H, W, G);
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward, part 1: the blending pairs recorded by the antialias pass (a few 10^4 per iteration, one thread each).
 //   * colour / albedo gradient of the two pixels of the pair (-alpha g_recv, +alpha g_recv), back-propagated through each
@@ -1295,10 +1376,23 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
     const unsigned long long* __restrict__ zbuf, const float4* __restrict__ vg, const float* __restrict__ viewM, int V,
     int H, int W, const float4* __restrict__ plane0, const float4* __restrict__ gplane0,
     const float4* __restrict__ gplane1, const float4* __restrict__ trirec, float invW, float invH,
-    const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, float4* __restrict__ G) {
+    const float* __restrict__ sh_coeffs, const int32_t* __restrict__ sh_idx, float4* __restrict__ G,
+    const uint2* __restrict__ qlist, const int* __restrict__ qcount, int qcap) {
     FMHR_TRACE_SCOPE(8);
     const int np = min(*pcount, pcap);
     const int hw = H * W;
+    if (PHASE == 1 && qlist) {
+        // corrections of the shade pass' speculative backward: pixels whose antialiased L1 sign differs from sign(pred -
+        // img); the shading backward is linear in its input, so the difference of the two signs is propagated here
+        const int nq = min(*qcount, qcap);
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nq; e += gridDim.x * blockDim.x) {
+            const uint2 it = qlist[e];
+            const float4 dg = make_float4((float)((int)(it.y & 7u) - 2), (float)((int)((it.y >> 3) & 7u) - 2),
+                                          (float)((int)((it.y >> 6) & 7u) - 2), 0.f);
+            const NbrKeys k = decode_key(zbuf[it.x]);
+            pixel_backward<PHASE>(it.x, k.tri, dg, trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
+        }
+    }
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < np; e += gridDim.x * blockDim.x) {
         const uint4 a = plist_a[e];
         AAPair pr;
@@ -2239,15 +2333,27 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     static const int g_aa = persistent_blocks(ham_aa_loss_kernel<PHASE>);
     static const int g_bwd = persistent_blocks(ham_pixel_bwd_kernel<PHASE>);
     const int pblock = 256;  // 8 warps = 8 independent workers (no block barrier in the pixel passes)
-    const int rcap = (int)(P / 2), pcap = (int)(P / 2);
+    const int rcap = (int)(P / 2), pcap = (int)(P / 2), qcap = (int)(P / 4);
+    // phase-B training step: the shade pass back-propagates the speculated L1 signs itself (no pixel backward pass);
+    // FMHR_NO_SPEC=1 keeps the separate backward pass (A/B measurements, tests)
+    static const bool no_spec = [] { const char* e = getenv("FMHR_NO_SPEC"); return e && e[0] == '1'; }();
+    const bool spec = PHASE == 1 && !forward_only && !init && !no_spec;
     ham_scan_kernel<<<g_scan, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt], ws.tcount[nxt],
                                                tiles_x, tiles_y, H, W, ws.clist, ws.ccount, ws.ringbits, ws.rlist,
                                                ws.rcount, rcap, ws.status);
     FMHR_LAUNCH_CHECK();
     if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->records, 0));  // normals + triangle records are ready
-    ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH, ws.trirec,
-                                                      b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, H, W, ws.plane[0],
-                                                      ws.plane[1], ws.acc);
+    if (spec) {
+        static const int g_shade_bwd = persistent_blocks(ham_shade_kernel<1, true>);
+        ham_shade_kernel<1, true><<<g_shade_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH,
+                                                                  ws.trirec, b->masks, b->sh_coeffs, b->view_idx, sh_idx,
+                                                                  V, H, W, ws.plane[0], ws.plane[1], ws.acc, b->imgs,
+                                                                  (float4*)b->packed);
+    } else {
+        ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH,
+                                                          ws.trirec, b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, H, W,
+                                                          ws.plane[0], ws.plane[1], ws.acc, nullptr, nullptr);
+    }
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 4: scan + shade
     float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
@@ -2257,12 +2363,19 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         ham_aa_loss_kernel<2><<<g_init, pblock, 0, st>>>(
             ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp,
             init->grayimgs, b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1,
-            ws.acc, ws.gsh, dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, init->init_acc);
+            ws.acc, ws.gsh, dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, init->init_acc,
+            nullptr, nullptr, 0);
+    } else if (spec) {
+        static const int g_aa_spec = persistent_blocks(ham_aa_loss_kernel<1, true>);
+        ham_aa_loss_kernel<1, true><<<g_aa_spec, pblock, 0, st>>>(
+            ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp, b->imgs,
+            b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1, ws.acc, ws.gsh,
+            dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, nullptr, ws.qlist, ws.qcount, qcap);
     } else {
         ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(
             ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp, b->imgs,
             b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1, ws.acc, ws.gsh,
-            dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, nullptr);
+            dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, nullptr, nullptr, nullptr, 0);
     }
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 5: antialias + losses
@@ -2277,14 +2390,14 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     if (!forward_only) {
         ham_pair_bwd_kernel<PHASE><<<296, 128, 0, ps>>>(ws.plist_a, ws.plist_b, ws.pcount, pcap, zcur, ws.vg, ws.viewM, V, H,
                                                        W, ws.plane[0], g0, g1, ws.trirec, invW, invH, b->sh_coeffs, sh_idx,
-                                                       (float4*)b->packed);
+                                                       (float4*)b->packed, spec ? ws.qlist : nullptr, ws.qcount, qcap);
         FMHR_LAUNCH_CHECK();
     }
     ham_finalize_scalars_kernel<<<1, 32, 0, ps>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,
                                                   b->packed + 12 * (size_t)V);
     FMHR_LAUNCH_CHECK();
     if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
-    if (!forward_only) {
+    if (!forward_only && !spec) {
         ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, ws.trirec, invW, invH, ws.viewM,
                                                               b->sh_coeffs, sh_idx, V, H, W, g0, g1, (float4*)b->packed);
         FMHR_LAUNCH_CHECK();

@@ -13,12 +13,24 @@ from . import raster as dr
 from .refmath import get_normals, get_radiance, laplacian_smoothing
 
 
+# "spec": the forward VALUES of the clip positions follow the fixed evaluation order the GPU path and this checker
+# share (oracle.raster.clip_positions; DESIGN.md section 2, rule 0), while autograd still flows through the reference's
+# two einsums.  "einsum": the reference lines alone - ATen's summation order, 1 ulp away from the GPU's, which flips
+# isolated silhouette pixels (coverage is discontinuous in the positions) and is therefore only used to REPORT that effect.
+POSITIONS = "spec"
+
+
 def _clip_positions(vertices, w2c, proj):
     """mesh_sfs_optim.py:262-264."""
     n = w2c.shape[0]
     vertsw = torch.cat([vertices, torch.ones_like(vertices[:, 0:1])], axis=1).unsqueeze(0).expand(n, -1, -1)
     rot_verts = torch.einsum('ijk,ikl->ijl', vertsw, w2c)
     proj_verts = torch.einsum('ijk,ikl->ijl', rot_verts, proj)
+    if POSITIONS == "spec":
+        from . import raster as _oraster  # (tests may rebind `dr` to the CUDA shim: the position rule stays the checker's)
+        spec = _oraster.clip_positions(vertices.detach().cpu(), w2c.cpu(), proj.cpu()).to(proj_verts.device)
+        # a + (b - a) == b exactly for floats 1 ulp apart (b - a is exact, the sum is representable)
+        proj_verts = proj_verts + (spec - proj_verts.detach())
     return vertsw, proj_verts
 
 
@@ -192,7 +204,8 @@ def phase_a_step(st, view_idx, keep=None):
     opt.zero_grad()
     loss.backward()
     if keep is not None:
-        keep.update(grad_albedo=st.albedo.grad.detach().clone(), grad_sh=st.sh_coeffs.grad.detach().clone())
+        keep.update(grad_albedo=st.albedo.grad.detach().clone(), grad_sh=st.sh_coeffs.grad.detach().clone(),
+                    pred_img=pred_img.detach(), valid_idx=valid_idx)
     opt.step()
     return dict(sfs=float(sfs_loss), albedo=float(albedo_loss), n_valid=valid_idx[0].numel())
 

@@ -51,6 +51,16 @@ def rasterize_fwd(pos, tri, resolution, want_db=True, want_keys=False):
     return rast, db, keys
 
 
+def clip_positions(vertices, w2cs, projs):
+    """[n,V,4] clip positions in the fixed evaluation order the GPU path and the checker share (orc_clip_positions)."""
+    v, w, p = _f32(vertices), _f32(w2cs), _f32(projs)
+    n, V = w.shape[0], v.shape[0]
+    out = torch.empty(n, V, 4, dtype=torch.float32)
+    rc = lib().orc_clip_positions(_p(v), V, _p(w), _p(p), n, _p(out))
+    assert rc == 0
+    return out
+
+
 def rasterize_bwd(pos, tri, rast, dy):
     pos = _f32(pos)
     tri = tri.detach().to(torch.int32).contiguous()

@@ -449,4 +449,31 @@ int orc_antialias_bwd(const float* color, const float* rast, const float* pos, c
     return 0;
 }
 
+
+// Clip positions of the documented rule (rule 0): the reference evaluates
+//   rot = [v,1] @ w2c ;  clip = rot @ proj                                    (mesh_sfs_optim.py:262-264)
+// with two batched fp32 GEMMs whose summation order is unspecified (it differs between ATen's CPU and CUDA back ends).
+// Coverage is a discontinuous function of the positions, so the GPU path and this checker share ONE fixed evaluation
+// order: the per-view combined matrix M = w2c @ proj and clip = [v,1] @ M, each a chain of single-rounded fused
+// multiply-adds (fmaf is exact: -ffp-contract only concerns implicit contraction).  Agrees with the einsum to 3e-7 relative.
+int orc_clip_positions(const float* verts /*[V,3]*/, int V, const float* w2cs /*[n,4,4] transposed*/,
+                       const float* projs /*[n,4,4] transposed*/, int n, float* out /*[n,V,4]*/) {
+    for (int k = 0; k < n; k++) {
+        const float* Wm = w2cs + 16 * (size_t)k;
+        const float* Pm = projs + 16 * (size_t)k;
+        float M[16];
+        for (int r = 0; r < 4; r++)
+            for (int j = 0; j < 4; j++)
+                M[4 * r + j] = fmaf(Wm[4 * r + 3], Pm[12 + j], fmaf(Wm[4 * r + 2], Pm[8 + j],
+                                    fmaf(Wm[4 * r + 1], Pm[4 + j], Wm[4 * r] * Pm[j])));
+#pragma omp parallel for
+        for (int i = 0; i < V; i++) {
+            const float x = verts[3 * (size_t)i], y = verts[3 * (size_t)i + 1], z = verts[3 * (size_t)i + 2];
+            float* o = out + ((size_t)k * V + i) * 4;
+            for (int j = 0; j < 4; j++) o[j] = fmaf(z, M[8 + j], fmaf(y, M[4 + j], fmaf(x, M[j], M[12 + j])));
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

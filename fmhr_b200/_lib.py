@@ -22,7 +22,7 @@ class HamConfig(ctypes.Structure):
     """struct fmhr_ham_config"""
     _fields_ = [("V", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
                 ("n_views", ctypes.c_int32), ("n_views_global", ctypes.c_int32), ("phase", ctypes.c_int32),
-                ("n_sh_rows", ctypes.c_int32), ("zbuf_slot", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_sh_rows", ctypes.c_int32), ("zbuf_slot", ctypes.c_int32), ("view_groups", ctypes.c_int32),
                 ("sfs_weight", c_f), ("lap_weight", c_f), ("albedo_weight", c_f), ("mask_weight", c_f),
                 ("edge_weight", c_f), ("delta_weight", c_f),
                 ("lr", c_f), ("albedo_lr", c_f), ("sh_lr", c_f),

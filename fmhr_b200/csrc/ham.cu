@@ -28,6 +28,18 @@
 #ifndef FMHR_LB_AA
 #define FMHR_LB_AA 4
 #endif
+#ifndef FMHR_LB_SCAN
+#define FMHR_LB_SCAN 6  // a short latency chain per warp: more resident warps = fewer serial units per warp (4: 4,810, 6: 4,895, 8: 4,875 iters/s)
+#endif
+#ifndef FMHR_SIDE_PRIO
+#define FMHR_SIDE_PRIO 0  // high priority for the vertex side stream delays the head of the coverage kernel: 4,810 vs 5,047 iters/s
+#endif
+#ifndef FMHR_DEFAULT_VIEW_GROUPS
+#define FMHR_DEFAULT_VIEW_GROUPS 1
+#endif
+#ifndef FMHR_AA_HOIST
+#define FMHR_AA_HOIST 0
+#endif
 #ifndef FMHR_LB_BWD
 #define FMHR_LB_BWD 3
 #endif
@@ -71,6 +83,7 @@ struct HamWs {
     float4* vattr;             // [V,2]  vattr[2i] = (unit normal, degenerate flag), vattr[2i+1] = (albedo b,g,r, 0)
     float4* raw4;              // [V]    (un-normalised normal sum N, |N|)
     float4* ys;                // [V,2]  ys[2i] = (yhat_v / deg, deg), ys[2i+1] = (yhat_a / deg, 0): Laplacian backward rows
+    float4* greg;              // [V,2]  phase B: (d regularisers / d delta, 0), (d albedo Laplacian / d albedo, 0), weighted
     float4* trirec;            // [T,10] per-triangle record of the pixel passes (kTriRec floats), rebuilt every step
     float* gsh;                // [n_sh_rows,9] un-normalised SH gradients by SH row (phase A)
     double* acc;               // [8][32] (32-way spread against same-address atomics):
@@ -129,6 +142,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take(V * 32); if (ws) ws->vattr = (float4*)p;
     p = take(V * 16); if (ws) ws->raw4 = (float4*)p;
     p = take(V * 32); if (ws) ws->ys = (float4*)p;
+    p = take(V * 32); if (ws) ws->greg = (float4*)p;
     p = take((size_t)c->T * 160); if (ws) ws->trirec = (float4*)p;
     p = take((size_t)c->n_sh_rows * 9 * 4); if (ws) ws->gsh = (float*)p;
     p = take(8 * sizeof(float)); if (ws) ws->adam_sc = (float*)p;
@@ -680,7 +694,7 @@ __device__ __forceinline__ NbrKeys decode_key(unsigned long long key) {
 //     into; a self-cleaning bitmap de-duplicates);
 //   * resets the tiles the OTHER z-buffer slot dirtied in the previous iteration (no separate clear pass).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ham_scan_kernel(const unsigned long long* __restrict__ zbuf,
+__global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsigned long long* __restrict__ zbuf,
                                                        unsigned long long* __restrict__ zbuf_next,
                                                        const uint32_t* __restrict__ tlist, const int* __restrict__ tcount,
                                                        const uint32_t* __restrict__ tlist_next,
@@ -885,6 +899,13 @@ __global__ void __launch_bounds__(256, BWD ? FMHR_LB_SHADE_BWD : FMHR_LB_SHADE) 
         const float* Mv = viewM + (size_t)n * kViewM;
         const int view = __ldg(view_idx + n);
         const bool valid = __ldg(masks + (size_t)view * hw + pa.rem) > 0.0f;
+        // BWD: the target pixel is needed only after the whole shading chain - issue its loads now, beside the mask and the
+        // triangle record, instead of as one more dependent DRAM round trip at the end of the iteration
+        float tg0 = 0.f, tg1 = 0.f, tg2 = 0.f;
+        if (BWD) {
+            const float* img = imgs + ((size_t)view * hw + pa.rem) * 3;
+            tg0 = __ldg(img); tg1 = __ldg(img + 1); tg2 = __ldg(img + 2);
+        }
         PixTri q;
         load_pixtri(t, px, py, trirec, Mv, invW, invH, q);
         AAGeom g;
@@ -916,8 +937,7 @@ __global__ void __launch_bounds__(256, BWD ? FMHR_LB_SHADE_BWD : FMHR_LB_SHADE) 
                 const float r = sh_radiance(sh, m.x * inv, m.y * inv, m.z * inv);
                 col = make_float4(r * a.x, r * a.y, r * a.z, 1.0f);
                 if (BWD) {
-                    const float* img = imgs + ((size_t)view * hw + pa.rem) * 3;
-                    const float s0 = sgnf(col.x - __ldg(img)), s1 = sgnf(col.y - __ldg(img + 1)), s2 = sgnf(col.z - __ldg(img + 2));
+                    const float s0 = sgnf(col.x - tg0), s1 = sgnf(col.y - tg1), s2 = sgnf(col.z - tg2);
                     col.w = __uint_as_float(pack_signs(s0, s1, s2));
                     pixel_backward_q<1>(q, px, py, make_float4(s0, s1, s2, 0.f), Mv, sh, V, H, W, G);
                 }
@@ -1019,6 +1039,19 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
         const size_t base = (size_t)n * hw;
         const unsigned long long* zb = zbuf + base;
         NbrKeys self = decode_key(ZB_EMPTY);
+#if FMHR_AA_HOIST
+        // loads whose addresses only depend on the pixel (own colour, target, valid_mask) are issued before the key /
+        // pair-analysis chain instead of behind it
+        float4 h_c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float h_t0 = 0.f, h_t1 = 0.f, h_t2 = 0.f, h_vm = 0.f;
+        if (PHASE == 1 && active) {
+            const int hview = __ldg(view_idx + n);
+            h_c0 = plane0[pix32];
+            const float* himg = imgs + ((size_t)hview * hw + rem) * 3;
+            h_t0 = __ldg(himg); h_t1 = __ldg(himg + 1); h_t2 = __ldg(himg + 2);
+            h_vm = __ldg(valid_masks + (size_t)hview * hw + rem);
+        }
+#endif
         if (lane == 0) { *q_n = 0; if (SPEC) recv_s[wib] = 0u; }
         spix[lane] = pix32;
         __syncwarp();
@@ -1102,7 +1135,11 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
             // own (pre-antialias) values; empty pixels are zero in every channel
             float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (self.tri >= 0) {
+#if FMHR_AA_HOIST
+                c0 = PHASE == 1 ? h_c0 : plane0[pix];
+#else
                 c0 = plane0[pix];
+#endif
                 if (PHASE == 0) c1 = plane1[pix];
             }
             float4 a0 = c0, a1 = c1;  // antialiased values
@@ -1131,7 +1168,11 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
             } else if (PHASE == 1) {
                 float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {  // mesh_sfs_optim.py:289  l1 over tmp_img[valid_idx]
+#if FMHR_AA_HOIST
+                    const float d0 = a0.x - h_t0, d1 = a0.y - h_t1, d2 = a0.z - h_t2;
+#else
                     const float d0 = a0.x - __ldg(img), d1 = a0.y - __ldg(img + 1), d2 = a0.z - __ldg(img + 2);
+#endif
                     abs_acc += fabsf(d0) + fabsf(d1) + fabsf(d2);
                     g.x = (d0 > 0.f) - (d0 < 0.f); g.y = (d1 > 0.f) - (d1 < 0.f); g.z = (d2 > 0.f) - (d2 < 0.f);
                     if (SPEC) {
@@ -1149,7 +1190,11 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                     }
                 }
                 // mesh_sfs_optim.py:295  mean((pred_mask - valid_mask)^2), as a correction to sum valid_mask^2
+#if FMHR_AA_HOIST
+                const float vm = h_vm;
+#else
                 const float vm = __ldg(valid_masks + (size_t)view * hw + rem);
+#endif
                 const float dm = amask - vm;
                 msk_acc += (double)dm * (double)dm - (double)vm * (double)vm;
                 g.w = dm;
@@ -1393,13 +1438,16 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
             pixel_backward<PHASE>(it.x, k.tri, dg, trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
         }
     }
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < np; e += gridDim.x * blockDim.x) {
+    // three work items per pair - the shading chains of its two pixels and the silhouette position gradient are independent
+    // gather chains, so they go to three threads instead of one after the other in one
+    for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < 3 * np; wi += gridDim.x * blockDim.x) {
+        const int e = wi / 3, role = wi - 3 * e;
         const uint4 a = plist_a[e];
         AAPair pr;
         const size_t pix0 = a.x;
         const int d = (int)(a.y & 1u);
         pr.from1 = (int)((a.y >> 1) & 1u); pr.clamped = (int)((a.y >> 2) & 1u); pr.di = (int)((a.y >> 3) & 3u);
-        pr.alpha = __uint_as_float(a.z); pr.i1 = (int)a.w; pr.i2 = (int)plist_b[e]; pr.tri = 0;
+        pr.alpha = __uint_as_float(a.z); pr.i1 = (int)a.w; pr.tri = 0;
         const size_t pix1 = pix0 + (d ? W : 1);
         const int n = (int)(pix0 / hw);
         const int rem0 = (int)(pix0 - (size_t)n * hw), qy = rem0 / W, qx = rem0 - qy * W;
@@ -1410,12 +1458,19 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
         // out[recv] += alpha*(c_second - c_first): d/dc_first = -alpha*g, d/dc_second = +alpha*g; only pixels on the
         // main pass' list consume it (phase B: valid, phase A: covered)
         const bool t0 = PHASE == 1 ? k0.valid : k0.tri >= 0, t1 = PHASE == 1 ? k1.valid : k1.tri >= 0;
-        if (t0)
-            pixel_backward<PHASE>((uint32_t)pix0, k0.tri, make_float4(-pr.alpha * gr.x, -pr.alpha * gr.y, -pr.alpha * gr.z, 0.f),
-                                  trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
-        if (t1)
-            pixel_backward<PHASE>((uint32_t)pix1, k1.tri, make_float4(pr.alpha * gr.x, pr.alpha * gr.y, pr.alpha * gr.z, 0.f),
-                                  trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
+        if (role == 0) {
+            if (t0)
+                pixel_backward<PHASE>((uint32_t)pix0, k0.tri, make_float4(-pr.alpha * gr.x, -pr.alpha * gr.y, -pr.alpha * gr.z, 0.f),
+                                      trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
+            continue;
+        }
+        if (role == 1) {
+            if (t1)
+                pixel_backward<PHASE>((uint32_t)pix1, k1.tri, make_float4(pr.alpha * gr.x, pr.alpha * gr.y, pr.alpha * gr.z, 0.f),
+                                      trirec, invW, invH, viewM, sh_coeffs, sh_idx, V, H, W, G);
+            continue;
+        }
+        pr.i2 = (int)plist_b[e];
         if (PHASE == 1 && !pr.clamped) {
             float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = f0;
             if (k0.tri >= 0) f0 = plane0[pix0];
@@ -1729,6 +1784,56 @@ __global__ void __launch_bounds__(256, 6) ham_regulariser_kernel(
     }
 }
 
+// Regulariser backward (phase B): gradient of  lap_weight * Laplacian(vertices) + edge hinge + delta loss  w.r.t. delta and
+// of  albedo_weight * Laplacian(albedo)  w.r.t. albedo, fully weighted.  View-independent like the regulariser forward
+// whose rows `ys` it gathers, so it runs behind it on the side stream, under the coverage kernel, and the update kernel on
+// the critical path is left with the normal backward and Adam.
+__global__ void __launch_bounds__(256, 6) ham_reg_grad_kernel(
+    fmhr_ham_config cfg, const float4* __restrict__ vg, const float* __restrict__ delta,
+    const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
+    const int32_t* __restrict__ v2v_idx, const float4* __restrict__ ys, float4* __restrict__ greg) {
+    FMHR_TRACE_SCOPE(18);
+    const int V = cfg.V;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / kLPV, sub = threadIdx.x & (kLPV - 1);
+    float3 lv = make_float3(0.f, 0.f, 0.f), la = lv, ge = lv;
+    if (i < V) {
+        const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
+        for (int q = b + sub; q < e; q += kLPV) {
+            const F8 y = ld256(ys + 2 * (size_t)__ldg(v2v_idx + q));
+            la.x += y.b.x; la.y += y.b.y; la.z += y.b.z;
+            lv.x += y.a.x; lv.y += y.a.y; lv.z += y.a.z;
+        }
+        const float4 v4 = vg[2 * (size_t)i];
+        const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
+        for (int j = fb + sub; j < fe; j += kLPV) {
+            const int2 nb = __ldg(v2f_nbr + j);
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                const float4 o = vg[2 * (size_t)(s2 == 0 ? nb.x : nb.y)];
+                const float dx = v4.x - o.x, dy = v4.y - o.y, dz = v4.z - o.z;
+                const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
+                if (x >= 0.0f && x <= 1.0f) { ge.x += 2.0f * dx; ge.y += 2.0f * dy; ge.z += 2.0f * dz; }
+            }
+        }
+    }
+    la.x = sub_sum(la.x); la.y = sub_sum(la.y); la.z = sub_sum(la.z);
+    lv.x = sub_sum(lv.x); lv.y = sub_sum(lv.y); lv.z = sub_sum(lv.z);
+    ge.x = sub_sum(ge.x); ge.y = sub_sum(ge.y); ge.z = sub_sum(ge.z);
+    if (i >= V || sub != 0) return;
+    const float iv = 1.0f / (float)V;
+    const F8 yself = ld256(ys + 2 * (size_t)i);
+    const float deg = yself.a.w;  // yhat_i = (yhat_i / deg_i) * deg_i
+    const float s_edge = cfg.edge_weight / (3.0f * (float)cfg.T);
+    const float s_delta = 2.0f * cfg.delta_weight / (float)V;
+    const float* dp = delta + 3 * (size_t)i;
+    const float3 lapv = make_float3((lv.x - yself.a.x * deg) * iv, (lv.y - yself.a.y * deg) * iv, (lv.z - yself.a.z * deg) * iv);
+    const float3 lapa = make_float3((la.x - yself.b.x * deg) * iv, (la.y - yself.b.y * deg) * iv, (la.z - yself.b.z * deg) * iv);
+    greg[2 * (size_t)i] = make_float4(cfg.lap_weight * lapv.x + s_edge * ge.x + s_delta * dp[0],
+                                      cfg.lap_weight * lapv.y + s_edge * ge.y + s_delta * dp[1],
+                                      cfg.lap_weight * lapv.z + s_edge * ge.z + s_delta * dp[2], 0.f);
+    greg[2 * (size_t)i + 1] = make_float4(cfg.albedo_weight * lapa.x, cfg.albedo_weight * lapa.y, cfg.albedo_weight * lapa.z, 0.f);
+}
+
 // Normal backward, step 1: gradient through the per-vertex normalisation (un-normalised photometric scale; linear, scaled
 // in the Adam pass), from the (all-reduced) tangential accumulators.  One thread per vertex.
 __global__ void __launch_bounds__(256) ham_normal_grad_kernel(int V, float4* __restrict__ vg,
@@ -1956,7 +2061,7 @@ __device__ __forceinline__ float pick3(const float3 v, int c) { return c == 0 ? 
 __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
     fmhr_ham_config cfg, const float4* __restrict__ vg, float* __restrict__ delta, float* __restrict__ albedo,
     const int32_t* __restrict__ v2f_ptr, const int2* __restrict__ v2f_nbr, const int32_t* __restrict__ v2v_ptr,
-    const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed, const float4* __restrict__ ys,
+    const int32_t* __restrict__ v2v_idx, const float* __restrict__ packed, const float4* __restrict__ greg,
     float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ adam_sc,
     const double* __restrict__ acc, float* __restrict__ losses, float* __restrict__ dbg_grad,
     const int* __restrict__ status, uint32_t* __restrict__ epoch_bump, int32_t* __restrict__ adam_step) {
@@ -1994,60 +2099,33 @@ __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
         if (status && (*status & 3)) losses[7] = __int_as_float(0x7fc00000);
         if (epoch_bump) *epoch_bump += 1u;  // peer exchange: this rank has consumed the step's buffers
     }
-    // Laplacian backward rows (L^T yhat) for vertices and albedo; normal backward + edge hinge over incident faces
-    float3 lv = make_float3(0.f, 0.f, 0.f), la = lv, gnb = lv, ge = lv;
-    if (i < V) {
-        const int b = __ldg(v2v_ptr + i), e = __ldg(v2v_ptr + i + 1);
-        for (int q = b + sub; q < e; q += kLPV) {
-            const F8 y = ldg256(ys + 2 * (size_t)__ldg(v2v_idx + q));
-            la.x += y.b.x; la.y += y.b.y; la.z += y.b.z;
-            lv.x += y.a.x; lv.y += y.a.y; lv.z += y.a.z;
-        }
-        if (cfg.phase == 1) {
-            const F8 self = ldg256(vg + 2 * (size_t)i);
-            const float3 vi = make_float3(self.a.x, self.a.y, self.a.z), gi = make_float3(self.b.x, self.b.y, self.b.z);
-            const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
-            for (int j = fb + sub; j < fe; j += kLPV) {
-                const int2 nb = __ldg(v2f_nbr + j);
-                const F8 A = ldg256(vg + 2 * (size_t)nb.x), B = ldg256(vg + 2 * (size_t)nb.y);
-                const float3 Gs = make_float3(gi.x + A.b.x + B.b.x, gi.y + A.b.y + B.b.y, gi.z + A.b.z + B.b.z);
-                const float3 ed = make_float3(A.a.x - B.a.x, A.a.y - B.a.y, A.a.z - B.a.z);
-                gnb.x += ed.y * Gs.z - ed.z * Gs.y; gnb.y += ed.z * Gs.x - ed.x * Gs.z; gnb.z += ed.x * Gs.y - ed.y * Gs.x;
-                const float4 o[2] = {A.a, B.a};
-#pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    const float dx = vi.x - o[s].x, dy = vi.y - o[s].y, dz = vi.z - o[s].z;
-                    const float x = dx * dx + dy * dy + dz * dz - cfg.edge_length_mean;
-                    if (x >= 0.0f && x <= 1.0f) { ge.x += 2.0f * dx; ge.y += 2.0f * dy; ge.z += 2.0f * dz; }
-                }
-            }
+    // normal backward over the incident faces (the regulariser gradients were summed by ham_reg_grad_kernel)
+    float3 gnb = make_float3(0.f, 0.f, 0.f);
+    if (i < V && cfg.phase == 1) {
+        const F8 self = ldg256(vg + 2 * (size_t)i);
+        const float3 gi = make_float3(self.b.x, self.b.y, self.b.z);
+        const int fb = __ldg(v2f_ptr + i), fe = __ldg(v2f_ptr + i + 1);
+        for (int j = fb + sub; j < fe; j += kLPV) {
+            const int2 nb = __ldg(v2f_nbr + j);
+            const F8 A = ldg256(vg + 2 * (size_t)nb.x), B = ldg256(vg + 2 * (size_t)nb.y);
+            const float3 Gs = make_float3(gi.x + A.b.x + B.b.x, gi.y + A.b.y + B.b.y, gi.z + A.b.z + B.b.z);
+            const float3 ed = make_float3(A.a.x - B.a.x, A.a.y - B.a.y, A.a.z - B.a.z);
+            gnb.x += ed.y * Gs.z - ed.z * Gs.y; gnb.y += ed.z * Gs.x - ed.x * Gs.z; gnb.z += ed.x * Gs.y - ed.y * Gs.x;
         }
     }
     // butterfly sums: every lane of the vertex's group ends up with the totals
-    la.x = sub_sum(la.x); la.y = sub_sum(la.y); la.z = sub_sum(la.z);
-    if (cfg.phase == 1) {
-        lv.x = sub_sum(lv.x); lv.y = sub_sum(lv.y); lv.z = sub_sum(lv.z);
-        gnb.x = sub_sum(gnb.x); gnb.y = sub_sum(gnb.y); gnb.z = sub_sum(gnb.z);
-        ge.x = sub_sum(ge.x); ge.y = sub_sum(ge.y); ge.z = sub_sum(ge.z);
-    }
+    if (cfg.phase == 1) { gnb.x = sub_sum(gnb.x); gnb.y = sub_sum(gnb.y); gnb.z = sub_sum(gnb.z); }
     if (i >= V || sub >= 3) return;
     // lane c of the vertex's group owns component c of delta and of albedo
     const int c = sub;
-    const float iv = 1.0f / (float)V;
-    const F8 yself = ldg256(ys + 2 * (size_t)i);
-    const float deg = yself.a.w;  // yhat_i = (yhat_i / deg_i) * deg_i
     const size_t k = 3 * (size_t)i + c;
     // albedo gradient (phase A: photometric only, mesh_sfs_optim.py:233; phase B adds the albedo Laplacian)
     float ga = s_photo * packed[8 * (size_t)i + 5 + c];
-    if (cfg.phase == 1)
-        ga += cfg.albedo_weight * ((pick3(la, c) - pick3(make_float3(yself.b.x, yself.b.y, yself.b.z), c) * deg) * iv);
     float gd = 0.0f;
     if (cfg.phase == 1) {
-        const float s_edge = cfg.edge_weight / (3.0f * (float)cfg.T);
-        const float s_delta = 2.0f * cfg.delta_weight / (float)V;
-        const float lap = (pick3(lv, c) - pick3(make_float3(yself.a.x, yself.a.y, yself.a.z), c) * deg) * iv;
-        gd = s_photo * (packed[8 * (size_t)i + c] + pick3(gnb, c)) + s_mask * packed[8 * (size_t)V + 4 * (size_t)i + c] +
-             cfg.lap_weight * lap + s_edge * pick3(ge, c) + s_delta * delta[k];
+        const float* gr = reinterpret_cast<const float*>(greg + 2 * (size_t)i);
+        ga += gr[4 + c];
+        gd = s_photo * (packed[8 * (size_t)i + c] + pick3(gnb, c)) + s_mask * packed[8 * (size_t)V + 4 * (size_t)i + c] + gr[c];
     }
     if (dbg_grad) { dbg_grad[6 * (size_t)i + c] = gd; dbg_grad[6 * (size_t)i + 3 + c] = ga; }
     if (cfg.phase == 1)
@@ -2093,6 +2171,7 @@ static int check_cfg(const fmhr_ham_config* c) {
     FMHR_CHECK_ARG(c->phase == 0 || c->phase == 1);
     FMHR_CHECK_ARG(c->n_sh_rows >= 1);
     FMHR_CHECK_ARG(c->zbuf_slot == 0 || c->zbuf_slot == 1);
+    FMHR_CHECK_ARG(c->view_groups >= 0 && c->view_groups <= 4);
     FMHR_CHECK_ARG(c->T < (1 << 28));  // triangle id shares the key's low word with 4 tag bits
     FMHR_CHECK_ARG(c->n_views < 4096 && c->W <= 16384 && c->H <= 16384);  // work-list entry = view:12 | ty:10 | tx:10
     FMHR_CHECK_ARG((long long)c->H * c->W < (1ll << 31));
@@ -2181,7 +2260,9 @@ struct BoxGraph {
     cudaGraphExec_t exec = nullptr;
 };
 struct SideStream {
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;                // vertex-domain kernels beside the coverage kernel (high priority)
+    cudaStream_t pix = nullptr;               // pixel passes of the view groups (high priority)
+    cudaEvent_t cov_done[4] = {nullptr, nullptr, nullptr, nullptr}, pix_join = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, records = nullptr;
     cudaStream_t copy = nullptr;              // host-batch uploads of fmhr_ham_step_host_u8
     cudaEvent_t copy_fork = nullptr, ready = nullptr;
@@ -2209,7 +2290,14 @@ static int side_stream(SideStream** out) {
     FMHR_CHECK_ARG(dev >= 0 && dev < 64);
     SideStream& s = side[dev];
     if (s.dev != dev) {
-        FMHR_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        // small latency-bound kernels must not queue behind the thousands of blocks of a coverage kernel: their streams
+        // get the highest priority, so the block scheduler serves them first whenever an SM slot frees up
+        int prio_lo = 0, prio_hi = 0;
+        FMHR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        FMHR_CUDA(cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, FMHR_SIDE_PRIO ? prio_hi : prio_lo));
+        FMHR_CUDA(cudaStreamCreateWithPriority(&s.pix, cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < 4; i++) FMHR_CUDA(cudaEventCreateWithFlags(&s.cov_done[i], cudaEventDisableTiming));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.pix_join, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.records, cudaEventDisableTiming));
@@ -2232,6 +2320,105 @@ struct InitArgs {
     double* init_acc;       // [(num + 1) * 56]
 };
 
+// View groups (phase-B training step): the batch's views are split into G consecutive groups, each with its own work lists,
+// and the issue-bound coverage kernel of group g + 1 runs on the caller's stream WHILE the latency-bound pixel passes of
+// group g (scan / shade + backward / antialias / pair) run on a high-priority stream - the block scheduler hands the SM
+// slots that coverage blocks free up to the pixel kernels first, so the two kinds of work share every SM instead of
+// taking turns.  Everything per group is pointer arithmetic on the one workspace (pixel indices are group-local).
+constexpr int kMaxGroups = 4;
+struct GroupView {
+    int v0, nv;
+    size_t p0, Pg;
+    unsigned long long *zcur, *znext;
+    float4* plane[4];
+    const float* viewM;
+    const int32_t *view_idx, *sh_idx;
+    uint2* clist; uint32_t* rlist; uint32_t* ringbits; uint4* plist_a; uint32_t* plist_b; uint2* qlist;
+    int *ccount, *rcount, *pcount, *qcount;
+    int* tcount[2]; uint32_t* tbits[2]; uint32_t* tlist[2];
+    int rcap, pcap, qcap;
+};
+static GroupView group_view(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b, const HamWs& ws, int g, int G) {
+    GroupView v;
+    const int n = cfg->n_views, per = cdiv(n, G);
+    const size_t hw = (size_t)cfg->H * cfg->W;
+    v.v0 = min(g * per, n);
+    v.nv = min(per, n - v.v0);
+    v.p0 = (size_t)v.v0 * hw;
+    v.Pg = (size_t)v.nv * hw;
+    v.zcur = ws.zbuf[cfg->zbuf_slot] + v.p0;
+    v.znext = ws.zbuf[cfg->zbuf_slot ^ 1] + v.p0;
+    for (int i = 0; i < 4; i++) v.plane[i] = ws.plane[i] ? ws.plane[i] + v.p0 : nullptr;
+    v.viewM = ws.viewM + (size_t)v.v0 * kViewM;
+    v.view_idx = b->view_idx + v.v0;
+    v.sh_idx = (b->sh_idx ? b->sh_idx : b->view_idx) + v.v0;
+    v.clist = ws.clist + v.p0;
+    v.rlist = ws.rlist + v.p0 / 2;
+    v.ringbits = ws.ringbits + v.p0 / 32 + g;
+    v.plist_a = ws.plist_a + v.p0 / 2;
+    v.plist_b = ws.plist_b + v.p0 / 2;
+    v.qlist = ws.qlist + v.p0 / 4;
+    int* cnt = ws.ccount + 8 * g;  // group 0: the historical slots (ccount, rcount, pcount, status, qcount)
+    v.ccount = cnt; v.rcount = cnt + 1; v.pcount = cnt + 2; v.qcount = cnt + 4;
+    const size_t tiles_pv = (size_t)cdiv(cfg->W, kTile) * cdiv(cfg->H, kTile), words_pv = (tiles_pv + 31) / 32;
+    for (int s2 = 0; s2 < 2; s2++) {
+        v.tcount[s2] = ws.tcount[s2] + g;
+        v.tbits[s2] = ws.tbits[s2] + (size_t)v.v0 * words_pv;
+        v.tlist[s2] = ws.tlist[s2] + (size_t)v.v0 * tiles_pv;
+    }
+    v.rcap = (int)(v.Pg / 2); v.pcap = (int)(v.Pg / 2); v.qcap = (int)(v.Pg / 4);
+    return v;
+}
+
+static int launch_coverage(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b, const HamWs& ws, const GroupView& gv,
+                           cudaStream_t st) {
+    const int H = cfg->H, W = cfg->W, cur = cfg->zbuf_slot;
+    const int tiles_x = cdiv(W, kTile), tiles_pv = tiles_x * cdiv(H, kTile);
+    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+    const size_t smem = (size_t)b->ml_max_verts * 24 + (size_t)((tiles_pv + 31) / 32) * sizeof(unsigned int);
+    if (smem > 96 * 1024) {
+        set_error("fmhr_ham_step_render: %d tiles per view exceed the coverage kernel's shared-memory bitmaps", tiles_pv);
+        return FMHR_EUNSUPPORTED;
+    }
+    const dim3 grid(b->n_meshlets, gv.nv);
+    const uint2* tri2 = (const uint2*)b->ml_tri2;
+    // more than four frame pixels per triangle (configs 1, 3, 5): triangles span several pixels, use the draining variant
+    const bool drain = (long long)H * W > 4ll * cfg->T;
+#define FMHR_COVERAGE(TPT)                                                                                             \
+    do {                                                                                                               \
+        static bool attr_set = false;                                                                                  \
+        if (!attr_set) {                                                                                               \
+            FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT>,                                           \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));                  \
+            FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT, false, true>,                              \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));                  \
+            attr_set = true;                                                                                           \
+        }                                                                                                              \
+        if (drain)                                                                                                     \
+            ham_coverage_meshlet_kernel<TPT, false, true><<<grid, kCovThreads, smem, st>>>(                            \
+                ws.vg, gv.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, gv.zcur,            \
+                gv.tbits[cur], gv.tlist[cur], gv.tcount[cur], tiles_x, tiles_pv, 0);                                   \
+        else                                                                                                           \
+            ham_coverage_meshlet_kernel<TPT><<<grid, kCovThreads, smem, st>>>(                                         \
+                ws.vg, gv.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, gv.zcur,            \
+                gv.tbits[cur], gv.tlist[cur], gv.tcount[cur], tiles_x, tiles_pv, 0);                                   \
+    } while (0)
+    if (b->ml_tris == 1024) FMHR_COVERAGE(1024 / kCovThreads);
+    else if (b->ml_tris == 512) FMHR_COVERAGE(512 / kCovThreads);
+    else FMHR_COVERAGE(256 / kCovThreads);
+#undef FMHR_COVERAGE
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
+static int view_groups_for(const fmhr_ham_config* cfg) {
+    static const int env = [] { const char* e = getenv("FMHR_VIEW_GROUPS"); return e ? atoi(e) : 0; }();
+    int G = cfg->view_groups > 0 ? cfg->view_groups : (env > 0 ? env : FMHR_DEFAULT_VIEW_GROUPS);
+    G = max(1, min(G, kMaxGroups));
+    while (G > 1 && cfg->n_views < 2 * G) G--;  // groups of at least two views
+    return G;
+}
+
 template <int PHASE>
 static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b, cudaStream_t st, float* dbg_image,
                            float* dbg_mask, bool forward_only, const InitArgs* init = nullptr) {
@@ -2239,12 +2426,13 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     ham_layout(cfg, (char*)b->workspace, &ws);
     const int V = cfg->V, T = cfg->T, H = cfg->H, W = cfg->W, n = cfg->n_views;
     const size_t P = (size_t)n * H * W;
-    unsigned long long* zcur = ws.zbuf[cfg->zbuf_slot];
-    unsigned long long* znext = ws.zbuf[cfg->zbuf_slot ^ 1];
     const int cur = cfg->zbuf_slot, nxt = cfg->zbuf_slot ^ 1;
     const int tiles_x = cdiv(W, kTile), tiles_y = cdiv(H, kTile);
     const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;  // IEEE single divides, identical to the device's __fdiv_rn
-    const int32_t* sh_idx = b->sh_idx ? b->sh_idx : b->view_idx;
+    // phase-B training step: the shade pass back-propagates the speculated L1 signs itself (no pixel backward pass);
+    // FMHR_NO_SPEC=1 keeps the separate backward pass (A/B measurements, tests)
+    static const bool no_spec = [] { const char* e = getenv("FMHR_NO_SPEC"); return e && e[0] == '1'; }();
+    const bool spec = PHASE == 1 && !forward_only && !init && !no_spec;
     FMHR_STAGE_MARK();  // 0: (no clear pass any more)
     // zeroed by the prep kernel: packed, loss accumulators + dilated work list (common), the work list of the slot
     // rasterised this step, SH gradients (phase A)
@@ -2255,9 +2443,9 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->w2cs, b->projs, b->view_idx, n, ws.viewM);
     FMHR_LAUNCH_CHECK();
     // The coverage + scan kernels only need the vertices and the view matrices (prep).  Normals -> per-triangle records
-    // (needed from the shade pass on) and the regulariser forward + Adam scalars (needed by the update) run on a side
-    // stream concurrently with them: latency-bound vertex kernels under the issue-bound coverage kernel.  Inline when the
-    // stages are being timed; the regulariser is skipped by the forward-only inspection path (it advances the counters).
+    // (needed from the shade pass on) and the regulariser forward / backward + Adam scalars (needed by the update) run on a
+    // side stream concurrently with them: latency-bound vertex kernels under the issue-bound coverage kernel.  Inline when
+    // the stages are being timed; the regulariser is skipped by the forward-only inspection path (it advances the counters).
     SideStream* side = nullptr;
     cudaStream_t vs = st;
     if (!g_timer) {
@@ -2266,6 +2454,17 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         FMHR_CUDA(cudaEventRecord(side->fork, st));
         FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
         vs = side->st;
+    }
+    const int G = (spec && side) ? view_groups_for(cfg) : 1;
+    GroupView gv[kMaxGroups];
+    for (int g = 0; g < G; g++) gv[g] = group_view(cfg, b, ws, g, G);
+    // coverage first in issue order: it is the head of the critical path (the vertex kernels below wait for SM slots anyway)
+    if (!g_timer) {
+        for (int g = 0; g < G; g++) {
+            int rc_ = launch_coverage(cfg, b, ws, gv[g], st);
+            if (rc_) return rc_;
+            if (G > 1) FMHR_CUDA(cudaEventRecord(side->cov_done[g], st));
+        }
     }
     ham_normals_kernel<<<cdiv((long long)V * 4, 256), 256, 0, vs>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
                                                                     ws.vattr, ws.raw4);
@@ -2278,54 +2477,33 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
             *cfg, ws.vg, b->delta, ws.vattr, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.acc,
             b->adam_step, ws.adam_sc);
         FMHR_LAUNCH_CHECK();
+        if (PHASE == 1) {
+            ham_reg_grad_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, vs>>>(
+                *cfg, ws.vg, b->delta, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.greg);
+            FMHR_LAUNCH_CHECK();
+        }
     }
     if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
     FMHR_STAGE_MARK();  // 2: (the clip transform is fused into the coverage kernel)
-    {
-        const int tiles_pv = tiles_x * tiles_y;
-        const size_t smem = (size_t)b->ml_max_verts * 24 + (size_t)((tiles_pv + 31) / 32) * sizeof(unsigned int);
-        if (smem > 96 * 1024) {
-            set_error("fmhr_ham_step_render: %d tiles per view exceed the coverage kernel's shared-memory bitmaps", tiles_pv);
-            return FMHR_EUNSUPPORTED;
-        }
-        const dim3 grid(b->n_meshlets, n);
-        const uint2* tri2 = (const uint2*)b->ml_tri2;
-        // more than four frame pixels per triangle (configs 1, 3, 5): triangles span several pixels, use the draining variant
-        const bool drain = (long long)H * W > 4ll * T;
-#define FMHR_COVERAGE(TPT)                                                                                             \
-        do {                                                                                                           \
-            static bool attr_set = false;                                                                              \
-            if (!attr_set) {                                                                                           \
-                FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT>,                                       \
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));              \
-                FMHR_CUDA(cudaFuncSetAttribute(ham_coverage_meshlet_kernel<TPT, false, true>,                          \
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));              \
-                attr_set = true;                                                                                       \
-            }                                                                                                          \
-            if (drain)                                                                                                 \
-                ham_coverage_meshlet_kernel<TPT, false, true><<<grid, kCovThreads, smem, st>>>(                        \
-                    ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,           \
-                    ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv, 0);                               \
-            else                                                                                                       \
-                ham_coverage_meshlet_kernel<TPT><<<grid, kCovThreads, smem, st>>>(                                     \
-                    ws.vg, ws.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, zcur,           \
-                    ws.tbits[cur], ws.tlist[cur], ws.tcount[cur], tiles_x, tiles_pv, 0);                               \
-        } while (0)
-        if (b->ml_tris == 1024) FMHR_COVERAGE(1024 / kCovThreads);
-        else if (b->ml_tris == 512) FMHR_COVERAGE(512 / kCovThreads);
-        else FMHR_COVERAGE(256 / kCovThreads);
-#undef FMHR_COVERAGE
-        FMHR_LAUNCH_CHECK();
+    if (g_timer) {
+        int rc_ = launch_coverage(cfg, b, ws, gv[0], st);
+        if (rc_) return rc_;
     }
     FMHR_STAGE_MARK();  // 3: coverage (transform + visibility)
+    // the pixel passes: on the caller's stream, or (view groups) on the high-priority pixel stream behind each group's coverage
+    cudaStream_t px = st;
+    if (G > 1) {
+        px = side->pix;
+        FMHR_CUDA(cudaStreamWaitEvent(px, side->cov_done[0], 0));
+    }
     if (g_pending.staging) {  // host batch of fmhr_ham_step_host_u8: first use of images / masks is the shade pass
-        if (g_pending.ready) FMHR_CUDA(cudaStreamWaitEvent(st, g_pending.ready, 0));
+        if (g_pending.ready) FMHR_CUDA(cudaStreamWaitEvent(px, g_pending.ready, 0));
         const size_t n_img4 = P * 3 / 4, n_all4 = n_img4 + P / 4;
-        ham_u8_to_f32_kernel<<<cdiv((long long)n_all4, 256), 256, 0, st>>>((const uchar4*)g_pending.staging, n_img4, n_all4,
+        ham_u8_to_f32_kernel<<<cdiv((long long)n_all4, 256), 256, 0, px>>>((const uchar4*)g_pending.staging, n_img4, n_all4,
                                                                           (float4*)b->imgs, (float4*)b->masks);
         FMHR_LAUNCH_CHECK();
-        if (g_pending.consumed) FMHR_CUDA(cudaEventRecord(g_pending.consumed, st));
+        if (g_pending.consumed) FMHR_CUDA(cudaEventRecord(g_pending.consumed, px));
         g_pending.staging = nullptr;
     }
     static const int g_scan = persistent_blocks(ham_scan_kernel);
@@ -2333,74 +2511,84 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     static const int g_aa = persistent_blocks(ham_aa_loss_kernel<PHASE>);
     static const int g_bwd = persistent_blocks(ham_pixel_bwd_kernel<PHASE>);
     const int pblock = 256;  // 8 warps = 8 independent workers (no block barrier in the pixel passes)
-    const int rcap = (int)(P / 2), pcap = (int)(P / 2), qcap = (int)(P / 4);
-    // phase-B training step: the shade pass back-propagates the speculated L1 signs itself (no pixel backward pass);
-    // FMHR_NO_SPEC=1 keeps the separate backward pass (A/B measurements, tests)
-    static const bool no_spec = [] { const char* e = getenv("FMHR_NO_SPEC"); return e && e[0] == '1'; }();
-    const bool spec = PHASE == 1 && !forward_only && !init && !no_spec;
-    ham_scan_kernel<<<g_scan, pblock, 0, st>>>(zcur, znext, ws.tlist[cur], ws.tcount[cur], ws.tlist[nxt], ws.tcount[nxt],
-                                               tiles_x, tiles_y, H, W, ws.clist, ws.ccount, ws.ringbits, ws.rlist,
-                                               ws.rcount, rcap, ws.status);
-    FMHR_LAUNCH_CHECK();
-    if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->records, 0));  // normals + triangle records are ready
-    if (spec) {
-        static const int g_shade_bwd = persistent_blocks(ham_shade_kernel<1, true>);
-        ham_shade_kernel<1, true><<<g_shade_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH,
-                                                                  ws.trirec, b->masks, b->sh_coeffs, b->view_idx, sh_idx,
-                                                                  V, H, W, ws.plane[0], ws.plane[1], ws.acc, b->imgs,
-                                                                  (float4*)b->packed);
-    } else {
-        ham_shade_kernel<PHASE><<<g_shade, pblock, 0, st>>>(ws.clist, ws.ccount, zcur, ws.vg, ws.viewM, invW, invH,
-                                                          ws.trirec, b->masks, b->sh_coeffs, b->view_idx, sh_idx, V, H, W,
-                                                          ws.plane[0], ws.plane[1], ws.acc, nullptr, nullptr);
-    }
-    FMHR_LAUNCH_CHECK();
-    FMHR_STAGE_MARK();  // 4: scan + shade
-    float4* g0 = PHASE == 0 ? ws.plane[2] : ws.plane[1];
-    float4* g1 = PHASE == 0 ? ws.plane[3] : nullptr;
-    if (init) {  // initialisation mode: normals + coverage antialiased, SH normal equations accumulated
-        static const int g_init = persistent_blocks(ham_aa_loss_kernel<2>);
-        ham_aa_loss_kernel<2><<<g_init, pblock, 0, st>>>(
-            ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp,
-            init->grayimgs, b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1,
-            ws.acc, ws.gsh, dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, init->init_acc,
-            nullptr, nullptr, 0);
-    } else if (spec) {
-        static const int g_aa_spec = persistent_blocks(ham_aa_loss_kernel<1, true>);
-        ham_aa_loss_kernel<1, true><<<g_aa_spec, pblock, 0, st>>>(
-            ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp, b->imgs,
-            b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1, ws.acc, ws.gsh,
-            dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, nullptr, ws.qlist, ws.qcount, qcap);
-    } else {
-        ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, st>>>(
-            ws.clist, ws.ccount, ws.rlist, ws.rcount, rcap, ws.ringbits, zcur, ws.vg, ws.viewM, b->tri, b->opp, b->imgs,
-            b->valid_masks, b->sh_coeffs, b->view_idx, sh_idx, V, T, H, W, ws.plane[0], ws.plane[1], g0, g1, ws.acc, ws.gsh,
-            dbg_image, dbg_mask, ws.plist_a, ws.plist_b, ws.pcount, pcap, ws.status, nullptr, nullptr, nullptr, 0);
-    }
-    FMHR_LAUNCH_CHECK();
-    FMHR_STAGE_MARK();  // 5: antialias + losses
-    // After the antialias pass three independent kernels remain: the pair backward and the loss-scalar finalize go to the
-    // side stream, the pixel backward stays on the caller's stream (all three only ADD into `packed`).
-    cudaStream_t ps = st;
-    if (side) {
-        FMHR_CUDA(cudaEventRecord(side->fork, st));
-        FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
-        ps = side->st;
-    }
-    if (!forward_only) {
-        ham_pair_bwd_kernel<PHASE><<<296, 128, 0, ps>>>(ws.plist_a, ws.plist_b, ws.pcount, pcap, zcur, ws.vg, ws.viewM, V, H,
-                                                       W, ws.plane[0], g0, g1, ws.trirec, invW, invH, b->sh_coeffs, sh_idx,
-                                                       (float4*)b->packed, spec ? ws.qlist : nullptr, ws.qcount, qcap);
+    for (int g = 0; g < G; g++) {
+        const GroupView& v = gv[g];
+        float* dimg = dbg_image ? dbg_image + v.p0 * 3 : nullptr;
+        float* dmsk = dbg_mask ? dbg_mask + v.p0 : nullptr;
+        if (G > 1 && g > 0) FMHR_CUDA(cudaStreamWaitEvent(px, side->cov_done[g], 0));
+        ham_scan_kernel<<<g_scan, pblock, 0, px>>>(v.zcur, v.znext, v.tlist[cur], v.tcount[cur], v.tlist[nxt], v.tcount[nxt],
+                                                   tiles_x, tiles_y, H, W, v.clist, v.ccount, v.ringbits, v.rlist, v.rcount,
+                                                   v.rcap, ws.status);
         FMHR_LAUNCH_CHECK();
-    }
-    ham_finalize_scalars_kernel<<<1, 32, 0, ps>>>(ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE,
-                                                  b->packed + 12 * (size_t)V);
-    FMHR_LAUNCH_CHECK();
-    if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
-    if (!forward_only && !spec) {
-        ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, st>>>(ws.clist, ws.ccount, ws.trirec, invW, invH, ws.viewM,
-                                                              b->sh_coeffs, sh_idx, V, H, W, g0, g1, (float4*)b->packed);
+        if (side && g == 0) FMHR_CUDA(cudaStreamWaitEvent(px, side->records, 0));  // normals + triangle records are ready
+        if (spec) {
+            static const int g_shade_bwd = persistent_blocks(ham_shade_kernel<1, true>);
+            ham_shade_kernel<1, true><<<g_shade_bwd, pblock, 0, px>>>(v.clist, v.ccount, v.zcur, ws.vg, v.viewM, invW, invH,
+                                                                      ws.trirec, b->masks, b->sh_coeffs, v.view_idx, v.sh_idx,
+                                                                      V, H, W, v.plane[0], v.plane[1], ws.acc, b->imgs,
+                                                                      (float4*)b->packed);
+        } else {
+            ham_shade_kernel<PHASE><<<g_shade, pblock, 0, px>>>(v.clist, v.ccount, v.zcur, ws.vg, v.viewM, invW, invH,
+                                                              ws.trirec, b->masks, b->sh_coeffs, v.view_idx, v.sh_idx, V, H,
+                                                              W, v.plane[0], v.plane[1], ws.acc, nullptr, nullptr);
+        }
         FMHR_LAUNCH_CHECK();
+        FMHR_STAGE_MARK();  // 4: scan + shade
+        float4* g0 = PHASE == 0 ? v.plane[2] : v.plane[1];
+        float4* g1 = PHASE == 0 ? v.plane[3] : nullptr;
+        if (init) {  // initialisation mode: normals + coverage antialiased, SH normal equations accumulated
+            static const int g_init = persistent_blocks(ham_aa_loss_kernel<2>);
+            ham_aa_loss_kernel<2><<<g_init, pblock, 0, px>>>(
+                v.clist, v.ccount, v.rlist, v.rcount, v.rcap, v.ringbits, v.zcur, ws.vg, v.viewM, b->tri, b->opp,
+                init->grayimgs, b->valid_masks, b->sh_coeffs, v.view_idx, v.sh_idx, V, T, H, W, v.plane[0], v.plane[1], g0, g1,
+                ws.acc, ws.gsh, dimg, dmsk, v.plist_a, v.plist_b, v.pcount, v.pcap, ws.status, init->init_acc, nullptr,
+                nullptr, 0);
+        } else if (spec) {
+            static const int g_aa_spec = persistent_blocks(ham_aa_loss_kernel<1, true>);
+            ham_aa_loss_kernel<1, true><<<g_aa_spec, pblock, 0, px>>>(
+                v.clist, v.ccount, v.rlist, v.rcount, v.rcap, v.ringbits, v.zcur, ws.vg, v.viewM, b->tri, b->opp, b->imgs,
+                b->valid_masks, b->sh_coeffs, v.view_idx, v.sh_idx, V, T, H, W, v.plane[0], v.plane[1], g0, g1, ws.acc,
+                ws.gsh, dimg, dmsk, v.plist_a, v.plist_b, v.pcount, v.pcap, ws.status, nullptr, v.qlist, v.qcount, v.qcap);
+        } else {
+            ham_aa_loss_kernel<PHASE><<<g_aa, pblock, 0, px>>>(
+                v.clist, v.ccount, v.rlist, v.rcount, v.rcap, v.ringbits, v.zcur, ws.vg, v.viewM, b->tri, b->opp, b->imgs,
+                b->valid_masks, b->sh_coeffs, v.view_idx, v.sh_idx, V, T, H, W, v.plane[0], v.plane[1], g0, g1, ws.acc,
+                ws.gsh, dimg, dmsk, v.plist_a, v.plist_b, v.pcount, v.pcap, ws.status, nullptr, nullptr, nullptr, 0);
+        }
+        FMHR_LAUNCH_CHECK();
+        FMHR_STAGE_MARK();  // 5: antialias + losses
+        // After the antialias pass independent kernels remain (all only ADD into `packed`): the pair backward goes to the
+        // vertex side stream (one group) or stays in the group's chain (view groups: the next group's coverage is running
+        // beside it anyway); the loss-scalar finalize and, without speculation, the pixel backward stay on this stream.
+        cudaStream_t ps = px;
+        if (side && G == 1) {
+            FMHR_CUDA(cudaEventRecord(side->fork, px));
+            FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+            ps = side->st;
+        }
+        if (!forward_only) {
+            ham_pair_bwd_kernel<PHASE><<<888, 128, 0, ps>>>(v.plist_a, v.plist_b, v.pcount, v.pcap, v.zcur, ws.vg, v.viewM, V,
+                                                           H, W, v.plane[0], g0, g1, ws.trirec, invW, invH, b->sh_coeffs,
+                                                           v.sh_idx, (float4*)b->packed, spec ? v.qlist : nullptr, v.qcount,
+                                                           v.qcap);
+            FMHR_LAUNCH_CHECK();
+        }
+        if (g == G - 1) {
+            // loss scalars of the whole batch: beside the last pair kernel when this stream is otherwise idle, else behind it
+            ham_finalize_scalars_kernel<<<1, 32, 0, (spec && G == 1) ? px : ps>>>(
+                ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE, b->packed + 12 * (size_t)V);
+            FMHR_LAUNCH_CHECK();
+        }
+        if (side && G == 1) FMHR_CUDA(cudaEventRecord(side->join, side->st));
+        if (!forward_only && !spec) {
+            ham_pixel_bwd_kernel<PHASE><<<g_bwd, pblock, 0, px>>>(v.clist, v.ccount, ws.trirec, invW, invH, v.viewM,
+                                                                  b->sh_coeffs, v.sh_idx, V, H, W, g0, g1, (float4*)b->packed);
+            FMHR_LAUNCH_CHECK();
+        }
+    }
+    if (G > 1) {
+        FMHR_CUDA(cudaEventRecord(side->pix_join, px));
+        FMHR_CUDA(cudaStreamWaitEvent(st, side->pix_join, 0));
     }
     if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
@@ -2530,7 +2718,7 @@ static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     FMHR_LAUNCH_CHECK();
     ham_update_pass2_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, st>>>(
         *cfg, ws.vg, buf->delta, buf->albedo, buf->v2f_ptr, (const int2*)buf->v2f_nbr, buf->v2v_ptr, buf->v2v_idx,
-        packed, ws.ys, buf->adam_m, buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status, bump,
+        packed, ws.greg, buf->adam_m, buf->adam_v, ws.adam_sc, ws.acc, buf->losses, buf->dbg_grad, ws.status, bump,
         buf->adam_step);
     FMHR_LAUNCH_CHECK();
     FMHR_STAGE_MARK();  // 7: update (regularisers, normal backward, Adam)

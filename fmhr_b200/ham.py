@@ -18,7 +18,8 @@ from .dr import Topology
 
 class HamOptimizer:
     def __init__(self, vertices, faces, imgs, masks, valid_masks, w2cs, projs, sh_coeffs, albedo, conf,
-                 process_group=None, n_views_global=None, debug=False, use_graphs=False, exchange=None):
+                 process_group=None, n_views_global=None, debug=False, use_graphs=False, exchange=None,
+                 view_groups=None):
         """All tensors CUDA.  vertices [V,3], faces [F,3] int32, imgs [num,H,W,3], masks/valid_masks [num,H,W],
         w2cs/projs [num,4,4] (transposed, get_data.py:96-97), sh_coeffs [num,9], albedo [1,V,3] or [V,3];
         conf: dict with the weights and learning rates of conf/*.conf."""
@@ -72,6 +73,7 @@ class HamOptimizer:
                 raise RuntimeError("fmhr_b200: peer exchange requested but the ranks' buffers could not be mapped")
             self.peer = px if px.ok else None
         self.n_views_global_override = n_views_global
+        self.view_groups = int(view_groups or 0)  # 0 = library default (fmhr_ham_config.view_groups)
         # The loss is a mean over the GLOBAL batch, so every rank must normalise by the same n_views_global.  The default
         # (local batch x world) is only right when every rank holds the same number of views in every step: checked once
         # here (collective); uneven shards (num_views % world != 0, short last batches) must pass n_views_global.
@@ -171,6 +173,7 @@ class HamOptimizer:
         cfg.phase = phase
         cfg.n_sh_rows = self.num
         cfg.zbuf_slot = 0
+        cfg.view_groups = self.view_groups
         cfg.sfs_weight, cfg.lap_weight = c["sfs_weight"], c["lap_weight"]
         cfg.albedo_weight = c["albedo_weight"] if albedo_weight is None else albedo_weight
         cfg.mask_weight, cfg.edge_weight, cfg.delta_weight = c["mask_weight"], c["edge_weight"], c["delta_weight"]

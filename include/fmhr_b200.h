@@ -157,7 +157,8 @@ typedef struct fmhr_ham_config {
     int32_t n_sh_rows;        /* rows of sh_coeffs resident on this rank (= its number of views) */
     int32_t zbuf_slot;        /* 0/1: z-buffer rasterised by THIS step; the step resets the other one, so the caller
                                  alternates the slot every step (after fmhr_ham_reset) */
-    int32_t reserved;
+    int32_t view_groups;      /* phase-B step: number of consecutive view groups whose pixel passes overlap the next
+                                 group's coverage kernel (1..4; 0 = library default, env FMHR_VIEW_GROUPS) */
     float sfs_weight, lap_weight, albedo_weight, mask_weight, edge_weight, delta_weight;
     float lr, albedo_lr, sh_lr;
     float beta1, beta2, eps;

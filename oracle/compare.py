@@ -31,11 +31,12 @@ LOSS_TERMS = ("sfs", "lap", "albedo", "mask", "edge", "delta")
 TOL_LOSS = 1e-5    # relative, per loss term
 TOL_IMAGE = 1e-5   # relative to the largest image value
 TOL_GRAD = 1e-4    # relative to the largest gradient entry (albedo / SH gradients: max-norm; delta: see below)
-# The gradient w.r.t. the vertex offsets passes through the rasteriser's barycentric backward, whose 1 / (2 * area) factor
-# amplifies fp32 rounding on sliver micro-triangles (the oracle is built with -ffp-contract=off, the CUDA backward
-# contracts to FMA): on the 48-view benchmark shape 99.99 % of the entries agree to 6e-5 of the largest entry and the
-# relative L2 error is 1e-5, but a handful of vertices reach 1.8e-4 (the CUDA path's own run-to-run noise is 2e-7).
-# So the delta gradient is held to 1e-4 in the relative L2 norm and at the 99.99 % quantile, and to 5e-4 in the max norm.
+# Gradients of delta and (phase B) albedo contain the two uniform-Laplacian terms, whose direction y / ||y|| is computed from
+# differences of O(1) numbers (laplacian_direction_allowance): on the 48-view benchmark shape that alone is worth 6.5e-5 of
+# the largest delta-gradient entry INSIDE the fp32 oracle (fp32 vs fp64 of the same formula).  The bar is therefore
+#   |g - g_oracle|_i <= 1e-4 * max|g_oracle| + allowance_i     for every entry,
+# and the raw max-norm (measured 2e-5 .. 1.8e-4 for delta; the CUDA path's own run-to-run noise is 2e-7), the relative L2
+# error (1e-5) and the 99.99 % quantile are reported and held to 5e-4 / 1e-4 / 1e-4.
 TOL_GRAD_DELTA_MAX = 5e-4
 TIE_EPS = 1e-4     # |prediction - target| below this is an L1 near-tie (GPU / oracle predictions differ by ~1e-6)
 
@@ -49,21 +50,26 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def laplacian_well_conditioned(x, faces, rel=1e-4):
-    """Per-vertex mask: the uniform Laplacian (L x)_i and those of all neighbours are well above rounding noise.  The
-    reference's loss sum_i ||(L x)_i|| (models/utils.py:696-722) has the gradient L^T (y / ||y||): where a vertex and its
-    neighbours carry the SAME value (albedo of vertices no view has touched yet) y is 0 up to one ulp and the unit vector
-    y / ||y|| is rounding noise - in the reference as much as here - so those entries cannot be compared."""
+def laplacian_direction_allowance(x, faces, weight):
+    """Per-vertex ABSOLUTE fp32 conditioning allowance of the gradient of  weight * mean_i ||(L x)_i||  (the reference's
+    uniform laplacian_smoothing, models/utils.py:696-722).  Its gradient is  weight / V * L^T yhat  with yhat_j = y_j / ||y_j||,
+    y = L x: y_j is a difference of O(|x|) numbers, so fp32 leaves an absolute error of a few eps |x|max in it and a
+    DIRECTION error of that over ||y_j|| in yhat_j - unbounded where a vertex and its neighbours carry the same value
+    (albedo of vertices no view has touched: y_j is one ulp of noise and yhat_j an arbitrary unit vector, in the reference
+    as much as here).  Both sides carry the error independently, hence the factor 2.  Returned: weight / V * (e_i +
+    sum_{j in N(i)} e_j / deg_j) with e_j = min(2, 2 * 2 eps |x|max / ||y_j||)  (2 eps |x|max: the rounding of the
+    neighbour mean and of the subtraction; measured fp32-vs-fp64 errors of the formula stay 10x below this bound)."""
     f = faces.long()
     a = torch.cat([f[:, 0], f[:, 1], f[:, 2], f[:, 1], f[:, 2], f[:, 0]])
     b = torch.cat([f[:, 1], f[:, 2], f[:, 0], f[:, 0], f[:, 1], f[:, 2]])
     V = x.shape[0]
+    x = x.double()
     s = torch.zeros_like(x).index_add_(0, a, x[b])
-    deg = torch.zeros(V).index_add_(0, a, torch.ones(a.numel()))
-    y = s / deg.clamp_min(1)[:, None] - x
-    good = y.norm(dim=1) > rel * x.abs().max()
-    bad_nb = torch.zeros(V).index_add_(0, a, (~good[b]).float()) > 0
-    return good & ~bad_nb
+    cnt = torch.zeros(V, dtype=torch.float64).index_add_(0, a, torch.ones(a.numel(), dtype=torch.float64)).clamp_min(1)
+    y = (s / cnt[:, None] - x).norm(dim=1)
+    e = (2.0 * 2.0 * 5.96e-8 * float(x.abs().max()) / y.clamp_min(1e-300)).clamp_max(2.0)
+    nb = torch.zeros(V, dtype=torch.float64).index_add_(0, a, e[b]) / cnt  # each neighbour is listed once per shared face
+    return (float(weight) / V * (e + nb)).float()
 
 
 def make_optimizer(scene, device, **kw):
@@ -155,14 +161,22 @@ def ham_step_parity(scene, views=None, device="cuda", phase="b", planes=False, e
         rep["gpu_run_to_run_grad_delta_rel"] = rel_to_max(opt2.dbg_grad.cpu()[:, :3], g[:, :3])
         del opt2
     ga_ref = keep["grad_albedo"][0]
-    rep["grad_albedo_rel_all_vertices"] = rel_to_max(g[:, 3:], ga_ref)
-    if phase == "b":  # phase B adds the albedo Laplacian to the loss: compare where its direction is defined
-        wc = laplacian_well_conditioned(torch.as_tensor(np.asarray(scene["albedo"]), dtype=torch.float32), st.faces)
-        rep["albedo_laplacian_ill_conditioned_frac"] = float(1.0 - wc.float().mean())
+    rep["grad_albedo_rel_raw"] = rel_to_max(g[:, 3:], ga_ref)
+    rep["grad_albedo_rel_l2"] = rel_l2(g[:, 3:], ga_ref)
+    if phase == "b":
+        # phase B has the two uniform-Laplacian terms in the loss: their fp32 conditioning allowance (per vertex, computed
+        # from the oracle's own state) is subtracted before the 1e-4 bar is applied; the raw numbers are reported beside
+        alb0 = torch.as_tensor(np.asarray(scene["albedo"]), dtype=torch.float32)
+        al_a = laplacian_direction_allowance(alb0, st.faces, scene["conf"]["albedo_weight"])
+        al_d = laplacian_direction_allowance(torch.as_tensor(np.asarray(scene["vertices"]), dtype=torch.float32), st.faces,
+                                             scene["conf"]["lap_weight"])
+        gd_ref = keep["grad_delta"]
+        rep["grad_albedo_rel"] = float(((g[:, 3:] - ga_ref).abs() - al_a[:, None]).clamp_min(0).max() / ga_ref.abs().max())
+        rep["grad_delta_rel_excess"] = float(((g[:, :3] - gd_ref).abs() - al_d[:, None]).clamp_min(0).max() / gd_ref.abs().max())
+        rep["laplacian_allowance_rel_median"] = {"albedo": float(al_a.median() / ga_ref.abs().max()),
+                                                 "delta": float(al_d.median() / gd_ref.abs().max())}
     else:
-        wc = torch.ones(ga_ref.shape[0], dtype=torch.bool)
-    rep["grad_albedo_rel"] = float((g[:, 3:] - ga_ref)[wc].abs().max() / ga_ref.abs().max().clamp_min(1e-30))
-    rep["grad_albedo_rel_l2"] = rel_l2(g[:, 3:][wc], ga_ref[wc])
+        rep["grad_albedo_rel"] = rep["grad_albedo_rel_raw"]
     if phase == "a":
         rep["grad_sh_rel"] = rel_to_max(opt.dbg_grad_sh.cpu(), keep["grad_sh"])
     # pass / fail per term with the fp32 resolution of the loss record as absolute floor (a term that is ~0 by
@@ -177,6 +191,7 @@ def ham_step_parity(scene, views=None, device="cuda", phase="b", planes=False, e
             ok = ok and rep[k] <= TOL_GRAD
     if "grad_delta_rel" in rep:
         ok = ok and rep["grad_delta_rel"] <= TOL_GRAD_DELTA_MAX and rep["grad_delta_err_quantiles"][0.9999] <= TOL_GRAD
+        ok = ok and rep["grad_delta_rel_excess"] <= TOL_GRAD
     if "image_rel" in rep:
         ok = ok and rep["rast_bit_exact"] and rep["image_rel"] <= TOL_IMAGE and rep["coverage_abs"] <= TOL_IMAGE
     rep["within_tolerance"] = bool(ok)

@@ -296,6 +296,27 @@ def test_graph_replay_matches_eager(scene):
     assert int(b.adam_step[0]) == 4 and len(b._graphs) == 2 and int(a.adam_step[0]) == 4
 
 
+@pytest.mark.parametrize("groups", [2, 3])
+def test_view_groups_match_single_chain(scene, groups):
+    """fmhr_ham_config.view_groups: the batch's views split into consecutive groups whose pixel passes overlap the next
+    group's coverage kernel (own work lists per group, high-priority pixel stream) - same losses, n_valid and gradients
+    as the single chain (which the tests above hold against the oracle), eager and under CUDA-graph replay."""
+    from fmhr_b200.ham import HamOptimizer
+    c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt).cuda()
+    mk = lambda **kw: HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
+                                   c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], **kw)
+    one, grp, gph = mk(debug=True, view_groups=1), mk(debug=True, view_groups=groups), mk(use_graphs=True, view_groups=groups)
+    n = scene["imgs"].shape[0]
+    for it, views in enumerate([list(range(n)), [n - 1, 0, 2, 1], list(range(n)), [1, 0, 3, 2, 4][: n]]):
+        la, lb, lc = one.step_phase_b(views).cpu(), grp.step_phase_b(views).cpu(), gph.step_phase_b(views).cpu()
+        assert la[6] == lb[6] == lc[6], (it, la, lb, lc)
+        assert torch.allclose(la, lb, rtol=1e-5, atol=1e-7) and torch.allclose(la, lc, rtol=1e-5, atol=1e-7), (it, la, lb, lc)
+        assert _rel(grp.dbg_grad[:, :3], one.dbg_grad[:, :3]) < 1e-5 and _rel(grp.dbg_grad[:, 3:], one.dbg_grad[:, 3:]) < 1e-5
+        # keep the three trajectories on identical state (L1 / hinge kinks amplify the atomics' summation noise)
+        for o in (grp, gph):
+            o.delta.copy_(one.delta); o.albedo.copy_(one.albedo); o.adam_m.copy_(one.adam_m); o.adam_v.copy_(one.adam_v)
+
+
 def test_peer_exchange_single_rank_matches_plain(scene):
     """fmhr_ham_step_update_peer with a world of one (the rank exchanges with itself through the cudaIpc-allocated,
     slot-alternating packed buffers, flag words and step counter) follows the plain update, eager and graph replay;

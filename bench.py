@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "HAM iters/sec (fwd+bwd, views x res)"
 UNIT = "iters/s"
-KERNELS_PER_STEP = 13  # prep, normals, regulariser, trirec, coverage, scan, shade, antialias_loss, pair_bwd, pixel_bwd, finalize, normal_grad, adam
+KERNELS_PER_STEP = 13  # prep, coverage, normals, trirec, regulariser, reg_grad, scan, shade+bwd, antialias_loss, pair_bwd, finalize, normal_grad, adam
 
 
 def b_alg_bytes(n, H, W, V, F, E):
@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank renders the workload's whole view set (global batch N x views); strong = "
+                         "the workload's views are dealt round-robin to the ranks (global batch fixed, SURVEY.md 8e)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-oneshot", "peer-twoshot", "nccl"],
                     help="N > 1: fused NVLink peer-memory exchange inside the update kernel, or one NCCL all-reduce")
     args = ap.parse_args()
@@ -235,13 +238,22 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     wl = dict(synth.WORKLOADS[args.workload])
-    scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), n_views=args.views, camera_seed=1 + rank)
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        # the workload's views (one camera set) dealt round-robin: rank r owns views r, r + world, ... (fmhr_b200.dist.shard_views)
+        total_views = args.views or wl["n"]
+        mine = len(range(rank, total_views, world))
+        scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), n_views=mine, view_offset=rank,
+                                  view_stride=world, camera_seed=1)
+    else:
+        total_views = (args.views or wl["n"]) * world
+        scene = synth.build_scene(wl, lambda *a: render_views(*a, device=dev), n_views=args.views, camera_seed=1 + rank)
     img_u8, msk_u8 = quantise_targets(scene)
     n, H, W = scene["imgs"].shape[0], scene["H"], scene["W"]
     c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt, device=dev)
     opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
                        c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs,
-                       exchange=args.exchange if world > 1 else None)
+                       exchange=args.exchange if world > 1 else None, n_views_global=total_views if world > 1 else None)
     exchange = "1 NCCL all-reduce/iter"
     kernels_per_step = KERNELS_PER_STEP  # own kernels per iteration (NCCL's all-reduce kernel is not counted)
     if opt.peer is not None:
@@ -295,7 +307,8 @@ def main():
     ms_total = float(ms.item())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_per_step = ms_total / args.steps
-    value = world * 1000.0 / ms_per_step  # 48-view iteration equivalents per second over all ranks
+    # weak: iteration equivalents of the workload's view set per second over all ranks; strong: iterations of the one job
+    value = (1.0 if strong else world) * 1000.0 / ms_per_step
     losses = opt.losses.cpu().tolist()
     if not all(np.isfinite(losses)) or losses[6] <= 0:
         raise SystemExit("bench.py: the optimisation state is not finite (losses %s) - refusing to report a number" % losses)
@@ -363,7 +376,7 @@ def main():
             ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
             if world > 1:
                 dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-            return world * 1000.0 * k_e2e / float(ms2.item())
+            return (1.0 if strong else world) * 1000.0 * k_e2e / float(ms2.item())
 
         full = {"value": time_leg(e2e_begin, e2e_step), "unit": UNIT, "steps": k_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -456,15 +469,18 @@ def main():
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_per_step, "steps_per_s": 1000.0 / ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "views_per_gpu": n, "global_views": n * world, "H": H, "W": W, "verts": V,
+        "config": {"workload": args.workload, "views_per_gpu": n, "global_views": total_views, "H": H, "W": W, "verts": V,
                    "faces": F, "phase": "B (delta+albedo, conf/ih_sfs.conf weights)",
                    "launch": "eager" if args.no_graphs else "cuda-graph replay",
                    "warmup_extra_steps": extra,
                    "l2": "per-iteration working set %.0f MB > 126 MB L2 (no flush needed)" % (
                        (8 + 32 + 20) * n * H * W / 1e6),
-                   "parallelism": "views x%d (weak), %s" % (world, exchange) if world > 1 else "single GPU"},
+                   "parallelism": "views x%d (%s), %s" % (world, "strong: the workload's views dealt round-robin" if strong else
+                                                          "weak: every rank renders its own view set", exchange)
+                   if world > 1 else "single GPU"},
         "gpu_launches": kernels_per_step * args.steps,
         "clocks": clocks,
         "e2e": e2e,

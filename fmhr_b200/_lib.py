@@ -91,6 +91,7 @@ _SIGS = {
     "fmhr_ham_stage_times": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), ctypes.POINTER(c_f),
                                    ctypes.POINTER(c_i), c_p]),
     "fmhr_trace_read": (c_i, [c_p, c_i, c_i]),
+    "fmhr_trace_mark": (c_i, [c_i, c_p]),
     "fmhr_ham_debug_export": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p]),
     "fmhr_ham_step_host": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "fmhr_ham_init_scratch_bytes": (c_sz, [c_i]),

@@ -31,6 +31,11 @@
 #ifndef FMHR_LB_SCAN
 #define FMHR_LB_SCAN 6  // a short latency chain per warp: more resident warps = fewer serial units per warp (4: 4,810, 6: 4,895, 8: 4,875 iters/s)
 #endif
+#ifndef FMHR_PEER_POST_DEFAULT
+// only block 0 posts this rank's step word: 193 blocks x (system fence + remote store) made the rendezvous of two ranks that
+// arrive together take 13-15 us; one remote store per peer: 2-3 us (profiles/r2_scaling_exchange.md)
+#define FMHR_PEER_POST_DEFAULT 2
+#endif
 #ifndef FMHR_SIDE_PRIO
 #define FMHR_SIDE_PRIO 0  // high priority for the vertex side stream delays the head of the coverage kernel: 4,810 vs 5,047 iters/s
 #endif
@@ -1882,6 +1887,7 @@ struct HamPeerArgs {
     const uint32_t* flags_b;
     int rank, chunk;                       // chunk = ceil(V / world) vertices per rank
     long long timeout_cycles;              // rendezvous give-up time (SM cycles)
+    int post_mode;                         // see peer_rendezvous
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -1911,15 +1917,18 @@ __device__ __forceinline__ void st_peer(float4* p, float4 v) {
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Block-level rendezvous with every peer: lanes 0..world-1 post this rank's step count into the peers' flag arrays and
-// wait for theirs.  Every block posts the (idempotent) word, so no block ever waits on another block of its own grid;
-// everything this rank wrote in earlier kernels of the stream is visible to a peer that has seen the word.
+// Block-level rendezvous with every peer: lanes 0..world-1 of BLOCK 0 post this rank's step count into the peers' flag
+// arrays (release at system scope: everything this rank wrote in earlier kernels of the stream is visible to a peer that
+// has seen the word), lanes 0..world-1 of EVERY block wait for the peers' words.  A block only ever waits for a peer's
+// block 0, which posts unconditionally when it starts - never for another block of its own grid.
 __device__ __forceinline__ void peer_rendezvous(uint32_t* const* signal, const uint32_t* flags, int world, uint32_t want,
-                                                int* status, long long timeout_cycles, int trace_slot) {
+                                                int* status, long long timeout_cycles, int trace_slot, int post_mode) {
     FMHR_TRACE_MIN(trace_slot, 0);  // first block of this rank posts
     if (threadIdx.x < world) {
-        __threadfence_system();
-        st_release_sys(signal[threadIdx.x], want);
+        // post_mode 0: every block posts behind a system-scope fence (round 1); 1: every block posts, the release store alone
+        // orders the earlier kernels' writes; 2: only block 0 posts (one remote store per peer instead of one per block)
+        if (post_mode == 0) __threadfence_system();
+        if (post_mode != 2 || blockIdx.x == 0) st_release_sys(signal[threadIdx.x], want);
         const uint32_t* f = flags + threadIdx.x;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
@@ -1935,7 +1944,7 @@ __device__ __forceinline__ void peer_rendezvous(uint32_t* const* signal, const u
 // rank*chunk + j over every rank's `packed` (rank order) and stores the three sums into EVERY rank's `reduced`.
 __global__ void __launch_bounds__(256) ham_peer_reduce_scatter_kernel(int V, HamPeerArgs pa, int* __restrict__ status) {
     FMHR_TRACE_SCOPE(13);
-    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 20);
+    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 20, pa.post_mode);
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == pa.chunk) {  // the four loss scalars: rank 0
         if (pa.rank != 0) return;
@@ -1976,7 +1985,7 @@ __global__ void __launch_bounds__(256) ham_peer_normal_grad_kernel(int V, float4
                                                                    const float4* __restrict__ raw4, HamPeerArgs pa,
                                                                    int* __restrict__ status) {
     FMHR_TRACE_SCOPE(14);
-    peer_rendezvous(pa.signal_b, pa.flags_b, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 22);
+    peer_rendezvous(pa.signal_b, pa.flags_b, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 22, pa.post_mode);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float4 ga = ld_peer(pa.reduced + 2 * (size_t)i), gb = ld_peer(pa.reduced + 2 * (size_t)i + 1);
@@ -2001,7 +2010,7 @@ __global__ void __launch_bounds__(256) ham_peer_reduce_normal_grad_kernel(int V,
                                                                           const float4* __restrict__ raw4, HamPeerArgs pa,
                                                                           int* __restrict__ status) {
     FMHR_TRACE_SCOPE(15);
-    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 20);
+    peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 20, pa.post_mode);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > V) return;
     if (i == V) {  // the four loss scalars behind the accumulators
@@ -2700,6 +2709,8 @@ static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         pa.rank = peers->rank;
         pa.chunk = cdiv(V, peers->world);
         pa.timeout_cycles = (long long)(peers->timeout_s > 0 ? peers->timeout_s : kPeerDefaultTimeoutS) * kPeerCyclesPerSecond;
+        static const int post_mode = [] { const char* e = getenv("FMHR_PEER_POST"); return e ? atoi(e) : FMHR_PEER_POST_DEFAULT; }();
+        pa.post_mode = post_mode;
         const bool two_shot = peers->mode == 2 || (peers->mode == 0 && peers->world > 2);
         if (two_shot) {
             // one-shot pulls world x 48 B per vertex into every rank; beyond two ranks the reduce-scatter form moves
@@ -2819,12 +2830,42 @@ extern "C" int fmhr_ham_stage_times(const fmhr_ham_config* cfg, const fmhr_ham_b
     return rc;
 }
 
+#ifdef FMHR_TRACE
+// steady-state tracing: a one-thread kernel between two steps moves the stamps of the step before it into ring entry `rep`
+// and re-arms the slots, so a free-running loop of steps (no host synchronisation in between) can be read back afterwards
+constexpr int kTraceRing = 64;
+static __device__ unsigned long long g_trace_ring[kTraceRing][kTraceSlots][2];
+__global__ void ham_trace_mark_kernel(int rep) {
+    for (int i = threadIdx.x; i < kTraceSlots; i += blockDim.x) {
+        if (rep >= 0 && rep < kTraceRing) { g_trace_ring[rep][i][0] = g_trace[i][0]; g_trace_ring[rep][i][1] = g_trace[i][1]; }
+        g_trace[i][0] = ~0ull; g_trace[i][1] = 0ull;
+    }
+}
+#endif
+// Diagnostic builds: enqueue "store the stamps collected since the previous mark as ring entry `rep` (< 64; negative: discard)
+// and re-arm" on `stream`; fmhr_trace_read with n_slots = -reps then returns reps x 64 x 2 stamps of the ring.
+extern "C" int fmhr_trace_mark(int rep, fmhr_stream_t stream) {
+#ifdef FMHR_TRACE
+    ham_trace_mark_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(rep);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+#else
+    (void)rep; (void)stream;
+    set_error("fmhr_trace_mark: this build has no timeline tracing (compile with -DFMHR_TRACE)");
+    return FMHR_EUNSUPPORTED;
+#endif
+}
+
 // Diagnostic builds (-DFMHR_TRACE): first-entry / last-exit %globaltimer stamps (ns) of every kernel slot since the last
 // reset; the product build returns FMHR_EUNSUPPORTED.  Synchronises the device.
 extern "C" int fmhr_trace_read(unsigned long long* stamps_host, int n_slots, int reset) {
 #ifdef FMHR_TRACE
-    FMHR_CHECK_ARG(n_slots >= 0 && n_slots <= kTraceSlots && (stamps_host || n_slots == 0));
+    FMHR_CHECK_ARG(n_slots >= -kTraceRing && n_slots <= kTraceSlots && (stamps_host || n_slots == 0));
     FMHR_CUDA(cudaDeviceSynchronize());
+    if (n_slots < 0) {  // the ring of fmhr_trace_mark
+        FMHR_CUDA(cudaMemcpyFromSymbol(stamps_host, g_trace_ring, (size_t)(-n_slots) * kTraceSlots * 2 * sizeof(unsigned long long)));
+        return FMHR_OK;
+    }
     if (n_slots > 0)
         FMHR_CUDA(cudaMemcpyFromSymbol(stamps_host, g_trace, (size_t)n_slots * 2 * sizeof(unsigned long long)));
     if (reset) {

@@ -255,6 +255,8 @@ WORKLOADS = {
     # triangles larger than a pixel: the regime where antialias finds silhouette edges (it only inspects the edges
     # of the triangle visible in the pixel, so micropolygon meshes rarely blend)
     "coarse": dict(n=4, H=288, W=240, subdiv=0, hands=1, conf="demo_sfs"),
+    "coarse8": dict(n=8, H=288, W=240, subdiv=0, hands=1, conf="demo_sfs"),    # one view per rank on an 8-GPU box
+    "coarse16": dict(n=16, H=288, W=240, subdiv=0, hands=1, conf="demo_sfs"),  # two views per rank on an 8-GPU box
 }
 
 

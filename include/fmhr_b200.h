@@ -274,6 +274,10 @@ int fmhr_ham_stage_times(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf
  * %globaltimer stamps in ns since the last reset, stamps_host[2 * slot + {0,1}]; slot numbering in csrc/ham.cu.
  * Synchronises the device.  The product build returns FMHR_EUNSUPPORTED. */
 int fmhr_trace_read(unsigned long long* stamps_host, int n_slots, int reset);
+/* Diagnostic builds: enqueue on `stream` "store the stamps collected since the previous mark as ring entry `rep` (0..63,
+ * negative = discard) and re-arm the slots"; fmhr_trace_read(out, -reps, 0) then returns reps x 64 x 2 stamps - the
+ * schedule of `reps` consecutive free-running steps without a host synchronisation between them. */
+int fmhr_trace_mark(int rep, fmhr_stream_t stream);
 /* Host-buffer variant (end-to-end measurement path): copies this step's view batch (img/mask/valid_mask/w2c/proj
  * rows, all HOST pinned pointers, n_views rows each) into the device staging planes named by `buf`, runs
  * render+update, and copies the 8-float loss record back to losses_host. */

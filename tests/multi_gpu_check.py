@@ -1,6 +1,6 @@
-"""Multi-GPU parity check (run with torchrun, one rank per GPU; not collected by pytest):
+"""Multi-GPU parity check (run with torchrun, one rank per GPU, any world size up to 8; not collected by pytest):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
         tests/multi_gpu_check.py
 
 Views are sharded round-robin over the ranks, each rank renders its shard, `packed` is summed once per iteration (NCCL all-reduce, or the
@@ -81,7 +81,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    scene = synth.build_scene("coarse" if len(sys.argv) < 2 else sys.argv[1], lambda *a: render_views(*a, device=dev))
+    # default scene: at least two views per rank where the workload list allows it (4 / 8 / 16 views)
+    default = "coarse" if world <= 2 else ("coarse8" if world <= 4 else "coarse16")
+    scene = synth.build_scene(default if len(sys.argv) < 2 else sys.argv[1], lambda *a: render_views(*a, device=dev))
     num = scene["imgs"].shape[0]
     c = lambda k, dt=torch.float32, sel=None: torch.tensor(scene[k] if sel is None else scene[k][sel], dtype=dt, device=dev)
     mine = shard_views(num, rank, world)

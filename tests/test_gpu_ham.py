@@ -558,18 +558,21 @@ def test_capture_room_and_stress_shapes():
     assert out.shape == (Nv, Np) and float((out.double() - want).abs().max()) < 2e-5
 
 
-def test_two_rank_exchange_on_two_gpus():
-    """The N > 1 path on real devices (skipped on a single-GPU box; the gloo test in test_host_logic.py covers the
-    reduction algebra on CPU): tests/multi_gpu_check.py under torchrun with two ranks - NCCL all-reduce, one-shot and
-    two-shot peer-memory exchange, eager and graph replay, alternating batch sizes, the host-batch step - each against a
-    single-rank optimiser that renders all views, and bit-identical replicas after the exchange."""
+def test_multi_rank_exchange_on_all_gpus():
+    """The N > 1 path on real devices, with as many ranks as the box has GPUs (2, 4 or 8; skipped on a single-GPU box,
+    where the gloo test in test_host_logic.py covers the reduction algebra on CPU): tests/multi_gpu_check.py under
+    torchrun - NCCL all-reduce, one-shot and two-shot (the default beyond two ranks) peer-memory exchange, eager and graph
+    replay, alternating batch sizes, the host-batch step - each against a single-rank optimiser that renders all views,
+    and bit-identical replicas after the exchange."""
     import os
     import subprocess
     import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    ranks = 8 if ndev >= 8 else (4 if ndev >= 4 else 2)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29577", os.path.join(root, "tests", "multi_gpu_check.py")]
-    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr",
+           "127.0.0.1", "--master-port", "29577", os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])

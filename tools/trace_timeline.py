@@ -52,17 +52,28 @@ def main():
     views = torch.arange(n, dtype=torch.int32, device=dev)
     for _ in range(20):
         opt.step_phase_b(views)
-    buf = (ctypes.c_ulonglong * 128)()
-    rows = []
-    for _ in range(a.reps):
-        if world > 1:
-            dist.barrier()
-        _lib.check(lib.fmhr_trace_read(buf, 0, 1), "trace_read")  # reset
+    reps = min(a.reps, 64)
+    # free-running loop: [mark][step][mark][step]... with no host synchronisation in between (the ranks of a multi-GPU job
+    # stay coupled through the exchange only, as in the benchmark); mark i stores the stamps of step i - 1
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _lib.check(lib.fmhr_trace_mark(-1, _lib.stream()), "trace_mark")
+    for _ in range(10):
         opt.step_phase_b(views)
-        _lib.check(lib.fmhr_trace_read(buf, 64, 0), "trace_read")
-        rows.append(np.array(list(buf), dtype=np.uint64).reshape(64, 2).astype(np.int64))
+    for r in range(reps):
+        _lib.check(lib.fmhr_trace_mark(r - 1, _lib.stream()), "trace_mark")
+        opt.step_phase_b(views)
+    _lib.check(lib.fmhr_trace_mark(reps - 1, _lib.stream()), "trace_mark")
+    buf = (ctypes.c_ulonglong * (reps * 128))()
+    _lib.check(lib.fmhr_trace_read(buf, -reps, 0), "trace_read")
+    allrows = np.array(list(buf), dtype=np.uint64).reshape(reps, 64, 2).astype(np.int64)
+    rows = [allrows[r] for r in range(reps)]
     rows = np.stack(rows)  # [reps, 64, 2]
+    for k in (21, 23):  # single-stamp slots ("first block that has seen every peer")
+        rows[:, k, 1] = np.where(rows[:, k, 0] >= 0, rows[:, k, 0], 0)
     used = [k for k in range(64) if (rows[:, k, 1] > 0).all() and (rows[:, k, 0] >= 0).all() and (rows[:, k, 0] != -1).all()]
+    period = float(np.median(np.diff(rows[:, used, 0].min(axis=1)))) / 1e3 if reps > 1 else 0.0
     t0 = rows[:, used, 0].min(axis=1, keepdims=True)
     out = {}
     for j, k in enumerate(used):
@@ -71,9 +82,11 @@ def main():
         out[NAMES.get(k, str(k))] = {"start_us": float(np.median(s)), "end_us": float(np.median(e)),
                                       "dur_us": float(np.median(e - s))}
     total = float(np.median((rows[:, used, 1].max(axis=1) - t0[:, 0]) / 1e3))
+    import time
+    time.sleep(0.2 * rank)  # keep the ranks' tables apart
     if rank == 0 or world > 1:
-        print("rank %d: %s, %d views, graph=%s: first block entry -> last warp exit = %.1f us (median of %d)" % (
-            rank, a.workload, n, not a.no_graphs, total, a.reps))
+        print("rank %d: %s, %d views, graph=%s: first block entry -> last block exit = %.1f us, step period %.1f us "
+              "(median of %d free-running steps)" % (rank, a.workload, n, not a.no_graphs, total, period, reps))
         for name, v in sorted(out.items(), key=lambda kv: kv[1]["start_us"]):
             print("  %-40s start %8.1f  end %8.1f  dur %7.1f" % (name, v["start_us"], v["end_us"], v["dur_us"]))
     if a.out and rank == 0:

@@ -1945,37 +1945,28 @@ __device__ __forceinline__ void peer_rendezvous(uint32_t* const* signal, const u
 __global__ void __launch_bounds__(256) ham_peer_reduce_scatter_kernel(int V, HamPeerArgs pa, int* __restrict__ status) {
     FMHR_TRACE_SCOPE(13);
     peer_rendezvous(pa.signal, pa.flags, pa.world, *pa.epoch + 1u, status, pa.timeout_cycles, 20, pa.post_mode);
+    // One thread per float4 of this rank's chunk (3 per vertex: the two halves of G8 and Gm - both contiguous ranges of the
+    // packed buffer), every rank's copy loaded in ONE round of up to 16 independent NVLink reads, summed in rank order and
+    // stored into every rank's `reduced`.  (One thread per vertex with the ranks taken four at a time was 3 float4 x 2
+    // dependent round trips deep on 1/3 of the threads: 13 us of the 8-rank step for 300 kB per rank.)
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == pa.chunk) {  // the four loss scalars: rank 0
-        if (pa.rank != 0) return;
-        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < pa.world; r++) sc = add4(sc, ld_peer(pa.packed[r] + 3 * (size_t)V));
-        for (int r = 0; r < pa.world; r++) st_peer(pa.reduced_all[r] + 3 * (size_t)V, sc);
-        return;
-    }
-    const int i = pa.rank * pa.chunk + j;
-    if (j > pa.chunk || i >= V) return;
-    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, gm = ga;
-    for (int r0 = 0; r0 < pa.world; r0 += 4) {
-        float4 a[4], b[4], m[4];
+    const int v0 = pa.rank * pa.chunk, nv = max(0, min(pa.chunk, V - v0));
+    size_t idx;
+    if (j < 2 * nv) idx = 2 * (size_t)v0 + j;                          // G8[2 v0 .. 2 (v0 + nv))
+    else if (j < 3 * nv) idx = 2 * (size_t)V + v0 + (j - 2 * nv);      // Gm[v0 .. v0 + nv)
+    else if (j == 3 * nv && pa.rank == 0) idx = 3 * (size_t)V;         // the four loss scalars: rank 0
+    else return;
+    float4 x[FMHR_MAX_PEERS];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (r0 + k < pa.world) {
-                const float4* p = pa.packed[r0 + k];
-                a[k] = ld_peer(p + 2 * (size_t)i);
-                b[k] = ld_peer(p + 2 * (size_t)i + 1);
-                m[k] = ld_peer(p + 2 * (size_t)V + i);
-            }
+    for (int r = 0; r < FMHR_MAX_PEERS; r++)
+        if (r < pa.world) x[r] = ld_peer(pa.packed[r] + idx);
+    float4 sum = x[0];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (r0 + k < pa.world) { ga = add4(ga, a[k]); gb = add4(gb, b[k]); gm = add4(gm, m[k]); }
-    }
-    for (int r = 0; r < pa.world; r++) {
-        float4* q = pa.reduced_all[r];
-        st_peer(q + 2 * (size_t)i, ga);
-        st_peer(q + 2 * (size_t)i + 1, gb);
-        st_peer(q + 2 * (size_t)V + i, gm);
-    }
+    for (int r = 1; r < FMHR_MAX_PEERS; r++)
+        if (r < pa.world) sum = add4(sum, x[r]);
+#pragma unroll
+    for (int r = 0; r < FMHR_MAX_PEERS; r++)
+        if (r < pa.world) st_peer(pa.reduced_all[r] + idx, sum);
 }
 
 // Two-shot exchange, kernel 2: second rendezvous (this rank's chunk is complete - the kernel boundary - and so is every
@@ -2715,7 +2706,7 @@ static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         if (two_shot) {
             // one-shot pulls world x 48 B per vertex into every rank; beyond two ranks the reduce-scatter form moves
             // 1/world of that in and the same out (8 ranks: 16.6 MB -> 2 x 2.1 MB per rank and step)
-            ham_peer_reduce_scatter_kernel<<<cdiv(pa.chunk + 1, 256), 256, 0, st>>>(V, pa, ws.status);
+            ham_peer_reduce_scatter_kernel<<<cdiv(3 * pa.chunk + 1, 256), 256, 0, st>>>(V, pa, ws.status);
             FMHR_LAUNCH_CHECK();
             ham_peer_normal_grad_kernel<<<cdiv(V, 256), 256, 0, st>>>(V, ws.vg, ws.vattr, ws.raw4, pa, ws.status);
         } else {

@@ -3,6 +3,7 @@ scripts (neural_render.py:90-96 reads `<scan>.pt` and `<scan>.obj`) can consume 
 
     <scan>.pt     torch.save({'sh_coeff': [num,9], 'albedo': [1,V,3]})                     (:323)
     <scan>.obj    refined mesh, vertex and face order preserved (trimesh export, :328-329)
+    ori_<scan>.obj  the subdivided input mesh before refinement (:114-118)
     <scan>_c.obj  vertices with per-vertex colour clamp(0.5 * albedo, 0, 1) in RGB (albedo is BGR), faces with
                   FLIPPED winding f0 f2 f1 (save_obj_mesh_with_color, :19-28, :336-337)
     rerender/mesh_%02d.png  the last epoch's antialiased renders, one per view (:339-345) - optional
@@ -35,10 +36,15 @@ def save_obj_mesh_with_color(mesh_path, verts, faces, colors):
             f.write("f %d %d %d\n" % (t[0] + 1, t[2] + 1, t[1] + 1))
 
 
-def save_ham_results(out_dir, scan_id, vertices, faces, albedo, sh_coeffs, rendered=None, perm_last=None):
+def save_ham_results(out_dir, scan_id, vertices, faces, albedo, sh_coeffs, rendered=None, perm_last=None,
+                     ori_vertices=None):
     """Writes the reference's result set.  vertices [V,3], faces [F,3], albedo [V,3] or [1,V,3] (BGR), sh_coeffs [num,9];
-    rendered [k,H,W,3] in [0,1] (BGR, as cv2 expects) with perm_last giving each image's view index."""
+    rendered [k,H,W,3] in [0,1] (BGR, as cv2 expects) with perm_last giving each image's view index; ori_vertices: the
+    subdivided input mesh, written as ori_<scan>.obj (mesh_sfs_optim.py:114-118)."""
     os.makedirs(out_dir, exist_ok=True)
+    if ori_vertices is not None:
+        save_obj_mesh(os.path.join(out_dir, "ori_%d.obj" % scan_id), torch.as_tensor(ori_vertices).detach().float().cpu().numpy(),
+                      torch.as_tensor(faces).detach().cpu().numpy())
     v = torch.as_tensor(vertices).detach().float().cpu()
     f = torch.as_tensor(faces).detach().cpu()
     a = torch.as_tensor(albedo).detach().float().cpu().reshape(1, -1, 3)

@@ -106,5 +106,35 @@ def main():
     print("wrote", os.path.join(OUT, "refmath_v1.npz"))
 
 
+def import_reference_repose():
+    """/root/reference/repose.py imported verbatim (its unrelated imports - smplx, pyhocon, segment_anything, trimesh -
+    are stubbed; `smplx.create` returns a dummy so that get_data's module-level MANO layers construct)."""
+    import_reference()
+    for name in ("smplx", "pyhocon", "segment_anything", "trimesh.remesh"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pyhocon"].ConfigFactory = object
+    sys.modules["segment_anything"].sam_model_registry = {}
+    sys.modules["segment_anything"].SamPredictor = object
+    sys.modules["smplx"].create = lambda *a, **k: types.SimpleNamespace()
+    import repose
+    return repose
+
+
+def gen_repose():
+    """tests/golden/repose_v1.npz: the reference's subdivide_weight (repose.py:14-24) on one round of subdivision of the
+    synthetic 778-vertex hand with random 16-joint skinning weights."""
+    from fmhr_b200 import synth
+    rp = import_reference_repose()
+    rng = np.random.default_rng(7)
+    v0, f0 = synth.base_hand_mesh()
+    w0 = rng.dirichlet(np.ones(16) * 0.3, size=v0.shape[0])
+    v1, f1 = synth.subdivide_loop(v0, f0, 1)
+    w1 = rp.subdivide_weight(w0, f1)
+    np.savez_compressed(os.path.join(OUT, "repose_v1.npz"), w0=w0.astype(np.float32), f0=f0.astype(np.int32),
+                        f1=f1.astype(np.int32), w1=w1.astype(np.float32))
+    print("repose golden:", w1.shape, "row sums", float(w1.sum(1).min()), float(w1.sum(1).max()))
+
+
 if __name__ == "__main__":
     main()
+    gen_repose()

@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--workload", default="interhand_48x512x334")
     ap.add_argument("--views", type=int, default=None,
                     help="keep only the first N views of the workload (e.g. 16 = one rank's shard of stress_128x2048x2048)")
+    ap.add_argument("--ncc", action="store_true",
+                    help="add the NCC photo-consistency term (BASELINE.json configs[2]): 50,000 surface points x 11x11 patches, "
+                         "reference view 0 against the other views (fmhr_b200.ncc_term; single GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
@@ -216,6 +219,8 @@ def main():
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
     args.warmup = max(args.warmup, 3)
+    if args.ncc:  # the host-batch step and the oracle leg run the iteration without extra terms
+        args.no_e2e = args.no_cpu_baseline = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -254,8 +259,16 @@ def main():
     opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
                        c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs,
                        exchange=args.exchange if world > 1 else None, n_views_global=total_views if world > 1 else None)
+    ncc_term = None
+    if args.ncc:
+        if world > 1:
+            raise SystemExit("bench.py: --ncc is single-GPU")
+        from fmhr_b200.ncc_term import NccTerm
+        gray = torch.tensor(np.asarray(scene["imgs"]).mean(-1).astype(np.float32), device=dev)
+        ncc_term = NccTerm(opt, gray, ref_view=0, src_views=list(range(1, scene["imgs"].shape[0])), weight=10.0,
+                           n_points=50000, half=5, seed=0)
     exchange = "1 NCCL all-reduce/iter"
-    kernels_per_step = KERNELS_PER_STEP  # own kernels per iteration (NCCL's all-reduce kernel is not counted)
+    kernels_per_step = KERNELS_PER_STEP + (5 if args.ncc else 0)  # own kernels per iteration (NCCL's all-reduce kernel is not counted)
     if opt.peer is not None:
         # one-shot: the exchange IS the normal-gradient kernel; two-shot: one extra reduce-scatter kernel in front of it
         kernels_per_step += 1 if (opt.peer.mode == 2 or (opt.peer.mode == 0 and world > 2)) else 0
@@ -420,7 +433,7 @@ def main():
     # the unit of the path is one whole iteration (one CUDA-graph launch of 13 kernels) and its
     # algorithmic bytes B_alg are the single figure for roofline.achieved; the dominant kernel is reported beside it.
     peak, peak_src = measured_peak_gbs()
-    balg = b_alg_bytes(n, H, W, V, F, E)
+    balg = b_alg_bytes(n, H, W, V, F, E) + (ncc_term.algorithmic_bytes() if ncc_term is not None else 0)
     iter_ach = balg / (ms_per_step * 1e-3) / 1e9
     traffic = measured_traffic()
     roof = {"bound": "hbm", "kernel": "fused HAM iteration (%d kernels, one graph launch)" % kernels_per_step,
@@ -476,6 +489,8 @@ def main():
                    "faces": F, "phase": "B (delta+albedo, conf/ih_sfs.conf weights)",
                    "launch": "eager" if args.no_graphs else "cuda-graph replay",
                    "warmup_extra_steps": extra,
+                   "ncc": ("50,000 surface points x 121-pixel patches, reference view 0 vs %d source views, weight 10" % (n - 1))
+                   if ncc_term is not None else None,
                    "l2": "per-iteration working set %.0f MB > 126 MB L2 (no flush needed)" % (
                        (8 + 32 + 20) * n * H * W / 1e6),
                    "parallelism": "views x%d (%s), %s" % (world, "strong: the workload's views dealt round-robin" if strong else

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfmhr_b200.so")
-SOURCES = ["api.cu", "raster.cu", "interpolate.cu", "antialias.cu", "mesh.cu", "meshlet.cu", "ham.cu"]
+SOURCES = ["api.cu", "raster.cu", "interpolate.cu", "antialias.cu", "mesh.cu", "meshlet.cu", "ncc_loop.cu", "ham.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

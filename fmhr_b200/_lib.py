@@ -77,6 +77,9 @@ _SIGS = {
     "fmhr_sh_radiance_bwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p]),
     "fmhr_ncc_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_ncc_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "fmhr_ncc_sample_fwd": (c_i, [c_p] * 7 + [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "fmhr_ncc_sample_bwd": (c_i, [c_p] * 7 + [c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "fmhr_ham_add_delta_grad": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p]),
     "fmhr_ham_workspace_bytes": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_packed_floats": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_reset": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),

@@ -2733,6 +2733,29 @@ static int ham_update_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     return FMHR_OK;
 }
 
+// Extra loss terms (the NCC term of ncc_loop.cu): a fully weighted gradient w.r.t. delta computed outside the fused passes is
+// added to the regulariser-gradient slot of the workspace, between fmhr_ham_step_render and fmhr_ham_step_update.
+__global__ void __launch_bounds__(256) ham_add_delta_grad_kernel(int V, const float* __restrict__ grad, float4* __restrict__ greg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    float4 g = greg[2 * (size_t)i];
+    g.x += grad[3 * (size_t)i]; g.y += grad[3 * (size_t)i + 1]; g.z += grad[3 * (size_t)i + 2];
+    greg[2 * (size_t)i] = g;
+}
+extern "C" int fmhr_ham_add_delta_grad(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* grad_delta,
+                                       fmhr_stream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = ham_check_buffers(cfg, buf);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(grad_delta && cfg->phase == 1);
+    HamWs ws;
+    ham_layout(cfg, (char*)buf->workspace, &ws);
+    ham_add_delta_grad_kernel<<<cdiv(cfg->V, 256), 256, 0, (cudaStream_t)stream>>>(cfg->V, grad_delta, ws.greg);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
 extern "C" int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;

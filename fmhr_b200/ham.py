@@ -86,6 +86,7 @@ class HamOptimizer:
         self.dbg_grad_sh = None
         self.debug = debug
         self.phase = 0
+        self.extra_terms = []  # phase-B loss terms outside the fused passes (fmhr_b200.ncc_term.NccTerm)
         self._view_idx_cache = {}
         self.use_graphs = bool(use_graphs) and not debug
         self._graphs = {}
@@ -276,6 +277,11 @@ class HamOptimizer:
             buf.packed = self.peer.packed[cfg.zbuf_slot].data_ptr()
         if part in (None, 0):
             check(self.lib.fmhr_ham_step_render(ctypes.byref(cfg), ctypes.byref(buf), sp), "ham_step_render")
+        if part in (None, 0) and cfg.phase == 1 and self.extra_terms:
+            # extra loss terms work on the step's vertices and add their delta gradient before the update (torch ops inside
+            # run on the current stream, which is `sp` in every caller)
+            for term in self.extra_terms:
+                term.accumulate(self, cfg, buf, sp)
         if part is None and self.world > 1 and self.peer is None:
             allreduce_packed(self.packed, self.pg)  # one NCCL sum per iteration
         if part in (None, 1):

@@ -225,6 +225,26 @@ int fmhr_ham_prepare_views(const float* valid_masks, int num, int H, int W, doub
 int fmhr_ham_step_render(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
 /* normalises with the (all-reduced) counts, adds the regulariser gradients, applies Adam, writes `losses`. */
 int fmhr_ham_step_update(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
+/* Extra loss terms of a phase-B step (the NCC term below): adds a fully weighted gradient w.r.t. delta [V,3], computed by
+ * the caller between fmhr_ham_step_render and fmhr_ham_step_update, to the gradient the update applies. */
+int fmhr_ham_add_delta_grad(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, const float* grad_delta,
+                            fmhr_stream_t stream);
+/* NCC photo-consistency term (BASELINE.json configs[2]; arithmetic of models/ncc_utils.py:4-35 = fmhr_ncc_fwd / _bwd above;
+ * the wiring has no counterpart in the reference, SURVEY.md F4, and is specified in DESIGN.md): Np points fixed on the
+ * surface (pt_face [Np], pt_bary [Np,2]; third weight = 1 - b0 - b1) are projected into the views view_idx[0] (reference)
+ * and view_idx[1..Nv1) (sources) of the camera arrays w2cs / projs (transposed, as everywhere), and a (2 half + 1)^2 patch
+ * of the gray image [num,H,W] is sampled bilinearly around each projection (0 outside the frame): patches [Nv1,Np,Npx];
+ * patch_mask = all four taps inside the frame and masks[view] > 0.5 at the nearest pixel.  The backward takes
+ * d loss / d patches (row 0, the reference view, is ignored: the reference patch is a constant of the step) and ADDS
+ * d loss / d vertices [V,3]. */
+int fmhr_ncc_sample_fwd(const float* vertices, const int32_t* tri, const int32_t* pt_face, const float* pt_bary,
+                        const float* w2cs, const float* projs, const int32_t* view_idx, int Nv1, const float* gray,
+                        const float* masks, int V, int Np, int H, int W, int half, float* patches, float* patch_mask,
+                        fmhr_stream_t stream);
+int fmhr_ncc_sample_bwd(const float* vertices, const int32_t* tri, const int32_t* pt_face, const float* pt_bary,
+                        const float* w2cs, const float* projs, const int32_t* view_idx, int Nv1, const float* gray, int V,
+                        int Np, int H, int W, int half, const float* grad_patches, float* grad_vertices,
+                        fmhr_stream_t stream);
 /* ---- multi-GPU exchange over NVLink peer memory (replaces the ncclAllReduce of `packed` the reference
  * design would place between loss.backward() and optimizer.step(), mesh_sfs_optim.py:309-310, when views shard) ----
  * Every rank allocates its exchange memory with fmhr_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; zero-filled), the

@@ -4,7 +4,7 @@ set -e
 NAME=$1; shift
 mkdir -p /root/repo/variants/obj_$NAME
 cd /root/repo/fmhr_b200/csrc
-for f in api raster interpolate antialias mesh meshlet ham; do
+for f in api raster interpolate antialias mesh meshlet ncc_loop ham; do
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c $f.cu -o /root/repo/variants/obj_$NAME/$f.o &
 done
 wait

@@ -60,15 +60,17 @@ def laplacian_direction_allowance(x, faces, weight):
     sum_{j in N(i)} e_j / deg_j) with e_j = min(2, 2 * 8 eps |x|max / ||y_j||)  (8 eps |x|max: a sum of ~6 neighbours,
     the division and the subtraction; for well-conditioned vertices this stays ~5e-6 of the largest gradient entry)."""
     f = faces.long()
+    V = x.shape[0]
     a = torch.cat([f[:, 0], f[:, 1], f[:, 2], f[:, 1], f[:, 2], f[:, 0]])
     b = torch.cat([f[:, 1], f[:, 2], f[:, 0], f[:, 0], f[:, 1], f[:, 2]])
-    V = x.shape[0]
+    key = torch.unique(a * V + b)  # every directed neighbour pair once (interior edges are listed by both of their faces)
+    a, b = key // V, key % V
     x = x.double()
     s = torch.zeros_like(x).index_add_(0, a, x[b])
-    cnt = torch.zeros(V, dtype=torch.float64).index_add_(0, a, torch.ones(a.numel(), dtype=torch.float64)).clamp_min(1)
-    y = (s / cnt[:, None] - x).norm(dim=1)
+    deg = torch.zeros(V, dtype=torch.float64).index_add_(0, a, torch.ones(a.numel(), dtype=torch.float64)).clamp_min(1)
+    y = (s / deg[:, None] - x).norm(dim=1)
     e = (2.0 * 8.0 * 5.96e-8 * float(x.abs().max()) / y.clamp_min(1e-300)).clamp_max(2.0)
-    nb = torch.zeros(V, dtype=torch.float64).index_add_(0, a, e[b]) / cnt  # each neighbour is listed once per shared face
+    nb = torch.zeros(V, dtype=torch.float64).index_add_(0, a, (e / deg)[b])  # L^T: column i holds 1 / deg_j for j in N(i)
     return (float(weight) / V * (e + nb)).float()
 
 

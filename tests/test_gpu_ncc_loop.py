@@ -66,7 +66,7 @@ def test_iteration_with_ncc_term_matches_the_oracle(scene):
     assert compare.rel_l2(g, gref) < 2e-4, compare.rel_l2(g, gref)
     # the term did change the gradient, and only the delta gradient (albedo is untouched)
     assert compare.rel_l2(plain.dbg_grad.cpu()[:, :3], gref) > 1e-2
-    assert torch.allclose(opt.dbg_grad[:, 3:], plain.dbg_grad[:, 3:], rtol=1e-4, atol=1e-9)   # (atomics order differs)
+    assert compare.rel_to_max(opt.dbg_grad[:, 3:], plain.dbg_grad[:, 3:]) < 1e-5   # (only the order of the atomics differs)
 
 
 def test_graph_replay_with_ncc_term_matches_eager(scene):

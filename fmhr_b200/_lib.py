@@ -38,7 +38,8 @@ class HamBuffers(ctypes.Structure):
         "packed", "losses", "workspace")] + [("workspace_bytes", c_sz), ("dbg_grad", c_p), ("dbg_grad_sh", c_p),
                                              ("ml_vptr", c_p), ("ml_verts", c_p), ("ml_tri2", c_p),
                                              ("n_meshlets", ctypes.c_int32), ("ml_tris", ctypes.c_int32),
-                                             ("ml_max_verts", ctypes.c_int32), ("ml_reserved", ctypes.c_int32)]
+                                             ("ml_max_verts", ctypes.c_int32), ("ml_reserved", ctypes.c_int32),
+                                             ("ml_pos", c_p)]
 
 
 MAX_PEERS = 16

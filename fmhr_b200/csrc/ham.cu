@@ -192,9 +192,22 @@ __global__ void __launch_bounds__(256) ham_vertex_prep_kernel(const float* __res
                                                               const float* __restrict__ w2cs,
                                                               const float* __restrict__ projs,
                                                               const int32_t* __restrict__ view_idx, int n_views,
-                                                              float* __restrict__ viewM) {
+                                                              float* __restrict__ viewM,
+                                                              const int32_t* __restrict__ ml_vptr,
+                                                              const int32_t* __restrict__ ml_verts, int ml_stride,
+                                                              int ml_total, float4* __restrict__ ml_pos) {
     FMHR_TRACE_SCOPE(0);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ml_total) {  // vertices in meshlet order, padded to ml_stride per meshlet (w = 0: the snap rejects the padding)
+        const int m = i / ml_stride, l = i - m * ml_stride;
+        const int vb = __ldg(ml_vptr + m), nv = __ldg(ml_vptr + m + 1) - vb;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < nv) {
+            const size_t k = 3 * (size_t)__ldg(ml_verts + vb + l);
+            p = make_float4(vtmp[k] + delta[k], vtmp[k + 1] + delta[k + 1], vtmp[k + 2] + delta[k + 2], 0.f);
+        }
+        ml_pos[i] = p;
+    }
     if (i < n_views * kViewM) {
         const int n = i >> 4, r = (i >> 2) & 3, j = i & 3;
         const float* Wm = w2cs + (size_t)view_idx[n] * 16;
@@ -294,6 +307,14 @@ __device__ __forceinline__ void ml_resolve(const float4* pos_s, uint2 rec, int p
     atomicMin(&zb[(size_t)py * W + px], ((unsigned long long)depth_key(b.zw) << 32) | rec.y);
 }
 
+// Tile bookkeeping of a fragment: the 16x16 tile's bit in the block-wide shared bitmap (read first: after the first few
+// fragments of a block the bit is set and no atomic is issued).
+__device__ __forceinline__ void ml_mark_tile(unsigned int* tbits, int tiles_x, int px, int py) {
+    const int tile = (py >> 4) * tiles_x + (px >> 4);
+    const unsigned int bit = 1u << (tile & 31);
+    if (!(tbits[tile >> 5] & bit)) atomicOr(tbits + (tile >> 5), bit);
+}
+
 template <typename I>
 __device__ __forceinline__ void ml_cover(int X0, int Y0, int X1, int Y1, int X2, int Y2, int px0, int px1, int py0, int py1,
                                          const float4* pos_s, uint2 rec, int e, int W, float invW, float invH,
@@ -312,12 +333,14 @@ __device__ __forceinline__ void ml_cover(int X0, int Y0, int X1, int Y1, int X2,
         I e2 = dx2 * (I)(Cy - Y0) - dy2 * (I)(Cx0 - X0);
         for (int px = px0; px <= px1; px++) {
             if (e0 + b0 > 0 && e1 + b1 > 0 && e2 + b2 > 0) {
-                const int tile = (py >> 4) * tiles_x + (px >> 4);
-                atomicOr(tbits + (tile >> 5), 1u << (tile & 31));
-                // the ~150-instruction depth resolve runs afterwards with the hits spread over all lanes
+                // the ~150-instruction depth resolve (and the tile bookkeeping) runs afterwards with the hits spread over
+                // all lanes
                 const int q = atomicAdd(qcount, 1);
                 if (q < kFragQueue) queue[q] = make_uint2((uint32_t)e, ((uint32_t)py << 16) | (uint32_t)px);
-                else ml_resolve(pos_s, rec, px, py, W, invW, invH, zb);
+                else {
+                    ml_mark_tile(tbits, tiles_x, px, py);
+                    ml_resolve(pos_s, rec, px, py, W, invW, invH, zb);
+                }
             }
             e0 -= dy0 * 256;
             e1 -= dy1 * 256;
@@ -387,11 +410,11 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned int* tbits = reinterpret_cast<unsigned int*>(snap_s + max_verts);  // block-wide tile bitmap
     __shared__ uint2 cand[kCovThreads / 32][TPT * 32];  // per warp: the triangles whose bounding box holds a pixel centre
+    __shared__ uint32_t cbox[kCovThreads / 32][TPT * 32];  // small-box candidates: px0 | py0 << 14 | wide << 28 | tall << 29
     __shared__ uint2 queue[kCovThreads / 32][kFragQueue];  // per warp: covered pixel centres (candidate index, py << 16 | px)
     __shared__ int qcount[kCovThreads / 32];
     const int m = blockIdx.x, n = blockIdx.y;
     for (int w = threadIdx.x; w < words; w += blockDim.x) tbits[w] = 0u;  // visible after the vertex-phase barrier
-    if (lane == 0) qcount[warp] = 0;
     ViewM Mv;
     if (!CLIP) Mv = load_viewM(viewM + (size_t)n * kViewM);  // uniform loads: L1 broadcast
     // triangle records of this thread: issued before the vertex phase so their latency hides behind it
@@ -399,53 +422,142 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
     const uint2* recs = ml_tri2 + (size_t)m * (TPT * kCovThreads);
 #pragma unroll
     for (int k = 0; k < TPT; k++) rec[k] = __ldg(recs + k * kCovThreads + threadIdx.x);
-    const int vb = __ldg(ml_vptr + m), nv = __ldg(ml_vptr + m + 1) - vb;
     const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-        const size_t gi = (size_t)__ldg(ml_verts + vb + i);
-        const float4 p = CLIP ? __ldg(vg + (size_t)n * clipV + gi) : clip_from_world(Mv.m, __ldg(vg + 2 * gi));
-        pos_s[i] = p;
-        int X = kSnapRejected, Y = 0;
-        if (!snap_vertex(p, hw, hh, X, Y)) X = kSnapRejected;
-        snap_s[i] = make_int2(X, Y);
+    if (CLIP) {
+        const int vb = __ldg(ml_vptr + m), nv = __ldg(ml_vptr + m + 1) - vb;
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+            const float4 p = __ldg(vg + (size_t)n * clipV + (size_t)__ldg(ml_verts + vb + i));
+            pos_s[i] = p;
+            int X = kSnapRejected, Y = 0;
+            if (!snap_vertex(p, hw, hh, X, Y)) X = kSnapRejected;
+            snap_s[i] = make_int2(X, Y);
+        }
+    } else {
+        // fused path: `vg` is the meshlet-ordered, padded copy of the step's vertices (ml_pos, written by the prologue): the
+        // block's loads - triangle records above, these, the view matrix - are all independent of each other
+        const float4* mp = vg + (size_t)m * max_verts;
+        for (int i = threadIdx.x; i < max_verts; i += blockDim.x) {
+            const float4 p = clip_from_world(Mv.m, __ldg(mp + i));
+            pos_s[i] = p;
+            int X = kSnapRejected, Y = 0;
+            if (!snap_vertex(p, hw, hh, X, Y)) X = kSnapRejected;
+            snap_s[i] = make_int2(X, Y);
+        }
     }
     __syncthreads();
-    // stage A: cheap bounding-box test of every triangle (all lanes busy), survivors compacted per warp
-    int nc = 0;  // warp-uniform
+    // stage A: cheap bounding-box test of every triangle (all lanes busy), survivors compacted per warp.  Candidates whose
+    // box holds at most 2 x 2 pixel centres (all but a handful on the subdivided mesh) go to the FRONT of the list with
+    // their box, the others to the back.
+    const unsigned lt = (1u << lane) - 1u;
+    int n1 = 0, nb = 0;  // warp-uniform: small-box candidates (front), big-box candidates (back)
+    const bool res_ok = W <= 16384 && H <= 16384;  // the packed box holds 14-bit pixel coordinates
 #pragma unroll
     for (int k = 0; k < TPT; k++) {
-        bool pass = false;
+        bool pass = false, fast = false;
+        uint32_t box = 0;
         if (rec[k].x != 0xffffffffu) {  // padding
             MlBox bx;
             pass = ml_bbox(snap_s[rec[k].x & 1023u], snap_s[(rec[k].x >> 10) & 1023u], snap_s[(rec[k].x >> 20) & 1023u], H, W, bx);
+            const int wide = bx.px1 - bx.px0, tall = bx.py1 - bx.py0;
+            fast = pass && !DRAIN && bx.small && res_ok && wide <= 1 && tall <= 1;
+            box = (uint32_t)bx.px0 | ((uint32_t)bx.py0 << 14) | ((uint32_t)wide << 28) | ((uint32_t)tall << 29);
         }
-        const unsigned mk = __ballot_sync(0xffffffffu, pass);
-        if (pass) cand[warp][nc + __popc(mk & ((1u << lane) - 1u))] = rec[k];
-        nc += __popc(mk);
+        const unsigned m1 = __ballot_sync(0xffffffffu, fast), mb = __ballot_sync(0xffffffffu, pass && !fast);
+        if (fast) {
+            const int at = n1 + __popc(m1 & lt);
+            cand[warp][at] = rec[k];
+            cbox[warp][at] = box;
+        } else if (pass) cand[warp][TPT * 32 - 1 - nb - __popc(mb & lt)] = rec[k];
+        n1 += __popc(m1);
+        nb += __popc(mb);
     }
     __syncwarp();
-    // stage B: edge functions of the survivors, spread densely over the lanes; hits go to the fragment queue
     unsigned long long* zb = zbuf + (size_t)n * H * W;
-    if (!DRAIN || nc <= 64) {
-        // micropolygons (config 2: ~40 % of a warp's 128 triangles are candidates, ~60 fragments): the queue cannot overflow
-        // by much, no drain logic in the loop
-        for (int e = lane; e < nc; e += 32)
+    // stage B1: small-box candidates, one per lane, straight-line code: the (up to) four pixel centres of the box are
+    // tested against the three 32-bit edge functions at once and the hits are appended to the warp's fragment queue at
+    // positions from a warp prefix sum (no loops over the box, no shared atomics, no divergence).
+    // Orientation: with E_i the edge functions of the ORIGINAL vertex order, the oriented triangle's are s * E_i and its
+    // edge vectors s * (dx_i, dy_i), s = sign(area) (exact in integers: swapping two vertices reverses every edge);
+    // inside <=> s * E_i + owns(s * dx_i, s * dy_i) > 0 for the three edges, as in ml_cover.
+    int qn = 0;  // warp-uniform queue length
+    for (int e0 = 0; e0 < n1; e0 += 32) {  // warp-uniform trip count
+        const int e = e0 + lane;
+        unsigned hits = 0;
+        int px0 = 0, py0 = 0;
+        uint2 r = make_uint2(0u, 0u);
+        if (e < n1) {
+            r = cand[warp][e];
+            const uint32_t box = cbox[warp][e];
+            const int2 s0 = snap_s[r.x & 1023u], s1 = snap_s[(r.x >> 10) & 1023u], s2 = snap_s[(r.x >> 20) & 1023u];
+            px0 = (int)(box & 0x3fffu); py0 = (int)((box >> 14) & 0x3fffu);
+            const int area = (s1.x - s0.x) * (s2.y - s0.y) - (s2.x - s0.x) * (s1.y - s0.y);  // |factors| < 2^15: exact
+            const int sg = area < 0 ? -1 : 1;
+            const int Cx = px0 * 256 + 128, Cy = py0 * 256 + 128;
+            // edges 1->2 (at vertex 1), 2->0 (at vertex 2), 0->1 (at vertex 0), oriented
+            const int dx0 = sg * (s2.x - s1.x), dy0 = sg * (s2.y - s1.y);
+            const int dx1 = sg * (s0.x - s2.x), dy1 = sg * (s0.y - s2.y);
+            const int dx2 = sg * (s1.x - s0.x), dy2 = sg * (s1.y - s0.y);
+            // f_i >= 0 <=> inside w.r.t. edge i (the tie rule folded in: e + owns > 0 <=> e + owns - 1 >= 0)
+            const int f0 = dx0 * (Cy - s1.y) - dy0 * (Cx - s1.x) + (ml_owns_edge(dx0, dy0) ? 0 : -1);
+            const int f1 = dx1 * (Cy - s2.y) - dy1 * (Cx - s2.x) + (ml_owns_edge(dx1, dy1) ? 0 : -1);
+            const int f2 = dx2 * (Cy - s0.y) - dy2 * (Cx - s0.x) + (ml_owns_edge(dx2, dy2) ? 0 : -1);
+            // one pixel to the right: e -= 256 dy; one pixel down: e += 256 dx
+            const int g0 = f0 - 256 * dy0, g1 = f1 - 256 * dy1, g2 = f2 - 256 * dy2;
+            const int ux0 = 256 * dx0, ux1 = 256 * dx1, ux2 = 256 * dx2;
+            const unsigned in00 = ~(unsigned)(f0 | f1 | f2) >> 31;
+            const unsigned in10 = ~(unsigned)(g0 | g1 | g2) >> 31;
+            const unsigned in01 = ~(unsigned)((f0 + ux0) | (f1 + ux1) | (f2 + ux2)) >> 31;
+            const unsigned in11 = ~(unsigned)((g0 + ux0) | (g1 + ux1) | (g2 + ux2)) >> 31;
+            const unsigned wide = (box >> 28) & 1u, tall = (box >> 29) & 1u;
+            hits = in00 | ((in10 & wide) << 1) | ((in01 & tall) << 2) | ((in11 & wide & tall) << 3);
+            if (area == 0) hits = 0;
+        }
+        // exclusive prefix sum of the hit counts over the warp
+        const int cnt = __popc(hits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        int at = qn + incl - cnt;
+        qn += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (hits & (1u << k)) {
+                const int px = px0 + (k & 1), py = py0 + (k >> 1);
+                if (at < kFragQueue) queue[warp][at] = make_uint2((uint32_t)e, ((uint32_t)py << 16) | (uint32_t)px);
+                else {  // (queue full: resolve in place)
+                    ml_mark_tile(tbits, tiles_x, px, py);
+                    ml_resolve(pos_s, r, px, py, W, invW, invH, zb);
+                }
+                at++;
+            }
+        }
+    }
+    if (lane == 0) qcount[warp] = min(qn, kFragQueue);
+    __syncwarp();
+    // stage B2: edge functions of the big-box candidates, spread over the lanes; hits go to the same queue
+    if (!DRAIN || nb <= 64) {
+        for (int e = TPT * 32 - 1 - lane; e >= TPT * 32 - nb; e -= 32)
             ml_candidate(cand[warp][e], e, pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x, &qcount[warp], queue[warp]);
         __syncwarp();
     } else {
         // Triangles of a few pixels (configs 1, 3, 5: nearly every triangle is a candidate) fill the queue long before the
         // candidates run out, and what does not fit is resolved in place at one or two active lanes: drain the queue
         // between rounds whenever the next round might not fit.
-        for (int e0 = 0; e0 < nc; e0 += 32) {  // warp-uniform trip count
-            const int e = e0 + lane;
-            if (e < nc)
+        for (int e0 = 0; e0 < nb; e0 += 32) {  // warp-uniform trip count
+            const int e = TPT * 32 - 1 - (e0 + lane);
+            if (e0 + lane < nb)
                 ml_candidate(cand[warp][e], e, pos_s, snap_s, H, W, invW, invH, zb, tbits, tiles_x, &qcount[warp], queue[warp]);
             __syncwarp();
-            if (e0 + 32 < nc && qcount[warp] > kFragQueue - 96) {
+            if (e0 + 32 < nb && qcount[warp] > kFragQueue - 96) {
                 const int nq0 = min(qcount[warp], kFragQueue);
                 for (int f = lane; f < nq0; f += 32) {
                     const uint2 fr = queue[warp][f];
-                    ml_resolve(pos_s, cand[warp][fr.x], (int)(fr.y & 0xffffu), (int)(fr.y >> 16), W, invW, invH, zb);
+                    const int px = (int)(fr.y & 0xffffu), py = (int)(fr.y >> 16);
+                    ml_mark_tile(tbits, tiles_x, px, py);
+                    ml_resolve(pos_s, cand[warp][fr.x], px, py, W, invW, invH, zb);
                 }
                 __syncwarp();
                 if (lane == 0) qcount[warp] = 0;
@@ -453,11 +565,13 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
             }
         }
     }
-    // stage C: depth resolve of the hits, again with all lanes busy
+    // stage C: tile bookkeeping + depth resolve of the hits, again with all lanes busy
     const int nq = min(qcount[warp], kFragQueue);
     for (int f = lane; f < nq; f += 32) {
         const uint2 fr = queue[warp][f];
-        ml_resolve(pos_s, cand[warp][fr.x], (int)(fr.y & 0xffffu), (int)(fr.y >> 16), W, invW, invH, zb);
+        const int px = (int)(fr.y & 0xffffu), py = (int)(fr.y >> 16);
+        ml_mark_tile(tbits, tiles_x, px, py);
+        ml_resolve(pos_s, cand[warp][fr.x], px, py, W, invW, invH, zb);
     }
     __syncthreads();
     // flush: tiles this block touched first (global bitmap de-duplicates) are appended to the slot's work list
@@ -2198,7 +2312,7 @@ static int ham_check_buffers(const fmhr_ham_config* cfg, const fmhr_ham_buffers*
     FMHR_CHECK_ARG(b->vertices_tmp && b->delta && b->albedo && b->sh_coeffs && b->adam_m && b->adam_v && b->adam_step);
     FMHR_CHECK_ARG(b->imgs && b->masks && b->valid_masks && b->w2cs && b->projs && b->view_idx && b->view_vm2);
     FMHR_CHECK_ARG(b->packed && b->losses && b->workspace);
-    FMHR_CHECK_ARG(b->ml_vptr && b->ml_verts && b->ml_tri2 && b->n_meshlets > 0);
+    FMHR_CHECK_ARG(b->ml_vptr && b->ml_verts && b->ml_tri2 && b->ml_pos && b->n_meshlets > 0);
     FMHR_CHECK_ARG((b->ml_tris == 256 || b->ml_tris == 512 || b->ml_tris == 1024) && b->ml_max_verts > 0 && b->ml_max_verts <= 1024);
     FMHR_CHECK_ARG(b->workspace_bytes >= fmhr_ham_workspace_bytes(cfg));
     FMHR_CHECK_ARG(((uintptr_t)b->packed & 15) == 0 && ((uintptr_t)b->workspace & 255) == 0);
@@ -2396,11 +2510,13 @@ static int launch_coverage(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         }                                                                                                              \
         if (drain)                                                                                                     \
             ham_coverage_meshlet_kernel<TPT, false, true><<<grid, kCovThreads, smem, st>>>(                            \
-                ws.vg, gv.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, gv.zcur,            \
+                (const float4*)b->ml_pos, gv.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH,  \
+                gv.zcur,                                                                                               \
                 gv.tbits[cur], gv.tlist[cur], gv.tcount[cur], tiles_x, tiles_pv, 0);                                   \
         else                                                                                                           \
             ham_coverage_meshlet_kernel<TPT><<<grid, kCovThreads, smem, st>>>(                                         \
-                ws.vg, gv.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH, gv.zcur,            \
+                (const float4*)b->ml_pos, gv.viewM, b->ml_vptr, b->ml_verts, tri2, b->ml_max_verts, H, W, invW, invH,  \
+                gv.zcur,                                                                                               \
                 gv.tbits[cur], gv.tlist[cur], gv.tcount[cur], tiles_x, tiles_pv, 0);                                   \
     } while (0)
     if (b->ml_tris == 1024) FMHR_COVERAGE(1024 / kCovThreads);
@@ -2437,10 +2553,12 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     // zeroed by the prep kernel: packed, loss accumulators + dilated work list (common), the work list of the slot
     // rasterised this step, SH gradients (phase A)
     const int n0 = (int)(ws.common_bytes / 4), n1 = (int)(ws.slot_bytes / 4), n2 = PHASE == 0 ? cfg->n_sh_rows * 9 : 0;
-    const int prep_threads = max(max(3 * V + 1, n * kViewM), max(n0, max(n1, n2)));
+    const int ml_total = b->n_meshlets * b->ml_max_verts;
+    const int prep_threads = max(max(max(3 * V + 1, n * kViewM), max(n0, max(n1, n2))), ml_total);
     ham_vertex_prep_kernel<<<cdiv(prep_threads, 256), 256, 0, st>>>(
         b->vertices_tmp, b->delta, V, ws.vg, (float4*)b->packed, (uint32_t*)ws.common_region, n0,
-        (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->w2cs, b->projs, b->view_idx, n, ws.viewM);
+        (uint32_t*)ws.slot_region[cfg->zbuf_slot], n1, (uint32_t*)ws.gsh, n2, b->w2cs, b->projs, b->view_idx, n, ws.viewM,
+        b->ml_vptr, b->ml_verts, b->ml_max_verts, ml_total, (float4*)b->ml_pos);
     FMHR_LAUNCH_CHECK();
     // The coverage + scan kernels only need the vertices and the view matrices (prep).  Normals -> per-triangle records
     // (needed from the shade pass on) and the regulariser forward / backward + Adam scalars (needed by the update) run on a

@@ -116,6 +116,7 @@ class HamOptimizer:
         self.ml_verts = torch.from_numpy(vrefs).to(dev)
         self.ml_tri2 = torch.from_numpy(tri2.view(np.int32)).to(dev)
         self.n_meshlets, self.ml_max_verts = nm.value, mv.value
+        self.ml_pos = torch.zeros(nm.value * mv.value, 4, dtype=torch.float32, device=dev)  # meshlet-ordered vertices (scratch)
 
     # ------------------------------------------------------------------ initialisation (mesh_sfs_optim.py:124-177)
     def initialise(self, grayimgs):
@@ -199,6 +200,7 @@ class HamOptimizer:
         b.v2f_nbr, b.inv_deg = ptr(t.v2f_nbr), ptr(t.inv_deg)
         b.ml_vptr, b.ml_verts, b.ml_tri2 = ptr(self.ml_vptr), ptr(self.ml_verts), ptr(self.ml_tri2)
         b.n_meshlets, b.ml_tris, b.ml_max_verts = self.n_meshlets, self.MESHLET_TRIS, self.ml_max_verts
+        b.ml_pos = ptr(self.ml_pos)
         b.vertices_tmp, b.delta, b.albedo, b.sh_coeffs = ptr(self.vertices_tmp), ptr(self.delta), ptr(self.albedo), ptr(self.sh_coeffs)
         b.adam_m, b.adam_v, b.adam_step = ptr(self.adam_m), ptr(self.adam_v), ptr(self.adam_step)
         b.imgs = ptr(self.imgs if imgs is None else imgs)

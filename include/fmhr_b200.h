@@ -210,6 +210,10 @@ typedef struct fmhr_ham_buffers {
     int32_t ml_tris;           /* triangles per meshlet (multiple of 256, <= 1024) */
     int32_t ml_max_verts;      /* largest meshlet vertex count (<= 1024) */
     int32_t ml_reserved;
+    /* caller-owned scratch [n_meshlets * ml_max_verts] float4: the step's world-space vertices in MESHLET order (written by
+     * the prologue kernel, padded per meshlet), so a coverage block fetches its vertices with independent coalesced loads
+     * instead of the vptr -> index -> record chain */
+    float* ml_pos;
 } fmhr_ham_buffers;
 
 size_t fmhr_ham_workspace_bytes(const fmhr_ham_config* cfg);

@@ -234,7 +234,13 @@ class _RasterizeFunc(torch.autograd.Function):
 
 
 def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
-    """-> (rast[N,H,W,4] = (u, v, z/w, triangle_id+1), rast_db[N,H,W,4])."""
+    """-> (rast[N,H,W,4] = (u, v, z/w, triangle_id+1), rast_db[N,H,W,4]).
+
+    Limitation (rule 1): a triangle with ANY vertex at w <= 0, outside -w <= z <= w, or outside the
+    +-16384 px guard band is dropped as a whole - upstream nvdiffrast clips such triangles against the view volume.  The
+    reference's cameras never produce one (projection z' = -0.1, w' = z_cam with the hand ~1.9 units away,
+    get_data.py:66-73), but a caller whose geometry crosses the near plane gets holes, not clipped triangles
+    (pinned by tests/test_gpu_ops.py::test_rasterize_drops_triangles_crossing_the_near_plane)."""
     if not isinstance(glctx, RasterizeCudaContext):
         raise RuntimeError("fmhr_b200.rasterize: glctx must be a RasterizeGLContext / RasterizeCudaContext")
     if ranges is not None:

@@ -123,6 +123,23 @@ def test_rasterize_known_answers(dr):
         assert torch.equal(rr.cpu(), ref)
 
 
+def test_rasterize_drops_triangles_crossing_the_near_plane(dr):
+    """Documented limitation of the shim (dr.rasterize docstring, DESIGN.md section 2 rule 1): a triangle with one vertex
+    behind the near plane (z < -w) or the eye (w <= 0) is dropped as a whole, where upstream nvdiffrast would clip it.
+    The same triangle pulled fully inside the volume is drawn; the oracle follows the same rule."""
+    H = W = 16
+    inside = [[-0.5, -0.5, 0.0, 1.0], [0.5, -0.5, 0.0, 1.0], [0.0, 0.5, 0.0, 1.0]]
+    for bad in ([0.0, 0.5, -2.0, 1.0], [0.0, 0.5, 0.0, -0.5]):   # z < -w (crosses the near plane); w <= 0 (behind the eye)
+        pos = torch.tensor([inside[:2] + [bad]], dtype=torch.float32)
+        tri = torch.tensor([[0, 1, 2]], dtype=torch.int32)
+        rast, _ = dr.rasterize(dr.RasterizeGLContext(), pos.cuda(), tri.cuda(), resolution=(H, W))
+        assert int((rast[..., 3] > 0).sum()) == 0
+        ref, _, _ = orc.rasterize_fwd(pos, tri, (H, W), want_db=False)
+        assert torch.equal(rast.cpu(), ref)
+    rast, _ = dr.rasterize(dr.RasterizeGLContext(), torch.tensor([inside]).cuda(), tri.cuda(), resolution=(H, W))
+    assert int((rast[..., 3] > 0).sum()) > 20
+
+
 def test_rasterize_backward(dr):
     pos, tri, H, W = _scene("small")
     rast_ref, _, _ = orc.rasterize_fwd(pos, tri, (H, W))
@@ -286,3 +303,31 @@ def test_mlp_forward_geometry_stage_on_the_shim(dr):
     assert torch.equal(m_gpu[..., 0] > 0, r_ref[..., 3] > 0), "the reference selects pixels with masks[..., 0] > 0"
     assert torch.allclose(f_gpu, f_ref, rtol=1e-5, atol=2e-6)
     assert _rel(g_gpu, g_ref) < 1e-4
+
+
+def test_interhand_rendered_mask_step_on_the_shim(dr):
+    """get_interhand_data's mask step (get_data.py:246-254) - the segmentation of an InterHand capture is
+    the rendered coverage of the fitted MANO mesh: rasterize, interpolate a ones attribute (A = 1), squeeze - line for line
+    on the CUDA shim and on the CPU oracle; the two einsums run once so that both sides rasterise the same positions."""
+    wl = synth.WORKLOADS["small"]
+    v, f = synth.hand_mesh(wl["subdiv"], 1, seed=0)
+    num, res = wl["n"], (wl["W"], wl["H"])   # the loader's `res` is (w, h)
+    w2c, proj = synth.make_cameras(num, wl["H"], wl["W"], v.mean(0).astype(np.float64),
+                                   extent=float(v[:, 1].max() - v[:, 1].min()))
+    vertices, faces = torch.tensor(v)[None], torch.tensor(f)
+    w2cs, projs = torch.tensor(w2c), torch.tensor(proj)
+    vertsw = torch.cat([vertices, torch.ones_like(vertices[:, :, 0:1])], axis=2).expand(num, -1, -1)
+    rot_verts = torch.einsum('ijk,ikl->ijl', vertsw, w2cs)
+    proj_verts = torch.einsum('ijk,ikl->ijl', rot_verts, projs)
+
+    def masks_of(drmod, dev):
+        glctx = drmod.RasterizeGLContext()
+        rast_out, _ = drmod.rasterize(glctx, proj_verts.to(dev), faces.to(dev), resolution=(res[1], res[0]))
+        feat = torch.ones_like(vertsw[:, :, :1]).to(dev)   # an expanded (stride-0) view, as in the loader
+        feat, _ = drmod.interpolate(feat, rast_out, faces.to(dev))
+        return feat[:, :, :, :1].contiguous().squeeze(-1).cpu()
+
+    ref, ours = masks_of(orc, "cpu"), masks_of(dr, "cuda")
+    assert ours.shape == (num, wl["H"], wl["W"]) and (ref > 0).float().mean() > 0.02
+    assert torch.equal(ours > 0, ref > 0)
+    assert float((ours - ref).abs().max()) <= 2e-6   # u + v + (1 - u - v) of a ones attribute

@@ -2364,6 +2364,86 @@ __global__ void __launch_bounds__(256) ham_pull_boxes_kernel(const uint8_t* __re
     }
 }
 
+// Converted-on-arrival form: the same row pull, but every 16-byte chunk is written as 16 floats into the planes the
+// kernels read (img = u8 / 255 with one IEEE divide per byte, mask = u8 > 127: bit-identical to ham_u8_to_f32_kernel; the
+// byte index of the u8 planes IS the float index of the f32 planes).  blockIdx.x == gridDim.x - 1 of view 0 also pulls the
+// step's cameras.  Chunks are aligned down / up to 16 bytes: the extra bytes are genuine neighbours (mask bytes outside a
+// box are <= 127 by the definition of the box, so they convert to the 0 the plane already holds).
+__device__ __forceinline__ void st_u8x16_as_f32(float* dst, uint4 v, bool mask) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t b0 = w[k] & 255u, b1 = (w[k] >> 8) & 255u, b2 = (w[k] >> 16) & 255u, b3 = w[k] >> 24;
+        float4 f;
+        if (mask) f = make_float4(b0 > 127u ? 1.f : 0.f, b1 > 127u ? 1.f : 0.f, b2 > 127u ? 1.f : 0.f, b3 > 127u ? 1.f : 0.f);
+        else f = make_float4(__fdiv_rn((float)b0, 255.0f), __fdiv_rn((float)b1, 255.0f), __fdiv_rn((float)b2, 255.0f),
+                             __fdiv_rn((float)b3, 255.0f));
+        reinterpret_cast<float4*>(dst)[k] = f;
+    }
+}
+// Footprint: the pull runs BESIDE the step's pixel passes for ~100 us (PCIe-bound), so it must not take their SM slots -
+// blocks of 128 threads, two per view (<= one small block per SM; with 8 x 256-thread blocks per view the shade pass lost
+// half of its occupancy and ran 2.4x longer).  Two rows per warp iteration keep ~0.8 MB of reads in flight.
+constexpr int kPullThreads = 128, kPullBlocksPerView = 2;
+__global__ void __launch_bounds__(kPullThreads) ham_pull_boxes_f32_kernel(const uint8_t* __restrict__ imgs_host,
+                                                                        const uint8_t* __restrict__ masks_host,
+                                                                        const int4* __restrict__ boxes, int H, int W,
+                                                                        float* __restrict__ imgs, float* __restrict__ masks,
+                                                                        const float* __restrict__ w2cs_host,
+                                                                        const float* __restrict__ projs_host,
+                                                                        float* __restrict__ w2cs, float* __restrict__ projs,
+                                                                        int n_cam_floats) {
+    const int v = blockIdx.y;
+    if (v == 0 && blockIdx.x == gridDim.x - 1) {
+        for (int i = threadIdx.x; i < n_cam_floats; i += blockDim.x) {
+            float a, b;
+            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(a) : "l"(w2cs_host + i) : "memory");
+            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(b) : "l"(projs_host + i) : "memory");
+            w2cs[i] = a;
+            projs[i] = b;
+        }
+    }
+    const int4 b = boxes[v];  // y0, y1, x0, x1
+    if (b.y <= b.x || b.w <= b.z) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    const size_t width = (size_t)(b.w - b.z);
+    for (int r = b.x + warp; r < b.y; r += 2 * nw) {
+        const bool two = r + nw < b.y;
+        const size_t p0 = ((size_t)v * H + r) * W + b.z, q0 = p0 + (size_t)nw * W;
+        if (3 * width <= 1024 - 16) {
+            // common case: an image row segment fits two 512-byte warp accesses and its mask segment one - all (up to) six
+            // loads of the two rows are in flight before the first store
+            const size_t ci = ((3 * p0) & ~(size_t)15) + 16 * (size_t)lane, cm = (p0 & ~(size_t)15) + 16 * (size_t)lane;
+            const size_t di = ((3 * q0) & ~(size_t)15) + 16 * (size_t)lane, dm = (q0 & ~(size_t)15) + 16 * (size_t)lane;
+            const size_t ei = 3 * (p0 + width), fi = 3 * (q0 + width);
+            const bool l0 = ci < ei, l1 = ci + 512 < ei, lm = cm < p0 + width;
+            const bool k0 = two && di < fi, k1 = two && di + 512 < fi, km = two && dm < q0 + width;
+            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0;
+            if (l0) a0 = ld_host16(imgs_host + ci);
+            if (l1) a1 = ld_host16(imgs_host + ci + 512);
+            if (lm) a2 = ld_host16(masks_host + cm);
+            if (k0) a3 = ld_host16(imgs_host + di);
+            if (k1) a4 = ld_host16(imgs_host + di + 512);
+            if (km) a5 = ld_host16(masks_host + dm);
+            if (l0) st_u8x16_as_f32(imgs + ci, a0, false);
+            if (l1) st_u8x16_as_f32(imgs + ci + 512, a1, false);
+            if (lm) st_u8x16_as_f32(masks + cm, a2, true);
+            if (k0) st_u8x16_as_f32(imgs + di, a3, false);
+            if (k1) st_u8x16_as_f32(imgs + di + 512, a4, false);
+            if (km) st_u8x16_as_f32(masks + dm, a5, true);
+        } else {
+            for (int k = 0; k < (two ? 2 : 1); k++) {
+                const size_t s0 = k ? q0 : p0, s1 = s0 + width;
+                for (size_t c = ((3 * s0) & ~(size_t)15) + 16 * (size_t)lane; c < 3 * s1; c += 512)
+                    st_u8x16_as_f32(imgs + c, ld_host16(imgs_host + c), false);
+                for (size_t c = (s0 & ~(size_t)15) + 16 * (size_t)lane; c < s1; c += 512)
+                    st_u8x16_as_f32(masks + c, ld_host16(masks_host + c), true);
+            }
+        }
+    }
+}
+
 // Side stream for work that is independent of the rendering chain (forked / joined with events, so it is captured into
 // the same CUDA graph when the caller's stream is being captured).
 struct BoxGraph {
@@ -3256,6 +3336,62 @@ extern "C" int fmhr_ham_host_u8_submit_boxes(const fmhr_ham_config* cfg, const u
     return FMHR_OK;
 }
 
+extern "C" int fmhr_ham_host_u8_submit_boxes_direct(const fmhr_ham_config* cfg, const uint8_t* imgs_host,
+                                                    const uint8_t* masks_host, const int32_t* boxes_host,
+                                                    const float* w2cs_host, const float* projs_host, float* imgs_dev,
+                                                    float* masks_dev, float* w2cs_dev, float* projs_dev,
+                                                    size_t* h2d_bytes) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(imgs_host && masks_host && boxes_host && w2cs_host && projs_host && imgs_dev && masks_dev && w2cs_dev &&
+                   projs_dev);
+    FMHR_CHECK_ARG((((uintptr_t)imgs_dev | (uintptr_t)masks_dev) & 15) == 0);
+    const int n = cfg->n_views, H = cfg->H, W = cfg->W;
+    const size_t P = (size_t)n * H * W;
+    for (int v = 0; v < n; v++) {
+        const int32_t* b = boxes_host + 4 * v;
+        FMHR_CHECK_ARG(b[0] >= 0 && b[1] <= H && b[2] >= 0 && b[3] <= W);
+    }
+    void *d_imgs = nullptr, *d_masks = nullptr, *d_w2cs = nullptr, *d_projs = nullptr;
+    const bool can_pull = (P % 16 == 0) && (((uintptr_t)imgs_host | (uintptr_t)masks_host) & 15) == 0 &&
+                          cudaHostGetDevicePointer(&d_imgs, (void*)imgs_host, 0) == cudaSuccess &&
+                          cudaHostGetDevicePointer(&d_masks, (void*)masks_host, 0) == cudaSuccess &&
+                          cudaHostGetDevicePointer(&d_w2cs, (void*)w2cs_host, 0) == cudaSuccess &&
+                          cudaHostGetDevicePointer(&d_projs, (void*)projs_host, 0) == cudaSuccess;
+    if (!can_pull) {
+        cudaGetLastError();
+        set_error("fmhr_ham_host_u8_submit_boxes_direct: needs device-mapped, 16-byte aligned pinned host buffers and "
+                  "n*H*W %% 16 == 0; use fmhr_ham_host_u8_submit_boxes");
+        return FMHR_EUNSUPPORTED;
+    }
+    SideStream* side = nullptr;
+    rc = side_stream(&side);
+    if (rc) return rc;
+    int slot = -1;
+    rc = submit_slot(side, imgs_dev, "fmhr_ham_host_u8_submit_boxes_direct", &slot);
+    if (rc) return rc;
+    size_t bytes = (size_t)n * 32 * sizeof(float);
+    for (int v = 0; v < n; v++) {
+        const int32_t* b = boxes_host + 4 * v;
+        if (b[1] > b[0] && b[3] > b[2]) bytes += (size_t)(b[1] - b[0]) * (size_t)(b[3] - b[2]) * 4;
+    }
+    if (side->box_cap[slot] < n) {
+        if (side->box_dev[slot]) FMHR_CUDA(cudaFree(side->box_dev[slot]));
+        side->box_dev[slot] = nullptr;
+        FMHR_CUDA(cudaMalloc(&side->box_dev[slot], (size_t)n * sizeof(int4)));
+        side->box_cap[slot] = n;
+    }
+    FMHR_CUDA(cudaMemcpyAsync(side->box_dev[slot], boxes_host, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, side->copy));
+    FMHR_CUDA(cudaMemsetAsync(masks_dev, 0, P * sizeof(float), side->copy));
+    ham_pull_boxes_f32_kernel<<<dim3(kPullBlocksPerView, n), kPullThreads, 0, side->copy>>>(
+        (const uint8_t*)d_imgs, (const uint8_t*)d_masks, side->box_dev[slot], H, W, imgs_dev, masks_dev, (const float*)d_w2cs,
+        (const float*)d_projs, w2cs_dev, projs_dev, n * 16);
+    FMHR_LAUNCH_CHECK();
+    FMHR_CUDA(cudaEventRecord(side->slot_ready[slot], side->copy));
+    if (h2d_bytes) *h2d_bytes = bytes;
+    return FMHR_OK;
+}
+
 // The submitted-batch step in three parts, so that a host can capture the device work (body) into a CUDA graph while the
 // cross-stream handshakes with the copy stream (acquire / release) stay ordinary stream operations around the replay.
 static int submitted_slot(SideStream* side, const void* staging, const char* who) {
@@ -3285,14 +3421,19 @@ extern "C" int fmhr_ham_step_host_u8_body(const fmhr_ham_config* cfg, const fmhr
     if (rc) return rc;
     rc = ham_check_buffers(cfg, buf);
     if (rc) return rc;
-    FMHR_CHECK_ARG(w2cs_host && projs_host && staging && losses_host);
+    FMHR_CHECK_ARG(staging && losses_host);
+    // converted-on-arrival batches (fmhr_ham_host_u8_submit_boxes_direct): the planes and cameras `buf` names ARE the batch
+    const bool direct = staging == (const void*)buf->imgs;
+    FMHR_CHECK_ARG(direct ? (!w2cs_host && !projs_host) : (w2cs_host && projs_host));
     FMHR_CHECK_ARG(((uintptr_t)buf->imgs & 15) == 0 && ((uintptr_t)buf->masks & 15) == 0);
     FMHR_CHECK_ARG(((size_t)cfg->n_views * cfg->H * cfg->W) % 4 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = cfg->n_views;
-    FMHR_CUDA(cudaMemcpyAsync((void*)buf->w2cs, w2cs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
-    FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
-    g_pending.staging = (const uint8_t*)staging;
+    if (!direct) {
+        FMHR_CUDA(cudaMemcpyAsync((void*)buf->w2cs, w2cs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+        FMHR_CUDA(cudaMemcpyAsync((void*)buf->projs, projs_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    g_pending.staging = direct ? nullptr : (const uint8_t*)staging;
     g_pending.ready = nullptr;     // acquire ordered the stream behind the upload
     g_pending.consumed = nullptr;  // release frees the buffer
     rc = fmhr_ham_step_render(cfg, buf, stream);

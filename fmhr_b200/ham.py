@@ -514,10 +514,13 @@ class HostStreamingStepper:
                 out[v] = (ys[0], ys[-1] + 1, xs[0], xs[-1] + 1)
         return torch.from_numpy(out)
 
-    def submit_u8(self, h_imgs_u8, h_masks_u8, boxes=None):
+    def submit_u8(self, h_imgs_u8, h_masks_u8, boxes=None, cameras=None):
         """Start the upload of a host batch (pinned uint8 images [n,H,W,3] / masks [n,H,W]) into the next free staging
         buffer; returns a ticket for step_submitted_u8.  At most two batches may be in flight.  boxes (mask_boxes(): int32
-        CPU tensor [n,4]) restricts the transfer to the rectangle of every view that holds its segmentation."""
+        CPU tensor [n,4]) restricts the transfer to the rectangle of every view that holds its segmentation.
+        cameras = (h_w2cs, h_projs) (pinned float32 [n,4,4], with boxes): converted-on-arrival form - the pull kernel writes
+        float planes of the ticket's own plane set and the cameras travel with the batch, so the step itself uploads and
+        converts nothing (fmhr_ham_host_u8_submit_boxes_direct); step_submitted_u8 is then called with h_w2cs = h_projs = None."""
         o = self.opt
         for t in (h_imgs_u8, h_masks_u8):
             if t.is_cuda or not t.is_contiguous() or t.dtype != torch.uint8 or not t.is_pinned():
@@ -525,6 +528,30 @@ class HostStreamingStepper:
         cfg = self.__dict__.get("_submit_cfg")
         if cfg is None:
             cfg = self._submit_cfg = o._cfg(self.n, 1, None)
+        if cameras is not None:
+            if boxes is None:
+                raise RuntimeError("HostStreamingStepper: the converted-on-arrival form needs the segmentation boxes")
+            h_w2cs, h_projs = cameras
+            for t in (h_w2cs, h_projs):
+                if t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or not t.is_pinned():
+                    raise RuntimeError("HostStreamingStepper: cameras must be pinned, contiguous float32 CPU tensors")
+            if boxes.is_cuda or boxes.dtype != torch.int32 or tuple(boxes.shape) != (self.n, 4) or not boxes.is_contiguous():
+                raise RuntimeError("HostStreamingStepper: boxes must be a contiguous int32 CPU tensor [n,4]")
+            if getattr(self, "_planes", None) is None:
+                mk = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=o.device)
+                self._planes = [(mk(self.n, o.H, o.W, 3), mk(self.n, o.H, o.W), mk(self.n, 4, 4), mk(self.n, 4, 4))
+                                for _ in range(2)]
+                self._next_plane = 0
+            slot = self._next_plane
+            self._next_plane ^= 1
+            pl = self._planes[slot]
+            nb = _lib.c_sz(0)
+            with torch.cuda.device(o.device):
+                check(o.lib.fmhr_ham_host_u8_submit_boxes_direct(
+                    ctypes.byref(cfg), ptr(h_imgs_u8), ptr(h_masks_u8), ptr(boxes), ptr(h_w2cs), ptr(h_projs), ptr(pl[0]),
+                    ptr(pl[1]), ptr(pl[2]), ptr(pl[3]), ctypes.byref(nb)), "ham_host_u8_submit_boxes_direct")
+            self.last_submit_bytes = int(nb.value)
+            return ("direct", slot)
         if getattr(self, "_stagings", None) is None:
             nbytes = o.lib.fmhr_ham_host_u8_staging_bytes(ctypes.byref(cfg))
             self._stagings = [torch.empty(nbytes, dtype=torch.uint8, device=o.device) for _ in range(2)]
@@ -546,13 +573,32 @@ class HostStreamingStepper:
                 self.last_submit_bytes = int(nb.value)
         return slot
 
-    def step_submitted_u8(self, ticket, h_w2cs, h_projs, sh_rows, albedo_weight=None):
+    def step_submitted_u8(self, ticket, h_w2cs, h_projs, sh_rows, albedo_weight=None, async_record=False):
         """The iteration on the batch submitted under `ticket` (cameras: pinned float32 [n,4,4]).  With use_graphs (the
         optimiser's setting) the device work - camera upload, conversion, render, update, loss read-back - is captured
         once per (staging buffer, z-buffer slot, host pointers) and replayed with one launch; the handshakes with the copy
-        stream stay outside the graph (fmhr_ham_step_host_u8_acquire / _release)."""
+        stream stay outside the graph (fmhr_ham_step_host_u8_acquire / _release).
+
+        async_record=True: the step's loss record is copied into slot `ticket` of a two-slot pinned ring and an event is
+        recorded behind it; nothing waits here.  read_record(ticket) returns it later (typically one step late, after the
+        next step has been launched), so the host never stalls the device between steps - the reference's per-iteration
+        `.item()` (mesh_sfs_optim.py:312) only feeds a progress bar."""
         o = self.opt
-        for t in (h_w2cs, h_projs):
+        direct = isinstance(ticket, tuple)
+        planes = None
+        if direct:
+            ticket = ticket[1]
+            planes = self._planes[ticket]
+            if h_w2cs is not None or h_projs is not None:
+                raise RuntimeError("HostStreamingStepper: the cameras of a converted-on-arrival batch travelled with submit_u8")
+        if async_record:
+            if getattr(self, "_ring", None) is None:
+                self._ring = torch.zeros(2, 8, dtype=torch.float32).pin_memory()
+                self._ring_events = [torch.cuda.Event(), torch.cuda.Event()]
+            record = self._ring[ticket]
+        else:
+            record = self.losses_host
+        for t in (() if direct else (h_w2cs, h_projs)):
             if t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or not t.is_pinned():
                 raise RuntimeError("HostStreamingStepper: cameras must be pinned, contiguous float32 CPU tensors")
         if o.phase != 1:
@@ -562,18 +608,18 @@ class HostStreamingStepper:
         # the per-step Python work is on the critical path (the loss record is read back after every step): the
         # configuration / buffer structs are built once per (albedo_weight, SH rows, workspace)
         ckey = (None if albedo_weight is None else float(albedo_weight), sh_rows.data_ptr(),
-                0 if o.workspace is None else o.workspace.data_ptr())
+                0 if o.workspace is None else o.workspace.data_ptr(), ticket if direct else -1)
         cache = self.__dict__.setdefault("_struct_cache", {})
         cb = cache.get(ckey)
         if cb is None or cb[2] != (0 if o.workspace is None else o.workspace.data_ptr()):
             cfg = o._cfg(self.n, 1, albedo_weight)
-            buf = o._buffers(cfg, self.rows, self.d_imgs, self.d_masks, self.d_valid, self.d_w2cs, self.d_projs, sh_rows,
-                             self.d_vm2)
+            src = planes if direct else (self.d_imgs, self.d_masks, self.d_w2cs, self.d_projs)
+            buf = o._buffers(cfg, self.rows, src[0], src[1], self.d_valid, src[2], src[3], sh_rows, self.d_vm2)
             if len(cache) > 32:
                 cache.clear()
-            cb = cache[(ckey[0], ckey[1], o.workspace.data_ptr())] = (cfg, buf, o.workspace.data_ptr(), sh_rows)
+            cb = cache[(ckey[0], ckey[1], o.workspace.data_ptr(), ckey[3])] = (cfg, buf, o.workspace.data_ptr(), sh_rows)
         cfg, buf = cb[0], cb[1]
-        staging = self._stagings[ticket]
+        staging = planes[0] if direct else self._stagings[ticket]
         with torch.cuda.device(o.device):
             o._prepare_zbuf(cfg, buf)
             peers = None
@@ -581,14 +627,15 @@ class HostStreamingStepper:
                 buf.packed = o.peer.packed[cfg.zbuf_slot].data_ptr()
                 peers = ctypes.byref(o.peer.structs[cfg.zbuf_slot])
             body = lambda sp: check(o.lib.fmhr_ham_step_host_u8_body(
-                ctypes.byref(cfg), ctypes.byref(buf), ptr(h_w2cs), ptr(h_projs), ptr(staging), ptr(self.losses_host), peers,
+                ctypes.byref(cfg), ctypes.byref(buf), ptr(h_w2cs), ptr(h_projs), ptr(staging), ptr(record), peers,
                 sp), "ham_step_host_u8_body")
             check(o.lib.fmhr_ham_step_host_u8_acquire(ptr(staging), stream()), "ham_step_host_u8_acquire")
             if not o.use_graphs:
                 body(stream())
             else:
-                key = (ticket, cfg.zbuf_slot, h_w2cs.data_ptr(), h_projs.data_ptr(), sh_rows.data_ptr(),
-                       None if albedo_weight is None else float(albedo_weight), o.workspace.data_ptr())
+                key = (ticket, direct, cfg.zbuf_slot, 0 if direct else h_w2cs.data_ptr(), 0 if direct else h_projs.data_ptr(),
+                       sh_rows.data_ptr(),
+                       None if albedo_weight is None else float(albedo_weight), o.workspace.data_ptr(), record.data_ptr())
                 graphs = self.__dict__.setdefault("_step_graphs", {})
                 gr = graphs.get(key)
                 if gr is None:
@@ -604,4 +651,11 @@ class HostStreamingStepper:
                     graphs[key] = gr
                 gr.replay()
             check(o.lib.fmhr_ham_step_host_u8_release(ptr(staging), stream()), "ham_step_host_u8_release")
-        return self.losses_host
+            if async_record:
+                self._ring_events[ticket].record(torch.cuda.current_stream(o.device))
+        return record
+
+    def read_record(self, ticket):
+        """Loss record of the step launched with async_record=True under `ticket` (waits for THAT step only)."""
+        self._ring_events[ticket].synchronize()
+        return self._ring[ticket].clone()

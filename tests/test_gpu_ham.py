@@ -397,6 +397,79 @@ def test_host_streaming_u8_step_matches_resident(scene):
         stepper.step_phase_b_u8(h[0].float().pin_memory(), h[1], h[2], h[3], views)
 
 
+@pytest.mark.parametrize("graphs,direct", [(False, False), (True, False), (False, True), (True, True)])
+def test_host_streaming_async_loss_ring(scene, graphs, direct):
+    """step_submitted_u8(async_record=True): the loss record of step i lands in slot i % 2 of a pinned ring and is read on
+    the host one step late, after step i + 1 has been launched (no device drain between steps).  Every record must equal
+    the one the synchronous form returns for the same step, in order.
+    direct: converted-on-arrival batches (submit_u8(cameras=...) -> fmhr_ham_host_u8_submit_boxes_direct): the pull kernel
+    writes the ticket's own float planes and the cameras travel with the batch; the planes are poisoned first (mask plane
+    with ones, image plane with NaN), and the records must equal the resident path's."""
+    import copy
+    from fmhr_b200.ham import HostStreamingStepper
+    n, H, W = scene["imgs"].shape[0], scene["imgs"].shape[1], scene["imgs"].shape[2]
+    if (n * H * W) % 4:
+        pytest.skip("u8 path needs n*H*W % 4 == 0")
+    img_a = np.clip(np.rint(np.asarray(scene["imgs"], dtype=np.float64) * 255.0), 0, 255).astype(np.uint8)
+    img_b = (img_a // 2 + 17).astype(np.uint8)
+    msk_u8 = (np.asarray(scene["masks"]) > 0).astype(np.uint8) * 255
+    q = copy.copy(scene)
+    q["imgs"] = img_a.astype(np.float32) / np.float32(255.0)
+    q["masks"] = (msk_u8 > 127).astype(np.float32)
+    pin = lambda x, dt: torch.tensor(x, dtype=dt).contiguous().pin_memory()
+    h_imgs = [pin(img_a, torch.uint8), pin(img_b, torch.uint8)]
+    h_msk, h_w2c, h_proj = pin(msk_u8, torch.uint8), pin(scene["w2cs"], torch.float32), pin(scene["projs"], torch.float32)
+    views = torch.arange(n, dtype=torch.int32, device="cuda")
+    boxes = HostStreamingStepper.mask_boxes(msk_u8)
+    steps = 6
+
+    def run(async_record):
+        o = _make_opt(q, debug=False)
+        o.use_graphs = graphs
+        st = HostStreamingStepper(o, n)
+        st.set_resident_valid_masks(o.valid_masks)
+        out, inflight = [], []
+        cams = (h_w2c, h_proj) if direct else None
+        slot_of = lambda t: t[1] if isinstance(t, tuple) else t
+        ticket = st.submit_u8(h_imgs[0], h_msk, boxes, cameras=cams)
+        if direct:  # poison both plane sets, then submit again (into the other set)
+            torch.cuda.synchronize()
+            for pl in st._planes:
+                pl[0].fill_(float("nan")); pl[1].fill_(1.0); pl[2].fill_(float("nan")); pl[3].fill_(float("nan"))
+            torch.cuda.synchronize()
+            ticket = st.submit_u8(h_imgs[0], h_msk, boxes, cameras=cams)
+        for i in range(steps):
+            nxt = st.submit_u8(h_imgs[(i + 1) % 2], h_msk, boxes, cameras=cams) if i + 1 < steps else None
+            rec = st.step_submitted_u8(ticket, None if direct else h_w2c, None if direct else h_proj, views,
+                                       async_record=async_record)
+            if async_record:
+                if inflight:
+                    out.append(st.read_record(inflight.pop(0)))
+                inflight.append(slot_of(ticket))
+            else:
+                torch.cuda.synchronize()
+                out.append(rec.clone())
+            ticket = nxt
+        while inflight:
+            out.append(st.read_record(inflight.pop(0)))
+        return torch.stack(out), o.delta.clone()
+
+    sync_recs, sync_delta = run(False)
+    ring_recs, ring_delta = run(True)
+    if direct:  # against the resident path on the same quantised batches
+        a = _make_opt(q, debug=False)
+        f_imgs = [torch.tensor(x.astype(np.float32) / np.float32(255.0)).cuda() for x in (img_a, img_b)]
+        res = []
+        for i in range(steps):
+            a.imgs.copy_(f_imgs[i % 2])
+            res.append(a.step_phase_b(views).cpu())
+        assert torch.allclose(torch.stack(res), sync_recs, rtol=1e-4, atol=1e-6), (torch.stack(res), sync_recs)
+    assert ring_recs.shape == (steps, 8) and torch.isfinite(ring_recs).all()
+    assert torch.allclose(ring_recs, sync_recs, rtol=1e-4, atol=1e-6), (ring_recs, sync_recs)
+    assert float((sync_recs[1:, 0] - sync_recs[:-1, 0]).abs().min()) > 0, "consecutive steps must have different records"
+    assert _traj_close(ring_delta, sync_delta, scene["conf"]["lr"])
+
+
 @pytest.mark.parametrize("use_boxes", [False, "pull", "dma"])
 def test_host_streaming_u8_pipelined_matches_resident(scene, use_boxes, monkeypatch):
     """fmhr_ham_host_u8_submit / fmhr_ham_step_host_u8_submitted: the batch of step i+1 is uploaded while step i runs, two

@@ -119,6 +119,8 @@ def test_stage2_iteration_on_the_shim():
     from fmhr_b200 import utils as futils
     g = np.load(GOLDEN)
     dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = False          # the stand-in convolutions must be fp32 on both sides
+    torch.backends.cuda.matmul.allow_tf32 = False
     nets = gu.standin_nets()
     nets = tuple(m.to(dev) for m in nets)
     fwd = unet_forward_lines(dr, futils.get_normals, [torch.tensor(g["uni_vertices_0"]), torch.tensor(g["uni_vertices_1"])],

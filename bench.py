@@ -58,8 +58,10 @@ def stage_bytes(stage, n, H, W, V, F):
 
 def measured_traffic():
     """DRAM bytes per iteration (dram__bytes_read.sum + dram__bytes_write.sum over the iteration's kernels) from the
-    committed ncu capture of this command, profiles/r1_traffic.json (written by tools/ncu_launch_table.py)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    committed ncu capture of this command, profiles/r2/traffic.json (written by tools/ncu_launch_table.py)."""
+    p = os.path.join(ROOT, "profiles", "r2", "traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
         return json.load(open(p))
     except Exception:

@@ -62,5 +62,37 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_variant(name, defines):
+    """Diagnostic / tuning build of the same sources with extra -D flags -> <repo>/variants/libfmhr_<name>.so (git-ignored;
+    selected with FMHR_B200_LIB).  Rebuilt only when a source is newer."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "variants", "libfmhr_%s.so" % name)
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(root, "include", "fmhr_b200.h"))
+    if not _stale(out, srcs + headers):
+        return out
+    objdir = os.path.join(root, "variants", "obj_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+
+    def run(src):
+        obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
+        r = subprocess.run([nvcc] + NVCC_FLAGS + list(defines) + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(run, srcs))
+    r = subprocess.run([nvcc, "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    for o in objs:
+        os.remove(o)
+    os.rmdir(objdir)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

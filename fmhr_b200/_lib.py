@@ -83,6 +83,7 @@ _SIGS = {
     "fmhr_ham_add_delta_grad": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p]),
     "fmhr_ham_workspace_bytes": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_packed_floats": (c_sz, [ctypes.POINTER(HamConfig)]),
+    "fmhr_debug_checks": (c_i, []),
     "fmhr_ham_reset": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),
     "fmhr_ham_prepare_views": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_ham_step_render": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p]),

@@ -16,6 +16,16 @@
 
 // resident 256-thread blocks per SM the pixel / coverage kernels are compiled for (register budget = 65536 / 256 / N);
 // measured on B200 (tools/run_variants.sh): shade and backward are faster spill-free at 3, coverage at 5
+// Checked builds (-DFMHR_CHECKED, tools/build_variant.sh checked -DFMHR_CHECKED; tests/test_gpu_checked.py): every write into a
+// per-warp shared buffer or a capacity-bounded work list asserts its index and records a site code in g_dcheck instead of
+// writing out of bounds (this pool refuses compute-sanitizer; these are the indices memcheck would have watched).  The
+// product build compiles the checks to nothing.
+#ifdef FMHR_CHECKED
+static __device__ unsigned int g_dcheck;
+#define FMHR_DCHECK(cond, site) ((cond) ? true : (atomicOr(&g_dcheck, 1u << (site)), false))
+#else
+#define FMHR_DCHECK(cond, site) (true)
+#endif
 #ifndef FMHR_LB_COVERAGE
 #define FMHR_LB_COVERAGE 5
 #endif
@@ -304,6 +314,7 @@ __device__ __forceinline__ void ml_resolve(const float4* pos_s, uint2 rec, int p
                                            unsigned long long* __restrict__ zb) {
     const float4 p0 = pos_s[rec.x & 1023u], p1 = pos_s[(rec.x >> 10) & 1023u], p2 = pos_s[(rec.x >> 20) & 1023u];
     const Bary b = bary_at(p0, p1, p2, px, py, invW, invH);
+    if (!FMHR_DCHECK(px >= 0 && px < W && py >= 0 && rec.x != 0xffffffffu, 7)) return;
     atomicMin(&zb[(size_t)py * W + px], ((unsigned long long)depth_key(b.zw) << 32) | rec.y);
 }
 
@@ -336,7 +347,7 @@ __device__ __forceinline__ void ml_cover(int X0, int Y0, int X1, int Y1, int X2,
                 // the ~150-instruction depth resolve (and the tile bookkeeping) runs afterwards with the hits spread over
                 // all lanes
                 const int q = atomicAdd(qcount, 1);
-                if (q < kFragQueue) queue[q] = make_uint2((uint32_t)e, ((uint32_t)py << 16) | (uint32_t)px);
+                if (q < kFragQueue && FMHR_DCHECK(q >= 0, 0)) queue[q] = make_uint2((uint32_t)e, ((uint32_t)py << 16) | (uint32_t)px);
                 else {
                     ml_mark_tile(tbits, tiles_x, px, py);
                     ml_resolve(pos_s, rec, px, py, W, invW, invH, zb);
@@ -465,9 +476,11 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
         const unsigned m1 = __ballot_sync(0xffffffffu, fast), mb = __ballot_sync(0xffffffffu, pass && !fast);
         if (fast) {
             const int at = n1 + __popc(m1 & lt);
-            cand[warp][at] = rec[k];
-            cbox[warp][at] = box;
-        } else if (pass) cand[warp][TPT * 32 - 1 - nb - __popc(mb & lt)] = rec[k];
+            if (FMHR_DCHECK(at >= 0 && at < TPT * 32 - nb, 1)) {
+                cand[warp][at] = rec[k];
+                cbox[warp][at] = box;
+            }
+        } else if (pass && FMHR_DCHECK(TPT * 32 - 1 - nb - __popc(mb & lt) >= n1, 2)) cand[warp][TPT * 32 - 1 - nb - __popc(mb & lt)] = rec[k];
         n1 += __popc(m1);
         nb += __popc(mb);
     }
@@ -526,7 +539,7 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
         for (int k = 0; k < 4; k++) {
             if (hits & (1u << k)) {
                 const int px = px0 + (k & 1), py = py0 + (k >> 1);
-                if (at < kFragQueue) queue[warp][at] = make_uint2((uint32_t)e, ((uint32_t)py << 16) | (uint32_t)px);
+                if (at < kFragQueue && FMHR_DCHECK(at >= 0 && e < n1, 3)) queue[warp][at] = make_uint2((uint32_t)e, ((uint32_t)py << 16) | (uint32_t)px);
                 else {  // (queue full: resolve in place)
                     ml_mark_tile(tbits, tiles_x, px, py);
                     ml_resolve(pos_s, r, px, py, W, invW, invH, zb);
@@ -585,7 +598,9 @@ __global__ void __launch_bounds__(kCovThreads, FMHR_LB_COVERAGE * (256 / kCovThr
             fresh &= fresh - 1;
             const int tile = (w << 5) + bit;
             const int by = tile / tiles_x, bx = tile - by * tiles_x;
-            glist[atomicAdd(gcount, 1)] = ((uint32_t)n << 20) | ((uint32_t)by << 10) | (uint32_t)bx;
+            const int gi_ = atomicAdd(gcount, 1);
+            if (FMHR_DCHECK(gi_ >= 0 && gi_ < (int)gridDim.y * tiles_per_view && by < 1024 && bx < 1024, 9))
+                glist[gi_] = ((uint32_t)n << 20) | ((uint32_t)by << 10) | (uint32_t)bx;
         }
     }
 }
@@ -835,7 +850,8 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
         int base = 0;
         if (lane == 0) base = atomicAdd(ccount, nbuf);
         base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane; i < nbuf; i += 32) clist[base + i] = cbuf[wib][i];
+        for (int i = lane; i < nbuf; i += 32)
+            if (FMHR_DCHECK(base >= 0 && i < kBuf, 8)) clist[base + i] = cbuf[wib][i];
         __syncwarp();
         nbuf = 0;
     };
@@ -915,7 +931,7 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
             const int py = py0 + 2 * k;
             if (key[k] != ZB_EMPTY) {
                 const uint32_t pix = (uint32_t)(((size_t)tc.n * H + py) * W + px);
-                cbuf[wib][off + __popc(m[k] & lt)] = make_uint2(pix, (uint32_t)key[k] & kTriMask);
+                if (FMHR_DCHECK(off + __popc(m[k] & lt) < kBuf, 4)) cbuf[wib][off + __popc(m[k] & lt)] = make_uint2(pix, (uint32_t)key[k] & kTriMask);
             }
             off += __popc(m[k]);
         }
@@ -942,7 +958,8 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
                         if (f) {
                             const int k = j >> 2, d = j & 3;
                             const int qx = px + (d == 0 ? 1 : (d == 1 ? -1 : 0)), qy = py0 + 2 * k + (d == 2 ? 1 : (d == 3 ? -1 : 0));
-                            rbuf[wib][nring + __popc(mr & lt)] = (uint32_t)(((size_t)tc.n * H + qy) * W + qx);
+                            if (FMHR_DCHECK(nring + __popc(mr & lt) < kRBuf && qx >= 0 && qx < W && qy >= 0 && qy < H, 5))
+                                rbuf[wib][nring + __popc(mr & lt)] = (uint32_t)(((size_t)tc.n * H + qy) * W + qx);
                         }
                         nring += __popc(mr);
                         __syncwarp();
@@ -1214,8 +1231,10 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
                         const int slot = npb + __popc(mrec & lt);
                         const uint32_t flags = (uint32_t)d | ((uint32_t)pr.from1 << 1) | ((uint32_t)pr.clamped << 2) |
                                                ((uint32_t)pr.di << 3);
-                        pbuf_a[wib][slot] = make_uint4((uint32_t)(qbase + r0), flags, __float_as_uint(pr.alpha), (uint32_t)pr.i1);
-                        pbuf_b[wib][slot] = (uint32_t)pr.i2;
+                        if (FMHR_DCHECK(slot >= 0 && slot < kPBuf, 6)) {
+                            pbuf_a[wib][slot] = make_uint4((uint32_t)(qbase + r0), flags, __float_as_uint(pr.alpha), (uint32_t)pr.i1);
+                            pbuf_b[wib][slot] = (uint32_t)pr.i2;
+                        }
                     }
                     npb += __popc(mrec);
                     __syncwarp();
@@ -2835,6 +2854,20 @@ int launch_meshlet_coverage_clip(const float* pos, int N, int V, int H, int W, c
     return FMHR_OK;
 }
 }  // namespace fmhr
+
+// Checked builds: returns and clears the mask of FMHR_DCHECK sites that fired since the last call (0 = clean); -1 in
+// product builds (no checks compiled in).
+extern "C" int fmhr_debug_checks(void) {
+#ifdef FMHR_CHECKED
+    unsigned int h = 0, z = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(&h, g_dcheck, sizeof(h)) != cudaSuccess) return -2;
+    cudaMemcpyToSymbol(g_dcheck, &z, sizeof(z));
+    return (int)h;
+#else
+    return -1;
+#endif
+}
 
 extern "C" int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream) {
     int rc = check_cfg(cfg);

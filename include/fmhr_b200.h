@@ -221,6 +221,9 @@ size_t fmhr_ham_packed_floats(const fmhr_ham_config* cfg);
 /* Resets both z-buffer slots of `workspace`.  Call once before the first step and whenever the workspace layout
  * changes (different n_views / phase / workspace pointer). */
 int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers* buf, fmhr_stream_t stream);
+/* Diagnostic builds (-DFMHR_CHECKED): bit mask of the index assertions that fired inside the kernels since the last call
+ * (synchronises the device; 0 = clean).  Product builds compile the assertions out and return -1. */
+int fmhr_debug_checks(void);
 /* Constants of the mask loss: view_vm2[i][t] = sum of valid_masks[i]^2 over 16x16 tile t (row-major tiles), and
  * view_vm2[i][tiles] = the view total, tiles = ceil(W/16)*ceil(H/16) (valid_masks are fixed during the optimisation,
  * mesh_sfs_optim.py:163).  Call once at setup, and again if valid_masks change. */

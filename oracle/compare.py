@@ -34,7 +34,7 @@ TOL_GRAD = 1e-4    # relative to the largest gradient entry (albedo / SH gradien
 # Gradients of delta and (phase B) albedo contain the two uniform-Laplacian terms, whose direction y / ||y|| is computed from
 # differences of O(1) numbers (laplacian_direction_allowance): on the 48-view benchmark shape that alone is worth 6.5e-5 of
 # the largest delta-gradient entry INSIDE the fp32 oracle (fp32 vs fp64 of the same formula).  The bar is therefore
-#   |g - g_oracle|_i <= 1e-4 * max|g_oracle| + allowance_i     for every entry,
+#   |g - g_oracle|_i <= 1e-4 * max|g_oracle| + allowance_i     for every entry  (asserted: grad_*_rel_excess / grad_albedo_rel),
 # and the raw max-norm (measured 2e-5 .. 1.8e-4 for delta; the CUDA path's own run-to-run noise is 2e-7), the relative L2
 # error (1e-5) and the 99.99 % quantile are reported and held to 5e-4 / 1e-4 / 1e-4.
 TOL_GRAD_DELTA_MAX = 5e-4
@@ -193,9 +193,7 @@ def ham_step_parity(scene, views=None, device="cuda", phase="b", planes=False, e
             ok = ok and rep[k] <= TOL_GRAD
     if "grad_delta_rel" in rep:
         ok = ok and rep["grad_delta_rel"] <= TOL_GRAD_DELTA_MAX and rep["grad_delta_err_quantiles"][0.9999] <= TOL_GRAD
-        # (grad_delta_rel_excess - the max-norm beyond the Laplacian allowance - is reported, not asserted: the few outliers of
-        #  the 48-view shape, 1.4e-4, are of the size of ONE pixel-channel's L1 contribution, 2 * sfs_weight / (3 N_valid) * |d pred
-        #  / d vertex| ~ 3e-5 absolute, and stay when either side is perturbed at rounding level)
+        ok = ok and rep["grad_delta_rel_excess"] <= TOL_GRAD  # every entry: 1e-4 of the largest + its conditioning allowance
     if "image_rel" in rep:
         ok = ok and rep["rast_bit_exact"] and rep["image_rel"] <= TOL_IMAGE and rep["coverage_abs"] <= TOL_IMAGE
     rep["within_tolerance"] = bool(ok)

@@ -44,6 +44,7 @@ def _assert_report(rep):
     if "grad_delta_rel" in rep:  # see oracle/compare.py: sliver triangles amplify fp32 rounding in a handful of entries
         assert rep["grad_delta_err_quantiles"][0.9999] <= compare.TOL_GRAD, rep["grad_delta_err_quantiles"]
         assert rep["grad_delta_rel"] <= compare.TOL_GRAD_DELTA_MAX, rep["grad_delta_rel"]
+        assert rep["grad_delta_rel_excess"] <= compare.TOL_GRAD, rep["grad_delta_rel_excess"]
     if "image_rel" in rep:
         assert rep["pos_bit_exact"] and rep["rast_bit_exact"], "positions / ids / depth / barycentrics must be bit-exact"
         assert rep["image_rel"] <= compare.TOL_IMAGE, rep["image_rel"]

@@ -8,5 +8,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ham_" -c 80 
     python bench.py --steps 3 --warmup 3 --no-graphs --no-e2e --no-cpu-baseline > gpurun_out/ncu_ll_$TAG.log 2>&1
 echo "ncu launch list rc=$?"
 tools/ncu_launches.sh ${TAG}w
-RE="ham_vertex_prep|ham_normals|ham_regulariser|ham_trirec|coverage_meshlet|ham_scan|ham_shade|ham_aa_loss|ham_pair_bwd|ham_pixel_bwd|ham_finalize|ham_normal_grad|ham_update_pass2"
+RE="ham_vertex_prep|ham_normals|ham_regulariser|ham_reg_grad|ham_trirec|coverage_meshlet|ham_scan|ham_shade|ham_aa_loss|ham_pair_bwd|ham_pixel_bwd|ham_finalize|ham_normal_grad|ham_update_pass2"
 tools/ncu_full.sh $TAG "$RE"

@@ -270,7 +270,7 @@ def main():
         ncc_term = NccTerm(opt, gray, ref_view=0, src_views=list(range(1, scene["imgs"].shape[0])), weight=10.0,
                            n_points=50000, half=5, seed=0)
     exchange = "1 NCCL all-reduce/iter"
-    kernels_per_step = KERNELS_PER_STEP + (5 if args.ncc else 0)  # own kernels per iteration (NCCL's all-reduce kernel is not counted)
+    kernels_per_step = KERNELS_PER_STEP + (2 if args.ncc else 0)  # own kernels per iteration (NCCL's all-reduce kernel is not counted)
     if opt.peer is not None:
         # one-shot: the exchange IS the normal-gradient kernel; two-shot: one extra reduce-scatter kernel in front of it
         kernels_per_step += 1 if (opt.peer.mode == 2 or (opt.peer.mode == 0 and world > 2)) else 0

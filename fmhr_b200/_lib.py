@@ -80,6 +80,7 @@ _SIGS = {
     "fmhr_ncc_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "fmhr_ncc_sample_fwd": (c_i, [c_p] * 7 + [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "fmhr_ncc_sample_bwd": (c_i, [c_p] * 7 + [c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "fmhr_ncc_term_fused": (c_i, [c_p] * 7 + [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
     "fmhr_ham_add_delta_grad": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p]),
     "fmhr_ham_workspace_bytes": (c_sz, [ctypes.POINTER(HamConfig)]),
     "fmhr_ham_packed_floats": (c_sz, [ctypes.POINTER(HamConfig)]),

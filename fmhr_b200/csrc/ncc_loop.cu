@@ -9,6 +9,7 @@
 //   fmhr_ncc_sample_fwd : vertices, points, cameras, gray images, masks -> patches [Nv+1,Np,Npx], patch masks
 //   fmhr_ncc_sample_bwd : d loss / d patches -> d loss / d vertices  (+=, world space, three atomics per (view, point))
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fmhr {
 
@@ -141,10 +142,179 @@ __global__ void __launch_bounds__(256) ncc_sample_bwd_kernel(
     }
 }
 
+// Fused form of the whole term for patches of at most 128 samples (11 x 11 = 121 in conf/demo_sfs.conf): one warp per POINT
+// keeps its reference patch in registers (4 samples per lane) and walks the source views; per view the patch is sampled
+// into registers together with its bilinear gradient coefficients, the masked NCC statistics are warp-reduced, the value
+// is stored and the analytic gradient (the arithmetic of ncc_bwd_kernel, mesh.cu) is contracted with the sampling
+// gradients on the spot.  Nothing of size [Nv, Np, Npx] is ever written: the unfused chain moves ~2.6 GB of patches, masks
+// and patch gradients through HBM per iteration for config 3, this kernel reads image pixels through L1 / L2 and issues
+// nine atomics per point.  g = d loss / d ncc (the same constant for every (view, point): -weight / (Nv Np)).
+//
+// Sampling: the patch offsets are whole pixels, so all samples of a (point, view) share ONE fractional position
+// (fx, fy) = (u - floor u, v - floor v) and read a (side + 1)^2 block of pixels: the warp stages that block (image and
+// mask, zero outside the frame) in shared memory with ~5 coalesced loads each, and every sample is four shared-memory
+// reads with the same weights - instead of four scattered global gathers, a floor and eight bounds tests per sample
+// (measured on config 3: the per-sample form was bound by L1 wavefronts and address arithmetic, 1.07 ms per iteration).
+constexpr int kNccTile = 12 * 12;  // (side + 1)^2 for side <= 11
+constexpr int kNccMaxViews = 64;   // view slots of the fused kernel (reference + sources)
+struct NccView { int x0, y0; float fx, fy; int bx, by; bool front; };
+template <int HALF>
+__device__ __forceinline__ NccView ncc_stage(const float* __restrict__ img, const float* __restrict__ msk, int H, int W,
+                                             int half_rt, float u, float v, bool front, float* timg, float* tmsk, int lane) {
+    const int half = HALF > 0 ? HALF : half_rt;  // compile-time for the configured patch sizes: t / ts becomes a multiply
+    NccView nv;
+    const float x0f = floorf(u), y0f = floorf(v);
+    nv.x0 = (int)x0f; nv.y0 = (int)y0f; nv.fx = u - x0f; nv.fy = v - y0f;
+    nv.bx = nv.fx >= 0.5f ? 1 : 0; nv.by = nv.fy >= 0.5f ? 1 : 0;
+    nv.front = front;
+    const int ts = 2 * half + 2;
+    __syncwarp();  // the previous view's samples have been read
+    for (int t = lane; t < ts * ts; t += 32) {
+        const int ty = t / ts, tx = t - ty * ts;
+        const int px = nv.x0 - half + tx, py = nv.y0 - half + ty;
+        const bool in = front && px >= 0 && px < W && py >= 0 && py < H;
+        timg[t] = in ? __ldg(img + (size_t)py * W + px) : 0.0f;
+        tmsk[t] = (in && msk) ? __ldg(msk + (size_t)py * W + px) : 0.0f;
+    }
+    __syncwarp();
+    return nv;
+}
+// sample (dx, dy) of the staged block: value, bilinear gradient coefficients, mask (same rules as ncc_taps)
+template <int HALF>
+__device__ __forceinline__ void ncc_tile_sample(const NccView& nv, const float* timg, const float* tmsk, int H, int W,
+                                                int half_rt, int dx, int dy, float& val, float& du, float& dv, float& mk) {
+    const int half = HALF > 0 ? HALF : half_rt;
+    const int ts = 2 * half + 2, o = (dy + half) * ts + dx + half;
+    const float i00 = timg[o], i10 = timg[o + 1], i01 = timg[o + ts], i11 = timg[o + ts + 1];
+    val = (1.0f - nv.fy) * ((1.0f - nv.fx) * i00 + nv.fx * i10) + nv.fy * ((1.0f - nv.fx) * i01 + nv.fx * i11);
+    du = (1.0f - nv.fy) * (i10 - i00) + nv.fy * (i11 - i01);
+    dv = (1.0f - nv.fx) * (i01 - i00) + nv.fx * (i11 - i10);
+    const int px = nv.x0 + dx, py = nv.y0 + dy;
+    const bool inside = px >= 0 && px + 1 < W && py >= 0 && py + 1 < H;
+    mk = (inside && tmsk[o + nv.by * ts + nv.bx] > 0.5f) ? 1.0f : 0.0f;
+}
+
+template <int HALF>
+__global__ void __launch_bounds__(256, 3) ncc_term_fused_kernel(
+    const float* __restrict__ vertices, const int32_t* __restrict__ tri, const int32_t* __restrict__ pt_face,
+    const float* __restrict__ pt_bary, const float* __restrict__ w2cs, const float* __restrict__ projs,
+    const int32_t* __restrict__ view_idx, int Nv1, const float* __restrict__ gray, const float* __restrict__ masks, int Np,
+    int H, int W, int half_rt, float g, float* __restrict__ ncc, float* __restrict__ grad_vertices, int chunk) {
+    const int half = HALF > 0 ? HALF : half_rt;
+    __shared__ float timg_s[8][kNccTile], tmsk_s[8][kNccTile];
+    // world -> clip matrices of the term's views, once per block (every lane of every warp multiplied them per view)
+    __shared__ NccCam Ms[kNccMaxViews];
+    for (int i = threadIdx.x; i < Nv1 * 16; i += blockDim.x) {
+        const int sl = i >> 4, e = i & 15, rr = e >> 2, jj = e & 3;
+        const int view = __ldg(view_idx + sl);
+        const float* Wm = w2cs + (size_t)view * 16;
+        const float* Pm = projs + (size_t)view * 16;
+        Ms[sl].m[e] = __fmaf_rn(Wm[4 * rr + 3], Pm[12 + jj], __fmaf_rn(Wm[4 * rr + 2], Pm[8 + jj],
+                                __fmaf_rn(Wm[4 * rr + 1], Pm[4 + jj], __fmul_rn(Wm[4 * rr], Pm[jj]))));
+    }
+    __syncthreads();
+    // a warp owns one point and `chunk` consecutive source views (the reference patch is re-sampled per chunk)
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_chunks = (Nv1 - 1 + chunk - 1) / chunk;
+    const int p = (int)(wid / n_chunks), ch = (int)(wid - (long long)p * n_chunks);
+    const int lane = threadIdx.x & 31;
+    if (p >= Np) return;  // (whole warps: no partial-warp exit before the __syncwarp()s below)
+    float* timg = timg_s[threadIdx.x >> 5];
+    float* tmsk = tmsk_s[threadIdx.x >> 5];
+    const int s_begin = 1 + ch * chunk, s_end = min(Nv1, s_begin + chunk);
+    const NccPoint q = ncc_point(vertices, tri, pt_face, pt_bary, p);
+    const int side = 2 * half + 1, npx = side * side;
+    int dxs[4], dys[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int k = min(lane + 32 * j, npx - 1);
+        dys[j] = k / side - half;
+        dxs[j] = k - (k / side) * side - half;
+    }
+    // reference patch (view slot 0): a constant of the step
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+        const int view = __ldg(view_idx);
+        const NccCam& M = Ms[0];
+        float u, v;
+        float4 clip;
+        ncc_project(M, q.X, H, W, u, v, clip);
+        const NccView nv = ncc_stage<HALF>(gray + (size_t)view * H * W, nullptr, H, W, half, u, v, clip.w > 0.0f, timg, tmsk, lane);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float du, dv, mk;
+            if (lane + 32 * j < npx) ncc_tile_sample<HALF>(nv, timg, tmsk, H, W, half, dxs[j], dys[j], r[j], du, dv, mk);
+        }
+    }
+    float3 gXsum = make_float3(0.f, 0.f, 0.f);
+    for (int s = s_begin; s < s_end; s++) {
+        const int view = __ldg(view_idx + s);
+        const NccCam& M = Ms[s];
+        float u, v;
+        float4 clip;
+        ncc_project(M, q.X, H, W, u, v, clip);
+        const bool front = clip.w > 0.0f;
+        const NccView nv = ncc_stage<HALF>(gray + (size_t)view * H * W, masks + (size_t)view * H * W, H, W, half, u, v, front, timg,
+                                     tmsk, lane);
+        float sv[4], mk[4], du[4], dv[4];
+        float cnt = 0.f, sr = 0.f, ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sv[j] = 0.f; mk[j] = 0.f; du[j] = 0.f; dv[j] = 0.f;
+            if (front && lane + 32 * j < npx) ncc_tile_sample<HALF>(nv, timg, tmsk, H, W, half, dxs[j], dys[j], sv[j], du[j], dv[j], mk[j]);
+            cnt += mk[j]; sr += r[j] * mk[j]; ss += sv[j] * mk[j];
+        }
+        cnt = warp_sum(cnt); sr = warp_sum(sr); ss = warp_sum(ss);
+        if (cnt == 0.0f) cnt = 1.0f;
+        const float rm = sr / cnt, sm = ss / cnt;
+        float vr = 0.f, vs = 0.f, cv = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (lane + 32 * j >= npx) continue;
+            const float dr = (r[j] - rm) * mk[j], dsv = (sv[j] - sm) * mk[j];
+            vr += dr * dr; vs += dsv * dsv; cv += (r[j] - rm) * (sv[j] - sm) * mk[j];
+            s1 += dsv * mk[j]; s2 += dr;
+        }
+        vr = warp_sum(vr) / cnt; vs = warp_sum(vs) / cnt; cv = warp_sum(cv) / cnt;
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (vr == 0.0f) vr = 1.0f;
+        if (vs == 0.0f) vs = 1.0f;
+        if (lane == 0) ncc[(size_t)(s - 1) * Np + p] = cv / (sqrtf(vr) * sqrtf(vs));
+        if (!front) continue;
+        const float ir = rsqrtf(vr), is = rsqrtf(vs);
+        const float c_cv = g * ir * is / cnt, c_vs = -g * cv * ir * is / vs / cnt;
+        float gu = 0.f, gv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (lane + 32 * j >= npx) continue;
+            const float dcv = (r[j] - rm) * mk[j] - mk[j] / cnt * s2;
+            const float dvs = (sv[j] - sm) * mk[j] * mk[j] - mk[j] / cnt * s1;
+            const float gk = c_cv * dcv + c_vs * dvs;
+            gu += gk * du[j]; gv += gk * dv[j];
+        }
+        gu = warp_sum(gu); gv = warp_sum(gv);
+        const float iw = 1.0f / clip.w, hu = 0.5f * (float)W * gu * iw, hv = 0.5f * (float)H * gv * iw;
+        const float gcw = -(hu * clip.x + hv * clip.y) * iw;
+        gXsum.x += M.m[0] * hu + M.m[1] * hv + M.m[3] * gcw;
+        gXsum.y += M.m[4] * hu + M.m[5] * hv + M.m[7] * gcw;
+        gXsum.z += M.m[8] * hu + M.m[9] * hv + M.m[11] * gcw;
+    }
+    if (lane != 0 || (gXsum.x == 0.0f && gXsum.y == 0.0f && gXsum.z == 0.0f)) return;
+    const int vi[3] = {q.i0, q.i1, q.i2};
+    const float bw[3] = {q.b0, q.b1, q.b2};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float* o = grad_vertices + 3 * (size_t)vi[c];
+        atomicAdd(o, bw[c] * gXsum.x); atomicAdd(o + 1, bw[c] * gXsum.y); atomicAdd(o + 2, bw[c] * gXsum.z);
+    }
+}
+
 }  // namespace fmhr
 
 using namespace fmhr;
 
+constexpr int kNccViewChunk = 64;  // source views per warp of the fused kernel: all of them (sweep on config 3, 1 / 3 / 5 / 15
+                                   // views per warp: 1.96 / 1.44 / 1.35 / 1.27 ms per iteration; override: FMHR_NCC_CHUNK)
 static int ncc_check(const void* vertices, const void* tri, const void* pt_face, const void* pt_bary, const void* w2cs,
                      const void* projs, const void* view_idx, int Nv1, const void* gray, int V, int Np, int H, int W, int half) {
     FMHR_CHECK_ARG(vertices && tri && pt_face && pt_bary && w2cs && projs && view_idx && gray);
@@ -177,6 +347,33 @@ extern "C" int fmhr_ncc_sample_bwd(const float* vertices, const int32_t* tri, co
     const long long threads = (long long)(Nv1 - 1) * Np * 32;
     ncc_sample_bwd_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(
         vertices, tri, pt_face, pt_bary, w2cs, projs, view_idx, Nv1, gray, Np, H, W, half, grad_patches, grad_vertices);
+    FMHR_LAUNCH_CHECK();
+    return FMHR_OK;
+}
+
+extern "C" int fmhr_ncc_term_fused(const float* vertices, const int32_t* tri, const int32_t* pt_face, const float* pt_bary,
+                                   const float* w2cs, const float* projs, const int32_t* view_idx, int Nv1,
+                                   const float* gray, const float* masks, int V, int Np, int H, int W, int half,
+                                   float grad_ncc, float* ncc, float* grad_vertices, fmhr_stream_t stream) {
+    int rc = ncc_check(vertices, tri, pt_face, pt_bary, w2cs, projs, view_idx, Nv1, gray, V, Np, H, W, half);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(masks && ncc && grad_vertices);
+    if ((2 * half + 1) * (2 * half + 1) > 128 || Nv1 > kNccMaxViews) {
+        set_error("fmhr_ncc_term_fused: patches of more than 128 samples need the unfused chain (fmhr_ncc_sample_fwd / "
+                  "fmhr_ncc_fwd / fmhr_ncc_bwd / fmhr_ncc_sample_bwd)");
+        return FMHR_EUNSUPPORTED;
+    }
+    static const int env_chunk = [] { const char* e = getenv("FMHR_NCC_CHUNK"); return e ? atoi(e) : 0; }();
+    const int chunk = max(1, min(Nv1 - 1, env_chunk > 0 ? env_chunk : kNccViewChunk));
+    const long long warps = (long long)Np * ((Nv1 - 1 + chunk - 1) / chunk);
+#define FMHR_NCC_FUSED(HALF)                                                                                              \
+    ncc_term_fused_kernel<HALF><<<cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(                                 \
+        vertices, tri, pt_face, pt_bary, w2cs, projs, view_idx, Nv1, gray, masks, Np, H, W, half, grad_ncc, ncc,          \
+        grad_vertices, chunk)
+    if (half == 5) FMHR_NCC_FUSED(5);
+    else if (half == 2) FMHR_NCC_FUSED(2);
+    else FMHR_NCC_FUSED(0);
+#undef FMHR_NCC_FUSED
     FMHR_LAUNCH_CHECK();
     return FMHR_OK;
 }

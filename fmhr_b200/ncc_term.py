@@ -34,7 +34,7 @@ def sample_surface_points(vertices, faces, n_points, seed=0):
 class NccTerm:
     """One instance per optimiser.  grayimgs [num,H,W] (CUDA); ref_view / src_views index the optimiser's view arrays."""
 
-    def __init__(self, opt, grayimgs, ref_view, src_views, weight, n_points=50000, half=5, seed=0):
+    def __init__(self, opt, grayimgs, ref_view, src_views, weight, n_points=50000, half=5, seed=0, fused=True):
         self.lib = _lib.load()
         dev = opt.device
         self.weight, self.half, self.npx = float(weight), int(half), (2 * int(half) + 1) ** 2
@@ -46,11 +46,9 @@ class NccTerm:
         if self.gray.shape != opt.masks.shape:
             raise RuntimeError("fmhr_b200.NccTerm: grayimgs must be [num,H,W]")
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        self.patches, self.patch_mask = f32(self.nv1, n_points, self.npx), f32(self.nv1, n_points, self.npx)
-        self.grad_patches = torch.zeros(self.nv1, n_points, self.npx, dtype=torch.float32, device=dev)
+        self.patches = self.patch_mask = self.grad_patches = self.grad_ncc = None   # unfused chain only (_alloc_patches)
+        self.fused = fused
         self.ncc = f32(self.nv1 - 1, n_points)
-        self.grad_ncc = torch.full((self.nv1 - 1, n_points), -self.weight / float((self.nv1 - 1) * n_points),
-                                   dtype=torch.float32, device=dev)
         self.vertices = f32(opt.V, 3)
         self.grad_delta = f32(opt.V, 3)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
@@ -62,23 +60,43 @@ class NccTerm:
         nv = self.nv1 - 1
         return 8 * nv * self.np_ * self.npx + 4 * self.np_ * self.npx + 4 * nv * self.np_
 
-    def accumulate(self, opt, cfg, buf, sp):
-        """Enqueue the term on stream `sp` (between fmhr_ham_step_render and fmhr_ham_step_update; graph-capturable)."""
+    def accumulate(self, opt, cfg, buf, sp, fused=None):
+        """Enqueue the term on stream `sp` (between fmhr_ham_step_render and fmhr_ham_step_update; graph-capturable).
+        fused (default: whenever the patch has at most 128 samples): ONE kernel samples, evaluates and back-propagates
+        (fmhr_ncc_term_fused); otherwise the four-call chain that materialises patches / masks / patch gradients (also
+        what the parity tests inspect: self.patches)."""
         lib = self.lib
         V, T, H, W = opt.V, opt.T, opt.H, opt.W
         torch.add(opt.vertices_tmp, opt.delta, out=self.vertices)
         args = (ptr(self.vertices), ptr(opt.faces), ptr(self.pt_face), ptr(self.pt_bary), ptr(opt.w2cs), ptr(opt.projs),
                 ptr(self.view_idx), self.nv1, ptr(self.gray))
-        check(lib.fmhr_ncc_sample_fwd(*args, ptr(opt.masks), V, self.np_, H, W, self.half, ptr(self.patches),
-                                      ptr(self.patch_mask), sp), "ncc_sample_fwd")
-        ref, src, msk = self.patches[0:1], self.patches[1:], self.patch_mask[1:]
         nv = self.nv1 - 1
-        check(lib.fmhr_ncc_fwd(ptr(ref), ptr(src), ptr(msk), nv, self.np_, self.npx, ptr(self.ncc), sp), "ncc_fwd")
-        check(lib.fmhr_ncc_bwd(ptr(ref), ptr(src), ptr(msk), ptr(self.grad_ncc), nv, self.np_, self.npx,
-                               ptr(self.grad_patches[1:]), sp), "ncc_bwd")
+        if fused is None:
+            fused = self.fused and self.npx <= 128
         self.grad_delta.zero_()
-        check(lib.fmhr_ncc_sample_bwd(*args, V, self.np_, H, W, self.half, ptr(self.grad_patches), ptr(self.grad_delta), sp),
-              "ncc_sample_bwd")
+        if fused:
+            check(lib.fmhr_ncc_term_fused(*args, ptr(opt.masks), V, self.np_, H, W, self.half,
+                                          -self.weight / float(nv * self.np_), ptr(self.ncc), ptr(self.grad_delta), sp),
+                  "ncc_term_fused")
+        else:
+            self._alloc_patches()
+            check(lib.fmhr_ncc_sample_fwd(*args, ptr(opt.masks), V, self.np_, H, W, self.half, ptr(self.patches),
+                                          ptr(self.patch_mask), sp), "ncc_sample_fwd")
+            ref, src, msk = self.patches[0:1], self.patches[1:], self.patch_mask[1:]
+            check(lib.fmhr_ncc_fwd(ptr(ref), ptr(src), ptr(msk), nv, self.np_, self.npx, ptr(self.ncc), sp), "ncc_fwd")
+            check(lib.fmhr_ncc_bwd(ptr(ref), ptr(src), ptr(msk), ptr(self.grad_ncc), nv, self.np_, self.npx,
+                                   ptr(self.grad_patches[1:]), sp), "ncc_bwd")
+            check(lib.fmhr_ncc_sample_bwd(*args, V, self.np_, H, W, self.half, ptr(self.grad_patches), ptr(self.grad_delta),
+                                          sp), "ncc_sample_bwd")
         check(lib.fmhr_ham_add_delta_grad(ctypes.byref(cfg), ctypes.byref(buf), ptr(self.grad_delta), sp),
               "ham_add_delta_grad")
         torch.mul(1.0 - self.ncc.mean(), self.weight, out=self.loss)
+
+    def _alloc_patches(self):
+        if self.patches is None:
+            dev = self.gray.device
+            f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            self.patches, self.patch_mask = f32(self.nv1, self.np_, self.npx), f32(self.nv1, self.np_, self.npx)
+            self.grad_patches = torch.zeros(self.nv1, self.np_, self.npx, dtype=torch.float32, device=dev)
+            self.grad_ncc = torch.full((self.nv1 - 1, self.np_), -self.weight / float((self.nv1 - 1) * self.np_),
+                                       dtype=torch.float32, device=dev)

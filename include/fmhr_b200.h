@@ -252,6 +252,14 @@ int fmhr_ncc_sample_bwd(const float* vertices, const int32_t* tri, const int32_t
                         const float* w2cs, const float* projs, const int32_t* view_idx, int Nv1, const float* gray, int V,
                         int Np, int H, int W, int half, const float* grad_patches, float* grad_vertices,
                         fmhr_stream_t stream);
+/* The whole term in one kernel for patches of at most 128 samples (half <= 5): sampling, masked NCC (models/ncc_utils.py:
+ * 4-35) and its gradient through the source sampling positions to the vertices, nothing of size [Nv,Np,Npx] materialised.
+ * grad_ncc = d loss / d ncc, the same for every (source view, point); ncc [Nv1-1,Np] receives the values;
+ * grad_vertices [V,3] is accumulated into (+=).  FMHR_EUNSUPPORTED for larger patches (use the four calls above). */
+int fmhr_ncc_term_fused(const float* vertices, const int32_t* tri, const int32_t* pt_face, const float* pt_bary,
+                        const float* w2cs, const float* projs, const int32_t* view_idx, int Nv1, const float* gray,
+                        const float* masks, int V, int Np, int H, int W, int half, float grad_ncc, float* ncc,
+                        float* grad_vertices, fmhr_stream_t stream);
 /* ---- multi-GPU exchange over NVLink peer memory (replaces the ncclAllReduce of `packed` the reference
  * design would place between loss.backward() and optimizer.step(), mesh_sfs_optim.py:309-310, when views shard) ----
  * Every rank allocates its exchange memory with fmhr_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; zero-filled), the

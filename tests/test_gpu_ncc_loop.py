@@ -18,18 +18,20 @@ def scene():
     return synth.build_scene("small", oham.render_views)
 
 
-def _setup(scene, n_points, half, weight=10.0, **kw):
+def _setup(scene, n_points, half, weight=10.0, fused=True, **kw):
     from fmhr_b200.ncc_term import NccTerm
     opt = compare.make_optimizer(scene, torch.device("cuda"), **kw)
     gray = torch.tensor(np.asarray(scene["imgs"]).mean(-1).astype(np.float32)).cuda()
     n = scene["imgs"].shape[0]
-    term = NccTerm(opt, gray, ref_view=0, src_views=list(range(1, n)), weight=weight, n_points=n_points, half=half, seed=3)
+    term = NccTerm(opt, gray, ref_view=0, src_views=list(range(1, n)), weight=weight, n_points=n_points, half=half, seed=3, fused=fused)
     return opt, term, gray
 
 
-@pytest.mark.parametrize("half", [2, 5])
-def test_ncc_term_matches_the_specification(scene, half):
-    opt, term, gray = _setup(scene, 3000, half, debug=True)
+@pytest.mark.parametrize("half,fused", [(2, False), (5, False), (2, True), (5, True), (6, True)])
+def test_ncc_term_matches_the_specification(scene, half, fused):
+    """fused: the one-kernel form (fmhr_ncc_term_fused, patches of <= 128 samples; half = 6 -> 169 samples falls back to the
+    chain); unfused: the four-call chain, whose materialised patches / masks are compared as well."""
+    opt, term, gray = _setup(scene, 3000, half, debug=True, fused=fused)
     n = scene["imgs"].shape[0]
     views = list(range(n))
     opt.step_phase_b(views)       # one iteration with the term enqueued between render and update
@@ -38,8 +40,11 @@ def test_ncc_term_matches_the_specification(scene, half):
     loss, ncc, patches, pmask = oncc.ncc_term(verts, st.faces, term.pt_face.cpu(), term.pt_bary.cpu(), st.w2cs, st.projs,
                                               term.view_idx.cpu(), gray.cpu(), st.masks, term.weight, half)
     loss.backward()
-    assert float((term.patches.cpu() - patches).abs().max()) < 2e-5
-    assert float((term.patch_mask.cpu() != pmask).float().mean()) < 1e-4    # (a sample exactly on a pixel border may round apart)
+    if fused and half <= 5:
+        assert term.patches is None, "the fused form must not materialise [Nv,Np,Npx] arrays"
+    else:
+        assert float((term.patches.cpu() - patches).abs().max()) < 2e-5
+        assert float((term.patch_mask.cpu() != pmask).float().mean()) < 1e-4    # (a sample exactly on a pixel border may round apart)
     # NCC divides by sqrt(var_ref * var_src): patches of nearly constant colour amplify rounding, hence the quantile bar
     dn = (term.ncc.cpu() - ncc.detach()).abs()
     assert float(torch.quantile(dn.flatten(), 0.999)) < 1e-3 and abs(float(term.loss) - float(loss)) < 1e-4 * abs(float(loss))
@@ -47,6 +52,21 @@ def test_ncc_term_matches_the_specification(scene, half):
     err = (g - gref).abs() / gref.abs().max()
     assert float(torch.quantile(err.flatten(), 0.999)) < 1e-3 and float((g - gref).norm() / gref.norm()) < 1e-3, \
         (float(err.max()), float((g - gref).norm() / gref.norm()))
+
+
+def test_fused_term_equals_the_chain(scene):
+    """Same arithmetic in the same order: NCC values and the vertex gradient of the fused kernel against the four-call chain."""
+    a, ta, _ = _setup(scene, 4000, 5, fused=True)
+    b, tb, _ = _setup(scene, 4000, 5, fused=False)
+    views = list(range(scene["imgs"].shape[0]))
+    a.step_phase_b(views)
+    b.step_phase_b(views)
+    # (the fused kernel evaluates the shared fractional sample position once per (point, view), the chain per sample: the
+    #  patches agree to ~1e-6, and NCC amplifies that where a patch is nearly constant - hence the quantile)
+    dn = (ta.ncc - tb.ncc).abs().flatten()
+    assert float(torch.quantile(dn, 0.999)) < 1e-4 and float(dn.max()) < 5e-2, (float(torch.quantile(dn, 0.999)), float(dn.max()))
+    assert compare.rel_l2(ta.grad_delta, tb.grad_delta) < 1e-4
+    assert abs(float(ta.loss) - float(tb.loss)) < 1e-5 * abs(float(tb.loss))
 
 
 def test_iteration_with_ncc_term_matches_the_oracle(scene):

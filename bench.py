@@ -208,9 +208,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "frames"],
                     help="N > 1: weak = every rank renders the workload's whole view set (global batch N x views); strong = "
-                         "the workload's views are dealt round-robin to the ranks (global batch fixed, SURVEY.md 8e)")
+                         "the workload's views are dealt round-robin to the ranks (global batch fixed, SURVEY.md 8e); frames = "
+                         "every rank optimises its OWN frame of a sequence (BASELINE.json configs[3]: independent problems, no "
+                         "exchange at all; value = frames' iterations per second summed over the ranks)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-oneshot", "peer-twoshot", "nccl"],
                     help="N > 1: fused NVLink peer-memory exchange inside the update kernel, or one NCCL all-reduce")
     args = ap.parse_args()
@@ -246,6 +248,7 @@ def main():
 
     wl = dict(synth.WORKLOADS[args.workload])
     strong = args.scaling == "strong" and world > 1
+    frames = args.scaling == "frames" and world > 1
     if strong:
         # the workload's views (one camera set) dealt round-robin: rank r owns views r, r + world, ... (fmhr_b200.dist.shard_views)
         total_views = args.views or wl["n"]
@@ -260,7 +263,9 @@ def main():
     c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt, device=dev)
     opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
                        c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], use_graphs=not args.no_graphs,
-                       exchange=args.exchange if world > 1 else None, n_views_global=total_views if world > 1 else None)
+                       exchange=args.exchange if (world > 1 and not frames) else None,
+                       n_views_global=total_views if (world > 1 and not frames) else None,
+                       process_group=False if frames else None)
     ncc_term = None
     if args.ncc:
         if world > 1:
@@ -269,7 +274,7 @@ def main():
         gray = torch.tensor(np.asarray(scene["imgs"]).mean(-1).astype(np.float32), device=dev)
         ncc_term = NccTerm(opt, gray, ref_view=0, src_views=list(range(1, scene["imgs"].shape[0])), weight=10.0,
                            n_points=50000, half=5, seed=0)
-    exchange = "1 NCCL all-reduce/iter"
+    exchange = "none: every rank optimises an independent frame" if frames else "1 NCCL all-reduce/iter"
     kernels_per_step = KERNELS_PER_STEP + (2 if args.ncc else 0)  # own kernels per iteration (NCCL's all-reduce kernel is not counted)
     if opt.peer is not None:
         # one-shot: the exchange IS the normal-gradient kernel; two-shot: one extra reduce-scatter kernel in front of it
@@ -339,7 +344,7 @@ def main():
         h_masks8 = torch.tensor(msk_u8).contiguous().pin_memory()
         h_w2cs, h_projs = pinf("w2cs"), pinf("projs")
         k_e2e = max(3, min(args.steps, 100))
-        if world == 1 or opt.peer is not None:
+        if world == 1 or opt.peer is not None or frames:
             stepper = HostStreamingStepper(opt, n)
             stepper.set_resident_valid_masks(opt.valid_masks)
             h2d, d2h = stepper.h2d_bytes_u8, stepper.d2h_bytes
@@ -398,9 +403,9 @@ def main():
                 "inputs": "the WHOLE 8-bit image batch + 8-bit masks + cameras from pinned host memory every step "
                           "(%s), loss record read back every step" % (
                               "fmhr_ham_host_u8_submit + fmhr_ham_step_host_u8_submitted, next batch in flight during "
-                              "the step" if (world == 1 or opt.peer is not None) else "torch copies + HamOptimizer.step_phase_b")}
+                              "the step" if (world == 1 or opt.peer is not None or frames) else "torch copies + HamOptimizer.step_phase_b")}
         e2e = full
-        if world == 1 or opt.peer is not None:
+        if world == 1 or opt.peer is not None or frames:
             # Headline leg: same pipelined step, but of every view only the bounding box of its segmentation travels
             # (fmhr_ham_host_u8_submit_boxes).  Outside it the mask is 0, no pixel is valid (mesh_sfs_optim.py:276-281) and
             # no image byte is read; the boxes are loader metadata, computed once from the masks outside the timed region.
@@ -520,8 +525,9 @@ def main():
                    if ncc_term is not None else None,
                    "l2": "per-iteration working set %.0f MB > 126 MB L2 (no flush needed)" % (
                        (8 + 32 + 20) * n * H * W / 1e6),
-                   "parallelism": "views x%d (%s), %s" % (world, "strong: the workload's views dealt round-robin" if strong else
-                                                          "weak: every rank renders its own view set", exchange)
+                   "parallelism": ("frames x%d (one independent frame of the sequence per rank), %s" % (world, exchange)) if frames
+                   else "views x%d (%s), %s" % (world, "strong: the workload's views dealt round-robin" if strong else
+                                                "weak: every rank renders its own view set", exchange)
                    if world > 1 else "single GPU"},
         "gpu_launches": kernels_per_step * args.steps,
         "clocks": clocks,

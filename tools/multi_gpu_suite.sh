@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU evidence run (N ranks on one box): parity check, exchange timeline, weak / strong scaling lines.
 # Usage: tools/multi_gpu_suite.sh N TAG [items...]   (under gpurun --gpus >= N)
-# items: check trace weak_peer weak_nccl strong_cfg2 strong_cfg5 strong_cfg1full strong_cfg3   (default: all)
+# items: check trace weak_peer weak_nccl strong_cfg2 strong_cfg5 strong_cfg1full strong_cfg3 frames_cfg4   (default: all but frames_cfg4)
 N=${1:-8}; TAG=${2:-m$N}; shift; shift
 ITEMS=${*:-check trace weak_peer weak_nccl strong_cfg2 strong_cfg5 strong_cfg1full strong_cfg3}
 if [ "$N" = 1 ]; then TR="timeout 600 python"; else TR="timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port"; fi
@@ -30,6 +30,7 @@ for it in $ITEMS; do
     strong_cfg2) run strong_cfg2 --scaling strong --no-e2e --no-cpu-baseline;;
     strong_cfg5) run strong_cfg5 --scaling strong --workload stress_128x2048x2048 --no-e2e --no-cpu-baseline --steps 100;;
     strong_cfg1full) run strong_cfg1full --scaling strong --workload demo_full --no-e2e --no-cpu-baseline;;
+    frames_cfg4) run frames_cfg4 --scaling frames --workload two_hands_48x512x334 --no-cpu-baseline;;
     strong_cfg3) run strong_cfg3 --scaling strong --workload capture_16x1024x1024 --no-e2e --no-cpu-baseline;;
   esac
 done

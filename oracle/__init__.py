@@ -3,7 +3,7 @@
 CPU restatement of the reference's HAM hot path (mesh_sfs_optim.py:193-317) used as the parity
 checker and as the timed CPU baseline.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this package; nothing under
-``fmhr_b200/`` does (tests/test_no_oracle_in_product.py enforces it).
+``fmhr_b200/`` does (tests/test_abi.py::test_product_never_touches_the_oracle enforces it).
 
 Pinning status
 --------------

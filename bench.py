@@ -186,8 +186,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1000.0 / rate, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "views": wl["n"], "H": wl["H"], "W": wl["W"],
-                   "verts": int(scene["vertices"].shape[0]), "faces": int(scene["faces"].shape[0])},
+        # same keys as the CUDA arm's config; the CPU arm times ONE 48-view batch (value is in 48-view iterations per second
+        # in both arms: at N > 1 the CUDA arm's weak-scaling value counts N such batches per step)
+        "config": {"workload": args.workload, "views_per_gpu": wl["n"], "global_views": wl["n"] * max(1, world), "H": wl["H"],
+                   "W": wl["W"], "verts": int(scene["vertices"].shape[0]), "faces": int(scene["faces"].shape[0]),
+                   "phase": "B (delta+albedo, conf/ih_sfs.conf weights)", "launch": "CPU, %d threads" % threads},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })

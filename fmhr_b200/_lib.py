@@ -110,7 +110,7 @@ _SIGS = {
     "fmhr_ham_step_host_u8_release": (c_i, [c_p, c_p]),
     "fmhr_ham_host_u8_submit_boxes": (c_i, [ctypes.POINTER(HamConfig), c_p, c_p, c_p, c_p, ctypes.POINTER(c_sz)]),
     "fmhr_ham_host_u8_submit_boxes_direct": (c_i, [ctypes.POINTER(HamConfig), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                                                   ctypes.POINTER(c_sz)]),
+                                                   c_i, ctypes.POINTER(c_sz)]),
     "fmhr_ham_step_host_u8_submitted": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p,
                                               ctypes.POINTER(HamPeers), c_p]),
     "fmhr_ham_step_host_u8": (c_i, [ctypes.POINTER(HamConfig), ctypes.POINTER(HamBuffers), c_p, c_p, c_p, c_p, c_p, c_p, c_p]),

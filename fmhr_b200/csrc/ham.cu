@@ -2400,18 +2400,32 @@ __device__ __forceinline__ void st_u8x16_as_f32(float* dst, uint4 v, bool mask) 
         reinterpret_cast<float4*>(dst)[k] = f;
     }
 }
-// Footprint: the pull runs BESIDE the step's pixel passes for ~100 us (PCIe-bound), so it must not take their SM slots -
-// blocks of 128 threads, two per view (<= one small block per SM; with 8 x 256-thread blocks per view the shade pass lost
-// half of its occupancy and ran 2.4x longer).  Two rows per warp iteration keep ~0.8 MB of reads in flight.
-constexpr int kPullThreads = 128, kPullBlocksPerView = 2;
-__global__ void __launch_bounds__(kPullThreads) ham_pull_boxes_f32_kernel(const uint8_t* __restrict__ imgs_host,
-                                                                        const uint8_t* __restrict__ masks_host,
-                                                                        const int4* __restrict__ boxes, int H, int W,
-                                                                        float* __restrict__ imgs, float* __restrict__ masks,
-                                                                        const float* __restrict__ w2cs_host,
-                                                                        const float* __restrict__ projs_host,
-                                                                        float* __restrict__ w2cs, float* __restrict__ projs,
-                                                                        int n_cam_floats) {
+// Footprint: the pull takes ~110 us (PCIe-bound) and must run BESIDE the step that is in flight without taking SM slots
+// from it.  The coverage kernel's five blocks per SM leave exactly 4,096 registers and no room for anything the size of a
+// normal block, so the pull uses blocks of 64 threads x 64 registers (one fits beside the coverage blocks on every SM) and
+// starts with the step instead of in the coverage kernel's last wave; with 8 x 256-thread blocks per view it ran beside
+// the shade pass, which lost half of its occupancy and took 2.4x as long.  No memset node in front of it either (a
+// memset also waits for the coverage kernel's tail): the mask plane is zero outside the boxes of the batch that was
+// pulled into this plane set before (prev), so the kernel zeroes those rows' chunks itself - except the chunks the new
+// rows write - and then pulls.  Chunk = 16 consecutive elements of the flat plane (the byte index of the u8 planes IS the
+// element index of the float planes); a row segment is written as the whole chunks it touches.
+constexpr int kPullThreads = 64;
+__device__ __forceinline__ bool pull_owns_chunk(size_t c, size_t vbase, int W, int4 nb) {
+    // is chunk [c, c + 16) written by the pull of box nb = (y0, y1, x0, x1) of the view starting at element vbase?
+    const size_t e0 = c - vbase;
+    const int r0 = (int)(e0 / (size_t)W), r1 = (int)((e0 + 15) / (size_t)W);
+    for (int r = r0; r <= r1; r++) {
+        if (r < nb.x || r >= nb.y) continue;
+        const size_t lo = (size_t)r * W + nb.z, hi = (size_t)r * W + nb.w;
+        if (e0 < hi && e0 + 16 > lo) return true;
+    }
+    return false;
+}
+__global__ void __launch_bounds__(kPullThreads, 16) ham_pull_boxes_f32_kernel(
+    const uint8_t* __restrict__ imgs_host, const uint8_t* __restrict__ masks_host, const int4* __restrict__ boxes,
+    const int4* __restrict__ prev_boxes, int H, int W, float* __restrict__ imgs, float* __restrict__ masks,
+    const float* __restrict__ w2cs_host, const float* __restrict__ projs_host, float* __restrict__ w2cs,
+    float* __restrict__ projs, int n_cam_floats) {
     const int v = blockIdx.y;
     if (v == 0 && blockIdx.x == gridDim.x - 1) {
         for (int i = threadIdx.x; i < n_cam_floats; i += blockDim.x) {
@@ -2423,41 +2437,57 @@ __global__ void __launch_bounds__(kPullThreads) ham_pull_boxes_f32_kernel(const 
         }
     }
     const int4 b = boxes[v];  // y0, y1, x0, x1
-    if (b.y <= b.x || b.w <= b.z) return;
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
-    const size_t width = (size_t)(b.w - b.z);
-    for (int r = b.x + warp; r < b.y; r += 2 * nw) {
-        const bool two = r + nw < b.y;
-        const size_t p0 = ((size_t)v * H + r) * W + b.z, q0 = p0 + (size_t)nw * W;
-        if (3 * width <= 1024 - 16) {
-            // common case: an image row segment fits two 512-byte warp accesses and its mask segment one - all (up to) six
-            // loads of the two rows are in flight before the first store
-            const size_t ci = ((3 * p0) & ~(size_t)15) + 16 * (size_t)lane, cm = (p0 & ~(size_t)15) + 16 * (size_t)lane;
-            const size_t di = ((3 * q0) & ~(size_t)15) + 16 * (size_t)lane, dm = (q0 & ~(size_t)15) + 16 * (size_t)lane;
-            const size_t ei = 3 * (p0 + width), fi = 3 * (q0 + width);
-            const bool l0 = ci < ei, l1 = ci + 512 < ei, lm = cm < p0 + width;
-            const bool k0 = two && di < fi, k1 = two && di + 512 < fi, km = two && dm < q0 + width;
-            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0;
-            if (l0) a0 = ld_host16(imgs_host + ci);
-            if (l1) a1 = ld_host16(imgs_host + ci + 512);
-            if (lm) a2 = ld_host16(masks_host + cm);
-            if (k0) a3 = ld_host16(imgs_host + di);
-            if (k1) a4 = ld_host16(imgs_host + di + 512);
-            if (km) a5 = ld_host16(masks_host + dm);
-            if (l0) st_u8x16_as_f32(imgs + ci, a0, false);
-            if (l1) st_u8x16_as_f32(imgs + ci + 512, a1, false);
-            if (lm) st_u8x16_as_f32(masks + cm, a2, true);
-            if (k0) st_u8x16_as_f32(imgs + di, a3, false);
-            if (k1) st_u8x16_as_f32(imgs + di + 512, a4, false);
-            if (km) st_u8x16_as_f32(masks + dm, a5, true);
-        } else {
-            for (int k = 0; k < (two ? 2 : 1); k++) {
-                const size_t s0 = k ? q0 : p0, s1 = s0 + width;
-                for (size_t c = ((3 * s0) & ~(size_t)15) + 16 * (size_t)lane; c < 3 * s1; c += 512)
-                    st_u8x16_as_f32(imgs + c, ld_host16(imgs_host + c), false);
-                for (size_t c = (s0 & ~(size_t)15) + 16 * (size_t)lane; c < s1; c += 512)
-                    st_u8x16_as_f32(masks + c, ld_host16(masks_host + c), true);
+    const size_t vbase = (size_t)v * H * W;
+    const bool have = b.y > b.x && b.w > b.z;
+    // 1. the pull: two rows per warp iteration, all (up to) six loads in flight before the first store
+    if (have) {
+        const size_t width = (size_t)(b.w - b.z);
+        for (int r = b.x + warp; r < b.y; r += 2 * nw) {
+            const bool two = r + nw < b.y;
+            const size_t p0 = vbase + (size_t)r * W + b.z, q0 = p0 + (size_t)nw * W;
+            if (3 * width <= 1024 - 16) {
+                const size_t ci = ((3 * p0) & ~(size_t)15) + 16 * (size_t)lane, cm = (p0 & ~(size_t)15) + 16 * (size_t)lane;
+                const size_t di = ((3 * q0) & ~(size_t)15) + 16 * (size_t)lane, dm = (q0 & ~(size_t)15) + 16 * (size_t)lane;
+                const size_t ei = 3 * (p0 + width), fi = 3 * (q0 + width);
+                const bool l0 = ci < ei, l1 = ci + 512 < ei, lm = cm < p0 + width;
+                const bool k0 = two && di < fi, k1 = two && di + 512 < fi, km = two && dm < q0 + width;
+                uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0;
+                if (l0) a0 = ld_host16(imgs_host + ci);
+                if (l1) a1 = ld_host16(imgs_host + ci + 512);
+                if (lm) a2 = ld_host16(masks_host + cm);
+                if (k0) a3 = ld_host16(imgs_host + di);
+                if (k1) a4 = ld_host16(imgs_host + di + 512);
+                if (km) a5 = ld_host16(masks_host + dm);
+                if (l0) st_u8x16_as_f32(imgs + ci, a0, false);
+                if (l1) st_u8x16_as_f32(imgs + ci + 512, a1, false);
+                if (lm) st_u8x16_as_f32(masks + cm, a2, true);
+                if (k0) st_u8x16_as_f32(imgs + di, a3, false);
+                if (k1) st_u8x16_as_f32(imgs + di + 512, a4, false);
+                if (km) st_u8x16_as_f32(masks + dm, a5, true);
+            } else {
+                for (int k = 0; k < (two ? 2 : 1); k++) {
+                    const size_t s0 = k ? q0 : p0, s1 = s0 + width;
+                    for (size_t c = ((3 * s0) & ~(size_t)15) + 16 * (size_t)lane; c < 3 * s1; c += 512)
+                        st_u8x16_as_f32(imgs + c, ld_host16(imgs_host + c), false);
+                    for (size_t c = (s0 & ~(size_t)15) + 16 * (size_t)lane; c < s1; c += 512)
+                        st_u8x16_as_f32(masks + c, ld_host16(masks_host + c), true);
+                }
+            }
+        }
+    }
+    // 2. zero what the previous batch left in this view's mask plane and this batch does not overwrite
+    const int4 pb = prev_boxes[v];
+    if (pb.y > pb.x && pb.w > pb.z) {
+        const int4 nb = have ? b : make_int4(0, 0, 0, 0);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = pb.x + warp; r < pb.y; r += nw) {
+            const size_t p0 = vbase + (size_t)r * W + pb.z, p1 = p0 + (size_t)(pb.w - pb.z);
+            for (size_t c = (p0 & ~(size_t)15) + 16 * (size_t)lane; c < p1; c += 512) {
+                if (pull_owns_chunk(c, vbase, W, nb)) continue;
+                float4* d = reinterpret_cast<float4*>(masks + c);
+                d[0] = z; d[1] = z; d[2] = z; d[3] = z;
             }
         }
     }
@@ -2486,6 +2516,12 @@ struct SideStream {
     BoxGraph box_graph[2];  // captured copy lists of fmhr_ham_host_u8_submit_boxes, one per staging slot
     int4* box_dev[2] = {nullptr, nullptr};  // device copies of the box tables (pull-kernel form)
     int box_cap[2] = {0, 0};
+    // converted-on-arrival form: per plane set two box tables (this batch / the batch before it, whose mask rows the pull
+    // kernel zeroes) and the plane set for which "mask plane == 0 outside the previous boxes" is known to hold
+    int4* dbox[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int dbox_cap[2] = {0, 0}, dbox_cur[2] = {0, 0};
+    const void* dprimed[2] = {nullptr, nullptr};
+    int dprimed_n[2] = {0, 0};
     int dev = -1;
 };
 // Host batch in flight (fmhr_ham_step_host_u8): the render chain converts it right before the first kernel that reads
@@ -3373,7 +3409,7 @@ extern "C" int fmhr_ham_host_u8_submit_boxes_direct(const fmhr_ham_config* cfg, 
                                                     const uint8_t* masks_host, const int32_t* boxes_host,
                                                     const float* w2cs_host, const float* projs_host, float* imgs_dev,
                                                     float* masks_dev, float* w2cs_dev, float* projs_dev,
-                                                    size_t* h2d_bytes) {
+                                                    int fresh, size_t* h2d_bytes) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     FMHR_CHECK_ARG(imgs_host && masks_host && boxes_host && w2cs_host && projs_host && imgs_dev && masks_dev && w2cs_dev &&
@@ -3386,7 +3422,8 @@ extern "C" int fmhr_ham_host_u8_submit_boxes_direct(const fmhr_ham_config* cfg, 
         FMHR_CHECK_ARG(b[0] >= 0 && b[1] <= H && b[2] >= 0 && b[3] <= W);
     }
     void *d_imgs = nullptr, *d_masks = nullptr, *d_w2cs = nullptr, *d_projs = nullptr;
-    const bool can_pull = (P % 16 == 0) && (((uintptr_t)imgs_host | (uintptr_t)masks_host) & 15) == 0 &&
+    // (H * W % 16 == 0: a 16-element chunk of the flat planes never straddles two views)
+    const bool can_pull = (((size_t)H * W) % 16 == 0) && (((uintptr_t)imgs_host | (uintptr_t)masks_host) & 15) == 0 &&
                           cudaHostGetDevicePointer(&d_imgs, (void*)imgs_host, 0) == cudaSuccess &&
                           cudaHostGetDevicePointer(&d_masks, (void*)masks_host, 0) == cudaSuccess &&
                           cudaHostGetDevicePointer(&d_w2cs, (void*)w2cs_host, 0) == cudaSuccess &&
@@ -3394,31 +3431,60 @@ extern "C" int fmhr_ham_host_u8_submit_boxes_direct(const fmhr_ham_config* cfg, 
     if (!can_pull) {
         cudaGetLastError();
         set_error("fmhr_ham_host_u8_submit_boxes_direct: needs device-mapped, 16-byte aligned pinned host buffers and "
-                  "n*H*W %% 16 == 0; use fmhr_ham_host_u8_submit_boxes");
+                  "H*W %% 16 == 0; use fmhr_ham_host_u8_submit_boxes");
         return FMHR_EUNSUPPORTED;
     }
     SideStream* side = nullptr;
     rc = side_stream(&side);
     if (rc) return rc;
-    int slot = -1;
-    rc = submit_slot(side, imgs_dev, "fmhr_ham_host_u8_submit_boxes_direct", &slot);
-    if (rc) return rc;
+    // which of the two plane sets (the slot protocol's bookkeeping is done by submit_slot below; here only the index)
+    int slot = side->slot_ptr[0] == (void*)imgs_dev ? 0 : (side->slot_ptr[1] == (void*)imgs_dev ? 1 : -1);
+    if (slot < 0) slot = side->slot_ptr[0] == nullptr ? 0 : (side->slot_ptr[1] == nullptr ? 1 : -1);
+    if (slot < 0) slot = side->slot_used[0] ? 0 : (side->slot_used[1] ? 1 : -1);
+    if (slot < 0) {
+        set_error("fmhr_ham_host_u8_submit_boxes_direct: two submitted batches are already waiting for their steps on this device");
+        return FMHR_EINVAL;
+    }
     size_t bytes = (size_t)n * 32 * sizeof(float);
     for (int v = 0; v < n; v++) {
         const int32_t* b = boxes_host + 4 * v;
         if (b[1] > b[0] && b[3] > b[2]) bytes += (size_t)(b[1] - b[0]) * (size_t)(b[3] - b[2]) * 4;
     }
-    if (side->box_cap[slot] < n) {
-        if (side->box_dev[slot]) FMHR_CUDA(cudaFree(side->box_dev[slot]));
-        side->box_dev[slot] = nullptr;
-        FMHR_CUDA(cudaMalloc(&side->box_dev[slot], (size_t)n * sizeof(int4)));
-        side->box_cap[slot] = n;
+    if (side->dbox_cap[slot] < n) {
+        for (int k = 0; k < 2; k++) {
+            if (side->dbox[slot][k]) FMHR_CUDA(cudaFree(side->dbox[slot][k]));
+            side->dbox[slot][k] = nullptr;
+            FMHR_CUDA(cudaMalloc(&side->dbox[slot][k], (size_t)n * sizeof(int4)));
+        }
+        side->dbox_cap[slot] = n;
+        side->dprimed[slot] = nullptr;
     }
-    FMHR_CUDA(cudaMemcpyAsync(side->box_dev[slot], boxes_host, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, side->copy));
-    FMHR_CUDA(cudaMemsetAsync(masks_dev, 0, P * sizeof(float), side->copy));
-    ham_pull_boxes_f32_kernel<<<dim3(kPullBlocksPerView, n), kPullThreads, 0, side->copy>>>(
-        (const uint8_t*)d_imgs, (const uint8_t*)d_masks, side->box_dev[slot], H, W, imgs_dev, masks_dev, (const float*)d_w2cs,
-        (const float*)d_projs, w2cs_dev, projs_dev, n * 16);
+    const int cur = side->dbox_cur[slot] ^ 1, prv = cur ^ 1;
+    side->dbox_cur[slot] = cur;
+    const bool prime = fresh || side->dprimed[slot] != (const void*)masks_dev || side->dprimed_n[slot] != n;
+    // The box table goes up BEFORE the copy stream starts waiting for the plane set: table `cur` was last read by the pull
+    // two batches ago (finished, same stream), and when the set is released the pull kernel is then the first thing to
+    // launch - ahead of the next step's coverage kernel, whose blocks would otherwise fill every SM first.
+    if (prime) FMHR_CUDA(cudaMemsetAsync(side->dbox[slot][prv], 0, (size_t)n * sizeof(int4), side->copy));
+    FMHR_CUDA(cudaMemcpyAsync(side->dbox[slot][cur], boxes_host, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, side->copy));
+    int slot2 = -1;
+    rc = submit_slot(side, imgs_dev, "fmhr_ham_host_u8_submit_boxes_direct", &slot2);
+    if (rc) return rc;
+    FMHR_CHECK_ARG(slot2 == slot);
+    if (prime) {
+        // first batch into this plane set (or the caller says its content is undefined): establish "zero outside the
+        // previous boxes"
+        FMHR_CUDA(cudaMemsetAsync(masks_dev, 0, P * sizeof(float), side->copy));
+        side->dprimed[slot] = masks_dev;
+        side->dprimed_n[slot] = n;
+    }
+    // at most one block per SM (a second one would cost that SM a coverage block for the whole pull)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, side->dev);
+    const int pull_blocks = max(1, min(8, sms / n));
+    ham_pull_boxes_f32_kernel<<<dim3(pull_blocks, n), kPullThreads, 0, side->copy>>>(
+        (const uint8_t*)d_imgs, (const uint8_t*)d_masks, side->dbox[slot][cur], side->dbox[slot][prv], H, W, imgs_dev, masks_dev,
+        (const float*)d_w2cs, (const float*)d_projs, w2cs_dev, projs_dev, n * 16);
     FMHR_LAUNCH_CHECK();
     FMHR_CUDA(cudaEventRecord(side->slot_ready[slot], side->copy));
     if (h2d_bytes) *h2d_bytes = bytes;

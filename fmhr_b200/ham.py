@@ -514,6 +514,18 @@ class HostStreamingStepper:
                 out[v] = (ys[0], ys[-1] + 1, xs[0], xs[-1] + 1)
         return torch.from_numpy(out)
 
+    def ensure_direct_planes(self):
+        """The two float plane sets (images, masks, cameras) of the converted-on-arrival form.  The library owns their
+        content between submits (it keeps the mask planes zero outside the boxes of the last batch)."""
+        if getattr(self, "_planes", None) is None:
+            o = self.opt
+            mk = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=o.device)
+            self._planes = [(mk(self.n, o.H, o.W, 3), mk(self.n, o.H, o.W), mk(self.n, 4, 4), mk(self.n, 4, 4))
+                            for _ in range(2)]
+            self._next_plane = 0
+            self._plane_fresh = [True, True]  # content undefined for the library until its first batch
+        return self._planes
+
     def submit_u8(self, h_imgs_u8, h_masks_u8, boxes=None, cameras=None):
         """Start the upload of a host batch (pinned uint8 images [n,H,W,3] / masks [n,H,W]) into the next free staging
         buffer; returns a ticket for step_submitted_u8.  At most two batches may be in flight.  boxes (mask_boxes(): int32
@@ -537,11 +549,7 @@ class HostStreamingStepper:
                     raise RuntimeError("HostStreamingStepper: cameras must be pinned, contiguous float32 CPU tensors")
             if boxes.is_cuda or boxes.dtype != torch.int32 or tuple(boxes.shape) != (self.n, 4) or not boxes.is_contiguous():
                 raise RuntimeError("HostStreamingStepper: boxes must be a contiguous int32 CPU tensor [n,4]")
-            if getattr(self, "_planes", None) is None:
-                mk = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=o.device)
-                self._planes = [(mk(self.n, o.H, o.W, 3), mk(self.n, o.H, o.W), mk(self.n, 4, 4), mk(self.n, 4, 4))
-                                for _ in range(2)]
-                self._next_plane = 0
+            self.ensure_direct_planes()
             slot = self._next_plane
             self._next_plane ^= 1
             pl = self._planes[slot]
@@ -549,7 +557,9 @@ class HostStreamingStepper:
             with torch.cuda.device(o.device):
                 check(o.lib.fmhr_ham_host_u8_submit_boxes_direct(
                     ctypes.byref(cfg), ptr(h_imgs_u8), ptr(h_masks_u8), ptr(boxes), ptr(h_w2cs), ptr(h_projs), ptr(pl[0]),
-                    ptr(pl[1]), ptr(pl[2]), ptr(pl[3]), ctypes.byref(nb)), "ham_host_u8_submit_boxes_direct")
+                    ptr(pl[1]), ptr(pl[2]), ptr(pl[3]), 1 if self._plane_fresh[slot] else 0, ctypes.byref(nb)),
+                    "ham_host_u8_submit_boxes_direct")
+            self._plane_fresh[slot] = False
             self.last_submit_bytes = int(nb.value)
             return ("direct", slot)
         if getattr(self, "_stagings", None) is None:

@@ -364,12 +364,14 @@ int fmhr_ham_step_host_u8_submitted(const fmhr_ham_config* cfg, const fmhr_ham_b
  * step.  The caller keeps two such plane sets and alternates them; `imgs_dev` is the handle the slot protocol knows the set
  * by: fmhr_ham_step_host_u8_acquire(imgs_dev) / _release(imgs_dev) bracket the step, and fmhr_ham_step_host_u8_body is
  * called with buf->imgs / masks / w2cs / projs pointing at the set, staging = imgs_dev and w2cs_host = projs_host = NULL.
- * Needs device-mapped, 16-byte aligned host buffers and n*H*W % 16 == 0 (FMHR_EUNSUPPORTED otherwise: use the staging
+ * The library keeps masks_dev zero outside the boxes: a batch submitted with fresh != 0 (the set's content is undefined: newly
+ * allocated, or written by the caller) clears the plane, every later one zeroes the rows of the batch before it.
+ * Needs device-mapped, 16-byte aligned host buffers and H*W % 16 == 0 (FMHR_EUNSUPPORTED otherwise: use the staging
  * form).  *h2d_bytes (optional) receives the bytes pulled (4 per pixel of the rectangles + the cameras). */
 int fmhr_ham_host_u8_submit_boxes_direct(const fmhr_ham_config* cfg, const uint8_t* imgs_host, const uint8_t* masks_host,
                                          const int32_t* boxes_host, const float* w2cs_host, const float* projs_host,
                                          float* imgs_dev, float* masks_dev, float* w2cs_dev, float* projs_dev,
-                                         size_t* h2d_bytes);
+                                         int fresh, size_t* h2d_bytes);
 
 /* HAM initialisation (mesh_sfs_optim.py:124-177) on the same fused forward chain: every view of the batch is rendered
  * once (n_views rows of view_idx, normally all views), normals and coverage are antialiased, and

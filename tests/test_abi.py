@@ -95,7 +95,7 @@ def test_bad_arguments_return_codes_not_crashes(lib):
     assert lib.fmhr_ham_step_update_peer(None, None, None, None) == -1
     assert lib.fmhr_ham_host_u8_submit(None, None, None, None) == -1
     assert lib.fmhr_ham_host_u8_submit_boxes(None, None, None, None, None, None) == -1
-    assert lib.fmhr_ham_host_u8_submit_boxes_direct(None, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.fmhr_ham_host_u8_submit_boxes_direct(None, None, None, None, None, None, None, None, None, None, 0, None) == -1
     assert lib.fmhr_ham_step_host_u8_acquire(None, None) == -1 and lib.fmhr_ham_step_host_u8_release(None, None) == -1
     assert lib.fmhr_ham_step_host_u8_body(None, None, None, None, None, None, None, None) == -1
 

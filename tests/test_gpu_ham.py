@@ -404,7 +404,9 @@ def test_host_streaming_async_loss_ring(scene, graphs, direct):
     the one the synchronous form returns for the same step, in order.
     direct: converted-on-arrival batches (submit_u8(cameras=...) -> fmhr_ham_host_u8_submit_boxes_direct): the pull kernel
     writes the ticket's own float planes and the cameras travel with the batch; the planes are poisoned first (mask plane
-    with ones, image plane with NaN), and the records must equal the resident path's."""
+    with ones, image plane with NaN), and the records must equal the resident path's.  The two alternating batches have
+    DIFFERENT boxes (the second one's are shrunk), so the rows the previous batch left in a mask plane must be zeroed by
+    the next pull."""
     import copy
     from fmhr_b200.ham import HostStreamingStepper
     n, H, W = scene["imgs"].shape[0], scene["imgs"].shape[1], scene["imgs"].shape[2]
@@ -418,10 +420,17 @@ def test_host_streaming_async_loss_ring(scene, graphs, direct):
     q["masks"] = (msk_u8 > 127).astype(np.float32)
     pin = lambda x, dt: torch.tensor(x, dtype=dt).contiguous().pin_memory()
     h_imgs = [pin(img_a, torch.uint8), pin(img_b, torch.uint8)]
-    h_msk, h_w2c, h_proj = pin(msk_u8, torch.uint8), pin(scene["w2cs"], torch.float32), pin(scene["projs"], torch.float32)
+    h_w2c, h_proj = pin(scene["w2cs"], torch.float32), pin(scene["projs"], torch.float32)
     views = torch.arange(n, dtype=torch.int32, device="cuda")
-    boxes = HostStreamingStepper.mask_boxes(msk_u8)
-    steps = 6
+    # three segmentation variants cycle (full / right half / lower half), so that every plane set sees its boxes change
+    # from batch to batch in both directions
+    mvar = [msk_u8.copy(), msk_u8.copy(), msk_u8.copy()]
+    mvar[1][:, :, : W // 2] = 0
+    mvar[2][:, : H // 2, :] = 0
+    h_msks = [pin(m, torch.uint8) for m in mvar]
+    boxes_v = [HostStreamingStepper.mask_boxes(m) for m in mvar]
+    assert not torch.equal(boxes_v[0], boxes_v[1]) and not torch.equal(boxes_v[0], boxes_v[2])
+    steps = 7
 
     def run(async_record):
         o = _make_opt(q, debug=False)
@@ -431,15 +440,14 @@ def test_host_streaming_async_loss_ring(scene, graphs, direct):
         out, inflight = [], []
         cams = (h_w2c, h_proj) if direct else None
         slot_of = lambda t: t[1] if isinstance(t, tuple) else t
-        ticket = st.submit_u8(h_imgs[0], h_msk, boxes, cameras=cams)
-        if direct:  # poison both plane sets, then submit again (into the other set)
-            torch.cuda.synchronize()
-            for pl in st._planes:
+        if direct:  # poison both plane sets before their first batch (which must clear the mask plane)
+            for pl in st.ensure_direct_planes():
                 pl[0].fill_(float("nan")); pl[1].fill_(1.0); pl[2].fill_(float("nan")); pl[3].fill_(float("nan"))
             torch.cuda.synchronize()
-            ticket = st.submit_u8(h_imgs[0], h_msk, boxes, cameras=cams)
+        ticket = st.submit_u8(h_imgs[0], h_msks[0], boxes_v[0], cameras=cams)
         for i in range(steps):
-            nxt = st.submit_u8(h_imgs[(i + 1) % 2], h_msk, boxes, cameras=cams) if i + 1 < steps else None
+            j = i + 1
+            nxt = st.submit_u8(h_imgs[j % 2], h_msks[j % 3], boxes_v[j % 3], cameras=cams) if j < steps else None
             rec = st.step_submitted_u8(ticket, None if direct else h_w2c, None if direct else h_proj, views,
                                        async_record=async_record)
             if async_record:
@@ -459,9 +467,11 @@ def test_host_streaming_async_loss_ring(scene, graphs, direct):
     if direct:  # against the resident path on the same quantised batches
         a = _make_opt(q, debug=False)
         f_imgs = [torch.tensor(x.astype(np.float32) / np.float32(255.0)).cuda() for x in (img_a, img_b)]
+        f_msks = [torch.tensor((m > 127).astype(np.float32)).cuda() for m in mvar]
         res = []
         for i in range(steps):
             a.imgs.copy_(f_imgs[i % 2])
+            a.masks.copy_(f_msks[i % 3])
             res.append(a.step_phase_b(views).cpu())
         assert torch.allclose(torch.stack(res), sync_recs, rtol=1e-4, atol=1e-6), (torch.stack(res), sync_recs)
     assert ring_recs.shape == (steps, 8) and torch.isfinite(ring_recs).all()

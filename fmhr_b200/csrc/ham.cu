@@ -2400,16 +2400,19 @@ __device__ __forceinline__ void st_u8x16_as_f32(float* dst, uint4 v, bool mask) 
         reinterpret_cast<float4*>(dst)[k] = f;
     }
 }
-// Footprint: the pull takes ~110 us (PCIe-bound) and must run BESIDE the step that is in flight without taking SM slots
-// from it.  The coverage kernel's five blocks per SM leave exactly 4,096 registers and no room for anything the size of a
-// normal block, so the pull uses blocks of 64 threads x 64 registers (one fits beside the coverage blocks on every SM) and
-// starts with the step instead of in the coverage kernel's last wave; with 8 x 256-thread blocks per view it ran beside
-// the shade pass, which lost half of its occupancy and took 2.4x as long.  No memset node in front of it either (a
-// memset also waits for the coverage kernel's tail): the mask plane is zero outside the boxes of the batch that was
-// pulled into this plane set before (prev), so the kernel zeroes those rows' chunks itself - except the chunks the new
-// rows write - and then pulls.  Chunk = 16 consecutive elements of the flat plane (the byte index of the u8 planes IS the
-// element index of the float planes); a row segment is written as the whole chunks it touches.
-constexpr int kPullThreads = 64;
+// Footprint: the pull takes ~110 - 160 us (PCIe-bound) and runs BESIDE the step that is in flight.  Its warps sit on
+// system-memory loads for microseconds, and the kernels that share the chip with them slow down by a roughly constant 35 - 40 us
+// per step wherever the pull lands (CUPTI timelines, profiles/r2/README.md): 384 x 256 threads beside the shade pass -> shade
+// 44 -> 107 us; 96 x 128 threads beside shade / antialias -> 62 / 48 instead of 44 / 35 us; one 64-thread block on EVERY SM
+// beside the coverage kernel -> coverage 66 -> 196 us; 48 ... 128 blocks of 256 threads launched ahead of the step -> coverage 92,
+// scan 23, shade 47 us, the end-to-end rate flat at 4,190 - 4,210 iters/s; fewer than 48 blocks cannot keep the PCIe link busy
+// (16 blocks: 350 us per pull).  So: kPullBlocks blocks of 256 threads, each walking several views, launched AHEAD of the
+// step's first kernel (the box table is uploaded before the copy stream waits for the plane set).  No memset node in front of
+// it either: the mask plane is zero outside the boxes of the batch that was pulled into this plane set before (prev), so the
+// kernel zeroes those rows' chunks itself - except the chunks the new rows write - and then pulls.  Chunk = 16 consecutive
+// elements of the flat plane (the byte index of the u8 planes IS the element index of the float planes); a row segment is
+// written as the whole chunks it touches.
+constexpr int kPullThreads = 256, kPullBlocks = 64;
 __device__ __forceinline__ bool pull_owns_chunk(size_t c, size_t vbase, int W, int4 nb) {
     // is chunk [c, c + 16) written by the pull of box nb = (y0, y1, x0, x1) of the view starting at element vbase?
     const size_t e0 = c - vbase;
@@ -2421,13 +2424,12 @@ __device__ __forceinline__ bool pull_owns_chunk(size_t c, size_t vbase, int W, i
     }
     return false;
 }
-__global__ void __launch_bounds__(kPullThreads, 16) ham_pull_boxes_f32_kernel(
+__global__ void __launch_bounds__(kPullThreads) ham_pull_boxes_f32_kernel(
     const uint8_t* __restrict__ imgs_host, const uint8_t* __restrict__ masks_host, const int4* __restrict__ boxes,
     const int4* __restrict__ prev_boxes, int H, int W, float* __restrict__ imgs, float* __restrict__ masks,
     const float* __restrict__ w2cs_host, const float* __restrict__ projs_host, float* __restrict__ w2cs,
-    float* __restrict__ projs, int n_cam_floats) {
-    const int v = blockIdx.y;
-    if (v == 0 && blockIdx.x == gridDim.x - 1) {
+    float* __restrict__ projs, int n_cam_floats, int n_views) {
+    if (blockIdx.x == gridDim.x - 1) {
         for (int i = threadIdx.x; i < n_cam_floats; i += blockDim.x) {
             float a, b;
             asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(a) : "l"(w2cs_host + i) : "memory");
@@ -2436,9 +2438,10 @@ __global__ void __launch_bounds__(kPullThreads, 16) ham_pull_boxes_f32_kernel(
             projs[i] = b;
         }
     }
-    const int4 b = boxes[v];  // y0, y1, x0, x1
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;  // a view is walked by the warps of ONE block
+    for (int v = blockIdx.x; v < n_views; v += gridDim.x) {
+    const int4 b = boxes[v];  // y0, y1, x0, x1
     const size_t vbase = (size_t)v * H * W;
     const bool have = b.y > b.x && b.w > b.z;
     // 1. the pull: two rows per warp iteration, all (up to) six loads in flight before the first store
@@ -2491,6 +2494,7 @@ __global__ void __launch_bounds__(kPullThreads, 16) ham_pull_boxes_f32_kernel(
             }
         }
     }
+    }  // views of this block
 }
 
 // Side stream for work that is independent of the rendering chain (forked / joined with events, so it is captured into
@@ -3478,13 +3482,11 @@ extern "C" int fmhr_ham_host_u8_submit_boxes_direct(const fmhr_ham_config* cfg, 
         side->dprimed[slot] = masks_dev;
         side->dprimed_n[slot] = n;
     }
-    // at most one block per SM (a second one would cost that SM a coverage block for the whole pull)
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, side->dev);
-    const int pull_blocks = max(1, min(8, sms / n));
-    ham_pull_boxes_f32_kernel<<<dim3(pull_blocks, n), kPullThreads, 0, side->copy>>>(
+    static const int env_blocks = [] { const char* e = getenv("FMHR_PULL_BLOCKS"); return e ? atoi(e) : 0; }();
+    const int pull_blocks = max(1, min(n, env_blocks > 0 ? env_blocks : kPullBlocks));
+    ham_pull_boxes_f32_kernel<<<pull_blocks, kPullThreads, 0, side->copy>>>(
         (const uint8_t*)d_imgs, (const uint8_t*)d_masks, side->dbox[slot][cur], side->dbox[slot][prv], H, W, imgs_dev, masks_dev,
-        (const float*)d_w2cs, (const float*)d_projs, w2cs_dev, projs_dev, n * 16);
+        (const float*)d_w2cs, (const float*)d_projs, w2cs_dev, projs_dev, n * 16, n);
     FMHR_LAUNCH_CHECK();
     FMHR_CUDA(cudaEventRecord(side->slot_ready[slot], side->copy));
     if (h2d_bytes) *h2d_bytes = bytes;

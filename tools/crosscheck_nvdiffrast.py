@@ -34,6 +34,8 @@ def import_upstream():
         del sys.modules[k]
     try:
         up = importlib.import_module("nvdiffrast.torch")
+    except ImportError:
+        raise SystemExit("crosscheck: upstream nvdiffrast is not installed on this box (nothing to compare against)")
     finally:
         sys.path[:] = saved
     if os.path.abspath(os.path.dirname(os.path.dirname(up.__file__))) == ROOT:

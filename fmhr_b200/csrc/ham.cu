@@ -2620,6 +2620,12 @@ static GroupView group_view(const fmhr_ham_config* cfg, const fmhr_ham_buffers* 
         v.tlist[s2] = ws.tlist[s2] + (size_t)v.v0 * tiles_pv;
     }
     v.rcap = (int)(v.Pg / 2); v.pcap = (int)(v.Pg / 2); v.qcap = (int)(v.Pg / 4);
+    // Test hook (tests/test_gpu_ham.py::test_work_list_overflow_poisons_the_loss_record): FMHR_TEST_LIST_CAP shrinks the ring
+    // and pair lists so that the overflow path - entries dropped, status bit set, losses[7] = NaN - can be exercised on a
+    // normal scene.  rcap = P/2 is NOT the worst case (scattered single-pixel coverage has up to 0.8 P ring pixels): such a
+    // frame is refused with the NaN flag, not silently mis-evaluated.
+    static const int test_cap = [] { const char* e = getenv("FMHR_TEST_LIST_CAP"); return e ? atoi(e) : 0; }();
+    if (test_cap > 0) { v.rcap = min(v.rcap, test_cap); v.pcap = min(v.pcap, test_cap); }
     return v;
 }
 

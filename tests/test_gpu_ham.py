@@ -1,5 +1,7 @@
 """GPU parity of the models/utils.py counterparts and of the fused HAM iteration against the oracle
 (oracle.refmath pinned by the reference's own outputs in tests/golden; oracle.ham = the restated loop)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -395,6 +397,37 @@ def test_host_streaming_u8_step_matches_resident(scene):
     assert _traj_close(a.delta, b.delta, scene["conf"]["lr"])
     with pytest.raises(RuntimeError):
         stepper.step_phase_b_u8(h[0].float().pin_memory(), h[1], h[2], h[3], views)
+
+
+def test_work_list_overflow_poisons_the_loss_record():
+    """The ring list (empty pixels next to covered ones) and the pair list have capacity P / 2.  When a frame needs more,
+    entries are dropped and the mask loss would be wrong - the step must say so: status bits 0 / 1 -> losses[7] = NaN (the
+    other entries stay finite).  FMHR_TEST_LIST_CAP shrinks both lists so that the small scene overflows them; the library
+    reads the variable once, hence the subprocess."""
+    import subprocess
+    import sys
+    script = r"""
+import sys, warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, %r)
+import torch
+from fmhr_b200 import synth
+from fmhr_b200.ham import HamOptimizer
+from oracle import ham as oham
+scene = synth.build_scene("small", oham.render_views)
+c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt).cuda()
+opt = HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"), c("projs"),
+                   c("sh_coeffs"), c("albedo"), scene["conf"])
+rec = opt.step_phase_b(list(range(scene["imgs"].shape[0]))).cpu()
+print("RECORD", rec.tolist())
+assert bool(torch.isfinite(rec[:7]).all()) and float(rec[6]) > 0
+print("TOTAL_IS_NAN", bool(torch.isnan(rec[7])))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cap, want in (("64", True), ("0", False)):
+        env = dict(os.environ, FMHR_TEST_LIST_CAP=cap)
+        r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        assert ("TOTAL_IS_NAN %s" % want) in r.stdout, (cap, r.stdout[-500:])
 
 
 @pytest.mark.parametrize("graphs,direct", [(False, False), (True, False), (False, True), (True, True)])

@@ -111,11 +111,21 @@ __device__ __forceinline__ unsigned long long trace_now() {
 }
 struct TraceScope {
     int id;
+    // slot id: [first block entry, last block exit]; slot id + 32: [first block EXIT, last block ENTRY] - the spread of the
+    // blocks' entries (fill: blocks that had to wait for a slot) and of their exits (tail: imbalance of the work split)
     __device__ __forceinline__ explicit TraceScope(int i) : id(i) {
-        if (threadIdx.x == 0) atomicMin(&g_trace[id][0], trace_now());
+        if (threadIdx.x == 0) {
+            const unsigned long long t = trace_now();
+            atomicMin(&g_trace[id][0], t);
+            if (id < 32) atomicMax(&g_trace[id + 32][1], t);
+        }
     }
     __device__ __forceinline__ ~TraceScope() {
-        if (threadIdx.x == 0) atomicMax(&g_trace[id][1], trace_now());  // (thread 0's exit stands for the block's)
+        if (threadIdx.x == 0) {  // (thread 0's exit stands for the block's)
+            const unsigned long long t = trace_now();
+            atomicMax(&g_trace[id][1], t);
+            if (id < 32) atomicMin(&g_trace[id + 32][0], t);
+        }
     }
 };
 __device__ __forceinline__ void trace_stamp_min(int id, int k) { atomicMin(&g_trace[id][k], trace_now()); }

@@ -55,6 +55,9 @@ static __device__ unsigned int g_dcheck;
 #ifndef FMHR_AA_HOIST
 #define FMHR_AA_HOIST 0
 #endif
+#ifndef FMHR_PAIR_SECTORS
+#define FMHR_PAIR_SECTORS 1  // shade pass: lane pairs complete whole 32-byte sectors per vector RED (scatter_sector_pairs)
+#endif
 #ifndef FMHR_LB_BWD
 #define FMHR_LB_BWD 3
 #endif
@@ -868,7 +871,12 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
     };
     const int u0 = blockIdx.x * 8 + wib, ustride = gridDim.x * 8;
     const int lx = lane & 15, ly = lane >> 4;
+    // A warp owns only one or two units of each loop, so the kernel's length is the length of its dependent load chains:
+    // both list lengths and the first tile entries of BOTH loops are requested up front, every unit's next tile entry is
+    // requested before its keys are consumed, and the border keys travel with the unit's own keys (one level instead of two).
     const int nd = *tcount_next;
+    const int nt = *tcount;
+    uint32_t te_next = u0 < 2 * nt ? __ldg(tlist + (u0 >> 1)) : 0u;
     for (int u = u0; u < 2 * nd; u += ustride) {
         const TileCtx tc = tile_decode(__ldg(tlist_next + (u >> 1)), tiles_x, tiles_y);
         const int px = tc.bx * kTile + lx, py0 = tc.by * kTile + (u & 1) * 8 + ly;
@@ -878,9 +886,9 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
                 if (py0 + 2 * k < H) zbuf_next[((size_t)tc.n * H + py0 + 2 * k) * W + px] = ZB_EMPTY;
         }
     }
-    const int nt = *tcount;
     for (int u = u0; u < 2 * nt; u += ustride) {
-        const TileCtx tc = tile_decode(__ldg(tlist + (u >> 1)), tiles_x, tiles_y);
+        const TileCtx tc = tile_decode(te_next, tiles_x, tiles_y);
+        if (u + ustride < 2 * nt) te_next = __ldg(tlist + ((u + ustride) >> 1));
         const int px = tc.bx * kTile + lx, py0 = tc.by * kTile + (u & 1) * 8 + ly;
         const unsigned long long* zb = zbuf + (size_t)tc.n * H * W;
         unsigned long long key[4];
@@ -889,26 +897,23 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
             const int py = py0 + 2 * k;
             key[k] = (px < W && py < H) ? zb[(size_t)py * W + px] : ZB_EMPTY;
         }
+        // Emptiness of the 4-neighbours of the covered pixels.  Inside the 16x8 unit it is in the ballot words (bit lx +
+        // 16 * (row & 1) of m[row >> 1]); only the unit's border needs keys from memory: ONE load for the rows above /
+        // below (lanes 0-15 / 16-31) and ONE for the columns left / right (lanes 0-7 / 8-15) instead of 16 per lane.
+        const int uy0 = tc.by * kTile + (u & 1) * 8;  // first row of the unit
+        const int qy = ly == 0 ? uy0 - 1 : uy0 + 8;
+        const bool in = px < W && qy >= 0 && qy < H;
+        const unsigned long long kq = in ? zb[(size_t)qy * W + px] : 0ull;
+        const int qx = lane < 8 ? tc.bx * kTile - 1 : tc.bx * kTile + 16, qr = uy0 + (lane & 7);
+        const bool in2 = lane < 16 && qx >= 0 && qx < W && qr < H;
+        const unsigned long long kq2 = in2 ? zb[(size_t)qr * W + qx] : 0ull;
         unsigned m[4];
         int total = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, key[k] != ZB_EMPTY); total += __popc(m[k]); }
         if (total == 0) continue;
-        // Emptiness of the 4-neighbours of the covered pixels.  Inside the 16x8 unit it is in the ballot words (bit lx +
-        // 16 * (row & 1) of m[row >> 1]); only the unit's border needs keys from memory: ONE load for the rows above /
-        // below (lanes 0-15 / 16-31) and ONE for the columns left / right (lanes 0-7 / 8-15) instead of 16 per lane.
-        const int uy0 = tc.by * kTile + (u & 1) * 8;  // first row of the unit
-        unsigned e_tb, e_lr;
-        {
-            const int qy = ly == 0 ? uy0 - 1 : uy0 + 8;
-            const bool in = px < W && qy >= 0 && qy < H;
-            const unsigned long long kq = in ? zb[(size_t)qy * W + px] : 0ull;
-            e_tb = __ballot_sync(0xffffffffu, in && kq == ZB_EMPTY);
-            const int qx = lane < 8 ? tc.bx * kTile - 1 : tc.bx * kTile + 16, qr = uy0 + (lane & 7);
-            const bool in2 = lane < 16 && qx >= 0 && qx < W && qr < H;
-            const unsigned long long kq2 = in2 ? zb[(size_t)qr * W + qx] : 0ull;
-            e_lr = __ballot_sync(0xffffffffu, in2 && kq2 == ZB_EMPTY);
-        }
+        const unsigned e_tb = __ballot_sync(0xffffffffu, in && kq == ZB_EMPTY);
+        const unsigned e_lr = __ballot_sync(0xffffffffu, in2 && kq2 == ZB_EMPTY);
         unsigned emask = 0u;  // bit 4k + d: neighbour d (right, left, down, up) of this lane's pixel in row 2k + ly is empty
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -992,9 +997,12 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
 // normals + albedo planes (phase A); tags the z-buffer key with the triangle's silhouette-candidate bits and the valid
 // flag (one 32-bit RED), and records the valid flag in the list entry for the backward pass.
 // ------------------------------------------------------------------------------------------------
-template <int PHASE>
+struct DeferredScatter { int vi[3]; float4 lo[3], hi[3]; };  // corner records of one pixel's backward, vi < 0: none
+template <int PHASE, bool DEFER>
 __device__ __forceinline__ void pixel_backward_q(const PixTri& q, int px, int py, float4 gin, const float* __restrict__ M,
-                                                 const float* __restrict__ c, int V, int H, int W, float4* __restrict__ G);
+                                                 const float* __restrict__ c, int V, int H, int W, float4* __restrict__ G,
+                                                 DeferredScatter* def);
+__device__ __forceinline__ void scatter_sector_pairs(const DeferredScatter& d, float4* __restrict__ G);
 
 // BWD (phase B training step): the pixel's own loss gradient is known right here for every pixel that does not RECEIVE an
 // antialias blend - tmp_img == pred_img there, so d|tmp - img| = sign(pred - img) - and those are > 95 % of the pixels.
@@ -1025,7 +1033,16 @@ __global__ void __launch_bounds__(256, BWD ? FMHR_LB_SHADE_BWD : FMHR_LB_SHADE) 
     // the NEXT list entry is loaded before this entry's gather chain starts (one dependent level less per iteration)
     const int e_first = blockIdx.x * blockDim.x + threadIdx.x, e_stride = gridDim.x * blockDim.x;
     uint2 ent_next = e_first < nc ? clist[e_first] : make_uint2(0u, 0u);
+#if FMHR_PAIR_SECTORS
+    // (the scatter at the end of the body exchanges records between lane pairs: the trip count is the warp's, not the lane's)
+    for (int e = e_first; e - (int)(threadIdx.x & 31) < nc; e += e_stride) {
+        DeferredScatter dsc;
+        dsc.vi[0] = dsc.vi[1] = dsc.vi[2] = -1;
+        if (e < nc) {
+#else
     for (int e = e_first; e < nc; e += e_stride) {
+        {
+#endif
         const uint2 ent = ent_next;
         if (e + e_stride < nc) ent_next = clist[e + e_stride];
         const size_t pix = ent.x;
@@ -1075,7 +1092,12 @@ __global__ void __launch_bounds__(256, BWD ? FMHR_LB_SHADE_BWD : FMHR_LB_SHADE) 
                 if (BWD) {
                     const float s0 = sgnf(col.x - tg0), s1 = sgnf(col.y - tg1), s2 = sgnf(col.z - tg2);
                     col.w = __uint_as_float(pack_signs(s0, s1, s2));
-                    pixel_backward_q<1>(q, px, py, make_float4(s0, s1, s2, 0.f), Mv, sh, V, H, W, G);
+#if FMHR_PAIR_SECTORS
+                    if (s0 != 0.f || s1 != 0.f || s2 != 0.f)
+                        pixel_backward_q<1, true>(q, px, py, make_float4(s0, s1, s2, 0.f), Mv, sh, V, H, W, G, &dsc);
+#else
+                    pixel_backward_q<1, false>(q, px, py, make_float4(s0, s1, s2, 0.f), Mv, sh, V, H, W, G, nullptr);
+#endif
                 }
             }
             plane0[pix] = col;
@@ -1083,6 +1105,10 @@ __global__ void __launch_bounds__(256, BWD ? FMHR_LB_SHADE_BWD : FMHR_LB_SHADE) 
             plane0[pix] = make_float4(m.x, m.y, m.z, valid ? 1.0f : 0.0f);
             plane1[pix] = make_float4(a.x, a.y, a.z, 0.0f);
         }
+        }
+#if FMHR_PAIR_SECTORS
+        if (BWD) scatter_sector_pairs(dsc, G);
+#endif
     }
     warp_acc_add(acc, 0, nvalid);
 }
@@ -1449,10 +1475,10 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
 // (pixel kernel) and the antialias pair terms (pair kernel) are back-propagated independently.
 // Core of the shading backward for a pixel whose triangle record `q` (clip positions, barycentrics, attributes) is
 // already in registers: the shade pass calls it right after the forward (phase B), pixel_backward() loads the record first.
-template <int PHASE>
+template <int PHASE, bool DEFER>
 __device__ __forceinline__ void pixel_backward_q(const PixTri& q, int px, int py, float4 gin, const float* __restrict__ M,
                                                  const float* __restrict__ c, int V, int H, int W,
-                                                 float4* __restrict__ G) {
+                                                 float4* __restrict__ G, DeferredScatter* def) {
     const float4 g0 = gin, g1 = gin;
     const float w = 1.0f - q.u - q.v;
     if (PHASE == 0) {
@@ -1525,9 +1551,37 @@ __device__ __forceinline__ void pixel_backward_q(const PixTri& q, int px, int py
             a1 = gk.x; a2 = gk.y;
             atomicAdd(reinterpret_cast<float*>(G + 2 * (size_t)V + vi[k]) + 3, gk.z);
         }
-        float4* Gk = G + 2 * (size_t)vi[k];
-        atomicAdd(Gk, make_float4(wp[k].x, wp[k].y, wp[k].z, a1));
-        atomicAdd(Gk + 1, make_float4(a2, wt[k] * ga.x, wt[k] * ga.y, wt[k] * ga.z));
+        if (DEFER) {
+            def->vi[k] = vi[k];
+            def->lo[k] = make_float4(wp[k].x, wp[k].y, wp[k].z, a1);
+            def->hi[k] = make_float4(a2, wt[k] * ga.x, wt[k] * ga.y, wt[k] * ga.z);
+        } else {
+            float4* Gk = G + 2 * (size_t)vi[k];
+            atomicAdd(Gk, make_float4(wp[k].x, wp[k].y, wp[k].z, a1));
+            atomicAdd(Gk + 1, make_float4(a2, wt[k] * ga.x, wt[k] * ga.y, wt[k] * ga.z));
+        }
+    }
+}
+
+// Scatter of the deferred corner records with every lane of the warp present (lanes without a record carry vi = -1):
+// lane pairs (2j, 2j+1) write BOTH 16-byte halves of one vertex record in the same instruction - first the even lane's
+// record, then the odd lane's - so every red.v4 instruction completes whole 32-byte sectors instead of touching 32 half
+// sectors (tools/ubench/red_bench.cu form C against form B: 20.5 vs 24.6 us for the iteration's references; in the shade
+// pass: 5,223 -> 5,292 iters/s, profiles/r2/README.md).
+__device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                       __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+__device__ __forceinline__ void scatter_sector_pairs(const DeferredScatter& d, float4* __restrict__ G) {
+    const bool odd = (threadIdx.x & 1) != 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        // the half the partner will write for this lane: an even lane writes lower halves, an odd lane upper halves
+        const float4 got = shfl_xor4(odd ? d.lo[k] : d.hi[k], 1);
+        const int vo = __shfl_xor_sync(0xffffffffu, d.vi[k], 1);
+        const int v_even = odd ? vo : d.vi[k], v_odd = odd ? d.vi[k] : vo;
+        if (v_even >= 0) atomicAdd(G + 2 * (size_t)v_even + (odd ? 1 : 0), odd ? got : d.lo[k]);
+        if (v_odd >= 0) atomicAdd(G + 2 * (size_t)v_odd + (odd ? 1 : 0), odd ? d.hi[k] : got);
     }
 }
 
@@ -1543,7 +1597,7 @@ __device__ __forceinline__ void pixel_backward(uint32_t pix32, int tself, float4
     const float* c = sh_coeffs + (size_t)__ldg(sh_idx + n) * 9;
     PixTri q;
     load_pixtri(tself, px, py, trirec, M, invW, invH, q);
-    pixel_backward_q<PHASE>(q, px, py, gin, M, c, V, H, W, G);
+    pixel_backward_q<PHASE, false>(q, px, py, gin, M, c, V, H, W, G, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

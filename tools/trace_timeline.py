@@ -76,11 +76,16 @@ def main():
     period = float(np.median(np.diff(rows[:, used, 0].min(axis=1)))) / 1e3 if reps > 1 else 0.0
     t0 = rows[:, used, 0].min(axis=1, keepdims=True)
     out = {}
+    used = [k for k in used if k < 32]
     for j, k in enumerate(used):
         s = (rows[:, k, 0] - t0[:, 0]) / 1e3
         e = (rows[:, k, 1] - t0[:, 0]) / 1e3
         out[NAMES.get(k, str(k))] = {"start_us": float(np.median(s)), "end_us": float(np.median(e)),
                                       "dur_us": float(np.median(e - s))}
+        if k < 20 and (rows[:, k + 32, 1] > 0).all():  # kernel scopes: spread of the blocks' entries and exits
+            le = (rows[:, k + 32, 1] - t0[:, 0]) / 1e3
+            fx = (rows[:, k + 32, 0] - t0[:, 0]) / 1e3
+            out[NAMES.get(k, str(k))].update({"last_entry_us": float(np.median(le)), "first_exit_us": float(np.median(fx))})
     total = float(np.median((rows[:, used, 1].max(axis=1) - t0[:, 0]) / 1e3))
     import time
     time.sleep(0.2 * rank)  # keep the ranks' tables apart
@@ -88,7 +93,9 @@ def main():
         print("rank %d: %s, %d views, graph=%s: first block entry -> last block exit = %.1f us, step period %.1f us "
               "(median of %d free-running steps)" % (rank, a.workload, n, not a.no_graphs, total, period, reps))
         for name, v in sorted(out.items(), key=lambda kv: kv[1]["start_us"]):
-            print("  %-40s start %8.1f  end %8.1f  dur %7.1f" % (name, v["start_us"], v["end_us"], v["dur_us"]))
+            extra = ("   last block entry %8.1f  first block exit %8.1f" % (v["last_entry_us"], v["first_exit_us"])
+                     if "last_entry_us" in v else "")
+            print("  %-40s start %8.1f  end %8.1f  dur %7.1f%s" % (name, v["start_us"], v["end_us"], v["dur_us"], extra))
     if a.out and rank == 0:
         json.dump({"workload": a.workload, "views": n, "total_us": total, "kernels": out}, open(a.out, "w"), indent=1)
     if world > 1:

@@ -55,6 +55,15 @@ static __device__ unsigned int g_dcheck;
 #ifndef FMHR_AA_HOIST
 #define FMHR_AA_HOIST 0
 #endif
+#ifndef FMHR_COV_SMEM_FLOOR
+#define FMHR_COV_SMEM_FLOOR 0
+#endif
+#ifndef FMHR_SIDE2
+#define FMHR_SIDE2 0  // regulariser forward / gradients on a second side stream behind the normals (beside the triangle records)
+#endif
+#ifndef FMHR_INTERLEAVE
+#define FMHR_INTERLEAVE 0  // bit 0: shade, bit 1: antialias - consecutive warp batches go to different blocks
+#endif
 #ifndef FMHR_PAIR_SECTORS
 #define FMHR_PAIR_SECTORS 1  // shade pass: lane pairs complete whole 32-byte sectors per vector RED (scatter_sector_pairs)
 #endif
@@ -772,11 +781,6 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ double acc_total(const double* acc, int k) {
-    double s = 0.0;
-    for (int j = 0; j < 32; j++) s += acc[k * 32 + j];
-    return s;
-}
 
 // global pixel index -> view slot, coordinates
 struct PixAddr { int n, px, py, rem; };
@@ -1031,7 +1035,9 @@ __global__ void __launch_bounds__(256, BWD ? FMHR_LB_SHADE_BWD : FMHR_LB_SHADE) 
     const int hw = H * W;
     float nvalid = 0.0f;
     // the NEXT list entry is loaded before this entry's gather chain starts (one dependent level less per iteration)
-    const int e_first = blockIdx.x * blockDim.x + threadIdx.x, e_stride = gridDim.x * blockDim.x;
+    const int e_stride = gridDim.x * blockDim.x;
+    const int e_first = (FMHR_INTERLEAVE & 1) ? (int)(((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31))
+                                              : (int)(blockIdx.x * blockDim.x + threadIdx.x);
     uint2 ent_next = e_first < nc ? clist[e_first] : make_uint2(0u, 0u);
 #if FMHR_PAIR_SECTORS
     // (the scatter at the end of the body exchanges records between lane pairs: the trip count is the warp's, not the lane's)
@@ -1189,8 +1195,10 @@ __global__ void __launch_bounds__(256, FMHR_LB_AA) ham_aa_loss_kernel(
     auto list_pixel = [&](int e) -> uint32_t { return e < nc ? clist[e].x : rlist[e - nc]; };
     const int e_stride = gridDim.x * blockDim.x;
     uint32_t pix_next = 0u;  // the NEXT list entry is loaded before this batch's key / analysis chain starts
-    if ((int)(blockIdx.x * blockDim.x + threadIdx.x) < total) pix_next = list_pixel(blockIdx.x * blockDim.x + threadIdx.x);
-    for (int e0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; e0 < total; e0 += e_stride) {
+    const int e_first = (FMHR_INTERLEAVE & 2) ? (int)((wib * gridDim.x + blockIdx.x) * 32 + lane)
+                                              : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (e_first < total) pix_next = list_pixel(e_first);
+    for (int e0 = e_first - lane; e0 < total; e0 += e_stride) {
         const int e = e0 + lane;
         const bool active = e < total;
         const uint32_t pix32 = active ? pix_next : 0u;
@@ -1621,8 +1629,11 @@ __global__ void __launch_bounds__(128) ham_pair_bwd_kernel(
     if (PHASE == 1 && qlist) {
         // corrections of the shade pass' speculative backward: pixels whose antialiased L1 sign differs from sign(pred -
         // img); the shading backward is linear in its input, so the difference of the two signs is propagated here
+        // (taken from the FAR end of the thread range: the pair items below start at thread 0, and a thread that had one
+        // of each ran the two gather chains one after the other - the kernel's tail)
         const int nq = min(*qcount, qcap);
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nq; e += gridDim.x * blockDim.x) {
+        const int n_threads = gridDim.x * blockDim.x;
+        for (int e = n_threads - 1 - (int)(blockIdx.x * blockDim.x + threadIdx.x); e < nq; e += n_threads) {
             const uint2 it = qlist[e];
             const float4 dg = make_float4((float)((int)(it.y & 7u) - 2), (float)((int)((it.y >> 3) & 7u) - 2),
                                           (float)((int)((it.y >> 6) & 7u) - 2), 0.f);
@@ -1805,7 +1816,8 @@ __global__ void ham_init_albedo_mean_kernel(const double* __restrict__ global_ro
 __global__ void __launch_bounds__(32) ham_finalize_scalars_kernel(const double* __restrict__ acc,
                                                                   const double* __restrict__ view_vm2,
                                                                   const int32_t* __restrict__ view_idx, int n_views,
-                                                                  int tiles, int phase, float* __restrict__ scal) {
+                                                                  int tiles, int phase, float* __restrict__ scal,
+                                                                  double* __restrict__ reg_totals) {
     FMHR_TRACE_SCOPE(10);
     const int lane = threadIdx.x;
     double vm2 = 0.0;  // sum of valid_mask^2 over the batch's views; acc[2] holds the listed pixels' corrections
@@ -1813,11 +1825,16 @@ __global__ void __launch_bounds__(32) ham_finalize_scalars_kernel(const double* 
         for (int n = lane; n < n_views; n += 32) vm2 += view_vm2[(size_t)view_idx[n] * (tiles + 1) + tiles];
     const double a0 = warp_sum_f64(acc[0 * 32 + lane]), a1 = warp_sum_f64(acc[1 * 32 + lane]);
     const double a2 = warp_sum_f64(acc[2 * 32 + lane] + vm2);
+    // regulariser totals (the regulariser kernel finished long ago: the caller orders this kernel behind it): summed here,
+    // beside the pair kernel, instead of by one thread of the update kernel (128 dependent fp64 adds = that kernel's tail)
+    const double r3 = warp_sum_f64(acc[3 * 32 + lane]), r4 = warp_sum_f64(acc[4 * 32 + lane]);
+    const double r5 = warp_sum_f64(acc[5 * 32 + lane]), r6 = warp_sum_f64(acc[6 * 32 + lane]);
     if (lane == 0) {
         scal[0] = (float)a0;
         scal[1] = (float)a1;
         scal[2] = (float)a2;
         scal[3] = 0.0f;
+        reg_totals[0] = r3; reg_totals[1] = r4; reg_totals[2] = r5; reg_totals[3] = r6;
     }
 }
 
@@ -2274,11 +2291,12 @@ __global__ void __launch_bounds__(256, 6) ham_update_pass2_kernel(
     const float s_mask = 2.0f * cfg.mask_weight / P_global;              // F.mse_loss mean over n*H*W
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const float sfs = cfg.sfs_weight * scal[1] / (3.0f * n_valid);
-        const float lap = cfg.lap_weight * (float)(acc_total(acc, 3) / (double)V);
-        const float alb = cfg.albedo_weight * (float)(acc_total(acc, 4) / (double)V);
+        const double* reg_totals = acc + 7 * 32;  // written by ham_finalize_scalars_kernel
+        const float lap = cfg.lap_weight * (float)(reg_totals[0] / (double)V);
+        const float alb = cfg.albedo_weight * (float)(reg_totals[1] / (double)V);
         const float msk = cfg.phase == 1 ? cfg.mask_weight * scal[2] / P_global : 0.0f;
-        const float edg = cfg.edge_weight * (float)(acc_total(acc, 5) / (3.0 * (double)cfg.T));
-        const float del = cfg.delta_weight * (float)(acc_total(acc, 6) / (double)V);
+        const float edg = cfg.edge_weight * (float)(reg_totals[2] / (3.0 * (double)cfg.T));
+        const float del = cfg.delta_weight * (float)(reg_totals[3] / (double)V);
         losses[0] = sfs; losses[1] = cfg.phase == 1 ? lap : 0.0f; losses[2] = alb; losses[3] = msk;
         losses[4] = cfg.phase == 1 ? edg : 0.0f; losses[5] = cfg.phase == 1 ? del : 0.0f; losses[6] = n_valid;
         losses[7] = cfg.phase == 1 ? sfs + lap + alb + msk + edg + del : sfs;
@@ -2565,6 +2583,8 @@ struct SideStream {
     cudaStream_t pix = nullptr;               // pixel passes of the view groups (high priority)
     cudaEvent_t cov_done[4] = {nullptr, nullptr, nullptr, nullptr}, pix_join = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, records = nullptr;
+    cudaStream_t st2 = nullptr;               // FMHR_SIDE2: regulariser forward / gradients, forked behind the normals
+    cudaEvent_t normals_done = nullptr, join2 = nullptr;
     cudaStream_t copy = nullptr;              // host-batch uploads of fmhr_ham_step_host_u8
     cudaEvent_t copy_fork = nullptr, ready = nullptr;
     // pipelined host batches (fmhr_ham_host_u8_submit): two staging slots in flight
@@ -2608,6 +2628,9 @@ static int side_stream(SideStream** out) {
         FMHR_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.records, cudaEventDisableTiming));
+        FMHR_CUDA(cudaStreamCreateWithPriority(&s.st2, cudaStreamNonBlocking, FMHR_SIDE_PRIO ? prio_hi : prio_lo));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.normals_done, cudaEventDisableTiming));
+        FMHR_CUDA(cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming));
         FMHR_CUDA(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.copy_fork, cudaEventDisableTiming));
         FMHR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
@@ -2688,11 +2711,15 @@ static int launch_coverage(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     const int H = cfg->H, W = cfg->W, cur = cfg->zbuf_slot;
     const int tiles_x = cdiv(W, kTile), tiles_pv = tiles_x * cdiv(H, kTile);
     const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
-    const size_t smem = (size_t)b->ml_max_verts * 24 + (size_t)((tiles_pv + 31) / 32) * sizeof(unsigned int);
+    size_t smem = (size_t)b->ml_max_verts * 24 + (size_t)((tiles_pv + 31) / 32) * sizeof(unsigned int);
     if (smem > 96 * 1024) {
         set_error("fmhr_ham_step_render: %d tiles per view exceed the coverage kernel's shared-memory bitmaps", tiles_pv);
         return FMHR_EUNSUPPORTED;
     }
+    // Tuning hook: a larger dynamic shared-memory request lowers the coverage blocks per SM (5 -> 4 at 24 KB with the
+    // 1024-triangle meshlets), which leaves a quarter of the register file to the side-stream vertex kernels.
+    static const size_t smem_floor = [] { const char* e = getenv("FMHR_COV_SMEM"); return e ? (size_t)atoi(e) : (size_t)FMHR_COV_SMEM_FLOOR; }();
+    if (smem < smem_floor && smem_floor <= 96 * 1024) smem = smem_floor;
     const dim3 grid(b->n_meshlets, gv.nv);
     const uint2* tri2 = (const uint2*)b->ml_tri2;
     // more than four frame pixels per triangle (configs 1, 3, 5): triangles span several pixels, use the draining variant
@@ -2786,21 +2813,28 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     ham_normals_kernel<<<cdiv((long long)V * 4, 256), 256, 0, vs>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
                                                                     ws.vattr, ws.raw4);
     FMHR_LAUNCH_CHECK();
+    cudaStream_t rs = vs;  // stream of the regulariser chain
+    if (side && FMHR_SIDE2 && !forward_only) {
+        FMHR_CUDA(cudaEventRecord(side->normals_done, side->st));
+        FMHR_CUDA(cudaStreamWaitEvent(side->st2, side->normals_done, 0));
+        rs = side->st2;
+    }
     ham_trirec_kernel<<<cdiv(T, 128), 128, 0, vs>>>(b->tri, b->opp, ws.vg, ws.vattr, V, T, ws.trirec);
     FMHR_LAUNCH_CHECK();
     if (side) FMHR_CUDA(cudaEventRecord(side->records, side->st));
     if (!forward_only) {
-        ham_regulariser_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, vs>>>(
+        ham_regulariser_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, rs>>>(
             *cfg, ws.vg, b->delta, ws.vattr, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.acc,
             b->adam_step, ws.adam_sc);
         FMHR_LAUNCH_CHECK();
         if (PHASE == 1) {
-            ham_reg_grad_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, vs>>>(
+            ham_reg_grad_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, rs>>>(
                 *cfg, ws.vg, b->delta, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.greg);
             FMHR_LAUNCH_CHECK();
         }
     }
     if (side) FMHR_CUDA(cudaEventRecord(side->join, side->st));
+    if (rs != vs) FMHR_CUDA(cudaEventRecord(side->join2, side->st2));
     FMHR_STAGE_MARK();  // 1: vertex prep + normals
     FMHR_STAGE_MARK();  // 2: (the clip transform is fused into the coverage kernel)
     if (g_timer) {
@@ -2878,6 +2912,10 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         // vertex side stream (one group) or stays in the group's chain (view groups: the next group's coverage is running
         // beside it anyway); the loss-scalar finalize and, without speculation, the pixel backward stay on this stream.
         cudaStream_t ps = px;
+        // the finalize kernel reads the regulariser's loss accumulators: order this stream behind the vertex side stream
+        // (its last record: after the regulariser gradients, long finished by now)
+        if (side && g == G - 1) FMHR_CUDA(cudaStreamWaitEvent(px, side->join, 0));
+        if (rs != vs && g == G - 1) FMHR_CUDA(cudaStreamWaitEvent(px, side->join2, 0));
         if (side && G == 1) {
             FMHR_CUDA(cudaEventRecord(side->fork, px));
             FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
@@ -2893,7 +2931,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         if (g == G - 1) {
             // loss scalars of the whole batch: beside the last pair kernel when this stream is otherwise idle, else behind it
             ham_finalize_scalars_kernel<<<1, 32, 0, (spec && G == 1) ? px : ps>>>(
-                ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE, b->packed + 12 * (size_t)V);
+                ws.acc, b->view_vm2, b->view_idx, n, tiles_x * tiles_y, PHASE, b->packed + 12 * (size_t)V, ws.acc + 7 * 32);
             FMHR_LAUNCH_CHECK();
         }
         if (side && G == 1) FMHR_CUDA(cudaEventRecord(side->join, side->st));
@@ -2908,6 +2946,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         FMHR_CUDA(cudaStreamWaitEvent(st, side->pix_join, 0));
     }
     if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    if (rs != vs) FMHR_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
     FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
     return FMHR_OK;
 }

@@ -981,13 +981,24 @@ __global__ void __launch_bounds__(256, FMHR_LB_SCAN) ham_scan_kernel(const unsig
         __syncwarp();
         if (nbuf > kBuf - 128) flush();
     }
-    __shared__ int s_cnt[10];
+    // last flush of both lists: ONE reservation phase (the two block-level atomics are issued by two threads side by side,
+    // not as two dependent round trips at the end of the kernel's critical chain)
+    __shared__ int s_cnt[20];
+    if (lane == 0) { s_cnt[wib] = nbuf; s_cnt[10 + wib] = nring; }
+    __syncthreads();
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        int* c = s_cnt + (threadIdx.x == 0 ? 0 : 10);
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { const int v = c[w]; c[w] = tot; tot += v; }
+        c[8] = tot > 0 ? atomicAdd(threadIdx.x == 0 ? ccount : rcount, tot) : 0;
+    }
+    __syncthreads();
     {
-        const int base = block_reserve(ccount, nbuf, s_cnt);
+        const int base = s_cnt[8] + s_cnt[wib];
         for (int i = lane; i < nbuf; i += 32) clist[base + i] = cbuf[wib][i];
     }
     {
-        const int base = block_reserve(rcount, nring, s_cnt);
+        const int base = s_cnt[18] + s_cnt[10 + wib];
         for (int i = lane; i < nring; i += 32) {
             if (base + i < rcap) rlist[base + i] = rbuf[wib][i];
             else atomicOr(status, 2);

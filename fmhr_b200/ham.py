@@ -16,6 +16,9 @@ from .dist import PeerExchange, allreduce_packed
 from .dr import Topology
 
 
+_IDX_COPY_ALWAYS = os.environ.get("FMHR_IDX_COPY_ALWAYS", "0") == "1"  # A/B measurements of the index-copy elision
+
+
 class HamOptimizer:
     def __init__(self, vertices, faces, imgs, masks, valid_masks, w2cs, projs, sh_coeffs, albedo, conf,
                  process_group=None, n_views_global=None, debug=False, use_graphs=False, exchange=None,
@@ -90,6 +93,7 @@ class HamOptimizer:
         self._view_idx_cache = {}
         self.use_graphs = bool(use_graphs) and not debug
         self._graphs = {}
+        self._idx_tags = {}
         self._struct_cache = {}
         self._zb_layout = None
         self._zb_slot = 0
@@ -146,7 +150,7 @@ class HamOptimizer:
             check(self.lib.fmhr_ham_prepare_views(ptr(self.valid_masks), self.num, self.H, self.W, ptr(self.view_vm2),
                                                   stream()), "ham_prepare_views")
         self._struct_cache.clear()
-        self._graphs = {}
+        self._graphs = {}; self._idx_tags = {}
         return dict(sh_coeff=sh_g, albedo_mean=alb)
 
     # ------------------------------------------------------------------ reference-shaped accessors
@@ -191,7 +195,7 @@ class HamOptimizer:
             raise RuntimeError("fmhr_b200: invalid HAM configuration")
         if self.workspace is None or self.workspace.numel() < need:
             self.workspace = None
-            self._graphs = {}
+            self._graphs = {}; self._idx_tags = {}
             self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         b = HamBuffers()
         t = self.topo
@@ -317,7 +321,13 @@ class HamOptimizer:
         self._zb_slot ^= 1
         vi = self._views(view_idx)
         if vi.data_ptr() != idx_buf.data_ptr():
-            idx_buf.copy_(vi, non_blocking=True)
+            # the captured kernels read the batch's view indices from `idx_buf`; a loop that passes the SAME index tensor
+            # again (same object, not written since: the reference's batch == all views case) needs no second copy - the
+            # tiny copy kernel between two graph launches costs ~3 us of every iteration
+            tag = self._idx_tags.get(key)
+            if tag is None or tag[0] is not vi or tag[1] != vi._version or _IDX_COPY_ALWAYS:
+                idx_buf.copy_(vi, non_blocking=True)
+                self._idx_tags[key] = (vi, vi._version)  # (holds the tensor: its address cannot be recycled)
         graphs[slot][0].replay()
         if len(graphs[slot]) > 1:
             allreduce_packed(self.packed, self.pg)

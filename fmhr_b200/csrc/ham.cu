@@ -58,6 +58,9 @@ static __device__ unsigned int g_dcheck;
 #ifndef FMHR_COV_SMEM_FLOOR
 #define FMHR_COV_SMEM_FLOOR 0
 #endif
+#ifndef FMHR_REG_GRAD_LATE
+#define FMHR_REG_GRAD_LATE 0
+#endif
 #ifndef FMHR_SIDE2
 #define FMHR_SIDE2 0  // regulariser forward / gradients on a second side stream behind the normals (beside the triangle records)
 #endif
@@ -2824,6 +2827,10 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
     ham_normals_kernel<<<cdiv((long long)V * 4, 256), 256, 0, vs>>>(ws.vg, b->albedo, b->v2f_ptr, (const int2*)b->v2f_nbr, V,
                                                                     ws.vattr, ws.raw4);
     FMHR_LAUNCH_CHECK();
+    // FMHR_REG_GRAD_LATE: the regulariser GRADIENTS (only the update needs them) are held back until the antialias pass has
+    // finished and run beside the pair kernel: launched right behind the regulariser they trickle into the SMs through the
+    // whole shade pass and slow down exactly the blocks that finish last
+    const bool late_rg = FMHR_REG_GRAD_LATE && side && G == 1 && PHASE == 1 && !forward_only && !init;
     cudaStream_t rs = vs;  // stream of the regulariser chain
     if (side && FMHR_SIDE2 && !forward_only) {
         FMHR_CUDA(cudaEventRecord(side->normals_done, side->st));
@@ -2838,7 +2845,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
             *cfg, ws.vg, b->delta, ws.vattr, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.acc,
             b->adam_step, ws.adam_sc);
         FMHR_LAUNCH_CHECK();
-        if (PHASE == 1) {
+        if (PHASE == 1 && !late_rg) {
             ham_reg_grad_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, rs>>>(
                 *cfg, ws.vg, b->delta, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.greg);
             FMHR_LAUNCH_CHECK();
@@ -2932,6 +2939,13 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
             FMHR_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
             ps = side->st;
         }
+        if (late_rg) {
+            FMHR_CUDA(cudaStreamWaitEvent(side->st2, side->fork, 0));  // (px is already ordered behind the regulariser)
+            ham_reg_grad_kernel<<<cdiv((long long)V * kLPV, 256), 256, 0, side->st2>>>(
+                *cfg, ws.vg, b->delta, b->v2f_ptr, (const int2*)b->v2f_nbr, b->v2v_ptr, b->v2v_idx, ws.ys, ws.greg);
+            FMHR_LAUNCH_CHECK();
+            FMHR_CUDA(cudaEventRecord(side->join2, side->st2));
+        }
         if (!forward_only) {
             ham_pair_bwd_kernel<PHASE><<<888, 128, 0, ps>>>(v.plist_a, v.plist_b, v.pcount, v.pcap, v.zcur, ws.vg, v.viewM, V,
                                                            H, W, v.plane[0], g0, g1, ws.trirec, invW, invH, b->sh_coeffs,
@@ -2957,7 +2971,7 @@ static int ham_render_impl(const fmhr_ham_config* cfg, const fmhr_ham_buffers* b
         FMHR_CUDA(cudaStreamWaitEvent(st, side->pix_join, 0));
     }
     if (side) FMHR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-    if (rs != vs) FMHR_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
+    if (rs != vs || late_rg) FMHR_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
     FMHR_STAGE_MARK();  // 6: pixel backward (+ scalar finalize)
     return FMHR_OK;
 }

@@ -298,6 +298,32 @@ def test_graph_replay_matches_eager(scene):
     assert int(b.adam_step[0]) == 4 and len(b._graphs) == 2 and int(a.adam_step[0]) == 4
 
 
+def test_graph_replay_index_copy_elision(scene):
+    """Graph replay skips the copy of the batch's view indices when the caller passes the SAME index tensor again
+    (HamOptimizer._step_graph); it must not skip it when that tensor was written in between (version counter), when a
+    different tensor of the same content / size arrives, or for Python lists."""
+    from fmhr_b200.ham import HamOptimizer
+    c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt).cuda()
+    mk = lambda **kw: HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
+                                   c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], **kw)
+    ref, gph = mk(), mk(use_graphs=True)
+    t = torch.tensor([0, 1, 2], dtype=torch.int32, device="cuda")
+    seq = []
+    seq.append(([0, 1, 2], lambda: t))                                   # first use: copied
+    seq.append(([0, 1, 2], lambda: t))                                   # same tensor, untouched: elided
+    seq.append(([3, 1, 0], lambda: t.copy_(torch.tensor([3, 1, 0], dtype=torch.int32, device="cuda"))))  # written in place
+    seq.append(([3, 1, 0], lambda: t))                                   # elided again
+    seq.append(([2, 0, 1], lambda: torch.tensor([2, 0, 1], dtype=torch.int32, device="cuda")))  # another tensor
+    seq.append(([1, 2, 3], lambda: [1, 2, 3]))                           # a list
+    seq.append(([3, 1, 0], lambda: t))                                   # back to the first tensor: its tag is stale
+    for views, arg in seq:
+        la = ref.step_phase_b(views).cpu()
+        lb = gph.step_phase_b(arg()).cpu()
+        assert la[6] == lb[6], (views, la, lb)  # n_valid is exact: a stale index buffer renders other views
+        assert torch.allclose(la, lb, rtol=1e-4, atol=1e-6), (views, la, lb)
+        gph.delta.copy_(ref.delta); gph.albedo.copy_(ref.albedo); gph.adam_m.copy_(ref.adam_m); gph.adam_v.copy_(ref.adam_v)
+
+
 @pytest.mark.parametrize("groups", [2, 3])
 def test_view_groups_match_single_chain(scene, groups):
     """fmhr_ham_config.view_groups: the batch's views split into consecutive groups whose pixel passes overlap the next

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Session-3 tuning cycle: bench line of every variant library given, live schedule of the trace variant, fused parity tests on one variant.
-#   tools/s3_variants.sh TAG TESTVARIANT name1 name2 ...
+#   tools/variant_cycle.sh TAG TESTVARIANT name1 name2 ...
 TAG=$1; shift
 TV=$1; shift
 mkdir -p gpurun_out

@@ -210,6 +210,8 @@ def main():
                          "reference view 0 against the other views (fmhr_b200.ncc_term; single GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--minibatch", type=int, default=32, help="views per step of the reference-faithful epoch leg (conf `batch`)")
+    ap.add_argument("--no-minibatch", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of CUDA-graph replay")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "frames"],
                     help="N > 1: weak = every rank renders the workload's whole view set (global batch N x views); strong = "
@@ -227,7 +229,7 @@ def main():
     os.dup2(2, 1)
     args.warmup = max(args.warmup, 3)
     if args.ncc:  # the host-batch step and the oracle leg run the iteration without extra terms
-        args.no_e2e = args.no_cpu_baseline = True
+        args.no_e2e = args.no_cpu_baseline = args.no_minibatch = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -335,6 +337,35 @@ def main():
     losses = opt.losses.cpu().tolist()
     if not all(np.isfinite(losses)) or losses[6] <= 0:
         raise SystemExit("bench.py: the optimisation state is not finite (losses %s) - refusing to report a number" % losses)
+
+    # ---------------------------------------------------------------- reference-faithful mini-batches (secondary)
+    # mesh_sfs_optim.py:248-260: every epoch draws a permutation of the views and steps through it in batches of
+    # conf `batch` views (conf/ih_sfs.conf:32: 32 -> 32 + 16 for 48 views), a NEW index tensor per step.
+    epochs = None
+    if world == 1 and not args.no_minibatch and n > args.minibatch:
+        bsz = args.minibatch
+
+        def run_epoch():
+            perm = torch.randperm(n, device=dev).to(torch.int32)
+            for k in range(0, n, bsz):
+                opt.step_phase_b(perm[k:k + bsz])
+
+        for _ in range(3):
+            run_epoch()
+        n_ep = max(10, args.steps // 4)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        m0.record()
+        for _ in range(n_ep):
+            run_epoch()
+        m1.record()
+        barrier()
+        ms_ep = m0.elapsed_time(m1) / n_ep
+        epochs = {"value": 1000.0 / ms_ep, "unit": "epochs/s", "batch": bsz, "views": n,
+                  "steps_per_epoch": (n + bsz - 1) // bsz, "ms_per_epoch": ms_ep, "epochs_timed": n_ep,
+                  "note": "torch.randperm per epoch, one optimiser step per batch of views (mesh_sfs_optim.py:248-310)"}
+        if not all(np.isfinite(opt.losses.cpu().tolist())):
+            raise SystemExit("bench.py: the mini-batch leg left a non-finite optimisation state")
 
     # ---------------------------------------------------------------- end to end (host buffers)
     e2e = None
@@ -535,6 +566,7 @@ def main():
         "gpu_launches": kernels_per_step * args.steps,
         "clocks": clocks,
         "e2e": e2e,
+        "epochs_minibatch": epochs,
         "roofline": roof,
         "cpu_baseline": cpu,
         "parity": parity,

@@ -344,6 +344,9 @@ def main():
     epochs = None
     if world == 1 and not args.no_minibatch and n > args.minibatch:
         bsz = args.minibatch
+        # one workspace layout for every batch size of the epoch (fmhr_ham_config.n_views_capacity): the short last batch
+        # does not force a z-buffer reset before and after it
+        opt.set_batch_capacity(n)
 
         def run_epoch():
             perm = torch.randperm(n, device=dev).to(torch.int32)
@@ -363,7 +366,8 @@ def main():
         ms_ep = m0.elapsed_time(m1) / n_ep
         epochs = {"value": 1000.0 / ms_ep, "unit": "epochs/s", "batch": bsz, "views": n,
                   "steps_per_epoch": (n + bsz - 1) // bsz, "ms_per_epoch": ms_ep, "epochs_timed": n_ep,
-                  "note": "torch.randperm per epoch, one optimiser step per batch of views (mesh_sfs_optim.py:248-310)"}
+                  "note": "torch.randperm per epoch, one optimiser step per batch of views (mesh_sfs_optim.py:248-310); "
+                          "workspace laid out for the largest batch (set_batch_capacity): no z-buffer reset between batch sizes"}
         if not all(np.isfinite(opt.losses.cpu().tolist())):
             raise SystemExit("bench.py: the mini-batch leg left a non-finite optimisation state")
 

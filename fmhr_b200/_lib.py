@@ -26,7 +26,8 @@ class HamConfig(ctypes.Structure):
                 ("sfs_weight", c_f), ("lap_weight", c_f), ("albedo_weight", c_f), ("mask_weight", c_f),
                 ("edge_weight", c_f), ("delta_weight", c_f),
                 ("lr", c_f), ("albedo_lr", c_f), ("sh_lr", c_f),
-                ("beta1", c_f), ("beta2", c_f), ("eps", c_f), ("edge_length_mean", c_f)]
+                ("beta1", c_f), ("beta2", c_f), ("eps", c_f), ("edge_length_mean", c_f),
+                ("n_views_capacity", ctypes.c_int32)]
 
 
 class HamBuffers(ctypes.Structure):

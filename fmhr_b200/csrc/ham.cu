@@ -135,7 +135,11 @@ static thread_local StageTimer* g_timer = nullptr;
 #define FMHR_STAGE_MARK() do { if (g_timer) g_timer->mark(); } while (0)
 
 static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
-    const size_t P = (size_t)c->n_views * c->H * c->W, V = (size_t)c->V;
+    // every per-view / per-pixel array is laid out for the configuration's view CAPACITY (>= the step's batch): steps with
+    // different batch sizes then share one layout (view slot k sits at the same addresses) and keep each other's
+    // z-buffer / tile-list invariants, so the caller does not have to reset between them
+    const size_t ncap = (size_t)(c->n_views_capacity > c->n_views ? c->n_views_capacity : c->n_views);
+    const size_t P = ncap * c->H * c->W, V = (size_t)c->V;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
     char* p;
@@ -145,7 +149,7 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
         p = (i < nplanes) ? take(P * 16) : nullptr;
         if (ws) ws->plane[i] = (float4*)p;
     }
-    p = take((size_t)c->n_views * kViewM * 4); if (ws) ws->viewM = (float*)p;
+    p = take(ncap * kViewM * 4); if (ws) ws->viewM = (float*)p;
     p = take(P * 8); if (ws) ws->clist = (uint2*)p;
     p = take((P / 2 + 64) * 4); if (ws) ws->rlist = (uint32_t*)p;
     p = take((P / 32 + 64) * 4); if (ws) ws->ringbits = (uint32_t*)p;
@@ -153,12 +157,12 @@ static size_t ham_layout(const fmhr_ham_config* c, char* base, HamWs* ws) {
     p = take((P / 2 + 64) * 4); if (ws) ws->plist_b = (uint32_t*)p;
     p = take((P / 4 + 64) * 8); if (ws) ws->qlist = (uint2*)p;
     const size_t tiles_pv = (size_t)((c->W + 15) / 16) * ((c->H + 15) / 16);
-    const size_t words = (size_t)c->n_views * ((tiles_pv + 31) / 32);
+    const size_t words = ncap * ((tiles_pv + 31) / 32);
     const size_t slot_bytes = 256 + align256(words * 4);
     for (int i = 0; i < 2; i++) {
         p = take(slot_bytes);
         if (ws) { ws->slot_region[i] = p; ws->tcount[i] = (int*)p; ws->tbits[i] = (uint32_t*)(p + 256); }
-        p = take((size_t)c->n_views * tiles_pv * 4); if (ws) ws->tlist[i] = (uint32_t*)p;
+        p = take(ncap * tiles_pv * 4); if (ws) ws->tlist[i] = (uint32_t*)p;
     }
     const size_t common_bytes = 8 * 32 * sizeof(double) + 256;
     p = take(common_bytes);
@@ -2393,6 +2397,7 @@ static int check_cfg(const fmhr_ham_config* c) {
     FMHR_CHECK_ARG(c->view_groups >= 0 && c->view_groups <= 4);
     FMHR_CHECK_ARG(c->T < (1 << 28));  // triangle id shares the key's low word with 4 tag bits
     FMHR_CHECK_ARG(c->n_views < 4096 && c->W <= 16384 && c->H <= 16384);  // work-list entry = view:12 | ty:10 | tx:10
+    FMHR_CHECK_ARG(c->n_views_capacity == 0 || (c->n_views_capacity >= c->n_views && c->n_views_capacity < 4096));
     FMHR_CHECK_ARG((long long)c->H * c->W < (1ll << 31));
     return FMHR_OK;
 }
@@ -3039,7 +3044,7 @@ extern "C" int fmhr_ham_reset(const fmhr_ham_config* cfg, const fmhr_ham_buffers
     FMHR_CHECK_ARG(buf && buf->workspace && buf->workspace_bytes >= fmhr_ham_workspace_bytes(cfg));
     HamWs ws;
     ham_layout(cfg, (char*)buf->workspace, &ws);
-    const size_t P = (size_t)cfg->n_views * cfg->H * cfg->W;
+    const size_t P = (size_t)(cfg->n_views_capacity > cfg->n_views ? cfg->n_views_capacity : cfg->n_views) * cfg->H * cfg->W;
     for (int i = 0; i < 2; i++) {
         FMHR_CUDA(cudaMemsetAsync(ws.zbuf[i], 0xFF, P * 8, (cudaStream_t)stream));
         FMHR_CUDA(cudaMemsetAsync(ws.slot_region[i], 0, ws.slot_bytes, (cudaStream_t)stream));

@@ -97,6 +97,7 @@ class HamOptimizer:
         self._struct_cache = {}
         self._zb_layout = None
         self._zb_slot = 0
+        self.batch_capacity = 0  # see set_batch_capacity
 
     MESHLET_TRIS = int(os.environ.get("FMHR_MESHLET_TRIS", "1024"))  # 256 / 512 / 1024 (tuning override)
 
@@ -186,6 +187,9 @@ class HamOptimizer:
         cfg.lr, cfg.albedo_lr, cfg.sh_lr = c["lr"], c["albedo_lr"], c["sh_lr"]
         cfg.beta1, cfg.beta2, cfg.eps = 0.9, 0.999, 1e-8
         cfg.edge_length_mean = self.edge_length_mean
+        if self.batch_capacity and n_views > self.batch_capacity:
+            self.set_batch_capacity(n_views)  # a larger batch than announced: the layout grows (and everything is re-armed)
+        cfg.n_views_capacity = self.batch_capacity
         return cfg
 
     def _buffers(self, cfg, view_idx, imgs=None, masks=None, valid_masks=None, w2cs=None, projs=None, sh_idx=None,
@@ -223,6 +227,24 @@ class HamOptimizer:
         b.dbg_grad_sh = ptr(self.dbg_grad_sh if (self.debug and cfg.phase == 0) else None)
         return b
 
+    def set_batch_capacity(self, n_views):
+        """Lay the workspace out for batches of UP TO n_views views (fmhr_ham_config.n_views_capacity).  Steps with different
+        batch sizes - the reference's loop ends every epoch with a short batch, mesh_sfs_optim.py:252-254 - then share one
+        layout and keep each other's z-buffer invariants: no fmhr_ham_reset (two z-buffer memsets) whenever the batch size
+        changes.  0 = lay out for each step's own size (a change of size resets).  Invalidates the workspace and the
+        captured graphs."""
+        n_views = int(n_views)
+        if n_views != self.batch_capacity:
+            self.batch_capacity = n_views
+            self.workspace = None
+            self._graphs = {}; self._idx_tags = {}
+            self._struct_cache.clear()
+            self._zb_layout = None
+
+    def _layout_views(self, n):
+        """Number of views the workspace of a step with n views is laid out for."""
+        return max(self.batch_capacity, n) if self.batch_capacity else n
+
     def _prepare_zbuf_local(self, cfg, buf):
         """_prepare_zbuf for rank-local helpers (initialise / stage_times / export): with the peer exchange the slot
         parity selects the shared `packed` buffer and must only advance on steps EVERY rank makes, so these helpers
@@ -237,7 +259,7 @@ class HamOptimizer:
     def _prepare_zbuf(self, cfg, buf):
         """The fused step rasterises z-buffer slot `cfg.zbuf_slot` and resets the other one for the next step, so the
         slot alternates every render; both slots are reset whenever the workspace layout changes."""
-        layout = (cfg.n_views, cfg.phase == 0, self.workspace.data_ptr())
+        layout = (self._layout_views(cfg.n_views), cfg.phase == 0, self.workspace.data_ptr())
         if layout != self._zb_layout:
             check(self.lib.fmhr_ham_reset(ctypes.byref(cfg), ctypes.byref(buf), stream()), "ham_reset")
             self._zb_layout = layout  # both slots are clean now: the parity simply carries on (see _run_step)
@@ -313,7 +335,7 @@ class HamOptimizer:
         graphs, idx_buf, ws_ptr, cfgs, bufs = ent
         if self.workspace.data_ptr() != ws_ptr:
             raise RuntimeError("fmhr_b200: workspace was reallocated after graph capture")
-        layout = (n, phase == 0, ws_ptr)
+        layout = (self._layout_views(n), phase == 0, ws_ptr)
         if layout != self._zb_layout:
             check(self.lib.fmhr_ham_reset(ctypes.byref(cfgs[0]), ctypes.byref(bufs[0]), stream()), "ham_reset")
             self._zb_layout = layout
@@ -370,7 +392,7 @@ class HamOptimizer:
         torch.cuda.current_stream(self.device).wait_stream(side)
         for t, sv in zip(state, saved):
             t.copy_(sv)
-        self._zb_layout = (n, phase == 0, ws_ptr)  # two warm-up steps: the parity is where it was
+        self._zb_layout = (self._layout_views(n), phase == 0, ws_ptr)  # two warm-up steps: the parity is where it was
         return graphs, idx_buf, ws_ptr, cfgs, bufs
 
     # ------------------------------------------------------------------ the two loops' bodies

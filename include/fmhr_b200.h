@@ -163,6 +163,9 @@ typedef struct fmhr_ham_config {
     float lr, albedo_lr, sh_lr;
     float beta1, beta2, eps;
     float edge_length_mean;   /* mesh_sfs_optim.py:188 */
+    int32_t n_views_capacity; /* 0, or >= n_views: the workspace is laid out for this many views, so that steps with
+                                 DIFFERENT batch sizes (the reference's last short batch of an epoch, mesh_sfs_optim.py:252-254)
+                                 share one layout and need no fmhr_ham_reset in between; 0 = laid out for n_views */
 } fmhr_ham_config;
 
 typedef struct fmhr_ham_buffers {

@@ -324,6 +324,44 @@ def test_graph_replay_index_copy_elision(scene):
         gph.delta.copy_(ref.delta); gph.albedo.copy_(ref.albedo); gph.adam_m.copy_(ref.adam_m); gph.adam_v.copy_(ref.adam_v)
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_batch_capacity_alternating_batch_sizes(scene, graphs):
+    """fmhr_ham_config.n_views_capacity / HamOptimizer.set_batch_capacity: steps with different batch sizes (the reference's
+    epochs end with a short batch, mesh_sfs_optim.py:252-254) share one workspace layout, so the optimiser does not reset
+    the z-buffers in between - and still follows, step by step, an optimiser that lays the workspace out per batch size
+    and resets on every change."""
+    from fmhr_b200.ham import HamOptimizer
+    c = lambda k, dt=torch.float32: torch.tensor(scene[k], dtype=dt).cuda()
+    mk = lambda **kw: HamOptimizer(c("vertices"), c("faces", torch.int32), c("imgs"), c("masks"), c("valid_masks"), c("w2cs"),
+                                   c("projs"), c("sh_coeffs"), c("albedo"), scene["conf"], **kw)
+    n = scene["imgs"].shape[0]
+    ref, cap = mk(), mk(use_graphs=graphs)
+    cap.set_batch_capacity(n)
+    resets = [0]
+    real_reset = cap.lib.fmhr_ham_reset
+
+    class Counting:  # counts the resets the capacity optimiser issues outside graph capture
+        def __getattr__(self, name):
+            if name == "fmhr_ham_reset":
+                def f(*a):
+                    resets[0] += 1
+                    return real_reset(*a)
+                return f
+            return getattr(_lib_real, name)
+    _lib_real = cap.lib
+    batches = [list(range(n)), [0, 1], [2, 1, 0], list(range(n))[::-1], [n - 1], [1, 3, 0], list(range(n)), [3, 2]]
+    for it, views in enumerate(batches):
+        if it == 3:
+            cap.lib = Counting()  # layout, graphs of the first sizes exist by now
+        la, lb = ref.step_phase_b(views).cpu(), cap.step_phase_b(views).cpu()
+        assert la[6] == lb[6], (it, views, la, lb)  # n_valid exact: stale z-buffer state would show here first
+        assert torch.allclose(la, lb, rtol=1e-4, atol=1e-6), (it, views, la, lb)
+        cap.delta.copy_(ref.delta); cap.albedo.copy_(ref.albedo); cap.adam_m.copy_(ref.adam_m); cap.adam_v.copy_(ref.adam_v)
+    cap.lib = _lib_real
+    if not graphs:
+        assert resets[0] == 0, "a batch-size change must not reset the shared layout"
+
+
 @pytest.mark.parametrize("groups", [2, 3])
 def test_view_groups_match_single_chain(scene, groups):
     """fmhr_ham_config.view_groups: the batch's views split into consecutive groups whose pixel passes overlap the next

@@ -158,6 +158,39 @@ def cpu_reference_step_rate(scene, steps, warmup, threads):
 _JSON_FD = None
 
 
+def minibatch_epochs(opt, n, bsz, n_ep, dev, barrier):
+    """SURVEY.md 8(d), secondary metric: the reference's own loop shape (mesh_sfs_optim.py:248-260) - every epoch draws a
+    permutation of the views and steps through it in batches of conf `batch` views (conf/ih_sfs.conf:32: 32 -> 32 + 16 for
+    48 views), a NEW index tensor per step.  Epochs per second, CUDA events around n_ep epochs."""
+    import numpy as np
+    import torch
+    # one workspace layout for every batch size of the epoch (fmhr_ham_config.n_views_capacity): the short last batch does
+    # not force a z-buffer reset before and after it
+    opt.set_batch_capacity(n)
+
+    def run_epoch():
+        perm = torch.randperm(n, device=dev).to(torch.int32)
+        for k in range(0, n, bsz):
+            opt.step_phase_b(perm[k:k + bsz])
+
+    for _ in range(3):
+        run_epoch()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    m0.record()
+    for _ in range(n_ep):
+        run_epoch()
+    m1.record()
+    barrier()
+    ms_ep = m0.elapsed_time(m1) / n_ep
+    if not all(np.isfinite(opt.losses.cpu().tolist())):
+        return {"error": "non-finite optimisation state after the mini-batch leg"}
+    return {"value": 1000.0 / ms_ep, "unit": "epochs/s", "batch": bsz, "views": n,
+            "steps_per_epoch": (n + bsz - 1) // bsz, "ms_per_epoch": ms_ep, "epochs_timed": n_ep,
+            "note": "torch.randperm per epoch, one optimiser step per batch of views (mesh_sfs_optim.py:248-310); "
+                    "workspace laid out for the largest batch (set_batch_capacity): no z-buffer reset between batch sizes"}
+
+
 def emit(obj):
     """The one JSON line of the run, on the process's ORIGINAL stdout."""
     line = (json.dumps(obj) + "\n").encode()
@@ -338,39 +371,6 @@ def main():
     if not all(np.isfinite(losses)) or losses[6] <= 0:
         raise SystemExit("bench.py: the optimisation state is not finite (losses %s) - refusing to report a number" % losses)
 
-    # ---------------------------------------------------------------- reference-faithful mini-batches (SURVEY.md 8d, secondary)
-    # mesh_sfs_optim.py:248-260: every epoch draws a permutation of the views and steps through it in batches of
-    # conf `batch` views (conf/ih_sfs.conf:32: 32 -> 32 + 16 for 48 views), a NEW index tensor per step.
-    epochs = None
-    if world == 1 and not args.no_minibatch and n > args.minibatch:
-        bsz = args.minibatch
-        # one workspace layout for every batch size of the epoch (fmhr_ham_config.n_views_capacity): the short last batch
-        # does not force a z-buffer reset before and after it
-        opt.set_batch_capacity(n)
-
-        def run_epoch():
-            perm = torch.randperm(n, device=dev).to(torch.int32)
-            for k in range(0, n, bsz):
-                opt.step_phase_b(perm[k:k + bsz])
-
-        for _ in range(3):
-            run_epoch()
-        n_ep = max(10, args.steps // 4)
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        m0.record()
-        for _ in range(n_ep):
-            run_epoch()
-        m1.record()
-        barrier()
-        ms_ep = m0.elapsed_time(m1) / n_ep
-        epochs = {"value": 1000.0 / ms_ep, "unit": "epochs/s", "batch": bsz, "views": n,
-                  "steps_per_epoch": (n + bsz - 1) // bsz, "ms_per_epoch": ms_ep, "epochs_timed": n_ep,
-                  "note": "torch.randperm per epoch, one optimiser step per batch of views (mesh_sfs_optim.py:248-310); "
-                          "workspace laid out for the largest batch (set_batch_capacity): no z-buffer reset between batch sizes"}
-        if not all(np.isfinite(opt.losses.cpu().tolist())):
-            raise SystemExit("bench.py: the mini-batch leg left a non-finite optimisation state")
-
     # ---------------------------------------------------------------- end to end (host buffers)
     e2e = None
     if not args.no_e2e:
@@ -549,6 +549,15 @@ def main():
         rate = 1.0 / (time.time() - t_cpu)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "full workload (%d views), 1 timed iteration after 1 warm-up (the warm-up is the parity iteration)" % n}
+
+    # ---------------------------------------------------------------- reference-faithful mini-batches (SURVEY.md 8d, secondary)
+    # last leg of the run, and guarded: nothing it does can touch the numbers above
+    epochs = None
+    if world == 1 and not args.no_minibatch and n > args.minibatch:
+        try:
+            epochs = minibatch_epochs(opt, n, args.minibatch, max(10, args.steps // 4), dev, barrier)
+        except Exception as ex:  # noqa: BLE001 - a secondary metric must not take the headline line down
+            epochs = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -75,6 +75,19 @@ def test_host_only_queries(lib):
     assert lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg)) > b1  # phase A antialiases six channels: two more planes
     cfg.n_views = 0
     assert lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg)) == 0
+    # n_views_capacity: the workspace is laid out for the capacity, whatever the step's batch size (steps of different sizes
+    # share one layout); a capacity below the batch is refused
+    cfg.phase, cfg.n_views, cfg.n_views_global = 1, 3, 3
+    cfg.n_views_capacity = 3
+    assert lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg)) == b1
+    cfg.n_views_capacity = 7
+    b7 = lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg))
+    assert b7 > b1
+    for nv in (1, 2, 5, 7):
+        cfg.n_views = cfg.n_views_global = nv
+        assert lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg)) == b7
+    cfg.n_views = cfg.n_views_global = 8
+    assert lib.fmhr_ham_workspace_bytes(ctypes.byref(cfg)) == 0
 
 
 def test_bad_arguments_return_codes_not_crashes(lib):
